@@ -1,0 +1,197 @@
+/* phy_engine_b200.h — C ABI of libphyengine_b200.so, the B200-native drop-in for Phy-Engine's analog MNA solve path.
+ *
+ * Part 1 re-declares, with identical names / signatures / return conventions, the analog-path entry points of the
+ * reference's C ABI (reference: include/phy_engine/dll_api.h, implemented in src/dll_main.cpp).  A caller bound to
+ * the reference library (python/phy_engine/_ffi.py:41-140, phy_lab_wrapper/pe_sim.h:415-428) can load this library
+ * instead and every analyze() runs on the GPU.  Part 2 is additive: batch (Monte-Carlo / sweep) handles that the
+ * reference does not have (SURVEY.md §8b last row).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Error convention (dll_main.cpp:2141-2259, 2467-2490): int 0 = ok, 1 = null/invalid argument or analyze failed,
+ * 2 = model not found, 3 = attribute not found; creators return NULL and set the thread-local error string.
+ * There is no CPU fallback: without a CUDA device every analyze entry point returns 1 with an explanatory error.
+ */
+#ifndef PHY_ENGINE_B200_H
+#define PHY_ENGINE_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    /* ===== Part 1: reference-compatible surface ================================================================== */
+
+    /* dll_api.h:43-47 */
+    char const* phy_engine_last_error(void);
+    void phy_engine_clear_error(void);
+    void phy_engine_string_free(char* s);
+
+    /* dll_api.h:143-150 / dll_main.cpp:2492-2640.  Element codes: dll_api.h:51-135.  In scope: 1-13 and 17
+     * (R, C, L, VDC, VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, SPST switch, PN junction, op-amp), 50-53 (BJT NPN/PNP,
+     * level-1 NMOS/PMOS).  Any other code makes the creator fail with "element code N is outside the B200 hot path".
+     * vec_pos / chunk_pos are malloc()ed and released by destroy_circuit(), like the reference. */
+    void* create_circuit(int* elements,
+                         size_t ele_size,
+                         int* wires,
+                         size_t wires_size,
+                         double* properties,
+                         size_t** vec_pos,
+                         size_t** chunk_pos,
+                         size_t* comp_size);
+
+    /* dll_api.h:156-168 (Verilog text tables are accepted and ignored; Verilog element codes are out of scope) */
+    void* create_circuit_ex(int* elements,
+                            size_t ele_size,
+                            int* wires,
+                            size_t wires_size,
+                            double* properties,
+                            char const* const* texts,
+                            size_t const* text_sizes,
+                            size_t text_count,
+                            size_t const* element_src_index,
+                            size_t const* element_top_index,
+                            size_t** vec_pos,
+                            size_t** chunk_pos,
+                            size_t* comp_size);
+
+    /* dll_api.h:170 */
+    void destroy_circuit(void* circuit_ptr, size_t* vec_pos, size_t* chunk_pos);
+
+    /* dll_api.h:173-180 / dll_main.cpp:2141-2267 */
+    int circuit_set_analyze_type(void* circuit_ptr, uint32_t analyze_type_value);
+    int circuit_set_tr(void* circuit_ptr, double t_step, double t_stop);
+    int circuit_set_ac_omega(void* circuit_ptr, double omega);
+    int circuit_set_temperature(void* circuit_ptr, double temp_c);
+    int circuit_set_tnom(void* circuit_ptr, double tnom_c);
+    int circuit_set_model_double_by_name(void* circuit_ptr, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double value);
+    int circuit_analyze(void* circuit_ptr);
+    int circuit_digital_clk(void* circuit_ptr);
+
+    /* dll_api.h:186-236 / dll_main.cpp:2269-2465 */
+    int circuit_sample_layout(void* circuit_ptr,
+                              size_t* vec_pos,
+                              size_t* chunk_pos,
+                              size_t comp_size,
+                              size_t* voltage_ord,
+                              size_t* current_ord,
+                              size_t* digital_ord);
+    int circuit_sample(void* circuit_ptr,
+                       size_t* vec_pos,
+                       size_t* chunk_pos,
+                       size_t comp_size,
+                       double* voltage,
+                       size_t* voltage_ord,
+                       double* current,
+                       size_t* current_ord,
+                       bool* digital,
+                       size_t* digital_ord);
+    int circuit_sample_u8(void* circuit_ptr,
+                          size_t* vec_pos,
+                          size_t* chunk_pos,
+                          size_t comp_size,
+                          double* voltage,
+                          size_t* voltage_ord,
+                          double* current,
+                          size_t* current_ord,
+                          uint8_t* digital,
+                          size_t* digital_ord);
+    int circuit_sample_digital_state_u8(void* circuit_ptr,
+                                        size_t* vec_pos,
+                                        size_t* chunk_pos,
+                                        size_t comp_size,
+                                        double* voltage,
+                                        size_t* voltage_ord,
+                                        double* current,
+                                        size_t* current_ord,
+                                        uint8_t* digital,
+                                        size_t* digital_ord);
+
+    /* dll_api.h:239 (no digital model is in scope: always returns 3) */
+    int circuit_set_model_digital(void* circuit_ptr, size_t vec_pos, size_t chunk_pos, size_t attribute_index, uint8_t state);
+
+    /* dll_api.h:242-255 / dll_main.cpp:2899-2934 */
+    int analyze_circuit(void* circuit_ptr,
+                        size_t* vec_pos,
+                        size_t* chunk_pos,
+                        size_t comp_size,
+                        int* changed_ele,
+                        size_t* changed_ind,
+                        double* changed_prop,
+                        size_t prop_size,
+                        double* voltage,
+                        size_t* voltage_ord,
+                        double* current,
+                        size_t* current_ord,
+                        bool* digital,
+                        size_t* digital_ord);
+
+    /* ===== Part 2: additive surface ============================================================================== */
+
+    /* C++-only knobs of the reference made reachable from C: phy_engine::environment (environment.h:7-22) and the AC
+     * sweep settings (analyzer/AC.h).  env8 = V_eps_max, V_epsr_max, I_eps_max, I_epsr_max, g_min, r_open,
+     * temperature, norm_temperature. */
+    int circuit_set_env(void* circuit_ptr, double const* env8);
+    int circuit_set_ac_sweep(void* circuit_ptr, int sweep_type, double omega_start, double omega_stop, size_t points);
+
+    /* unknown vector layout of circult::prepare() (circuit.h:481-540): node_index, then node_counter + branch.index */
+    int circuit_unknown_count(void* circuit_ptr, size_t* n_nodes, size_t* n_branches);
+    long long circuit_pin_unknown(void* circuit_ptr, size_t vec_pos, size_t chunk_pos, size_t pin); /* -1 ground, -2 n/c */
+    long long circuit_branch_unknown(void* circuit_ptr, size_t vec_pos, size_t chunk_pos, size_t branch);
+    /* last solution of circuit_analyze(): re[n], im[n] (im may be NULL; zero outside AC) */
+    int circuit_get_solution(void* circuit_ptr, double* re, double* im);
+
+    /* Batch of independent instances of one netlist (Monte-Carlo / parameter sweep / frequency sweep). */
+    void* circuit_batch_create(void* circuit_ptr, size_t n_instances);
+    void circuit_batch_destroy(void* batch);
+    int circuit_batch_set_device(void* batch, int device);
+    int circuit_batch_set_stream(void* batch, void* cuda_stream);
+    /* per-instance values of one model attribute; values[n_instances] in the attribute's public unit */
+    int circuit_batch_set_param(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values);
+    int circuit_batch_set_ac_sweep(void* batch, int sweep_type, double omega_start, double omega_stop, size_t points);
+    /* record these unknowns after every transient step (waveform store [steps][n_probes][n_instances]) */
+    int circuit_batch_set_probes(void* batch, size_t const* unknowns, size_t n_probes);
+    /* compile + allocate + upload parameters without running (so device pointers below are valid) */
+    int circuit_batch_prepare(void* batch);
+    /* zero x and all device state, keep the per-instance parameters (a fresh Monte-Carlo start) */
+    int circuit_batch_reset_state(void* batch);
+    /* analysis type / settings are those of the parent circuit.  0 = every lane ok; 1 = error or some lane failed. */
+    int circuit_batch_analyze(void* batch);
+
+    size_t circuit_batch_lanes(void* batch);  /* n_instances * frequency points of the last analyze */
+    size_t circuit_batch_points(void* batch);
+    uint64_t circuit_batch_total_solves(void* batch); /* sum of solve_once-equivalents in the last analyze */
+    double circuit_batch_tr_duration(void* batch);
+    int circuit_batch_solution(void* batch, double* x);        /* [n_instances][n] real state */
+    int circuit_batch_ac_solution(void* batch, double* x);     /* [lanes][n][2] */
+    int circuit_batch_ac_omegas(void* batch, double* omegas);  /* [points] */
+    int circuit_batch_status(void* batch, int32_t* status);    /* [lanes] 0 ok, 1 no convergence, 2 singular */
+    int circuit_batch_newton_iters(void* batch, uint32_t* n);  /* [lanes] solves per lane */
+    int circuit_batch_waveform(void* batch, double* w);        /* [steps][n_probes][n_instances] */
+    /* program statistics for roofline accounting: mode 0 DC/OP, 1 TR, 2 TROP, 3 AC */
+    int circuit_batch_stats(void* batch, int mode, size_t* n_unknowns, size_t* nnz_a, size_t* nnz_lu, size_t* n_fma, size_t* n_lane_slots, size_t* n_inst_slots);
+    /* HBM-resident access: device row of a swept parameter (n_instances doubles) and of the real solution
+     * (unknown j at x0 + j * lane_stride) */
+    int circuit_batch_param_device_ptr(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double** dptr);
+    int circuit_batch_solution_device_ptr(void* batch, double** x0, size_t* lane_stride);
+
+    /* ===== Part 3: introspection of the symbolic phase (no device needed; used by tests and DESIGN.md tooling) ===== */
+    int circuit_batch_compile_host(void* batch);
+    size_t circuit_batch_program_words(void* batch, int mode, int section); /* section 0 prep, 1 step, 2 iter */
+    int circuit_batch_program_copy(void* batch, int mode, int section, uint32_t* out);
+    size_t circuit_batch_const_count(void* batch);
+    int circuit_batch_const_copy(void* batch, double* out);
+    /* info[8] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns */
+    int circuit_batch_program_info(void* batch, int mode, int64_t* info);
+    long long circuit_batch_swept_slot(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size);
+    int circuit_batch_swept_values(void* batch, long long slot, double* out);
+
+    int phy_engine_b200_device_count(void);
+    uint64_t phy_engine_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,506 @@
+// batch.cpp — the analysis driver: circult::analyze() (circuits/circuit.h:179-296) re-stated as a launch plan
+// over the sm_100a kernels, for B independent instances at once.  The host only sequences phases and moves
+// parameters/results; every solve runs on the device.  No CUDA device => analyze() fails with an error.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "pe_host.hpp"
+
+namespace pe_b200
+{
+    namespace
+    {
+        thread_local std::string g_last_error;
+
+        std::int64_t round_up32(std::size_t n) { return static_cast<std::int64_t>((n + 31) / 32 * 32); }
+
+        bool dev_fail(std::string& err, char const* what)
+        {
+            err = std::string{what} + ": " + pe_b200_dev_last_error();
+            set_last_error(err);
+            return false;
+        }
+    }  // namespace
+
+    void set_last_error(std::string s) { g_last_error = std::move(s); }
+
+    char const* last_error() { return g_last_error.c_str(); }
+
+    device_buf::~device_buf() { release(); }
+
+    void device_buf::release()
+    {
+        if(p) { (void)pe_b200_dev_free(p); }
+        p = nullptr;
+        bytes = 0;
+    }
+
+    bool device_buf::ensure(std::size_t n)
+    {
+        if(n <= bytes && p != nullptr) { return true; }
+        release();
+        if(pe_b200_dev_malloc(&p, n) != 0)
+        {
+            p = nullptr;
+            return false;
+        }
+        bytes = n;
+        return true;
+    }
+
+    bool batch::compile_host(bool& layout_change)
+    {
+        std::vector<sweep_key> keys;
+        for(auto const& [k, v]: sweeps) { keys.push_back(k); }
+        layout_change = !cc || cc_structure_rev != parent->structure_rev || keys != layout_keys;
+        bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step};
+        if(!need) { return true; }
+        layout_keys = keys;
+
+        compile_input in;
+        in.nl = &parent->nl;
+        in.env = parent->env;
+        in.dt = parent->tr.t_step;
+        auto const& a{ac.points > 0 || ac.omega != 0.0 || ac.omega_start != 0.0 ? ac : parent->ac};
+        in.omega0 = (a.sweep == sweep_type::single || a.points <= 1) ? a.omega : std::sqrt(std::fabs(a.omega_start * a.omega_stop));
+        if(!(in.omega0 > 0.0)) { in.omega0 = 1.0; }
+        for(auto const& [k, v]: sweeps) { in.swept_lane0[k] = v.empty() ? 0.0 : v[0]; }
+        cc = compile_circuit(in);
+        if(!cc)
+        {
+            error = "compile failed";
+            set_last_error(error);
+            return false;
+        }
+        cc_structure_rev = parent->structure_rev;
+        cc_param_rev = parent->param_rev;
+        cc_dt = parent->tr.t_step;
+        uploaded.fill(false);
+        device_stale = true;
+        return true;
+    }
+
+    bool batch::ensure_compiled()
+    {
+        if(pe_b200_dev_count() <= 0)
+        {
+            error = "no CUDA device visible: the B200 MNA path has no CPU fallback";
+            set_last_error(error);
+            return false;
+        }
+        if(pe_b200_dev_set(device) != 0) { return dev_fail(error, "set device"); }
+        bool layout_change{};
+        if(!compile_host(layout_change)) { return false; }
+        if(layout_change) { layout_pending = true; }
+        if(!device_stale) { return true; }
+        device_stale = false;
+        bool const lc{layout_pending};
+        layout_pending = false;
+
+        LSi = round_up32(n_inst);
+        std::size_t const wi_bytes{static_cast<std::size_t>(cc->n_inst_slots) * static_cast<std::size_t>(LSi) * sizeof(double)};
+        if(lc)
+        {
+            if(!d_wi.ensure(wi_bytes)) { return dev_fail(error, "alloc instance workspace"); }
+            if(pe_b200_dev_memset0(d_wi.p, wi_bytes, stream) != 0) { return dev_fail(error, "zero instance workspace"); }
+            sweeps_dirty = true;
+            tr_duration = 0.0;
+            last_step = 0.0;
+        }
+        else if(d_wi.bytes < wi_bytes)
+        {
+            // derived slots were added behind the persistent ones: grow, keeping state is not possible -> reset
+            if(!d_wi.ensure(wi_bytes)) { return dev_fail(error, "alloc instance workspace"); }
+            if(pe_b200_dev_memset0(d_wi.p, wi_bytes, stream) != 0) { return dev_fail(error, "zero instance workspace"); }
+            sweeps_dirty = true;
+        }
+        if(!d_prep.ensure(cc->prep.size() * 4)) { return dev_fail(error, "alloc prep"); }
+        if(pe_b200_dev_h2d(d_prep.p, cc->prep.data(), cc->prep.size() * 4, stream) != 0) { return dev_fail(error, "upload prep"); }
+        if(!d_status.ensure(static_cast<std::size_t>(LSi) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSi) * 4)) { return dev_fail(error, "alloc status"); }
+        return true;
+    }
+
+    bool batch::upload_sweeps()
+    {
+        if(!sweeps_dirty) { return true; }
+        for(auto const& [k, v]: sweeps)
+        {
+            auto it{cc->swept_slot.find(k)};
+            if(it == cc->swept_slot.end()) { continue; }
+            auto* dst{static_cast<double*>(d_wi.p) + static_cast<std::int64_t>(it->second) * LSi};
+            if(pe_b200_dev_h2d(dst, v.data(), std::min(v.size(), n_inst) * sizeof(double), stream) != 0) { return dev_fail(error, "upload sweep"); }
+        }
+        sweeps_dirty = false;
+        return true;
+    }
+
+    bool batch::run_phase(prog_mode m, bool with_prep, bool nonlinear, int n_steps, bool time_stepping, double t0, double dt, std::size_t lanes, int ppi)
+    {
+        int const mi{static_cast<int>(m)};
+        auto& pr{cc->prog[static_cast<std::size_t>(mi)]};
+        if(!uploaded[static_cast<std::size_t>(mi)])
+        {
+            if(!d_step[static_cast<std::size_t>(mi)].ensure(pr.step.size() * 4) || !d_iter[static_cast<std::size_t>(mi)].ensure(pr.iter.size() * 4))
+            {
+                return dev_fail(error, "alloc program");
+            }
+            if(pe_b200_dev_h2d(d_step[static_cast<std::size_t>(mi)].p, pr.step.data(), pr.step.size() * 4, stream) != 0 ||
+               pe_b200_dev_h2d(d_iter[static_cast<std::size_t>(mi)].p, pr.iter.data(), pr.iter.size() * 4, stream) != 0)
+            {
+                return dev_fail(error, "upload program");
+            }
+            uploaded[static_cast<std::size_t>(mi)] = true;
+        }
+        // constants (dt patched in place)
+        if(cc->dt_slot >= 0) { cc->cst[static_cast<std::size_t>(cc->dt_slot)] = dt; }
+        if(!d_cst.ensure(cc->cst.size() * sizeof(double))) { return dev_fail(error, "alloc const table"); }
+        if(pe_b200_dev_h2d(d_cst.p, cc->cst.data(), cc->cst.size() * sizeof(double), stream) != 0) { return dev_fail(error, "upload const table"); }
+
+        std::int64_t const LSl{round_up32(lanes)};
+        std::size_t const wl_bytes{static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double)};
+        if(!d_wl.ensure(wl_bytes)) { return dev_fail(error, "alloc lane workspace"); }
+        if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
+
+        pe_b200_run r{};
+        r.prep = with_prep ? static_cast<std::uint32_t const*>(d_prep.p) : nullptr;
+        r.step = static_cast<std::uint32_t const*>(d_step[static_cast<std::size_t>(mi)].p);
+        r.iter = static_cast<std::uint32_t const*>(d_iter[static_cast<std::size_t>(mi)].p);
+        r.cst = static_cast<double const*>(d_cst.p);
+        r.wi = static_cast<double*>(d_wi.p);
+        r.wl = static_cast<double*>(d_wl.p);
+        r.status = static_cast<std::int32_t*>(d_status.p);
+        r.solves = static_cast<std::uint32_t*>(d_solves.p);
+        r.wave = nullptr;
+        r.probes = nullptr;
+        r.n_probe = 0;
+        if(time_stepping && !probes.empty())
+        {
+            std::vector<std::uint32_t> po;
+            for(int u: probes) { po.push_back(pr.x_opnd[static_cast<std::size_t>(u)]); }
+            if(!d_probes.ensure(po.size() * 4) || !d_wave.ensure(static_cast<std::size_t>(n_steps) * po.size() * static_cast<std::size_t>(LSl) * sizeof(double)))
+            {
+                return dev_fail(error, "alloc waveform store");
+            }
+            if(pe_b200_dev_h2d(d_probes.p, po.data(), po.size() * 4, stream) != 0) { return dev_fail(error, "upload probes"); }
+            r.wave = static_cast<double*>(d_wave.p);
+            r.probes = static_cast<std::uint32_t const*>(d_probes.p);
+            r.n_probe = static_cast<std::int32_t>(po.size());
+            wave_steps = static_cast<std::size_t>(n_steps);
+        }
+        r.LSi = LSi;
+        r.LSl = LSl;
+        r.n_lanes = static_cast<std::int32_t>(lanes);
+        r.ppi = ppi;
+        r.cplx = pr.cplx ? 1 : 0;
+        r.nonlinear = nonlinear ? 1 : 0;
+        r.max_iter = 64;  // circuit.h:898
+        r.n_steps = n_steps;
+        r.time_stepping = time_stepping ? 1 : 0;
+        r.t0 = t0;
+        r.dt = dt;
+        auto const& env{parent->env};
+        // default tolerances of circult::solve() (circuit.h:900-903)
+        r.v_abstol = env.V_eps_max > 0.0 ? env.V_eps_max : 1e-6;
+        r.v_reltol = env.V_epsr_max > 0.0 ? env.V_epsr_max : 1e-3;
+        r.i_abstol = env.I_eps_max > 0.0 ? env.I_eps_max : 1e-12;
+        r.i_reltol = env.I_epsr_max > 0.0 ? env.I_epsr_max : r.v_reltol;
+        last_LSl = LSl;
+        last_lanes = lanes;
+        last_cplx = pr.cplx;
+        if(pe_b200_launch(&r, stream) != 0) { return dev_fail(error, "launch"); }
+        return true;
+    }
+
+    bool batch::analyze()
+    {
+        error.clear();
+        if(parent == nullptr || n_inst == 0)
+        {
+            error = "empty batch";
+            set_last_error(error);
+            return false;
+        }
+        if(!ensure_compiled() || !upload_sweeps()) { return false; }
+        auto const at{parent->at};
+        int const n{cc->num.unknowns()};
+        if(n == 0) { return true; }  // circuit.h:1116-1120: nothing to solve
+        bool const nonlin{parent->nl.has_nonlinear()};
+        // status / solve counters start clean for every analyze()
+        if(pe_b200_dev_memset0(d_status.p, d_status.bytes, stream) != 0 || pe_b200_dev_memset0(d_solves.p, d_solves.bytes, stream) != 0)
+        {
+            return dev_fail(error, "zero status");
+        }
+        last_points = 1;
+
+        auto run_tr = [&](bool with_prep) -> bool
+        {
+            double const dt{parent->tr.t_step};
+            // step count with the reference's floating-point time accumulation (circuit.h:242-248)
+            double const end_time{tr_duration + parent->tr.t_stop};
+            double t{tr_duration};
+            int steps{};
+            while(t < end_time)
+            {
+                t = t + dt;
+                ++steps;
+            }
+            if(steps == 0)
+            {
+                if(with_prep) { return run_phase(prog_mode::TR, true, nonlin, 0, false, tr_duration, dt, n_inst, 1); }
+                return true;
+            }
+            if(!run_phase(prog_mode::TR, with_prep, nonlin, steps, true, tr_duration, dt, n_inst, 1)) { return false; }
+            tr_duration = t;
+            last_step = dt;
+            return true;
+        };
+
+        auto run_ac = [&]() -> bool
+        {
+            auto const& a{(ac.points > 0 || ac.omega != 0.0) ? ac : parent->ac};
+            ac_omegas.clear();
+            if(a.sweep == sweep_type::single || a.points <= 1) { ac_omegas.push_back(a.omega); }
+            else if(a.sweep == sweep_type::linear)
+            {
+                // circuit.h:399-410
+                double const step{(a.omega_stop - a.omega_start) / static_cast<double>(a.points - 1)};
+                for(std::size_t i{}; i < a.points; ++i) { ac_omegas.push_back(a.omega_start + step * static_cast<double>(i)); }
+            }
+            else
+            {
+                // circuit.h:412-428: cumulative product (the drift is part of the contract)
+                if(a.omega_start <= 0.0 || a.omega_stop <= 0.0)
+                {
+                    error = "log sweep needs positive omega_start/omega_stop";
+                    set_last_error(error);
+                    return false;
+                }
+                double const ratio{std::pow(a.omega_stop / a.omega_start, 1.0 / static_cast<double>(a.points - 1))};
+                double om{a.omega_start};
+                for(std::size_t i{}; i < a.points; ++i)
+                {
+                    ac_omegas.push_back(om);
+                    om *= ratio;
+                }
+            }
+            std::size_t const P{ac_omegas.size()};
+            std::size_t const lanes{n_inst * P};
+            std::int64_t const LSl{round_up32(lanes)};
+            auto const& pr{cc->prog[static_cast<int>(prog_mode::AC)]};
+            if(!d_wl.ensure(static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double)))
+            {
+                return dev_fail(error, "alloc lane workspace");
+            }
+            std::vector<double> om(lanes);
+            for(std::size_t i{}; i < n_inst; ++i) { std::copy(ac_omegas.begin(), ac_omegas.end(), om.begin() + static_cast<std::ptrdiff_t>(i * P)); }
+            auto* dst{static_cast<double*>(d_wl.p) + static_cast<std::int64_t>(pr.omega_slot) * LSl};
+            if(pe_b200_dev_h2d(dst, om.data(), lanes * sizeof(double), stream) != 0) { return dev_fail(error, "upload omega"); }
+            if(pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "sync"); }  // `om` is pageable host memory
+            // the AC phase re-uses status/solves with `lanes` entries
+            if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
+            if(pe_b200_dev_memset0(d_status.p, d_status.bytes, stream) != 0 || pe_b200_dev_memset0(d_solves.p, d_solves.bytes, stream) != 0)
+            {
+                return dev_fail(error, "zero status");
+            }
+            last_points = P;
+            return run_phase(prog_mode::AC, false, false, 1, false, 0.0, parent->tr.t_step, lanes, static_cast<int>(P));
+        };
+
+        bool ok{true};
+        std::uint64_t op_solves{};
+        bool op_failed{false};
+        switch(at)
+        {
+            case analyze_type::OP:
+            case analyze_type::DC: ok = run_phase(prog_mode::DC, true, nonlin, 1, false, tr_duration, parent->tr.t_step, n_inst, 1); break;
+            case analyze_type::TR:
+            {
+                if(parent->tr.t_step <= 0.0)
+                {
+                    error = "TR needs t_step > 0";
+                    set_last_error(error);
+                    return false;
+                }
+                ok = run_tr(true);
+                break;
+            }
+            case analyze_type::TROP:
+            {
+                if(parent->tr.t_step <= 0.0)
+                {
+                    error = "TROP needs t_step > 0";
+                    set_last_error(error);
+                    return false;
+                }
+                // 1) operating point with C open / L short, sources at t = 0 (circuit.h:264-266; base.h:289-292)
+                ok = run_phase(prog_mode::TROP, true, nonlin, 1, false, 0.0, parent->tr.t_step, n_inst, 1);
+                // 2) transient from there (lanes that failed stay flagged and are skipped)
+                if(ok) { ok = run_tr(false); }
+                break;
+            }
+            case analyze_type::AC:
+            case analyze_type::ACOP:
+            {
+                // bias point first when needed (circuit.h:199-209, 213-224), then the sweep
+                bool const need_op{at == analyze_type::ACOP || nonlin};
+                if(need_op) { ok = run_phase(prog_mode::DC, true, nonlin, 1, false, tr_duration, parent->tr.t_step, n_inst, 1); }
+                else
+                {
+                    ok = run_phase(prog_mode::DC, true, false, 0, false, tr_duration, parent->tr.t_step, n_inst, 1);  // prep only
+                }
+                if(ok && need_op)
+                {
+                    std::vector<std::int32_t> st(n_inst);
+                    std::vector<std::uint32_t> sv(n_inst);
+                    if(pe_b200_dev_d2h(st.data(), d_status.p, n_inst * 4, stream) != 0 || pe_b200_dev_d2h(sv.data(), d_solves.p, n_inst * 4, stream) != 0 ||
+                       pe_b200_dev_sync(stream) != 0)
+                    {
+                        return dev_fail(error, "download bias status");
+                    }
+                    for(std::size_t i{}; i < n_inst; ++i)
+                    {
+                        op_solves += sv[i];
+                        if(st[i] != PE_ST_OK) { op_failed = true; }
+                    }
+                    if(op_failed)
+                    {
+                        error = "AC: bias-point solve failed on at least one instance";
+                        set_last_error(error);
+                        total_solves = op_solves;
+                        return false;
+                    }
+                }
+                if(ok) { ok = run_ac(); }
+                break;
+            }
+            default: ok = false; break;
+        }
+        if(!ok) { return false; }
+
+        // one host sync per analyze(): status + solve counters
+        std::vector<std::int32_t> st(last_lanes);
+        std::vector<std::uint32_t> sv(last_lanes);
+        if(pe_b200_dev_d2h(st.data(), d_status.p, last_lanes * 4, stream) != 0 || pe_b200_dev_d2h(sv.data(), d_solves.p, last_lanes * 4, stream) != 0 ||
+           pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download status");
+        }
+        total_solves = op_solves;
+        bool all_ok{true};
+        for(std::size_t i{}; i < last_lanes; ++i)
+        {
+            total_solves += sv[i];
+            if(st[i] != PE_ST_OK) { all_ok = false; }
+        }
+        if(!all_ok)
+        {
+            error = "analyze: at least one lane failed (no convergence or singular matrix)";
+            set_last_error(error);
+        }
+        return all_ok;
+    }
+
+    bool batch::get_status(std::int32_t* st)
+    {
+        if(last_lanes == 0) { return false; }
+        if(pe_b200_dev_d2h(st, d_status.p, last_lanes * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download status"); }
+        return true;
+    }
+
+    bool batch::get_solves(std::uint32_t* sv)
+    {
+        if(last_lanes == 0) { return false; }
+        if(pe_b200_dev_d2h(sv, d_solves.p, last_lanes * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download solves"); }
+        return true;
+    }
+
+    bool batch::get_solution(double* x)
+    {
+        if(!cc) { return false; }
+        std::size_t const n{static_cast<std::size_t>(cc->num.unknowns())};
+        if(n == 0) { return true; }
+        // x lives in INST slots [0, n): rows of LSi doubles -> packed [n][n_inst], then transposed on the host
+        std::vector<double> tmp(n * n_inst);
+        if(pe_b200_dev_d2h_2d(tmp.data(), n_inst * sizeof(double), d_wi.p, static_cast<std::size_t>(LSi) * sizeof(double), n_inst * sizeof(double), n, stream) != 0 ||
+           pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download solution");
+        }
+        for(std::size_t j{}; j < n; ++j)
+        {
+            for(std::size_t i{}; i < n_inst; ++i) { x[i * n + j] = tmp[j * n_inst + i]; }
+        }
+        return true;
+    }
+
+    bool batch::get_ac_solution(double* x)
+    {
+        if(!cc || !last_cplx) { return false; }
+        auto const& pr{cc->prog[static_cast<int>(prog_mode::AC)]};
+        std::size_t const n{static_cast<std::size_t>(cc->num.unknowns())};
+        std::size_t const lanes{last_lanes};
+        if(n == 0) { return true; }
+        // x_opnd slots are contiguous: [x0.re, x0.im, x1.re, ...] rows of LSl doubles
+        std::size_t const slot0{PE_OPND_SLOT(pr.x_opnd[0])};
+        std::vector<double> tmp(2 * n * lanes);
+        auto const* src{static_cast<double const*>(d_wl.p) + static_cast<std::int64_t>(slot0) * last_LSl};
+        if(pe_b200_dev_d2h_2d(tmp.data(), lanes * sizeof(double), src, static_cast<std::size_t>(last_LSl) * sizeof(double), lanes * sizeof(double), 2 * n, stream) != 0 ||
+           pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download AC solution");
+        }
+        for(std::size_t j{}; j < 2 * n; ++j)
+        {
+            for(std::size_t l{}; l < lanes; ++l) { x[l * 2 * n + j] = tmp[j * lanes + l]; }
+        }
+        return true;
+    }
+
+    bool batch::get_wave(double* w)
+    {
+        if(probes.empty() || wave_steps == 0 || d_wave.p == nullptr) { return false; }
+        std::size_t const rows{wave_steps * probes.size()};
+        if(pe_b200_dev_d2h_2d(w, n_inst * sizeof(double), d_wave.p, static_cast<std::size_t>(last_LSl) * sizeof(double), n_inst * sizeof(double), rows, stream) != 0 ||
+           pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download waveform");
+        }
+        return true;
+    }
+
+    bool circuit::analyze()
+    {
+        if(!solo)
+        {
+            solo = std::make_unique<batch>();
+            solo->parent = this;
+            solo->n_inst = 1;
+        }
+        solo->ac = {};
+        bool const ok{solo->analyze()};
+        if(!solo->cc) { return false; }
+        num_host = solo->cc->num;
+        std::size_t const n{static_cast<std::size_t>(num_host.unknowns())};
+        x_host.assign(n, 0.0);
+        xi_host.assign(n, 0.0);
+        if(n == 0) { return ok; }
+        if(solo->last_cplx && solo->last_lanes >= 1)
+        {
+            // node_t::an.voltage keeps the complex AC solution of the last point (circuit.h:1521)
+            std::vector<double> all(solo->last_lanes * 2 * n);
+            if(!solo->get_ac_solution(all.data())) { return false; }
+            std::size_t const l{solo->last_lanes - 1};
+            for(std::size_t j{}; j < n; ++j)
+            {
+                x_host[j] = all[l * 2 * n + 2 * j];
+                xi_host[j] = all[l * 2 * n + 2 * j + 1];
+            }
+        }
+        else
+        {
+            if(!solo->get_solution(x_host.data())) { return false; }
+        }
+        return ok;
+    }
+}  // namespace pe_b200

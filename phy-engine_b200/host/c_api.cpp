@@ -1,0 +1,733 @@
+// c_api.cpp — the extern "C" surface declared in include/phy_engine_b200.h.
+// Part 1 mirrors src/dll_main.cpp of the reference entry point by entry point (citations in the header); the
+// handle is a pe_b200::circuit instead of a phy_engine::circult, everything a caller can observe through the
+// C ABI (wire format, component order, prefix-sum layouts, return codes) is kept.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/phy_engine_b200.h"
+#include "pe_host.hpp"
+
+namespace
+{
+    using namespace pe_b200;
+
+    // netlist::model_pos of the reference: models live in 4 KiB chunks of sizeof(model_base) = 80 bytes
+    // (netlist/netlist.h:20-21) -> 51 models per chunk; component i sits at (i % 51, i / 51).
+    constexpr std::size_t k_chunk{4096 / 80};
+
+    int elem_of(circuit const& c, std::size_t vec_pos, std::size_t chunk_pos)
+    {
+        if(vec_pos >= k_chunk) { return -1; }
+        std::size_t const e{chunk_pos * k_chunk + vec_pos};
+        return e < c.nl.elems.size() ? static_cast<int>(e) : -1;
+    }
+
+    int uf_find(int x, std::vector<int>& parent, std::vector<char>& visited)
+    {
+        if(parent[static_cast<std::size_t>(x)] != x) { parent[static_cast<std::size_t>(x)] = uf_find(parent[static_cast<std::size_t>(x)], parent, visited); }
+        visited[static_cast<std::size_t>(x)] = 1;
+        return parent[static_cast<std::size_t>(x)];
+    }
+
+    // build_netlist_from_wires (dll_main.cpp:1529-1705): nets = union-find over pin slots, ground forced root,
+    // nodes created in ascending root-slot order.
+    void wire_up(netlist& nl, int const* elements, int ele_size, int const* wires, int wire_count, std::vector<int> const& elem_of_ele)
+    {
+        std::vector<std::size_t> base(static_cast<std::size_t>(ele_size) + 1, 0), pins(static_cast<std::size_t>(ele_size), 0);
+        for(int i{}; i < ele_size; ++i)
+        {
+            if(elements[i] && elem_of_ele[static_cast<std::size_t>(i)] >= 0)
+            {
+                pins[static_cast<std::size_t>(i)] = static_cast<std::size_t>(nl.elems[static_cast<std::size_t>(elem_of_ele[static_cast<std::size_t>(i)])].d->pins);
+            }
+            base[static_cast<std::size_t>(i) + 1] = base[static_cast<std::size_t>(i)] + pins[static_cast<std::size_t>(i)];
+        }
+        int const total{static_cast<int>(base[static_cast<std::size_t>(ele_size)])};
+        int const GROUND{total};
+        std::vector<int> parent(static_cast<std::size_t>(total) + 1);
+        std::vector<char> visited(static_cast<std::size_t>(total) + 1, 0);
+        for(int i{}; i <= total; ++i) { parent[static_cast<std::size_t>(i)] = i; }
+        for(int w{}; w < wire_count; ++w)
+        {
+            int const e1{wires[w * 4]}, p1{wires[w * 4 + 1]}, e2{wires[w * 4 + 2]}, p2{wires[w * 4 + 3]};
+            if(e1 < 0 || e2 < 0 || e1 >= ele_size || e2 >= ele_size) { continue; }
+            int n1, n2;
+            if(!elements[e1]) { n1 = GROUND; }
+            else
+            {
+                if(p1 < 0 || static_cast<std::size_t>(p1) >= pins[static_cast<std::size_t>(e1)]) { continue; }
+                n1 = static_cast<int>(base[static_cast<std::size_t>(e1)]) + p1;
+            }
+            if(!elements[e2]) { n2 = GROUND; }
+            else
+            {
+                if(p2 < 0 || static_cast<std::size_t>(p2) >= pins[static_cast<std::size_t>(e2)]) { continue; }
+                n2 = static_cast<int>(base[static_cast<std::size_t>(e2)]) + p2;
+            }
+            int const r1{uf_find(n1, parent, visited)};
+            int const r2{uf_find(n2, parent, visited)};
+            if(r1 != r2)
+            {
+                if(r1 == GROUND) { parent[static_cast<std::size_t>(r2)] = r1; }
+                else if(r2 == GROUND) { parent[static_cast<std::size_t>(r1)] = r2; }
+                else
+                {
+                    parent[static_cast<std::size_t>(r2)] = r1;
+                }
+            }
+        }
+        std::unordered_map<int, int> node_map;
+        for(int i{}; i < total; ++i)
+        {
+            if(parent[static_cast<std::size_t>(i)] == i && visited[static_cast<std::size_t>(i)]) { node_map[i] = nl.create_node(); }
+        }
+        node_map[GROUND] = -1;
+        for(int i{}; i < ele_size; ++i)
+        {
+            if(!elements[i] || elem_of_ele[static_cast<std::size_t>(i)] < 0) { continue; }
+            for(std::size_t p{}; p < pins[static_cast<std::size_t>(i)]; ++p)
+            {
+                int const id{static_cast<int>(base[static_cast<std::size_t>(i)] + p)};
+                if(!visited[static_cast<std::size_t>(id)]) { continue; }
+                int const root{uf_find(id, parent, visited)};
+                (void)nl.add_to_node(elem_of_ele[static_cast<std::size_t>(i)], static_cast<int>(p), node_map[root]);
+            }
+        }
+    }
+
+    double to_internal(int code, int idx, double v)
+    {
+        if(code == E_VAC || code == E_IAC)
+        {
+            if(idx == 1) { return v * (2.0 * 3.14159265358979323846264338327950288); }
+            if(idx == 2) { return v * (3.14159265358979323846264338327950288 / 180.0); }
+        }
+        if((code == E_SWITCH && idx == 0) || (code == E_PN && idx == 7)) { return v != 0.0 ? 1.0 : 0.0; }
+        return v;
+    }
+
+    int sample_impl(circuit& c, std::size_t* vec_pos, std::size_t* chunk_pos, std::size_t comp_size, double* voltage, std::size_t* vo, double* current, std::size_t* co)
+    {
+        bool const have{!c.x_host.empty()};
+        for(std::size_t i{}; i < comp_size; ++i)
+        {
+            int const ei{elem_of(c, vec_pos[i], chunk_pos[i])};
+            if(ei < 0) { continue; }
+            auto const& e{c.nl.elems[static_cast<std::size_t>(ei)]};
+            for(int j{}; j < e.d->pins; ++j)
+            {
+                double v{};
+                int const node{e.pin_node[j]};
+                if(have && node >= 0)
+                {
+                    int const u{c.num_host.node_index[static_cast<std::size_t>(node)]};
+                    if(u >= 0) { v = c.x_host[static_cast<std::size_t>(u)]; }
+                }
+                voltage[static_cast<std::size_t>(j) + vo[i]] = v;
+            }
+            for(int j{}; j < e.d->branches; ++j)
+            {
+                double v{};
+                if(have) { v = c.x_host[static_cast<std::size_t>(c.num_host.n_nodes + c.num_host.branch0[static_cast<std::size_t>(ei)] + j)]; }
+                current[static_cast<std::size_t>(j) + co[i]] = v;
+            }
+        }
+        return 0;
+    }
+}  // namespace
+
+extern "C"
+{
+    char const* phy_engine_last_error(void) { return pe_b200::last_error(); }
+
+    void phy_engine_clear_error(void) { pe_b200::set_last_error({}); }
+
+    void phy_engine_string_free(char* s) { delete[] s; }
+
+    void* create_circuit(int* elements, size_t ele_size, int* wires, size_t wires_size, double* properties, size_t** vec_pos, size_t** chunk_pos, size_t* comp_size)
+    {
+        set_last_error({});
+        if(vec_pos == nullptr || chunk_pos == nullptr || comp_size == nullptr)
+        {
+            set_last_error("create_circuit: output pointers are null");
+            return nullptr;
+        }
+        *vec_pos = nullptr;
+        *chunk_pos = nullptr;
+        *comp_size = 0;
+        if(elements == nullptr || properties == nullptr)
+        {
+            set_last_error("create_circuit: elements/properties are null");
+            return nullptr;
+        }
+        auto* c{new(std::nothrow) circuit{}};
+        if(c == nullptr) { return nullptr; }
+        // defaults of dll_main.cpp:2530-2535
+        c->at = analyze_type::TR;
+        c->tr.t_step = 1e-6;
+        c->tr.t_stop = 1e-6;
+        *vec_pos = static_cast<size_t*>(std::malloc((ele_size ? ele_size : 1) * sizeof(size_t)));
+        *chunk_pos = static_cast<size_t*>(std::malloc((ele_size ? ele_size : 1) * sizeof(size_t)));
+        std::vector<int> elem_of_ele(ele_size, -1);
+        double const* prop{properties};
+        std::size_t k{};
+        for(std::size_t i{}; i < ele_size; ++i)
+        {
+            if(!elements[i]) { continue; }
+            std::size_t used{};
+            int const ei{c->nl.add_model(elements[i], prop, &used)};
+            if(ei < 0)
+            {
+                set_last_error("create_circuit: element code " + std::to_string(elements[i]) + " at index " + std::to_string(i) +
+                               " is outside the B200 hot path (SURVEY.md §8)");
+                std::free(*vec_pos);
+                std::free(*chunk_pos);
+                *vec_pos = nullptr;
+                *chunk_pos = nullptr;
+                delete c;
+                return nullptr;
+            }
+            prop += used;
+            elem_of_ele[i] = ei;
+            (*vec_pos)[k] = static_cast<std::size_t>(ei) % k_chunk;
+            (*chunk_pos)[k] = static_cast<std::size_t>(ei) / k_chunk;
+            ++k;
+        }
+        *comp_size = k;
+        int const wire_count{static_cast<int>(wires_size / 4)};
+        if(wires != nullptr && wire_count > 0) { wire_up(c->nl, elements, static_cast<int>(ele_size), wires, wire_count, elem_of_ele); }
+        return c;
+    }
+
+    void* create_circuit_ex(int* elements,
+                            size_t ele_size,
+                            int* wires,
+                            size_t wires_size,
+                            double* properties,
+                            char const* const*,
+                            size_t const*,
+                            size_t,
+                            size_t const*,
+                            size_t const*,
+                            size_t** vec_pos,
+                            size_t** chunk_pos,
+                            size_t* comp_size)
+    {
+        return create_circuit(elements, ele_size, wires, wires_size, properties, vec_pos, chunk_pos, comp_size);
+    }
+
+    void destroy_circuit(void* circuit_ptr, size_t* vec_pos, size_t* chunk_pos)
+    {
+        delete static_cast<circuit*>(circuit_ptr);
+        std::free(vec_pos);
+        std::free(chunk_pos);
+    }
+
+    int circuit_set_analyze_type(void* p, uint32_t v)
+    {
+        if(p == nullptr) { return 1; }
+        static_cast<circuit*>(p)->at = static_cast<analyze_type>(v);
+        return 0;
+    }
+
+    int circuit_set_tr(void* p, double t_step, double t_stop)
+    {
+        if(p == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->tr.t_step = t_step;
+        c->tr.t_stop = t_stop;
+        return 0;
+    }
+
+    int circuit_set_ac_omega(void* p, double omega)
+    {
+        if(p == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->ac.sweep = sweep_type::single;  // dll_main.cpp:2162
+        c->ac.omega = omega;
+        return 0;
+    }
+
+    int circuit_set_temperature(void* p, double t)
+    {
+        if(p == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->env.temperature = t;
+        ++c->param_rev;
+        return 0;
+    }
+
+    int circuit_set_tnom(void* p, double t)
+    {
+        if(p == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->env.norm_temperature = t;
+        ++c->param_rev;
+        return 0;
+    }
+
+    int circuit_set_model_double_by_name(void* p, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double value)
+    {
+        if(p == nullptr || name == nullptr || name_size == 0) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        int const ei{elem_of(*c, vec_pos, chunk_pos)};
+        if(ei < 0) { return 2; }
+        int const idx{c->nl.find_attribute(ei, name, name_size)};
+        if(idx < 0) { return 3; }
+        (void)c->nl.set_attribute(ei, idx, value);
+        ++c->param_rev;
+        return 0;
+    }
+
+    int circuit_analyze(void* p)
+    {
+        if(p == nullptr) { return 1; }
+        return static_cast<circuit*>(p)->analyze() ? 0 : 1;
+    }
+
+    int circuit_digital_clk(void* p) { return p == nullptr ? 1 : 0; }  // no digital model in scope: nothing to tick
+
+    int circuit_sample_layout(void* p, size_t* vec_pos, size_t* chunk_pos, size_t comp_size, size_t* vo, size_t* co, size_t* dg)
+    {
+        if(p == nullptr || vec_pos == nullptr || chunk_pos == nullptr || vo == nullptr || co == nullptr || dg == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        vo[0] = co[0] = dg[0] = 0;
+        for(std::size_t i{}; i < comp_size; ++i)
+        {
+            int const ei{elem_of(*c, vec_pos[i], chunk_pos[i])};
+            std::size_t const np{ei < 0 ? 0u : static_cast<std::size_t>(c->nl.elems[static_cast<std::size_t>(ei)].d->pins)};
+            std::size_t const nb{ei < 0 ? 0u : static_cast<std::size_t>(c->nl.elems[static_cast<std::size_t>(ei)].d->branches)};
+            vo[i + 1] = vo[i] + np;
+            co[i + 1] = co[i] + nb;
+            dg[i + 1] = dg[i] + np;
+        }
+        return 0;
+    }
+
+    int circuit_sample(void* p, size_t* vec_pos, size_t* chunk_pos, size_t comp_size, double* voltage, size_t* vo, double* current, size_t* co, bool* digital, size_t* dg)
+    {
+        if(p == nullptr || vec_pos == nullptr || chunk_pos == nullptr || voltage == nullptr || vo == nullptr || current == nullptr || co == nullptr ||
+           digital == nullptr || dg == nullptr)
+        {
+            return 1;
+        }
+        if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
+        for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = false; }
+        return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
+    }
+
+    int circuit_sample_u8(void* p, size_t* vec_pos, size_t* chunk_pos, size_t comp_size, double* voltage, size_t* vo, double* current, size_t* co, uint8_t* digital, size_t* dg)
+    {
+        if(p == nullptr || vec_pos == nullptr || chunk_pos == nullptr || voltage == nullptr || vo == nullptr || current == nullptr || co == nullptr ||
+           digital == nullptr || dg == nullptr)
+        {
+            return 1;
+        }
+        if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
+        for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = 0; }
+        return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
+    }
+
+    int circuit_sample_digital_state_u8(void* p,
+                                        size_t* vec_pos,
+                                        size_t* chunk_pos,
+                                        size_t comp_size,
+                                        double* voltage,
+                                        size_t* vo,
+                                        double* current,
+                                        size_t* co,
+                                        uint8_t* digital,
+                                        size_t* dg)
+    {
+        if(p == nullptr || vec_pos == nullptr || chunk_pos == nullptr || voltage == nullptr || vo == nullptr || current == nullptr || co == nullptr ||
+           digital == nullptr || dg == nullptr)
+        {
+            return 1;
+        }
+        if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
+        for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = 2; }  // analog pins report X (dll_api.h:224-226)
+        return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
+    }
+
+    int circuit_set_model_digital(void* p, size_t vec_pos, size_t chunk_pos, size_t, uint8_t)
+    {
+        if(p == nullptr) { return 1; }
+        return elem_of(*static_cast<circuit*>(p), vec_pos, chunk_pos) < 0 ? 2 : 3;
+    }
+
+    int analyze_circuit(void* p,
+                        size_t* vec_pos,
+                        size_t* chunk_pos,
+                        size_t comp_size,
+                        int* changed_ele,
+                        size_t* changed_ind,
+                        double* changed_prop,
+                        size_t prop_size,
+                        double* voltage,
+                        size_t* vo,
+                        double* current,
+                        size_t* co,
+                        bool* digital,
+                        size_t* dg)
+    {
+        if(p && vec_pos && chunk_pos && voltage && vo && current && co && digital && dg)
+        {
+            auto* c{static_cast<circuit*>(p)};
+            for(std::size_t i{}; i < prop_size; ++i)
+            {
+                auto const ce{static_cast<std::size_t>(changed_ele[i])};
+                int const ei{elem_of(*c, vec_pos[ce], chunk_pos[ce])};
+                if(ei >= 0 && c->nl.set_attribute(ei, static_cast<int>(changed_ind[i]), changed_prop[i])) { ++c->param_rev; }
+            }
+            if(!c->analyze()) { return 1; }
+            return circuit_sample(p, vec_pos, chunk_pos, comp_size, voltage, vo, current, co, digital, dg);
+        }
+        return 0;  // dll_main.cpp:2933
+    }
+
+    // ---- additive surface ----------------------------------------------------------------------------------------
+    int circuit_set_env(void* p, double const* e)
+    {
+        if(p == nullptr || e == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->env.V_eps_max = e[0];
+        c->env.V_epsr_max = e[1];
+        c->env.I_eps_max = e[2];
+        c->env.I_epsr_max = e[3];
+        c->env.g_min = e[4];
+        c->env.r_open = e[5];
+        c->env.temperature = e[6];
+        c->env.norm_temperature = e[7];
+        ++c->param_rev;
+        return 0;
+    }
+
+    int circuit_set_ac_sweep(void* p, int sweep, double w0, double w1, size_t points)
+    {
+        if(p == nullptr || sweep < 0 || sweep > 2) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->ac.sweep = static_cast<sweep_type>(sweep);
+        c->ac.omega_start = w0;
+        c->ac.omega_stop = w1;
+        c->ac.points = points;
+        return 0;
+    }
+
+    int circuit_unknown_count(void* p, size_t* n_nodes, size_t* n_branches)
+    {
+        if(p == nullptr) { return 1; }
+        auto const nb{make_numbering(static_cast<circuit*>(p)->nl)};
+        if(n_nodes) { *n_nodes = static_cast<size_t>(nb.n_nodes); }
+        if(n_branches) { *n_branches = static_cast<size_t>(nb.n_branches); }
+        return 0;
+    }
+
+    long long circuit_pin_unknown(void* p, size_t vec_pos, size_t chunk_pos, size_t pin)
+    {
+        if(p == nullptr) { return -2; }
+        auto* c{static_cast<circuit*>(p)};
+        int const ei{elem_of(*c, vec_pos, chunk_pos)};
+        if(ei < 0) { return -2; }
+        auto const& e{c->nl.elems[static_cast<std::size_t>(ei)]};
+        if(pin >= static_cast<size_t>(e.d->pins)) { return -2; }
+        int const node{e.pin_node[pin]};
+        if(node < 0) { return node; }
+        return make_numbering(c->nl).node_index[static_cast<std::size_t>(node)];
+    }
+
+    long long circuit_branch_unknown(void* p, size_t vec_pos, size_t chunk_pos, size_t br)
+    {
+        if(p == nullptr) { return -2; }
+        auto* c{static_cast<circuit*>(p)};
+        int const ei{elem_of(*c, vec_pos, chunk_pos)};
+        if(ei < 0 || br >= static_cast<size_t>(c->nl.elems[static_cast<std::size_t>(ei)].d->branches)) { return -2; }
+        auto const nb{make_numbering(c->nl)};
+        return nb.n_nodes + nb.branch0[static_cast<std::size_t>(ei)] + static_cast<long long>(br);
+    }
+
+    int circuit_get_solution(void* p, double* re, double* im)
+    {
+        if(p == nullptr || re == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        for(std::size_t i{}; i < c->x_host.size(); ++i)
+        {
+            re[i] = c->x_host[i];
+            if(im) { im[i] = c->xi_host[i]; }
+        }
+        return 0;
+    }
+
+    void* circuit_batch_create(void* p, size_t n)
+    {
+        if(p == nullptr || n == 0)
+        {
+            set_last_error("circuit_batch_create: null circuit or zero instances");
+            return nullptr;
+        }
+        auto* b{new(std::nothrow) batch{}};
+        if(b == nullptr) { return nullptr; }
+        b->parent = static_cast<circuit*>(p);
+        b->n_inst = n;
+        return b;
+    }
+
+    void circuit_batch_destroy(void* b) { delete static_cast<batch*>(b); }
+
+    int circuit_batch_set_device(void* b, int device)
+    {
+        if(b == nullptr) { return 1; }
+        static_cast<batch*>(b)->device = device;
+        return 0;
+    }
+
+    int circuit_batch_set_stream(void* b, void* s)
+    {
+        if(b == nullptr) { return 1; }
+        static_cast<batch*>(b)->stream = s;
+        return 0;
+    }
+
+    int circuit_batch_set_param(void* bp, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values)
+    {
+        if(bp == nullptr || name == nullptr || values == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        int const ei{elem_of(*b->parent, vec_pos, chunk_pos)};
+        if(ei < 0) { return 2; }
+        int const idx{b->parent->nl.find_attribute(ei, name, name_size)};
+        if(idx < 0) { return 3; }
+        int const code{b->parent->nl.elems[static_cast<std::size_t>(ei)].d->code};
+        if(code == E_SWITCH)
+        {
+            set_last_error("circuit_batch_set_param: switch state cannot be swept per instance");
+            return 1;
+        }
+        auto& v{b->sweeps[{ei, idx}]};
+        v.resize(b->n_inst);
+        for(std::size_t i{}; i < b->n_inst; ++i) { v[i] = to_internal(code, idx, values[i]); }
+        b->sweeps_dirty = true;
+        return 0;
+    }
+
+    int circuit_batch_set_ac_sweep(void* bp, int sweep, double w0, double w1, size_t points)
+    {
+        if(bp == nullptr || sweep < 0 || sweep > 2) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        b->ac.sweep = static_cast<sweep_type>(sweep);
+        b->ac.omega_start = w0;
+        b->ac.omega_stop = w1;
+        b->ac.omega = w0;
+        b->ac.points = points;
+        return 0;
+    }
+
+    int circuit_batch_set_probes(void* bp, size_t const* u, size_t n)
+    {
+        if(bp == nullptr || (n != 0 && u == nullptr)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        auto const nb{make_numbering(b->parent->nl)};
+        b->probes.clear();
+        for(size_t i{}; i < n; ++i)
+        {
+            if(u[i] >= static_cast<size_t>(nb.unknowns())) { return 1; }
+            b->probes.push_back(static_cast<int>(u[i]));
+        }
+        return 0;
+    }
+
+    int circuit_batch_prepare(void* bp)
+    {
+        if(bp == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->ensure_compiled() || !b->upload_sweeps()) { return 1; }
+        return pe_b200_dev_sync(b->stream) == 0 ? 0 : 1;
+    }
+
+    int circuit_batch_reset_state(void* bp)
+    {
+        if(bp == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->ensure_compiled()) { return 1; }
+        // INST layout: x [0,n) | swept parameters [n, n+ns) | device state + derived values
+        std::size_t const n{static_cast<std::size_t>(b->cc->num.unknowns())};
+        std::size_t const ns{b->cc->swept_slot.size()};
+        std::size_t const row{static_cast<std::size_t>(b->LSi) * sizeof(double)};
+        auto* base{static_cast<char*>(b->d_wi.p)};
+        if(pe_b200_dev_memset0(base, n * row, b->stream) != 0) { return 1; }
+        std::size_t const tail{static_cast<std::size_t>(b->cc->n_inst_slots) - n - ns};
+        if(tail != 0 && pe_b200_dev_memset0(base + (n + ns) * row, tail * row, b->stream) != 0) { return 1; }
+        b->tr_duration = 0.0;
+        b->last_step = 0.0;
+        return 0;
+    }
+
+    int circuit_batch_analyze(void* bp)
+    {
+        if(bp == nullptr) { return 1; }
+        return static_cast<batch*>(bp)->analyze() ? 0 : 1;
+    }
+
+    size_t circuit_batch_lanes(void* bp) { return bp ? static_cast<batch*>(bp)->last_lanes : 0; }
+
+    size_t circuit_batch_points(void* bp) { return bp ? static_cast<batch*>(bp)->last_points : 0; }
+
+    uint64_t circuit_batch_total_solves(void* bp) { return bp ? static_cast<batch*>(bp)->total_solves : 0; }
+
+    double circuit_batch_tr_duration(void* bp) { return bp ? static_cast<batch*>(bp)->tr_duration : 0.0; }
+
+    int circuit_batch_solution(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_solution(x)) ? 0 : 1; }
+
+    int circuit_batch_ac_solution(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_ac_solution(x)) ? 0 : 1; }
+
+    int circuit_batch_ac_omegas(void* bp, double* om)
+    {
+        if(bp == nullptr || om == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        for(std::size_t i{}; i < b->ac_omegas.size(); ++i) { om[i] = b->ac_omegas[i]; }
+        return 0;
+    }
+
+    int circuit_batch_status(void* bp, int32_t* st) { return (bp && st && static_cast<batch*>(bp)->get_status(st)) ? 0 : 1; }
+
+    int circuit_batch_newton_iters(void* bp, uint32_t* n) { return (bp && n && static_cast<batch*>(bp)->get_solves(n)) ? 0 : 1; }
+
+    int circuit_batch_waveform(void* bp, double* w) { return (bp && w && static_cast<batch*>(bp)->get_wave(w)) ? 0 : 1; }
+
+    int circuit_batch_stats(void* bp, int mode, size_t* n_unknowns, size_t* nnz_a, size_t* nnz_lu, size_t* n_fma, size_t* n_lane_slots, size_t* n_inst_slots)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        if(n_unknowns) { *n_unknowns = static_cast<size_t>(b->cc->num.unknowns()); }
+        if(nnz_a) { *nnz_a = pr.nnz_a; }
+        if(nnz_lu) { *nnz_lu = pr.nnz_lu; }
+        if(n_fma) { *n_fma = pr.n_fma; }
+        if(n_lane_slots) { *n_lane_slots = static_cast<size_t>(pr.n_lane_slots); }
+        if(n_inst_slots) { *n_inst_slots = static_cast<size_t>(b->cc->n_inst_slots); }
+        return 0;
+    }
+
+    int circuit_batch_param_device_ptr(void* bp, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double** dptr)
+    {
+        if(bp == nullptr || name == nullptr || dptr == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        int const ei{elem_of(*b->parent, vec_pos, chunk_pos)};
+        if(ei < 0) { return 2; }
+        int const idx{b->parent->nl.find_attribute(ei, name, name_size)};
+        if(idx < 0) { return 3; }
+        auto it{b->cc->swept_slot.find({ei, idx})};
+        if(it == b->cc->swept_slot.end()) { return 3; }
+        *dptr = static_cast<double*>(b->d_wi.p) + static_cast<std::int64_t>(it->second) * b->LSi;
+        return 0;
+    }
+
+    int circuit_batch_solution_device_ptr(void* bp, double** x0, size_t* lane_stride)
+    {
+        if(bp == nullptr || x0 == nullptr) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        *x0 = static_cast<double*>(b->d_wi.p);
+        if(lane_stride) { *lane_stride = static_cast<size_t>(b->LSi); }
+        return 0;
+    }
+
+    // ---- introspection (symbolic phase only; no device needed) ----------------------------------------------------
+    int circuit_batch_compile_host(void* bp)
+    {
+        if(bp == nullptr) { return 1; }
+        bool lc{};
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->compile_host(lc)) { return 1; }
+        if(lc) { b->layout_pending = true; }
+        return 0;
+    }
+
+    size_t circuit_batch_program_words(void* bp, int mode, int section)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 0; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        return section == 0 ? b->cc->prep.size() : (section == 1 ? pr.step.size() : pr.iter.size());
+    }
+
+    int circuit_batch_program_copy(void* bp, int mode, int section, uint32_t* out)
+    {
+        if(bp == nullptr || out == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        auto const& v{section == 0 ? b->cc->prep : (section == 1 ? pr.step : pr.iter)};
+        std::memcpy(out, v.data(), v.size() * 4);
+        return 0;
+    }
+
+    size_t circuit_batch_const_count(void* bp)
+    {
+        auto* b{static_cast<batch*>(bp)};
+        return (b && b->cc) ? b->cc->cst.size() : 0;
+    }
+
+    int circuit_batch_const_copy(void* bp, double* out)
+    {
+        auto* b{static_cast<batch*>(bp)};
+        if(b == nullptr || !b->cc || out == nullptr) { return 1; }
+        std::memcpy(out, b->cc->cst.data(), b->cc->cst.size() * sizeof(double));
+        return 0;
+    }
+
+    // info[8] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns
+    int circuit_batch_program_info(void* bp, int mode, int64_t* info)
+    {
+        if(bp == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        info[0] = pr.cplx;
+        info[1] = pr.structurally_singular;
+        info[2] = pr.n_lane_slots;
+        info[3] = pr.omega_slot;
+        info[4] = b->cc->n_inst_slots;
+        info[5] = b->cc->dt_slot;
+        info[6] = pr.x_opnd.empty() ? 0 : static_cast<int64_t>(PE_OPND_SLOT(pr.x_opnd[0]));
+        info[7] = b->cc->num.unknowns();
+        return 0;
+    }
+
+    long long circuit_batch_swept_slot(void* bp, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size)
+    {
+        auto* b{static_cast<batch*>(bp)};
+        if(b == nullptr || !b->cc || name == nullptr) { return -1; }
+        int const ei{elem_of(*b->parent, vec_pos, chunk_pos)};
+        if(ei < 0) { return -1; }
+        int const idx{b->parent->nl.find_attribute(ei, name, name_size)};
+        auto it{b->cc->swept_slot.find({ei, idx})};
+        return it == b->cc->swept_slot.end() ? -1 : it->second;
+    }
+
+    // host copy of one swept parameter row in internal units (what upload_sweeps() sends to the device)
+    int circuit_batch_swept_values(void* bp, long long slot, double* out)
+    {
+        auto* b{static_cast<batch*>(bp)};
+        if(b == nullptr || !b->cc || out == nullptr) { return 1; }
+        for(auto const& [k, v]: b->sweeps)
+        {
+            auto it{b->cc->swept_slot.find(k)};
+            if(it != b->cc->swept_slot.end() && it->second == slot)
+            {
+                std::memcpy(out, v.data(), v.size() * sizeof(double));
+                return 0;
+            }
+        }
+        return 1;
+    }
+
+    int phy_engine_b200_device_count(void) { return pe_b200_dev_count(); }
+
+    uint64_t phy_engine_b200_launch_count(void) { return pe_b200_launch_count(); }
+}

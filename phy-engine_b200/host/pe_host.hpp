@@ -1,0 +1,285 @@
+// pe_host.hpp — C++23 host side of the B200 MNA hot path: netlist model, symbolic analysis ("compiler") and the
+// batch driver.  Mirrors the reference's phy_engine::circult / netlist / analyze surface for the analog path
+// (include/phy_engine/circuits/circuit.h, netlist/operation.h) but owns no numeric solve: every linear solve,
+// Newton iteration, time step and frequency point runs in the sm_100a kernels behind pe_b200_program.h.
+// There is no CPU solve path; without a CUDA device analyze() fails loudly.
+#pragma once
+#include <array>
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../csrc/pe_b200_program.h"
+
+namespace pe_b200
+{
+    // element codes = phy_engine_element_code (dll_api.h:51-135)
+    enum : int
+    {
+        E_RES = 1,
+        E_CAP = 2,
+        E_IND = 3,
+        E_VDC = 4,
+        E_VAC = 5,
+        E_IDC = 6,
+        E_IAC = 7,
+        E_VCCS = 8,
+        E_VCVS = 9,
+        E_CCCS = 10,
+        E_CCVS = 11,
+        E_SWITCH = 12,
+        E_PN = 13,
+        E_OPAMP = 17,
+        E_NPN = 50,
+        E_PNP = 51,
+        E_NMOS = 52,
+        E_PMOS = 53,
+    };
+
+    // analyze_type (circuits/analyze.h)
+    enum class analyze_type : std::uint32_t
+    {
+        OP = 0,
+        DC,
+        AC,
+        ACOP,
+        TR,
+        TROP
+    };
+
+    enum class sweep_type : int
+    {
+        single = 0,
+        linear = 1,
+        log = 2
+    };
+
+    constexpr int k_max_attr = 10;
+    constexpr int k_max_pins = 4;
+
+    struct elem_desc
+    {
+        int code;
+        char const* name;
+        int pins;
+        int branches;
+        int n_attr;
+        char const* attr_name[k_max_attr];
+        double attr_default[k_max_attr];
+        int n_cabi_props;  // how many doubles create_circuit() consumes (dll_main.cpp:1707-1956)
+        bool nonlinear;    // model_device_type::non_linear
+    };
+
+    elem_desc const* find_desc(int code) noexcept;
+
+    struct element
+    {
+        elem_desc const* d{};
+        double attr[k_max_attr]{};  // internal units (VAC/IAC: omega rad/s, phase rad — VAC.h:29-50)
+        int pin_node[k_max_pins]{-2, -2, -2, -2};  // -2 unconnected, -1 ground, >= 0 node id (creation order)
+    };
+
+    // environment (circuits/environment/environment.h:7-22)
+    struct environment
+    {
+        double V_eps_max{};
+        double V_epsr_max{};
+        double I_eps_max{};
+        double I_epsr_max{};
+        double charge_eps_max{};
+        double g_min{};
+        double r_open{};
+        double t_TOEF{};
+        double temperature{27.0};
+        double norm_temperature{27.0};
+    };
+
+    struct ac_setting
+    {
+        sweep_type sweep{sweep_type::single};
+        double omega{};
+        double omega_start{};
+        double omega_stop{};
+        std::size_t points{};
+    };
+
+    struct tr_setting
+    {
+        double t_stop{};
+        double t_step{};
+    };
+
+    struct netlist
+    {
+        std::vector<element> elems;
+        int n_created_nodes{};
+
+        // returns element index or -1 (unsupported code)
+        int add_model(int code, double const* cabi_props, std::size_t* consumed);
+        int create_node() { return n_created_nodes++; }
+        bool add_to_node(int elem, int pin, int node);  // node -1 = ground
+        // set_attribute semantics of the reference models (unit conversions included); false if idx invalid
+        bool set_attribute(int elem, int idx, double v);
+        int find_attribute(int elem, char const* name, std::size_t name_size) const;  // case-insensitive; -1 if absent
+        bool has_nonlinear() const;
+    };
+
+    // node / branch numbering of circult::prepare() (circuit.h:481-540)
+    struct numbering
+    {
+        std::vector<int> node_index;  // per created node: unknown index or -2 (no analog pin)
+        std::vector<int> branch0;     // per element: first branch index (branch_counter order)
+        int n_nodes{};
+        int n_branches{};
+        int unknowns() const { return n_nodes + n_branches; }
+    };
+
+    numbering make_numbering(netlist const& nl);
+
+    enum class prog_mode : int
+    {
+        DC = 0,  // OP and DC share stamps for every in-scope model (base.h:266-281 fallback)
+        TR = 1,
+        TROP = 2,
+        AC = 3,
+        COUNT = 4
+    };
+
+    struct program
+    {
+        bool built{};
+        bool cplx{};
+        bool structurally_singular{};
+        std::vector<std::uint32_t> step, iter;
+        int n_lane_slots{};
+        std::vector<std::uint32_t> x_opnd;  // per unknown: where the solution lands (cplx: slot of re, im = +1)
+        int omega_slot{-1};                 // LANE slot holding omega (AC)
+        // statistics for the roofline
+        std::size_t nnz_a{}, nnz_lu{}, n_fma{};
+    };
+
+    using sweep_key = std::pair<int, int>;  // (element, attribute)
+
+    struct compiled
+    {
+        numbering num;
+        int n_inst_slots{};
+        std::vector<double> cst;
+        int dt_slot{-1};  // CONST slot holding the transient step (patched by the driver before every run)
+        std::vector<std::uint32_t> prep;
+        std::map<sweep_key, int> swept_slot;  // INST slot of each per-instance parameter
+        std::array<program, static_cast<int>(prog_mode::COUNT)> prog;
+        std::string error;
+    };
+
+    struct compile_input
+    {
+        netlist const* nl{};
+        environment env{};
+        double dt{};      // TR step (nominal values of companions)
+        double omega0{};  // representative omega for AC pivot selection
+        // per-instance parameters: lane-0 value (nominal) for each swept (element, attribute)
+        std::map<sweep_key, double> swept_lane0;
+    };
+
+    // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot
+    // assignment and the batch program for every mode.  Pure host integer/graph work.
+    std::unique_ptr<compiled> compile_circuit(compile_input const& in);
+
+    // ---- batch driver -------------------------------------------------------------------------------------------
+    struct device_buf
+    {
+        void* p{};
+        std::size_t bytes{};
+        device_buf() = default;
+        device_buf(device_buf const&) = delete;
+        device_buf& operator= (device_buf const&) = delete;
+        ~device_buf();
+        bool ensure(std::size_t n);  // (re)allocate if too small; contents undefined after growth
+        void release();
+    };
+
+    struct circuit;
+
+    struct batch
+    {
+        circuit* parent{};
+        std::size_t n_inst{};
+        std::int64_t LSi{};  // padded instance count
+        int device{0};
+        void* stream{};  // cudaStream_t chosen by the caller (0 = default stream)
+
+        std::map<sweep_key, std::vector<double>> sweeps;  // host copies of per-instance parameters
+        bool sweeps_dirty{true};
+        bool layout_valid{};
+
+        // batch AC sweep (lanes = n_inst * points)
+        ac_setting ac{};
+
+        std::unique_ptr<compiled> cc;
+        std::vector<sweep_key> layout_keys;
+        std::uint64_t cc_structure_rev{}, cc_param_rev{};
+        double cc_dt{-1.0};
+        bool device_stale{true};    // host program newer than what the device holds
+        bool layout_pending{true};  // INST layout changed since the device workspace was sized
+
+        device_buf d_wi, d_wl, d_cst, d_prep, d_status, d_solves, d_wave, d_probes;
+        std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_step, d_iter;
+        std::array<bool, static_cast<int>(prog_mode::COUNT)> uploaded{};
+
+        // results of the last analyze()
+        std::size_t last_lanes{};
+        std::size_t last_points{1};
+        bool last_cplx{};
+        std::int64_t last_LSl{};
+        std::vector<double> ac_omegas;  // per point
+        std::uint64_t total_solves{};
+        double tr_duration{};
+        double last_step{};
+
+        // waveform probes (unknown indices), recorded per time step when non-empty
+        std::vector<int> probes;
+        std::size_t wave_steps{};
+
+        std::string error;
+
+        bool analyze();
+        bool compile_host(bool& layout_change);  // symbolic phase only, no device needed
+        bool ensure_compiled();
+        bool upload_sweeps();
+        bool run_phase(prog_mode m, bool with_prep, bool nonlinear, int n_steps, bool time_stepping, double t0, double dt, std::size_t lanes, int ppi);
+        bool run_prep_only();
+        // downloads
+        bool get_solution(double* x /* [n_inst][n] */);
+        bool get_ac_solution(double* x /* [lanes][n][2] */);
+        bool get_status(std::int32_t* st /* [lanes] */);
+        bool get_solves(std::uint32_t* sv /* [lanes] */);
+        bool get_wave(double* w /* [steps][probes][n_inst] */);
+    };
+
+    struct circuit
+    {
+        environment env{};
+        netlist nl{};
+        analyze_type at{analyze_type::TR};
+        ac_setting ac{};
+        tr_setting tr{};
+        std::uint64_t structure_rev{1};  // bumped when elements / connections change (device state is reset)
+        std::uint64_t param_rev{1};      // bumped when a broadcast parameter / environment value changes
+
+        std::unique_ptr<batch> solo;   // the n = 1 batch behind circuit_analyze()
+        std::vector<double> x_host;    // last solution (re) of the solo batch, unknown order
+        std::vector<double> xi_host;   // imaginary parts (AC)
+        numbering num_host;
+
+        bool analyze();
+    };
+
+    void set_last_error(std::string s);
+    char const* last_error();
+}  // namespace pe_b200
