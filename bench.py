@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — circuit-solves/s of the batched MNA hot path on N B200s (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): RC ladder, 1000 sections (1002 unknowns, nnz(A) = 3003),
+transient, t_step 1e-8 / t_stop 1e-6 (100 time steps), 10 000 instances per GPU with element-wise per-instance R_i, C_i
+draws (a batched parameter sweep).  One "step" = one analyze() of that batch = 1e6 solve_once-equivalents
+(stamp + numeric LU refactor + forward/back substitution) per GPU.  Instances shard across ranks with no data-path
+collective (weak scaling: 10 000 instances per GPU).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this framework (CUDA kernels through the C ABI)
+  python bench.py --impl reference ...                     # the reference's own CPU solver (oracle/_ref), host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "phy-engine_b200"))
+
+METRIC = "circuit-solves/sec"
+UNIT = "solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sections", type=int, default=1000)
+    ap.add_argument("--instances", type=int, default=10000, help="instances per GPU")
+    ap.add_argument("--time-steps", type=int, default=100)
+    ap.add_argument("--subtree-warps", type=int, default=0, help="0 = library default")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, seed):
+    import workloads as wl
+
+    nl, info = wl.rc_ladder(args.sections)
+    rng = np.random.default_rng(seed)
+    items = [(e, "r") for e in info["R"]] + [(e, "c") for e in info["C"]]
+    nominal = np.array([1e3] * len(info["R"]) + [1e-9] * len(info["C"]))
+    return nl, info, items, nominal, rng
+
+
+def config_of(args):
+    return {
+        "workload": f"RC ladder {args.sections} sections ({args.sections + 2} unknowns) transient, {args.time_steps} time steps, "
+                    f"{args.instances} instances/GPU batched R_i,C_i parameter sweep (BASELINE.json configs[1])",
+        "instances_per_gpu": args.instances,
+        "time_steps": args.time_steps,
+        "t_step": 1e-8,
+        "l2_policy": "working set (~0.6 GB per GPU) is larger than the 126 MB L2; no explicit flush",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(args, n_inst, seed=1234, threads=None):
+    """The reference's own CPU implementation (Eigen SparseLU behind circult::analyze) on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refapi
+    import pe_b200 as pe
+
+    fast = os.path.exists(refapi.REF_LIB_FAST)
+    nl, info, items, nominal, rng = workload(args, seed)
+    vals = nominal[:, None] * rng.uniform(0.8, 1.2, size=(len(items), n_inst))
+    over = [(e, name, vals[k]) for k, (e, name) in enumerate(items)]
+    threads = threads or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    r = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-8, t_stop=1e-8 * (args.time_steps - 0.5), threads=threads, n_unknowns=args.sections + 2, fast=fast)
+    wall = time.perf_counter() - t0
+    solves = int(r["solves"].sum())
+    return {"solves": solves, "wall_s": wall, "analyze_s": r["seconds"], "threads": threads, "ok": bool((r["ok"] == 1).all()),
+            "build": "oracle/_ref/libpe_ref_fast.so (-O3 -march=x86-64-v3)" if fast else "oracle/_ref/libpe_ref.so (-O2)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_inst = args.cpu_sample or max(cores, 2 * cores)
+    for _ in range(args.warmup):
+        cpu_reference_run(args, max(1, cores // 2))
+    t_total, solves = 0.0, 0
+    for _ in range(args.steps):
+        r = cpu_reference_run(args, n_inst)
+        t_total += r["wall_s"]
+        solves += r["solves"]
+    v = solves / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                         "sample": f"{n_inst} instances x {args.time_steps} time steps per step, {r['build']}, one circult per instance, {r['threads']} worker threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import pe_b200 as pe
+
+    if not torch.cuda.is_available() or pe.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    nl, info, items, nominal, rng = workload(args, 1000 + rank)
+    n_inst = args.instances
+    P = len(items)
+    host_vals = torch.empty((P, n_inst), dtype=torch.float64).pin_memory()
+    host_vals.numpy()[:] = nominal[:, None] * rng.uniform(0.8, 1.2, size=(P, n_inst))
+    n_unk = args.sections + 2
+    host_x = torch.empty((n_unk, n_inst), dtype=torch.float64).pin_memory()
+
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.TR)
+    c.set_tr(1e-8, 1e-8 * (args.time_steps - 0.5))
+    b = c.batch(n_inst)
+    b.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    if args.subtree_warps:
+        b.set_subtree_warps(args.subtree_warps)
+    table = b.param_table(items)
+    b.set_params(table, host_vals.data_ptr())  # first time: host copies + layout
+    b.prepare()
+    st = b.stats(pe.MODE_TR)
+    bytes_per_solve = 8 * (st["nnz_a"] + 2 * st["nnz_lu"] + 2 * st["n_unknowns"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def step_resident():
+        b.reset_state()
+        if not b.analyze():
+            raise SystemExit("bench.py: analyze failed: " + c.abi.last_error())
+        return b.total_solves
+
+    def step_e2e():
+        b.set_params(table, host_vals.data_ptr())  # H2D of this step's inputs (pinned)
+        b.reset_state()
+        if not b.analyze():
+            raise SystemExit("bench.py: analyze failed: " + c.abi.last_error())
+        b.solution_soa_into(host_x.data_ptr())  # D2H of the step's result (final state of every instance)
+        return b.total_solves
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    pe.kernel_timing(True)
+    pe.kernel_ms()
+    l0 = pe.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solves = 0
+    for _ in range(args.steps):
+        solves += step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pe.launch_count() - l0
+    kernel_ms = pe.kernel_ms()
+    pe.kernel_timing(False)
+    clocks = sampler.stop() if sampler else None
+    ms_max = max_over_ranks(ms)
+    total_solves = sum_over_ranks(float(solves))
+    value = total_solves / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        s2 = 0
+        for _ in range(args.steps):
+            s2 += step_e2e()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        dt = max_over_ranks(t1 - t0)
+        e2e = {"value": sum_over_ranks(float(s2)) / dt, "unit": UNIT, "h2d_bytes_per_step": int(P * n_inst * 8), "d2h_bytes_per_step": int(n_unk * n_inst * 8)}
+
+    checksum = float(np.abs(host_x.numpy()).sum()) if e2e else None
+
+    # ---- roofline of the dominant kernel (the solve kernel; one launch per analyze) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    solves_per_launch = solves / max(launches, 1)
+    avg_launch_ms = kernel_ms / max(launches, 1)
+    achieved = bytes_per_solve * solves_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "pe_b200_solve_kernel", "avg_launch_ms": avg_launch_ms, "bytes_per_solve": bytes_per_solve, "solves_per_launch": solves_per_launch,
+                "peak_source": peak_src, "kernel_share_of_step": kernel_ms / ms if ms > 0 else None}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or 2 * cores
+        try:
+            r = cpu_reference_run(args, sample)
+            cpu = {"value": r["solves"] / r["wall_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                   "sample": f"{sample} instances x {args.time_steps} time steps, {r['build']}, {r['threads']} worker threads, wall {r['wall_s']:.2f} s"}
+        except Exception as ex:  # the compiled reference is test infrastructure; its absence must not break the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "program": st, "checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,9 @@ extern "C"
     int circuit_batch_set_stream(void* batch, void* cuda_stream);
     /* per-instance values of one model attribute; values[n_instances] in the attribute's public unit */
     int circuit_batch_set_param(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values);
+    /* many parameters in one call: values[n_params][n_instances].  Once the batch is prepared and every parameter
+     * already has a device row, rows are copied host->device straight from `values` (pinned memory recommended). */
+    int circuit_batch_set_params(void* batch, size_t n_params, size_t const* vec_pos, size_t const* chunk_pos, char const* const* names, double const* values);
     int circuit_batch_set_ac_sweep(void* batch, int sweep_type, double omega_start, double omega_stop, size_t points);
     /* record these unknowns after every transient step (waveform store [steps][n_probes][n_instances]) */
     int circuit_batch_set_probes(void* batch, size_t const* unknowns, size_t n_probes);
@@ -165,6 +168,7 @@ extern "C"
     uint64_t circuit_batch_total_solves(void* batch); /* sum of solve_once-equivalents in the last analyze */
     double circuit_batch_tr_duration(void* batch);
     int circuit_batch_solution(void* batch, double* x);        /* [n_instances][n] real state */
+    int circuit_batch_solution_soa(void* batch, double* x);    /* [n][n_instances]: the device-native layout, no transpose */
     int circuit_batch_ac_solution(void* batch, double* x);     /* [lanes][n][2] */
     int circuit_batch_ac_omegas(void* batch, double* omegas);  /* [points] */
     int circuit_batch_status(void* batch, int32_t* status);    /* [lanes] 0 ok, 1 no convergence, 2 singular */
@@ -190,6 +194,10 @@ extern "C"
 
     int phy_engine_b200_device_count(void);
     uint64_t phy_engine_b200_launch_count(void);
+    /* device-side timing of the solve kernels (CUDA events on the launching stream): enable, then read-and-reset the
+     * accumulated milliseconds (waits for the launches to finish) */
+    void phy_engine_b200_timing(int on);
+    double phy_engine_b200_kernel_ms(void);
 
 #ifdef __cplusplus
 }

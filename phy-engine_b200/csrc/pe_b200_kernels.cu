@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <utility>
+#include <vector>
 
 #include "pe_b200_program.h"
 #include "pe_b200_models.h"
@@ -430,6 +432,10 @@ namespace
     thread_local char g_err[256] = "";
     std::atomic<uint64_t> g_launches{0};
 
+    // optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the roofline line
+    bool g_timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+
     int chk(cudaError_t e, char const* what)
     {
         if(e == cudaSuccess) { return 0; }
@@ -487,13 +493,43 @@ extern "C"
         // small batches: narrower blocks so that the grid still covers all 148 SMs
         int const block = (run->n_lanes <= 148 * 64) ? 32 : ((run->n_lanes <= 148 * 512) ? 64 : 128);
         int const grid = (run->n_lanes + block - 1) / block;
+        cudaEvent_t e0{}, e1{};
+        if(g_timing)
+        {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, (cudaStream_t)stream);
+        }
         if(run->cplx) { pe_b200_run_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*run); }
         else
         {
             pe_b200_run_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*run);
         }
+        if(g_timing)
+        {
+            cudaEventRecord(e1, (cudaStream_t)stream);
+            g_events.emplace_back(e0, e1);
+        }
         g_launches.fetch_add(1);
         return chk(cudaGetLastError(), "pe_b200_run_kernel launch");
+    }
+
+    void pe_b200_timing_enable(int on) { g_timing = on != 0; }
+
+    // total device time (ms) of the solve-kernel launches since the last collect; waits for them to finish
+    double pe_b200_timing_collect(void)
+    {
+        double total = 0.0;
+        for(auto& [a, b]: g_events)
+        {
+            float ms = 0.f;
+            cudaEventSynchronize(b);
+            if(cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { total += ms; }
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+        g_events.clear();
+        return total;
     }
 
     char const* pe_b200_dev_last_error(void) { return g_err; }

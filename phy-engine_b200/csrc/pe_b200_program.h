@@ -136,6 +136,8 @@ extern "C"
     char const* pe_b200_dev_last_error(void);
     // number of kernels this library has launched so far in this process (bench.py's gpu_launches evidence)
     uint64_t pe_b200_launch_count(void);
+    void pe_b200_timing_enable(int on);
+    double pe_b200_timing_collect(void);
 
 #ifdef __cplusplus
 }

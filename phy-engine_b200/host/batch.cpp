@@ -129,7 +129,13 @@ namespace pe_b200
             auto it{cc->swept_slot.find(k)};
             if(it == cc->swept_slot.end()) { continue; }
             auto* dst{static_cast<double*>(d_wi.p) + static_cast<std::int64_t>(it->second) * LSi};
-            if(pe_b200_dev_h2d(dst, v.data(), std::min(v.size(), n_inst) * sizeof(double), stream) != 0) { return dev_fail(error, "upload sweep"); }
+            if(v.size() < n_inst)
+            {
+                error = "a swept parameter was set through the device-direct path and the workspace was re-laid out: set it again";
+                set_last_error(error);
+                return false;
+            }
+            if(pe_b200_dev_h2d(dst, v.data(), n_inst * sizeof(double), stream) != 0) { return dev_fail(error, "upload sweep"); }
         }
         sweeps_dirty = false;
         return true;
@@ -430,6 +436,20 @@ namespace pe_b200
         for(std::size_t j{}; j < n; ++j)
         {
             for(std::size_t i{}; i < n_inst; ++i) { x[i * n + j] = tmp[j * n_inst + i]; }
+        }
+        return true;
+    }
+
+    bool batch::get_solution_soa(double* x)
+    {
+        if(!cc) { return false; }
+        std::size_t const n{static_cast<std::size_t>(cc->num.unknowns())};
+        if(n == 0) { return true; }
+        // device-native layout: unknown-major rows of n_inst doubles, no host transpose
+        if(pe_b200_dev_d2h_2d(x, n_inst * sizeof(double), d_wi.p, static_cast<std::size_t>(LSi) * sizeof(double), n_inst * sizeof(double), n, stream) != 0 ||
+           pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download solution");
         }
         return true;
     }

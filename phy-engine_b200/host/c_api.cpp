@@ -512,6 +512,50 @@ extern "C"
         return 0;
     }
 
+    int circuit_batch_set_params(void* bp, size_t n_params, size_t const* vec_pos, size_t const* chunk_pos, char const* const* names, double const* values)
+    {
+        if(bp == nullptr || (n_params != 0 && (vec_pos == nullptr || chunk_pos == nullptr || names == nullptr || values == nullptr))) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        bool direct{b->cc && !b->device_stale && !b->layout_pending && b->d_wi.p != nullptr};
+        for(size_t k{}; k < n_params && direct; ++k)
+        {
+            // fast path only when every parameter already has a device row and needs no unit conversion
+            int const ei{elem_of(*b->parent, vec_pos[k], chunk_pos[k])};
+            if(ei < 0 || names[k] == nullptr) { return 2; }
+            int const idx{b->parent->nl.find_attribute(ei, names[k], std::strlen(names[k]))};
+            if(idx < 0) { return 3; }
+            int const code{b->parent->nl.elems[static_cast<std::size_t>(ei)].d->code};
+            if(code == E_VAC || code == E_IAC || code == E_SWITCH || (code == E_PN && idx == 7)) { direct = false; }
+            else if(b->cc->swept_slot.find({ei, idx}) == b->cc->swept_slot.end()) { direct = false; }
+        }
+        if(!direct)
+        {
+            for(size_t k{}; k < n_params; ++k)
+            {
+                int const rc{circuit_batch_set_param(bp, vec_pos[k], chunk_pos[k], names[k], names[k] ? std::strlen(names[k]) : 0, values + k * b->n_inst)};
+                if(rc != 0) { return rc; }
+            }
+            return 0;
+        }
+        if(pe_b200_dev_set(b->device) != 0) { return 1; }
+        for(size_t k{}; k < n_params; ++k)
+        {
+            int const ei{elem_of(*b->parent, vec_pos[k], chunk_pos[k])};
+            int const idx{b->parent->nl.find_attribute(ei, names[k], std::strlen(names[k]))};
+            double const* src{values + k * b->n_inst};
+            auto& v{b->sweeps[{ei, idx}]};
+            v.assign(1, src[0]);  // nominal (lane-0) value for the symbolic phase; the full row lives on the device only
+            auto* dst{static_cast<double*>(b->d_wi.p) + static_cast<std::int64_t>(b->cc->swept_slot.at({ei, idx})) * b->LSi};
+            if(pe_b200_dev_h2d(dst, src, b->n_inst * sizeof(double), b->stream) != 0)
+            {
+                set_last_error(std::string{"circuit_batch_set_params: "} + pe_b200_dev_last_error());
+                return 1;
+            }
+        }
+        // the caller's buffer may be reused as soon as we return
+        return pe_b200_dev_sync(b->stream) == 0 ? 0 : 1;
+    }
+
     int circuit_batch_set_ac_sweep(void* bp, int sweep, double w0, double w1, size_t points)
     {
         if(bp == nullptr || sweep < 0 || sweep > 2) { return 1; }
@@ -579,6 +623,8 @@ extern "C"
     double circuit_batch_tr_duration(void* bp) { return bp ? static_cast<batch*>(bp)->tr_duration : 0.0; }
 
     int circuit_batch_solution(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_solution(x)) ? 0 : 1; }
+
+    int circuit_batch_solution_soa(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_solution_soa(x)) ? 0 : 1; }
 
     int circuit_batch_ac_solution(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_ac_solution(x)) ? 0 : 1; }
 
@@ -730,4 +776,8 @@ extern "C"
     int phy_engine_b200_device_count(void) { return pe_b200_dev_count(); }
 
     uint64_t phy_engine_b200_launch_count(void) { return pe_b200_launch_count(); }
+
+    void phy_engine_b200_timing(int on) { pe_b200_timing_enable(on); }
+
+    double phy_engine_b200_kernel_ms(void) { return pe_b200_timing_collect(); }
 }

@@ -1,0 +1,190 @@
+"""Synthetic netlists of the BASELINE.json configs, in create_circuit() wire format.
+
+Every generator returns (Netlist, info) where info names the elements whose parameters are swept per instance.
+The reference builds the same shapes through its C++ API in benchmark/ and test/ (cited per function); here they are
+expressed once in the C-ABI wire format so that the product and the compiled reference consume identical inputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import pe_b200 as pe
+from pe_b200 import Netlist
+
+
+def rc_ladder(n_sections: int = 1000, r: float = 1e3, c: float = 1e-9, v: float = 1.0):
+    """Config B: VDC -> n x (series R_i, shunt C_i to ground).  n nodes... n_sections+1 nodes + 1 branch unknowns.
+    Same topology as test/0005.models/rc_step_tr.cpp generalised to n sections."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, v)
+    nl.wire(src, 1, g, 0)
+    rs, cs = [], []
+    prev = (src, 0)
+    for _ in range(n_sections):
+        ri = nl.add(pe.R, r)
+        ci = nl.add(pe.C, c)
+        nl.wire(prev[0], prev[1], ri, 0)
+        nl.wire(ri, 1, ci, 0)
+        nl.wire(ci, 1, g, 0)
+        prev = (ri, 1)
+        rs.append(ri)
+        cs.append(ci)
+    return nl, {"src": src, "R": rs, "C": cs}
+
+
+def rlc_ladder(n_sections: int = 64, r: float = 10.0, l: float = 1e-6, c: float = 1e-9, vp: float = 1.0):
+    """Config D: VAC -> n x (series R, series L, shunt C).  2n+1 nodes + n+1 branches (test/0012.ac/ac_omega.cpp shape)."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, vp, 50.0, 0.0)
+    nl.wire(src, 1, g, 0)
+    rs, ls, cs = [], [], []
+    prev = (src, 0)
+    for _ in range(n_sections):
+        ri = nl.add(pe.R, r)
+        li = nl.add(pe.L, l)
+        ci = nl.add(pe.C, c)
+        nl.wire(prev[0], prev[1], ri, 0)
+        nl.wire(ri, 1, li, 0)
+        nl.wire(li, 1, ci, 0)
+        nl.wire(ci, 1, g, 0)
+        prev = (li, 1)
+        rs.append(ri)
+        ls.append(li)
+        cs.append(ci)
+    return nl, {"src": src, "R": rs, "L": ls, "C": cs}
+
+
+def diode_resistor(v: float = 1.0, r: float = 1e3, n_diodes: int = 1):
+    """Config C (c1): V - R - n series diodes to ground (test/0011.nonlinear/op_pn_junction.cpp for n = 1)."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, v)
+    rr = nl.add(pe.R, r)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, rr, 0)
+    prev = (rr, 1)
+    ds = []
+    for _ in range(n_diodes):
+        d = nl.add(pe.PN, *pe.PN_DEFAULT)
+        nl.wire(prev[0], prev[1], d, 0)
+        prev = (d, 1)
+        ds.append(d)
+    nl.wire(prev[0], prev[1], g, 0)
+    return nl, {"src": src, "R": rr, "D": ds}
+
+
+def diode_ladder(n_stages: int = 16, v: float = 5.0, r: float = 1e3):
+    """Config C (c4): V -> n x (series R_i, shunt diode_i to ground): n+1 nodes + 1 branch, n non-linear devices."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, v)
+    nl.wire(src, 1, g, 0)
+    prev = (src, 0)
+    rs, ds = [], []
+    for _ in range(n_stages):
+        ri = nl.add(pe.R, r)
+        di = nl.add(pe.PN, *pe.PN_DEFAULT)
+        nl.wire(prev[0], prev[1], ri, 0)
+        nl.wire(ri, 1, di, 0)
+        nl.wire(di, 1, g, 0)
+        prev = (ri, 1)
+        rs.append(ri)
+        ds.append(di)
+    return nl, {"src": src, "R": rs, "D": ds}
+
+
+def npn_stage(vb: float = 0.65, vcc: float = 5.0, rc: float = 1e3):
+    """Config C (c2): NPN with a voltage-driven base, RC to VCC, emitter grounded (the
+    resistor-biased stage does not converge in the reference)."""
+    nl = Netlist()
+    g = nl.ground()
+    vbs = nl.add(pe.VDC, vb)
+    vcs = nl.add(pe.VDC, vcc)
+    r = nl.add(pe.R, rc)
+    q = nl.add(pe.NPN, 1e-16, 1.0, 100.0, 27.0, 1.0)
+    nl.wire(vbs, 1, g, 0)
+    nl.wire(vcs, 1, g, 0)
+    nl.wire(vbs, 0, q, 0)
+    nl.wire(vcs, 0, r, 0)
+    nl.wire(r, 1, q, 1)
+    nl.wire(q, 2, g, 0)
+    return nl, {"Vb": vbs, "Vcc": vcs, "R": r, "Q": q}
+
+
+def npn_resistor_biased(vcc: float = 5.0, rb: float = 1e5, rc: float = 1e3):
+    """Failure-parity case: the reference's un-limited BJT diverges on this."""
+    nl = Netlist()
+    g = nl.ground()
+    vcs = nl.add(pe.VDC, vcc)
+    r_b = nl.add(pe.R, rb)
+    r_c = nl.add(pe.R, rc)
+    q = nl.add(pe.NPN, 1e-16, 1.0, 100.0, 27.0, 1.0)
+    nl.wire(vcs, 1, g, 0)
+    nl.wire(vcs, 0, r_b, 0)
+    nl.wire(vcs, 0, r_c, 0)
+    nl.wire(r_b, 1, q, 0)
+    nl.wire(r_c, 1, q, 1)
+    nl.wire(q, 2, g, 0)
+    return nl, {"Vcc": vcs, "Rb": r_b, "Rc": r_c, "Q": q}
+
+
+def cmos_stage(vdd: float = 5.0, vg: float = 2.0, rd: float = 1e3, with_pmos: bool = True):
+    """Config C (c3): NMOS common source; load = PMOS (gate grounded-ish via Vgp) in parallel with RD."""
+    nl = Netlist()
+    g = nl.ground()
+    vd = nl.add(pe.VDC, vdd)
+    vgs = nl.add(pe.VDC, vg)
+    r = nl.add(pe.R, rd)
+    mn = nl.add(pe.NMOS, 1e-3, 0.01, 1.0)
+    nl.wire(vd, 1, g, 0)
+    nl.wire(vgs, 1, g, 0)
+    nl.wire(vd, 0, r, 0)
+    nl.wire(r, 1, mn, 0)
+    nl.wire(vgs, 0, mn, 1)
+    nl.wire(mn, 2, g, 0)
+    info = {"Vdd": vd, "Vg": vgs, "R": r, "MN": mn}
+    if with_pmos:
+        vgp = nl.add(pe.VDC, vdd - 2.0)
+        mp = nl.add(pe.PMOS, 5e-4, 0.02, 1.0)
+        nl.wire(vgp, 1, g, 0)
+        nl.wire(mp, 2, vd, 0)  # source at VDD
+        nl.wire(mp, 1, vgp, 0)
+        nl.wire(mp, 0, mn, 0)  # drains tied
+        info.update({"Vgp": vgp, "MP": mp})
+    return nl, info
+
+
+def random_links(n_nodes: int = 1000, n_links: int = 10, seed: int = 1, r: float = 1e3):
+    """benchmark/0001.models/100000_random_links_cpu.cpp shape: chain of n 1 kOhm resistors from a 1 V source plus
+    random chord resistors (seeded here; the reference benchmark draws them from a non-deterministic engine)."""
+    rng = np.random.default_rng(seed)
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, 1.0)
+    nl.wire(src, 1, g, 0)
+    chain = []
+    prev = (src, 0)
+    for _ in range(n_nodes):
+        ri = nl.add(pe.R, r)
+        nl.wire(prev[0], prev[1], ri, 0)
+        prev = (ri, 1)
+        chain.append(ri)
+    load = nl.add(pe.R, r)
+    nl.wire(prev[0], prev[1], load, 0)
+    nl.wire(load, 1, g, 0)
+    links = []
+    for _ in range(n_links):
+        a, b = rng.integers(0, n_nodes, size=2)
+        if a == b:
+            continue
+        lk = nl.add(pe.R, r)
+        nl.wire(lk, 0, chain[a], 1)
+        nl.wire(lk, 1, chain[b], 1)
+        links.append(lk)
+    return nl, {"src": src, "chain": chain, "links": links, "load": load}
+
+
+def sweep_values(rng: np.random.Generator, nominal: float, n_inst: int, lo: float = 0.8, hi: float = 1.2) -> np.ndarray:
+    return nominal * rng.uniform(lo, hi, size=n_inst)

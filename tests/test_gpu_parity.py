@@ -1,0 +1,273 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the compiled reference on the same netlists.
+
+Tolerance (BASELINE.json north_star): node voltages and branch currents within 1e-9 relative / 1e-12 absolute in
+FP64, identical Newton iteration counts (solve_once-equivalents per analyze()).
+"""
+import numpy as np
+import pytest
+
+import pe_b200 as pe
+import refapi
+import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-9, 1e-12
+
+
+def assert_close(got, want, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    err = np.abs(got - want)
+    tol = ATOL + RTOL * np.maximum(np.abs(got), np.abs(want))
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError(f"{what}: {bad.sum()} of {bad.size} values differ; worst at {i}: got {got[i]!r} want {want[i]!r} (err {err[i]:.3e}, tol {tol[i]:.3e})")
+
+
+def ref_solo(nl, at, ref, **kw):
+    c = refapi.RefCircuit(nl)
+    c.set_analyze_type(at)
+    if "tr" in kw:
+        c.set_tr(*kw["tr"])
+    if "omega" in kw:
+        c.set_ac_omega(kw["omega"])
+    if "sweep" in kw:
+        c.set_ac_sweep(*kw["sweep"])
+    ok, n = c.analyze_counted()
+    return c, ok, n
+
+
+def gpu_solo(nl, at, **kw):
+    c = pe.Circuit(nl)
+    c.set_analyze_type(at)
+    if "tr" in kw:
+        c.set_tr(*kw["tr"])
+    if "omega" in kw:
+        c.set_ac_omega(kw["omega"])
+    if "sweep" in kw:
+        c.set_ac_sweep(*kw["sweep"])
+    ok = c.analyze()
+    return c, ok
+
+
+def test_rc_step_tr_matches_reference(ref):
+    # test/0005.models/rc_step_tr.cpp: 1 V, 1 kOhm, 1 nF, dt 1e-8, 100 steps; oracle vout = 0.63027499952138644
+    nl, info = wl.rc_ladder(1)
+    rc, rok, rn = ref_solo(nl, pe.TR, ref, tr=(1e-8, 1e-6))
+    gc, gok = gpu_solo(nl, pe.TR, tr=(1e-8, 1e-6))
+    assert rok and gok, gc.abi.last_error()
+    assert rn == 100
+    assert abs(rc.solution()[1].real - 0.63027499952138644) < 1e-15
+    assert_close(gc.solution(), rc.solution(), "rc step")
+    # sampled through the reference-compatible circuit_sample_u8
+    gv, gvo, gi, gco = gc.sample()
+    rv, rvo, ri, rco = rc.sample()
+    assert (gvo == rvo).all() and (gco == rco).all()
+    assert_close(gv, rv, "sample voltages")
+    assert_close(gi, ri, "sample currents")
+
+
+def test_tr_resume_continues_like_reference(ref):
+    nl, _ = wl.rc_ladder(3)
+    rc, _, _ = ref_solo(nl, pe.TR, ref, tr=(1e-8, 3e-7))
+    gc, gok = gpu_solo(nl, pe.TR, tr=(1e-8, 3e-7))
+    assert gok
+    assert_close(gc.solution(), rc.solution(), "first analyze")
+    for _ in range(2):  # analyze() again continues the transient (circuit.h:242)
+        assert rc.analyze() and gc.analyze()
+        assert_close(gc.solution(), rc.solution(), "resumed analyze")
+
+
+@pytest.mark.parametrize("n_sections,n_inst", [(8, 33), (50, 64), (200, 40)])
+def test_rc_ladder_batch_sweep(ref, n_sections, n_inst):
+    nl, info = wl.rc_ladder(n_sections)
+    rng = np.random.default_rng(7)
+    over = []
+    for e in info["R"]:
+        over.append((e, "r", wl.sweep_values(rng, 1e3, n_inst)))
+    for e in info["C"]:
+        over.append((e, "c", wl.sweep_values(rng, 1e-9, n_inst)))
+    want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-8, t_stop=2e-7)
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.TR)
+    c.set_tr(1e-8, 2e-7)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    assert (want["ok"] == 1).all()
+    assert_close(b.solution(), want["x"].real, "ladder state")
+    assert b.total_solves == int(want["solves"].sum())
+    assert (b.status() == 0).all()
+
+
+def test_diode_op_iteration_trajectory(ref):
+    # test/0011.nonlinear/op_pn_junction.cpp; SURVEY.md 8(c): 7 iterations, Vd = 0.62944165509863270
+    nl, info = wl.diode_resistor()
+    rc, rok, rn = ref_solo(nl, pe.OP, ref)
+    gc, gok = gpu_solo(nl, pe.OP)
+    assert rok and gok
+    assert rn == 7
+    assert abs(rc.solution()[1].real - 0.62944165509863270) < 1e-15
+    b = gc.batch(1)
+    assert b.analyze()
+    assert int(b.newton_iters()[0]) == 7
+    assert_close(gc.solution(), rc.solution(), "diode op")
+    assert_close(b.solution()[0], rc.solution().real, "diode op (batch of 1)")
+
+
+def test_diode_monte_carlo(ref):
+    n_inst = 257
+    nl, info = wl.diode_resistor(n_diodes=2, v=3.0)
+    rng = np.random.default_rng(11)
+    over = [(info["R"], "r", wl.sweep_values(rng, 1e3, n_inst, 0.95, 1.05))]
+    for d in info["D"]:
+        over.append((d, "Is", 1e-14 * np.exp(0.3 * rng.standard_normal(n_inst))))
+        over.append((d, "N", rng.uniform(1.0, 1.2, n_inst)))
+    want = refapi.run_batch(nl, pe.OP, n_inst, over)
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.OP)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    assert (b.newton_iters() == want["solves"]).all()
+    assert_close(b.solution(), want["x"].real, "diode MC")
+
+
+def test_diode_ladder_newton(ref):
+    n_inst = 64
+    nl, info = wl.diode_ladder(16)
+    rng = np.random.default_rng(5)
+    over = [(e, "r", wl.sweep_values(rng, 1e3, n_inst, 0.95, 1.05)) for e in info["R"]]
+    want = refapi.run_batch(nl, pe.OP, n_inst, over)
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.OP)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    assert (b.newton_iters() == want["solves"]).all()
+    assert_close(b.solution(), want["x"].real, "diode ladder")
+
+
+def test_bjt_and_mos_op(ref):
+    for nl, info, sweeps in (
+        (*wl.npn_stage(), [("Vb", "V", 0.55, 0.70), ("R", "r", 900.0, 1100.0)]),
+        (*wl.cmos_stage(), [("Vg", "V", 1.2, 3.0), ("R", "r", 900.0, 1100.0)]),
+        (*wl.cmos_stage(with_pmos=False), [("Vg", "V", 0.5, 3.0)]),
+    ):
+        n_inst = 96
+        rng = np.random.default_rng(3)
+        over = [(info[k], name, rng.uniform(lo, hi, n_inst)) for k, name, lo, hi in sweeps]
+        want = refapi.run_batch(nl, pe.OP, n_inst, over)
+        c = pe.Circuit(nl)
+        c.set_analyze_type(pe.OP)
+        b = c.batch(n_inst)
+        for e, name, v in over:
+            b.set_param(e, name, v)
+        ok = b.analyze()
+        assert ok == bool((want["ok"] == 1).all())
+        assert (b.newton_iters() == want["solves"]).all()
+        good = want["ok"] == 1
+        assert_close(b.solution()[good], want["x"].real[good], "transistor stage")
+
+
+def test_failure_parity_resistor_biased_npn(ref):
+    # the reference itself does not converge here (64 iterations, analyze() false)
+    nl, info = wl.npn_resistor_biased()
+    rc, rok, rn = ref_solo(nl, pe.OP, ref)
+    assert not rok and rn == 64
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.OP)
+    b = c.batch(3)
+    assert not b.analyze()
+    assert (b.status() != 0).all()
+    assert (b.newton_iters() == 64).all()
+
+
+def test_ac_single_point(ref):
+    # test/0012.ac/ac_omega.cpp shape: R-C low pass at the corner frequency -> (0.5, -0.5)
+    nl = pe.Netlist()
+    g = nl.ground()
+    s = nl.add(pe.VAC, 1.0, 50.0, 0.0)
+    r = nl.add(pe.R, 1e3)
+    cc = nl.add(pe.C, 1e-6)
+    nl.wire(s, 1, g, 0)
+    nl.wire(s, 0, r, 0)
+    nl.wire(r, 1, cc, 0)
+    nl.wire(cc, 1, g, 0)
+    rc, rok, _ = ref_solo(nl, pe.AC, ref, omega=1e3)
+    gc, gok = gpu_solo(nl, pe.AC, omega=1e3)
+    assert rok and gok
+    assert_close(gc.solution(), rc.solution(), "ac point")
+    assert abs(rc.solution()[1] - (0.5 - 0.5j)) < 1e-12
+
+
+@pytest.mark.parametrize("n_sections,points", [(2, 17), (8, 200), (64, 64)])
+def test_ac_log_sweep_rlc(ref, n_sections, points):
+    nl, info = wl.rlc_ladder(n_sections)
+    sweep = (pe.SWEEP_LOG, 1e3, 1e10, points)
+    rc, rok, rn = ref_solo(nl, pe.AC, ref, sweep=sweep)
+    assert rok and rn == points
+    om, xr = rc.ac_results()
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.AC)
+    b = c.batch(1)
+    b.set_ac_sweep(*sweep)
+    assert b.analyze(), c.abi.last_error()
+    assert (b.ac_omegas() == om).all()  # cumulative-product omegas are bit-identical
+    assert_close(b.ac_solution()[0], xr, "ac sweep")
+    assert b.total_solves == points
+
+
+def test_ac_sweep_with_instances(ref):
+    n_inst, points = 5, 40
+    nl, info = wl.rlc_ladder(4)
+    rng = np.random.default_rng(2)
+    over = [(e, "r", wl.sweep_values(rng, 10.0, n_inst)) for e in info["R"]] + [(e, "L", wl.sweep_values(rng, 1e-6, n_inst)) for e in info["L"]]
+    want = refapi.run_batch(nl, pe.AC, n_inst, over, ac=(pe.SWEEP_LINEAR, 1e5, 1e8, points))
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.AC)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    b.set_ac_sweep(pe.SWEEP_LINEAR, 1e5, 1e8, points)
+    assert b.analyze(), c.abi.last_error()
+    assert_close(b.ac_solution(), want["x"], "ac sweep x instances")
+
+
+def test_random_links_dc(ref):
+    # test/0013.cuda/cuda_random_links_correctness.cu shape (chain + random 1 kOhm chords), scaled down
+    nl, info = wl.random_links(256, 64, seed=3)
+    rc, rok, _ = ref_solo(nl, pe.DC, ref)
+    gc, gok = gpu_solo(nl, pe.DC)
+    assert rok and gok
+    assert_close(gc.solution(), rc.solution(), "random links")
+
+
+def test_diode_tr_with_transit_time(ref):
+    nl, info = wl.diode_resistor(v=2.0)
+    n_inst = 16
+    rng = np.random.default_rng(9)
+    over = [(info["D"][0], "tt", rng.uniform(1e-9, 1e-8, n_inst)), (info["R"], "r", wl.sweep_values(rng, 1e3, n_inst))]
+    want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-9, t_stop=2e-8)
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.TR)
+    c.set_tr(1e-9, 2e-8)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    assert (b.newton_iters() == want["solves"]).all()
+    assert_close(b.solution(), want["x"].real, "diode TR")
+
+
+def test_no_cpu_fallback_and_native_launches():
+    n0 = pe.launch_count()
+    nl, _ = wl.rc_ladder(2)
+    c, ok = gpu_solo(nl, pe.DC)
+    assert ok
+    assert pe.launch_count() > n0  # the answer came from our kernels
