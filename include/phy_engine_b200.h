@@ -148,6 +148,9 @@ extern "C"
     void circuit_batch_destroy(void* batch);
     int circuit_batch_set_device(void* batch, int device);
     int circuit_batch_set_stream(void* batch, void* cuda_stream);
+    /* warps per CTA cooperating on each block of 32 instances (sub-tree parallel LU): 0 = automatic from the lane count,
+     * else a power of two <= 16 */
+    int circuit_batch_set_subtree_warps(void* batch, int warps);
     /* per-instance values of one model attribute; values[n_instances] in the attribute's public unit */
     int circuit_batch_set_param(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values);
     /* many parameters in one call: values[n_params][n_instances].  Once the batch is prepared and every parameter
@@ -183,11 +186,13 @@ extern "C"
 
     /* ===== Part 3: introspection of the symbolic phase (no device needed; used by tests and DESIGN.md tooling) ===== */
     int circuit_batch_compile_host(void* batch);
-    size_t circuit_batch_program_words(void* batch, int mode, int section); /* section 0 prep, 1 step, 2 iter */
-    int circuit_batch_program_copy(void* batch, int mode, int section, uint32_t* out);
+    size_t circuit_batch_program_words(void* batch, int mode);
+    int circuit_batch_program_copy(void* batch, int mode, uint32_t* out);
     size_t circuit_batch_const_count(void* batch);
     int circuit_batch_const_copy(void* batch, double* out);
-    /* info[8] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns */
+    /* info[64]: [0..15] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns,
+     * warps, n_real_lane_slots, n_leaves, n_leaf_rows, n_top_rows, max_warp_words, nnz_a, nnz_lu;
+     * [16 + 16 * s + g] = word offset of warp g's stream of section s (0 prep, 1 step, 2 iter), -1 if absent */
     int circuit_batch_program_info(void* batch, int mode, int64_t* info);
     long long circuit_batch_swept_slot(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size);
     int circuit_batch_swept_values(void* batch, long long slot, double* out);

@@ -3,15 +3,19 @@
 // (SURVEY.md probe table), so nothing here refers to them.
 //
 // Execution model: one *lane* = one independent circuit solve stream (a Monte-Carlo instance, or one
-// (instance, frequency point) pair in an AC sweep).  Every lane interprets the same batch program; all per-lane
-// doubles live in *lane-interleaved* HBM arrays  w[slot][lane]  so that a warp touching slot s reads 32 consecutive
-// doubles (one fully coalesced 256-byte request).
+// (instance, frequency point) pair in an AC sweep).  All per-lane doubles live in *lane-interleaved* HBM arrays
+// w[slot][lane], so that the 32 threads of a warp (= 32 consecutive lanes) touching slot s read 32 consecutive
+// doubles (one fully coalesced 256-byte request).  A CTA is 32 lanes x G warps: the G warps cooperate on the SAME
+// 32 lanes, each interpreting its own word stream (its sub-trees of the elimination tree) with CTA barriers where
+// the streams meet.
 //
-// Three operand spaces:
+// Operand spaces:
 //   CONST  cst[slot]                         values shared by every lane (broadcast parameters, folded constants)
-//   INST   wi[slot * LSi + inst]             per-instance state: swept parameters, device state, real solution x
-//   LANE   wl[slot * LSl + lane]             per-lane scratch: matrix/rhs values (LU in place), AC solution, omega
-// with inst = lane / ppi (ppi = frequency points per instance; 1 outside AC sweeps).
+//   U      wu[slot * LSu + lane]             the lane-strided workspace of this launch
+//   INSTX  wx[slot * LSx + lane / ppi]       per-instance values seen from a frequency-point lane (AC sweeps only)
+// In the real-valued modes (DC/OP/TR/TROP) lanes == instances and everything (x, parameters, device state, matrix
+// and rhs scratch) is one U workspace; in AC the U workspace holds the per-point complex scratch and INSTX the
+// per-instance values.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
@@ -28,50 +32,50 @@ extern "C"
     enum
     {
         PE_SP_CONST = 0,
-        PE_SP_INST = 1,
-        PE_SP_LANE = 2,
+        PE_SP_U = 1,
+        PE_SP_INSTX = 2,
     };
 #define PE_OPND(space, slot) ((((uint32_t)(space)) << 29) | ((uint32_t)(slot) & 0x1fffffffu))
 #define PE_OPND_NEG 0x80000000u
 #define PE_OPND_SPACE(o) (((o) >> 29) & 3u)
 #define PE_OPND_SLOT(o) ((o) & 0x1fffffffu)
 
-    // ---- opcodes; header word = opcode | (n << 8) -----------------------------------------------------------------
-    // Operand lists follow the header as uint32 operand words.  "cx" = in a complex program the slot and slot+1 hold
-    // (re, im).
+    // ---- opcodes; header word: bits 7:0 opcode, the rest op-specific --------------------------------------------
     enum pe_b200_opcode
     {
         PE_OP_END = 0,
+        PE_OP_BAR = 1,  // CTA barrier: every warp stream of a section holds the same number of them
 
-        // assembly (stamp gather): dst = sum_i (+/-) src_i, accumulated in list order = the reference's model order
-        // (mna.h:60-157 accumulate semantics; "assign" stamps restart the list on the host side).  n = #src.
-        PE_OP_ASM = 1,  // [dst][src * n]
+        // The one numeric-factorisation primitive.  Every matrix entry of L, U, the pivots, the forward-substituted
+        // rhs and the solution is produced exactly once by
+        //     v = sum_i (+/-)src_i  -  sum_p a_p * b_p ;   [v *= scale] ;  [v = 1 / v] ;  store
+        // (row-wise "dot product" form of LU on the fixed pattern: stamp assembly, elimination, forward and back
+        // substitution are all this op).  header = op | flags << 8 | nsrc << 16 | npair << 24
+        //   words: [dst (U slot)] [scale (U slot), if F_SCALE] [src operand x nsrc] [(a, b) U slots x npair]
+        PE_OP_DOT = 2,
+        // complex variant (AC): slots hold re at s, im at s + 1.
+        //   header = op | flags << 8 | npair << 16 ; second word = nsrc_re | nsrc_im << 16
+        //   words: [dst] [scale, if F_SCALE] [src_re x nsrc_re] [src_im x nsrc_im] [(a, b) x npair]
+        PE_OP_CDOT = 3,
 
-        // LU on the fixed pattern, right-looking, augmented with the rhs column
-        PE_OP_PIVOT = 2,  // [kk]                r = 1 / w[kk]; w[kk] = r                       (cx)
-        PE_OP_ELIM = 3,   // [ik][(ij,kj) * n]   l = w[ik] * r; w[ij] -= l * w[kj]              (cx)
-        // back substitution fused with the Newton convergence test (circuit.h:923-948).  flag bit 0 of n's top bit:
-        // header = opcode | (n << 8) | (is_branch << 31)
-        PE_OP_BACK = 4,  // [bk][kk][xk][(kj,xj) * n]  x = (w[bk] - sum w[kj]*x[xj]) * w[kk]      (cx)
-
-        // scalar value ops (real)
-        PE_OP_RECIP = 10,   // [dst][a]          dst = 1.0 / a
-        PE_OP_MUL = 11,     // [dst][a][b]       dst = a * b
-        PE_OP_SUB = 12,     // [dst][a][b]       dst = a - b
-        PE_OP_COPY = 13,    // [dst][a]
-        PE_OP_VSIN = 14,    // [dst][Vp][omega][phase]   dst = Vp * sin(omega * t + phase)      (VAC.h:176, IAC.h:154)
-        PE_OP_SINCOS = 15,  // [dre][dim][Vp][phase]     dre = Vp cos(phase), dim = Vp sin(phase) (VAC.h:115-121)
-        PE_OP_MUL2DIV = 16, // [dst][a][b]       dst = 2.0 * a / b                              (2C/dt, 2L/dt)
+        // scalar value ops (real), generic operands
+        PE_OP_RECIP = 10,    // [dst][a]          dst = 1.0 / a
+        PE_OP_MUL = 11,      // [dst][a][b]       dst = a * b
+        PE_OP_SUB = 12,      // [dst][a][b]       dst = a - b
+        PE_OP_COPY = 13,     // [dst][a]
+        PE_OP_VSIN = 14,     // [dst][Vp][omega][phase]   dst = Vp * sin(omega * t + phase)      (VAC.h:176, IAC.h:154)
+        PE_OP_SINCOS = 15,   // [dre][dim][Vp][phase]     dre = Vp cos(phase), dim = Vp sin(phase) (VAC.h:115-121)
+        PE_OP_MUL2DIV = 16,  // [dst][a][b]       dst = 2.0 * a / b                              (2C/dt, 2L/dt)
 
         // trapezoidal companions (capacitor.h:106-128, inductor.h:134-160)
         PE_OP_CAP_STEP = 20,  // [hist][prev_g][C][dt][va][vb]
         PE_OP_IND_STEP = 21,  // [req][ueq][L][dt][va][vb][ib]
 
         // PN junction (PN_junction.h)
-        PE_OP_PN_PREP = 30,  // [is_eff][isr_eff][bv_eff][ut][uth] <- [Is][Isr][Area][N][Temp][Ibv][Bv][bv_set]
-        PE_OP_PN_EVAL = 31,  // [ud_last][geq][ieq] <- [va][vb][is_eff][isr_eff][bv_eff][ut][uth][N][Nr][bv_set]
-        PE_OP_PN_STEP = 32,  // [ud_last][hist][prev_g] <- [va][vb][geq][tt][dt]
-        PE_OP_PN_ACCAP = 33, // [dst] <- [geq][tt][omega]     dst = (omega!=0 && tt>0 && geq>0 && tt*geq>0) ? tt*geq*omega : 0
+        PE_OP_PN_PREP = 30,   // [is_eff][isr_eff][bv_eff][ut][uth] <- [Is][Isr][Area][N][Temp][Ibv][Bv][bv_set]
+        PE_OP_PN_EVAL = 31,   // [ud_last][geq][ieq] <- [va][vb][is_eff][isr_eff][bv_eff][ut][uth][N][Nr][bv_set]
+        PE_OP_PN_STEP = 32,   // [ud_last][hist][prev_g] <- [va][vb][geq][tt][dt]
+        PE_OP_PN_ACCAP = 33,  // [dst] <- [geq][tt][omega]     dst = (omega!=0 && tt>0 && geq>0 && tt*geq>0) ? tt*geq*omega : 0
 
         // BJT (BJT_NPN.h:116-159; PNP = same with the controlling voltage operands swapped)
         PE_OP_BJT_PREP = 40,  // [ut] <- [Temp]
@@ -82,6 +86,18 @@ extern "C"
         PE_OP_PMOS_EVAL = 51,  // [gm][gds][ieq] <- [vd][vg][vs][Kp][lambda][Vth]
     };
 
+    // DOT / CDOT flags
+    enum
+    {
+        PE_F_SCALE = 1,    // multiply by the value at the scale slot (a stored pivot reciprocal)
+        PE_F_RECIP = 2,    // store the reciprocal; a zero / non-finite value marks the lane singular
+        PE_F_CHECK_V = 4,  // Newton test against the old value at dst with the voltage tolerances (circuit.h:923-933)
+        PE_F_CHECK_I = 8,  // ... with the branch-current tolerances (circuit.h:937-947)
+    };
+#define PE_DOT_MAX_SRC 255u
+#define PE_DOT_MAX_PAIR 255u
+#define PE_MAX_WARPS 16
+
     // ---- lane status ------------------------------------------------------------------------------------------------
     enum
     {
@@ -90,29 +106,38 @@ extern "C"
         PE_ST_SINGULAR = 2,        // zero / non-finite pivot (circuit.h:1517 factorizationIsOk() == false)
     };
 
+    // A section = one word stream per warp of the CTA; off[g] is the start of warp g's stream inside `words`
+    // (PE_NO_SECTION: the section is absent).
+#define PE_NO_SECTION 0xffffffffu
+    typedef struct pe_b200_section
+    {
+        uint32_t off[PE_MAX_WARPS];
+    } pe_b200_section;
+
     // ---- one kernel launch = one analysis phase over all lanes -----------------------------------------------------
     typedef struct pe_b200_run
     {
-        // device pointers
-        uint32_t const* prep;  // once per launch (may be NULL)
-        uint32_t const* step;  // once per time step, before the Newton loop (TR only; may be NULL)
-        uint32_t const* iter;  // one linearised MNA solve: eval + assemble + factor + back-substitute(+check)
+        uint32_t const* words;  // device: program word pool
+        pe_b200_section prep;   // once per launch
+        pe_b200_section step;   // once per time step, before the Newton loop (TR only)
+        pe_b200_section iter;   // one linearised MNA solve: eval + assemble + factor + substitute (+ convergence test)
         double const* cst;
-        double* wi;
-        double* wl;
-        int32_t* status;   // [n_lanes]  (in/out: lanes with status != 0 on entry are skipped)
+        double* wu;
+        double* wx;
+        int32_t* status;   // [n_lanes]  (in/out: lanes with status != 0 on entry keep their status and are not counted)
         uint32_t* solves;  // [n_lanes]  += number of solve_once-equivalents executed
-        double* wave;      // optional waveform store [n_steps][n_probe][LSl] (NULL = off)
+        double* wave;      // optional waveform store [n_steps][n_probe][LSu] (NULL = off)
         uint32_t const* probes;  // [n_probe] operand words
 
-        int64_t LSi;  // lane stride (elements) of wi
-        int64_t LSl;  // lane stride of wl
+        int64_t LSu;  // lane stride (elements) of wu; a multiple of 32, >= n_lanes
+        int64_t LSx;  // stride of wx
         int32_t n_lanes;
-        int32_t ppi;  // lanes per instance
-        int32_t cplx;       // 0 real program, 1 complex program (AC)
+        int32_t ppi;        // lanes per instance (frequency points per instance in an AC sweep, else 1)
+        int32_t warps;      // G: warps per CTA = word streams per section (1..PE_MAX_WARPS)
+        int32_t cplx;       // informational: 1 when the iter section is a complex (AC) program
         int32_t nonlinear;  // 0: single solve per step; 1: Newton loop with convergence test
         int32_t max_iter;   // 64
-        int32_t n_steps;    // >= 1
+        int32_t n_steps;    // >= 0
         int32_t n_probe;
         int32_t time_stepping;  // 1: run `step` section and advance t by dt before each step's solve
         double t0;              // tr_duration at entry

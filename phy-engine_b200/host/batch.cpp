@@ -54,7 +54,12 @@ namespace pe_b200
         std::vector<sweep_key> keys;
         for(auto const& [k, v]: sweeps) { keys.push_back(k); }
         layout_change = !cc || cc_structure_rev != parent->structure_rev || keys != layout_keys;
-        bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step};
+        auto const& acs{ac.points > 0 || ac.omega != 0.0 || ac.omega_start != 0.0 ? ac : parent->ac};
+        std::size_t const ac_points{(acs.sweep == sweep_type::single || acs.points <= 1) ? 1u : acs.points};
+        int const n_unk{make_numbering(parent->nl).unknowns()};
+        int const w_real{pick_warps(n_inst, n_unk)};
+        int const w_ac{pick_warps(n_inst * ac_points, n_unk)};
+        bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac};
         if(!need) { return true; }
         layout_keys = keys;
 
@@ -66,6 +71,10 @@ namespace pe_b200
         in.omega0 = (a.sweep == sweep_type::single || a.points <= 1) ? a.omega : std::sqrt(std::fabs(a.omega_start * a.omega_stop));
         if(!(in.omega0 > 0.0)) { in.omega0 = 1.0; }
         for(auto const& [k, v]: sweeps) { in.swept_lane0[k] = v.empty() ? 0.0 : v[0]; }
+        in.warps_real = w_real;
+        in.warps_ac = w_ac;
+        cc_warps_real = w_real;
+        cc_warps_ac = w_ac;
         cc = compile_circuit(in);
         if(!cc)
         {
@@ -79,6 +88,23 @@ namespace pe_b200
         uploaded.fill(false);
         device_stale = true;
         return true;
+    }
+
+    int batch::pick_warps(std::size_t lanes, int n_unknowns) const
+    {
+        // G warps cooperate on each block of 32 lanes.  With plenty of lanes one warp per block already fills the GPU;
+        // a small batch of large circuits needs G > 1 to have enough resident warps to hide HBM latency.
+        int g{subtree_warps};
+        if(g <= 0)
+        {
+            std::size_t const blocks{(lanes + 31) / 32};
+            std::size_t const want{148u * 40u};  // resident warps we would like to have
+            g = 1;
+            while(g < PE_MAX_WARPS && blocks * static_cast<std::size_t>(g) * 2 <= want) { g *= 2; }
+        }
+        g = std::clamp(g, 1, PE_MAX_WARPS);
+        while(g > 1 && n_unknowns < 48 * g) { g /= 2; }  // leaves need enough rows to amortise the barriers
+        return g;
     }
 
     bool batch::ensure_compiled()
@@ -99,7 +125,8 @@ namespace pe_b200
         layout_pending = false;
 
         LSi = round_up32(n_inst);
-        std::size_t const wi_bytes{static_cast<std::size_t>(cc->n_inst_slots) * static_cast<std::size_t>(LSi) * sizeof(double)};
+        // instance workspace = persistent INST slots followed by the scratch of the real-valued programs (one U space)
+        std::size_t const wi_bytes{static_cast<std::size_t>(cc->n_inst_slots + cc->n_real_lane_slots) * static_cast<std::size_t>(LSi) * sizeof(double)};
         if(lc)
         {
             if(!d_wi.ensure(wi_bytes)) { return dev_fail(error, "alloc instance workspace"); }
@@ -115,8 +142,6 @@ namespace pe_b200
             if(pe_b200_dev_memset0(d_wi.p, wi_bytes, stream) != 0) { return dev_fail(error, "zero instance workspace"); }
             sweeps_dirty = true;
         }
-        if(!d_prep.ensure(cc->prep.size() * 4)) { return dev_fail(error, "alloc prep"); }
-        if(pe_b200_dev_h2d(d_prep.p, cc->prep.data(), cc->prep.size() * 4, stream) != 0) { return dev_fail(error, "upload prep"); }
         if(!d_status.ensure(static_cast<std::size_t>(LSi) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSi) * 4)) { return dev_fail(error, "alloc status"); }
         return true;
     }
@@ -145,17 +170,11 @@ namespace pe_b200
     {
         int const mi{static_cast<int>(m)};
         auto& pr{cc->prog[static_cast<std::size_t>(mi)]};
+        auto& d_w{d_words[static_cast<std::size_t>(mi)]};
         if(!uploaded[static_cast<std::size_t>(mi)])
         {
-            if(!d_step[static_cast<std::size_t>(mi)].ensure(pr.step.size() * 4) || !d_iter[static_cast<std::size_t>(mi)].ensure(pr.iter.size() * 4))
-            {
-                return dev_fail(error, "alloc program");
-            }
-            if(pe_b200_dev_h2d(d_step[static_cast<std::size_t>(mi)].p, pr.step.data(), pr.step.size() * 4, stream) != 0 ||
-               pe_b200_dev_h2d(d_iter[static_cast<std::size_t>(mi)].p, pr.iter.data(), pr.iter.size() * 4, stream) != 0)
-            {
-                return dev_fail(error, "upload program");
-            }
+            if(!d_w.ensure(pr.words.size() * 4)) { return dev_fail(error, "alloc program"); }
+            if(pe_b200_dev_h2d(d_w.p, pr.words.data(), pr.words.size() * 4, stream) != 0) { return dev_fail(error, "upload program"); }
             uploaded[static_cast<std::size_t>(mi)] = true;
         }
         // constants (dt patched in place)
@@ -163,18 +182,27 @@ namespace pe_b200
         if(!d_cst.ensure(cc->cst.size() * sizeof(double))) { return dev_fail(error, "alloc const table"); }
         if(pe_b200_dev_h2d(d_cst.p, cc->cst.data(), cc->cst.size() * sizeof(double), stream) != 0) { return dev_fail(error, "upload const table"); }
 
-        std::int64_t const LSl{round_up32(lanes)};
-        std::size_t const wl_bytes{static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double)};
-        if(!d_wl.ensure(wl_bytes)) { return dev_fail(error, "alloc lane workspace"); }
+        std::int64_t const LSl{pr.cplx ? round_up32(lanes) : LSi};
+        if(pr.cplx)
+        {
+            std::size_t const wl_bytes{static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double)};
+            if(!d_wl.ensure(wl_bytes)) { return dev_fail(error, "alloc lane workspace"); }
+        }
         if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
 
         pe_b200_run r{};
-        r.prep = with_prep ? static_cast<std::uint32_t const*>(d_prep.p) : nullptr;
-        r.step = static_cast<std::uint32_t const*>(d_step[static_cast<std::size_t>(mi)].p);
-        r.iter = static_cast<std::uint32_t const*>(d_iter[static_cast<std::size_t>(mi)].p);
+        r.words = static_cast<std::uint32_t const*>(d_w.p);
+        r.prep = pr.prep;
+        if(!with_prep)
+        {
+            for(auto& o: r.prep.off) { o = PE_NO_SECTION; }
+        }
+        r.step = pr.step;
+        r.iter = pr.iter;
         r.cst = static_cast<double const*>(d_cst.p);
-        r.wi = static_cast<double*>(d_wi.p);
-        r.wl = static_cast<double*>(d_wl.p);
+        r.wu = static_cast<double*>(pr.cplx ? d_wl.p : d_wi.p);
+        r.wx = static_cast<double*>(d_wi.p);
+        r.warps = pr.warps;
         r.status = static_cast<std::int32_t*>(d_status.p);
         r.solves = static_cast<std::uint32_t*>(d_solves.p);
         r.wave = nullptr;
@@ -194,8 +222,8 @@ namespace pe_b200
             r.n_probe = static_cast<std::int32_t>(po.size());
             wave_steps = static_cast<std::size_t>(n_steps);
         }
-        r.LSi = LSi;
-        r.LSl = LSl;
+        r.LSu = LSl;
+        r.LSx = LSi;
         r.n_lanes = static_cast<std::int32_t>(lanes);
         r.ppi = ppi;
         r.cplx = pr.cplx ? 1 : 0;

@@ -484,6 +484,13 @@ extern "C"
         return 0;
     }
 
+    int circuit_batch_set_subtree_warps(void* b, int warps)
+    {
+        if(b == nullptr || warps < 0 || warps > PE_MAX_WARPS || (warps & (warps - 1)) != 0) { return 1; }
+        static_cast<batch*>(b)->subtree_warps = warps;
+        return 0;
+    }
+
     int circuit_batch_set_stream(void* b, void* s)
     {
         if(b == nullptr) { return 1; }
@@ -693,22 +700,20 @@ extern "C"
         return 0;
     }
 
-    size_t circuit_batch_program_words(void* bp, int mode, int section)
+    size_t circuit_batch_program_words(void* bp, int mode)
     {
         if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
         auto* b{static_cast<batch*>(bp)};
         if(!b->cc) { return 0; }
-        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
-        return section == 0 ? b->cc->prep.size() : (section == 1 ? pr.step.size() : pr.iter.size());
+        return b->cc->prog[static_cast<std::size_t>(mode)].words.size();
     }
 
-    int circuit_batch_program_copy(void* bp, int mode, int section, uint32_t* out)
+    int circuit_batch_program_copy(void* bp, int mode, uint32_t* out)
     {
         if(bp == nullptr || out == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
         auto* b{static_cast<batch*>(bp)};
         if(!b->cc) { return 1; }
-        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
-        auto const& v{section == 0 ? b->cc->prep : (section == 1 ? pr.step : pr.iter)};
+        auto const& v{b->cc->prog[static_cast<std::size_t>(mode)].words};
         std::memcpy(out, v.data(), v.size() * 4);
         return 0;
     }
@@ -727,7 +732,9 @@ extern "C"
         return 0;
     }
 
-    // info[8] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns
+    // info[0..15] = cplx, structurally_singular, n_lane_slots, omega_slot, n_inst_slots, dt_slot, x_slot0, n_unknowns, warps,
+    // n_real_lane_slots, n_leaves, n_leaf_rows, n_top_rows, max_warp_words, nnz_a, nnz_lu;
+    // info[16 + 16 * s + g] = word offset of warp g's stream of section s (0 prep, 1 step, 2 iter), -1 if absent
     int circuit_batch_program_info(void* bp, int mode, int64_t* info)
     {
         if(bp == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
@@ -742,6 +749,23 @@ extern "C"
         info[5] = b->cc->dt_slot;
         info[6] = pr.x_opnd.empty() ? 0 : static_cast<int64_t>(PE_OPND_SLOT(pr.x_opnd[0]));
         info[7] = b->cc->num.unknowns();
+        info[8] = pr.warps;
+        info[9] = b->cc->n_real_lane_slots;
+        info[10] = static_cast<int64_t>(pr.n_leaves);
+        info[11] = static_cast<int64_t>(pr.n_leaf_rows);
+        info[12] = static_cast<int64_t>(pr.n_top_rows);
+        info[13] = static_cast<int64_t>(pr.max_warp_words);
+        info[14] = static_cast<int64_t>(pr.nnz_a);
+        info[15] = static_cast<int64_t>(pr.nnz_lu);
+        pe_b200_section const* secs[3]{&pr.prep, &pr.step, &pr.iter};
+        for(int s{}; s < 3; ++s)
+        {
+            for(int g{}; g < PE_MAX_WARPS; ++g)
+            {
+                auto const o{secs[s]->off[g]};
+                info[16 + 16 * s + g] = o == PE_NO_SECTION ? -1 : static_cast<int64_t>(o);
+            }
+        }
         return 0;
     }
 

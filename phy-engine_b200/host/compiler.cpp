@@ -1,17 +1,25 @@
-// compiler.cpp — the symbolic phase: netlist -> per-mode batch programs for the sm_100a interpreter kernels.
+// compiler.cpp — the symbolic phase: netlist -> per-mode batch programs for the sm_100a solve kernel.
 //
 // What it restates from the reference (all host-side, integer/graph work, once per netlist):
 //   * prepare() numbering                                   circuits/circuit.h:481-540
 //   * the per-model stamps of iterate_{dc,ac,tr,trop}_define  model/models/**  (cited at each stamp below)
 //   * accumulate-vs-assign semantics of MNA::{G,B,C,D,I,E}_ref  circuits/MNA/mna.h:60-157
 //   * gmin on the node diagonal                              circuits/circuit.h:1107-1110
-// What replaces Eigen::SparseLU::analyzePattern + factorize (circuit.h:1516): a Markowitz ordering with threshold
-// pivoting evaluated ONCE on nominal (lane-0) values, the resulting fill pattern, and a right-looking elimination
-// schedule emitted as PE_OP_PIVOT / PE_OP_ELIM / PE_OP_BACK words.  Numeric factorisation itself never runs here.
+// What replaces Eigen::SparseLU::analyzePattern + factorize (circuit.h:1516):
+//   1. a nested-dissection partition of the unknown graph into G-warp-sized leaves + a separator "top" (only when the
+//      batch has too few lanes to fill the GPU with one warp per 32 lanes; G = 1 otherwise),
+//   2. a Markowitz ordering with threshold pivoting, restricted to pivots inside one region at a time, evaluated ONCE
+//      on nominal (lane-0) values, and the resulting fill pattern,
+//   3. a row-wise ("dot product form") elimination schedule: every entry of L, U, the pivots, the forward-substituted
+//      rhs and the solution is produced exactly once by one PE_OP_DOT, rows of different leaves on different warps,
+//      separator rows after a CTA barrier.
+// Numeric factorisation itself never runs here.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <numeric>
+#include <queue>
 #include <set>
 
 #include "../csrc/pe_b200_models.h"
@@ -23,9 +31,14 @@ namespace pe_b200
     {
         using cplx = std::complex<double>;
 
+        // internal operand spaces of the builder; translated to the kernel's spaces per mode at emission (xlat)
+        constexpr std::uint32_t I_CONST{0}, I_INST{1}, I_LANE{2};
+        constexpr std::uint32_t IOP(std::uint32_t space, int slot) { return (space << 29) | (static_cast<std::uint32_t>(slot) & 0x1fffffffu); }
+        constexpr std::uint32_t IOP(std::uint32_t space, std::uint32_t slot) { return (space << 29) | (slot & 0x1fffffffu); }
+
         struct val
         {
-            std::uint32_t op{};  // operand word without the negate bit
+            std::uint32_t op{};  // internal operand word without the negate bit
             double nom{};        // lane-0 / nominal value (pivot selection only)
             bool cst{};
         };
@@ -35,6 +48,8 @@ namespace pe_b200
             std::vector<std::uint32_t> re, im;
             cplx nom{};
         };
+
+        using op_t = std::vector<std::uint32_t>;  // [opcode header][internal operand words...]
 
         constexpr double k_nl_nominal = 1e-12;  // nominal conductance of a not-yet-evaluated non-linear device
         constexpr double k_pivot_tau = 1e-3;    // relative threshold (SPICE PIVREL)
@@ -55,6 +70,7 @@ namespace pe_b200
             numbering const& num;
             std::map<std::uint64_t, int> cst_index;
             std::vector<elem_vals> ev;
+            std::vector<op_t> prep_ops;
             int n_inst{};
             int dt_slot{-1};
 
@@ -76,15 +92,17 @@ namespace pe_b200
                 {
                     slot = it->second;
                 }
-                return {PE_OPND(PE_SP_CONST, slot), v, true};
+                return {IOP(I_CONST, slot), v, true};
             }
 
-            val inst_slot(double nominal) { return {PE_OPND(PE_SP_INST, n_inst++), nominal, false}; }
+            val inst_slot(double nominal) { return {IOP(I_INST, n_inst++), nominal, false}; }
 
-            static void emit(std::vector<std::uint32_t>& sec, std::uint32_t opcode, std::initializer_list<std::uint32_t> ops, std::uint32_t n = 0)
+            static void emit(std::vector<op_t>& sec, std::uint32_t opcode, std::initializer_list<std::uint32_t> ops)
             {
-                sec.push_back(opcode | (n << 8));
-                for(auto o: ops) { sec.push_back(o); }
+                op_t o;
+                o.push_back(opcode);
+                for(auto w: ops) { o.push_back(w); }
+                sec.push_back(std::move(o));
             }
 
             int nidx(int node) const { return node < 0 ? -1 : num.node_index[static_cast<std::size_t>(node)]; }
@@ -93,7 +111,7 @@ namespace pe_b200
             {
                 int const i{nidx(node)};
                 if(i < 0) { return constant(0.0); }
-                return {PE_OPND(PE_SP_INST, i), 0.0, false};
+                return {IOP(I_INST, i), 0.0, false};
             }
 
             static bool connected(element const& e)
@@ -170,7 +188,7 @@ namespace pe_b200
                     }
                 }
                 // derived quantities: folded on the host when every input is a broadcast constant, PREP ops otherwise
-                auto& prep{out.prep};
+                auto& prep{prep_ops};
                 val const temp{constant(in.env.temperature)};  // load_temperature fallback overwrites Temp (base.h:326-381)
                 for(std::size_t ei{}; ei < nl.elems.size(); ++ei)
                 {
@@ -263,12 +281,11 @@ namespace pe_b200
                         default: break;
                     }
                 }
-                prep.push_back(PE_OP_END);
                 dt_slot = static_cast<int>(out.cst.size());
                 out.cst.push_back(in.dt);  // dedicated (never de-duplicated) so the driver can patch it per analyze
                 out.n_inst_slots = n_inst;
             }
-            val dt_val() const { return {PE_OPND(PE_SP_CONST, dt_slot), in.dt, true}; }
+            val dt_val() const { return {IOP(I_CONST, dt_slot), in.dt, true}; }
 
             // ---- one program ------------------------------------------------------------------------------------
             struct pstate
@@ -277,13 +294,13 @@ namespace pe_b200
                 bool cplx;
                 std::map<std::pair<int, int>, entry> A;
                 std::vector<entry> Z;
-                std::vector<std::uint32_t> head;  // per-iteration value ops (device evaluation, sources)
-                std::vector<std::uint32_t> step;
+                std::vector<op_t> head;  // per-iteration value ops (device evaluation, sources)
+                std::vector<op_t> step;
                 int n_lane{};
                 val omega{};
             };
 
-            val lane_slot(pstate& ps, double nominal) { return {PE_OPND(PE_SP_LANE, ps.n_lane++), nominal, false}; }
+            val lane_slot(pstate& ps, double nominal) { return {IOP(I_LANE, ps.n_lane++), nominal, false}; }
 
             static std::uint32_t sg(val const& v, bool neg) { return v.op | (neg ? PE_OPND_NEG : 0u); }
 
@@ -409,7 +426,7 @@ namespace pe_b200
                             // inductor.h:134-195
                             emit(ps.step,
                                  PE_OP_IND_STEP,
-                                 {v.s[0].op, v.s[1].op, v.p[0].op, dt_val().op, vx(e.pin_node[0]).op, vx(e.pin_node[1]).op, PE_OPND(PE_SP_INST, k)});
+                                 {v.s[0].op, v.s[1].op, v.p[0].op, dt_val().op, vx(e.pin_node[0]).op, vx(e.pin_node[1]).op, IOP(I_INST, k)});
                             A_set(ps, k, k, &v.s[0], true);
                             Z_set(ps, k, &v.s[1]);
                         }
@@ -667,15 +684,177 @@ namespace pe_b200
                     default: break;
                 }
             }
+            // ---- nested-dissection partition of the unknown graph ------------------------------------------------
+            // region[i] >= 0: leaf id (rows/columns that may be pivoted inside that leaf, concurrently with the other
+            // leaves); -1: the separator "top", eliminated after all leaves.  Equation i and unknown i share a region.
+            static std::vector<int> partition(int n, std::vector<std::vector<int>> const& adj, int target_leaves, int min_leaf)
+            {
+                std::vector<int> region(static_cast<std::size_t>(n), -1);
+                if(target_leaves <= 1 || n < 2 * min_leaf) { return region; }
+                // hubs (supply rails, ...) go to the top straight away: they would glue every BFS level together
+                std::size_t deg_sum{};
+                for(auto const& a: adj) { deg_sum += a.size(); }
+                std::size_t const hub_deg{std::max<std::size_t>(32, 10 * (deg_sum / static_cast<std::size_t>(n) + 1))};
+                std::vector<char> in_top(static_cast<std::size_t>(n), 0);
+                std::vector<int> all;
+                for(int i{}; i < n; ++i)
+                {
+                    if(adj[static_cast<std::size_t>(i)].size() > hub_deg) { in_top[static_cast<std::size_t>(i)] = 1; }
+                    else
+                    {
+                        all.push_back(i);
+                    }
+                }
+                std::vector<std::vector<int>> parts;
+                std::vector<char> frozen;  // parts that could not be split
+                parts.push_back(std::move(all));
+                frozen.push_back(0);
+                std::vector<int> mark(static_cast<std::size_t>(n), -1), level(static_cast<std::size_t>(n), -1);
+                int stamp{};
+
+                auto bfs = [&](std::vector<int> const& part, int start, int my_stamp, std::vector<int>& order) -> int
+                {
+                    // BFS inside the vertices whose mark == my_stamp; returns the number of levels
+                    order.clear();
+                    for(int v: part) { level[static_cast<std::size_t>(v)] = -1; }
+                    level[static_cast<std::size_t>(start)] = 0;
+                    order.push_back(start);
+                    int maxl{};
+                    for(std::size_t h{}; h < order.size(); ++h)
+                    {
+                        int const v{order[h]};
+                        for(int u: adj[static_cast<std::size_t>(v)])
+                        {
+                            if(mark[static_cast<std::size_t>(u)] != my_stamp || level[static_cast<std::size_t>(u)] >= 0) { continue; }
+                            level[static_cast<std::size_t>(u)] = level[static_cast<std::size_t>(v)] + 1;
+                            maxl = std::max(maxl, level[static_cast<std::size_t>(u)]);
+                            order.push_back(u);
+                        }
+                    }
+                    return maxl + 1;
+                };
+
+                while(static_cast<int>(parts.size()) < target_leaves)
+                {
+                    int best{-1};
+                    for(std::size_t p{}; p < parts.size(); ++p)
+                    {
+                        if(frozen[p] || static_cast<int>(parts[p].size()) < 2 * min_leaf) { continue; }
+                        if(best < 0 || parts[p].size() > parts[static_cast<std::size_t>(best)].size()) { best = static_cast<int>(p); }
+                    }
+                    if(best < 0) { break; }
+                    auto part{std::move(parts[static_cast<std::size_t>(best)])};
+                    int const st{++stamp};
+                    for(int v: part) { mark[static_cast<std::size_t>(v)] = st; }
+                    std::vector<int> order;
+                    // connected components first
+                    std::vector<std::vector<int>> comps;
+                    {
+                        std::vector<char> seen_local;
+                        for(int v: part) { level[static_cast<std::size_t>(v)] = -1; }
+                        std::vector<int> q;
+                        for(int s: part)
+                        {
+                            if(level[static_cast<std::size_t>(s)] >= 0) { continue; }
+                            q.clear();
+                            q.push_back(s);
+                            level[static_cast<std::size_t>(s)] = 0;
+                            for(std::size_t h{}; h < q.size(); ++h)
+                            {
+                                for(int u: adj[static_cast<std::size_t>(q[h])])
+                                {
+                                    if(mark[static_cast<std::size_t>(u)] != st || level[static_cast<std::size_t>(u)] >= 0) { continue; }
+                                    level[static_cast<std::size_t>(u)] = 0;
+                                    q.push_back(u);
+                                }
+                            }
+                            comps.push_back(q);
+                        }
+                    }
+                    std::vector<int> A, B, S;
+                    if(comps.size() > 1)
+                    {
+                        std::sort(comps.begin(), comps.end(), [](auto const& x, auto const& y) { return x.size() > y.size(); });
+                        for(auto const& cmp: comps)
+                        {
+                            auto& dst{A.size() <= B.size() ? A : B};
+                            dst.insert(dst.end(), cmp.begin(), cmp.end());
+                        }
+                    }
+                    else
+                    {
+                        // pseudo-peripheral start: two BFS sweeps
+                        bfs(part, part[0], st, order);
+                        int const far{order.back()};
+                        int const nl{bfs(part, far, st, order)};
+                        if(nl >= 3)
+                        {
+                            std::vector<int> cnt(static_cast<std::size_t>(nl), 0);
+                            for(int v: part) { ++cnt[static_cast<std::size_t>(level[static_cast<std::size_t>(v)])]; }
+                            int const total{static_cast<int>(part.size())};
+                            int below{cnt[0]}, best_t{-1};
+                            long best_cost{std::numeric_limits<long>::max()};
+                            for(int t{1}; t + 1 < nl; ++t)
+                            {
+                                int const above{total - below - cnt[static_cast<std::size_t>(t)]};
+                                int const lo{std::min(below, above)};
+                                // separator size first; strongly penalise lopsided cuts
+                                long cost{static_cast<long>(cnt[static_cast<std::size_t>(t)]) * 8};
+                                if(lo * 10 < total * 3) { cost += static_cast<long>(total) * 8 + static_cast<long>(std::abs(below - above)); }
+                                else
+                                {
+                                    cost += std::abs(below - above) / 8;
+                                }
+                                if(lo > 0 && cost < best_cost)
+                                {
+                                    best_cost = cost;
+                                    best_t = t;
+                                }
+                                below += cnt[static_cast<std::size_t>(t)];
+                            }
+                            if(best_t >= 0)
+                            {
+                                for(int v: part)
+                                {
+                                    int const l{level[static_cast<std::size_t>(v)]};
+                                    (l < best_t ? A : (l > best_t ? B : S)).push_back(v);
+                                }
+                            }
+                        }
+                    }
+                    if(A.empty() || B.empty())
+                    {
+                        parts[static_cast<std::size_t>(best)] = std::move(part);
+                        frozen[static_cast<std::size_t>(best)] = 1;
+                        continue;
+                    }
+                    for(int v: S) { in_top[static_cast<std::size_t>(v)] = 1; }
+                    parts[static_cast<std::size_t>(best)] = std::move(A);
+                    parts.push_back(std::move(B));
+                    frozen.push_back(0);
+                }
+                if(parts.size() < 2) { return region; }
+                for(std::size_t p{}; p < parts.size(); ++p)
+                {
+                    for(int v: parts[p]) { region[static_cast<std::size_t>(v)] = static_cast<int>(p); }
+                }
+                return region;
+            }
 
             // ---- symbolic LU + emission ------------------------------------------------------------------------
             struct lu_step
             {
                 int r, c, piv;
+                int leaf;                       // region the pivot was taken in (-1 = top)
                 std::vector<int> lrows, l_ent;  // rows i with (i,c), entry ids
                 std::vector<int> ucols, u_ent;  // cols j with (r,j), entry ids
                 std::vector<int> t_ent;         // lrows.size() * ucols.size() target entry ids
-                std::vector<char> t_new;        // fill created at this step
+            };
+
+            struct stream
+            {
+                std::vector<std::uint32_t> w;
+                int tmp_slot{-1};
             };
 
             void build_program(prog_mode mode)
@@ -684,7 +863,9 @@ namespace pe_b200
                 pstate ps;
                 ps.mode = mode;
                 ps.cplx = (mode == prog_mode::AC);
+                bool const ac{ps.cplx};
                 int const n{num.unknowns()};
+                int G{std::clamp(ac ? in.warps_ac : in.warps_real, 1, PE_MAX_WARPS)};
                 ps.Z.resize(static_cast<std::size_t>(n));
                 if(ps.cplx)
                 {
@@ -700,31 +881,58 @@ namespace pe_b200
                 pr.cplx = ps.cplx;
                 pr.nnz_a = ps.A.size();
 
-                // --- Markowitz ordering with threshold pivoting on nominal values
+                // --- entries + active structure
                 std::vector<int> ent_r, ent_c;
                 std::vector<cplx> nv;
+                std::vector<entry const*> orig;
                 std::vector<std::map<int, int>> rows(static_cast<std::size_t>(n));  // col -> id (all entries ever)
                 std::vector<std::set<int>> rowcols(static_cast<std::size_t>(n)), colrows(static_cast<std::size_t>(n));
+                std::vector<std::vector<int>> adj(static_cast<std::size_t>(n));
                 for(auto const& [rc, e]: ps.A)
                 {
                     int const id{static_cast<int>(nv.size())};
                     ent_r.push_back(rc.first);
                     ent_c.push_back(rc.second);
                     nv.push_back(e.nom);
+                    orig.push_back(&e);
                     rows[static_cast<std::size_t>(rc.first)][rc.second] = id;
                     rowcols[static_cast<std::size_t>(rc.first)].insert(rc.second);
                     colrows[static_cast<std::size_t>(rc.second)].insert(rc.first);
+                    if(rc.first != rc.second)
+                    {
+                        adj[static_cast<std::size_t>(rc.first)].push_back(rc.second);
+                        adj[static_cast<std::size_t>(rc.second)].push_back(rc.first);
+                    }
                 }
-                int const n_orig{static_cast<int>(nv.size())};
-                std::set<std::pair<int, int>> rq, cq;
+                for(auto& a: adj)
+                {
+                    std::sort(a.begin(), a.end());
+                    a.erase(std::unique(a.begin(), a.end()), a.end());
+                }
+
+                // --- regions: leaves (concurrent) + top
+                int const min_leaf{12};
+                std::vector<int> region{partition(n, adj, G, min_leaf)};
+                int n_leaves{};
+                for(int v: region) { n_leaves = std::max(n_leaves, v + 1); }
+                if(n_leaves < 2)
+                {
+                    n_leaves = 0;
+                    std::fill(region.begin(), region.end(), -1);
+                    G = 1;
+                }
+                pr.n_leaves = static_cast<std::size_t>(n_leaves);
+
+                // --- Markowitz ordering with threshold pivoting on nominal values, one region at a time
+                int const R{n_leaves + 1};  // queue index: leaf id, or n_leaves for the top
+                auto qi = [&](int idx) { return region[static_cast<std::size_t>(idx)] < 0 ? n_leaves : region[static_cast<std::size_t>(idx)]; };
+                std::vector<std::set<std::pair<int, int>>> rq(static_cast<std::size_t>(R)), cq(static_cast<std::size_t>(R));
                 for(int i{}; i < n; ++i)
                 {
-                    rq.insert({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
-                    cq.insert({static_cast<int>(colrows[static_cast<std::size_t>(i)].size()), i});
+                    rq[static_cast<std::size_t>(qi(i))].insert({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
+                    cq[static_cast<std::size_t>(qi(i))].insert({static_cast<int>(colrows[static_cast<std::size_t>(i)].size()), i});
                 }
-                std::vector<char> bnz(static_cast<std::size_t>(n), 0);
-                for(int i{}; i < n; ++i) { bnz[static_cast<std::size_t>(i)] = !(ps.Z[static_cast<std::size_t>(i)].re.empty() && ps.Z[static_cast<std::size_t>(i)].im.empty()); }
-                std::vector<char> step_bnz;
+                std::vector<char> row_done(static_cast<std::size_t>(n), 0), col_done(static_cast<std::size_t>(n), 0);
                 std::vector<lu_step> steps;
                 steps.reserve(static_cast<std::size_t>(n));
                 bool singular{false};
@@ -736,255 +944,510 @@ namespace pe_b200
                     return m;
                 };
 
-                for(int k{}; k < n; ++k)
+                for(int cur{}; cur < R && !singular; ++cur)
                 {
-                    long best_cost{std::numeric_limits<long>::max()};
-                    int br{-1}, bc{-1};
-                    double best_ratio{};
-                    auto consider = [&](int r, int c, double cm)
+                    bool const top{cur == n_leaves};
+                    auto& RQ{rq[static_cast<std::size_t>(cur)]};
+                    auto& CQ{cq[static_cast<std::size_t>(cur)]};
+                    for(;;)
                     {
-                        double const mag{std::abs(nv[static_cast<std::size_t>(rows[static_cast<std::size_t>(r)][c])])};
-                        if(!(mag > 0.0) || mag < k_pivot_tau * cm) { return; }
-                        long const cost{static_cast<long>(rowcols[static_cast<std::size_t>(r)].size() - 1) * static_cast<long>(colrows[static_cast<std::size_t>(c)].size() - 1)};
-                        double const ratio{mag / cm};
-                        if(cost < best_cost || (cost == best_cost && ratio > 4.0 * best_ratio))
+                        long best_cost{std::numeric_limits<long>::max()};
+                        int br{-1}, bc{-1};
+                        double best_ratio{};
+                        auto consider = [&](int r, int c, double cm)
                         {
-                            best_cost = cost;
-                            br = r;
-                            bc = c;
-                            best_ratio = ratio;
-                        }
-                    };
-                    auto itc{cq.begin()};
-                    auto itr{rq.begin()};
-                    int examined{};
-                    while(itc != cq.end() || itr != rq.end())
-                    {
-                        bool const take_col{itr == rq.end() || (itc != cq.end() && itc->first <= itr->first)};
-                        int const cnt{take_col ? itc->first : itr->first};
-                        if(br >= 0 && best_cost <= static_cast<long>(cnt - 1) * static_cast<long>(cnt - 1)) { break; }
-                        if(take_col)
-                        {
-                            int const c{itc->second};
-                            ++itc;
-                            if(cnt == 0) { continue; }
-                            double const cm{colmax(c)};
-                            for(int i: colrows[static_cast<std::size_t>(c)]) { consider(i, c, cm); }
-                        }
-                        else
-                        {
-                            int const r{itr->second};
-                            ++itr;
-                            if(cnt == 0) { continue; }
-                            for(int j: rowcols[static_cast<std::size_t>(r)]) { consider(r, j, colmax(j)); }
-                        }
-                        if(++examined > 64 && br >= 0) { break; }
-                    }
-                    if(br < 0)
-                    {
-                        singular = true;
-                        break;
-                    }
-                    lu_step st;
-                    st.r = br;
-                    st.c = bc;
-                    st.piv = rows[static_cast<std::size_t>(br)][bc];
-                    for(int i: colrows[static_cast<std::size_t>(bc)])
-                    {
-                        if(i != br)
-                        {
-                            st.lrows.push_back(i);
-                            st.l_ent.push_back(rows[static_cast<std::size_t>(i)][bc]);
-                        }
-                    }
-                    for(int j: rowcols[static_cast<std::size_t>(br)])
-                    {
-                        if(j != bc)
-                        {
-                            st.ucols.push_back(j);
-                            st.u_ent.push_back(rows[static_cast<std::size_t>(br)][j]);
-                        }
-                    }
-                    // remove pivot row / col from the active structure
-                    for(int j: rowcols[static_cast<std::size_t>(br)])
-                    {
-                        cq.erase({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
-                        colrows[static_cast<std::size_t>(j)].erase(br);
-                        if(j != bc) { cq.insert({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j}); }
-                    }
-                    for(int i: st.lrows)
-                    {
-                        rq.erase({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
-                        rowcols[static_cast<std::size_t>(i)].erase(bc);
-                    }
-                    rq.erase({static_cast<int>(rowcols[static_cast<std::size_t>(br)].size()), br});
-                    rowcols[static_cast<std::size_t>(br)].clear();
-                    colrows[static_cast<std::size_t>(bc)].clear();
-                    // numeric (nominal) elimination + fill
-                    cplx const pv{nv[static_cast<std::size_t>(st.piv)]};
-                    st.t_ent.reserve(st.lrows.size() * st.ucols.size());
-                    for(std::size_t a{}; a < st.lrows.size(); ++a)
-                    {
-                        int const i{st.lrows[a]};
-                        cplx const l{nv[static_cast<std::size_t>(st.l_ent[a])] / pv};
-                        for(std::size_t b{}; b < st.ucols.size(); ++b)
-                        {
-                            int const j{st.ucols[b]};
-                            auto& rowi{rows[static_cast<std::size_t>(i)]};
-                            auto it{rowi.find(j)};
-                            int id;
-                            bool fresh{false};
-                            if(it == rowi.end())
+                            if(qi(r) != cur || qi(c) != cur) { return; }
+                            double const mag{std::abs(nv[static_cast<std::size_t>(rows[static_cast<std::size_t>(r)][c])])};
+                            if(!(mag > 0.0) || mag < k_pivot_tau * cm) { return; }
+                            long const cost{static_cast<long>(rowcols[static_cast<std::size_t>(r)].size() - 1) *
+                                            static_cast<long>(colrows[static_cast<std::size_t>(c)].size() - 1)};
+                            double const ratio{mag / cm};
+                            if(cost < best_cost || (cost == best_cost && ratio > 4.0 * best_ratio))
                             {
-                                id = static_cast<int>(nv.size());
-                                nv.push_back({});
-                                ent_r.push_back(i);
-                                ent_c.push_back(j);
-                                rowi[j] = id;
-                                rowcols[static_cast<std::size_t>(i)].insert(j);
-                                cq.erase({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
-                                colrows[static_cast<std::size_t>(j)].insert(i);
-                                cq.insert({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
-                                fresh = true;
+                                best_cost = cost;
+                                br = r;
+                                bc = c;
+                                best_ratio = ratio;
+                            }
+                        };
+                        auto itc{CQ.begin()};
+                        auto itr{RQ.begin()};
+                        int examined{};
+                        while(itc != CQ.end() || itr != RQ.end())
+                        {
+                            bool const take_col{itr == RQ.end() || (itc != CQ.end() && itc->first <= itr->first)};
+                            int const cnt{take_col ? itc->first : itr->first};
+                            if(br >= 0 && best_cost <= static_cast<long>(cnt - 1) * static_cast<long>(cnt - 1)) { break; }
+                            if(take_col)
+                            {
+                                int const c{itc->second};
+                                ++itc;
+                                if(cnt == 0) { continue; }
+                                double const cm{colmax(c)};
+                                for(int i: colrows[static_cast<std::size_t>(c)]) { consider(i, c, cm); }
                             }
                             else
                             {
-                                id = it->second;
+                                int const r{itr->second};
+                                ++itr;
+                                if(cnt == 0) { continue; }
+                                for(int j: rowcols[static_cast<std::size_t>(r)]) { consider(r, j, colmax(j)); }
                             }
-                            nv[static_cast<std::size_t>(id)] -= l * nv[static_cast<std::size_t>(st.u_ent[b])];
-                            st.t_ent.push_back(id);
-                            st.t_new.push_back(fresh ? 1 : 0);
+                            if(++examined > 64 && br >= 0) { break; }
                         }
-                        rq.insert({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
-                        if(bnz[static_cast<std::size_t>(br)]) { bnz[static_cast<std::size_t>(i)] = 1; }
+                        if(br < 0) { break; }
+                        lu_step st;
+                        st.r = br;
+                        st.c = bc;
+                        st.leaf = top ? -1 : cur;
+                        st.piv = rows[static_cast<std::size_t>(br)][bc];
+                        for(int i: colrows[static_cast<std::size_t>(bc)])
+                        {
+                            if(i != br)
+                            {
+                                st.lrows.push_back(i);
+                                st.l_ent.push_back(rows[static_cast<std::size_t>(i)][bc]);
+                            }
+                        }
+                        for(int j: rowcols[static_cast<std::size_t>(br)])
+                        {
+                            if(j != bc)
+                            {
+                                st.ucols.push_back(j);
+                                st.u_ent.push_back(rows[static_cast<std::size_t>(br)][j]);
+                            }
+                        }
+                        // remove pivot row / col from the active structure
+                        for(int j: rowcols[static_cast<std::size_t>(br)])
+                        {
+                            auto& q{cq[static_cast<std::size_t>(qi(j))]};
+                            q.erase({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
+                            colrows[static_cast<std::size_t>(j)].erase(br);
+                            if(j != bc) { q.insert({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j}); }
+                        }
+                        for(int i: st.lrows)
+                        {
+                            rq[static_cast<std::size_t>(qi(i))].erase({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
+                            rowcols[static_cast<std::size_t>(i)].erase(bc);
+                        }
+                        RQ.erase({static_cast<int>(rowcols[static_cast<std::size_t>(br)].size()), br});
+                        rowcols[static_cast<std::size_t>(br)].clear();
+                        colrows[static_cast<std::size_t>(bc)].clear();
+                        row_done[static_cast<std::size_t>(br)] = 1;
+                        col_done[static_cast<std::size_t>(bc)] = 1;
+                        // numeric (nominal) elimination + fill
+                        cplx const pv{nv[static_cast<std::size_t>(st.piv)]};
+                        st.t_ent.reserve(st.lrows.size() * st.ucols.size());
+                        for(std::size_t a{}; a < st.lrows.size(); ++a)
+                        {
+                            int const i{st.lrows[a]};
+                            cplx const l{nv[static_cast<std::size_t>(st.l_ent[a])] / pv};
+                            for(std::size_t b{}; b < st.ucols.size(); ++b)
+                            {
+                                int const j{st.ucols[b]};
+                                auto& rowi{rows[static_cast<std::size_t>(i)]};
+                                auto it{rowi.find(j)};
+                                int id;
+                                if(it == rowi.end())
+                                {
+                                    id = static_cast<int>(nv.size());
+                                    nv.push_back({});
+                                    ent_r.push_back(i);
+                                    ent_c.push_back(j);
+                                    orig.push_back(nullptr);
+                                    rowi[j] = id;
+                                    rowcols[static_cast<std::size_t>(i)].insert(j);
+                                    auto& q{cq[static_cast<std::size_t>(qi(j))]};
+                                    q.erase({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
+                                    colrows[static_cast<std::size_t>(j)].insert(i);
+                                    q.insert({static_cast<int>(colrows[static_cast<std::size_t>(j)].size()), j});
+                                }
+                                else
+                                {
+                                    id = it->second;
+                                }
+                                nv[static_cast<std::size_t>(id)] -= l * nv[static_cast<std::size_t>(st.u_ent[b])];
+                                st.t_ent.push_back(id);
+                            }
+                            rq[static_cast<std::size_t>(qi(i))].insert({static_cast<int>(rowcols[static_cast<std::size_t>(i)].size()), i});
+                        }
+                        steps.push_back(std::move(st));
                     }
-                    step_bnz.push_back(bnz[static_cast<std::size_t>(br)]);
-                    steps.push_back(std::move(st));
+                    if(!top)
+                    {
+                        // rows / columns of this leaf that found no acceptable pivot inside it are promoted to the top
+                        for(auto const& [cnt, i]: RQ) { rq[static_cast<std::size_t>(n_leaves)].insert({cnt, i}); }
+                        for(auto const& [cnt, j]: CQ) { cq[static_cast<std::size_t>(n_leaves)].insert({cnt, j}); }
+                        // indices whose row AND column are still active simply change region; a half-eliminated index
+                        // (row done, column not, or vice versa) also moves: the restriction only looks at active ones
+                        for(int i{}; i < n; ++i)
+                        {
+                            if(region[static_cast<std::size_t>(i)] == cur && (!row_done[static_cast<std::size_t>(i)] || !col_done[static_cast<std::size_t>(i)]))
+                            {
+                                region[static_cast<std::size_t>(i)] = -1;
+                            }
+                        }
+                        RQ.clear();
+                        CQ.clear();
+                    }
+                    else if(static_cast<int>(steps.size()) < n) { singular = true; }
                 }
                 pr.structurally_singular = singular;
                 pr.nnz_lu = nv.size();
-                (void)n_orig;
 
-                // --- emission
-                auto& it_sec{pr.iter};
-                it_sec = std::move(ps.head);
-                pr.step = std::move(ps.step);
-                pr.step.push_back(PE_OP_END);
+                // --- operand translation to the kernel's spaces
+                std::uint32_t const lane0{ac ? 0u : static_cast<std::uint32_t>(out.n_inst_slots)};
+                auto xl = [&](std::uint32_t o) -> std::uint32_t
+                {
+                    std::uint32_t const neg{o & PE_OPND_NEG};
+                    std::uint32_t const sp{(o >> 29) & 3u};
+                    std::uint32_t const slot{o & 0x1fffffffu};
+                    if(sp == I_CONST) { return neg | PE_OPND(PE_SP_CONST, slot); }
+                    if(sp == I_INST) { return neg | (ac ? PE_OPND(PE_SP_INSTX, slot) : PE_OPND(PE_SP_U, slot)); }
+                    return neg | PE_OPND(PE_SP_U, slot + lane0);
+                };
+                auto emit_value_op = [&](stream& S, op_t const& o)
+                {
+                    S.w.push_back(o[0]);
+                    for(std::size_t k{1}; k < o.size(); ++k) { S.w.push_back(xl(o[k])); }
+                };
+
+                std::vector<stream> prep_s(static_cast<std::size_t>(G)), step_s(static_cast<std::size_t>(G)), iter_s(static_cast<std::size_t>(G));
+                auto distribute = [&](std::vector<op_t> const& ops, std::vector<stream>& dst)
+                {
+                    for(std::size_t k{}; k < ops.size(); ++k) { emit_value_op(dst[k % static_cast<std::size_t>(G)], ops[k]); }
+                };
+                // PREP always addresses the instance workspace (it runs in a real-mode launch)
+                if(!ac) { distribute(prep_ops, prep_s); }
+                distribute(ps.step, step_s);
+                distribute(ps.head, iter_s);
+
+                auto finish = [&]()
+                {
+                    // word pool + section offsets
+                    pr.words.clear();
+                    auto place = [&](std::vector<stream>& ss, pe_b200_section& sec, bool present)
+                    {
+                        for(int g{}; g < PE_MAX_WARPS; ++g) { sec.off[g] = PE_NO_SECTION; }
+                        if(!present) { return; }
+                        for(int g{}; g < G; ++g)
+                        {
+                            sec.off[g] = static_cast<std::uint32_t>(pr.words.size());
+                            auto& w{ss[static_cast<std::size_t>(g)].w};
+                            pr.words.insert(pr.words.end(), w.begin(), w.end());
+                            pr.words.push_back(PE_OP_END);
+                        }
+                    };
+                    bool const has_prep{!ac && !prep_ops.empty()};
+                    place(prep_s, pr.prep, has_prep);
+                    place(step_s, pr.step, !ps.step.empty());
+                    for(auto const& s: iter_s) { pr.max_warp_words = std::max(pr.max_warp_words, s.w.size()); }
+                    place(iter_s, pr.iter, true);
+                    pr.warps = G;
+                    pr.n_lane_slots = ps.n_lane;
+                    pr.built = true;
+                };
+
                 if(singular)
                 {
-                    it_sec.clear();
-                    it_sec.push_back(0xffu);  // unknown opcode -> every lane reports PE_ST_SINGULAR
-                    it_sec.push_back(PE_OP_END);
-                    pr.n_lane_slots = ps.n_lane;
+                    for(auto& s: iter_s)
+                    {
+                        s.w.clear();
+                        s.w.push_back(0xffu);  // unknown opcode -> every lane reports PE_ST_SINGULAR
+                    }
                     pr.x_opnd.assign(static_cast<std::size_t>(n), PE_OPND(PE_SP_CONST, 0));
-                    pr.built = true;
+                    finish();
                     return;
                 }
+
+                // --- symbolic structure in row-wise (dot product) form
                 int const w{ps.cplx ? 2 : 1};
-                std::vector<int> eslot(nv.size(), -1), bslot(static_cast<std::size_t>(n), -1);
-                auto slot_of = [&](int id)
-                {
-                    if(eslot[static_cast<std::size_t>(id)] < 0)
-                    {
-                        eslot[static_cast<std::size_t>(id)] = ps.n_lane;
-                        ps.n_lane += w;
-                    }
-                    return PE_OPND(PE_SP_LANE, eslot[static_cast<std::size_t>(id)]);
-                };
-                auto emit_asm = [&](std::uint32_t dst, std::vector<std::uint32_t> const& src)
-                {
-                    it_sec.push_back(PE_OP_ASM | (static_cast<std::uint32_t>(src.size()) << 8));
-                    it_sec.push_back(dst);
-                    for(auto s: src) { it_sec.push_back(s); }
-                };
-                std::vector<char> assembled(static_cast<std::size_t>(n), 0);
-                auto assemble_row = [&](int r)
-                {
-                    if(assembled[static_cast<std::size_t>(r)]) { return; }
-                    assembled[static_cast<std::size_t>(r)] = 1;
-                    auto lo{ps.A.lower_bound({r, std::numeric_limits<int>::min()})};
-                    for(auto it{lo}; it != ps.A.end() && it->first.first == r; ++it)
-                    {
-                        int const id{rows[static_cast<std::size_t>(r)][it->first.second]};
-                        std::uint32_t const d{slot_of(id)};
-                        emit_asm(d, it->second.re);
-                        if(ps.cplx) { emit_asm(d + 1, it->second.im); }
-                    }
-                    bslot[static_cast<std::size_t>(r)] = ps.n_lane;
-                    ps.n_lane += w;
-                    std::uint32_t const bd{PE_OPND(PE_SP_LANE, bslot[static_cast<std::size_t>(r)])};
-                    emit_asm(bd, ps.Z[static_cast<std::size_t>(r)].re);
-                    if(ps.cplx) { emit_asm(bd + 1, ps.Z[static_cast<std::size_t>(r)].im); }
-                };
-                static std::vector<std::uint32_t> const k_none{};
+                std::size_t const n_ent{nv.size()};
+                std::vector<int> pos_r(static_cast<std::size_t>(n), -1), pos_c(static_cast<std::size_t>(n), -1);
                 for(std::size_t k{}; k < steps.size(); ++k)
                 {
-                    auto const& st{steps[k]};
-                    assemble_row(st.r);
-                    for(int i: st.lrows) { assemble_row(i); }
-                    for(std::size_t q{}; q < st.t_ent.size(); ++q)
-                    {
-                        if(st.t_new[q])
-                        {
-                            std::uint32_t const d{slot_of(st.t_ent[q])};
-                            emit_asm(d, k_none);
-                            if(ps.cplx) { emit_asm(d + 1, k_none); }
-                        }
-                    }
-                    it_sec.push_back(PE_OP_PIVOT);
-                    it_sec.push_back(slot_of(st.piv));
-                    bool const rb{step_bnz[k] != 0};
+                    pos_r[static_cast<std::size_t>(steps[k].r)] = static_cast<int>(k);
+                    pos_c[static_cast<std::size_t>(steps[k].c)] = static_cast<int>(k);
+                }
+                struct upd
+                {
+                    int l, u;  // l: L entry id; u: U entry id (matrix entries) or pivot-row index (rhs)
+                    int leaf;  // region of the elimination step that generates this update (-1 = top)
+                };
+                std::vector<std::vector<upd>> pairs(n_ent);                          // entry -> updates, in step order
+                std::vector<std::vector<upd>> ypairs(static_cast<std::size_t>(n));   // row -> rhs updates (u = pivot row)
+                std::vector<char> ynz(static_cast<std::size_t>(n), 0);
+                for(int i{}; i < n; ++i) { ynz[static_cast<std::size_t>(i)] = !(ps.Z[static_cast<std::size_t>(i)].re.empty() && ps.Z[static_cast<std::size_t>(i)].im.empty()); }
+                for(auto const& st: steps)
+                {
+                    std::size_t const nu{st.ucols.size()};
                     for(std::size_t a{}; a < st.lrows.size(); ++a)
                     {
-                        std::uint32_t const cnt{static_cast<std::uint32_t>(st.ucols.size() + (rb ? 1 : 0))};
-                        it_sec.push_back(PE_OP_ELIM | (cnt << 8));
-                        it_sec.push_back(slot_of(st.l_ent[a]));
-                        for(std::size_t b{}; b < st.ucols.size(); ++b)
+                        int const i{st.lrows[a]};
+                        for(std::size_t b{}; b < nu; ++b) { pairs[static_cast<std::size_t>(st.t_ent[a * nu + b])].push_back({st.l_ent[a], st.u_ent[b], st.leaf}); }
+                        if(ynz[static_cast<std::size_t>(st.r)])
                         {
-                            it_sec.push_back(slot_of(st.t_ent[a * st.ucols.size() + b]));
-                            it_sec.push_back(slot_of(st.u_ent[b]));
+                            ypairs[static_cast<std::size_t>(i)].push_back({st.l_ent[a], st.r, st.leaf});
+                            ynz[static_cast<std::size_t>(i)] = 1;
                         }
-                        if(rb)
-                        {
-                            it_sec.push_back(PE_OPND(PE_SP_LANE, bslot[static_cast<std::size_t>(st.lrows[a])]));
-                            it_sec.push_back(PE_OPND(PE_SP_LANE, bslot[static_cast<std::size_t>(st.r)]));
-                        }
-                        pr.n_fma += cnt;
                     }
                 }
-                // solution operands
+
+                // --- slots
+                std::vector<int> eslot(n_ent, -1), yslot(static_cast<std::size_t>(n), -1);
+                auto new_lane = [&]()
+                {
+                    int const s{ps.n_lane};
+                    ps.n_lane += w;
+                    return s;
+                };
+                auto uslot_e = [&](int id) -> std::uint32_t
+                {
+                    if(eslot[static_cast<std::size_t>(id)] < 0) { eslot[static_cast<std::size_t>(id)] = new_lane(); }
+                    return static_cast<std::uint32_t>(eslot[static_cast<std::size_t>(id)]) + lane0;
+                };
+                auto uslot_y = [&](int row) -> std::uint32_t
+                {
+                    if(yslot[static_cast<std::size_t>(row)] < 0) { yslot[static_cast<std::size_t>(row)] = new_lane(); }
+                    return static_cast<std::uint32_t>(yslot[static_cast<std::size_t>(row)]) + lane0;
+                };
+                // solution: real -> the persistent INST slots [0, n); AC -> fresh lane slots (contiguous: the driver
+                // downloads them as one block)
+                std::vector<std::uint32_t> xs(static_cast<std::size_t>(n));
                 pr.x_opnd.resize(static_cast<std::size_t>(n));
-                if(ps.cplx)
+
+                auto emit_dot = [&](stream& S, std::uint32_t dst, std::uint32_t flags, std::uint32_t scale, std::vector<std::uint32_t> const& sre,
+                                    std::vector<std::uint32_t> const& sim, std::vector<std::pair<std::uint32_t, std::uint32_t>> const& pp)
                 {
-                    for(int j{}; j < n; ++j)
+                    std::size_t const max_src{ps.cplx ? 65535u : PE_DOT_MAX_SRC};
+                    std::size_t const max_pair{ps.cplx ? 65535u : PE_DOT_MAX_PAIR};
+                    std::size_t ri{}, ii{}, pi{};
+                    bool first{true};
+                    for(;;)
                     {
-                        pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_LANE, ps.n_lane);
-                        ps.n_lane += 2;
+                        std::size_t const carry{first ? 0u : 1u};
+                        std::size_t const nr{std::min(sre.size() - ri, max_src - carry)};
+                        std::size_t const ni{std::min(sim.size() - ii, max_src - carry)};
+                        std::size_t const np{std::min(pp.size() - pi, max_pair)};
+                        bool const last{ri + nr == sre.size() && ii + ni == sim.size() && pi + np == pp.size()};
+                        std::uint32_t d{dst};
+                        if(!last || !first)
+                        {
+                            if(S.tmp_slot < 0) { S.tmp_slot = new_lane(); }
+                        }
+                        std::uint32_t const tmp{S.tmp_slot < 0 ? 0u : static_cast<std::uint32_t>(S.tmp_slot) + lane0};
+                        if(!last) { d = tmp; }
+                        std::uint32_t const f{last ? flags : 0u};
+                        if(ps.cplx)
+                        {
+                            S.w.push_back(PE_OP_CDOT | (f << 8) | (static_cast<std::uint32_t>(np) << 16));
+                            S.w.push_back(static_cast<std::uint32_t>(nr + carry) | (static_cast<std::uint32_t>(ni + carry) << 16));
+                        }
+                        else
+                        {
+                            S.w.push_back(PE_OP_DOT | (f << 8) | (static_cast<std::uint32_t>(nr + carry) << 16) | (static_cast<std::uint32_t>(np) << 24));
+                        }
+                        S.w.push_back(d);
+                        if(f & PE_F_SCALE) { S.w.push_back(scale); }
+                        if(carry) { S.w.push_back(PE_OPND(PE_SP_U, tmp)); }
+                        for(std::size_t k{}; k < nr; ++k) { S.w.push_back(sre[ri + k]); }
+                        if(ps.cplx)
+                        {
+                            if(carry) { S.w.push_back(PE_OPND(PE_SP_U, tmp + 1)); }
+                            for(std::size_t k{}; k < ni; ++k) { S.w.push_back(sim[ii + k]); }
+                        }
+                        for(std::size_t k{}; k < np; ++k)
+                        {
+                            S.w.push_back(pp[pi + k].first);
+                            S.w.push_back(pp[pi + k].second);
+                        }
+                        ri += nr;
+                        ii += ni;
+                        pi += np;
+                        first = false;
+                        if(last) { break; }
+                    }
+                };
+
+                std::vector<std::uint32_t> sre, sim;
+                std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;
+                auto load_sources = [&](entry const* e)
+                {
+                    sre.clear();
+                    sim.clear();
+                    if(e == nullptr) { return; }
+                    for(auto o: e->re) { sre.push_back(xl(o)); }
+                    for(auto o: e->im) { sim.push_back(xl(o)); }
+                };
+                // Updates generated by leaf steps but landing on an entry owned by a top step are summed by the leaf's own
+                // warp into a contribution slot (the "update matrix" of the multifrontal method); the top step then only
+                // adds the contributions.  contrib[(target, leaf)] -> slot; target = entry id, or n_ent + row for the rhs.
+                std::map<std::pair<std::int64_t, int>, std::uint32_t> contrib;
+                std::vector<std::vector<std::pair<std::int64_t, std::uint32_t>>> leaf_contribs(static_cast<std::size_t>(std::max(n_leaves, 1)));
+                auto load_updates = [&](std::int64_t target, std::vector<upd> const& ups, bool owner_is_top, bool rhs)
+                {
+                    // fills pp with the updates the owner applies itself and appends contribution slots to sre / sim
+                    pp.clear();
+                    std::map<int, std::uint32_t> seen;
+                    for(auto const& u: ups)
+                    {
+                        if(owner_is_top && u.leaf >= 0)
+                        {
+                            if(seen.find(u.leaf) == seen.end())
+                            {
+                                std::uint32_t const slot{static_cast<std::uint32_t>(new_lane()) + lane0};
+                                seen[u.leaf] = slot;
+                                contrib[{target, u.leaf}] = slot;
+                                leaf_contribs[static_cast<std::size_t>(u.leaf)].push_back({target, slot});
+                                sre.push_back(PE_OPND(PE_SP_U, slot));
+                                if(ps.cplx) { sim.push_back(PE_OPND(PE_SP_U, slot + 1)); }
+                            }
+                            continue;
+                        }
+                        pp.push_back({uslot_e(u.l), rhs ? uslot_y(u.u) : uslot_e(u.u)});
+                    }
+                };
+
+                // Crout step k: pivot, row k of U, column k of L (scaled by the fresh pivot reciprocal), rhs entry k
+                auto emit_fwd_step = [&](stream& S, std::size_t k)
+                {
+                    auto const& st{steps[k]};
+                    bool const top{st.leaf < 0};
+                    load_sources(orig[static_cast<std::size_t>(st.piv)]);
+                    load_updates(st.piv, pairs[static_cast<std::size_t>(st.piv)], top, false);
+                    emit_dot(S, uslot_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
+                    for(int e: st.u_ent)
+                    {
+                        load_sources(orig[static_cast<std::size_t>(e)]);
+                        load_updates(e, pairs[static_cast<std::size_t>(e)], top, false);
+                        emit_dot(S, uslot_e(e), 0, 0, sre, sim, pp);
+                    }
+                    for(int e: st.l_ent)
+                    {
+                        load_sources(orig[static_cast<std::size_t>(e)]);
+                        load_updates(e, pairs[static_cast<std::size_t>(e)], top, false);
+                        emit_dot(S, uslot_e(e), PE_F_SCALE, uslot_e(st.piv), sre, sim, pp);
+                    }
+                    if(ynz[static_cast<std::size_t>(st.r)])
+                    {
+                        load_sources(&ps.Z[static_cast<std::size_t>(st.r)]);
+                        load_updates(static_cast<std::int64_t>(n_ent) + st.r, ypairs[static_cast<std::size_t>(st.r)], top, true);
+                        emit_dot(S, uslot_y(st.r), 0, 0, sre, sim, pp);
+                    }
+                };
+                // contribution of one leaf to one top-owned target: - sum of that leaf's updates
+                auto emit_contrib = [&](stream& S, int leaf, std::int64_t target, std::uint32_t slot)
+                {
+                    bool const rhs{target >= static_cast<std::int64_t>(n_ent)};
+                    auto const& ups{rhs ? ypairs[static_cast<std::size_t>(target - static_cast<std::int64_t>(n_ent))] : pairs[static_cast<std::size_t>(target)]};
+                    sre.clear();
+                    sim.clear();
+                    pp.clear();
+                    for(auto const& u: ups)
+                    {
+                        if(u.leaf == leaf) { pp.push_back({uslot_e(u.l), rhs ? uslot_y(u.u) : uslot_e(u.u)}); }
+                    }
+                    emit_dot(S, slot, 0, 0, sre, sim, pp);
+                };
+                auto emit_back_row = [&](stream& S, std::size_t k)
+                {
+                    auto const& st{steps[k]};
+                    sre.clear();
+                    sim.clear();
+                    pp.clear();
+                    if(ynz[static_cast<std::size_t>(st.r)])
+                    {
+                        sre.push_back(PE_OPND(PE_SP_U, uslot_y(st.r)));
+                        if(ps.cplx) { sim.push_back(PE_OPND(PE_SP_U, uslot_y(st.r) + 1)); }
+                    }
+                    for(std::size_t b{}; b < st.ucols.size(); ++b) { pp.push_back({uslot_e(st.u_ent[b]), xs[static_cast<std::size_t>(st.ucols[b])]}); }
+                    std::uint32_t flags{};
+                    if(!sre.empty() || !pp.empty()) { flags |= PE_F_SCALE; }
+                    if(!ps.cplx) { flags |= (st.c >= num.n_nodes) ? PE_F_CHECK_I : PE_F_CHECK_V; }
+                    emit_dot(S, xs[static_cast<std::size_t>(st.c)], flags, uslot_e(st.piv), sre, sim, pp);
+                };
+
+                // --- schedule: leaves -> warps (longest processing time first), top -> warp 0
+                std::vector<std::size_t> leaf_cost(static_cast<std::size_t>(std::max(n_leaves, 1)), 0);
+                for(auto const& st: steps)
+                {
+                    if(st.leaf >= 0) { leaf_cost[static_cast<std::size_t>(st.leaf)] += 4 + st.lrows.size() * (st.ucols.size() + 1) + st.ucols.size(); }
+                }
+                std::vector<int> leaf_warp(static_cast<std::size_t>(std::max(n_leaves, 1)), 0);
+                {
+                    std::vector<int> order(static_cast<std::size_t>(n_leaves));
+                    std::iota(order.begin(), order.end(), 0);
+                    std::sort(order.begin(), order.end(), [&](int a, int b) { return leaf_cost[static_cast<std::size_t>(a)] > leaf_cost[static_cast<std::size_t>(b)]; });
+                    std::vector<std::size_t> load(static_cast<std::size_t>(G), 0);
+                    for(int lf: order)
+                    {
+                        int const g{static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin())};
+                        leaf_warp[static_cast<std::size_t>(lf)] = g;
+                        load[static_cast<std::size_t>(g)] += leaf_cost[static_cast<std::size_t>(lf)];
                     }
                 }
-                else
+                // x slots (AC) are allocated before any row is emitted so that they stay contiguous
+                for(int j{}; j < n; ++j)
                 {
-                    for(int j{}; j < n; ++j) { pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_INST, j); }
-                }
-                for(std::size_t kk{steps.size()}; kk-- > 0;)
-                {
-                    auto const& st{steps[kk]};
-                    std::uint32_t const cnt{static_cast<std::uint32_t>(st.ucols.size())};
-                    bool const is_branch{st.c >= num.n_nodes};
-                    it_sec.push_back(PE_OP_BACK | (cnt << 8) | (is_branch ? 0x80000000u : 0u));
-                    it_sec.push_back(PE_OPND(PE_SP_LANE, bslot[static_cast<std::size_t>(st.r)]));
-                    it_sec.push_back(slot_of(st.piv));
-                    it_sec.push_back(pr.x_opnd[static_cast<std::size_t>(st.c)]);
-                    for(std::size_t b{}; b < st.ucols.size(); ++b)
+                    if(ps.cplx)
                     {
-                        it_sec.push_back(slot_of(st.u_ent[b]));
-                        it_sec.push_back(pr.x_opnd[static_cast<std::size_t>(st.ucols[b])]);
+                        xs[static_cast<std::size_t>(j)] = static_cast<std::uint32_t>(new_lane());
+                        pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_U, xs[static_cast<std::size_t>(j)]);
                     }
-                    pr.n_fma += cnt;
+                    else
+                    {
+                        xs[static_cast<std::size_t>(j)] = static_cast<std::uint32_t>(j);
+                        pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_U, static_cast<std::uint32_t>(j));
+                    }
                 }
-                it_sec.push_back(PE_OP_END);
-                pr.n_lane_slots = ps.n_lane;
-                pr.built = true;
+                auto bar_all = [&]()
+                {
+                    if(G > 1)
+                    {
+                        for(auto& s: iter_s) { s.w.push_back(PE_OP_BAR); }
+                    }
+                };
+                bar_all();  // device evaluation / source values are visible to every warp
+                // The top steps are emitted into a side stream first: that is what discovers which contributions the
+                // leaves owe; the leaf streams (which run earlier on the device) are completed afterwards.
+                stream top_s;
+                top_s.tmp_slot = -1;
+                for(std::size_t k{}; k < steps.size(); ++k)
+                {
+                    if(steps[k].leaf >= 0)
+                    {
+                        emit_fwd_step(iter_s[static_cast<std::size_t>(leaf_warp[static_cast<std::size_t>(steps[k].leaf)])], k);
+                        ++pr.n_leaf_rows;
+                    }
+                }
+                for(std::size_t k{}; k < steps.size(); ++k)
+                {
+                    if(steps[k].leaf < 0)
+                    {
+                        emit_fwd_step(top_s, k);
+                        ++pr.n_top_rows;
+                    }
+                }
+                for(std::size_t k{steps.size()}; k-- > 0;)
+                {
+                    if(steps[k].leaf < 0) { emit_back_row(top_s, k); }
+                }
+                for(int lf{}; lf < n_leaves; ++lf)
+                {
+                    auto& S{iter_s[static_cast<std::size_t>(leaf_warp[static_cast<std::size_t>(lf)])]};
+                    for(auto const& [target, slot]: leaf_contribs[static_cast<std::size_t>(lf)]) { emit_contrib(S, lf, target, slot); }
+                }
+                bar_all();
+                iter_s[0].w.insert(iter_s[0].w.end(), top_s.w.begin(), top_s.w.end());
+                bar_all();
+                for(std::size_t k{steps.size()}; k-- > 0;)
+                {
+                    if(steps[k].leaf >= 0) { emit_back_row(iter_s[static_cast<std::size_t>(leaf_warp[static_cast<std::size_t>(steps[k].leaf)])], k); }
+                }
+                for(auto const& p: pairs) { pr.n_fma += p.size(); }
+                for(auto const& p: ypairs) { pr.n_fma += p.size(); }
+                for(auto const& st: steps) { pr.n_fma += st.ucols.size(); }
+                finish();
             }
         };
     }  // namespace
@@ -999,6 +1462,10 @@ namespace pe_b200
         b.build_layout_and_prep();
         for(int m{}; m < static_cast<int>(prog_mode::COUNT); ++m) { b.build_program(static_cast<prog_mode>(m)); }
         out->dt_slot = b.dt_slot;
+        for(int m{}; m < static_cast<int>(prog_mode::COUNT); ++m)
+        {
+            if(static_cast<prog_mode>(m) != prog_mode::AC) { out->n_real_lane_slots = std::max(out->n_real_lane_slots, out->prog[static_cast<std::size_t>(m)].n_lane_slots); }
+        }
         return out;
     }
 }  // namespace pe_b200

@@ -155,12 +155,16 @@ namespace pe_b200
         bool built{};
         bool cplx{};
         bool structurally_singular{};
-        std::vector<std::uint32_t> step, iter;
+        int warps{1};                     // G: word streams per section = warps per CTA
+        std::vector<std::uint32_t> words;  // word pool of this mode (prep + step + iter streams)
+        pe_b200_section prep{}, step{}, iter{};
         int n_lane_slots{};
         std::vector<std::uint32_t> x_opnd;  // per unknown: where the solution lands (cplx: slot of re, im = +1)
-        int omega_slot{-1};                 // LANE slot holding omega (AC)
-        // statistics for the roofline
+        int omega_slot{-1};                 // U slot holding omega (AC)
+        // statistics for the roofline and the schedule
         std::size_t nnz_a{}, nnz_lu{}, n_fma{};
+        std::size_t n_leaf_rows{}, n_top_rows{}, n_leaves{};
+        std::size_t max_warp_words{};  // longest iter stream (critical path in words)
     };
 
     using sweep_key = std::pair<int, int>;  // (element, attribute)
@@ -169,9 +173,9 @@ namespace pe_b200
     {
         numbering num;
         int n_inst_slots{};
+        int n_real_lane_slots{};  // max over the real-valued modes (their scratch shares the instance workspace)
         std::vector<double> cst;
         int dt_slot{-1};  // CONST slot holding the transient step (patched by the driver before every run)
-        std::vector<std::uint32_t> prep;
         std::map<sweep_key, int> swept_slot;  // INST slot of each per-instance parameter
         std::array<program, static_cast<int>(prog_mode::COUNT)> prog;
         std::string error;
@@ -185,6 +189,8 @@ namespace pe_b200
         double omega0{};  // representative omega for AC pivot selection
         // per-instance parameters: lane-0 value (nominal) for each swept (element, attribute)
         std::map<sweep_key, double> swept_lane0;
+        int warps_real{1};  // requested warps per CTA for the real-valued programs (DC/TR/TROP)
+        int warps_ac{1};    // ... for the AC program
     };
 
     // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot
@@ -228,9 +234,12 @@ namespace pe_b200
         bool device_stale{true};    // host program newer than what the device holds
         bool layout_pending{true};  // INST layout changed since the device workspace was sized
 
-        device_buf d_wi, d_wl, d_cst, d_prep, d_status, d_solves, d_wave, d_probes;
-        std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_step, d_iter;
+        device_buf d_wi, d_wl, d_cst, d_status, d_solves, d_wave, d_probes;
+        std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_words;
         std::array<bool, static_cast<int>(prog_mode::COUNT)> uploaded{};
+        int subtree_warps{0};  // 0 = choose from the lane count; else the requested G (power of two, <= PE_MAX_WARPS)
+        int cc_warps_real{-1}, cc_warps_ac{-1};
+        int pick_warps(std::size_t lanes, int n_unknowns) const;
 
         // results of the last analyze()
         std::size_t last_lanes{};

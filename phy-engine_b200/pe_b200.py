@@ -192,9 +192,13 @@ _product = None
 def product() -> CAbi:
     """Load libphyengine_b200.so once and declare the additive (Part 2/3) entry points."""
     global _product
-    if _product is not None:
-        return _product
-    abi = CAbi(LIB_PATH)
+    if _product is None:
+        _product = bind_full_abi(CAbi(LIB_PATH))
+    return _product
+
+
+def bind_full_abi(abi: CAbi) -> CAbi:
+    """declare Parts 2 and 3 of include/phy_engine_b200.h on a loaded library"""
     lib = abi.lib
     V = ct.c_void_p
     PU32 = ct.POINTER(ct.c_uint32)
@@ -219,8 +223,7 @@ def product() -> CAbi:
     lib.circuit_batch_set_params.argtypes = [V, _SZ, _PSZ, _PSZ, ct.POINTER(ct.c_char_p), ct.c_void_p]
     lib.circuit_batch_solution_soa.argtypes = [V, ct.c_void_p]
     lib.circuit_batch_set_probes.argtypes = [V, _PSZ, _SZ]
-    if hasattr(lib, "circuit_batch_set_subtree_warps"):
-        lib.circuit_batch_set_subtree_warps.argtypes = [V, ct.c_int]
+    lib.circuit_batch_set_subtree_warps.argtypes = [V, ct.c_int]
     for f in ("circuit_batch_prepare", "circuit_batch_reset_state", "circuit_batch_analyze", "circuit_batch_compile_host"):
         getattr(lib, f).argtypes = [V]
     lib.circuit_batch_lanes.restype = _SZ
@@ -241,8 +244,8 @@ def product() -> CAbi:
     lib.circuit_batch_param_device_ptr.argtypes = [V, _SZ, _SZ, ct.c_char_p, _SZ, ct.POINTER(_PD)]
     lib.circuit_batch_solution_device_ptr.argtypes = [V, ct.POINTER(_PD), _PSZ]
     lib.circuit_batch_program_words.restype = _SZ
-    lib.circuit_batch_program_words.argtypes = [V, ct.c_int, ct.c_int]
-    lib.circuit_batch_program_copy.argtypes = [V, ct.c_int, ct.c_int, PU32]
+    lib.circuit_batch_program_words.argtypes = [V, ct.c_int]
+    lib.circuit_batch_program_copy.argtypes = [V, ct.c_int, PU32]
     lib.circuit_batch_const_count.restype = _SZ
     lib.circuit_batch_const_count.argtypes = [V]
     lib.circuit_batch_const_copy.argtypes = [V, _PD]
@@ -255,7 +258,6 @@ def product() -> CAbi:
     lib.phy_engine_b200_timing.restype = None
     lib.phy_engine_b200_timing.argtypes = [ct.c_int]
     lib.phy_engine_b200_kernel_ms.restype = ct.c_double
-    _product = abi
     return abi
 
 
@@ -279,8 +281,8 @@ def kernel_ms() -> float:
 class Circuit(CircuitBase):
     """Handle of the B200 library (circuit_* of include/phy_engine_b200.h)."""
 
-    def __init__(self, nl: Netlist):
-        super().__init__(product(), nl)
+    def __init__(self, nl: Netlist, abi: CAbi | None = None):
+        super().__init__(abi or product(), nl)
 
     def set_env(self, V_eps_max=0.0, V_epsr_max=0.0, I_eps_max=0.0, I_epsr_max=0.0, g_min=0.0, r_open=0.0, temperature=27.0, norm_temperature=27.0):
         a = np.array([V_eps_max, V_epsr_max, I_eps_max, I_epsr_max, g_min, r_open, temperature, norm_temperature], dtype=np.float64)
@@ -461,10 +463,10 @@ class Batch:
         return (ct.cast(p, ct.c_void_p).value or 0), s.value
 
     # ---- introspection of the symbolic phase (host only) ----
-    def program(self, mode: int, section: int) -> np.ndarray:
-        n = int(self.lib.circuit_batch_program_words(self.h, mode, section))
+    def program(self, mode: int) -> np.ndarray:
+        n = int(self.lib.circuit_batch_program_words(self.h, mode))
         out = np.zeros(max(n, 1), dtype=np.uint32)
-        self._rc(self.lib.circuit_batch_program_copy(self.h, mode, section, _p(out, ct.POINTER(ct.c_uint32))), "circuit_batch_program_copy")
+        self._rc(self.lib.circuit_batch_program_copy(self.h, mode, _p(out, ct.POINTER(ct.c_uint32))), "circuit_batch_program_copy")
         return out[:n]
 
     def constants(self) -> np.ndarray:
@@ -474,7 +476,11 @@ class Batch:
         return out[:n]
 
     def program_info(self, mode: int) -> dict:
-        info = np.zeros(8, dtype=np.int64)
+        info = np.zeros(64, dtype=np.int64)
         self._rc(self.lib.circuit_batch_program_info(self.h, mode, _p(info, ct.POINTER(ct.c_int64))), "circuit_batch_program_info")
-        keys = ("cplx", "structurally_singular", "n_lane_slots", "omega_slot", "n_inst_slots", "dt_slot", "x_slot0", "n_unknowns")
-        return dict(zip(keys, (int(v) for v in info)))
+        keys = ("cplx", "structurally_singular", "n_lane_slots", "omega_slot", "n_inst_slots", "dt_slot", "x_slot0", "n_unknowns", "warps",
+                "n_real_lane_slots", "n_leaves", "n_leaf_rows", "n_top_rows", "max_warp_words", "nnz_a", "nnz_lu")
+        d = dict(zip(keys, (int(v) for v in info[:16])))
+        for s, name in enumerate(("prep", "step", "iter")):
+            d[name] = [int(v) for v in info[16 + 16 * s: 32 + 16 * s]]
+        return d

@@ -1,4 +1,8 @@
-"""GPU parity: the CUDA path, called through the C ABI, against the compiled reference on the same netlists.
+"""Parity: the solve path, called through the C ABI, against the compiled reference on the same netlists.
+
+backend "gpu" (-m gpu, on the B200): libphyengine_b200.so, i.e. the CUDA kernels.  These are the parity tests proper.
+backend "emu" (CPU suite): tests/emu/libpe_emu.so = the same host side with the kernel's interpreter replayed on the host
+(test infrastructure; checks the symbolic phase and the warp-stream schedules, including a race detector).
 
 Tolerance (BASELINE.json north_star): node voltages and branch currents within 1e-9 relative / 1e-12 absolute in
 FP64, identical Newton iteration counts (solve_once-equivalents per analyze()).
@@ -10,9 +14,22 @@ import pe_b200 as pe
 import refapi
 import workloads as wl
 
-pytestmark = pytest.mark.gpu
-
 RTOL, ATOL = 1e-9, 1e-12
+
+
+@pytest.fixture(params=[pytest.param("gpu", marks=pytest.mark.gpu), "emu"])
+def abi(request):
+    if request.param == "gpu":
+        return pe.product()
+    import emuapi
+
+    return emuapi.emulator()
+
+
+@pytest.fixture(params=[0, 4])
+def warps(request):
+    """0 = automatic warp count, 4 = force the sub-tree parallel schedule where the circuit is large enough"""
+    return request.param
 
 
 def assert_close(got, want, what=""):
@@ -39,8 +56,8 @@ def ref_solo(nl, at, ref, **kw):
     return c, ok, n
 
 
-def gpu_solo(nl, at, **kw):
-    c = pe.Circuit(nl)
+def gpu_solo(nl, at, abi, **kw):
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(at)
     if "tr" in kw:
         c.set_tr(*kw["tr"])
@@ -52,11 +69,11 @@ def gpu_solo(nl, at, **kw):
     return c, ok
 
 
-def test_rc_step_tr_matches_reference(ref):
+def test_rc_step_tr_matches_reference(ref, abi):
     # test/0005.models/rc_step_tr.cpp: 1 V, 1 kOhm, 1 nF, dt 1e-8, 100 steps; oracle vout = 0.63027499952138644
     nl, info = wl.rc_ladder(1)
     rc, rok, rn = ref_solo(nl, pe.TR, ref, tr=(1e-8, 1e-6))
-    gc, gok = gpu_solo(nl, pe.TR, tr=(1e-8, 1e-6))
+    gc, gok = gpu_solo(nl, pe.TR, abi, tr=(1e-8, 1e-6))
     assert rok and gok, gc.abi.last_error()
     assert rn == 100
     assert abs(rc.solution()[1].real - 0.63027499952138644) < 1e-15
@@ -69,10 +86,10 @@ def test_rc_step_tr_matches_reference(ref):
     assert_close(gi, ri, "sample currents")
 
 
-def test_tr_resume_continues_like_reference(ref):
+def test_tr_resume_continues_like_reference(ref, abi):
     nl, _ = wl.rc_ladder(3)
     rc, _, _ = ref_solo(nl, pe.TR, ref, tr=(1e-8, 3e-7))
-    gc, gok = gpu_solo(nl, pe.TR, tr=(1e-8, 3e-7))
+    gc, gok = gpu_solo(nl, pe.TR, abi, tr=(1e-8, 3e-7))
     assert gok
     assert_close(gc.solution(), rc.solution(), "first analyze")
     for _ in range(2):  # analyze() again continues the transient (circuit.h:242)
@@ -81,7 +98,7 @@ def test_tr_resume_continues_like_reference(ref):
 
 
 @pytest.mark.parametrize("n_sections,n_inst", [(8, 33), (50, 64), (200, 40)])
-def test_rc_ladder_batch_sweep(ref, n_sections, n_inst):
+def test_rc_ladder_batch_sweep(ref, abi, warps, n_sections, n_inst):
     nl, info = wl.rc_ladder(n_sections)
     rng = np.random.default_rng(7)
     over = []
@@ -90,24 +107,27 @@ def test_rc_ladder_batch_sweep(ref, n_sections, n_inst):
     for e in info["C"]:
         over.append((e, "c", wl.sweep_values(rng, 1e-9, n_inst)))
     want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-8, t_stop=2e-7)
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.TR)
     c.set_tr(1e-8, 2e-7)
     b = c.batch(n_inst)
+    b.set_subtree_warps(warps)
     for e, name, v in over:
         b.set_param(e, name, v)
     assert b.analyze(), c.abi.last_error()
+    if warps and n_sections >= 200:
+        assert b.program_info(pe.MODE_TR)["warps"] == warps
     assert (want["ok"] == 1).all()
     assert_close(b.solution(), want["x"].real, "ladder state")
     assert b.total_solves == int(want["solves"].sum())
     assert (b.status() == 0).all()
 
 
-def test_diode_op_iteration_trajectory(ref):
+def test_diode_op_iteration_trajectory(ref, abi):
     # test/0011.nonlinear/op_pn_junction.cpp; SURVEY.md 8(c): 7 iterations, Vd = 0.62944165509863270
     nl, info = wl.diode_resistor()
     rc, rok, rn = ref_solo(nl, pe.OP, ref)
-    gc, gok = gpu_solo(nl, pe.OP)
+    gc, gok = gpu_solo(nl, pe.OP, abi)
     assert rok and gok
     assert rn == 7
     assert abs(rc.solution()[1].real - 0.62944165509863270) < 1e-15
@@ -118,7 +138,7 @@ def test_diode_op_iteration_trajectory(ref):
     assert_close(b.solution()[0], rc.solution().real, "diode op (batch of 1)")
 
 
-def test_diode_monte_carlo(ref):
+def test_diode_monte_carlo(ref, abi):
     n_inst = 257
     nl, info = wl.diode_resistor(n_diodes=2, v=3.0)
     rng = np.random.default_rng(11)
@@ -127,7 +147,7 @@ def test_diode_monte_carlo(ref):
         over.append((d, "Is", 1e-14 * np.exp(0.3 * rng.standard_normal(n_inst))))
         over.append((d, "N", rng.uniform(1.0, 1.2, n_inst)))
     want = refapi.run_batch(nl, pe.OP, n_inst, over)
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.OP)
     b = c.batch(n_inst)
     for e, name, v in over:
@@ -137,13 +157,13 @@ def test_diode_monte_carlo(ref):
     assert_close(b.solution(), want["x"].real, "diode MC")
 
 
-def test_diode_ladder_newton(ref):
+def test_diode_ladder_newton(ref, abi):
     n_inst = 64
     nl, info = wl.diode_ladder(16)
     rng = np.random.default_rng(5)
     over = [(e, "r", wl.sweep_values(rng, 1e3, n_inst, 0.95, 1.05)) for e in info["R"]]
     want = refapi.run_batch(nl, pe.OP, n_inst, over)
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.OP)
     b = c.batch(n_inst)
     for e, name, v in over:
@@ -153,7 +173,7 @@ def test_diode_ladder_newton(ref):
     assert_close(b.solution(), want["x"].real, "diode ladder")
 
 
-def test_bjt_and_mos_op(ref):
+def test_bjt_and_mos_op(ref, abi):
     for nl, info, sweeps in (
         (*wl.npn_stage(), [("Vb", "V", 0.55, 0.70), ("R", "r", 900.0, 1100.0)]),
         (*wl.cmos_stage(), [("Vg", "V", 1.2, 3.0), ("R", "r", 900.0, 1100.0)]),
@@ -163,7 +183,7 @@ def test_bjt_and_mos_op(ref):
         rng = np.random.default_rng(3)
         over = [(info[k], name, rng.uniform(lo, hi, n_inst)) for k, name, lo, hi in sweeps]
         want = refapi.run_batch(nl, pe.OP, n_inst, over)
-        c = pe.Circuit(nl)
+        c = pe.Circuit(nl, abi)
         c.set_analyze_type(pe.OP)
         b = c.batch(n_inst)
         for e, name, v in over:
@@ -175,12 +195,12 @@ def test_bjt_and_mos_op(ref):
         assert_close(b.solution()[good], want["x"].real[good], "transistor stage")
 
 
-def test_failure_parity_resistor_biased_npn(ref):
+def test_failure_parity_resistor_biased_npn(ref, abi):
     # the reference itself does not converge here (64 iterations, analyze() false)
     nl, info = wl.npn_resistor_biased()
     rc, rok, rn = ref_solo(nl, pe.OP, ref)
     assert not rok and rn == 64
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.OP)
     b = c.batch(3)
     assert not b.analyze()
@@ -188,7 +208,7 @@ def test_failure_parity_resistor_biased_npn(ref):
     assert (b.newton_iters() == 64).all()
 
 
-def test_ac_single_point(ref):
+def test_ac_single_point(ref, abi):
     # test/0012.ac/ac_omega.cpp shape: R-C low pass at the corner frequency -> (0.5, -0.5)
     nl = pe.Netlist()
     g = nl.ground()
@@ -200,22 +220,23 @@ def test_ac_single_point(ref):
     nl.wire(r, 1, cc, 0)
     nl.wire(cc, 1, g, 0)
     rc, rok, _ = ref_solo(nl, pe.AC, ref, omega=1e3)
-    gc, gok = gpu_solo(nl, pe.AC, omega=1e3)
+    gc, gok = gpu_solo(nl, pe.AC, abi, omega=1e3)
     assert rok and gok
     assert_close(gc.solution(), rc.solution(), "ac point")
     assert abs(rc.solution()[1] - (0.5 - 0.5j)) < 1e-12
 
 
 @pytest.mark.parametrize("n_sections,points", [(2, 17), (8, 200), (64, 64)])
-def test_ac_log_sweep_rlc(ref, n_sections, points):
+def test_ac_log_sweep_rlc(ref, abi, warps, n_sections, points):
     nl, info = wl.rlc_ladder(n_sections)
     sweep = (pe.SWEEP_LOG, 1e3, 1e10, points)
     rc, rok, rn = ref_solo(nl, pe.AC, ref, sweep=sweep)
     assert rok and rn == points
     om, xr = rc.ac_results()
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.AC)
     b = c.batch(1)
+    b.set_subtree_warps(warps)
     b.set_ac_sweep(*sweep)
     assert b.analyze(), c.abi.last_error()
     assert (b.ac_omegas() == om).all()  # cumulative-product omegas are bit-identical
@@ -223,13 +244,13 @@ def test_ac_log_sweep_rlc(ref, n_sections, points):
     assert b.total_solves == points
 
 
-def test_ac_sweep_with_instances(ref):
+def test_ac_sweep_with_instances(ref, abi):
     n_inst, points = 5, 40
     nl, info = wl.rlc_ladder(4)
     rng = np.random.default_rng(2)
     over = [(e, "r", wl.sweep_values(rng, 10.0, n_inst)) for e in info["R"]] + [(e, "L", wl.sweep_values(rng, 1e-6, n_inst)) for e in info["L"]]
     want = refapi.run_batch(nl, pe.AC, n_inst, over, ac=(pe.SWEEP_LINEAR, 1e5, 1e8, points))
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.AC)
     b = c.batch(n_inst)
     for e, name, v in over:
@@ -239,22 +260,22 @@ def test_ac_sweep_with_instances(ref):
     assert_close(b.ac_solution(), want["x"], "ac sweep x instances")
 
 
-def test_random_links_dc(ref):
+def test_random_links_dc(ref, abi):
     # test/0013.cuda/cuda_random_links_correctness.cu shape (chain + random 1 kOhm chords), scaled down
     nl, info = wl.random_links(256, 64, seed=3)
     rc, rok, _ = ref_solo(nl, pe.DC, ref)
-    gc, gok = gpu_solo(nl, pe.DC)
+    gc, gok = gpu_solo(nl, pe.DC, abi)
     assert rok and gok
     assert_close(gc.solution(), rc.solution(), "random links")
 
 
-def test_diode_tr_with_transit_time(ref):
+def test_diode_tr_with_transit_time(ref, abi):
     nl, info = wl.diode_resistor(v=2.0)
     n_inst = 16
     rng = np.random.default_rng(9)
     over = [(info["D"][0], "tt", rng.uniform(1e-9, 1e-8, n_inst)), (info["R"], "r", wl.sweep_values(rng, 1e3, n_inst))]
     want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-9, t_stop=2e-8)
-    c = pe.Circuit(nl)
+    c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.TR)
     c.set_tr(1e-9, 2e-8)
     b = c.batch(n_inst)
@@ -265,9 +286,18 @@ def test_diode_tr_with_transit_time(ref):
     assert_close(b.solution(), want["x"].real, "diode TR")
 
 
+@pytest.mark.gpu
 def test_no_cpu_fallback_and_native_launches():
     n0 = pe.launch_count()
     nl, _ = wl.rc_ladder(2)
-    c, ok = gpu_solo(nl, pe.DC)
+    c, ok = gpu_solo(nl, pe.DC, pe.product())
     assert ok
     assert pe.launch_count() > n0  # the answer came from our kernels
+
+
+def test_emulator_saw_no_races_or_unbalanced_barriers():
+    """runs last in this file: the warp streams of every program replayed above were race-free between barriers"""
+    import emuapi
+
+    assert emuapi.races() == 0
+    assert emuapi.unbalanced() == 0
