@@ -151,6 +151,13 @@ extern "C"
     /* warps per CTA cooperating on each block of 32 instances (sub-tree parallel LU): 0 = automatic from the lane count,
      * else a power of two <= 16 */
     int circuit_batch_set_subtree_warps(void* batch, int warps);
+    /* resident (shared-memory) solve path: `streams` word streams per instance (-1 = never use it, 0 = automatic, else a
+     * power of two), `instances_per_cta` (0 = automatic, else a power of two <= 32), `instances_per_thread` (0 = automatic,
+     * 1 or 2).  A circuit whose workspace does not fit one CTA's shared memory runs on the HBM-streaming kernel. */
+    int circuit_batch_set_resident(void* batch, int streams, int instances_per_cta, int instances_per_thread);
+    /* info[12] = resident, streams, shared-memory slots per instance, I, J (0 = does not fit), io entries,
+     * last launch S / I / J (0 = the HBM-streaming kernel ran), phases of the iter section, words, longest warp stream */
+    int circuit_batch_resident_info(void* batch, int mode, int64_t* info);
     /* per-instance values of one model attribute; values[n_instances] in the attribute's public unit */
     int circuit_batch_set_param(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values);
     /* many parameters in one call: values[n_params][n_instances].  Once the batch is prepared and every parameter
@@ -197,6 +204,9 @@ extern "C"
     long long circuit_batch_swept_slot(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size);
     int circuit_batch_swept_values(void* batch, long long slot, double* out);
 
+    /* process-wide defaults every batch created afterwards (including the one behind circuit_analyze) starts from:
+     * the arguments of circuit_batch_set_resident and circuit_batch_set_subtree_warps */
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps);
     int phy_engine_b200_device_count(void);
     uint64_t phy_engine_b200_launch_count(void);
     /* device-side timing of the solve kernels (CUDA events on the launching stream): enable, then read-and-reset the

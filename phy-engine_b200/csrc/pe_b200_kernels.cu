@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "pe_b200_interp.h"
+#include "pe_b200_rinterp.h"
 
 namespace
 {
@@ -116,6 +117,193 @@ namespace
         }
     }
 
+    // ---- resident kernel ---------------------------------------------------------------------------
+    // CTA = S streams x I instances, workspace ws[slot][I] in dynamic shared memory for the whole launch.  Thread
+    // (stream, ig) executes the vector ops of its warp for the J instances [ig * J, ig * J + J) of the CTA.
+    template <int J, int MAXT>
+    __global__ void __launch_bounds__(MAXT, 1) pe_b200_resident_kernel(pe_b200_rrun const r)
+    {
+        extern __shared__ __align__(16) double ws[];
+        __shared__ uint32_t s_flags[3][32];
+
+        using namespace pe_rinterp;
+        uint32_t const I = (uint32_t)r.I, IG = I / J, S = (uint32_t)r.S;
+        uint32_t const tid = threadIdx.x;
+        uint32_t const ig = tid % IG, stream = tid / IG;
+        uint32_t const warp = tid >> 5, n_warps = blockDim.x >> 5;
+        int64_t const lane0 = (int64_t)blockIdx.x * I + ig * J;
+
+        rctx c;
+        c.ws = ws + ig * J;
+        c.I = I;
+        c.S = S;
+        c.C = 32u / IG;
+        c.col = (tid & 31u) / IG;
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+
+        bool real_lane[J], counted[J], ok[J];
+        int32_t status[J];
+        uint32_t solves[J];
+#pragma unroll
+        for(int j = 0; j < J; ++j)
+        {
+            real_lane[j] = lane0 + j < r.n_lanes;
+            status[j] = real_lane[j] ? r.status[lane0 + j] : (int32_t)PE_ST_SINGULAR;
+            counted[j] = real_lane[j] && status[j] == PE_ST_OK;
+            ok[j] = counted[j];
+            solves[j] = 0;
+        }
+
+        // ---- load: persistent values, broadcast constants, per-instance values seen from a frequency-point lane
+        for(uint32_t e = stream; e < (uint32_t)r.n_io; e += S)
+        {
+            pe_b200_io const io = r.io[e];
+            uint32_t const fl = io.slot_kind >> 20;
+            if(!(fl & PE_IO_LOAD)) { continue; }
+            uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
+            double* dst = c.ws + (io.slot_kind & 0xffffu) * I;
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                int64_t const lane = lane0 + j;
+                double v;
+                if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+                else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + lane]; }
+                else { v = r.wx[(int64_t)io.src * r.LSx + (real_lane[j] ? lane / r.ppi : 0)]; }
+                dst[j] = v;
+            }
+        }
+        if(tid < 96) { (&s_flags[0][0])[tid] = 0u; }
+        __syncthreads();
+
+        double t = r.t0;
+        auto run_section = [&](int sec, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
+        {
+            uint32_t const off = __ldg(r.sec_off + sec * n_warps + warp);
+            uint32_t const* pc = r.words + off;
+            for(;;)
+            {
+                uint32_t len;
+                int const k = rvop<J>(pc, c, t, tol, en, check, nconv, fail, len);
+                if(k == V_END || k == V_BAD) { break; }
+                if(k == V_BAR) { __syncthreads(); }
+                pc += len;
+            }
+            __syncthreads();  // results of this section are visible to every stream of the CTA
+        };
+
+        int fi = 0;
+        if(r.has_prep)
+        {
+            bool a[J], b[J];
+#pragma unroll
+            for(int j = 0; j < J; ++j) { a[j] = b[j] = false; }
+            run_section(0, ok, false, a, b);
+        }
+        for(int32_t s = 0; s < r.n_steps; ++s)
+        {
+            if(r.time_stepping)
+            {
+                // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
+                if(r.has_step)
+                {
+                    bool a[J], b[J];
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { a[j] = b[j] = false; }
+                    run_section(1, ok, false, a, b);
+                }
+                t = t + r.dt;
+            }
+            bool done[J];
+#pragma unroll
+            for(int j = 0; j < J; ++j) { done[j] = !ok[j]; }
+            int32_t it = 0;
+            for(;;)
+            {
+                int const fn = fi == 2 ? 0 : fi + 1;
+                if(stream == 0)
+                {
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { s_flags[fn][ig * J + j] = 0u; }
+                }
+                bool nconv[J], fail[J], en[J];
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    nconv[j] = fail[j] = false;
+                    en[j] = !done[j];
+                }
+                run_section(2, en, r.nonlinear != 0, nconv, fail);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    if(nconv[j] || fail[j]) { atomicOr(&s_flags[fi][ig * J + j], (nconv[j] ? 1u : 0u) | (fail[j] ? 2u : 0u)); }
+                }
+                __syncthreads();
+                bool all_done = true;
+                ++it;
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    uint32_t const f = s_flags[fi][ig * J + j];
+                    if(!done[j])
+                    {
+                        ++solves[j];
+                        if(f & 2u)
+                        {
+                            status[j] = PE_ST_SINGULAR;
+                            ok[j] = false;
+                            done[j] = true;
+                        }
+                        else if(!r.nonlinear || !(f & 1u)) { done[j] = true; }
+                        else if(it >= r.max_iter)
+                        {
+                            status[j] = PE_ST_NO_CONVERGENCE;
+                            ok[j] = false;
+                            done[j] = true;
+                        }
+                    }
+                    all_done = all_done && done[j];
+                }
+                fi = fn;
+                if(__syncthreads_and(all_done ? 1 : 0)) { break; }
+            }
+            if(r.wave != nullptr && stream == 0)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    if(!ok[j]) { continue; }
+                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane0 + j] = c.ws[__ldg(r.probes + p) * I + j]; }
+                }
+            }
+        }
+        // ---- store the mutable persistent values back
+        for(uint32_t e = stream; e < (uint32_t)r.n_io; e += S)
+        {
+            pe_b200_io const io = r.io[e];
+            if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
+            double const* src = c.ws + (io.slot_kind & 0xffffu) * I;
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                if(counted[j]) { r.wu[(int64_t)io.src * r.LSu + lane0 + j] = src[j]; }
+            }
+        }
+        if(stream == 0)
+        {
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                if(counted[j])
+                {
+                    r.status[lane0 + j] = status[j];
+                    r.solves[lane0 + j] += solves[j];
+                }
+            }
+        }
+    }
+
     thread_local char g_err[256] = "";
     std::atomic<uint64_t> g_launches{0};
 
@@ -199,6 +387,50 @@ extern "C"
         }
         g_launches.fetch_add(1);
         return chk(cudaGetLastError(), "pe_b200_solve_kernel launch");
+    }
+
+    size_t pe_b200_resident_smem_limit(void)
+    {
+        int dev = 0, v = 0;
+        if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            return 0;
+        }
+        return v > 1024 ? (size_t)v - 1024 : 0;  // static shared memory of the kernel (flags) comes out of the same budget
+    }
+
+    int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream)
+    {
+        if(run == nullptr || run->n_lanes <= 0) { return 0; }
+        int const I = run->I, J = run->J, S = run->S;
+        if(I < 1 || I > 32 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024)
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
+            return 1;
+        }
+        int const block = S * (I / J);
+        int const grid = (run->n_lanes + I - 1) / I;
+        size_t const smem = (size_t)run->n_slots * (size_t)I * sizeof(double);
+        // two register budgets: CTAs of up to 512 threads get 128 registers per thread, larger ones 64
+        auto kern = block <= 512 ? (J == 2 ? pe_b200_resident_kernel<2, 512> : pe_b200_resident_kernel<1, 512>)
+                                 : (J == 2 ? pe_b200_resident_kernel<2, 1024> : pe_b200_resident_kernel<1, 1024>);
+        if(chk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") != 0) { return 1; }
+        cudaEvent_t e0{}, e1{};
+        if(g_timing)
+        {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, (cudaStream_t)stream);
+        }
+        kern<<<grid, block, smem, (cudaStream_t)stream>>>(*run);
+        if(g_timing)
+        {
+            cudaEventRecord(e1, (cudaStream_t)stream);
+            g_events.emplace_back(e0, e1);
+        }
+        g_launches.fetch_add(1);
+        return chk(cudaGetLastError(), "pe_b200_resident_kernel launch");
     }
 
     void pe_b200_timing_enable(int on) { g_timing = on != 0; }

@@ -145,6 +145,83 @@ extern "C"
         double v_abstol, v_reltol, i_abstol, i_reltol;
     } pe_b200_run;
 
+    // ================================================================================================================
+    // RESIDENT programs: the whole per-instance workspace of a CTA lives in shared memory for the whole
+    // launch (all time steps / Newton iterations / the frequency point), HBM is touched only by the load of the
+    // persistent values at kernel entry and the store of the mutable ones at exit.
+    //
+    // CTA = S streams x I instances.  Thread (s, ig) runs word stream s for the J = I / IG instances
+    // [ig * J, ig * J + J) of the CTA (tid = s * IG + ig).  A warp therefore carries C = 32 / IG consecutive streams;
+    // its program is a sequence of VECTOR OPS: one warp-uniform header followed by rows of C words, column c belonging
+    // to stream (warp * C + c).  All C streams execute the same opcode with the same (padded) trip counts, so there
+    // is no divergence; every operand is a 15-bit shared-memory slot (+ negate bit), the value of slot q for instance
+    // i of the CTA lives at ws[q * I + i].  Slots are allocated "interleaved": the k-th value owned by stream s is
+    // slot k * S + s, so the threads of a warp touching "their" k-th value hit consecutive addresses (no bank
+    // conflicts), and a complex value (re at q) has its imaginary part at q + S.
+    //
+    //   header            op | a << 8 | b << 16 | c << 24
+    //   END / BAR         as above (BAR = __syncthreads of the CTA; every warp holds the same number per section)
+    //   DOT               a = rows of packed sources, b = rows of pairs, c = union of the streams' flags
+    //                     rows: [ctl] [scale, iff c & F_SCALE] [src x a] [pair x b]
+    //   CDOT              same, a = rows of packed re-sources; a second uniform header word holds the im-source rows
+    //                     rows: [ctl] [scale] [src_re x a] [src_im x a2] [pair x b]
+    //   value ops         a = number of operand rows (one operand per row, the same order as the v2 encoding)
+    //   ctl word          dst | ACTIVE << 15 | flags << 16      (value ops: operand 0 | ACTIVE << 16)
+    //   src word          s0 | neg0 << 15 | s1 << 16 | neg1 << 31      (padding: the -0.0 slot)
+    //   pair word         a | b << 16                                   (padding: (zero, zero))
+#define PE_R_SLOT(w) ((w) & 0x7fffu)
+#define PE_R_NEG 0x8000u
+#define PE_R_ACTIVE 0x8000u       /* in a DOT ctl word */
+#define PE_R_VACTIVE 0x10000u     /* in row 0 of a value op */
+#define PE_R_MAX_SLOTS 32768
+#define PE_R_MAX_WARPS 32
+
+    // load / store table of a resident program: which shared-memory slots are filled from (and written back to) HBM
+    enum
+    {
+        PE_IO_CONST = 0,  // cst[src]
+        PE_IO_U = 1,      // wu[src * LSu + lane]
+        PE_IO_INSTX = 2,  // wx[src * LSx + lane / ppi]
+    };
+#define PE_IO_LOAD 1u
+#define PE_IO_STORE 2u
+    typedef struct pe_b200_io
+    {
+        uint32_t slot_kind;  // slot | kind << 16 | (LOAD | STORE) << 20
+        uint32_t src;
+    } pe_b200_io;
+
+    typedef struct pe_b200_rrun
+    {
+        uint32_t const* words;
+        uint32_t const* sec_off;  // device: [3][n_warps] offsets of the prep / step / iter stream of each warp (PE_NO_SECTION)
+        pe_b200_io const* io;
+        int32_t n_io;
+        int32_t has_prep, has_step;
+        double const* cst;
+        double* wu;
+        double* wx;
+        int32_t* status;
+        uint32_t* solves;
+        double* wave;
+        uint32_t const* probes;  // [n_probe] shared-memory slots
+        int64_t LSu, LSx;
+        int32_t n_lanes;
+        int32_t ppi;
+        int32_t S;        // streams per instance
+        int32_t I;        // instances per CTA
+        int32_t J;        // instances per thread (1 or 2; I % J == 0)
+        int32_t n_slots;  // shared-memory slots per instance (a multiple of S)
+        int32_t cplx;
+        int32_t nonlinear;
+        int32_t max_iter;
+        int32_t n_steps;
+        int32_t n_probe;
+        int32_t time_stepping;
+        double t0, dt;
+        double v_abstol, v_reltol, i_abstol, i_reltol;
+    } pe_b200_rrun;
+
     // ---- device seam (implemented in pe_b200_kernels.cu; everything CUDA stays behind these) ---------------------
     int pe_b200_dev_count(void);
     int pe_b200_dev_set(int device);
@@ -158,6 +235,9 @@ extern "C"
     int pe_b200_dev_h2d_2d(void* dst, size_t dpitch, void const* src, size_t spitch, size_t width, size_t height, void* stream);
     int pe_b200_dev_d2h_2d(void* dst, size_t dpitch, void const* src, size_t spitch, size_t width, size_t height, void* stream);
     int pe_b200_launch(pe_b200_run const* run, void* stream);
+    int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream);
+    // largest dynamic shared memory (bytes) one CTA of the resident kernel may use on the current device
+    size_t pe_b200_resident_smem_limit(void);
     char const* pe_b200_dev_last_error(void);
     // number of kernels this library has launched so far in this process (bench.py's gpu_launches evidence)
     uint64_t pe_b200_launch_count(void);

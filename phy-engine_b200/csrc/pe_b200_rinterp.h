@@ -1,0 +1,463 @@
+// pe_b200_rinterp.h — per-thread executor of the vector ops of a RESIDENT batch program (pe_b200_program.h).
+//
+// Included by pe_b200_kernels.cu (body of the sm_100a resident kernel: thread = one word stream x J instances of the
+// CTA, every operand a shared-memory slot) and by the test-only emulator tests/emu/emu.cpp, which replays the same
+// vector ops thread by thread on host memory.  Replaces, per instance, solve_once (circuit.h:987-1527): stamping,
+// Eigen::SparseLU factorize + solve and the Newton test of circult::solve (circuit.h:923-948).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "pe_b200_interp.h"
+
+namespace pe_rinterp
+{
+    using pe_interp::tol_t;
+
+    struct rctx
+    {
+        double* ws;    // shared-memory workspace of the CTA, already offset to this thread's first instance
+        uint32_t I;    // instances per CTA = distance (in doubles) between consecutive slots
+        uint32_t S;    // streams per instance = distance (in slots) between re and im of a complex value
+        uint32_t C;    // streams (word columns) per warp
+        uint32_t col;  // this thread's column
+    };
+
+    template <int J>
+    struct vd
+    {
+        double v[J];
+    };
+
+    template <int J>
+    PE_HD double* slot_ptr(rctx const& c, uint32_t slot)
+    {
+        return c.ws + slot * c.I;
+    }
+
+    template <int J>
+    PE_HD vd<J> ldv(rctx const& c, uint32_t slot)
+    {
+        vd<J> r;
+        double const* p = slot_ptr<J>(c, slot);
+#if defined(__CUDA_ARCH__)
+        if constexpr(J == 2)
+        {
+            double2 const t = *reinterpret_cast<double2 const*>(p);
+            r.v[0] = t.x;
+            r.v[1] = t.y;
+            return r;
+        }
+#endif
+        for(int j = 0; j < J; ++j)
+        {
+            PE_TRACE_LD(p + j);
+            r.v[j] = p[j];
+        }
+        return r;
+    }
+
+    // operand word: slot | neg << 15
+    template <int J>
+    PE_HD vd<J> ldo(rctx const& c, uint32_t w)
+    {
+        vd<J> r = ldv<J>(c, PE_R_SLOT(w));
+        if(w & PE_R_NEG)
+        {
+            for(int j = 0; j < J; ++j) { r.v[j] = -r.v[j]; }
+        }
+        return r;
+    }
+
+    template <int J>
+    PE_HD void stv(rctx const& c, uint32_t slot, vd<J> const& x, bool const (&en)[J])
+    {
+        double* p = slot_ptr<J>(c, slot);
+#if defined(__CUDA_ARCH__)
+        if constexpr(J == 2)
+        {
+            if(en[0] && en[1])
+            {
+                *reinterpret_cast<double2*>(p) = make_double2(x.v[0], x.v[1]);
+                return;
+            }
+        }
+#endif
+        for(int j = 0; j < J; ++j)
+        {
+            if(en[j])
+            {
+                PE_TRACE_ST(p + j);
+                p[j] = x.v[j];
+            }
+        }
+    }
+
+    enum
+    {
+        V_END = 0,
+        V_BAR = 1,
+        V_OK = 2,
+        V_BAD = 3,
+    };
+
+    // Execute the vector op at pc for this thread.  en[j]: stores of instance j are enabled (the lane is still being
+    // solved); nconv / fail accumulate the Newton test and the pivot test.  Returns V_*; len = words to advance.
+    template <int J>
+    PE_HD int rvop(uint32_t const* pc, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J], uint32_t& len)
+    {
+        uint32_t const h = PE_LDW(pc);
+        uint32_t const op = h & 0xffu;
+        uint32_t const C = c.C;
+        uint32_t const* p0 = pc + 1 + c.col;  // row 0, this thread's column
+#define PE_ROW(r) PE_LDW(p0 + (r) * C)
+        switch(op)
+        {
+            case PE_OP_END: len = 0; return V_END;
+            case PE_OP_BAR: len = 1; return V_BAR;
+            case PE_OP_DOT:
+            {
+                uint32_t const na = (h >> 8) & 0xffu, nb = (h >> 16) & 0xffu, ufl = h >> 24;
+                uint32_t const* p = p0;
+                uint32_t const ctl = PE_LDW(p);
+                p += C;
+                uint32_t scale = 0;
+                if(ufl & PE_F_SCALE)
+                {
+                    scale = PE_LDW(p);
+                    p += C;
+                }
+                len = 1 + C * (1 + ((ufl & PE_F_SCALE) ? 1u : 0u) + na + nb);
+                vd<J> acc;
+                for(int j = 0; j < J; ++j) { acc.v[j] = 0.0; }
+                for(uint32_t r = 0; r < na; ++r)
+                {
+                    uint32_t const w = PE_LDW(p);
+                    p += C;
+                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                    vd<J> const s1 = ldo<J>(c, w >> 16);
+                    for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
+                }
+                for(uint32_t r = 0; r < nb; ++r)
+                {
+                    uint32_t const w = PE_LDW(p);
+                    p += C;
+                    vd<J> const a = ldv<J>(c, PE_R_SLOT(w));
+                    vd<J> const b = ldv<J>(c, PE_R_SLOT(w >> 16));
+                    for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
+                }
+                uint32_t const flags = ctl >> 16;
+                if(!(ctl & PE_R_ACTIVE)) { return V_OK; }
+                if(flags & PE_F_SCALE)
+                {
+                    vd<J> const s = ldv<J>(c, PE_R_SLOT(scale));
+                    for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], s.v[j]); }
+                }
+                if(flags & PE_F_RECIP)
+                {
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { fail[j] = true; }
+                        acc.v[j] = PE_DIV(1.0, acc.v[j]);
+                    }
+                }
+                uint32_t const dst = PE_R_SLOT(ctl);
+                if(check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I)))
+                {
+                    // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
+                    vd<J> const xo = ldv<J>(c, dst);
+                    bool const br = (flags & PE_F_CHECK_I) != 0u;
+                    double const at = br ? tol.i_abstol : tol.v_abstol, rt = br ? tol.i_reltol : tol.v_reltol;
+                    for(int j = 0; j < J; ++j)
+                    {
+                        double const tl = at + rt * fmax(fabs(acc.v[j]), fabs(xo.v[j]));
+                        if(fabs(acc.v[j] - xo.v[j]) > tl) { nconv[j] = true; }
+                    }
+                }
+                stv<J>(c, dst, acc, en);
+                return V_OK;
+            }
+            case PE_OP_CDOT:
+            {
+                uint32_t const nre = (h >> 8) & 0xffu, nb = (h >> 16) & 0xffu, ufl = h >> 24;
+                uint32_t const nim = PE_LDW(pc + 1) & 0xffu;
+                uint32_t const* p = p0 + 1;  // two uniform header words
+                uint32_t const ctl = PE_LDW(p);
+                p += C;
+                uint32_t scale = 0;
+                if(ufl & PE_F_SCALE)
+                {
+                    scale = PE_LDW(p);
+                    p += C;
+                }
+                len = 2 + C * (1 + ((ufl & PE_F_SCALE) ? 1u : 0u) + nre + nim + nb);
+                vd<J> are, aim;
+                for(int j = 0; j < J; ++j) { are.v[j] = aim.v[j] = 0.0; }
+                for(uint32_t r = 0; r < nre; ++r)
+                {
+                    uint32_t const w = PE_LDW(p);
+                    p += C;
+                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                    vd<J> const s1 = ldo<J>(c, w >> 16);
+                    for(int j = 0; j < J; ++j) { are.v[j] = PE_ADD(PE_ADD(are.v[j], s0.v[j]), s1.v[j]); }
+                }
+                for(uint32_t r = 0; r < nim; ++r)
+                {
+                    uint32_t const w = PE_LDW(p);
+                    p += C;
+                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                    vd<J> const s1 = ldo<J>(c, w >> 16);
+                    for(int j = 0; j < J; ++j) { aim.v[j] = PE_ADD(PE_ADD(aim.v[j], s0.v[j]), s1.v[j]); }
+                }
+                for(uint32_t r = 0; r < nb; ++r)
+                {
+                    uint32_t const w = PE_LDW(p);
+                    p += C;
+                    uint32_t const sa = PE_R_SLOT(w), sb = PE_R_SLOT(w >> 16);
+                    vd<J> const ar = ldv<J>(c, sa), ai = ldv<J>(c, sa + c.S);
+                    vd<J> const br = ldv<J>(c, sb), bi = ldv<J>(c, sb + c.S);
+                    for(int j = 0; j < J; ++j)
+                    {
+                        are.v[j] = fma(-ar.v[j], br.v[j], are.v[j]);
+                        are.v[j] = fma(ai.v[j], bi.v[j], are.v[j]);
+                        aim.v[j] = fma(-ar.v[j], bi.v[j], aim.v[j]);
+                        aim.v[j] = fma(-ai.v[j], br.v[j], aim.v[j]);
+                    }
+                }
+                uint32_t const flags = ctl >> 16;
+                if(!(ctl & PE_R_ACTIVE)) { return V_OK; }
+                if(flags & PE_F_SCALE)
+                {
+                    uint32_t const ss = PE_R_SLOT(scale);
+                    vd<J> const sr = ldv<J>(c, ss), si = ldv<J>(c, ss + c.S);
+                    for(int j = 0; j < J; ++j)
+                    {
+                        double const nr = are.v[j] * sr.v[j] - aim.v[j] * si.v[j];
+                        double const ni = are.v[j] * si.v[j] + aim.v[j] * sr.v[j];
+                        are.v[j] = nr;
+                        aim.v[j] = ni;
+                    }
+                }
+                if(flags & PE_F_RECIP)
+                {
+                    for(int j = 0; j < J; ++j)
+                    {
+                        double const m = are.v[j] * are.v[j] + aim.v[j] * aim.v[j];
+                        if(!(m > 0.0) || !isfinite(m)) { fail[j] = true; }
+                        double const s = 1.0 / m;
+                        are.v[j] = are.v[j] * s;
+                        aim.v[j] = -aim.v[j] * s;
+                    }
+                }
+                uint32_t const dst = PE_R_SLOT(ctl);
+                stv<J>(c, dst, are, en);
+                stv<J>(c, dst + c.S, aim, en);
+                return V_OK;
+            }
+            default: break;
+        }
+        // ---- value ops: a = operand rows; row 0 carries the ACTIVE bit
+        uint32_t const rows = (h >> 8) & 0xffu;
+        if(op < PE_OP_RECIP || op > PE_OP_PMOS_EVAL)
+        {
+            // unknown opcode (also what the compiler emits for a structurally singular system)
+            for(int j = 0; j < J; ++j) { fail[j] = true; }
+            len = 0;
+            return V_BAD;
+        }
+        len = 1 + C * rows;
+        uint32_t const w0 = PE_ROW(0);
+        if(!(w0 & PE_R_VACTIVE)) { return V_OK; }
+#define PE_LDR(r) ldo<J>(c, PE_ROW(r) & 0xffffu)
+#define PE_STR(r, val) stv<J>(c, PE_R_SLOT(PE_ROW(r)), (val), en)
+        switch(op)
+        {
+            case PE_OP_RECIP:
+            {
+                vd<J> a = PE_LDR(1);
+                for(int j = 0; j < J; ++j) { a.v[j] = PE_DIV(1.0, a.v[j]); }
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_MUL:
+            {
+                vd<J> a = PE_LDR(1);
+                vd<J> const b = PE_LDR(2);
+                for(int j = 0; j < J; ++j) { a.v[j] = PE_MUL(a.v[j], b.v[j]); }
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_SUB:
+            {
+                vd<J> a = PE_LDR(1);
+                vd<J> const b = PE_LDR(2);
+                for(int j = 0; j < J; ++j) { a.v[j] = PE_SUB(a.v[j], b.v[j]); }
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_COPY:
+            {
+                vd<J> const a = PE_LDR(1);
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_VSIN:
+            {
+                vd<J> vp = PE_LDR(1);
+                vd<J> const om = PE_LDR(2), ph = PE_LDR(3);
+                for(int j = 0; j < J; ++j) { vp.v[j] = PE_MUL(vp.v[j], sin(PE_ADD(PE_MUL(om.v[j], t), ph.v[j]))); }
+                PE_STR(0, vp);
+                return V_OK;
+            }
+            case PE_OP_SINCOS:
+            {
+                vd<J> const vp = PE_LDR(2), ph = PE_LDR(3);
+                vd<J> re, im;
+                for(int j = 0; j < J; ++j)
+                {
+                    re.v[j] = PE_MUL(vp.v[j], cos(ph.v[j]));
+                    im.v[j] = PE_MUL(vp.v[j], sin(ph.v[j]));
+                }
+                PE_STR(0, re);
+                PE_STR(1, im);
+                return V_OK;
+            }
+            case PE_OP_MUL2DIV:
+            {
+                vd<J> a = PE_LDR(1);
+                vd<J> const b = PE_LDR(2);
+                for(int j = 0; j < J; ++j) { a.v[j] = PE_DIV(PE_MUL(2.0, a.v[j]), b.v[j]); }
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_CAP_STEP:
+            {
+                vd<J> hv = PE_LDR(0), gv = PE_LDR(1);
+                vd<J> const C_ = PE_LDR(2), dt = PE_LDR(3), va = PE_LDR(4), vb = PE_LDR(5);
+                for(int j = 0; j < J; ++j) { pe_models::cap_step(C_.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hv.v[j], gv.v[j]); }
+                PE_STR(0, hv);
+                PE_STR(1, gv);
+                return V_OK;
+            }
+            case PE_OP_IND_STEP:
+            {
+                vd<J> const L = PE_LDR(2), dt = PE_LDR(3), va = PE_LDR(4), vb = PE_LDR(5), ib = PE_LDR(6);
+                vd<J> req, ueq;
+                for(int j = 0; j < J; ++j) { pe_models::ind_step(L.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), ib.v[j], req.v[j], ueq.v[j]); }
+                PE_STR(0, req);
+                PE_STR(1, ueq);
+                return V_OK;
+            }
+            case PE_OP_PN_PREP:
+            {
+                vd<J> const Is = PE_LDR(5), Isr = PE_LDR(6), Ar = PE_LDR(7), N = PE_LDR(8), Tc = PE_LDR(9), Ibv = PE_LDR(10), Bv = PE_LDR(11), bs = PE_LDR(12);
+                vd<J> o0, o1, o2, o3, o4;
+                for(int j = 0; j < J; ++j)
+                {
+                    auto const d = pe_models::pn_prepare(Is.v[j], Isr.v[j], Ar.v[j], N.v[j], Tc.v[j], Ibv.v[j], Bv.v[j], bs.v[j] != 0.0);
+                    o0.v[j] = d.is_eff;
+                    o1.v[j] = d.isr_eff;
+                    o2.v[j] = d.bv_eff;
+                    o3.v[j] = d.ut;
+                    o4.v[j] = d.uth;
+                }
+                PE_STR(0, o0);
+                PE_STR(1, o1);
+                PE_STR(2, o2);
+                PE_STR(3, o3);
+                PE_STR(4, o4);
+                return V_OK;
+            }
+            case PE_OP_PN_EVAL:
+            {
+                vd<J> const udl = PE_LDR(0), va = PE_LDR(3), vb = PE_LDR(4), ise = PE_LDR(5), isr = PE_LDR(6), bve = PE_LDR(7), ut = PE_LDR(8), uth = PE_LDR(9),
+                            N = PE_LDR(10), Nr = PE_LDR(11), bs = PE_LDR(12);
+                vd<J> o0, o1, o2;
+                for(int j = 0; j < J; ++j)
+                {
+                    auto const o = pe_models::pn_eval(PE_SUB(va.v[j], vb.v[j]), udl.v[j], ise.v[j], isr.v[j], bve.v[j], ut.v[j], uth.v[j], N.v[j], Nr.v[j], bs.v[j] != 0.0);
+                    o0.v[j] = o.ud;
+                    o1.v[j] = o.geq;
+                    o2.v[j] = o.ieq;
+                }
+                PE_STR(0, o0);
+                PE_STR(1, o1);
+                PE_STR(2, o2);
+                return V_OK;
+            }
+            case PE_OP_PN_STEP:
+            {
+                vd<J> hv = PE_LDR(1), gv = PE_LDR(2);
+                vd<J> const va = PE_LDR(3), vb = PE_LDR(4), geq = PE_LDR(5), tt = PE_LDR(6), dt = PE_LDR(7);
+                vd<J> ud;
+                for(int j = 0; j < J; ++j)
+                {
+                    ud.v[j] = PE_SUB(va.v[j], vb.v[j]);
+                    pe_models::pn_step(ud.v[j], geq.v[j], tt.v[j], dt.v[j], hv.v[j], gv.v[j]);
+                }
+                PE_STR(0, ud);
+                PE_STR(1, hv);
+                PE_STR(2, gv);
+                return V_OK;
+            }
+            case PE_OP_PN_ACCAP:
+            {
+                vd<J> g = PE_LDR(1);
+                vd<J> const tt = PE_LDR(2), om = PE_LDR(3);
+                for(int j = 0; j < J; ++j) { g.v[j] = pe_models::pn_ac_cap(g.v[j], tt.v[j], om.v[j]); }
+                PE_STR(0, g);
+                return V_OK;
+            }
+            case PE_OP_BJT_PREP:
+            {
+                vd<J> a = PE_LDR(1);
+                for(int j = 0; j < J; ++j) { a.v[j] = pe_models::thermal_voltage(a.v[j]); }
+                PE_STR(0, a);
+                return V_OK;
+            }
+            case PE_OP_BJT_EVAL:
+            {
+                vd<J> const vp = PE_LDR(4), vm = PE_LDR(5), Is = PE_LDR(6), Ar = PE_LDR(7), N = PE_LDR(8), ut = PE_LDR(9), bf = PE_LDR(10);
+                vd<J> o0, o1, o2, o3;
+                for(int j = 0; j < J; ++j)
+                {
+                    auto const o = pe_models::bjt_eval(PE_SUB(vp.v[j], vm.v[j]), Is.v[j], Ar.v[j], N.v[j], ut.v[j], bf.v[j]);
+                    o0.v[j] = o.geq;
+                    o1.v[j] = o.ieq_be;
+                    o2.v[j] = o.gm;
+                    o3.v[j] = o.ieq_c;
+                }
+                PE_STR(0, o0);
+                PE_STR(1, o1);
+                PE_STR(2, o2);
+                PE_STR(3, o3);
+                return V_OK;
+            }
+            case PE_OP_NMOS_EVAL:
+            case PE_OP_PMOS_EVAL:
+            {
+                vd<J> const vdd = PE_LDR(3), vg = PE_LDR(4), vs = PE_LDR(5), kp = PE_LDR(6), la = PE_LDR(7), vt = PE_LDR(8);
+                vd<J> o0, o1, o2;
+                for(int j = 0; j < J; ++j)
+                {
+                    auto const o = (op == PE_OP_NMOS_EVAL) ? pe_models::nmos_eval(vdd.v[j], vg.v[j], vs.v[j], kp.v[j], la.v[j], vt.v[j])
+                                                           : pe_models::pmos_eval(vdd.v[j], vg.v[j], vs.v[j], kp.v[j], la.v[j], vt.v[j]);
+                    o0.v[j] = o.gm;
+                    o1.v[j] = o.gds;
+                    o2.v[j] = o.ieq;
+                }
+                PE_STR(0, o0);
+                PE_STR(1, o1);
+                PE_STR(2, o2);
+                return V_OK;
+            }
+            default: break;
+        }
+#undef PE_LDR
+#undef PE_STR
+#undef PE_ROW
+        for(int j = 0; j < J; ++j) { fail[j] = true; }
+        len = 0;
+        return V_BAD;
+    }
+}  // namespace pe_rinterp

@@ -23,6 +23,12 @@ namespace pe_b200
         }
     }  // namespace
 
+    path_defaults& default_path()
+    {
+        static path_defaults d;
+        return d;
+    }
+
     void set_last_error(std::string s) { g_last_error = std::move(s); }
 
     char const* last_error() { return g_last_error.c_str(); }
@@ -59,7 +65,10 @@ namespace pe_b200
         int const n_unk{make_numbering(parent->nl).unknowns()};
         int const w_real{pick_warps(n_inst, n_unk)};
         int const w_ac{pick_warps(n_inst * ac_points, n_unk)};
-        bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac};
+        int r_real{pick_streams(n_unk)};
+        int r_ac{pick_streams(n_unk)};
+        bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac ||
+                        r_real != cc_res_real || r_ac != cc_res_ac};
         if(!need) { return true; }
         layout_keys = keys;
 
@@ -75,17 +84,48 @@ namespace pe_b200
         in.warps_ac = w_ac;
         cc_warps_real = w_real;
         cc_warps_ac = w_ac;
-        cc = compile_circuit(in);
-        if(!cc)
+        cc_res_real = r_real;
+        cc_res_ac = r_ac;
+        for(int attempt{}; attempt < 3; ++attempt)
         {
-            error = "compile failed";
-            set_last_error(error);
-            return false;
+            in.resident_real = r_real;
+            in.resident_ac = r_ac;
+            cc = compile_circuit(in);
+            if(!cc)
+            {
+                error = "compile failed";
+                set_last_error(error);
+                return false;
+            }
+            // a resident program whose workspace does not fit the shared memory of one CTA falls back to the
+            // HBM-streaming form (all real-valued modes together: they share the instance workspace layout)
+            bool redo{false};
+            bool real_fits{true};
+            for(int m{}; m < static_cast<int>(prog_mode::COUNT); ++m)
+            {
+                auto const& pr{cc->prog[static_cast<std::size_t>(m)]};
+                bool const is_ac{static_cast<prog_mode>(m) == prog_mode::AC};
+                if((is_ac ? r_ac : r_real) <= 0) { continue; }
+                int I{}, J{};
+                bool const fits{pr.built && pr.resident && pick_geometry(pr, I, J)};
+                if(!fits)
+                {
+                    if(is_ac) { r_ac = 0; }
+                    else
+                    {
+                        real_fits = false;
+                    }
+                    redo = true;
+                }
+            }
+            if(!real_fits) { r_real = 0; }
+            if(!redo) { break; }
         }
         cc_structure_rev = parent->structure_rev;
         cc_param_rev = parent->param_rev;
         cc_dt = parent->tr.t_step;
         uploaded.fill(false);
+        uploaded_ig.fill(0);
         device_stale = true;
         return true;
     }
@@ -105,6 +145,51 @@ namespace pe_b200
         g = std::clamp(g, 1, PE_MAX_WARPS);
         while(g > 1 && n_unknowns < 48 * g) { g /= 2; }  // leaves need enough rows to amortise the barriers
         return g;
+    }
+
+    int batch::pick_streams(int n_unknowns) const
+    {
+        if(res_S < 0) { return 0; }
+        if(res_S > 0) { return res_S; }
+        // small circuits: one thread per instance (no barriers, no divergence); larger ones: leaves of ~4 rows, which
+        // keeps a CTA of S threads busy while the (logarithmic) separator levels stay short
+        if(n_unknowns <= 64) { return 1; }
+        int s{1};
+        while(s < 256 && s * 2 * 4 <= n_unknowns) { s *= 2; }
+        return s;
+    }
+
+    bool batch::pick_geometry(program const& pr, int& I, int& J) const
+    {
+        std::size_t const limit{pe_b200_resident_smem_limit()};
+        std::size_t const per_inst{static_cast<std::size_t>(std::max(pr.r_slots, 1)) * sizeof(double)};
+        int const S{pr.rS};
+        int const i_fit{static_cast<int>(std::min<std::size_t>(limit / per_inst, 32))};
+        int const i_min{std::max(1, 32 / S)};
+        if(i_fit < i_min) { return false; }
+        auto pow2_floor = [](int v)
+        {
+            int p{1};
+            while(p * 2 <= v) { p *= 2; }
+            return p;
+        };
+        if(res_I > 0)
+        {
+            I = res_I;
+            J = res_J > 0 ? res_J : 1;
+            if(I > i_fit || I % J != 0 || I / J < i_min || (I & (I - 1)) != 0 || S * (I / J) > 1024) { return false; }
+            return true;
+        }
+        J = res_J > 0 ? res_J : ((S >= 32 && i_fit >= 2) ? 2 : 1);
+        // prefer two CTAs per SM (one hides the barrier stalls of the other) when the workspace allows it
+        int i{pow2_floor(i_fit)};
+        if(i / 2 >= i_min * J && i / 2 >= J && S * (i / 2 / J) >= 128) { i /= 2; }
+        while(i > i_min * J && S * (i / J) > 512) { i /= 2; }
+        if(i < J) { J = 1; }
+        if(i / J < i_min) { J = 1; }
+        if(i / J < i_min) { return false; }
+        I = i;
+        return true;
     }
 
     bool batch::ensure_compiled()
@@ -170,6 +255,8 @@ namespace pe_b200
     {
         int const mi{static_cast<int>(m)};
         auto& pr{cc->prog[static_cast<std::size_t>(mi)]};
+        if(pr.resident) { return run_phase_resident(m, with_prep, nonlinear, n_steps, time_stepping, t0, dt, lanes, ppi); }
+        last_I = last_J = last_S = 0;
         auto& d_w{d_words[static_cast<std::size_t>(mi)]};
         if(!uploaded[static_cast<std::size_t>(mi)])
         {
@@ -243,6 +330,109 @@ namespace pe_b200
         last_lanes = lanes;
         last_cplx = pr.cplx;
         if(pe_b200_launch(&r, stream) != 0) { return dev_fail(error, "launch"); }
+        return true;
+    }
+
+    bool batch::run_phase_resident(prog_mode m, bool with_prep, bool nonlinear, int n_steps, bool time_stepping, double t0, double dt, std::size_t lanes, int ppi)
+    {
+        int const mi{static_cast<int>(m)};
+        auto& pr{cc->prog[static_cast<std::size_t>(mi)]};
+        int I{}, J{};
+        if(!pick_geometry(pr, I, J))
+        {
+            error = "resident program does not fit the shared memory of one CTA";
+            set_last_error(error);
+            return false;
+        }
+        int const ig{I / J};
+        auto& d_w{d_words[static_cast<std::size_t>(mi)]};
+        auto& d_so{d_secoff[static_cast<std::size_t>(mi)]};
+        auto& d_i{d_io[static_cast<std::size_t>(mi)]};
+        if(!uploaded[static_cast<std::size_t>(mi)] || uploaded_ig[static_cast<std::size_t>(mi)] != ig)
+        {
+            pr.pack(ig);
+            if(!d_w.ensure(pr.words.size() * 4) || !d_so.ensure(pr.sec_off.size() * 4) || !d_i.ensure(std::max<std::size_t>(pr.io.size(), 1) * sizeof(pe_b200_io)))
+            {
+                return dev_fail(error, "alloc program");
+            }
+            if(pe_b200_dev_h2d(d_w.p, pr.words.data(), pr.words.size() * 4, stream) != 0 ||
+               pe_b200_dev_h2d(d_so.p, pr.sec_off.data(), pr.sec_off.size() * 4, stream) != 0 ||
+               (!pr.io.empty() && pe_b200_dev_h2d(d_i.p, pr.io.data(), pr.io.size() * sizeof(pe_b200_io), stream) != 0))
+            {
+                return dev_fail(error, "upload program");
+            }
+            uploaded[static_cast<std::size_t>(mi)] = true;
+            uploaded_ig[static_cast<std::size_t>(mi)] = ig;
+        }
+        if(cc->dt_slot >= 0) { cc->cst[static_cast<std::size_t>(cc->dt_slot)] = dt; }
+        if(!d_cst.ensure(cc->cst.size() * sizeof(double))) { return dev_fail(error, "alloc const table"); }
+        if(pe_b200_dev_h2d(d_cst.p, cc->cst.data(), cc->cst.size() * sizeof(double), stream) != 0) { return dev_fail(error, "upload const table"); }
+
+        std::int64_t const LSl{pr.cplx ? round_up32(lanes) : LSi};
+        if(pr.cplx)
+        {
+            std::size_t const wl_bytes{static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double)};
+            if(!d_wl.ensure(wl_bytes)) { return dev_fail(error, "alloc lane workspace"); }
+        }
+        if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
+
+        pe_b200_rrun r{};
+        r.words = static_cast<std::uint32_t const*>(d_w.p);
+        r.sec_off = static_cast<std::uint32_t const*>(d_so.p);
+        r.io = static_cast<pe_b200_io const*>(d_i.p);
+        r.n_io = static_cast<std::int32_t>(pr.io.size());
+        r.has_prep = (with_prep && pr.has_sec[0]) ? 1 : 0;
+        r.has_step = pr.has_sec[1] ? 1 : 0;
+        r.cst = static_cast<double const*>(d_cst.p);
+        r.wu = static_cast<double*>(pr.cplx ? d_wl.p : d_wi.p);
+        r.wx = static_cast<double*>(d_wi.p);
+        r.status = static_cast<std::int32_t*>(d_status.p);
+        r.solves = static_cast<std::uint32_t*>(d_solves.p);
+        r.wave = nullptr;
+        r.probes = nullptr;
+        r.n_probe = 0;
+        if(time_stepping && !probes.empty())
+        {
+            std::vector<std::uint32_t> po;
+            for(int u: probes) { po.push_back(pr.x_slot[static_cast<std::size_t>(u)]); }
+            if(!d_probes.ensure(po.size() * 4) || !d_wave.ensure(static_cast<std::size_t>(n_steps) * po.size() * static_cast<std::size_t>(LSl) * sizeof(double)))
+            {
+                return dev_fail(error, "alloc waveform store");
+            }
+            if(pe_b200_dev_h2d(d_probes.p, po.data(), po.size() * 4, stream) != 0) { return dev_fail(error, "upload probes"); }
+            if(pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "sync"); }  // `po` is pageable host memory
+            r.wave = static_cast<double*>(d_wave.p);
+            r.probes = static_cast<std::uint32_t const*>(d_probes.p);
+            r.n_probe = static_cast<std::int32_t>(po.size());
+            wave_steps = static_cast<std::size_t>(n_steps);
+        }
+        r.LSu = LSl;
+        r.LSx = LSi;
+        r.n_lanes = static_cast<std::int32_t>(lanes);
+        r.ppi = ppi;
+        r.S = pr.rS;
+        r.I = I;
+        r.J = J;
+        r.n_slots = pr.r_slots;
+        r.cplx = pr.cplx ? 1 : 0;
+        r.nonlinear = nonlinear ? 1 : 0;
+        r.max_iter = 64;  // circuit.h:898
+        r.n_steps = n_steps;
+        r.time_stepping = time_stepping ? 1 : 0;
+        r.t0 = t0;
+        r.dt = dt;
+        auto const& env{parent->env};
+        r.v_abstol = env.V_eps_max > 0.0 ? env.V_eps_max : 1e-6;
+        r.v_reltol = env.V_epsr_max > 0.0 ? env.V_epsr_max : 1e-3;
+        r.i_abstol = env.I_eps_max > 0.0 ? env.I_eps_max : 1e-12;
+        r.i_reltol = env.I_epsr_max > 0.0 ? env.I_epsr_max : r.v_reltol;
+        last_LSl = LSl;
+        last_lanes = lanes;
+        last_cplx = pr.cplx;
+        last_I = I;
+        last_J = J;
+        last_S = pr.rS;
+        if(pe_b200_launch_resident(&r, stream) != 0) { return dev_fail(error, "launch"); }
         return true;
     }
 
@@ -524,6 +714,11 @@ namespace pe_b200
             solo = std::make_unique<batch>();
             solo->parent = this;
             solo->n_inst = 1;
+            auto const& d{default_path()};
+            solo->res_S = d.res_S;
+            solo->res_I = d.res_I;
+            solo->res_J = d.res_J;
+            solo->subtree_warps = d.subtree_warps;
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

@@ -472,6 +472,11 @@ extern "C"
         if(b == nullptr) { return nullptr; }
         b->parent = static_cast<circuit*>(p);
         b->n_inst = n;
+        auto const& d{default_path()};
+        b->res_S = d.res_S;
+        b->res_I = d.res_I;
+        b->res_J = d.res_J;
+        b->subtree_warps = d.subtree_warps;
         return b;
     }
 
@@ -488,6 +493,44 @@ extern "C"
     {
         if(b == nullptr || warps < 0 || warps > PE_MAX_WARPS || (warps & (warps - 1)) != 0) { return 1; }
         static_cast<batch*>(b)->subtree_warps = warps;
+        return 0;
+    }
+
+    int circuit_batch_set_resident(void* b, int streams, int instances_per_cta, int instances_per_thread)
+    {
+        auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+        if(b == nullptr || streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
+        if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
+        if(instances_per_thread < 0 || instances_per_thread > 2) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        bp->res_S = streams;
+        bp->res_I = instances_per_cta;
+        bp->res_J = instances_per_thread;
+        return 0;
+    }
+
+    int circuit_batch_resident_info(void* b, int mode, int64_t* info)
+    {
+        if(b == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        if(!bp->cc) { return 1; }
+        auto const& pr{bp->cc->prog[static_cast<std::size_t>(mode)]};
+        int I{}, J{};
+        bool const fits{pr.resident && bp->pick_geometry(pr, I, J)};
+        info[0] = pr.resident ? 1 : 0;
+        info[1] = pr.rS;
+        info[2] = pr.r_slots;
+        info[3] = fits ? I : 0;
+        info[4] = fits ? J : 0;
+        info[5] = static_cast<int64_t>(pr.io.size());
+        info[6] = bp->last_S;
+        info[7] = bp->last_I;
+        info[8] = bp->last_J;
+        std::size_t nph{};
+        if(pr.resident && !pr.rstreams.empty()) { nph = pr.rstreams[0].sec[2].size(); }
+        info[9] = static_cast<int64_t>(nph);
+        info[10] = static_cast<int64_t>(pr.words.size());
+        info[11] = static_cast<int64_t>(pr.max_warp_words);
         return 0;
     }
 
@@ -795,6 +838,21 @@ extern "C"
             }
         }
         return 1;
+    }
+
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps)
+    {
+        auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+        if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
+        if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
+        if(instances_per_thread < 0 || instances_per_thread > 2) { return 1; }
+        if(subtree_warps < 0 || subtree_warps > PE_MAX_WARPS || (subtree_warps > 0 && !pow2(subtree_warps))) { return 1; }
+        auto& d{default_path()};
+        d.res_S = streams;
+        d.res_I = instances_per_cta;
+        d.res_J = instances_per_thread;
+        d.subtree_warps = subtree_warps;
+        return 0;
     }
 
     int phy_engine_b200_device_count(void) { return pe_b200_dev_count(); }

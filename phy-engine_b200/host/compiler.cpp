@@ -49,7 +49,11 @@ namespace pe_b200
             cplx nom{};
         };
 
-        using op_t = std::vector<std::uint32_t>;  // [opcode header][internal operand words...]
+        struct op_t
+        {
+            std::vector<std::uint32_t> w;  // [opcode header][internal operand words...]
+            int aff{-1};                   // unknown index the op's element hangs on (resident schedule: which stream runs it)
+        };
 
         constexpr double k_nl_nominal = 1e-12;  // nominal conductance of a not-yet-evaluated non-linear device
         constexpr double k_pivot_tau = 1e-3;    // relative threshold (SPICE PIVREL)
@@ -97,12 +101,26 @@ namespace pe_b200
 
             val inst_slot(double nominal) { return {IOP(I_INST, n_inst++), nominal, false}; }
 
-            static void emit(std::vector<op_t>& sec, std::uint32_t opcode, std::initializer_list<std::uint32_t> ops)
+            int cur_aff{-1};
+            void emit(std::vector<op_t>& sec, std::uint32_t opcode, std::initializer_list<std::uint32_t> ops)
             {
                 op_t o;
-                o.push_back(opcode);
-                for(auto w: ops) { o.push_back(w); }
+                o.w.push_back(opcode);
+                for(auto w: ops) { o.w.push_back(w); }
+                o.aff = cur_aff;
                 sec.push_back(std::move(o));
+            }
+
+            // the unknown an element's ops are scheduled next to: its first non-ground pin, else its first branch
+            int affinity(std::size_t ei) const
+            {
+                auto const& e{nl.elems[ei]};
+                for(int p{}; p < e.d->pins; ++p)
+                {
+                    if(e.pin_node[p] >= 0 && num.node_index[static_cast<std::size_t>(e.pin_node[p])] >= 0) { return num.node_index[static_cast<std::size_t>(e.pin_node[p])]; }
+                }
+                if(e.d->branches > 0) { return num.n_nodes + num.branch0[ei]; }
+                return -1;
             }
 
             int nidx(int node) const { return node < 0 ? -1 : num.node_index[static_cast<std::size_t>(node)]; }
@@ -195,6 +213,7 @@ namespace pe_b200
                     auto const& e{nl.elems[ei]};
                     auto& v{ev[ei]};
                     if(!connected(e)) { continue; }
+                    cur_aff = affinity(ei);
                     switch(e.d->code)
                     {
                         case E_RES:
@@ -373,6 +392,7 @@ namespace pe_b200
                 auto const& e{nl.elems[ei]};
                 auto& v{ev[ei]};
                 if(!connected(e)) { return; }  // unconnected pin: the whole stamp is skipped (resistance.h:86)
+                cur_aff = affinity(ei);
                 auto const mode{ps.mode};
                 int const n0{nidx(e.pin_node[0])};
                 int const n1{nidx(e.pin_node[1])};
@@ -841,11 +861,256 @@ namespace pe_b200
                 return region;
             }
 
+            // ---- elimination tree of regions -----------------------------------------------------------------------
+            // Nodes are regions of unknowns: leaves (level 0) are eliminated concurrently by different word streams, a
+            // separator node after both of its children.  `stream` says which stream owns a node: leaf number for a
+            // leaf, the last leaf of the left subtree for a separator (so every stream owns at most one node per level).
+            struct etree
+            {
+                std::vector<int> region;                  // per unknown: node id
+                std::vector<int> parent, level, stream;   // per node
+                std::vector<int> order;                   // nodes in elimination order (level, then stream)
+                int n_leaves{};
+                int n_levels{1};
+            };
+
+            // v2 shape: G leaves + one top node
+            static etree flat_tree(std::vector<int> const& leaf_region, int n_leaves)
+            {
+                etree t;
+                t.region = leaf_region;
+                int const root{n_leaves};
+                for(auto& r: t.region)
+                {
+                    if(r < 0) { r = root; }
+                }
+                for(int l{}; l < n_leaves; ++l)
+                {
+                    t.parent.push_back(root);
+                    t.level.push_back(0);
+                    t.stream.push_back(l);
+                    t.order.push_back(l);
+                }
+                t.parent.push_back(-1);
+                t.level.push_back(n_leaves > 0 ? 1 : 0);
+                t.stream.push_back(0);
+                t.order.push_back(root);
+                t.n_leaves = n_leaves;
+                t.n_levels = n_leaves > 0 ? 2 : 1;
+                return t;
+            }
+
+            // recursive nested dissection into (up to) S leaves
+            static etree partition_tree(int n, std::vector<std::vector<int>> const& adj, int S, int min_leaf)
+            {
+                etree t;
+                t.region.assign(static_cast<std::size_t>(n), -1);
+                std::size_t deg_sum{};
+                for(auto const& a: adj) { deg_sum += a.size(); }
+                std::size_t const hub_deg{std::max<std::size_t>(32, 10 * (deg_sum / static_cast<std::size_t>(std::max(n, 1)) + 1))};
+                std::vector<int> all, hubs;
+                for(int i{}; i < n; ++i) { (adj[static_cast<std::size_t>(i)].size() > hub_deg ? hubs : all).push_back(i); }
+                std::vector<int> mark(static_cast<std::size_t>(n), -1), lvl(static_cast<std::size_t>(n), -1);
+                int stamp{};
+                int leaf_counter{};
+
+                auto bfs = [&](int start, int my_stamp, std::vector<int>& order) -> int
+                {
+                    for(int v: order) { lvl[static_cast<std::size_t>(v)] = -1; }
+                    order.clear();
+                    lvl[static_cast<std::size_t>(start)] = 0;
+                    order.push_back(start);
+                    int maxl{};
+                    for(std::size_t h{}; h < order.size(); ++h)
+                    {
+                        int const v{order[h]};
+                        for(int u: adj[static_cast<std::size_t>(v)])
+                        {
+                            if(mark[static_cast<std::size_t>(u)] != my_stamp || lvl[static_cast<std::size_t>(u)] >= 0) { continue; }
+                            lvl[static_cast<std::size_t>(u)] = lvl[static_cast<std::size_t>(v)] + 1;
+                            maxl = std::max(maxl, lvl[static_cast<std::size_t>(u)]);
+                            order.push_back(u);
+                        }
+                    }
+                    return maxl + 1;
+                };
+
+                // split `part` into A | Sep | B; false if it cannot be split
+                auto bisect = [&](std::vector<int> const& part, std::vector<int>& A, std::vector<int>& B, std::vector<int>& Sep) -> bool
+                {
+                    int const st{++stamp};
+                    for(int v: part)
+                    {
+                        mark[static_cast<std::size_t>(v)] = st;
+                        lvl[static_cast<std::size_t>(v)] = -1;
+                    }
+                    // connected components first
+                    std::vector<std::vector<int>> comps;
+                    for(int s0: part)
+                    {
+                        if(lvl[static_cast<std::size_t>(s0)] >= 0) { continue; }
+                        std::vector<int> q{s0};
+                        lvl[static_cast<std::size_t>(s0)] = 0;
+                        for(std::size_t h{}; h < q.size(); ++h)
+                        {
+                            for(int u: adj[static_cast<std::size_t>(q[h])])
+                            {
+                                if(mark[static_cast<std::size_t>(u)] != st || lvl[static_cast<std::size_t>(u)] >= 0) { continue; }
+                                lvl[static_cast<std::size_t>(u)] = 0;
+                                q.push_back(u);
+                            }
+                        }
+                        comps.push_back(std::move(q));
+                    }
+                    if(comps.size() > 1)
+                    {
+                        std::sort(comps.begin(), comps.end(), [](auto const& x, auto const& y) { return x.size() > y.size(); });
+                        if(comps[0].size() * 4 <= part.size() * 3)
+                        {
+                            for(auto const& cmp: comps)
+                            {
+                                auto& dst{A.size() <= B.size() ? A : B};
+                                dst.insert(dst.end(), cmp.begin(), cmp.end());
+                            }
+                            return !A.empty() && !B.empty();
+                        }
+                        // one dominant component: cut it, the small ones ride along with the lighter side
+                        std::vector<int> big{comps[0]};
+                        std::vector<int> rest;
+                        for(std::size_t k{1}; k < comps.size(); ++k) { rest.insert(rest.end(), comps[k].begin(), comps[k].end()); }
+                        int const st2{++stamp};
+                        for(int v: big) { mark[static_cast<std::size_t>(v)] = st2; }
+                        std::vector<int> order{big};
+                        bfs(big[0], st2, order);
+                        int const far{order.back()};
+                        order = big;
+                        int const nl{bfs(far, st2, order)};
+                        if(nl < 3) { return false; }
+                        std::vector<int> cnt(static_cast<std::size_t>(nl), 0);
+                        for(int v: big) { ++cnt[static_cast<std::size_t>(lvl[static_cast<std::size_t>(v)])]; }
+                        int const total{static_cast<int>(big.size())};
+                        int below{cnt[0]}, best_t{-1};
+                        long best_cost{std::numeric_limits<long>::max()};
+                        for(int tt{1}; tt + 1 < nl; ++tt)
+                        {
+                            int const above{total - below - cnt[static_cast<std::size_t>(tt)]};
+                            long const cost{static_cast<long>(cnt[static_cast<std::size_t>(tt)]) * 8 + std::abs(below - above)};
+                            if(std::min(below, above) > 0 && cost < best_cost)
+                            {
+                                best_cost = cost;
+                                best_t = tt;
+                            }
+                            below += cnt[static_cast<std::size_t>(tt)];
+                        }
+                        if(best_t < 0) { return false; }
+                        for(int v: big)
+                        {
+                            int const l{lvl[static_cast<std::size_t>(v)]};
+                            (l < best_t ? A : (l > best_t ? B : Sep)).push_back(v);
+                        }
+                        auto& dst{A.size() <= B.size() ? A : B};
+                        dst.insert(dst.end(), rest.begin(), rest.end());
+                        return true;
+                    }
+                    std::vector<int> order{part};
+                    bfs(part[0], st, order);
+                    int const far{order.back()};
+                    order = part;
+                    int const nl{bfs(far, st, order)};
+                    if(nl < 3) { return false; }
+                    std::vector<int> cnt(static_cast<std::size_t>(nl), 0);
+                    for(int v: part) { ++cnt[static_cast<std::size_t>(lvl[static_cast<std::size_t>(v)])]; }
+                    int const total{static_cast<int>(part.size())};
+                    int below{cnt[0]}, best_t{-1};
+                    long best_cost{std::numeric_limits<long>::max()};
+                    for(int tt{1}; tt + 1 < nl; ++tt)
+                    {
+                        int const above{total - below - cnt[static_cast<std::size_t>(tt)]};
+                        int const lo{std::min(below, above)};
+                        long cost{static_cast<long>(cnt[static_cast<std::size_t>(tt)]) * 8};
+                        if(lo * 10 < total * 3) { cost += static_cast<long>(total) * 8 + static_cast<long>(std::abs(below - above)); }
+                        else
+                        {
+                            cost += std::abs(below - above) / 2;
+                        }
+                        if(lo > 0 && cost < best_cost)
+                        {
+                            best_cost = cost;
+                            best_t = tt;
+                        }
+                        below += cnt[static_cast<std::size_t>(tt)];
+                    }
+                    if(best_t < 0) { return false; }
+                    for(int v: part)
+                    {
+                        int const l{lvl[static_cast<std::size_t>(v)]};
+                        (l < best_t ? A : (l > best_t ? B : Sep)).push_back(v);
+                    }
+                    return !A.empty() && !B.empty();
+                };
+
+                auto new_node = [&](int level, int stream) -> int
+                {
+                    t.parent.push_back(-1);
+                    t.level.push_back(level);
+                    t.stream.push_back(stream);
+                    return static_cast<int>(t.parent.size()) - 1;
+                };
+
+                auto build = [&](auto&& self, std::vector<int> part, int k) -> int
+                {
+                    std::vector<int> A, B, Sep;
+                    if(k <= 1 || static_cast<int>(part.size()) < 2 * min_leaf || !bisect(part, A, B, Sep))
+                    {
+                        int const id{new_node(0, leaf_counter++)};
+                        for(int v: part) { t.region[static_cast<std::size_t>(v)] = id; }
+                        return id;
+                    }
+                    part.clear();
+                    part.shrink_to_fit();
+                    int const l{self(self, std::move(A), k / 2)};
+                    int const owner{leaf_counter - 1};
+                    int const r{self(self, std::move(B), k - k / 2)};
+                    int const id{new_node(1 + std::max(t.level[static_cast<std::size_t>(l)], t.level[static_cast<std::size_t>(r)]), owner)};
+                    t.parent[static_cast<std::size_t>(l)] = id;
+                    t.parent[static_cast<std::size_t>(r)] = id;
+                    for(int v: Sep) { t.region[static_cast<std::size_t>(v)] = id; }
+                    return id;
+                };
+                int root{build(build, std::move(all), std::max(S, 1))};
+                if(!hubs.empty())
+                {
+                    if(t.level[static_cast<std::size_t>(root)] == 0)
+                    {
+                        int const id{new_node(1, t.stream[static_cast<std::size_t>(root)])};
+                        t.parent[static_cast<std::size_t>(root)] = id;
+                        root = id;
+                    }
+                    for(int v: hubs) { t.region[static_cast<std::size_t>(v)] = root; }
+                }
+                t.n_leaves = leaf_counter;
+                t.n_levels = t.level[static_cast<std::size_t>(root)] + 1;
+                t.order.resize(t.parent.size());
+                std::iota(t.order.begin(), t.order.end(), 0);
+                std::stable_sort(t.order.begin(),
+                                 t.order.end(),
+                                 [&](int a, int b)
+                                 {
+                                     if(t.level[static_cast<std::size_t>(a)] != t.level[static_cast<std::size_t>(b)])
+                                     {
+                                         return t.level[static_cast<std::size_t>(a)] < t.level[static_cast<std::size_t>(b)];
+                                     }
+                                     return t.stream[static_cast<std::size_t>(a)] < t.stream[static_cast<std::size_t>(b)];
+                                 });
+                return t;
+            }
+
             // ---- symbolic LU + emission ------------------------------------------------------------------------
             struct lu_step
             {
                 int r, c, piv;
-                int leaf;                       // region the pivot was taken in (-1 = top)
+                int leaf;                       // v2 schedule: leaf the pivot was taken in (-1 = top)
+                int node;                       // elimination-tree node the pivot was taken in
                 std::vector<int> lrows, l_ent;  // rows i with (i,c), entry ids
                 std::vector<int> ucols, u_ent;  // cols j with (r,j), entry ids
                 std::vector<int> t_ent;         // lrows.size() * ucols.size() target entry ids
@@ -856,6 +1121,628 @@ namespace pe_b200
                 std::vector<std::uint32_t> w;
                 int tmp_slot{-1};
             };
+
+            struct upd
+            {
+                int l, u;  // l: L entry id; u: U entry id (matrix entries) or pivot-row index (rhs)
+                int leaf;  // v2 schedule: leaf of the elimination step that generates this update (-1 = top)
+                int node;  // elimination-tree node of that step
+            };
+
+            // ================= resident (shared-memory) schedule: DESIGN.md §5 =================================
+            struct resident_ctx
+            {
+                pstate& ps;
+                program& pr;
+                etree const& tree;
+                int S;
+                std::vector<lu_step> const& steps;
+                std::vector<std::vector<upd>> const& pairs;
+                std::vector<std::vector<upd>> const& ypairs;
+                std::vector<char> const& ynz;
+                std::vector<entry const*> const& orig;
+                int n;
+                std::size_t n_ent;
+            };
+
+            static int value_op_outputs(std::uint32_t opcode)
+            {
+                switch(opcode)
+                {
+                    case PE_OP_SINCOS:
+                    case PE_OP_CAP_STEP:
+                    case PE_OP_IND_STEP: return 2;
+                    case PE_OP_PN_PREP: return 5;
+                    case PE_OP_PN_EVAL:
+                    case PE_OP_PN_STEP:
+                    case PE_OP_NMOS_EVAL:
+                    case PE_OP_PMOS_EVAL: return 3;
+                    case PE_OP_BJT_EVAL: return 4;
+                    default: return 1;
+                }
+            }
+
+            void resident_singular(program& pr, pstate& ps, int S, int n)
+            {
+                pr.resident = true;
+                pr.rS = S;
+                pr.cplx = ps.cplx;
+                pr.rstreams.assign(static_cast<std::size_t>(S), {});
+                for(auto& rs: pr.rstreams)
+                {
+                    rs.sec[2].resize(1);
+                    rop bad;
+                    bad.opcode = 0xffu;  // unknown opcode -> every lane reports PE_ST_SINGULAR
+                    rs.sec[2][0].push_back(bad);
+                }
+                pr.r_slots = S;
+                pr.r_zero = 0;
+                pr.io.clear();
+                pr.io.push_back({0u | (static_cast<std::uint32_t>(PE_IO_CONST) << 16) | (PE_IO_LOAD << 20), 0u});
+                pr.x_slot.assign(static_cast<std::size_t>(n), 0u);
+                pr.x_opnd.assign(static_cast<std::size_t>(n), PE_OPND(PE_SP_CONST, 0));
+                pr.n_lane_slots = ps.cplx ? 1 + 2 * n : 0;
+                pr.omega_slot = ps.cplx ? 0 : -1;
+                pr.warps = 1;
+                pr.built = true;
+            }
+
+            void emit_resident(resident_ctx& rc)
+            {
+                auto& ps{rc.ps};
+                auto& pr{rc.pr};
+                auto const& tree{rc.tree};
+                auto const& steps{rc.steps};
+                int const S{rc.S};
+                int const n{rc.n};
+                std::size_t const n_ent{rc.n_ent};
+                bool const cplx{ps.cplx};
+                int const w{cplx ? 2 : 1};
+                int const L{tree.n_levels};
+                int const n_ph{2 * L};
+                constexpr std::uint32_t NEG{0x80000000u};
+
+                pr.resident = true;
+                pr.rS = S;
+                pr.cplx = cplx;
+                auto& RS{pr.rstreams};
+                RS.assign(static_cast<std::size_t>(S), {});
+                for(auto& rs: RS)
+                {
+                    rs.sec[0].resize(1);
+                    rs.sec[1].resize(1);
+                    rs.sec[2].resize(static_cast<std::size_t>(n_ph));
+                }
+
+                // lane-space values: 0 scalar, 1 re of a complex unit, 2 its im
+                std::vector<std::uint8_t> lkind(static_cast<std::size_t>(ps.n_lane), 0);
+                auto new_lane = [&]() -> std::uint32_t
+                {
+                    int const s{ps.n_lane};
+                    ps.n_lane += w;
+                    lkind.resize(static_cast<std::size_t>(ps.n_lane), 0);
+                    if(cplx)
+                    {
+                        lkind[static_cast<std::size_t>(s)] = 1;
+                        lkind[static_cast<std::size_t>(s) + 1] = 2;
+                    }
+                    return IOP(I_LANE, s);
+                };
+                std::vector<std::uint32_t> ekey(n_ent, 0u), ykey(static_cast<std::size_t>(n), 0u);
+                std::vector<char> ehas(n_ent, 0), yhas(static_cast<std::size_t>(n), 0);
+                auto key_e = [&](int id) -> std::uint32_t
+                {
+                    if(!ehas[static_cast<std::size_t>(id)])
+                    {
+                        ekey[static_cast<std::size_t>(id)] = new_lane();
+                        ehas[static_cast<std::size_t>(id)] = 1;
+                    }
+                    return ekey[static_cast<std::size_t>(id)];
+                };
+                auto key_y = [&](int row) -> std::uint32_t
+                {
+                    if(!yhas[static_cast<std::size_t>(row)])
+                    {
+                        ykey[static_cast<std::size_t>(row)] = new_lane();
+                        yhas[static_cast<std::size_t>(row)] = 1;
+                    }
+                    return ykey[static_cast<std::size_t>(row)];
+                };
+                std::vector<std::uint32_t> xs(static_cast<std::size_t>(n));
+                for(int j{}; j < n; ++j) { xs[static_cast<std::size_t>(j)] = cplx ? new_lane() : IOP(I_INST, j); }
+
+                auto node_stream = [&](int node) { return tree.stream[static_cast<std::size_t>(node)] % S; };
+                auto fwd_phase = [&](int node) { return 1 + tree.level[static_cast<std::size_t>(node)]; };
+                auto back_phase = [&](int node)
+                {
+                    int const l{tree.level[static_cast<std::size_t>(node)]};
+                    return l == L - 1 ? L : 2 * L - 1 - l;
+                };
+
+                // ---- owners and contributions
+                std::vector<int> ent_owner(n_ent, -1), row_owner(static_cast<std::size_t>(n), -1);
+                for(auto const& st: steps)
+                {
+                    ent_owner[static_cast<std::size_t>(st.piv)] = st.node;
+                    for(int e: st.u_ent) { ent_owner[static_cast<std::size_t>(e)] = st.node; }
+                    for(int e: st.l_ent) { ent_owner[static_cast<std::size_t>(e)] = st.node; }
+                    row_owner[static_cast<std::size_t>(st.r)] = st.node;
+                }
+                // contribution of node M to a target it does not own, when M generates at least two updates to it
+                std::map<std::pair<std::int64_t, int>, std::uint32_t> contrib;
+                std::vector<std::vector<std::pair<std::int64_t, std::uint32_t>>> node_contribs(tree.parent.size());
+                auto scan_contribs = [&](std::int64_t target, std::vector<upd> const& ups, int owner)
+                {
+                    std::map<int, int> cnt;
+                    for(auto const& u: ups)
+                    {
+                        if(u.node != owner) { ++cnt[u.node]; }
+                    }
+                    for(auto const& [m, c]: cnt)
+                    {
+                        if(c >= 2)
+                        {
+                            std::uint32_t const k{new_lane()};
+                            contrib[{target, m}] = k;
+                            node_contribs[static_cast<std::size_t>(m)].push_back({target, k});
+                        }
+                    }
+                };
+                for(std::size_t e{}; e < n_ent; ++e)
+                {
+                    if(ent_owner[e] >= 0) { scan_contribs(static_cast<std::int64_t>(e), rc.pairs[e], ent_owner[e]); }
+                }
+                for(int r{}; r < n; ++r) { scan_contribs(static_cast<std::int64_t>(n_ent) + r, rc.ypairs[static_cast<std::size_t>(r)], row_owner[static_cast<std::size_t>(r)]); }
+
+                // ---- abstract DOT emission (operands are internal words; translated to slots after allocation)
+                std::vector<std::uint32_t> tmp_key(static_cast<std::size_t>(S), 0u);
+                std::vector<char> tmp_has(static_cast<std::size_t>(S), 0);
+                std::uint32_t const dot_op{cplx ? static_cast<std::uint32_t>(PE_OP_CDOT) : static_cast<std::uint32_t>(PE_OP_DOT)};
+                auto emit_dot = [&](int sj, int phase, std::uint32_t dst, std::uint32_t flags, std::uint32_t scale, std::vector<std::uint32_t> const& sre,
+                                    std::vector<std::uint32_t> const& sim, std::vector<std::pair<std::uint32_t, std::uint32_t>> const& pp)
+                {
+                    std::size_t const max_src{500}, max_pair{250};
+                    auto& dstv{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(phase)]};
+                    std::size_t ri{}, ii{}, pi{};
+                    bool first{true};
+                    for(;;)
+                    {
+                        std::size_t const carry{first ? 0u : 1u};
+                        std::size_t const nr{std::min(sre.size() - ri, max_src - carry)};
+                        std::size_t const ni{std::min(sim.size() - ii, max_src - carry)};
+                        std::size_t const np{std::min(pp.size() - pi, max_pair)};
+                        bool const last{ri + nr == sre.size() && ii + ni == sim.size() && pi + np == pp.size()};
+                        rop o;
+                        o.opcode = dot_op;
+                        if(!last || !first)
+                        {
+                            if(!tmp_has[static_cast<std::size_t>(sj)])
+                            {
+                                tmp_key[static_cast<std::size_t>(sj)] = new_lane();
+                                tmp_has[static_cast<std::size_t>(sj)] = 1;
+                            }
+                        }
+                        std::uint32_t const tk{tmp_key[static_cast<std::size_t>(sj)]};
+                        o.dst = last ? dst : tk;
+                        o.flags = last ? flags : 0u;
+                        o.scale = (o.flags & PE_F_SCALE) ? scale : 0u;
+                        if(carry)
+                        {
+                            o.sre.push_back(tk);
+                            if(cplx) { o.sim.push_back(tk + 1); }
+                        }
+                        o.sre.insert(o.sre.end(), sre.begin() + static_cast<std::ptrdiff_t>(ri), sre.begin() + static_cast<std::ptrdiff_t>(ri + nr));
+                        o.sim.insert(o.sim.end(), sim.begin() + static_cast<std::ptrdiff_t>(ii), sim.begin() + static_cast<std::ptrdiff_t>(ii + ni));
+                        o.pp.insert(o.pp.end(), pp.begin() + static_cast<std::ptrdiff_t>(pi), pp.begin() + static_cast<std::ptrdiff_t>(pi + np));
+                        dstv.push_back(std::move(o));
+                        ri += nr;
+                        ii += ni;
+                        pi += np;
+                        first = false;
+                        if(last) { break; }
+                    }
+                };
+
+                std::vector<std::uint32_t> sre, sim;
+                std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;
+                auto load_sources = [&](entry const* e)
+                {
+                    sre.clear();
+                    sim.clear();
+                    if(e == nullptr) { return; }
+                    sre = e->re;
+                    sim = e->im;
+                };
+                auto load_updates = [&](std::int64_t target, std::vector<upd> const& ups, int owner, bool rhs)
+                {
+                    pp.clear();
+                    std::set<int> seen;
+                    for(auto const& u: ups)
+                    {
+                        if(u.node != owner)
+                        {
+                            auto it{contrib.find({target, u.node})};
+                            if(it != contrib.end())
+                            {
+                                if(seen.insert(u.node).second)
+                                {
+                                    sre.push_back(it->second);
+                                    if(cplx) { sim.push_back(it->second + 1); }
+                                }
+                                continue;
+                            }
+                        }
+                        pp.push_back({key_e(u.l), rhs ? key_y(u.u) : key_e(u.u)});
+                    }
+                };
+
+                // ---- forward steps (Crout: pivot, row of U, column of L, rhs entry), then the node's contributions
+                for(std::size_t k{}; k < steps.size(); ++k)
+                {
+                    auto const& st{steps[k]};
+                    int const sj{node_stream(st.node)};
+                    int const ph{fwd_phase(st.node)};
+                    load_sources(rc.orig[static_cast<std::size_t>(st.piv)]);
+                    load_updates(st.piv, rc.pairs[static_cast<std::size_t>(st.piv)], st.node, false);
+                    emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
+                    for(int e: st.u_ent)
+                    {
+                        load_sources(rc.orig[static_cast<std::size_t>(e)]);
+                        load_updates(e, rc.pairs[static_cast<std::size_t>(e)], st.node, false);
+                        emit_dot(sj, ph, key_e(e), 0, 0, sre, sim, pp);
+                    }
+                    for(int e: st.l_ent)
+                    {
+                        load_sources(rc.orig[static_cast<std::size_t>(e)]);
+                        load_updates(e, rc.pairs[static_cast<std::size_t>(e)], st.node, false);
+                        emit_dot(sj, ph, key_e(e), PE_F_SCALE, key_e(st.piv), sre, sim, pp);
+                    }
+                    if(rc.ynz[static_cast<std::size_t>(st.r)])
+                    {
+                        load_sources(&ps.Z[static_cast<std::size_t>(st.r)]);
+                        load_updates(static_cast<std::int64_t>(n_ent) + st.r, rc.ypairs[static_cast<std::size_t>(st.r)], st.node, true);
+                        emit_dot(sj, ph, key_y(st.r), 0, 0, sre, sim, pp);
+                    }
+                }
+                for(std::size_t m{}; m < node_contribs.size(); ++m)
+                {
+                    int const sj{node_stream(static_cast<int>(m))};
+                    int const ph{fwd_phase(static_cast<int>(m))};
+                    for(auto const& [target, key]: node_contribs[m])
+                    {
+                        bool const rhs{target >= static_cast<std::int64_t>(n_ent)};
+                        auto const& ups{rhs ? rc.ypairs[static_cast<std::size_t>(target - static_cast<std::int64_t>(n_ent))] : rc.pairs[static_cast<std::size_t>(target)]};
+                        sre.clear();
+                        sim.clear();
+                        pp.clear();
+                        for(auto const& u: ups)
+                        {
+                            if(u.node == static_cast<int>(m)) { pp.push_back({key_e(u.l), rhs ? key_y(u.u) : key_e(u.u)}); }
+                        }
+                        emit_dot(sj, ph, key, 0, 0, sre, sim, pp);
+                    }
+                }
+                // ---- back substitution, root first
+                for(std::size_t k{steps.size()}; k-- > 0;)
+                {
+                    auto const& st{steps[k]};
+                    sre.clear();
+                    sim.clear();
+                    pp.clear();
+                    if(rc.ynz[static_cast<std::size_t>(st.r)])
+                    {
+                        sre.push_back(key_y(st.r));
+                        if(cplx) { sim.push_back(key_y(st.r) + 1); }
+                    }
+                    for(std::size_t b{}; b < st.ucols.size(); ++b) { pp.push_back({key_e(st.u_ent[b]), xs[static_cast<std::size_t>(st.ucols[b])]}); }
+                    std::uint32_t flags{};
+                    if(!sre.empty() || !pp.empty()) { flags |= PE_F_SCALE; }
+                    if(!cplx) { flags |= (st.c >= num.n_nodes) ? PE_F_CHECK_I : PE_F_CHECK_V; }
+                    emit_dot(node_stream(st.node), back_phase(st.node), xs[static_cast<std::size_t>(st.c)], flags, key_e(st.piv), sre, sim, pp);
+                }
+
+                // ---- value ops: next to the stream that owns their element's unknown, same opcodes aligned
+                auto deal = [&](std::vector<op_t> const& ops, int sec, int phase)
+                {
+                    if(ops.empty()) { return; }
+                    std::vector<std::vector<op_t const*>> per(static_cast<std::size_t>(S));
+                    std::size_t rr{};
+                    for(auto const& o: ops)
+                    {
+                        int sj;
+                        if(o.aff >= 0 && o.aff < n) { sj = node_stream(tree.region[static_cast<std::size_t>(o.aff)]); }
+                        else
+                        {
+                            sj = static_cast<int>(rr++ % static_cast<std::size_t>(S));
+                        }
+                        per[static_cast<std::size_t>(sj)].push_back(&o);
+                    }
+                    // cap the imbalance: a hub node would otherwise serialise every device hanging on it
+                    std::size_t const cap{2 * ((ops.size() + static_cast<std::size_t>(S) - 1) / static_cast<std::size_t>(S)) + 4};
+                    std::vector<op_t const*> spill;
+                    for(auto& v: per)
+                    {
+                        while(v.size() > cap)
+                        {
+                            spill.push_back(v.back());
+                            v.pop_back();
+                        }
+                    }
+                    for(auto const* o: spill)
+                    {
+                        auto it{std::min_element(per.begin(), per.end(), [](auto const& a, auto const& b) { return a.size() < b.size(); })};
+                        it->push_back(o);
+                    }
+                    for(int sj{}; sj < S; ++sj)
+                    {
+                        auto& v{per[static_cast<std::size_t>(sj)]};
+                        std::stable_sort(v.begin(), v.end(), [](op_t const* a, op_t const* b) { return a->w[0] < b->w[0]; });
+                        auto& dstv{RS[static_cast<std::size_t>(sj)].sec[sec][static_cast<std::size_t>(phase)]};
+                        for(auto const* o: v)
+                        {
+                            rop r;
+                            r.opcode = o->w[0];
+                            r.opnd.assign(o->w.begin() + 1, o->w.end());
+                            dstv.push_back(std::move(r));
+                        }
+                    }
+                };
+                if(!cplx) { deal(prep_ops, 0, 0); }
+                deal(ps.step, 1, 0);
+                deal(ps.head, 2, 0);
+                pr.has_sec[0] = !cplx && !prep_ops.empty();
+                pr.has_sec[1] = !ps.step.empty();
+                pr.has_sec[2] = true;
+
+                // ---- shared-memory slot allocation: column = owner stream, row = order of first touch in that stream
+                std::uint32_t const zero_key{IOP(I_CONST, 0)};
+                auto unit_of = [&](std::uint32_t key) -> std::pair<std::uint32_t, int>  // (first key of the unit, rows)
+                {
+                    std::uint32_t const k{key & ~NEG};
+                    // the padding operand of complex pairs is read as (re, im): 0.0 needs a zero imaginary row as well
+                    if(cplx && k == zero_key) { return {k, 2}; }
+                    if((k >> 29) == I_LANE)
+                    {
+                        std::uint32_t const s{k & 0x1fffffffu};
+                        std::uint8_t const kd{s < lkind.size() ? lkind[s] : static_cast<std::uint8_t>(0)};
+                        if(kd == 1) { return {k, 2}; }
+                        if(kd == 2) { return {k - 1, 2}; }
+                    }
+                    return {k, 1};
+                };
+                // visit every scalar key an op touches: fn(key, is_write)
+                auto visit = [&](rop const& o, auto&& fn)
+                {
+                    if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
+                    {
+                        bool const cx{o.opcode == PE_OP_CDOT};
+                        fn(o.dst, true);
+                        if(cx) { fn(o.dst + 1, true); }
+                        if(o.flags & PE_F_SCALE)
+                        {
+                            fn(o.scale, false);
+                            if(cx) { fn(o.scale + 1, false); }
+                        }
+                        for(auto k: o.sre) { fn(k & ~NEG, false); }
+                        for(auto k: o.sim) { fn(k & ~NEG, false); }
+                        for(auto const& [a, b]: o.pp)
+                        {
+                            fn(a, false);
+                            fn(b, false);
+                            if(cx)
+                            {
+                                fn(a + 1, false);
+                                fn(b + 1, false);
+                            }
+                        }
+                    }
+                    else if(o.opcode != 0xffu)
+                    {
+                        int const no{value_op_outputs(o.opcode)};
+                        for(std::size_t k{}; k < o.opnd.size(); ++k) { fn(o.opnd[k] & ~NEG, static_cast<int>(k) < no); }
+                    }
+                };
+                struct vinfo
+                {
+                    int owner{-1};
+                    int rank{99};
+                    bool written{};
+                    int col{-1}, row{-1};
+                };
+                std::map<std::uint32_t, vinfo> vals;  // key = first key of the unit
+                vals[zero_key];  // the padding operand always exists
+                int const sec_order[3]{2, 1, 0};
+                for(int so{}; so < 3; ++so)
+                {
+                    int const sec{sec_order[so]};
+                    for(int sj{}; sj < S; ++sj)
+                    {
+                        for(auto const& ph: RS[static_cast<std::size_t>(sj)].sec[sec])
+                        {
+                            for(auto const& o: ph)
+                            {
+                                visit(o,
+                                      [&](std::uint32_t key, bool wr)
+                                      {
+                                          auto const [u0, rows]{unit_of(key)};
+                                          (void)rows;
+                                          auto& v{vals[u0]};
+                                          int const rank{wr ? so : 3};
+                                          if(rank < v.rank)
+                                          {
+                                              v.rank = rank;
+                                              v.owner = sj;
+                                          }
+                                          v.written = v.written || wr;
+                                      });
+                            }
+                        }
+                    }
+                }
+                if(vals[zero_key].owner < 0) { vals[zero_key].owner = 0; }
+                std::size_t total_rows{};
+                for(auto const& [k, v]: vals) { total_rows += static_cast<std::size_t>(unit_of(k).second); }
+                int const cap_rows{static_cast<int>((total_rows + static_cast<std::size_t>(S) - 1) / static_cast<std::size_t>(S) * 5 / 4 + 4)};
+                std::vector<int> height(static_cast<std::size_t>(S), 0);
+                std::vector<std::uint32_t> spilled;
+                for(int so{}; so < 3; ++so)
+                {
+                    int const sec{sec_order[so]};
+                    for(int sj{}; sj < S; ++sj)
+                    {
+                        for(auto const& ph: RS[static_cast<std::size_t>(sj)].sec[sec])
+                        {
+                            for(auto const& o: ph)
+                            {
+                                visit(o,
+                                      [&](std::uint32_t key, bool)
+                                      {
+                                          auto const [u0, rows]{unit_of(key)};
+                                          auto& v{vals[u0]};
+                                          if(v.owner != sj || v.col >= 0 || v.row == -2) { return; }
+                                          if(height[static_cast<std::size_t>(sj)] + rows > cap_rows)
+                                          {
+                                              v.row = -2;  // placed after everything else, in the shortest column
+                                              spilled.push_back(u0);
+                                              return;
+                                          }
+                                          v.col = sj;
+                                          v.row = height[static_cast<std::size_t>(sj)];
+                                          height[static_cast<std::size_t>(sj)] += rows;
+                                      });
+                            }
+                        }
+                    }
+                }
+                // anything never touched by its owner in program order (cannot happen) or spilled
+                for(auto& [k, v]: vals)
+                {
+                    if(v.col < 0 && v.row != -2)
+                    {
+                        v.row = -2;
+                        spilled.push_back(k);
+                    }
+                }
+                for(auto k: spilled)
+                {
+                    auto& v{vals[k]};
+                    int const rows{unit_of(k).second};
+                    int const cj{static_cast<int>(std::min_element(height.begin(), height.end()) - height.begin())};
+                    v.col = cj;
+                    v.row = height[static_cast<std::size_t>(cj)];
+                    height[static_cast<std::size_t>(cj)] += rows;
+                }
+                int const K{std::max(1, *std::max_element(height.begin(), height.end()))};
+                pr.r_slots = K * S;
+                if(pr.r_slots > PE_R_MAX_SLOTS)
+                {
+                    out.error = "resident program needs more than 32768 shared-memory slots";
+                    pr.resident = false;  // the caller falls back to the HBM-streaming form
+                    pr.built = false;
+                    return;
+                }
+                auto slot_of = [&](std::uint32_t key) -> std::uint32_t
+                {
+                    std::uint32_t const k{key & ~NEG};
+                    auto const [u0, rows]{unit_of(k)};
+                    (void)rows;
+                    auto const& v{vals.at(u0)};
+                    return static_cast<std::uint32_t>((v.row + static_cast<int>(k - u0)) * S + v.col);
+                };
+                auto opnd_of = [&](std::uint32_t key) -> std::uint32_t { return slot_of(key) | ((key & NEG) ? PE_R_NEG : 0u); };
+                pr.r_zero = slot_of(zero_key);
+                for(auto& rs: RS)
+                {
+                    for(auto& sec: rs.sec)
+                    {
+                        for(auto& ph: sec)
+                        {
+                            for(auto& o: ph)
+                            {
+                                if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
+                                {
+                                    o.dst = slot_of(o.dst);
+                                    o.scale = (o.flags & PE_F_SCALE) ? slot_of(o.scale) : pr.r_zero;
+                                    for(auto& k: o.sre) { k = opnd_of(k); }
+                                    for(auto& k: o.sim) { k = opnd_of(k); }
+                                    for(auto& [a, b]: o.pp)
+                                    {
+                                        a = slot_of(a);
+                                        b = slot_of(b);
+                                    }
+                                }
+                                else if(o.opcode != 0xffu)
+                                {
+                                    for(auto& k: o.opnd) { k = opnd_of(k); }
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- load / store table
+                pr.io.clear();
+                auto add_io = [&](std::uint32_t slot, std::uint32_t kind, std::uint32_t fl, std::uint32_t src) { pr.io.push_back({slot | (kind << 16) | (fl << 20), src}); };
+                std::vector<char> is_x(static_cast<std::size_t>(ps.n_lane) + 2, 0);
+                if(cplx)
+                {
+                    for(int j{}; j < n; ++j) { is_x[xs[static_cast<std::size_t>(j)] & 0x1fffffffu] = 1; }
+                }
+                for(auto const& [k, v]: vals)
+                {
+                    std::uint32_t const sp{k >> 29}, sl{k & 0x1fffffffu};
+                    std::uint32_t const slot{static_cast<std::uint32_t>(v.row * S + v.col)};
+                    if(sp == I_CONST)
+                    {
+                        add_io(slot, PE_IO_CONST, PE_IO_LOAD, sl);
+                        if(cplx && k == zero_key) { add_io(slot + static_cast<std::uint32_t>(S), PE_IO_CONST, PE_IO_LOAD, 0u); }
+                    }
+                    else if(sp == I_INST)
+                    {
+                        if(cplx) { add_io(slot, PE_IO_INSTX, PE_IO_LOAD, sl); }
+                        else
+                        {
+                            add_io(slot, PE_IO_U, PE_IO_LOAD | (v.written ? PE_IO_STORE : 0u), sl);
+                        }
+                    }
+                    else if(cplx && sl == static_cast<std::uint32_t>(PE_OPND_SLOT(ps.omega.op))) { add_io(slot, PE_IO_U, PE_IO_LOAD, 0u); }
+                }
+                pr.x_slot.resize(static_cast<std::size_t>(n));
+                pr.x_opnd.resize(static_cast<std::size_t>(n));
+                for(int j{}; j < n; ++j)
+                {
+                    // an unknown no op ever touches (cannot happen for a non-singular system) reads as the zero slot
+                    std::uint32_t const key{xs[static_cast<std::size_t>(j)]};
+                    bool const known{vals.find(unit_of(key).first) != vals.end()};
+                    std::uint32_t const slot{known ? slot_of(key) : pr.r_zero};
+                    pr.x_slot[static_cast<std::size_t>(j)] = slot;
+                    if(cplx)
+                    {
+                        pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_U, static_cast<std::uint32_t>(1 + 2 * j));
+                        if(known)
+                        {
+                            add_io(slot, PE_IO_U, PE_IO_STORE, static_cast<std::uint32_t>(1 + 2 * j));
+                            add_io(slot + static_cast<std::uint32_t>(S), PE_IO_U, PE_IO_STORE, static_cast<std::uint32_t>(2 + 2 * j));
+                        }
+                    }
+                    else
+                    {
+                        pr.x_opnd[static_cast<std::size_t>(j)] = PE_OPND(PE_SP_U, static_cast<std::uint32_t>(j));
+                    }
+                }
+                pr.omega_slot = cplx ? 0 : -1;
+                pr.n_lane_slots = cplx ? 1 + 2 * n : 0;  // HBM lane space: omega + the solution
+                pr.warps = 1;
+                pr.packed_ig = -1;
+                pr.built = true;
+                for(auto const& st: steps)
+                {
+                    if(tree.level[static_cast<std::size_t>(st.node)] == 0) { ++pr.n_leaf_rows; }
+                    else
+                    {
+                        ++pr.n_top_rows;
+                    }
+                }
+            }
 
             void build_program(prog_mode mode)
             {
@@ -910,22 +1797,36 @@ namespace pe_b200
                     a.erase(std::unique(a.begin(), a.end()), a.end());
                 }
 
-                // --- regions: leaves (concurrent) + top
-                int const min_leaf{12};
-                std::vector<int> region{partition(n, adj, G, min_leaf)};
+                // --- regions: elimination tree (resident: recursive dissection; v2: G leaves + one top)
+                bool const resident{(ac ? in.resident_ac : in.resident_real) > 0};
+                int const rS{resident ? (ac ? in.resident_ac : in.resident_real) : 0};
+                etree tree;
                 int n_leaves{};
-                for(int v: region) { n_leaves = std::max(n_leaves, v + 1); }
-                if(n_leaves < 2)
+                if(resident)
                 {
-                    n_leaves = 0;
-                    std::fill(region.begin(), region.end(), -1);
+                    tree = partition_tree(n, adj, rS, 3);
+                    n_leaves = tree.n_leaves;
                     G = 1;
                 }
+                else
+                {
+                    int const min_leaf{12};
+                    std::vector<int> region{partition(n, adj, G, min_leaf)};
+                    for(int v: region) { n_leaves = std::max(n_leaves, v + 1); }
+                    if(n_leaves < 2)
+                    {
+                        n_leaves = 0;
+                        std::fill(region.begin(), region.end(), -1);
+                        G = 1;
+                    }
+                    tree = flat_tree(region, n_leaves);
+                }
+                auto& region{tree.region};
                 pr.n_leaves = static_cast<std::size_t>(n_leaves);
 
                 // --- Markowitz ordering with threshold pivoting on nominal values, one region at a time
-                int const R{n_leaves + 1};  // queue index: leaf id, or n_leaves for the top
-                auto qi = [&](int idx) { return region[static_cast<std::size_t>(idx)] < 0 ? n_leaves : region[static_cast<std::size_t>(idx)]; };
+                int const R{static_cast<int>(tree.parent.size())};
+                auto qi = [&](int idx) { return region[static_cast<std::size_t>(idx)]; };
                 std::vector<std::set<std::pair<int, int>>> rq(static_cast<std::size_t>(R)), cq(static_cast<std::size_t>(R));
                 for(int i{}; i < n; ++i)
                 {
@@ -944,9 +1845,10 @@ namespace pe_b200
                     return m;
                 };
 
-                for(int cur{}; cur < R && !singular; ++cur)
+                for(int cur: tree.order)
                 {
-                    bool const top{cur == n_leaves};
+                    int const up{tree.parent[static_cast<std::size_t>(cur)]};
+                    bool const top{up < 0};
                     auto& RQ{rq[static_cast<std::size_t>(cur)]};
                     auto& CQ{cq[static_cast<std::size_t>(cur)]};
                     for(;;)
@@ -999,7 +1901,8 @@ namespace pe_b200
                         lu_step st;
                         st.r = br;
                         st.c = bc;
-                        st.leaf = top ? -1 : cur;
+                        st.leaf = (!resident && cur < n_leaves) ? cur : -1;
+                        st.node = cur;
                         st.piv = rows[static_cast<std::size_t>(br)][bc];
                         for(int i: colrows[static_cast<std::size_t>(bc)])
                         {
@@ -1075,23 +1978,18 @@ namespace pe_b200
                     }
                     if(!top)
                     {
-                        // rows / columns of this leaf that found no acceptable pivot inside it are promoted to the top
-                        for(auto const& [cnt, i]: RQ) { rq[static_cast<std::size_t>(n_leaves)].insert({cnt, i}); }
-                        for(auto const& [cnt, j]: CQ) { cq[static_cast<std::size_t>(n_leaves)].insert({cnt, j}); }
+                        // rows / columns of this region that found no acceptable pivot inside it are promoted to its parent
+                        for(auto const& [cnt, i]: RQ) { rq[static_cast<std::size_t>(up)].insert({cnt, i}); }
+                        for(auto const& [cnt, j]: CQ) { cq[static_cast<std::size_t>(up)].insert({cnt, j}); }
                         // indices whose row AND column are still active simply change region; a half-eliminated index
                         // (row done, column not, or vice versa) also moves: the restriction only looks at active ones
-                        for(int i{}; i < n; ++i)
-                        {
-                            if(region[static_cast<std::size_t>(i)] == cur && (!row_done[static_cast<std::size_t>(i)] || !col_done[static_cast<std::size_t>(i)]))
-                            {
-                                region[static_cast<std::size_t>(i)] = -1;
-                            }
-                        }
+                        for(auto const& [cnt, i]: RQ) { region[static_cast<std::size_t>(i)] = up; }
+                        for(auto const& [cnt, j]: CQ) { region[static_cast<std::size_t>(j)] = up; }
                         RQ.clear();
                         CQ.clear();
                     }
-                    else if(static_cast<int>(steps.size()) < n) { singular = true; }
                 }
+                if(static_cast<int>(steps.size()) < n) { singular = true; }
                 pr.structurally_singular = singular;
                 pr.nnz_lu = nv.size();
 
@@ -1108,8 +2006,8 @@ namespace pe_b200
                 };
                 auto emit_value_op = [&](stream& S, op_t const& o)
                 {
-                    S.w.push_back(o[0]);
-                    for(std::size_t k{1}; k < o.size(); ++k) { S.w.push_back(xl(o[k])); }
+                    S.w.push_back(o.w[0]);
+                    for(std::size_t k{1}; k < o.w.size(); ++k) { S.w.push_back(xl(o.w[k])); }
                 };
 
                 std::vector<stream> prep_s(static_cast<std::size_t>(G)), step_s(static_cast<std::size_t>(G)), iter_s(static_cast<std::size_t>(G));
@@ -1148,6 +2046,11 @@ namespace pe_b200
                     pr.built = true;
                 };
 
+                if(singular && resident)
+                {
+                    resident_singular(pr, ps, rS, n);
+                    return;
+                }
                 if(singular)
                 {
                     for(auto& s: iter_s)
@@ -1169,11 +2072,6 @@ namespace pe_b200
                     pos_r[static_cast<std::size_t>(steps[k].r)] = static_cast<int>(k);
                     pos_c[static_cast<std::size_t>(steps[k].c)] = static_cast<int>(k);
                 }
-                struct upd
-                {
-                    int l, u;  // l: L entry id; u: U entry id (matrix entries) or pivot-row index (rhs)
-                    int leaf;  // region of the elimination step that generates this update (-1 = top)
-                };
                 std::vector<std::vector<upd>> pairs(n_ent);                          // entry -> updates, in step order
                 std::vector<std::vector<upd>> ypairs(static_cast<std::size_t>(n));   // row -> rhs updates (u = pivot row)
                 std::vector<char> ynz(static_cast<std::size_t>(n), 0);
@@ -1184,13 +2082,23 @@ namespace pe_b200
                     for(std::size_t a{}; a < st.lrows.size(); ++a)
                     {
                         int const i{st.lrows[a]};
-                        for(std::size_t b{}; b < nu; ++b) { pairs[static_cast<std::size_t>(st.t_ent[a * nu + b])].push_back({st.l_ent[a], st.u_ent[b], st.leaf}); }
+                        for(std::size_t b{}; b < nu; ++b) { pairs[static_cast<std::size_t>(st.t_ent[a * nu + b])].push_back({st.l_ent[a], st.u_ent[b], st.leaf, st.node}); }
                         if(ynz[static_cast<std::size_t>(st.r)])
                         {
-                            ypairs[static_cast<std::size_t>(i)].push_back({st.l_ent[a], st.r, st.leaf});
+                            ypairs[static_cast<std::size_t>(i)].push_back({st.l_ent[a], st.r, st.leaf, st.node});
                             ynz[static_cast<std::size_t>(i)] = 1;
                         }
                     }
+                }
+
+                if(resident)
+                {
+                    resident_ctx rc{ps, pr, tree, rS, steps, pairs, ypairs, ynz, orig, n, n_ent};
+                    emit_resident(rc);
+                    for(auto const& p: pairs) { pr.n_fma += p.size(); }
+                    for(auto const& p: ypairs) { pr.n_fma += p.size(); }
+                    for(auto const& st: steps) { pr.n_fma += st.ucols.size(); }
+                    return;
                 }
 
                 // --- slots
@@ -1451,6 +2359,148 @@ namespace pe_b200
             }
         };
     }  // namespace
+
+    // Pack the abstract stream programs into warp vector ops for CTAs of rS * ig threads (pe_b200_program.h):
+    // a warp carries C = 32 / ig consecutive streams; ops of the C streams are aligned greedily by opcode, missing
+    // operands padded with the zero slot (exact: x + (-0.0) = x, fma(-0, 0, x) = x).
+    void program::pack(int ig)
+    {
+        if(!resident || ig == packed_ig) { return; }
+        int const C{std::max(1, 32 / std::max(ig, 1))};
+        int const W{std::max(1, (rS + C - 1) / C)};
+        n_warps = W;
+        packed_ig = ig;
+        words.clear();
+        sec_off.assign(static_cast<std::size_t>(3 * W), PE_NO_SECTION);
+        std::uint32_t const zero{r_zero};
+        std::uint32_t const pad_src{(zero | PE_R_NEG) | ((zero | PE_R_NEG) << 16)};
+        std::uint32_t const pad_pair{zero | (zero << 16)};
+        max_warp_words = 0;
+        for(int sec{}; sec < 3; ++sec)
+        {
+            if(!has_sec[sec] && sec != 2) { continue; }
+            for(int wv{}; wv < W; ++wv)
+            {
+                sec_off[static_cast<std::size_t>(sec * W + wv)] = static_cast<std::uint32_t>(words.size());
+                std::size_t const w_begin{words.size()};
+                std::size_t n_ph{};
+                for(int c{}; c < C; ++c)
+                {
+                    int const sj{wv * C + c};
+                    if(sj < rS) { n_ph = std::max(n_ph, rstreams[static_cast<std::size_t>(sj)].sec[sec].size()); }
+                }
+                for(std::size_t ph{}; ph < n_ph; ++ph)
+                {
+                    std::vector<rphase const*> col(static_cast<std::size_t>(C), nullptr);
+                    std::vector<std::size_t> idx(static_cast<std::size_t>(C), 0);
+                    for(int c{}; c < C; ++c)
+                    {
+                        int const sj{wv * C + c};
+                        if(sj < rS && ph < rstreams[static_cast<std::size_t>(sj)].sec[sec].size()) { col[static_cast<std::size_t>(c)] = &rstreams[static_cast<std::size_t>(sj)].sec[sec][ph]; }
+                    }
+                    for(;;)
+                    {
+                        // opcode present at the head of the most columns
+                        std::map<std::uint32_t, int> votes;
+                        for(int c{}; c < C; ++c)
+                        {
+                            auto const* v{col[static_cast<std::size_t>(c)]};
+                            if(v != nullptr && idx[static_cast<std::size_t>(c)] < v->size()) { ++votes[(*v)[idx[static_cast<std::size_t>(c)]].opcode]; }
+                        }
+                        if(votes.empty()) { break; }
+                        std::uint32_t opc{};
+                        int best{-1};
+                        for(auto const& [o, k]: votes)
+                        {
+                            if(k > best)
+                            {
+                                best = k;
+                                opc = o;
+                            }
+                        }
+                        std::vector<rop const*> act(static_cast<std::size_t>(C), nullptr);
+                        for(int c{}; c < C; ++c)
+                        {
+                            auto const* v{col[static_cast<std::size_t>(c)]};
+                            if(v != nullptr && idx[static_cast<std::size_t>(c)] < v->size() && (*v)[idx[static_cast<std::size_t>(c)]].opcode == opc)
+                            {
+                                act[static_cast<std::size_t>(c)] = &(*v)[idx[static_cast<std::size_t>(c)]];
+                                ++idx[static_cast<std::size_t>(c)];
+                            }
+                        }
+                        if(opc == PE_OP_DOT || opc == PE_OP_CDOT)
+                        {
+                            bool const cx{opc == PE_OP_CDOT};
+                            std::size_t na{}, ni{}, nb{};
+                            std::uint32_t ufl{};
+                            for(auto const* o: act)
+                            {
+                                if(o == nullptr) { continue; }
+                                na = std::max(na, (o->sre.size() + 1) / 2);
+                                ni = std::max(ni, (o->sim.size() + 1) / 2);
+                                nb = std::max(nb, o->pp.size());
+                                ufl |= o->flags;
+                            }
+                            words.push_back(opc | (static_cast<std::uint32_t>(na) << 8) | (static_cast<std::uint32_t>(nb) << 16) | (ufl << 24));
+                            if(cx) { words.push_back(static_cast<std::uint32_t>(ni)); }
+                            for(auto const* o: act) { words.push_back(o ? (o->dst | PE_R_ACTIVE | (o->flags << 16)) : 0u); }
+                            if(ufl & PE_F_SCALE)
+                            {
+                                for(auto const* o: act) { words.push_back(o ? o->scale : zero); }
+                            }
+                            auto src_rows = [&](bool im, std::size_t rows)
+                            {
+                                for(std::size_t r{}; r < rows; ++r)
+                                {
+                                    for(auto const* o: act)
+                                    {
+                                        if(o == nullptr)
+                                        {
+                                            words.push_back(pad_src);
+                                            continue;
+                                        }
+                                        auto const& sv{im ? o->sim : o->sre};
+                                        std::uint32_t const s0{2 * r < sv.size() ? sv[2 * r] : (zero | PE_R_NEG)};
+                                        std::uint32_t const s1{2 * r + 1 < sv.size() ? sv[2 * r + 1] : (zero | PE_R_NEG)};
+                                        words.push_back(s0 | (s1 << 16));
+                                    }
+                                }
+                            };
+                            src_rows(false, na);
+                            if(cx) { src_rows(true, ni); }
+                            for(std::size_t r{}; r < nb; ++r)
+                            {
+                                for(auto const* o: act) { words.push_back((o && r < o->pp.size()) ? (o->pp[r].first | (o->pp[r].second << 16)) : pad_pair); }
+                            }
+                        }
+                        else
+                        {
+                            std::size_t rows{};
+                            for(auto const* o: act)
+                            {
+                                if(o) { rows = std::max(rows, o->opnd.size()); }
+                            }
+                            words.push_back(opc | (static_cast<std::uint32_t>(rows) << 8));
+                            for(std::size_t r{}; r < rows; ++r)
+                            {
+                                for(auto const* o: act)
+                                {
+                                    std::uint32_t wd{(o && r < o->opnd.size()) ? o->opnd[r] : zero};
+                                    if(o && r == 0) { wd |= PE_R_VACTIVE; }
+                                    words.push_back(wd);
+                                }
+                            }
+                        }
+                    }
+                    if(ph + 1 < n_ph) { words.push_back(PE_OP_BAR); }
+                }
+                words.push_back(PE_OP_END);
+                max_warp_words = std::max(max_warp_words, words.size() - w_begin);
+            }
+        }
+        // the interpreter may read a few rows past the last header speculatively
+        for(int k{}; k < 4 * C + 4; ++k) { words.push_back(PE_OP_END); }
+    }
 
     std::unique_ptr<compiled> compile_circuit(compile_input const& in)
     {

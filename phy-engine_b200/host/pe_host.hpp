@@ -150,8 +150,39 @@ namespace pe_b200
         COUNT = 4
     };
 
+    // ---- resident (shared-memory) form of a program: abstract per-stream op lists + slot allocation, packed into
+    // warp vector-op words once the launch geometry (instance groups per CTA) is known.  See pe_b200_program.h.
+    struct rop
+    {
+        std::uint32_t opcode{};
+        std::uint32_t flags{};
+        std::uint32_t dst{}, scale{};                               // shared-memory slots
+        std::vector<std::uint32_t> sre, sim;                        // slot | neg << 15
+        std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;   // (slot, slot)
+        std::vector<std::uint32_t> opnd;                            // value ops: slot | neg << 15, encoding order
+    };
+    using rphase = std::vector<rop>;
+    struct rstream
+    {
+        std::vector<rphase> sec[3];  // prep, step, iter; every stream holds the same number of phases per section
+    };
+
     struct program
     {
+        // resident form (resident == true: `words` hold vector ops, see pack())
+        bool resident{};
+        int rS{1};                          // streams per instance
+        int r_slots{};                      // shared-memory slots per instance (a multiple of rS)
+        std::uint32_t r_zero{};             // slot holding 0.0 (padding operand)
+        std::vector<rstream> rstreams;      // [rS]
+        std::vector<pe_b200_io> io;
+        std::vector<std::uint32_t> x_slot;  // per unknown: shared-memory slot of the solution (cplx: re, im at + rS)
+        int packed_ig{-1};                  // instance groups per CTA the words were packed for
+        int n_warps{};
+        std::vector<std::uint32_t> sec_off;  // [3][n_warps]
+        bool has_sec[3]{};
+        void pack(int ig);                   // (re)build words / sec_off for CTAs of rS * ig threads
+
         bool built{};
         bool cplx{};
         bool structurally_singular{};
@@ -191,6 +222,8 @@ namespace pe_b200
         std::map<sweep_key, double> swept_lane0;
         int warps_real{1};  // requested warps per CTA for the real-valued programs (DC/TR/TROP)
         int warps_ac{1};    // ... for the AC program
+        int resident_real{0};  // > 0: build the real-valued programs in resident form with this many streams
+        int resident_ac{0};    // > 0: ... the AC program
     };
 
     // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot
@@ -240,6 +273,15 @@ namespace pe_b200
         int subtree_warps{0};  // 0 = choose from the lane count; else the requested G (power of two, <= PE_MAX_WARPS)
         int cc_warps_real{-1}, cc_warps_ac{-1};
         int pick_warps(std::size_t lanes, int n_unknowns) const;
+        // resident (shared-memory) path: streams per instance (-1 = never, 0 = choose, else forced), instances per CTA
+        // and per thread (0 = choose)
+        int res_S{0}, res_I{0}, res_J{0};
+        int cc_res_real{-1}, cc_res_ac{-1};
+        int pick_streams(int n_unknowns) const;
+        bool pick_geometry(program const& pr, int& I, int& J) const;
+        std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_secoff, d_io;
+        std::array<int, static_cast<int>(prog_mode::COUNT)> uploaded_ig{};
+        int last_I{}, last_J{}, last_S{};  // geometry of the last resident launch (0 = the HBM-streaming kernel ran)
 
         // results of the last analyze()
         std::size_t last_lanes{};
@@ -262,6 +304,7 @@ namespace pe_b200
         bool ensure_compiled();
         bool upload_sweeps();
         bool run_phase(prog_mode m, bool with_prep, bool nonlinear, int n_steps, bool time_stepping, double t0, double dt, std::size_t lanes, int ppi);
+        bool run_phase_resident(prog_mode m, bool with_prep, bool nonlinear, int n_steps, bool time_stepping, double t0, double dt, std::size_t lanes, int ppi);
         bool run_prep_only();
         // downloads
         bool get_solution(double* x /* [n_inst][n] */);
@@ -289,6 +332,14 @@ namespace pe_b200
 
         bool analyze();
     };
+
+    // process-wide defaults a new batch starts from (tests and benches run every path through the same API calls)
+    struct path_defaults
+    {
+        int res_S{0}, res_I{0}, res_J{0};
+        int subtree_warps{0};
+    };
+    path_defaults& default_path();
 
     void set_last_error(std::string s);
     char const* last_error();

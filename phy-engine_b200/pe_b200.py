@@ -224,6 +224,9 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_solution_soa.argtypes = [V, ct.c_void_p]
     lib.circuit_batch_set_probes.argtypes = [V, _PSZ, _SZ]
     lib.circuit_batch_set_subtree_warps.argtypes = [V, ct.c_int]
+    lib.circuit_batch_set_resident.argtypes = [V, ct.c_int, ct.c_int, ct.c_int]
+    lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int]
+    lib.circuit_batch_resident_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
     for f in ("circuit_batch_prepare", "circuit_batch_reset_state", "circuit_batch_analyze", "circuit_batch_compile_host"):
         getattr(lib, f).argtypes = [V]
     lib.circuit_batch_lanes.restype = _SZ
@@ -348,6 +351,16 @@ class Batch:
 
     def set_subtree_warps(self, g: int):
         self._rc(self.lib.circuit_batch_set_subtree_warps(self.h, g), "circuit_batch_set_subtree_warps")
+
+    def set_resident(self, streams: int = 0, instances_per_cta: int = 0, instances_per_thread: int = 0):
+        """Resident (shared-memory) solve path: streams -1 = never, 0 = automatic, else a power of two."""
+        self._rc(self.lib.circuit_batch_set_resident(self.h, streams, instances_per_cta, instances_per_thread), "circuit_batch_set_resident")
+
+    def resident_info(self, mode: int) -> dict:
+        v = (ct.c_int64 * 12)()
+        self._rc(self.lib.circuit_batch_resident_info(self.h, mode, v), "circuit_batch_resident_info")
+        keys = ("resident", "streams", "smem_slots", "I", "J", "io_entries", "last_S", "last_I", "last_J", "iter_phases", "words", "max_warp_words")
+        return {k: int(x) for k, x in zip(keys, v)}
 
     def set_param(self, ele: int, name: str, values):
         a = np.ascontiguousarray(values, dtype=np.float64)

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <array>
 #include <unordered_map>
 #include <vector>
 
@@ -19,7 +20,8 @@ namespace emu_trace
     {
         int w_phase{-1}, w_warp{-1};
         int r_phase{-1};
-        uint32_t r_mask{};
+        int r_first{-1};   // first stream that read the slot in r_phase
+        bool r_many{};     // ... and some other stream read it too
     };
 
     static std::unordered_map<double const*, rec> g_map;
@@ -36,9 +38,10 @@ namespace emu_trace
         if(r.r_phase != g_phase)
         {
             r.r_phase = g_phase;
-            r.r_mask = 0;
+            r.r_first = g_warp;
+            r.r_many = false;
         }
-        r.r_mask |= 1u << g_warp;
+        else if(r.r_first != g_warp) { r.r_many = true; }
     }
 
     static inline void on_store(double const* p)
@@ -46,7 +49,7 @@ namespace emu_trace
         if(!tracked(p)) { return; }
         auto& r = g_map[p];
         if(r.w_phase == g_phase && r.w_warp != g_warp) { ++g_races; }
-        if(r.r_phase == g_phase && (r.r_mask & ~(1u << g_warp)) != 0u) { ++g_races; }
+        if(r.r_phase == g_phase && (r.r_many || r.r_first != g_warp)) { ++g_races; }
         r.w_phase = g_phase;
         r.w_warp = g_warp;
     }
@@ -55,6 +58,7 @@ namespace emu_trace
 #define PE_TRACE_LD(ptr) emu_trace::on_load(ptr)
 #define PE_TRACE_ST(ptr) emu_trace::on_store(ptr)
 #include "../../phy-engine_b200/csrc/pe_b200_interp.h"
+#include "../../phy-engine_b200/csrc/pe_b200_rinterp.h"
 
 namespace
 {
@@ -142,6 +146,9 @@ extern "C"
     void pe_b200_timing_enable(int) {}
     double pe_b200_timing_collect(void) { return 0.0; }
 
+    size_t pe_b200_resident_smem_limit(void) { return 227 * 1024 - 1024; }
+
+    uint64_t pe_emu_resident_launches(void);
     uint64_t pe_emu_races(void) { return emu_trace::g_races; }
     uint64_t pe_emu_unbalanced_barriers(void) { return g_unbalanced; }
     void pe_emu_trace(int on) { emu_trace::g_on = on != 0; }
@@ -211,6 +218,275 @@ extern "C"
                 r.status[lane] = status;
                 r.solves[lane] += solves;
             }
+        }
+        return 0;
+    }
+}
+
+// ---- resident programs: one CTA (S streams x I instances, workspace in "shared memory") at a time --------------------
+namespace
+{
+    uint64_t g_resident_launches = 0;
+
+    template <int J>
+    void run_resident(pe_b200_rrun const& r)
+    {
+        using namespace pe_rinterp;
+        uint32_t const I = (uint32_t)r.I, IG = I / J, S = (uint32_t)r.S;
+        uint32_t const T = S * IG, W = T / 32, C = 32 / IG;
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        int64_t const n_cta = (r.n_lanes + I - 1) / I;
+        std::vector<double> ws((size_t)r.n_slots * I);
+        struct tstate
+        {
+            bool real_lane[J], counted[J], ok[J], done[J];
+            int32_t status[J];
+            uint32_t solves[J];
+        };
+        std::vector<tstate> ts(T);
+        for(int64_t cta = 0; cta < n_cta; ++cta)
+        {
+            // poison the workspace: a slot read before it is loaded or written shows up as NaN in the results
+            for(auto& v: ws) { v = __builtin_nan(""); }
+            emu_trace::g_map.clear();
+            emu_trace::g_phase = 0;
+            uint32_t s_flags[3][32] = {};
+            for(uint32_t tid = 0; tid < T; ++tid)
+            {
+                uint32_t const ig = tid % IG;
+                int64_t const lane0 = cta * I + ig * J;
+                auto& st = ts[tid];
+                for(int j = 0; j < J; ++j)
+                {
+                    st.real_lane[j] = lane0 + j < r.n_lanes;
+                    st.status[j] = st.real_lane[j] ? r.status[lane0 + j] : (int32_t)PE_ST_SINGULAR;
+                    st.counted[j] = st.real_lane[j] && st.status[j] == PE_ST_OK;
+                    st.ok[j] = st.counted[j];
+                    st.solves[j] = 0;
+                }
+            }
+            bool const trace_was = emu_trace::g_on;
+            emu_trace::g_on = false;
+            for(int32_t e = 0; e < r.n_io; ++e)
+            {
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
+                uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
+                for(uint32_t i = 0; i < I; ++i)
+                {
+                    int64_t const lane = cta * I + i;
+                    bool const real = lane < r.n_lanes;
+                    double v;
+                    if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+                    else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + lane]; }
+                    else { v = r.wx[(int64_t)io.src * r.LSx + (real ? lane / r.ppi : 0)]; }
+                    ws[(size_t)(io.slot_kind & 0xffffu) * I + i] = v;
+                }
+            }
+            emu_trace::g_on = trace_was;
+            double t = r.t0;
+
+            // one section: warps advance phase by phase; within a phase thread after thread (no cross-thread
+            // dependency may exist inside a phase: the race detector checks exactly that)
+            auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 2>>& nconv, std::vector<std::array<bool, 2>>& fail)
+            {
+                std::vector<uint32_t const*> pc(W);
+                for(uint32_t w = 0; w < W; ++w) { pc[w] = r.words + r.sec_off[sec * W + w]; }
+                for(;;)
+                {
+                    int n_bar = 0, n_end = 0;
+                    for(uint32_t w = 0; w < W; ++w)
+                    {
+                        for(;;)
+                        {
+                            uint32_t len = 0;
+                            int kind = V_END;
+                            for(uint32_t l = 0; l < 32; ++l)
+                            {
+                                uint32_t const tid = w * 32 + l;
+                                uint32_t const ig = tid % IG;
+                                rctx c;
+                                c.ws = ws.data() + ig * J;
+                                c.I = I;
+                                c.S = S;
+                                c.C = C;
+                                c.col = l / IG;
+                                emu_trace::g_warp = (int)(tid / IG);
+                                bool en[J], nc[J], fl[J];
+                                for(int j = 0; j < J; ++j)
+                                {
+                                    en[j] = use_done ? !ts[tid].done[j] : ts[tid].ok[j];
+                                    nc[j] = fl[j] = false;
+                                }
+                                kind = rvop<J>(pc[w], c, t, tol, en, check, nc, fl, len);
+                                for(int j = 0; j < J; ++j)
+                                {
+                                    nconv[tid][j] = nconv[tid][j] || nc[j];
+                                    fail[tid][j] = fail[tid][j] || fl[j];
+                                }
+                                if(kind == V_END || kind == V_BAR || kind == V_BAD) { break; }
+                            }
+                            if(kind == V_BAD)
+                            {
+                                if(getenv("PE_EMU_DEBUG")) { fprintf(stderr, "emu: bad op sec %d warp %u off %ld word %08x\n", sec, w, (long)(pc[w] - r.words), *pc[w]); }
+                                for(uint32_t l = 0; l < 32; ++l)
+                                {
+                                    for(int j = 0; j < J; ++j) { fail[w * 32 + l][j] = true; }
+                                }
+                                ++n_end;
+                                break;
+                            }
+                            if(kind == V_END)
+                            {
+                                ++n_end;
+                                break;
+                            }
+                            pc[w] += len;
+                            if(kind == V_BAR)
+                            {
+                                ++n_bar;
+                                break;
+                            }
+                        }
+                    }
+                    ++emu_trace::g_phase;
+                    if(n_bar != 0 && n_end != 0)
+                    {
+                        ++g_unbalanced;
+                        return;
+                    }
+                    if(n_end != 0) { return; }
+                }
+            };
+            std::vector<std::array<bool, 2>> nconv(T), fail(T);
+            auto clear_flags = [&]()
+            {
+                for(auto& a: nconv) { a = {false, false}; }
+                for(auto& a: fail) { a = {false, false}; }
+            };
+            if(r.has_prep)
+            {
+                clear_flags();
+                run_section(0, false, false, nconv, fail);
+            }
+            for(int32_t s = 0; s < r.n_steps; ++s)
+            {
+                if(r.time_stepping)
+                {
+                    if(r.has_step)
+                    {
+                        clear_flags();
+                        run_section(1, false, false, nconv, fail);
+                    }
+                    t = t + r.dt;
+                }
+                for(uint32_t tid = 0; tid < T; ++tid)
+                {
+                    for(int j = 0; j < J; ++j) { ts[tid].done[j] = !ts[tid].ok[j]; }
+                }
+                int32_t it = 0;
+                int fi = 0;
+                for(;;)
+                {
+                    for(uint32_t i = 0; i < 32; ++i) { s_flags[fi][i] = 0; }
+                    clear_flags();
+                    run_section(2, true, r.nonlinear != 0, nconv, fail);
+                    for(uint32_t tid = 0; tid < T; ++tid)
+                    {
+                        uint32_t const ig = tid % IG;
+                        for(int j = 0; j < J; ++j) { s_flags[fi][ig * J + j] |= (nconv[tid][j] ? 1u : 0u) | (fail[tid][j] ? 2u : 0u); }
+                    }
+                    ++it;
+                    bool all_done = true;
+                    for(uint32_t tid = 0; tid < T; ++tid)
+                    {
+                        uint32_t const ig = tid % IG;
+                        auto& st = ts[tid];
+                        for(int j = 0; j < J; ++j)
+                        {
+                            uint32_t const f = s_flags[fi][ig * J + j];
+                            if(!st.done[j])
+                            {
+                                ++st.solves[j];
+                                if(f & 2u)
+                                {
+                                    st.status[j] = PE_ST_SINGULAR;
+                                    st.ok[j] = false;
+                                    st.done[j] = true;
+                                }
+                                else if(!r.nonlinear || !(f & 1u)) { st.done[j] = true; }
+                                else if(it >= r.max_iter)
+                                {
+                                    st.status[j] = PE_ST_NO_CONVERGENCE;
+                                    st.ok[j] = false;
+                                    st.done[j] = true;
+                                }
+                            }
+                            all_done = all_done && st.done[j];
+                        }
+                    }
+                    if(all_done) { break; }
+                }
+                if(r.wave != nullptr)
+                {
+                    for(uint32_t ig = 0; ig < IG; ++ig)
+                    {
+                        auto const& st = ts[ig];  // stream 0
+                        for(int j = 0; j < J; ++j)
+                        {
+                            if(!st.ok[j]) { continue; }
+                            int64_t const lane = cta * I + ig * J + j;
+                            for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = ws[(size_t)r.probes[p] * I + ig * J + j]; }
+                        }
+                    }
+                }
+            }
+            for(int32_t e = 0; e < r.n_io; ++e)
+            {
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
+                for(uint32_t ig = 0; ig < IG; ++ig)
+                {
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(ts[ig].counted[j]) { r.wu[(int64_t)io.src * r.LSu + cta * I + ig * J + j] = ws[(size_t)(io.slot_kind & 0xffffu) * I + ig * J + j]; }
+                    }
+                }
+            }
+            for(uint32_t ig = 0; ig < IG; ++ig)
+            {
+                for(int j = 0; j < J; ++j)
+                {
+                    if(ts[ig].counted[j])
+                    {
+                        r.status[cta * I + ig * J + j] = ts[ig].status[j];
+                        r.solves[cta * I + ig * J + j] += ts[ig].solves[j];
+                    }
+                }
+            }
+        }
+    }
+}  // namespace
+
+extern "C"
+{
+    uint64_t pe_emu_resident_launches(void) { return g_resident_launches; }
+
+    int pe_b200_launch_resident(pe_b200_rrun const* rp, void*)
+    {
+        if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
+        int const I = rp->I, J = rp->J, S = rp->S;
+        if(I < 1 || I > 32 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024)
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
+            return 1;
+        }
+        ++g_launches;
+        ++g_resident_launches;
+        if(J == 2) { run_resident<2>(*rp); }
+        else
+        {
+            run_resident<1>(*rp);
         }
         return 0;
     }

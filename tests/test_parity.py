@@ -26,10 +26,27 @@ def abi(request):
     return emuapi.emulator()
 
 
-@pytest.fixture(params=[0, 4])
-def warps(request):
-    """0 = automatic warp count, 4 = force the sub-tree parallel schedule where the circuit is large enough"""
-    return request.param
+# Every test runs once per solve path (set as the process-wide default every new batch starts from):
+#   resident        shared-memory kernel, automatic geometry (the product default)
+#   resident-s8     ... forced 8 word streams per instance (4 instances per warp)
+#   resident-s32j2  ... forced 32 streams, 2 instances per CTA handled by the same thread (vector loads)
+#   stream          HBM-streaming kernel, one warp per 32 instances
+#   stream-g4       ... 4 sub-tree warps per 32 instances
+PATHS = {
+    "resident": (0, 0, 0, 0),
+    "resident-s8": (8, 0, 1, 0),
+    "resident-s32j2": (32, 2, 2, 0),
+    "stream": (-1, 0, 0, 0),
+    "stream-g4": (-1, 0, 0, 4),
+}
+
+
+@pytest.fixture(params=list(PATHS), autouse=True)
+def path(request, abi):
+    rc = abi.lib.phy_engine_b200_set_default_path(*PATHS[request.param])
+    assert rc == 0
+    yield request.param
+    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0)
 
 
 def assert_close(got, want, what=""):
@@ -98,7 +115,7 @@ def test_tr_resume_continues_like_reference(ref, abi):
 
 
 @pytest.mark.parametrize("n_sections,n_inst", [(8, 33), (50, 64), (200, 40)])
-def test_rc_ladder_batch_sweep(ref, abi, warps, n_sections, n_inst):
+def test_rc_ladder_batch_sweep(ref, abi, path, n_sections, n_inst):
     nl, info = wl.rc_ladder(n_sections)
     rng = np.random.default_rng(7)
     over = []
@@ -111,12 +128,16 @@ def test_rc_ladder_batch_sweep(ref, abi, warps, n_sections, n_inst):
     c.set_analyze_type(pe.TR)
     c.set_tr(1e-8, 2e-7)
     b = c.batch(n_inst)
-    b.set_subtree_warps(warps)
     for e, name, v in over:
         b.set_param(e, name, v)
     assert b.analyze(), c.abi.last_error()
-    if warps and n_sections >= 200:
-        assert b.program_info(pe.MODE_TR)["warps"] == warps
+    if path == "stream-g4" and n_sections >= 200:
+        assert b.program_info(pe.MODE_TR)["warps"] == 4
+    if path.startswith("resident"):
+        ri = b.resident_info(pe.MODE_TR)
+        assert ri["resident"] == 1 and ri["last_S"] == ri["streams"] and ri["last_I"] > 0
+        if path == "resident-s32j2":
+            assert (ri["last_S"], ri["last_I"], ri["last_J"]) == (32, 2, 2)
     assert (want["ok"] == 1).all()
     assert_close(b.solution(), want["x"].real, "ladder state")
     assert b.total_solves == int(want["solves"].sum())
@@ -227,7 +248,7 @@ def test_ac_single_point(ref, abi):
 
 
 @pytest.mark.parametrize("n_sections,points", [(2, 17), (8, 200), (64, 64)])
-def test_ac_log_sweep_rlc(ref, abi, warps, n_sections, points):
+def test_ac_log_sweep_rlc(ref, abi, path, n_sections, points):
     nl, info = wl.rlc_ladder(n_sections)
     sweep = (pe.SWEEP_LOG, 1e3, 1e10, points)
     rc, rok, rn = ref_solo(nl, pe.AC, ref, sweep=sweep)
@@ -236,7 +257,6 @@ def test_ac_log_sweep_rlc(ref, abi, warps, n_sections, points):
     c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.AC)
     b = c.batch(1)
-    b.set_subtree_warps(warps)
     b.set_ac_sweep(*sweep)
     assert b.analyze(), c.abi.last_error()
     assert (b.ac_omegas() == om).all()  # cumulative-product omegas are bit-identical
