@@ -158,6 +158,9 @@ extern "C"
     /* info[12] = resident, streams, shared-memory slots per instance, I, J (0 = does not fit), io entries,
      * last launch S / I / J (0 = the HBM-streaming kernel ran), phases of the iter section, words, longest warp stream */
     int circuit_batch_resident_info(void* batch, int mode, int64_t* info);
+    /* word offsets [3][n_warps] of the prep / step / iter stream of each warp of the packed resident program (0xffffffff =
+     * absent); returns the number of entries (out may be NULL) */
+    size_t circuit_batch_resident_secoff(void* batch, int mode, uint32_t* out);
     /* per-instance values of one model attribute; values[n_instances] in the attribute's public unit */
     int circuit_batch_set_param(void* batch, size_t vec_pos, size_t chunk_pos, char const* name, size_t name_size, double const* values);
     /* many parameters in one call: values[n_params][n_instances].  Once the batch is prepared and every parameter

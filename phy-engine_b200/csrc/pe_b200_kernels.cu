@@ -120,6 +120,88 @@ namespace
     // ---- resident kernel ---------------------------------------------------------------------------
     // CTA = S streams x I instances, workspace ws[slot][I] in dynamic shared memory for the whole launch.  Thread
     // (stream, ig) executes the vector ops of its warp for the J instances [ig * J, ig * J + J) of the CTA.
+    // Warp-cooperative reader of a warp's program (same interface as pe_rinterp::host_reader).
+    // MAIN stream (headers, masks, warp-uniform rows): three consecutive 128-byte lines are held in registers, lane l
+    // keeping word l of each; a word is handed to the whole warp with one shuffle, and the line after next is already in
+    // flight while the current one is consumed, so L2 latency never sits on the critical path of an op.
+    // SIDE stream (per-column rows, C words each): every lane reads the word of its own column (one coalesced line per
+    // row); the next four rows are kept in flight in a register queue.
+    struct warp_reader
+    {
+        uint32_t const* main;
+        uint32_t const* side;
+        uint32_t w0, w1, w2, line, pos;
+        uint32_t q0, q1, q2, q3, srow;
+        uint32_t C, col, lane;
+        uint32_t cur, m, pos_next;
+
+        __device__ __forceinline__ void init(uint32_t const* main_, uint32_t const* side_, uint32_t C_, uint32_t col_, uint32_t lane_)
+        {
+            main = main_;
+            side = side_;
+            C = C_;
+            col = col_;
+            lane = lane_;
+            line = 0;
+            pos = 0;
+            w0 = __ldg(main + lane);
+            w1 = __ldg(main + 32 + lane);
+            w2 = __ldg(main + 64 + lane);
+            srow = 0;
+            q0 = __ldg(side + col);
+            q1 = __ldg(side + C + col);
+            q2 = __ldg(side + 2 * C + col);
+            q3 = __ldg(side + 3 * C + col);
+        }
+        __device__ __forceinline__ uint32_t peek(uint32_t a) const
+        {
+            uint32_t const l = (a >> 5) - line;
+            uint32_t const v = l == 0u ? w0 : (l == 1u ? w1 : w2);
+            return __shfl_sync(0xffffffffu, v, (int)(a & 31u));
+        }
+        __device__ __forceinline__ uint32_t head() const { return peek(pos); }
+        __device__ __forceinline__ uint32_t open(uint32_t rows)
+        {
+            m = peek(pos + 1u);
+            cur = pos + 2u;
+            pos_next = pos + 2u + rows - (uint32_t)__popc(m);
+            return m;
+        }
+        __device__ __forceinline__ uint32_t next()
+        {
+            uint32_t w;
+            if(m & 1u)
+            {
+                w = q0;
+                q0 = q1;
+                q1 = q2;
+                q2 = q3;
+                q3 = __ldg(side + (srow + 4u) * C + col);
+                ++srow;
+            }
+            else
+            {
+                w = peek(cur);
+                ++cur;
+            }
+            m >>= 1;
+            return w;
+        }
+        __device__ __forceinline__ void advance(uint32_t np)
+        {
+            pos = np;
+            while((pos >> 5) > line)
+            {
+                w0 = w1;
+                w1 = w2;
+                ++line;
+                w2 = __ldg(main + (line + 2u) * 32u + lane);
+            }
+        }
+        __device__ __forceinline__ void close() { advance(pos_next); }
+        __device__ __forceinline__ void bar() { advance(pos + 1u); }
+    };
+
     template <int J, int MAXT>
     __global__ void __launch_bounds__(MAXT, 1) pe_b200_resident_kernel(pe_b200_rrun const r)
     {
@@ -139,6 +221,7 @@ namespace
         c.S = S;
         c.C = 32u / IG;
         c.col = (tid & 31u) / IG;
+        c.stream = stream;
         tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
 
         bool real_lane[J], counted[J], ok[J];
@@ -179,15 +262,21 @@ namespace
         double t = r.t0;
         auto run_section = [&](int sec, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
         {
-            uint32_t const off = __ldg(r.sec_off + sec * n_warps + warp);
-            uint32_t const* pc = r.words + off;
+            warp_reader rd;
+            rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), r.words + __ldg(r.sec_off + (3 + sec) * n_warps + warp), c.C, c.col, tid & 31u);
             for(;;)
             {
-                uint32_t len;
-                int const k = rvop<J>(pc, c, t, tol, en, check, nconv, fail, len);
+                int const k = rvop<J>(rd, c, t, tol, en, check, nconv, fail);
                 if(k == V_END || k == V_BAD) { break; }
-                if(k == V_BAR) { __syncthreads(); }
-                pc += len;
+                if(k == V_BAR)
+                {
+                    __syncthreads();
+                    rd.bar();
+                }
+                else
+                {
+                    rd.close();
+                }
             }
             __syncthreads();  // results of this section are visible to every stream of the CTA
         };

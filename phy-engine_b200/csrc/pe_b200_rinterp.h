@@ -21,7 +21,16 @@ namespace pe_rinterp
         uint32_t S;    // streams per instance = distance (in slots) between re and im of a complex value
         uint32_t C;    // streams (word columns) per warp
         uint32_t col;  // this thread's column
+        uint32_t stream;  // this thread's stream: operand words are relative to it (row * S + ((column - stream) mod S))
     };
+
+    // absolute slot of a stream-relative operand word (S is a power of two)
+    PE_HD uint32_t abs_slot(rctx const& c, uint32_t w)
+    {
+        uint32_t const sm = c.S - 1u;
+        uint32_t const r = w & 0x7fffu;
+        return (r & ~sm) | ((r + c.stream) & sm);
+    }
 
     template <int J>
     struct vd
@@ -61,7 +70,7 @@ namespace pe_rinterp
     template <int J>
     PE_HD vd<J> ldo(rctx const& c, uint32_t w)
     {
-        vd<J> r = ldv<J>(c, PE_R_SLOT(w));
+        vd<J> r = ldv<J>(c, abs_slot(c, w));
         if(w & PE_R_NEG)
         {
             for(int j = 0; j < J; ++j) { r.v[j] = -r.v[j]; }
@@ -101,175 +110,264 @@ namespace pe_rinterp
         V_BAD = 3,
     };
 
-    // Execute the vector op at pc for this thread.  en[j]: stores of instance j are enabled (the lane is still being
-    // solved); nconv / fail accumulate the Newton test and the pivot test.  Returns V_*; len = words to advance.
-    template <int J>
-    PE_HD int rvop(uint32_t const* pc, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J], uint32_t& len)
+    // Word reader of one warp's program (host form; the sm_100a kernel has a warp-cooperative one with the same
+    // interface).  A program is two word sequences: the MAIN stream holds, per vector op, [h0][mask][uniform rows...]
+    // (BAR / END are single words), the SIDE stream the per-column rows (C words each) in consumption order.
+    struct host_reader
     {
-        uint32_t const h = PE_LDW(pc);
-        uint32_t const op = h & 0xffu;
-        uint32_t const C = c.C;
-        uint32_t const* p0 = pc + 1 + c.col;  // row 0, this thread's column
-#define PE_ROW(r) PE_LDW(p0 + (r) * C)
-        switch(op)
+        uint32_t const* p;  // main stream, at the current op
+        uint32_t const* q;  // side stream, at the first per-column row of the current op
+        uint32_t C, col;
+        uint32_t cur{}, m{};
+        uint32_t const* qc{};
+        uint32_t const* p_next{};
+        uint32_t const* q_next{};
+
+        uint32_t head() const { return p[0]; }
+        uint32_t open(uint32_t rows)
         {
-            case PE_OP_END: len = 0; return V_END;
-            case PE_OP_BAR: len = 1; return V_BAR;
-            case PE_OP_DOT:
+            m = p[1];
+            cur = 2;
+            qc = q;
+            uint32_t const pcnt = (uint32_t)__builtin_popcount(m);
+            p_next = p + 2 + rows - pcnt;
+            q_next = q + pcnt * C;
+            return m;
+        }
+        uint32_t next()
+        {
+            uint32_t w;
+            if(m & 1u)
             {
-                uint32_t const na = (h >> 8) & 0xffu, nb = (h >> 16) & 0xffu, ufl = h >> 24;
-                uint32_t const* p = p0;
-                uint32_t const ctl = PE_LDW(p);
-                p += C;
-                uint32_t scale = 0;
-                if(ufl & PE_F_SCALE)
+                w = qc[col];
+                qc += C;
+            }
+            else
+            {
+                w = p[cur++];
+            }
+            m >>= 1;
+            return w;
+        }
+        void close()
+        {
+            p = p_next;
+            q = q_next;
+        }
+        void bar() { p += 1; }
+    };
+
+    // Execute the vector op the reader stands on, for this thread.  en[j]: stores of instance j are enabled (the lane
+    // is still being solved); nconv / fail accumulate the Newton test and the pivot test.  Returns V_*; after V_OK the
+    // caller closes the op on the reader (rd.close()), after V_BAR it steps over the barrier word (rd.bar()).
+    // On the GPU every thread of the warp consumes every row of the op before any divergence (the reader is
+    // warp-cooperative); an idle column then simply does not store.
+    template <int J, class R>
+    PE_HD int rvop(R& rd, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
+    {
+        uint32_t const h = rd.head();
+        uint32_t const op = h & 0xffu;
+        if(op == PE_OP_END) { return V_END; }
+        if(op == PE_OP_BAR) { return V_BAR; }
+        auto fetch = [&]() -> uint32_t { return rd.next(); };
+        if(op == PE_OP_DOT)
+        {
+            uint32_t const na = (h >> 8) & 0x1fu, nb = (h >> 18) & 0x3fu;
+            rd.open(2u + na + nb);
+            uint32_t const ctl = fetch();
+            uint32_t const scale = fetch();
+            constexpr uint32_t MA = 3, MB = 4;
+            vd<J> acc;
+            for(int j = 0; j < J; ++j) { acc.v[j] = 0.0; }
+            if(na <= MA && nb <= MB)
+            {
+                // every operand word of the op is requested before the first one is used
+                uint32_t sw[MA], pw[MB];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for(uint32_t r = 0; r < MA; ++r)
                 {
-                    scale = PE_LDW(p);
-                    p += C;
+                    if(r < na) { sw[r] = fetch(); }
                 }
-                len = 1 + C * (1 + ((ufl & PE_F_SCALE) ? 1u : 0u) + na + nb);
-                vd<J> acc;
-                for(int j = 0; j < J; ++j) { acc.v[j] = 0.0; }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for(uint32_t r = 0; r < MB; ++r)
+                {
+                    if(r < nb) { pw[r] = fetch(); }
+                }
+                if(!(ctl & PE_R_ACTIVE)) { return V_OK; }  // every row has been consumed: idle columns may leave
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for(uint32_t r = 0; r < MA; ++r)
+                {
+                    if(r < na)
+                    {
+                        vd<J> const s0 = ldo<J>(c, sw[r] & 0xffffu);
+                        vd<J> const s1 = ldo<J>(c, sw[r] >> 16);
+                        for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
+                    }
+                }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+                for(uint32_t r = 0; r < MB; ++r)
+                {
+                    if(r < nb)
+                    {
+                        vd<J> const a = ldv<J>(c, abs_slot(c, pw[r]));
+                        vd<J> const b = ldv<J>(c, abs_slot(c, pw[r] >> 16));
+                        for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
+                    }
+                }
+            }
+            else
+            {
+                // long op: rows are consumed one by one by the whole warp; an idle column computes on its padding
+                // operands and does not store (host: it skips the loads, the race detector watches real accesses only)
+                bool const idle = !(ctl & PE_R_ACTIVE);
+#if !defined(__CUDA_ARCH__)
+                if(idle) { return V_OK; }
+#endif
                 for(uint32_t r = 0; r < na; ++r)
                 {
-                    uint32_t const w = PE_LDW(p);
-                    p += C;
+                    uint32_t const w = fetch();
                     vd<J> const s0 = ldo<J>(c, w & 0xffffu);
                     vd<J> const s1 = ldo<J>(c, w >> 16);
                     for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
                 }
                 for(uint32_t r = 0; r < nb; ++r)
                 {
-                    uint32_t const w = PE_LDW(p);
-                    p += C;
-                    vd<J> const a = ldv<J>(c, PE_R_SLOT(w));
-                    vd<J> const b = ldv<J>(c, PE_R_SLOT(w >> 16));
+                    uint32_t const w = fetch();
+                    vd<J> const a = ldv<J>(c, abs_slot(c, w));
+                    vd<J> const b = ldv<J>(c, abs_slot(c, w >> 16));
                     for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
                 }
-                uint32_t const flags = ctl >> 16;
-                if(!(ctl & PE_R_ACTIVE)) { return V_OK; }
-                if(flags & PE_F_SCALE)
-                {
-                    vd<J> const s = ldv<J>(c, PE_R_SLOT(scale));
-                    for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], s.v[j]); }
-                }
-                if(flags & PE_F_RECIP)
-                {
-                    for(int j = 0; j < J; ++j)
-                    {
-                        if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { fail[j] = true; }
-                        acc.v[j] = PE_DIV(1.0, acc.v[j]);
-                    }
-                }
-                uint32_t const dst = PE_R_SLOT(ctl);
-                if(check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I)))
-                {
-                    // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
-                    vd<J> const xo = ldv<J>(c, dst);
-                    bool const br = (flags & PE_F_CHECK_I) != 0u;
-                    double const at = br ? tol.i_abstol : tol.v_abstol, rt = br ? tol.i_reltol : tol.v_reltol;
-                    for(int j = 0; j < J; ++j)
-                    {
-                        double const tl = at + rt * fmax(fabs(acc.v[j]), fabs(xo.v[j]));
-                        if(fabs(acc.v[j] - xo.v[j]) > tl) { nconv[j] = true; }
-                    }
-                }
-                stv<J>(c, dst, acc, en);
-                return V_OK;
+                if(idle) { return V_OK; }
             }
-            case PE_OP_CDOT:
+            uint32_t const flags = ctl >> 16;
+            if(flags & PE_F_SCALE)
             {
-                uint32_t const nre = (h >> 8) & 0xffu, nb = (h >> 16) & 0xffu, ufl = h >> 24;
-                uint32_t const nim = PE_LDW(pc + 1) & 0xffu;
-                uint32_t const* p = p0 + 1;  // two uniform header words
-                uint32_t const ctl = PE_LDW(p);
-                p += C;
-                uint32_t scale = 0;
-                if(ufl & PE_F_SCALE)
-                {
-                    scale = PE_LDW(p);
-                    p += C;
-                }
-                len = 2 + C * (1 + ((ufl & PE_F_SCALE) ? 1u : 0u) + nre + nim + nb);
-                vd<J> are, aim;
-                for(int j = 0; j < J; ++j) { are.v[j] = aim.v[j] = 0.0; }
-                for(uint32_t r = 0; r < nre; ++r)
-                {
-                    uint32_t const w = PE_LDW(p);
-                    p += C;
-                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
-                    vd<J> const s1 = ldo<J>(c, w >> 16);
-                    for(int j = 0; j < J; ++j) { are.v[j] = PE_ADD(PE_ADD(are.v[j], s0.v[j]), s1.v[j]); }
-                }
-                for(uint32_t r = 0; r < nim; ++r)
-                {
-                    uint32_t const w = PE_LDW(p);
-                    p += C;
-                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
-                    vd<J> const s1 = ldo<J>(c, w >> 16);
-                    for(int j = 0; j < J; ++j) { aim.v[j] = PE_ADD(PE_ADD(aim.v[j], s0.v[j]), s1.v[j]); }
-                }
-                for(uint32_t r = 0; r < nb; ++r)
-                {
-                    uint32_t const w = PE_LDW(p);
-                    p += C;
-                    uint32_t const sa = PE_R_SLOT(w), sb = PE_R_SLOT(w >> 16);
-                    vd<J> const ar = ldv<J>(c, sa), ai = ldv<J>(c, sa + c.S);
-                    vd<J> const br = ldv<J>(c, sb), bi = ldv<J>(c, sb + c.S);
-                    for(int j = 0; j < J; ++j)
-                    {
-                        are.v[j] = fma(-ar.v[j], br.v[j], are.v[j]);
-                        are.v[j] = fma(ai.v[j], bi.v[j], are.v[j]);
-                        aim.v[j] = fma(-ar.v[j], bi.v[j], aim.v[j]);
-                        aim.v[j] = fma(-ai.v[j], br.v[j], aim.v[j]);
-                    }
-                }
-                uint32_t const flags = ctl >> 16;
-                if(!(ctl & PE_R_ACTIVE)) { return V_OK; }
-                if(flags & PE_F_SCALE)
-                {
-                    uint32_t const ss = PE_R_SLOT(scale);
-                    vd<J> const sr = ldv<J>(c, ss), si = ldv<J>(c, ss + c.S);
-                    for(int j = 0; j < J; ++j)
-                    {
-                        double const nr = are.v[j] * sr.v[j] - aim.v[j] * si.v[j];
-                        double const ni = are.v[j] * si.v[j] + aim.v[j] * sr.v[j];
-                        are.v[j] = nr;
-                        aim.v[j] = ni;
-                    }
-                }
-                if(flags & PE_F_RECIP)
-                {
-                    for(int j = 0; j < J; ++j)
-                    {
-                        double const m = are.v[j] * are.v[j] + aim.v[j] * aim.v[j];
-                        if(!(m > 0.0) || !isfinite(m)) { fail[j] = true; }
-                        double const s = 1.0 / m;
-                        are.v[j] = are.v[j] * s;
-                        aim.v[j] = -aim.v[j] * s;
-                    }
-                }
-                uint32_t const dst = PE_R_SLOT(ctl);
-                stv<J>(c, dst, are, en);
-                stv<J>(c, dst + c.S, aim, en);
-                return V_OK;
+                vd<J> const sc = ldv<J>(c, abs_slot(c, scale));
+                for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], sc.v[j]); }
             }
-            default: break;
+            if(flags & PE_F_RECIP)
+            {
+                for(int j = 0; j < J; ++j)
+                {
+                    if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { fail[j] = true; }
+                    acc.v[j] = PE_DIV(1.0, acc.v[j]);
+                }
+            }
+            uint32_t const dst = abs_slot(c, ctl);
+            if(check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I)))
+            {
+                // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
+                vd<J> const xo = ldv<J>(c, dst);
+                bool const br = (flags & PE_F_CHECK_I) != 0u;
+                double const at = br ? tol.i_abstol : tol.v_abstol, rt = br ? tol.i_reltol : tol.v_reltol;
+                for(int j = 0; j < J; ++j)
+                {
+                    double const tl = at + rt * fmax(fabs(acc.v[j]), fabs(xo.v[j]));
+                    if(fabs(acc.v[j] - xo.v[j]) > tl) { nconv[j] = true; }
+                }
+            }
+            stv<J>(c, dst, acc, en);
+            return V_OK;
+        }
+        if(op == PE_OP_CDOT)
+        {
+            uint32_t const nre = (h >> 8) & 0x1fu, nim = (h >> 13) & 0x1fu, nb = (h >> 18) & 0x3fu;
+            rd.open(2u + nre + nim + nb);
+            uint32_t const ctl = fetch();
+            uint32_t const scale = fetch();
+            bool const idle = !(ctl & PE_R_ACTIVE);
+#if !defined(__CUDA_ARCH__)
+            if(idle) { return V_OK; }
+#endif
+            vd<J> are, aim;
+            for(int j = 0; j < J; ++j) { are.v[j] = aim.v[j] = 0.0; }
+            for(uint32_t r = 0; r < nre; ++r)
+            {
+                uint32_t const w = fetch();
+                vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                vd<J> const s1 = ldo<J>(c, w >> 16);
+                for(int j = 0; j < J; ++j) { are.v[j] = PE_ADD(PE_ADD(are.v[j], s0.v[j]), s1.v[j]); }
+            }
+            for(uint32_t r = 0; r < nim; ++r)
+            {
+                uint32_t const w = fetch();
+                vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                vd<J> const s1 = ldo<J>(c, w >> 16);
+                for(int j = 0; j < J; ++j) { aim.v[j] = PE_ADD(PE_ADD(aim.v[j], s0.v[j]), s1.v[j]); }
+            }
+            for(uint32_t r = 0; r < nb; ++r)
+            {
+                uint32_t const w = fetch();
+                uint32_t const sa = abs_slot(c, w), sb = abs_slot(c, w >> 16);
+                vd<J> const ar = ldv<J>(c, sa), ai = ldv<J>(c, sa + c.S);
+                vd<J> const br = ldv<J>(c, sb), bi = ldv<J>(c, sb + c.S);
+                for(int j = 0; j < J; ++j)
+                {
+                    are.v[j] = fma(-ar.v[j], br.v[j], are.v[j]);
+                    are.v[j] = fma(ai.v[j], bi.v[j], are.v[j]);
+                    aim.v[j] = fma(-ar.v[j], bi.v[j], aim.v[j]);
+                    aim.v[j] = fma(-ai.v[j], br.v[j], aim.v[j]);
+                }
+            }
+            if(idle) { return V_OK; }
+            uint32_t const flags = ctl >> 16;
+            if(flags & PE_F_SCALE)
+            {
+                uint32_t const ss = abs_slot(c, scale);
+                vd<J> const sr = ldv<J>(c, ss), si = ldv<J>(c, ss + c.S);
+                for(int j = 0; j < J; ++j)
+                {
+                    double const nr = are.v[j] * sr.v[j] - aim.v[j] * si.v[j];
+                    double const ni = are.v[j] * si.v[j] + aim.v[j] * sr.v[j];
+                    are.v[j] = nr;
+                    aim.v[j] = ni;
+                }
+            }
+            if(flags & PE_F_RECIP)
+            {
+                for(int j = 0; j < J; ++j)
+                {
+                    double const mm = are.v[j] * are.v[j] + aim.v[j] * aim.v[j];
+                    if(!(mm > 0.0) || !isfinite(mm)) { fail[j] = true; }
+                    double const sc = 1.0 / mm;
+                    are.v[j] = are.v[j] * sc;
+                    aim.v[j] = -aim.v[j] * sc;
+                }
+            }
+            uint32_t const dst = abs_slot(c, ctl);
+            stv<J>(c, dst, are, en);
+            stv<J>(c, dst + c.S, aim, en);
+            return V_OK;
         }
         // ---- value ops: a = operand rows; row 0 carries the ACTIVE bit
-        uint32_t const rows = (h >> 8) & 0xffu;
+        uint32_t const rows = (h >> 8) & 0x1fu;
         if(op < PE_OP_RECIP || op > PE_OP_PMOS_EVAL)
         {
             // unknown opcode (also what the compiler emits for a structurally singular system)
             for(int j = 0; j < J; ++j) { fail[j] = true; }
-            len = 0;
             return V_BAD;
         }
-        len = 1 + C * rows;
-        uint32_t const w0 = PE_ROW(0);
-        if(!(w0 & PE_R_VACTIVE)) { return V_OK; }
-#define PE_LDR(r) ldo<J>(c, PE_ROW(r) & 0xffffu)
-#define PE_STR(r, val) stv<J>(c, PE_R_SLOT(PE_ROW(r)), (val), en)
+        rd.open(rows);
+        uint32_t ow[13];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for(uint32_t r = 0; r < 13u; ++r)
+        {
+            ow[r] = 0u;
+            if(r < rows) { ow[r] = fetch(); }
+        }
+        if(!(ow[0] & PE_R_VACTIVE)) { return V_OK; }
+#define PE_LDR(r) ldo<J>(c, ow[r] & 0xffffu)
+#define PE_STR(r, val) stv<J>(c, abs_slot(c, ow[r]), (val), en)
         switch(op)
         {
             case PE_OP_RECIP:
@@ -455,9 +553,7 @@ namespace pe_rinterp
         }
 #undef PE_LDR
 #undef PE_STR
-#undef PE_ROW
         for(int j = 0; j < J; ++j) { fail[j] = true; }
-        len = 0;
         return V_BAD;
     }
 }  // namespace pe_rinterp

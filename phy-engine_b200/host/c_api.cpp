@@ -534,6 +534,16 @@ extern "C"
         return 0;
     }
 
+    size_t circuit_batch_resident_secoff(void* b, int mode, uint32_t* out)
+    {
+        if(b == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
+        auto* bp{static_cast<batch*>(b)};
+        if(!bp->cc) { return 0; }
+        auto const& so{bp->cc->prog[static_cast<std::size_t>(mode)].sec_off};
+        if(out != nullptr) { std::memcpy(out, so.data(), so.size() * sizeof(std::uint32_t)); }
+        return so.size();
+    }
+
     int circuit_batch_set_stream(void* b, void* s)
     {
         if(b == nullptr) { return 1; }

@@ -1088,6 +1088,26 @@ namespace pe_b200
                     }
                     for(int v: hubs) { t.region[static_cast<std::size_t>(v)] = root; }
                 }
+                // separators of one level are owned by consecutive streams (level 1 first), so that a level keeps whole
+                // warps busy instead of one thread in every warp; every stream still owns at most one node per level
+                {
+                    std::vector<int> seps;
+                    for(std::size_t k{}; k < t.parent.size(); ++k)
+                    {
+                        if(t.level[k] > 0) { seps.push_back(static_cast<int>(k)); }
+                    }
+                    std::stable_sort(seps.begin(),
+                                     seps.end(),
+                                     [&](int a, int b)
+                                     {
+                                         if(t.level[static_cast<std::size_t>(a)] != t.level[static_cast<std::size_t>(b)])
+                                         {
+                                             return t.level[static_cast<std::size_t>(a)] < t.level[static_cast<std::size_t>(b)];
+                                         }
+                                         return t.stream[static_cast<std::size_t>(a)] < t.stream[static_cast<std::size_t>(b)];
+                                     });
+                    for(std::size_t k{}; k < seps.size(); ++k) { t.stream[static_cast<std::size_t>(seps[k])] = static_cast<int>(k); }
+                }
                 t.n_leaves = leaf_counter;
                 t.n_levels = t.level[static_cast<std::size_t>(root)] + 1;
                 t.order.resize(t.parent.size());
@@ -1301,7 +1321,8 @@ namespace pe_b200
                 auto emit_dot = [&](int sj, int phase, std::uint32_t dst, std::uint32_t flags, std::uint32_t scale, std::vector<std::uint32_t> const& sre,
                                     std::vector<std::uint32_t> const& sim, std::vector<std::pair<std::uint32_t, std::uint32_t>> const& pp)
                 {
-                    std::size_t const max_src{500}, max_pair{250};
+                    // a vector op holds at most 32 rows (one mask bit each): ctl, scale, packed sources, pairs
+                    std::size_t const max_src{cplx ? 12u : 16u}, max_pair{cplx ? 16u : 20u};
                     auto& dstv{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(phase)]};
                     std::size_t ri{}, ii{}, pi{};
                     bool first{true};
@@ -1494,7 +1515,62 @@ namespace pe_b200
                 pr.has_sec[1] = !ps.step.empty();
                 pr.has_sec[2] = true;
 
-                // ---- shared-memory slot allocation: column = owner stream, row = order of first touch in that stream
+                // ---- global alignment: within every phase the S op lists are merged position by position (greedy on
+                // the op signature), bubbles fill the gaps.  Isomorphic sub-trees end up executing the same op at the same
+                // position, which is what makes their operand rows warp-uniform after the relative slot encoding below.
+                auto signature = [](rop const& o) -> std::uint64_t
+                {
+                    return (static_cast<std::uint64_t>(o.opcode) << 56) ^ (static_cast<std::uint64_t>(o.flags) << 48) ^ (static_cast<std::uint64_t>(o.sre.size()) << 36) ^
+                           (static_cast<std::uint64_t>(o.sim.size()) << 24) ^ (static_cast<std::uint64_t>(o.pp.size()) << 12) ^ static_cast<std::uint64_t>(o.opnd.size());
+                };
+                for(int sec{}; sec < 3; ++sec)
+                {
+                    std::size_t const nph{RS[0].sec[sec].size()};
+                    for(std::size_t ph{}; ph < nph; ++ph)
+                    {
+                        std::vector<rphase> outl(static_cast<std::size_t>(S));
+                        std::vector<std::size_t> idx(static_cast<std::size_t>(S), 0);
+                        for(;;)
+                        {
+                            std::map<std::uint64_t, int> votes;
+                            for(int sj{}; sj < S; ++sj)
+                            {
+                                auto const& l{RS[static_cast<std::size_t>(sj)].sec[sec][ph]};
+                                if(idx[static_cast<std::size_t>(sj)] < l.size()) { ++votes[signature(l[idx[static_cast<std::size_t>(sj)]])]; }
+                            }
+                            if(votes.empty()) { break; }
+                            std::uint64_t best_sig{};
+                            int best{-1};
+                            for(auto const& [sg, k]: votes)
+                            {
+                                if(k > best)
+                                {
+                                    best = k;
+                                    best_sig = sg;
+                                }
+                            }
+                            for(int sj{}; sj < S; ++sj)
+                            {
+                                auto& l{RS[static_cast<std::size_t>(sj)].sec[sec][ph]};
+                                auto& o{outl[static_cast<std::size_t>(sj)]};
+                                if(idx[static_cast<std::size_t>(sj)] < l.size() && signature(l[idx[static_cast<std::size_t>(sj)]]) == best_sig)
+                                {
+                                    o.push_back(std::move(l[idx[static_cast<std::size_t>(sj)]]));
+                                    ++idx[static_cast<std::size_t>(sj)];
+                                }
+                                else
+                                {
+                                    rop b;
+                                    b.bubble = 1;
+                                    o.push_back(std::move(b));
+                                }
+                            }
+                        }
+                        for(int sj{}; sj < S; ++sj) { RS[static_cast<std::size_t>(sj)].sec[sec][ph] = std::move(outl[static_cast<std::size_t>(sj)]); }
+                    }
+                }
+
+                // ---- shared-memory slot allocation
                 std::uint32_t const zero_key{IOP(I_CONST, 0)};
                 auto unit_of = [&](std::uint32_t key) -> std::pair<std::uint32_t, int>  // (first key of the unit, rows)
                 {
@@ -1503,16 +1579,17 @@ namespace pe_b200
                     if(cplx && k == zero_key) { return {k, 2}; }
                     if((k >> 29) == I_LANE)
                     {
-                        std::uint32_t const s{k & 0x1fffffffu};
-                        std::uint8_t const kd{s < lkind.size() ? lkind[s] : static_cast<std::uint8_t>(0)};
+                        std::uint32_t const sl{k & 0x1fffffffu};
+                        std::uint8_t const kd{sl < lkind.size() ? lkind[sl] : static_cast<std::uint8_t>(0)};
                         if(kd == 1) { return {k, 2}; }
                         if(kd == 2) { return {k - 1, 2}; }
                     }
                     return {k, 1};
                 };
-                // visit every scalar key an op touches: fn(key, is_write)
+                // the scalar keys an op touches, in a canonical role order: fn(key, is_write)
                 auto visit = [&](rop const& o, auto&& fn)
                 {
+                    if(o.bubble) { return; }
                     if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
                     {
                         bool const cx{o.opcode == PE_OP_CDOT};
@@ -1547,10 +1624,12 @@ namespace pe_b200
                     int owner{-1};
                     int rank{99};
                     bool written{};
+                    bool replicated{};
                     int col{-1}, row{-1};
+                    std::set<int> users;
                 };
                 std::map<std::uint32_t, vinfo> vals;  // key = first key of the unit
-                vals[zero_key];  // the padding operand always exists
+                vals[zero_key];                       // the padding operand always exists
                 int const sec_order[3]{2, 1, 0};
                 for(int so{}; so < 3; ++so)
                 {
@@ -1564,9 +1643,7 @@ namespace pe_b200
                                 visit(o,
                                       [&](std::uint32_t key, bool wr)
                                       {
-                                          auto const [u0, rows]{unit_of(key)};
-                                          (void)rows;
-                                          auto& v{vals[u0]};
+                                          auto& v{vals[unit_of(key).first]};
                                           int const rank{wr ? so : 3};
                                           if(rank < v.rank)
                                           {
@@ -1574,65 +1651,82 @@ namespace pe_b200
                                               v.owner = sj;
                                           }
                                           v.written = v.written || wr;
+                                          if((key >> 29) == I_CONST && v.users.size() < 64) { v.users.insert(sj); }
                                       });
                             }
+                        }
+                    }
+                }
+                // constants many streams read get one copy per column (relative offset 0 => warp-uniform operand words)
+                int n_rep_rows{};
+                {
+                    std::size_t const many{std::max<std::size_t>(2, static_cast<std::size_t>(S) / 8)};
+                    for(auto& [k, v]: vals)
+                    {
+                        if((k >> 29) != I_CONST || v.written) { continue; }
+                        if(k == zero_key || (S > 1 && v.users.size() >= many))
+                        {
+                            v.replicated = true;
+                            v.col = 0;
+                            v.row = n_rep_rows;
+                            n_rep_rows += unit_of(k).second;
                         }
                     }
                 }
                 if(vals[zero_key].owner < 0) { vals[zero_key].owner = 0; }
-                std::size_t total_rows{};
-                for(auto const& [k, v]: vals) { total_rows += static_cast<std::size_t>(unit_of(k).second); }
-                int const cap_rows{static_cast<int>((total_rows + static_cast<std::size_t>(S) - 1) / static_cast<std::size_t>(S) * 5 / 4 + 4)};
-                std::vector<int> height(static_cast<std::size_t>(S), 0);
-                std::vector<std::uint32_t> spilled;
+                std::vector<int> next_free(static_cast<std::size_t>(S), n_rep_rows);
                 for(int so{}; so < 3; ++so)
                 {
                     int const sec{sec_order[so]};
-                    for(int sj{}; sj < S; ++sj)
+                    std::size_t const nph{RS[0].sec[sec].size()};
+                    for(std::size_t ph{}; ph < nph; ++ph)
                     {
-                        for(auto const& ph: RS[static_cast<std::size_t>(sj)].sec[sec])
+                        std::size_t const npos{RS[0].sec[sec][ph].size()};
+                        for(std::size_t pos{}; pos < npos; ++pos)
                         {
-                            for(auto const& o: ph)
+                            // role-major: the r-th key of every active stream is allocated together, on a common row
+                            std::vector<std::vector<std::uint32_t>> keys(static_cast<std::size_t>(S));
+                            std::size_t max_roles{};
+                            for(int sj{}; sj < S; ++sj)
                             {
-                                visit(o,
-                                      [&](std::uint32_t key, bool)
-                                      {
-                                          auto const [u0, rows]{unit_of(key)};
-                                          auto& v{vals[u0]};
-                                          if(v.owner != sj || v.col >= 0 || v.row == -2) { return; }
-                                          if(height[static_cast<std::size_t>(sj)] + rows > cap_rows)
-                                          {
-                                              v.row = -2;  // placed after everything else, in the shortest column
-                                              spilled.push_back(u0);
-                                              return;
-                                          }
-                                          v.col = sj;
-                                          v.row = height[static_cast<std::size_t>(sj)];
-                                          height[static_cast<std::size_t>(sj)] += rows;
-                                      });
+                                visit(RS[static_cast<std::size_t>(sj)].sec[sec][ph][pos], [&](std::uint32_t key, bool) { keys[static_cast<std::size_t>(sj)].push_back(key); });
+                                max_roles = std::max(max_roles, keys[static_cast<std::size_t>(sj)].size());
+                            }
+                            for(std::size_t r{}; r < max_roles; ++r)
+                            {
+                                int row{-1};
+                                std::vector<std::pair<int, std::uint32_t>> todo;
+                                for(int sj{}; sj < S; ++sj)
+                                {
+                                    if(r >= keys[static_cast<std::size_t>(sj)].size()) { continue; }
+                                    auto const [u0, rows]{unit_of(keys[static_cast<std::size_t>(sj)][r])};
+                                    (void)rows;
+                                    auto& v{vals[u0]};
+                                    if(v.owner != sj || v.col >= 0) { continue; }
+                                    v.col = sj;  // claimed (row set below)
+                                    todo.push_back({sj, u0});
+                                    row = std::max(row, next_free[static_cast<std::size_t>(sj)]);
+                                }
+                                for(auto const& [sj, u0]: todo)
+                                {
+                                    vals[u0].row = row;
+                                    next_free[static_cast<std::size_t>(sj)] = row + unit_of(u0).second;
+                                }
                             }
                         }
                     }
                 }
-                // anything never touched by its owner in program order (cannot happen) or spilled
                 for(auto& [k, v]: vals)
                 {
-                    if(v.col < 0 && v.row != -2)
+                    if(v.col < 0)  // never touched by its owner in program order (cannot happen)
                     {
-                        v.row = -2;
-                        spilled.push_back(k);
+                        int const cj{static_cast<int>(std::min_element(next_free.begin(), next_free.end()) - next_free.begin())};
+                        v.col = cj;
+                        v.row = next_free[static_cast<std::size_t>(cj)];
+                        next_free[static_cast<std::size_t>(cj)] += unit_of(k).second;
                     }
                 }
-                for(auto k: spilled)
-                {
-                    auto& v{vals[k]};
-                    int const rows{unit_of(k).second};
-                    int const cj{static_cast<int>(std::min_element(height.begin(), height.end()) - height.begin())};
-                    v.col = cj;
-                    v.row = height[static_cast<std::size_t>(cj)];
-                    height[static_cast<std::size_t>(cj)] += rows;
-                }
-                int const K{std::max(1, *std::max_element(height.begin(), height.end()))};
+                int const K{std::max(1, *std::max_element(next_free.begin(), next_free.end()))};
                 pr.r_slots = K * S;
                 if(pr.r_slots > PE_R_MAX_SLOTS)
                 {
@@ -1641,6 +1735,8 @@ namespace pe_b200
                     pr.built = false;
                     return;
                 }
+                // absolute slot of a key; operand words are stream-relative: row * S + ((col - stream) mod S), 0 for a
+                // replicated constant; the interpreter adds its own stream index back (mod S)
                 auto slot_of = [&](std::uint32_t key) -> std::uint32_t
                 {
                     std::uint32_t const k{key & ~NEG};
@@ -1649,31 +1745,40 @@ namespace pe_b200
                     auto const& v{vals.at(u0)};
                     return static_cast<std::uint32_t>((v.row + static_cast<int>(k - u0)) * S + v.col);
                 };
-                auto opnd_of = [&](std::uint32_t key) -> std::uint32_t { return slot_of(key) | ((key & NEG) ? PE_R_NEG : 0u); };
-                pr.r_zero = slot_of(zero_key);
-                for(auto& rs: RS)
+                auto rel_of = [&](std::uint32_t key, int sj) -> std::uint32_t
                 {
-                    for(auto& sec: rs.sec)
+                    std::uint32_t const k{key & ~NEG};
+                    auto const [u0, rows]{unit_of(k)};
+                    (void)rows;
+                    auto const& v{vals.at(u0)};
+                    int const d{v.replicated ? 0 : ((v.col - sj) % S + S) % S};
+                    return static_cast<std::uint32_t>((v.row + static_cast<int>(k - u0)) * S + d) | ((key & NEG) ? PE_R_NEG : 0u);
+                };
+                pr.r_zero = slot_of(zero_key);  // row * S (column 0 of a replicated row): valid as a relative word for every stream
+                for(int sj{}; sj < S; ++sj)
+                {
+                    for(auto& sec: RS[static_cast<std::size_t>(sj)].sec)
                     {
                         for(auto& ph: sec)
                         {
                             for(auto& o: ph)
                             {
+                                if(o.bubble) { continue; }
                                 if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
                                 {
-                                    o.dst = slot_of(o.dst);
-                                    o.scale = (o.flags & PE_F_SCALE) ? slot_of(o.scale) : pr.r_zero;
-                                    for(auto& k: o.sre) { k = opnd_of(k); }
-                                    for(auto& k: o.sim) { k = opnd_of(k); }
+                                    o.dst = rel_of(o.dst, sj);
+                                    o.scale = (o.flags & PE_F_SCALE) ? rel_of(o.scale, sj) : pr.r_zero;
+                                    for(auto& k: o.sre) { k = rel_of(k, sj); }
+                                    for(auto& k: o.sim) { k = rel_of(k, sj); }
                                     for(auto& [a, b]: o.pp)
                                     {
-                                        a = slot_of(a);
-                                        b = slot_of(b);
+                                        a = rel_of(a, sj);
+                                        b = rel_of(b, sj);
                                     }
                                 }
                                 else if(o.opcode != 0xffu)
                                 {
-                                    for(auto& k: o.opnd) { k = opnd_of(k); }
+                                    for(auto& k: o.opnd) { k = rel_of(k, sj); }
                                 }
                             }
                         }
@@ -1693,8 +1798,12 @@ namespace pe_b200
                     std::uint32_t const slot{static_cast<std::uint32_t>(v.row * S + v.col)};
                     if(sp == I_CONST)
                     {
-                        add_io(slot, PE_IO_CONST, PE_IO_LOAD, sl);
-                        if(cplx && k == zero_key) { add_io(slot + static_cast<std::uint32_t>(S), PE_IO_CONST, PE_IO_LOAD, 0u); }
+                        int const copies{v.replicated ? S : 1};
+                        for(int cj{}; cj < copies; ++cj)
+                        {
+                            add_io(slot + static_cast<std::uint32_t>(cj), PE_IO_CONST, PE_IO_LOAD, sl);
+                            if(cplx && k == zero_key) { add_io(slot + static_cast<std::uint32_t>(S + cj), PE_IO_CONST, PE_IO_LOAD, 0u); }
+                        }
                     }
                     else if(sp == I_INST)
                     {
@@ -2360,9 +2469,11 @@ namespace pe_b200
         };
     }  // namespace
 
-    // Pack the abstract stream programs into warp vector ops for CTAs of rS * ig threads (pe_b200_program.h):
-    // a warp carries C = 32 / ig consecutive streams; ops of the C streams are aligned greedily by opcode, missing
-    // operands padded with the zero slot (exact: x + (-0.0) = x, fma(-0, 0, x) = x).
+    // Pack the (globally aligned) stream programs into warp vector ops for CTAs of rS * ig threads
+    // (pe_b200_program.h): a warp carries C = 32 / ig consecutive streams.  Per position the C ops become rows of operand
+    // words; a row whose words agree over every active column is stored once (warp-uniform), otherwise once per column.
+    // Missing operands are padded with the zero slot (exact: x + (-0.0) = x, fma(-0, 0, x) = x).  Identical warp
+    // streams (isomorphic sub-trees) share one copy of the words.
     void program::pack(int ig)
     {
         if(!resident || ig == packed_ig) { return; }
@@ -2371,18 +2482,21 @@ namespace pe_b200
         n_warps = W;
         packed_ig = ig;
         words.clear();
-        sec_off.assign(static_cast<std::size_t>(3 * W), PE_NO_SECTION);
+        sec_off.assign(static_cast<std::size_t>(6 * W), PE_NO_SECTION);  // [main | side][section][warp]
         std::uint32_t const zero{r_zero};
         std::uint32_t const pad_src{(zero | PE_R_NEG) | ((zero | PE_R_NEG) << 16)};
         std::uint32_t const pad_pair{zero | (zero << 16)};
         max_warp_words = 0;
+        std::map<std::pair<std::vector<std::uint32_t>, std::vector<std::uint32_t>>, std::pair<std::uint32_t, std::uint32_t>> seen;  // warp streams -> offsets
+        std::vector<std::uint32_t> ww, sw;  // main stream (headers, masks, uniform rows) and side stream (per-column rows)
+        std::vector<std::vector<std::uint32_t>> rows;  // rows[r][c]
         for(int sec{}; sec < 3; ++sec)
         {
             if(!has_sec[sec] && sec != 2) { continue; }
             for(int wv{}; wv < W; ++wv)
             {
-                sec_off[static_cast<std::size_t>(sec * W + wv)] = static_cast<std::uint32_t>(words.size());
-                std::size_t const w_begin{words.size()};
+                ww.clear();
+                sw.clear();
                 std::size_t n_ph{};
                 for(int c{}; c < C; ++c)
                 {
@@ -2391,43 +2505,31 @@ namespace pe_b200
                 }
                 for(std::size_t ph{}; ph < n_ph; ++ph)
                 {
-                    std::vector<rphase const*> col(static_cast<std::size_t>(C), nullptr);
-                    std::vector<std::size_t> idx(static_cast<std::size_t>(C), 0);
+                    std::size_t n_pos{};
                     for(int c{}; c < C; ++c)
                     {
                         int const sj{wv * C + c};
-                        if(sj < rS && ph < rstreams[static_cast<std::size_t>(sj)].sec[sec].size()) { col[static_cast<std::size_t>(c)] = &rstreams[static_cast<std::size_t>(sj)].sec[sec][ph]; }
+                        if(sj < rS && ph < rstreams[static_cast<std::size_t>(sj)].sec[sec].size()) { n_pos = std::max(n_pos, rstreams[static_cast<std::size_t>(sj)].sec[sec][ph].size()); }
                     }
-                    for(;;)
+                    for(std::size_t pos{}; pos < n_pos; ++pos)
                     {
-                        // opcode present at the head of the most columns
-                        std::map<std::uint32_t, int> votes;
-                        for(int c{}; c < C; ++c)
-                        {
-                            auto const* v{col[static_cast<std::size_t>(c)]};
-                            if(v != nullptr && idx[static_cast<std::size_t>(c)] < v->size()) { ++votes[(*v)[idx[static_cast<std::size_t>(c)]].opcode]; }
-                        }
-                        if(votes.empty()) { break; }
-                        std::uint32_t opc{};
-                        int best{-1};
-                        for(auto const& [o, k]: votes)
-                        {
-                            if(k > best)
-                            {
-                                best = k;
-                                opc = o;
-                            }
-                        }
                         std::vector<rop const*> act(static_cast<std::size_t>(C), nullptr);
+                        rop const* any{nullptr};
                         for(int c{}; c < C; ++c)
                         {
-                            auto const* v{col[static_cast<std::size_t>(c)]};
-                            if(v != nullptr && idx[static_cast<std::size_t>(c)] < v->size() && (*v)[idx[static_cast<std::size_t>(c)]].opcode == opc)
+                            int const sj{wv * C + c};
+                            if(sj >= rS || ph >= rstreams[static_cast<std::size_t>(sj)].sec[sec].size()) { continue; }
+                            auto const& l{rstreams[static_cast<std::size_t>(sj)].sec[sec][ph]};
+                            if(pos < l.size() && !l[pos].bubble)
                             {
-                                act[static_cast<std::size_t>(c)] = &(*v)[idx[static_cast<std::size_t>(c)]];
-                                ++idx[static_cast<std::size_t>(c)];
+                                act[static_cast<std::size_t>(c)] = &l[pos];
+                                any = &l[pos];
                             }
                         }
+                        if(any == nullptr) { continue; }  // no stream of this warp works at this position
+                        std::uint32_t const opc{any->opcode};
+                        rows.clear();
+                        std::uint32_t h0{};
                         if(opc == PE_OP_DOT || opc == PE_OP_CDOT)
                         {
                             bool const cx{opc == PE_OP_CDOT};
@@ -2441,65 +2543,116 @@ namespace pe_b200
                                 nb = std::max(nb, o->pp.size());
                                 ufl |= o->flags;
                             }
-                            words.push_back(opc | (static_cast<std::uint32_t>(na) << 8) | (static_cast<std::uint32_t>(nb) << 16) | (ufl << 24));
-                            if(cx) { words.push_back(static_cast<std::uint32_t>(ni)); }
-                            for(auto const* o: act) { words.push_back(o ? (o->dst | PE_R_ACTIVE | (o->flags << 16)) : 0u); }
-                            if(ufl & PE_F_SCALE)
+                            h0 = opc | (static_cast<std::uint32_t>(na) << 8) | (static_cast<std::uint32_t>(cx ? ni : 0) << 13) | (static_cast<std::uint32_t>(nb) << 18) | (ufl << 24);
+                            auto add_row = [&](auto&& word_of)
                             {
-                                for(auto const* o: act) { words.push_back(o ? o->scale : zero); }
-                            }
-                            auto src_rows = [&](bool im, std::size_t rows)
+                                rows.emplace_back(static_cast<std::size_t>(C));
+                                for(int c{}; c < C; ++c) { rows.back()[static_cast<std::size_t>(c)] = word_of(act[static_cast<std::size_t>(c)]); }
+                            };
+                            add_row([&](rop const* o) { return o ? (o->dst | PE_R_ACTIVE | (o->flags << 16)) : 0u; });
+                            add_row([&](rop const* o) { return (o && (o->flags & PE_F_SCALE)) ? o->scale : zero; });
+                            auto src_rows = [&](bool im, std::size_t nr)
                             {
-                                for(std::size_t r{}; r < rows; ++r)
+                                for(std::size_t r{}; r < nr; ++r)
                                 {
-                                    for(auto const* o: act)
-                                    {
-                                        if(o == nullptr)
+                                    add_row(
+                                        [&](rop const* o) -> std::uint32_t
                                         {
-                                            words.push_back(pad_src);
-                                            continue;
-                                        }
-                                        auto const& sv{im ? o->sim : o->sre};
-                                        std::uint32_t const s0{2 * r < sv.size() ? sv[2 * r] : (zero | PE_R_NEG)};
-                                        std::uint32_t const s1{2 * r + 1 < sv.size() ? sv[2 * r + 1] : (zero | PE_R_NEG)};
-                                        words.push_back(s0 | (s1 << 16));
-                                    }
+                                            if(o == nullptr) { return pad_src; }
+                                            auto const& sv{im ? o->sim : o->sre};
+                                            std::uint32_t const s0{2 * r < sv.size() ? sv[2 * r] : (zero | PE_R_NEG)};
+                                            std::uint32_t const s1{2 * r + 1 < sv.size() ? sv[2 * r + 1] : (zero | PE_R_NEG)};
+                                            return s0 | (s1 << 16);
+                                        });
                                 }
                             };
                             src_rows(false, na);
                             if(cx) { src_rows(true, ni); }
                             for(std::size_t r{}; r < nb; ++r)
                             {
-                                for(auto const* o: act) { words.push_back((o && r < o->pp.size()) ? (o->pp[r].first | (o->pp[r].second << 16)) : pad_pair); }
+                                add_row([&](rop const* o) { return (o && r < o->pp.size()) ? (o->pp[r].first | (o->pp[r].second << 16)) : pad_pair; });
                             }
                         }
                         else
                         {
-                            std::size_t rows{};
+                            std::size_t nr{};
                             for(auto const* o: act)
                             {
-                                if(o) { rows = std::max(rows, o->opnd.size()); }
+                                if(o) { nr = std::max(nr, o->opnd.size()); }
                             }
-                            words.push_back(opc | (static_cast<std::uint32_t>(rows) << 8));
-                            for(std::size_t r{}; r < rows; ++r)
+                            h0 = opc | (static_cast<std::uint32_t>(nr) << 8);
+                            for(std::size_t r{}; r < nr; ++r)
                             {
-                                for(auto const* o: act)
+                                rows.emplace_back(static_cast<std::size_t>(C));
+                                for(int c{}; c < C; ++c)
                                 {
+                                    auto const* o{act[static_cast<std::size_t>(c)]};
                                     std::uint32_t wd{(o && r < o->opnd.size()) ? o->opnd[r] : zero};
                                     if(o && r == 0) { wd |= PE_R_VACTIVE; }
-                                    words.push_back(wd);
+                                    rows.back()[static_cast<std::size_t>(c)] = wd;
                                 }
                             }
                         }
+                        // uniform rows: row 0 carries the activity bit, so it is uniform only when every column works; the
+                        // other rows are never looked at by an idle column, which simply copies an active one
+                        std::uint32_t mask{};
+                        for(std::size_t r{}; r < rows.size() && r < 32; ++r)
+                        {
+                            auto& rw{rows[r]};
+                            bool uni{true};
+                            std::uint32_t first{};
+                            bool have{false};
+                            for(int c{}; c < C; ++c)
+                            {
+                                bool const on{act[static_cast<std::size_t>(c)] != nullptr};
+                                if(r == 0 && !on) { uni = false; }
+                                if(!on) { continue; }
+                                if(!have)
+                                {
+                                    first = rw[static_cast<std::size_t>(c)];
+                                    have = true;
+                                }
+                                else if(rw[static_cast<std::size_t>(c)] != first) { uni = false; }
+                            }
+                            if(C == 1) { uni = true; }
+                            if(!uni) { mask |= 1u << r; }
+                            else
+                            {
+                                rw.assign(1, first);
+                            }
+                        }
+                        ww.push_back(h0);
+                        ww.push_back(mask);
+                        for(std::size_t r{}; r < rows.size(); ++r)
+                        {
+                            auto& dst{(mask >> r) & 1u ? sw : ww};
+                            dst.insert(dst.end(), rows[r].begin(), rows[r].end());
+                        }
                     }
-                    if(ph + 1 < n_ph) { words.push_back(PE_OP_BAR); }
+                    if(ph + 1 < n_ph) { ww.push_back(PE_OP_BAR); }
                 }
-                words.push_back(PE_OP_END);
-                max_warp_words = std::max(max_warp_words, words.size() - w_begin);
+                ww.push_back(PE_OP_END);
+                max_warp_words = std::max(max_warp_words, ww.size() + sw.size());
+                auto key{std::make_pair(ww, sw)};
+                auto it{seen.find(key)};
+                if(it == seen.end())
+                {
+                    // main streams start on a 128-byte line; both streams are read a few lines / rows ahead
+                    while(words.size() % 32 != 0) { words.push_back(PE_OP_END); }
+                    std::uint32_t const o_main{static_cast<std::uint32_t>(words.size())};
+                    words.insert(words.end(), ww.begin(), ww.end());
+                    for(int k{}; k < 128; ++k) { words.push_back(PE_OP_END); }
+                    while(words.size() % 32 != 0) { words.push_back(PE_OP_END); }
+                    std::uint32_t const o_side{static_cast<std::uint32_t>(words.size())};
+                    words.insert(words.end(), sw.begin(), sw.end());
+                    for(int k{}; k < 8 * C; ++k) { words.push_back(0u); }
+                    it = seen.emplace(std::move(key), std::make_pair(o_main, o_side)).first;
+                }
+                sec_off[static_cast<std::size_t>(sec * W + wv)] = it->second.first;
+                sec_off[static_cast<std::size_t>(3 * W + sec * W + wv)] = it->second.second;
             }
         }
-        // the interpreter may read a few rows past the last header speculatively
-        for(int k{}; k < 4 * C + 4; ++k) { words.push_back(PE_OP_END); }
+        for(int k{}; k < 64; ++k) { words.push_back(PE_OP_END); }
     }
 
     std::unique_ptr<compiled> compile_circuit(compile_input const& in)

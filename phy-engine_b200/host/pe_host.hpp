@@ -156,10 +156,12 @@ namespace pe_b200
     {
         std::uint32_t opcode{};
         std::uint32_t flags{};
+        std::uint8_t bubble{};  // no op for this stream at this (globally aligned) position
         std::uint32_t dst{}, scale{};                               // shared-memory slots
-        std::vector<std::uint32_t> sre, sim;                        // slot | neg << 15
-        std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;   // (slot, slot)
-        std::vector<std::uint32_t> opnd;                            // value ops: slot | neg << 15, encoding order
+        // operand words are stream-relative: row * S + ((column - stream) mod S), | neg << 15 for sources
+        std::vector<std::uint32_t> sre, sim;
+        std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;
+        std::vector<std::uint32_t> opnd;  // value ops, encoding order
     };
     using rphase = std::vector<rop>;
     struct rstream

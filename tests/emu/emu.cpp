@@ -290,8 +290,14 @@ namespace
             // dependency may exist inside a phase: the race detector checks exactly that)
             auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 2>>& nconv, std::vector<std::array<bool, 2>>& fail)
             {
-                std::vector<uint32_t const*> pc(W);
-                for(uint32_t w = 0; w < W; ++w) { pc[w] = r.words + r.sec_off[sec * W + w]; }
+                std::vector<host_reader> rdw(W);
+                for(uint32_t w = 0; w < W; ++w)
+                {
+                    rdw[w].p = r.words + r.sec_off[sec * W + w];
+                    rdw[w].q = r.words + r.sec_off[3 * W + sec * W + w];
+                    rdw[w].C = C;
+                    rdw[w].col = 0;
+                }
                 for(;;)
                 {
                     int n_bar = 0, n_end = 0;
@@ -299,8 +305,8 @@ namespace
                     {
                         for(;;)
                         {
-                            uint32_t len = 0;
                             int kind = V_END;
+                            host_reader after = rdw[w];
                             for(uint32_t l = 0; l < 32; ++l)
                             {
                                 uint32_t const tid = w * 32 + l;
@@ -311,6 +317,7 @@ namespace
                                 c.S = S;
                                 c.C = C;
                                 c.col = l / IG;
+                                c.stream = tid / IG;
                                 emu_trace::g_warp = (int)(tid / IG);
                                 bool en[J], nc[J], fl[J];
                                 for(int j = 0; j < J; ++j)
@@ -318,7 +325,12 @@ namespace
                                     en[j] = use_done ? !ts[tid].done[j] : ts[tid].ok[j];
                                     nc[j] = fl[j] = false;
                                 }
-                                kind = rvop<J>(pc[w], c, t, tol, en, check, nc, fl, len);
+                                host_reader rd = rdw[w];
+                                rd.col = c.col;
+                                kind = rvop<J>(rd, c, t, tol, en, check, nc, fl);
+                                if(kind == V_OK) { rd.close(); }
+                                if(kind == V_BAR) { rd.bar(); }
+                                after = rd;
                                 for(int j = 0; j < J; ++j)
                                 {
                                     nconv[tid][j] = nconv[tid][j] || nc[j];
@@ -328,7 +340,7 @@ namespace
                             }
                             if(kind == V_BAD)
                             {
-                                if(getenv("PE_EMU_DEBUG")) { fprintf(stderr, "emu: bad op sec %d warp %u off %ld word %08x\n", sec, w, (long)(pc[w] - r.words), *pc[w]); }
+                                if(getenv("PE_EMU_DEBUG")) { fprintf(stderr, "emu: bad op sec %d warp %u off %ld word %08x\n", sec, w, (long)(rdw[w].p - r.words), *rdw[w].p); }
                                 for(uint32_t l = 0; l < 32; ++l)
                                 {
                                     for(int j = 0; j < J; ++j) { fail[w * 32 + l][j] = true; }
@@ -341,7 +353,7 @@ namespace
                                 ++n_end;
                                 break;
                             }
-                            pc[w] += len;
+                            rdw[w] = after;
                             if(kind == V_BAR)
                             {
                                 ++n_bar;
