@@ -155,8 +155,12 @@ extern "C"
      * power of two), `instances_per_cta` (0 = automatic, else a power of two <= 32), `instances_per_thread` (0 = automatic,
      * 1 or 2).  A circuit whose workspace does not fit one CTA's shared memory runs on the HBM-streaming kernel. */
     int circuit_batch_set_resident(void* batch, int streams, int instances_per_cta, int instances_per_thread);
-    /* info[12] = resident, streams, shared-memory slots per instance, I, J (0 = does not fit), io entries,
-     * last launch S / I / J (0 = the HBM-streaming kernel ran), phases of the iter section, words, longest warp stream */
+    /* where a tree-scheduled program keeps its workspace: 0 = automatic (shared memory for small circuits, HBM with one
+     * warp per sub-tree otherwise), 1 = shared memory, 2 = HBM */
+    int circuit_batch_set_workspace(void* batch, int where);
+    /* info[13] = resident, streams, workspace slots per instance, I, J (0 = does not fit), io entries,
+     * last launch S / I / J (0 = the flat HBM-streaming kernel ran), phases of the iter section, words, longest warp
+     * stream, workspace in HBM (1) or shared memory (0) */
     int circuit_batch_resident_info(void* batch, int mode, int64_t* info);
     /* word offsets [3][n_warps] of the prep / step / iter stream of each warp of the packed resident program (0xffffffff =
      * absent); returns the number of entries (out may be NULL) */
@@ -208,8 +212,8 @@ extern "C"
     int circuit_batch_swept_values(void* batch, long long slot, double* out);
 
     /* process-wide defaults every batch created afterwards (including the one behind circuit_analyze) starts from:
-     * the arguments of circuit_batch_set_resident and circuit_batch_set_subtree_warps */
-    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps);
+     * the arguments of circuit_batch_set_resident, circuit_batch_set_subtree_warps and circuit_batch_set_workspace */
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace);
     int phy_engine_b200_device_count(void);
     uint64_t phy_engine_b200_launch_count(void);
     /* device-side timing of the solve kernels (CUDA events on the launching stream): enable, then read-and-reset the

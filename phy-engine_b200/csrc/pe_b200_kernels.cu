@@ -200,15 +200,18 @@ namespace
         }
         __device__ __forceinline__ void close() { advance(pos_next); }
         __device__ __forceinline__ void bar() { advance(pos + 1u); }
+        __device__ __forceinline__ void skip() { advance(((pos >> 5) + 1u) << 5); }
     };
 
-    template <int J, int MAXT>
-    __global__ void __launch_bounds__(MAXT, 1) pe_b200_resident_kernel(pe_b200_rrun const r)
+    template <int J, int MAXT, bool HBM>
+    __global__ void __launch_bounds__(MAXT, HBM ? 2 : 1) pe_b200_resident_kernel(pe_b200_rrun const r)
     {
-        extern __shared__ __align__(16) double ws[];
+        extern __shared__ __align__(16) double ws_shared[];
         __shared__ uint32_t s_flags[3][32];
 
         using namespace pe_rinterp;
+        // HBM form: the CTA's 32 lanes own columns [32 * blockIdx.x, +32) of the global workspace ws[slot][LSw]
+        double* const ws = HBM ? r.wsg + (int64_t)blockIdx.x * 32 : ws_shared;
         uint32_t const I = (uint32_t)r.I, IG = I / J, S = (uint32_t)r.S;
         uint32_t const tid = threadIdx.x;
         uint32_t const ig = tid % IG, stream = tid / IG;
@@ -217,7 +220,7 @@ namespace
 
         rctx c;
         c.ws = ws + ig * J;
-        c.I = I;
+        c.I = HBM ? (uint64_t)r.LSw : (uint64_t)I;
         c.S = S;
         c.C = 32u / IG;
         c.col = (tid & 31u) / IG;
@@ -244,7 +247,7 @@ namespace
             uint32_t const fl = io.slot_kind >> 20;
             if(!(fl & PE_IO_LOAD)) { continue; }
             uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
-            double* dst = c.ws + (io.slot_kind & 0xffffu) * I;
+            double* dst = c.ws + (uint64_t)(io.slot_kind & 0xffffu) * c.I;
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
@@ -273,6 +276,7 @@ namespace
                     __syncthreads();
                     rd.bar();
                 }
+                else if(k == V_SKIP) { rd.skip(); }
                 else
                 {
                     rd.close();
@@ -363,7 +367,7 @@ namespace
                 for(int j = 0; j < J; ++j)
                 {
                     if(!ok[j]) { continue; }
-                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane0 + j] = c.ws[__ldg(r.probes + p) * I + j]; }
+                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane0 + j] = c.ws[(uint64_t)__ldg(r.probes + p) * c.I + j]; }
                 }
             }
         }
@@ -372,7 +376,7 @@ namespace
         {
             pe_b200_io const io = r.io[e];
             if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
-            double const* src = c.ws + (io.slot_kind & 0xffffu) * I;
+            double const* src = c.ws + (uint64_t)(io.slot_kind & 0xffffu) * c.I;
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
@@ -390,6 +394,317 @@ namespace
                     r.solves[lane0 + j] += solves[j];
                 }
             }
+        }
+    }
+
+    // ---- tree-streaming kernel: the tree-scheduled program with its workspace in HBM ---------------
+    // CTA = S warps x 32 lanes: warp s runs word stream s (a sub-tree of the elimination tree) for the CTA's 32
+    // instances, thread = one instance.  ws[slot][lane] is lane-interleaved in HBM (one coalesced 256-byte request per
+    // warp access).  The program words are warp-uniform, so the warp decodes them cooperatively: lane l holds word l of
+    // the current 32-word line (and of the next one, already in flight), pre-decodes both 16-bit operand fields of it
+    // once, and an operand costs the whole warp one shuffle + one address multiply-add + the load.
+    struct line_reader
+    {
+        uint32_t const* base;
+        uint32_t lane, stream, sm;
+        uint32_t w, nw;      // this lane's raw word of the current / next line
+        uint32_t dlo, dhi;   // its two operand fields decoded: absolute slot | neg << 31
+        uint32_t line, off;  // current line, offset of the current op inside it
+        // generic-reader state (ops the fast path does not take)
+        uint32_t cur, m;
+
+        __device__ __forceinline__ uint32_t dec(uint32_t f) const
+        {
+            uint32_t const r = f & 0x7fffu;
+            return ((r & ~sm) | ((r + stream) & sm)) | ((f & 0x8000u) << 16);
+        }
+        __device__ __forceinline__ void decode()
+        {
+            dlo = dec(w & 0xffffu);
+            dhi = dec(w >> 16);
+        }
+        __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S)
+        {
+            base = b;
+            lane = lane_;
+            stream = stream_;
+            sm = S - 1u;
+            line = 0;
+            off = 0;
+            w = __ldg(base + lane);
+            nw = __ldg(base + 32 + lane);
+            decode();
+        }
+        __device__ __forceinline__ uint32_t raw(uint32_t k) const { return __shfl_sync(0xffffffffu, w, (int)(off + k)); }
+        __device__ __forceinline__ uint32_t lo(uint32_t k) const { return __shfl_sync(0xffffffffu, dlo, (int)(off + k)); }
+        __device__ __forceinline__ uint32_t hi(uint32_t k) const { return __shfl_sync(0xffffffffu, dhi, (int)(off + k)); }
+        __device__ __forceinline__ void next_line()
+        {
+            w = nw;
+            ++line;
+            off = 0;
+            nw = __ldg(base + (line + 1u) * 32u + lane);
+            decode();
+        }
+        __device__ __forceinline__ void adv(uint32_t n)
+        {
+            off += n;
+            if(off >= 32u) { next_line(); }
+        }
+        // pe_rinterp reader interface (mask is always 0: one stream per warp has no per-column rows)
+        __device__ __forceinline__ uint32_t head() const { return raw(0); }
+        __device__ __forceinline__ uint32_t open(uint32_t rows)
+        {
+            cur = 2u;
+            m = rows;
+            return 0u;
+        }
+        __device__ __forceinline__ uint32_t next() { return raw(cur++); }
+        __device__ __forceinline__ void close() { adv(2u + m); }
+        __device__ __forceinline__ void bar() { adv(1u); }
+        __device__ __forceinline__ void skip() { next_line(); }
+    };
+
+    // address of slot `slot` of this thread's lane in the HBM workspace (by-value functor: lives in registers)
+    struct lane_ws
+    {
+        char* wl;
+        uint32_t LS8;
+        __device__ __forceinline__ double* operator() (uint32_t slot) const { return reinterpret_cast<double*>(wl + (uint64_t)slot * LS8); }
+    };
+
+    // one DOT with NA rows of packed sources and NB pairs: every operand load is issued before the first value is used
+    template <int NA, int NB>
+    __device__ __forceinline__ void tree_dot(line_reader const& rd, lane_ws const& at, pe_rinterp::tol_t const& tol, bool en, bool check, bool& nconv, bool& fail)
+    {
+        // words of the op: [h][mask][ctl][scale][src x NA][pair x NB]
+        uint32_t const flags = rd.raw(2) >> 16;
+        uint32_t const dst = rd.lo(2) & 0x7fffu;
+        uint32_t g[2 * NA + 1];
+        double sv[2 * NA + 1], av[NB + 1], bv[NB + 1];
+#pragma unroll
+        for(int i = 0; i < NA; ++i)
+        {
+            g[2 * i] = rd.lo(4 + i);
+            g[2 * i + 1] = rd.hi(4 + i);
+            sv[2 * i] = *at(g[2 * i] & 0x7fffu);
+            sv[2 * i + 1] = *at(g[2 * i + 1] & 0x7fffu);
+        }
+#pragma unroll
+        for(int i = 0; i < NB; ++i)
+        {
+            av[i] = *at(rd.lo(4 + NA + i) & 0x7fffu);
+            bv[i] = *at(rd.hi(4 + NA + i) & 0x7fffu);
+        }
+        double sc = 1.0, xo = 0.0;
+        if(flags & PE_F_SCALE) { sc = *at(rd.lo(3) & 0x7fffu); }
+        bool const chk = check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I));
+        if(chk) { xo = *at(dst); }
+        double acc = 0.0;
+#pragma unroll
+        for(int i = 0; i < 2 * NA; ++i) { acc = PE_ADD(acc, (g[i] >> 31) ? -sv[i] : sv[i]); }
+#pragma unroll
+        for(int i = 0; i < NB; ++i) { acc = fma(-av[i], bv[i], acc); }
+        if(flags & PE_F_SCALE) { acc = PE_MUL(acc, sc); }
+        if(flags & PE_F_RECIP)
+        {
+            if(acc == 0.0 || !isfinite(acc)) { fail = true; }
+            acc = PE_DIV(1.0, acc);
+        }
+        if(chk)
+        {
+            // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
+            bool const br = (flags & PE_F_CHECK_I) != 0u;
+            double const tl = (br ? tol.i_abstol : tol.v_abstol) + (br ? tol.i_reltol : tol.v_reltol) * fmax(fabs(acc), fabs(xo));
+            if(fabs(acc - xo) > tl) { nconv = true; }
+        }
+        if(en) { *at(dst) = acc; }
+    }
+
+    template <int MAXT, int MINB>
+    __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
+    {
+        __shared__ uint32_t s_flags[3][32];
+        using namespace pe_rinterp;
+        uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
+        uint32_t const S = (uint32_t)r.S;
+        int64_t const glane = (int64_t)blockIdx.x * 32 + lane;
+        lane_ws const at{reinterpret_cast<char*>(r.wsg + glane), (uint32_t)(r.LSw * 8)};
+
+        rctx c;
+        c.ws = r.wsg + glane;
+        c.I = (uint64_t)r.LSw;
+        c.S = S;
+        c.C = 1;
+        c.col = 0;
+        c.stream = warp;
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+
+        bool const real_lane = glane < r.n_lanes;
+        int32_t status = real_lane ? r.status[glane] : (int32_t)PE_ST_SINGULAR;
+        bool const counted = real_lane && status == PE_ST_OK;
+        bool ok = counted;
+        uint32_t solves = 0;
+
+        for(uint32_t e = warp; e < (uint32_t)r.n_io; e += n_warps)
+        {
+            pe_b200_io const io = r.io[e];
+            if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
+            uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
+            double v;
+            if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+            else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + glane]; }
+            else { v = r.wx[(int64_t)io.src * r.LSx + (real_lane ? glane / r.ppi : 0)]; }
+            *at(io.slot_kind & 0xffffu) = v;
+        }
+        if(tid < 96) { (&s_flags[0][0])[tid] = 0u; }
+        __syncthreads();
+
+        // One copy of the interpreter serves the three sections: stage 0 = prep, 1 = the step section of time step s,
+        // 2 = one Newton iteration (the iter section).  The sequencing is uniform over the CTA.
+        double t = r.t0;
+        int32_t s = 0, it = 0;
+        int stage = r.has_prep ? 0 : 1;
+        int fi = 0;
+        bool done = false;
+        for(;;)
+        {
+            int sec;
+            bool en1, check;
+            if(stage == 0)
+            {
+                sec = 0;
+                en1 = ok;
+                check = false;
+            }
+            else if(stage == 1)
+            {
+                if(s >= r.n_steps) { break; }
+                if(!(r.time_stepping && r.has_step))
+                {
+                    if(r.time_stepping) { t = t + r.dt; }
+                    done = !ok;
+                    it = 0;
+                    stage = 2;
+                    continue;
+                }
+                // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
+                sec = 1;
+                en1 = ok;
+                check = false;
+            }
+            else
+            {
+                sec = 2;
+                en1 = !done;
+                check = r.nonlinear != 0;
+                if(warp == 0) { s_flags[fi == 2 ? 0 : fi + 1][lane] = 0u; }
+            }
+
+            // ---- run the section
+            bool nconv1 = false, fail1 = false;
+            {
+                line_reader rd;
+                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
+                bool const en[1] = {en1};
+                bool nconv[1] = {false}, fail[1] = {false};
+                for(;;)
+                {
+                    uint32_t const h = rd.raw(0);
+                    uint32_t const op = h & 0xffu;
+                    uint32_t const na = (h >> 8) & 0x1fu, nb = (h >> 18) & 0x3fu;
+                    if(op == PE_OP_DOT && na <= 2u && nb <= 3u)
+                    {
+                        switch(na * 4u + nb)
+                        {
+                            case 0: tree_dot<0, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 1: tree_dot<0, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 2: tree_dot<0, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 3: tree_dot<0, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 4: tree_dot<1, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 5: tree_dot<1, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 6: tree_dot<1, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 7: tree_dot<1, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 8: tree_dot<2, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 9: tree_dot<2, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 10: tree_dot<2, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            default: tree_dot<2, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
+                        }
+                        rd.adv(4u + na + nb);
+                        continue;
+                    }
+                    int const k = rvop<1>(rd, c, t, tol, en, check, nconv, fail);
+                    if(k == V_END || k == V_BAD) { break; }
+                    if(k == V_BAR)
+                    {
+                        __syncthreads();
+                        rd.bar();
+                    }
+                    else if(k == V_SKIP) { rd.skip(); }
+                    else
+                    {
+                        rd.close();
+                    }
+                }
+                nconv1 = nconv1 || nconv[0];
+                fail1 = fail1 || fail[0];
+                __syncthreads();  // results of this section are visible to every warp of the CTA
+            }
+
+            // ---- what comes next
+            if(stage == 0) { stage = 1; }
+            else if(stage == 1)
+            {
+                t = t + r.dt;
+                done = !ok;
+                it = 0;
+                stage = 2;
+            }
+            else
+            {
+                if(nconv1 || fail1) { atomicOr(&s_flags[fi][lane], (nconv1 ? 1u : 0u) | (fail1 ? 2u : 0u)); }
+                __syncthreads();
+                uint32_t const f = s_flags[fi][lane];
+                fi = fi == 2 ? 0 : fi + 1;
+                ++it;
+                if(!done)
+                {
+                    ++solves;
+                    if(f & 2u)
+                    {
+                        status = PE_ST_SINGULAR;
+                        ok = false;
+                        done = true;
+                    }
+                    else if(!r.nonlinear || !(f & 1u)) { done = true; }
+                    else if(it >= r.max_iter)
+                    {
+                        status = PE_ST_NO_CONVERGENCE;
+                        ok = false;
+                        done = true;
+                    }
+                }
+                if(__syncthreads_and(done ? 1 : 0))
+                {
+                    if(r.wave != nullptr && ok && warp == 0)
+                    {
+                        for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + glane] = *at(__ldg(r.probes + p)); }
+                    }
+                    ++s;
+                    stage = 1;
+                }
+            }
+        }
+        for(uint32_t e = warp; e < (uint32_t)r.n_io; e += n_warps)
+        {
+            pe_b200_io const io = r.io[e];
+            if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
+            if(counted) { r.wu[(int64_t)io.src * r.LSu + glane] = *at(io.slot_kind & 0xffffu); }
+        }
+        if(warp == 0 && counted)
+        {
+            r.status[glane] = status;
+            r.solves[glane] += solves;
         }
     }
 
@@ -498,12 +813,41 @@ extern "C"
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
             return 1;
         }
+        bool const hbm{run->wsg != nullptr};
+        if(hbm && (I != 32 || J != 1 || S > 32))
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: the HBM form needs I=32 J=1 S<=32 (S=%d I=%d J=%d)", S, I, J);
+            return 1;
+        }
         int const block = S * (I / J);
         int const grid = (run->n_lanes + I - 1) / I;
-        size_t const smem = (size_t)run->n_slots * (size_t)I * sizeof(double);
+        size_t const smem = hbm ? 0 : (size_t)run->n_slots * (size_t)I * sizeof(double);
         // two register budgets: CTAs of up to 512 threads get 128 registers per thread, larger ones 64
-        auto kern = block <= 512 ? (J == 2 ? pe_b200_resident_kernel<2, 512> : pe_b200_resident_kernel<1, 512>)
-                                 : (J == 2 ? pe_b200_resident_kernel<2, 1024> : pe_b200_resident_kernel<1, 1024>);
+        if(hbm)
+        {
+            cudaEvent_t e0{}, e1{};
+            if(g_timing)
+            {
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                cudaEventRecord(e0, (cudaStream_t)stream);
+            }
+            if(block <= 256) { pe_b200_tree_kernel<256, 4><<<grid, block, 0, (cudaStream_t)stream>>>(*run); }
+            else if(block <= 512) { pe_b200_tree_kernel<512, 2><<<grid, block, 0, (cudaStream_t)stream>>>(*run); }
+            else
+            {
+                pe_b200_tree_kernel<1024, 1><<<grid, block, 0, (cudaStream_t)stream>>>(*run);
+            }
+            if(g_timing)
+            {
+                cudaEventRecord(e1, (cudaStream_t)stream);
+                g_events.emplace_back(e0, e1);
+            }
+            g_launches.fetch_add(1);
+            return chk(cudaGetLastError(), "pe_b200_tree_kernel launch");
+        }
+        auto kern = block <= 512 ? (J == 2 ? pe_b200_resident_kernel<2, 512, false> : pe_b200_resident_kernel<1, 512, false>)
+                                 : (J == 2 ? pe_b200_resident_kernel<2, 1024, false> : pe_b200_resident_kernel<1, 1024, false>);
         if(chk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") != 0) { return 1; }
         cudaEvent_t e0{}, e1{};
         if(g_timing)

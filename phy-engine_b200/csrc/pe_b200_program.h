@@ -57,6 +57,9 @@ extern "C"
         //   header = op | flags << 8 | npair << 16 ; second word = nsrc_re | nsrc_im << 16
         //   words: [dst] [scale, if F_SCALE] [src_re x nsrc_re] [src_im x nsrc_im] [(a, b) x npair]
         PE_OP_CDOT = 3,
+        // resident programs packed for one stream per warp: the rest of this 32-word line of the main stream is padding
+        // (a vector op never straddles two lines, so that the warp reader hands out its words with one shuffle each)
+        PE_OP_SKIP = 4,
 
         // scalar value ops (real), generic operands
         PE_OP_RECIP = 10,    // [dst][a]          dst = 1.0 / a
@@ -212,6 +215,10 @@ extern "C"
         int32_t I;        // instances per CTA
         int32_t J;        // instances per thread (1 or 2; I % J == 0)
         int32_t n_slots;  // shared-memory slots per instance (a multiple of S)
+        // Tree-streaming form of the same program: the workspace ws[slot][lane] lives in HBM
+        // (wsg != NULL, lane stride LSw), a CTA is S warps x 32 lanes (I = 32, J = 1), warp s runs stream s.
+        double* wsg;
+        int64_t LSw;
         int32_t cplx;
         int32_t nonlinear;
         int32_t max_iter;

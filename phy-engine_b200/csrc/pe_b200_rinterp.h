@@ -17,7 +17,7 @@ namespace pe_rinterp
     struct rctx
     {
         double* ws;    // shared-memory workspace of the CTA, already offset to this thread's first instance
-        uint32_t I;    // instances per CTA = distance (in doubles) between consecutive slots
+        uint64_t I;    // distance (in doubles) between consecutive slots: instances per CTA (shared) or the lane stride (HBM)
         uint32_t S;    // streams per instance = distance (in slots) between re and im of a complex value
         uint32_t C;    // streams (word columns) per warp
         uint32_t col;  // this thread's column
@@ -41,7 +41,7 @@ namespace pe_rinterp
     template <int J>
     PE_HD double* slot_ptr(rctx const& c, uint32_t slot)
     {
-        return c.ws + slot * c.I;
+        return c.ws + (uint64_t)slot * c.I;
     }
 
     template <int J>
@@ -108,6 +108,7 @@ namespace pe_rinterp
         V_BAR = 1,
         V_OK = 2,
         V_BAD = 3,
+        V_SKIP = 4,
     };
 
     // Word reader of one warp's program (host form; the sm_100a kernel has a warp-cooperative one with the same
@@ -115,8 +116,9 @@ namespace pe_rinterp
     // (BAR / END are single words), the SIDE stream the per-column rows (C words each) in consumption order.
     struct host_reader
     {
-        uint32_t const* p;  // main stream, at the current op
-        uint32_t const* q;  // side stream, at the first per-column row of the current op
+        uint32_t const* p0;  // start of the main stream (128-byte line aligned)
+        uint32_t const* p;   // main stream, at the current op
+        uint32_t const* q;   // side stream, at the first per-column row of the current op
         uint32_t C, col;
         uint32_t cur{}, m{};
         uint32_t const* qc{};
@@ -155,6 +157,7 @@ namespace pe_rinterp
             q = q_next;
         }
         void bar() { p += 1; }
+        void skip() { p = p0 + (((p - p0) >> 5) + 1) * 32; }
     };
 
     // Execute the vector op the reader stands on, for this thread.  en[j]: stores of instance j are enabled (the lane
@@ -169,6 +172,7 @@ namespace pe_rinterp
         uint32_t const op = h & 0xffu;
         if(op == PE_OP_END) { return V_END; }
         if(op == PE_OP_BAR) { return V_BAR; }
+        if(op == PE_OP_SKIP) { return V_SKIP; }
         auto fetch = [&]() -> uint32_t { return rd.next(); };
         if(op == PE_OP_DOT)
         {

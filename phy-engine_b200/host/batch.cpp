@@ -151,16 +151,38 @@ namespace pe_b200
     {
         if(res_S < 0) { return 0; }
         if(res_S > 0) { return res_S; }
-        // small circuits: one thread per instance (no barriers, no divergence); larger ones: leaves of ~4 rows, which
-        // keeps a CTA of S threads busy while the (logarithmic) separator levels stay short
-        if(n_unknowns <= 64) { return 1; }
+        // small circuits: one thread per instance, workspace in shared memory (no barriers, no divergence, no HBM
+        // traffic inside the Newton / time loops)
+        if(n_unknowns <= 64 && res_ws != 2) { return 1; }
+        if(res_ws == 1)
+        {
+            // shared-memory workspace, thread per stream: leaves of ~4 rows
+            int s{1};
+            while(s < 256 && s * 2 * 4 <= n_unknowns) { s *= 2; }
+            return s;
+        }
+        // larger circuits stream their workspace through HBM, warp per sub-tree: enough sub-trees to keep ~32 warps per
+        // 32 lanes in flight (latency hiding), leaves of at least ~16 rows
         int s{1};
-        while(s < 256 && s * 2 * 4 <= n_unknowns) { s *= 2; }
+        while(s < 32 && s * 2 * 16 <= n_unknowns) { s *= 2; }
         return s;
+    }
+
+    bool batch::use_hbm(program const& pr) const
+    {
+        if(res_ws == 2) { return true; }
+        if(res_ws == 1) { return false; }
+        return pr.rS > 1;
     }
 
     bool batch::pick_geometry(program const& pr, int& I, int& J) const
     {
+        if(use_hbm(pr))
+        {
+            I = 32;
+            J = 1;
+            return pr.rS <= 32;
+        }
         std::size_t const limit{pe_b200_resident_smem_limit()};
         std::size_t const per_inst{static_cast<std::size_t>(std::max(pr.r_slots, 1)) * sizeof(double)};
         int const S{pr.rS};
@@ -414,6 +436,15 @@ namespace pe_b200
         r.I = I;
         r.J = J;
         r.n_slots = pr.r_slots;
+        r.wsg = nullptr;
+        r.LSw = 0;
+        if(use_hbm(pr))
+        {
+            std::int64_t const LSw{round_up32(lanes)};
+            if(!d_ws.ensure(static_cast<std::size_t>(pr.r_slots) * static_cast<std::size_t>(LSw) * sizeof(double))) { return dev_fail(error, "alloc HBM workspace"); }
+            r.wsg = static_cast<double*>(d_ws.p);
+            r.LSw = LSw;
+        }
         r.cplx = pr.cplx ? 1 : 0;
         r.nonlinear = nonlinear ? 1 : 0;
         r.max_iter = 64;  // circuit.h:898
@@ -719,6 +750,7 @@ namespace pe_b200
             solo->res_I = d.res_I;
             solo->res_J = d.res_J;
             solo->subtree_warps = d.subtree_warps;
+            solo->res_ws = d.res_ws;
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

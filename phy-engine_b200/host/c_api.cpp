@@ -477,6 +477,7 @@ extern "C"
         b->res_I = d.res_I;
         b->res_J = d.res_J;
         b->subtree_warps = d.subtree_warps;
+        b->res_ws = d.res_ws;
         return b;
     }
 
@@ -509,6 +510,13 @@ extern "C"
         return 0;
     }
 
+    int circuit_batch_set_workspace(void* b, int where)
+    {
+        if(b == nullptr || where < 0 || where > 2) { return 1; }
+        static_cast<batch*>(b)->res_ws = where;
+        return 0;
+    }
+
     int circuit_batch_resident_info(void* b, int mode, int64_t* info)
     {
         if(b == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
@@ -531,6 +539,7 @@ extern "C"
         info[9] = static_cast<int64_t>(nph);
         info[10] = static_cast<int64_t>(pr.words.size());
         info[11] = static_cast<int64_t>(pr.max_warp_words);
+        info[12] = (pr.resident && bp->use_hbm(pr)) ? 1 : 0;
         return 0;
     }
 
@@ -850,8 +859,9 @@ extern "C"
         return 1;
     }
 
-    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps)
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace)
     {
+        if(workspace < 0 || workspace > 2) { return 1; }
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
@@ -862,6 +872,7 @@ extern "C"
         d.res_I = instances_per_cta;
         d.res_J = instances_per_thread;
         d.subtree_warps = subtree_warps;
+        d.res_ws = workspace;
         return 0;
     }
 

@@ -2621,6 +2621,16 @@ namespace pe_b200
                                 rw.assign(1, first);
                             }
                         }
+                        if(C == 1)
+                        {
+                            // one stream per warp: an op never straddles two 32-word lines of the main stream
+                            std::size_t const len{2 + rows.size()};
+                            if(ww.size() % 32 + len > 32)
+                            {
+                                ww.push_back(PE_OP_SKIP);
+                                while(ww.size() % 32 != 0) { ww.push_back(PE_OP_SKIP); }
+                            }
+                        }
                         ww.push_back(h0);
                         ww.push_back(mask);
                         for(std::size_t r{}; r < rows.size(); ++r)

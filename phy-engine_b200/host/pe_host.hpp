@@ -278,6 +278,9 @@ namespace pe_b200
         // resident (shared-memory) path: streams per instance (-1 = never, 0 = choose, else forced), instances per CTA
         // and per thread (0 = choose)
         int res_S{0}, res_I{0}, res_J{0};
+        int res_ws{0};  // where the tree-scheduled program keeps its workspace: 0 = choose, 1 = shared memory, 2 = HBM
+        device_buf d_ws;  // HBM workspace of the tree-streaming form [slots][lanes]
+        bool use_hbm(program const& pr) const;
         int cc_res_real{-1}, cc_res_ac{-1};
         int pick_streams(int n_unknowns) const;
         bool pick_geometry(program const& pr, int& I, int& J) const;
@@ -340,6 +343,7 @@ namespace pe_b200
     {
         int res_S{0}, res_I{0}, res_J{0};
         int subtree_warps{0};
+        int res_ws{0};
     };
     path_defaults& default_path();
 

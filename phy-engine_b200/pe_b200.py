@@ -225,7 +225,8 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_set_probes.argtypes = [V, _PSZ, _SZ]
     lib.circuit_batch_set_subtree_warps.argtypes = [V, ct.c_int]
     lib.circuit_batch_set_resident.argtypes = [V, ct.c_int, ct.c_int, ct.c_int]
-    lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int]
+    lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int]
+    lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
     lib.circuit_batch_resident_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
     for f in ("circuit_batch_prepare", "circuit_batch_reset_state", "circuit_batch_analyze", "circuit_batch_compile_host"):
         getattr(lib, f).argtypes = [V]
@@ -356,10 +357,14 @@ class Batch:
         """Resident (shared-memory) solve path: streams -1 = never, 0 = automatic, else a power of two."""
         self._rc(self.lib.circuit_batch_set_resident(self.h, streams, instances_per_cta, instances_per_thread), "circuit_batch_set_resident")
 
+    def set_workspace(self, where: int):
+        """0 = automatic, 1 = shared memory (resident kernel), 2 = HBM (tree-streaming kernel)"""
+        self._rc(self.lib.circuit_batch_set_workspace(self.h, where), "circuit_batch_set_workspace")
+
     def resident_info(self, mode: int) -> dict:
-        v = (ct.c_int64 * 12)()
+        v = (ct.c_int64 * 13)()
         self._rc(self.lib.circuit_batch_resident_info(self.h, mode, v), "circuit_batch_resident_info")
-        keys = ("resident", "streams", "smem_slots", "I", "J", "io_entries", "last_S", "last_I", "last_J", "iter_phases", "words", "max_warp_words")
+        keys = ("resident", "streams", "smem_slots", "I", "J", "io_entries", "last_S", "last_I", "last_J", "iter_phases", "words", "max_warp_words", "hbm")
         return {k: int(x) for k, x in zip(keys, v)}
 
     def set_param(self, ele: int, name: str, values):

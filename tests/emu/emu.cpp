@@ -236,7 +236,9 @@ namespace
         uint32_t const T = S * IG, W = T / 32, C = 32 / IG;
         tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
         int64_t const n_cta = (r.n_lanes + I - 1) / I;
-        std::vector<double> ws((size_t)r.n_slots * I);
+        bool const hbm = r.wsg != nullptr;
+        uint64_t const sstride = hbm ? (uint64_t)r.LSw : (uint64_t)I;  // distance between consecutive slots
+        std::vector<double> ws_local(hbm ? 0 : (size_t)r.n_slots * I);
         struct tstate
         {
             bool real_lane[J], counted[J], ok[J], done[J];
@@ -247,7 +249,18 @@ namespace
         for(int64_t cta = 0; cta < n_cta; ++cta)
         {
             // poison the workspace: a slot read before it is loaded or written shows up as NaN in the results
-            for(auto& v: ws) { v = __builtin_nan(""); }
+            double* const wsb = hbm ? r.wsg + cta * 32 : ws_local.data();
+            if(hbm)
+            {
+                for(int32_t k = 0; k < r.n_slots; ++k)
+                {
+                    for(uint32_t i = 0; i < I; ++i) { wsb[(uint64_t)k * sstride + i] = __builtin_nan(""); }
+                }
+            }
+            else
+            {
+                for(auto& v: ws_local) { v = __builtin_nan(""); }
+            }
             emu_trace::g_map.clear();
             emu_trace::g_phase = 0;
             uint32_t s_flags[3][32] = {};
@@ -280,7 +293,7 @@ namespace
                     if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
                     else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + lane]; }
                     else { v = r.wx[(int64_t)io.src * r.LSx + (real ? lane / r.ppi : 0)]; }
-                    ws[(size_t)(io.slot_kind & 0xffffu) * I + i] = v;
+                    wsb[(uint64_t)(io.slot_kind & 0xffffu) * sstride + i] = v;
                 }
             }
             emu_trace::g_on = trace_was;
@@ -293,7 +306,8 @@ namespace
                 std::vector<host_reader> rdw(W);
                 for(uint32_t w = 0; w < W; ++w)
                 {
-                    rdw[w].p = r.words + r.sec_off[sec * W + w];
+                    rdw[w].p0 = r.words + r.sec_off[sec * W + w];
+                    rdw[w].p = rdw[w].p0;
                     rdw[w].q = r.words + r.sec_off[3 * W + sec * W + w];
                     rdw[w].C = C;
                     rdw[w].col = 0;
@@ -312,8 +326,8 @@ namespace
                                 uint32_t const tid = w * 32 + l;
                                 uint32_t const ig = tid % IG;
                                 rctx c;
-                                c.ws = ws.data() + ig * J;
-                                c.I = I;
+                                c.ws = wsb + ig * J;
+                                c.I = sstride;
                                 c.S = S;
                                 c.C = C;
                                 c.col = l / IG;
@@ -330,13 +344,14 @@ namespace
                                 kind = rvop<J>(rd, c, t, tol, en, check, nc, fl);
                                 if(kind == V_OK) { rd.close(); }
                                 if(kind == V_BAR) { rd.bar(); }
+                                if(kind == V_SKIP) { rd.skip(); }
                                 after = rd;
                                 for(int j = 0; j < J; ++j)
                                 {
                                     nconv[tid][j] = nconv[tid][j] || nc[j];
                                     fail[tid][j] = fail[tid][j] || fl[j];
                                 }
-                                if(kind == V_END || kind == V_BAR || kind == V_BAD) { break; }
+                                if(kind == V_END || kind == V_BAR || kind == V_BAD || kind == V_SKIP) { break; }
                             }
                             if(kind == V_BAD)
                             {
@@ -448,7 +463,7 @@ namespace
                         {
                             if(!st.ok[j]) { continue; }
                             int64_t const lane = cta * I + ig * J + j;
-                            for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = ws[(size_t)r.probes[p] * I + ig * J + j]; }
+                            for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = wsb[(uint64_t)r.probes[p] * sstride + ig * J + j]; }
                         }
                     }
                 }
@@ -461,7 +476,7 @@ namespace
                 {
                     for(int j = 0; j < J; ++j)
                     {
-                        if(ts[ig].counted[j]) { r.wu[(int64_t)io.src * r.LSu + cta * I + ig * J + j] = ws[(size_t)(io.slot_kind & 0xffffu) * I + ig * J + j]; }
+                        if(ts[ig].counted[j]) { r.wu[(int64_t)io.src * r.LSu + cta * I + ig * J + j] = wsb[(uint64_t)(io.slot_kind & 0xffffu) * sstride + ig * J + j]; }
                     }
                 }
             }

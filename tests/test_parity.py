@@ -27,17 +27,22 @@ def abi(request):
 
 
 # Every test runs once per solve path (set as the process-wide default every new batch starts from):
-#   resident        shared-memory kernel, automatic geometry (the product default)
-#   resident-s8     ... forced 8 word streams per instance (4 instances per warp)
-#   resident-s32j2  ... forced 32 streams, 2 instances per CTA handled by the same thread (vector loads)
-#   stream          HBM-streaming kernel, one warp per 32 instances
-#   stream-g4       ... 4 sub-tree warps per 32 instances
+#   auto            the product default: shared-memory resident kernel for small circuits, tree-streaming (HBM
+#                   workspace, one warp per sub-tree) otherwise
+#   tree-hbm-s4     tree-streaming kernel forced, 4 sub-tree warps per 32 lanes
+#   tree-hbm-s16    ... 16 sub-tree warps
+#   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp)
+#   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
+#   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
+#   flat-g4         ... 4 sub-tree warps per 32 instances
 PATHS = {
-    "resident": (0, 0, 0, 0),
-    "resident-s8": (8, 0, 1, 0),
-    "resident-s32j2": (32, 2, 2, 0),
-    "stream": (-1, 0, 0, 0),
-    "stream-g4": (-1, 0, 0, 4),
+    "auto": (0, 0, 0, 0, 0),
+    "tree-hbm-s4": (4, 0, 0, 0, 2),
+    "tree-hbm-s16": (16, 0, 0, 0, 2),
+    "resident-s8": (8, 0, 1, 0, 1),
+    "resident-s32j2": (32, 2, 2, 0, 1),
+    "flat": (-1, 0, 0, 0, 0),
+    "flat-g4": (-1, 0, 0, 4, 0),
 }
 
 
@@ -46,7 +51,7 @@ def path(request, abi):
     rc = abi.lib.phy_engine_b200_set_default_path(*PATHS[request.param])
     assert rc == 0
     yield request.param
-    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0)
+    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0, 0)
 
 
 def assert_close(got, want, what=""):
@@ -131,8 +136,11 @@ def test_rc_ladder_batch_sweep(ref, abi, path, n_sections, n_inst):
     for e, name, v in over:
         b.set_param(e, name, v)
     assert b.analyze(), c.abi.last_error()
-    if path == "stream-g4" and n_sections >= 200:
+    if path == "flat-g4" and n_sections >= 200:
         assert b.program_info(pe.MODE_TR)["warps"] == 4
+    if path.startswith("tree-hbm"):
+        ri = b.resident_info(pe.MODE_TR)
+        assert ri["resident"] == 1 and ri["hbm"] == 1 and (ri["last_I"], ri["last_J"]) == (32, 1)
     if path.startswith("resident"):
         ri = b.resident_info(pe.MODE_TR)
         assert ri["resident"] == 1 and ri["last_S"] == ri["streams"] and ri["last_I"] > 0
