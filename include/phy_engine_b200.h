@@ -158,6 +158,9 @@ extern "C"
     /* where a tree-scheduled program keeps its workspace: 0 = automatic (shared memory for small circuits, HBM with one
      * warp per sub-tree otherwise), 1 = shared memory, 2 = HBM */
     int circuit_batch_set_workspace(void* batch, int where);
+    /* tree-streaming kernel: number of chunks the time loop is cut into for dynamic (group, chunk) scheduling over
+     * persistent CTAs: 0 = automatic, 1 = static (one CTA per 32-lane group runs the whole launch), up to 32 */
+    int circuit_batch_set_chunks(void* batch, int chunks);
     /* info[13] = resident, streams, workspace slots per instance, I, J (0 = does not fit), io entries,
      * last launch S / I / J (0 = the flat HBM-streaming kernel ran), phases of the iter section, words, longest warp
      * stream, workspace in HBM (1) or shared memory (0) */

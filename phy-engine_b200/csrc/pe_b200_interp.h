@@ -130,7 +130,7 @@ namespace pe_interp
                     if(flags & PE_F_RECIP)
                     {
                         if(acc == 0.0 || !isfinite(acc)) { fail = true; }
-                        acc = PE_DIV(1.0, acc);
+                        acc = PE_RCP(acc);
                     }
                     double* pd = uaddr(c, dst);
                     if(check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I)))

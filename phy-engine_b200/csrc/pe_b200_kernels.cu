@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <utility>
 #include <vector>
@@ -509,7 +510,7 @@ namespace
         if(flags & PE_F_RECIP)
         {
             if(acc == 0.0 || !isfinite(acc)) { fail = true; }
-            acc = PE_DIV(1.0, acc);
+            acc = PE_RCP(acc);
         }
         if(chk)
         {
@@ -525,11 +526,44 @@ namespace
     __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
     {
         __shared__ uint32_t s_flags[3][32];
+        __shared__ uint32_t s_item;
         using namespace pe_rinterp;
         uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
         uint32_t const S = (uint32_t)r.S;
-        int64_t const glane = (int64_t)blockIdx.x * 32 + lane;
+        uint32_t const NG = (uint32_t)((r.n_lanes + 31) / 32), NC = r.sched != nullptr ? (uint32_t)r.n_chunks : 1u;
+        for(;;)
+        {
+        // ---- next work item: (chunk c of the time loop, 32-lane group g)
+        uint32_t item = blockIdx.x;
+        if(r.sched != nullptr)
+        {
+            if(tid == 0) { s_item = atomicAdd(r.sched, 1u); }
+            __syncthreads();
+            item = s_item;
+        }
+        if(item >= NC * NG) { break; }
+        uint32_t const chunk = item / NG, group = item - chunk * NG;
+        if(r.sched != nullptr && chunk > 0u)
+        {
+            // chunk c of a group starts when its chunk c - 1 (run by some other CTA) has published its results; the
+            // acquire load also drops whatever this SM's L1 still holds of the group's workspace
+            if(tid == 0)
+            {
+                uint32_t v;
+                for(;;)
+                {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(r.sched + 1 + group) : "memory");
+                    if(v >= chunk) { break; }
+                    __nanosleep(256);
+                }
+            }
+            __syncthreads();
+        }
+        int64_t const glane = (int64_t)group * 32 + lane;
         lane_ws const at{reinterpret_cast<char*>(r.wsg + glane), (uint32_t)(r.LSw * 8)};
+        bool const first_chunk = chunk == 0u, last_chunk = chunk + 1u == NC;
+        int32_t const s_begin = r.sched != nullptr ? (int32_t)chunk * r.chunk_steps : 0;
+        int32_t const s_end = r.sched != nullptr ? min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
 
         rctx c;
         c.ws = r.wsg + glane;
@@ -546,7 +580,7 @@ namespace
         bool ok = counted;
         uint32_t solves = 0;
 
-        for(uint32_t e = warp; e < (uint32_t)r.n_io; e += n_warps)
+        for(uint32_t e = warp; first_chunk && e < (uint32_t)r.n_io; e += n_warps)
         {
             pe_b200_io const io = r.io[e];
             if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
@@ -562,9 +596,9 @@ namespace
 
         // One copy of the interpreter serves the three sections: stage 0 = prep, 1 = the step section of time step s,
         // 2 = one Newton iteration (the iter section).  The sequencing is uniform over the CTA.
-        double t = r.t0;
-        int32_t s = 0, it = 0;
-        int stage = r.has_prep ? 0 : 1;
+        double t = r.sched != nullptr ? r.t_chunk[chunk] : r.t0;
+        int32_t s = s_begin, it = 0;
+        int stage = (r.has_prep && first_chunk) ? 0 : 1;
         int fi = 0;
         bool done = false;
         for(;;)
@@ -579,7 +613,7 @@ namespace
             }
             else if(stage == 1)
             {
-                if(s >= r.n_steps) { break; }
+                if(s >= s_end) { break; }
                 if(!(r.time_stepping && r.has_step))
                 {
                     if(r.time_stepping) { t = t + r.dt; }
@@ -631,6 +665,23 @@ namespace
                             default: tree_dot<2, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
                         }
                         rd.adv(4u + na + nb);
+                        continue;
+                    }
+                    if(op == PE_OP_CAP_STEP)
+                    {
+                        // [h][mask][hist][prev_g][C][dt][va][vb]  (capacitor.h:106-128)
+                        double* const ph = at(rd.lo(2) & 0x7fffu);
+                        double* const pg = at(rd.lo(3) & 0x7fffu);
+                        double hv = *ph, gv = *pg;
+                        double const C_ = *at(rd.lo(4) & 0x7fffu), dtv = *at(rd.lo(5) & 0x7fffu);
+                        double const va = *at(rd.lo(6) & 0x7fffu), vb = *at(rd.lo(7) & 0x7fffu);
+                        pe_models::cap_step(C_, dtv, PE_SUB(va, vb), hv, gv);
+                        if(en1)
+                        {
+                            *ph = hv;
+                            *pg = gv;
+                        }
+                        rd.adv(8u);
                         continue;
                     }
                     int const k = rvop<1>(rd, c, t, tol, en, check, nconv, fail);
@@ -695,7 +746,7 @@ namespace
                 }
             }
         }
-        for(uint32_t e = warp; e < (uint32_t)r.n_io; e += n_warps)
+        for(uint32_t e = warp; last_chunk && e < (uint32_t)r.n_io; e += n_warps)
         {
             pe_b200_io const io = r.io[e];
             if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
@@ -705,6 +756,12 @@ namespace
         {
             r.status[glane] = status;
             r.solves[glane] += solves;
+        }
+        if(r.sched == nullptr) { break; }
+        // publish the chunk: every thread's stores are visible device-wide before the group's counter moves
+        __threadfence();
+        __syncthreads();
+        if(tid == 0) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(r.sched + 1 + group), "r"(chunk + 1u) : "memory"); }
         }
     }
 
@@ -832,12 +889,22 @@ extern "C"
                 cudaEventCreate(&e1);
                 cudaEventRecord(e0, (cudaStream_t)stream);
             }
-            if(block <= 256) { pe_b200_tree_kernel<256, 4><<<grid, block, 0, (cudaStream_t)stream>>>(*run); }
-            else if(block <= 512) { pe_b200_tree_kernel<512, 2><<<grid, block, 0, (cudaStream_t)stream>>>(*run); }
-            else
+            void (*tk)(pe_b200_rrun) = block <= 256 ? pe_b200_tree_kernel<256, 4> : (block <= 512 ? pe_b200_tree_kernel<512, 2> : pe_b200_tree_kernel<1024, 1>);
+            int tgrid = grid;
+            if(run->sched != nullptr)
             {
-                pe_b200_tree_kernel<1024, 1><<<grid, block, 0, (cudaStream_t)stream>>>(*run);
+                // persistent CTAs, all co-resident (an item may wait for the previous chunk of its group, which is always
+                // already running): grid = occupancy x SMs
+                int dev = 0, sms = 0, occ = 0;
+                if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, block, 0) != cudaSuccess || occ < 1)
+                {
+                    return chk(cudaGetLastError(), "occupancy query") != 0 ? 1 : (snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: occupancy query failed"), 1);
+                }
+                long long const items = (long long)run->n_chunks * grid;
+                tgrid = (int)std::min<long long>(items, (long long)occ * sms);
             }
+            tk<<<tgrid, block, 0, (cudaStream_t)stream>>>(*run);
             if(g_timing)
             {
                 cudaEventRecord(e1, (cudaStream_t)stream);

@@ -219,6 +219,14 @@ extern "C"
         // (wsg != NULL, lane stride LSw), a CTA is S warps x 32 lanes (I = 32, J = 1), warp s runs stream s.
         double* wsg;
         int64_t LSw;
+        // Dynamic (group, chunk) scheduling of the tree-streaming form: the time loop of every 32-lane group is cut into
+        // n_chunks chunks of chunk_steps steps; persistent CTAs take (chunk, group) items from an atomic counter in
+        // chunk-major order, so a group migrates between SMs and the last wave is one chunk long instead of one run.
+        // sched = NULL: one CTA per group runs the whole launch.
+        int32_t chunk_steps;
+        int32_t n_chunks;
+        uint32_t* sched;      // device: [0] next item, [1 + g] chunks of group g completed (zeroed before the launch)
+        double t_chunk[32];   // tr_duration at the start of chunk c (the host accumulates t = t + dt like circuit.h:243-248)
         int32_t cplx;
         int32_t nonlinear;
         int32_t max_iter;

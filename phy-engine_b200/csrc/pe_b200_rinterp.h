@@ -262,7 +262,7 @@ namespace pe_rinterp
                 for(int j = 0; j < J; ++j)
                 {
                     if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { fail[j] = true; }
-                    acc.v[j] = PE_DIV(1.0, acc.v[j]);
+                    acc.v[j] = PE_RCP(acc.v[j]);
                 }
             }
             uint32_t const dst = abs_slot(c, ctl);

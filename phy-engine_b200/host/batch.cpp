@@ -444,6 +444,26 @@ namespace pe_b200
             if(!d_ws.ensure(static_cast<std::size_t>(pr.r_slots) * static_cast<std::size_t>(LSw) * sizeof(double))) { return dev_fail(error, "alloc HBM workspace"); }
             r.wsg = static_cast<double*>(d_ws.p);
             r.LSw = LSw;
+            // dynamic (group, chunk) scheduling of long time loops: up to 32 chunks of at least 4 steps
+            int nc{res_chunks > 0 ? res_chunks : std::min(32, n_steps / 4)};
+            nc = std::clamp(nc, 1, 32);
+            if(time_stepping && n_steps > 1 && nc > 1)
+            {
+                int const cs{(n_steps + nc - 1) / nc};
+                nc = (n_steps + cs - 1) / cs;
+                std::size_t const groups{(lanes + 31) / 32};
+                if(!d_sched.ensure((1 + groups) * sizeof(std::uint32_t))) { return dev_fail(error, "alloc scheduler"); }
+                if(pe_b200_dev_memset0(d_sched.p, (1 + groups) * sizeof(std::uint32_t), stream) != 0) { return dev_fail(error, "zero scheduler"); }
+                r.sched = static_cast<std::uint32_t*>(d_sched.p);
+                r.chunk_steps = cs;
+                r.n_chunks = nc;
+                double tc{t0};
+                for(int k{}; k < nc; ++k)
+                {
+                    r.t_chunk[k] = tc;
+                    for(int q{}; q < cs; ++q) { tc = tc + dt; }  // the reference's accumulation (circuit.h:243-248)
+                }
+            }
         }
         r.cplx = pr.cplx ? 1 : 0;
         r.nonlinear = nonlinear ? 1 : 0;
@@ -751,6 +771,7 @@ namespace pe_b200
             solo->res_J = d.res_J;
             solo->subtree_warps = d.subtree_warps;
             solo->res_ws = d.res_ws;
+            solo->res_chunks = d.res_chunks;
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

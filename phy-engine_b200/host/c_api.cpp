@@ -478,6 +478,7 @@ extern "C"
         b->res_J = d.res_J;
         b->subtree_warps = d.subtree_warps;
         b->res_ws = d.res_ws;
+        b->res_chunks = d.res_chunks;
         return b;
     }
 
@@ -514,6 +515,13 @@ extern "C"
     {
         if(b == nullptr || where < 0 || where > 2) { return 1; }
         static_cast<batch*>(b)->res_ws = where;
+        return 0;
+    }
+
+    int circuit_batch_set_chunks(void* b, int chunks)
+    {
+        if(b == nullptr || chunks < 0 || chunks > 32) { return 1; }
+        static_cast<batch*>(b)->res_chunks = chunks;
         return 0;
     }
 

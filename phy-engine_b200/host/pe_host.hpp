@@ -280,6 +280,8 @@ namespace pe_b200
         int res_S{0}, res_I{0}, res_J{0};
         int res_ws{0};  // where the tree-scheduled program keeps its workspace: 0 = choose, 1 = shared memory, 2 = HBM
         device_buf d_ws;  // HBM workspace of the tree-streaming form [slots][lanes]
+        device_buf d_sched;  // work-item counter + per-group chunk counters of the tree-streaming form
+        int res_chunks{0};   // chunks the time loop is cut into for dynamic scheduling: 0 = choose, 1 = static (one CTA per group)
         bool use_hbm(program const& pr) const;
         int cc_res_real{-1}, cc_res_ac{-1};
         int pick_streams(int n_unknowns) const;
@@ -344,6 +346,7 @@ namespace pe_b200
         int res_S{0}, res_I{0}, res_J{0};
         int subtree_warps{0};
         int res_ws{0};
+        int res_chunks{0};
     };
     path_defaults& default_path();
 

@@ -227,6 +227,7 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_set_resident.argtypes = [V, ct.c_int, ct.c_int, ct.c_int]
     lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int]
     lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
+    lib.circuit_batch_set_chunks.argtypes = [V, ct.c_int]
     lib.circuit_batch_resident_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
     for f in ("circuit_batch_prepare", "circuit_batch_reset_state", "circuit_batch_analyze", "circuit_batch_compile_host"):
         getattr(lib, f).argtypes = [V]
@@ -360,6 +361,10 @@ class Batch:
     def set_workspace(self, where: int):
         """0 = automatic, 1 = shared memory (resident kernel), 2 = HBM (tree-streaming kernel)"""
         self._rc(self.lib.circuit_batch_set_workspace(self.h, where), "circuit_batch_set_workspace")
+
+    def set_chunks(self, chunks: int):
+        """tree-streaming kernel: chunks of the time loop for dynamic scheduling (0 = automatic, 1 = static)"""
+        self._rc(self.lib.circuit_batch_set_chunks(self.h, chunks), "circuit_batch_set_chunks")
 
     def resident_info(self, mode: int) -> dict:
         v = (ct.c_int64 * 13)()

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <array>
 #include <unordered_map>
 #include <vector>
@@ -246,11 +247,19 @@ namespace
             uint32_t solves[J];
         };
         std::vector<tstate> ts(T);
+        // (chunk, group) items of the tree-streaming form are replayed in the order the device hands them out
+        bool const chunked = hbm && r.sched != nullptr;
+        int32_t const NC = chunked ? r.n_chunks : 1;
+        for(int32_t chunk = 0; chunk < NC; ++chunk)
         for(int64_t cta = 0; cta < n_cta; ++cta)
         {
+            bool const first_chunk = chunk == 0, last_chunk = chunk + 1 == NC;
+            int32_t const s_begin = chunked ? chunk * r.chunk_steps : 0;
+            int32_t const s_end = chunked ? std::min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
             // poison the workspace: a slot read before it is loaded or written shows up as NaN in the results
             double* const wsb = hbm ? r.wsg + cta * 32 : ws_local.data();
-            if(hbm)
+            if(!first_chunk) {}
+            else if(hbm)
             {
                 for(int32_t k = 0; k < r.n_slots; ++k)
                 {
@@ -280,7 +289,7 @@ namespace
             }
             bool const trace_was = emu_trace::g_on;
             emu_trace::g_on = false;
-            for(int32_t e = 0; e < r.n_io; ++e)
+            for(int32_t e = 0; first_chunk && e < r.n_io; ++e)
             {
                 pe_b200_io const io = r.io[e];
                 if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
@@ -297,7 +306,7 @@ namespace
                 }
             }
             emu_trace::g_on = trace_was;
-            double t = r.t0;
+            double t = chunked ? r.t_chunk[chunk] : r.t0;
 
             // one section: warps advance phase by phase; within a phase thread after thread (no cross-thread
             // dependency may exist inside a phase: the race detector checks exactly that)
@@ -391,12 +400,12 @@ namespace
                 for(auto& a: nconv) { a = {false, false}; }
                 for(auto& a: fail) { a = {false, false}; }
             };
-            if(r.has_prep)
+            if(r.has_prep && first_chunk)
             {
                 clear_flags();
                 run_section(0, false, false, nconv, fail);
             }
-            for(int32_t s = 0; s < r.n_steps; ++s)
+            for(int32_t s = s_begin; s < s_end; ++s)
             {
                 if(r.time_stepping)
                 {
@@ -468,7 +477,7 @@ namespace
                     }
                 }
             }
-            for(int32_t e = 0; e < r.n_io; ++e)
+            for(int32_t e = 0; last_chunk && e < r.n_io; ++e)
             {
                 pe_b200_io const io = r.io[e];
                 if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
