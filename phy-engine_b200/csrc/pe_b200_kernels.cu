@@ -413,6 +413,27 @@ namespace
         uint32_t line, off;  // current line, offset of the current op inside it
         // generic-reader state (ops the fast path does not take)
         uint32_t cur, m;
+        // operand prefetch: when a line of words arrives, lane l asks L2 for the two workspace rows word l names (a
+        // row = this group's 32 lanes = two 128-byte lines), five or so ops before they are used
+        char const* pf_base;
+        uint32_t pf_LS8, pf_slots;
+
+        __device__ __forceinline__ void prefetch_operands() const
+        {
+            uint32_t const a = dlo & 0x7fffu, b = dhi & 0x7fffu;
+            if(a < pf_slots)
+            {
+                char const* p = pf_base + (uint64_t)a * pf_LS8;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            }
+            if(b < pf_slots && b != a)
+            {
+                char const* p = pf_base + (uint64_t)b * pf_LS8;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            }
+        }
 
         __device__ __forceinline__ uint32_t dec(uint32_t f) const
         {
@@ -424,12 +445,15 @@ namespace
             dlo = dec(w & 0xffffu);
             dhi = dec(w >> 16);
         }
-        __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S)
+        __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S, char const* pf_base_, uint32_t pf_LS8_, uint32_t pf_slots_)
         {
             base = b;
             lane = lane_;
             stream = stream_;
             sm = S - 1u;
+            pf_base = pf_base_;
+            pf_LS8 = pf_LS8_;
+            pf_slots = pf_slots_;
             line = 0;
             off = 0;
             w = __ldg(base + lane);
@@ -446,6 +470,7 @@ namespace
             off = 0;
             nw = __ldg(base + (line + 1u) * 32u + lane);
             decode();
+            prefetch_operands();
         }
         __device__ __forceinline__ void adv(uint32_t n)
         {
@@ -503,7 +528,8 @@ namespace
         if(chk) { xo = *at(dst); }
         double acc = 0.0;
 #pragma unroll
-        for(int i = 0; i < 2 * NA; ++i) { acc = PE_ADD(acc, (g[i] >> 31) ? -sv[i] : sv[i]); }
+        // acc +/- s as fma(s, +/-1.0, acc): one rounding, the same value as the add, no select on the operand
+        for(int i = 0; i < 2 * NA; ++i) { acc = fma(sv[i], __hiloint2double((int)(0x3ff00000u | (g[i] & 0x80000000u)), 0), acc); }
 #pragma unroll
         for(int i = 0; i < NB; ++i) { acc = fma(-av[i], bv[i], acc); }
         if(flags & PE_F_SCALE) { acc = PE_MUL(acc, sc); }
@@ -639,7 +665,8 @@ namespace
             bool nconv1 = false, fail1 = false;
             {
                 line_reader rd;
-                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
+                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S, reinterpret_cast<char const*>(r.wsg + (int64_t)group * 32), (uint32_t)(r.LSw * 8),
+                        r.prefetch ? (uint32_t)r.n_slots : 0u);
                 bool const en[1] = {en1};
                 bool nconv[1] = {false}, fail[1] = {false};
                 for(;;)

@@ -223,6 +223,7 @@ extern "C"
         // n_chunks chunks of chunk_steps steps; persistent CTAs take (chunk, group) items from an atomic counter in
         // chunk-major order, so a group migrates between SMs and the last wave is one chunk long instead of one run.
         // sched = NULL: one CTA per group runs the whole launch.
+        int32_t prefetch;     // tree-streaming form: 1 = L2 prefetch of the operands of the next line of program words
         int32_t chunk_steps;
         int32_t n_chunks;
         uint32_t* sched;      // device: [0] next item, [1 + g] chunks of group g completed (zeroed before the launch)

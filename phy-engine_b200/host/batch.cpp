@@ -444,6 +444,7 @@ namespace pe_b200
             if(!d_ws.ensure(static_cast<std::size_t>(pr.r_slots) * static_cast<std::size_t>(LSw) * sizeof(double))) { return dev_fail(error, "alloc HBM workspace"); }
             r.wsg = static_cast<double*>(d_ws.p);
             r.LSw = LSw;
+            r.prefetch = res_prefetch;
             // dynamic (group, chunk) scheduling of long time loops: up to 32 chunks of at least 4 steps
             int nc{res_chunks > 0 ? res_chunks : std::min(32, n_steps / 4)};
             nc = std::clamp(nc, 1, 32);
