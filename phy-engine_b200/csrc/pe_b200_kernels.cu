@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -415,21 +416,18 @@ namespace
         uint32_t cur, m;
         // operand prefetch: when a line of words arrives, lane l asks L2 for the two workspace rows word l names (a
         // row = this group's 32 lanes = two 128-byte lines), five or so ops before they are used
-        char const* pf_base;
-        uint32_t pf_LS8, pf_slots;
-
-        __device__ __forceinline__ void prefetch_operands() const
+        __device__ __forceinline__ void prefetch_operands(char const* group_base, uint32_t LS8, uint32_t n_slots) const
         {
             uint32_t const a = dlo & 0x7fffu, b = dhi & 0x7fffu;
-            if(a < pf_slots)
+            if(a < n_slots)
             {
-                char const* p = pf_base + (uint64_t)a * pf_LS8;
+                char const* p = group_base + (uint64_t)a * LS8;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
             }
-            if(b < pf_slots && b != a)
+            if(b < n_slots && b != a)
             {
-                char const* p = pf_base + (uint64_t)b * pf_LS8;
+                char const* p = group_base + (uint64_t)b * LS8;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
             }
@@ -445,15 +443,12 @@ namespace
             dlo = dec(w & 0xffffu);
             dhi = dec(w >> 16);
         }
-        __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S, char const* pf_base_, uint32_t pf_LS8_, uint32_t pf_slots_)
+        __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S)
         {
             base = b;
             lane = lane_;
             stream = stream_;
             sm = S - 1u;
-            pf_base = pf_base_;
-            pf_LS8 = pf_LS8_;
-            pf_slots = pf_slots_;
             line = 0;
             off = 0;
             w = __ldg(base + lane);
@@ -470,12 +465,17 @@ namespace
             off = 0;
             nw = __ldg(base + (line + 1u) * 32u + lane);
             decode();
-            prefetch_operands();
         }
-        __device__ __forceinline__ void adv(uint32_t n)
+        // returns true when a new line of words was taken (the caller then prefetches its operands)
+        __device__ __forceinline__ bool adv(uint32_t n)
         {
             off += n;
-            if(off >= 32u) { next_line(); }
+            if(off >= 32u)
+            {
+                next_line();
+                return true;
+            }
+            return false;
         }
         // pe_rinterp reader interface (mask is always 0: one stream per warp has no per-column rows)
         __device__ __forceinline__ uint32_t head() const { return raw(0); }
@@ -486,9 +486,14 @@ namespace
             return 0u;
         }
         __device__ __forceinline__ uint32_t next() { return raw(cur++); }
-        __device__ __forceinline__ void close() { adv(2u + m); }
-        __device__ __forceinline__ void bar() { adv(1u); }
-        __device__ __forceinline__ void skip() { next_line(); }
+        __device__ __forceinline__ void close() { fresh = adv(2u + m) || fresh; }
+        __device__ __forceinline__ void bar() { fresh = adv(1u) || fresh; }
+        __device__ __forceinline__ void skip()
+        {
+            next_line();
+            fresh = true;
+        }
+        bool fresh;  // a line was taken through the generic interface since the caller last looked
     };
 
     // address of slot `slot` of this thread's lane in the HBM workspace (by-value functor: lives in registers)
@@ -501,7 +506,7 @@ namespace
 
     // one DOT with NA rows of packed sources and NB pairs: every operand load is issued before the first value is used
     template <int NA, int NB>
-    __device__ __forceinline__ void tree_dot(line_reader const& rd, lane_ws const& at, pe_rinterp::tol_t const& tol, bool en, bool check, bool& nconv, bool& fail)
+    __device__ __forceinline__ void tree_dot(line_reader const& rd, lane_ws const& at, pe_b200_rrun const& r, bool en, bool check, bool& nconv, bool& fail)
     {
         // words of the op: [h][mask][ctl][scale][src x NA][pair x NB]
         uint32_t const flags = rd.raw(2) >> 16;
@@ -542,7 +547,7 @@ namespace
         {
             // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
             bool const br = (flags & PE_F_CHECK_I) != 0u;
-            double const tl = (br ? tol.i_abstol : tol.v_abstol) + (br ? tol.i_reltol : tol.v_reltol) * fmax(fabs(acc), fabs(xo));
+            double const tl = (br ? r.i_abstol : r.v_abstol) + (br ? r.i_reltol : r.v_reltol) * fmax(fabs(acc), fabs(xo));
             if(fabs(acc - xo) > tl) { nconv = true; }
         }
         if(en) { *at(dst) = acc; }
@@ -590,15 +595,6 @@ namespace
         bool const first_chunk = chunk == 0u, last_chunk = chunk + 1u == NC;
         int32_t const s_begin = r.sched != nullptr ? (int32_t)chunk * r.chunk_steps : 0;
         int32_t const s_end = r.sched != nullptr ? min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
-
-        rctx c;
-        c.ws = r.wsg + glane;
-        c.I = (uint64_t)r.LSw;
-        c.S = S;
-        c.C = 1;
-        c.col = 0;
-        c.stream = warp;
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
 
         bool const real_lane = glane < r.n_lanes;
         int32_t status = real_lane ? r.status[glane] : (int32_t)PE_ST_SINGULAR;
@@ -665,12 +661,15 @@ namespace
             bool nconv1 = false, fail1 = false;
             {
                 line_reader rd;
-                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S, reinterpret_cast<char const*>(r.wsg + (int64_t)group * 32), (uint32_t)(r.LSw * 8),
-                        r.prefetch ? (uint32_t)r.n_slots : 0u);
-                bool const en[1] = {en1};
-                bool nconv[1] = {false}, fail[1] = {false};
+                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
+                rd.fresh = false;
                 for(;;)
                 {
+                    if(rd.fresh)
+                    {
+                        rd.fresh = false;
+                        if(r.prefetch) { rd.prefetch_operands(at.wl - lane * 8u, at.LS8, (uint32_t)r.n_slots); }
+                    }
                     uint32_t const h = rd.raw(0);
                     uint32_t const op = h & 0xffu;
                     uint32_t const na = (h >> 8) & 0x1fu, nb = (h >> 18) & 0x3fu;
@@ -678,20 +677,20 @@ namespace
                     {
                         switch(na * 4u + nb)
                         {
-                            case 0: tree_dot<0, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 1: tree_dot<0, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 2: tree_dot<0, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 3: tree_dot<0, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 4: tree_dot<1, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 5: tree_dot<1, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 6: tree_dot<1, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 7: tree_dot<1, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 8: tree_dot<2, 0>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 9: tree_dot<2, 1>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            case 10: tree_dot<2, 2>(rd, at, tol, en1, check, nconv1, fail1); break;
-                            default: tree_dot<2, 3>(rd, at, tol, en1, check, nconv1, fail1); break;
+                            case 0: tree_dot<0, 0>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 1: tree_dot<0, 1>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 2: tree_dot<0, 2>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 3: tree_dot<0, 3>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 4: tree_dot<1, 0>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 5: tree_dot<1, 1>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 6: tree_dot<1, 2>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 7: tree_dot<1, 3>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 8: tree_dot<2, 0>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 9: tree_dot<2, 1>(rd, at, r, en1, check, nconv1, fail1); break;
+                            case 10: tree_dot<2, 2>(rd, at, r, en1, check, nconv1, fail1); break;
+                            default: tree_dot<2, 3>(rd, at, r, en1, check, nconv1, fail1); break;
                         }
-                        rd.adv(4u + na + nb);
+                        rd.fresh = rd.adv(4u + na + nb);
                         continue;
                     }
                     if(op == PE_OP_CAP_STEP)
@@ -708,10 +707,23 @@ namespace
                             *ph = hv;
                             *pg = gv;
                         }
-                        rd.adv(8u);
+                        rd.fresh = rd.adv(8u);
                         continue;
                     }
+                    // everything else goes through the generic vector-op executor (pe_b200_rinterp.h)
+                    rctx c;
+                    c.ws = r.wsg + glane;
+                    c.I = (uint64_t)r.LSw;
+                    c.S = S;
+                    c.C = 1;
+                    c.col = 0;
+                    c.stream = warp;
+                    tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+                    bool const en[1] = {en1};
+                    bool nconv[1] = {false}, fail[1] = {false};
                     int const k = rvop<1>(rd, c, t, tol, en, check, nconv, fail);
+                    nconv1 = nconv1 || nconv[0];
+                    fail1 = fail1 || fail[0];
                     if(k == V_END || k == V_BAD) { break; }
                     if(k == V_BAR)
                     {
@@ -724,8 +736,6 @@ namespace
                         rd.close();
                     }
                 }
-                nconv1 = nconv1 || nconv[0];
-                fail1 = fail1 || fail[0];
                 __syncthreads();  // results of this section are visible to every warp of the CTA
             }
 
@@ -917,6 +927,14 @@ extern "C"
                 cudaEventRecord(e0, (cudaStream_t)stream);
             }
             void (*tk)(pe_b200_rrun) = block <= 256 ? pe_b200_tree_kernel<256, 4> : (block <= 512 ? pe_b200_tree_kernel<512, 2> : pe_b200_tree_kernel<1024, 1>);
+            if(char const* ev = getenv("PE_B200_TREE_VARIANT"))
+            {
+                // tuning experiments: register budget / CTAs per SM
+                int const v = atoi(ev);
+                if(v == 3 && block <= 512) { tk = pe_b200_tree_kernel<512, 3>; }
+                if(v == 6 && block <= 256) { tk = pe_b200_tree_kernel<256, 6>; }
+                if(v == 2 && block <= 1024) { tk = pe_b200_tree_kernel<1024, 2>; }
+            }
             int tgrid = grid;
             if(run->sched != nullptr)
             {

@@ -523,7 +523,7 @@ extern "C"
         // bit 8 of `chunks` switches the L2 operand prefetch of the tree-streaming kernel off (tuning knob)
         if(b == nullptr || chunks < 0 || (chunks & 0xff) > 32) { return 1; }
         static_cast<batch*>(b)->res_chunks = chunks & 0xff;
-        static_cast<batch*>(b)->res_prefetch = (chunks & 0x100) ? 0 : 1;
+        static_cast<batch*>(b)->res_prefetch = (chunks & 0x100) ? 0 : ((chunks & 0x200) ? 2 : 1);  // bit 9: prefetch into L1
         return 0;
     }
 
