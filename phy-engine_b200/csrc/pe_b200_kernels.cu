@@ -505,300 +505,429 @@ namespace
     };
 
     // one DOT with NA rows of packed sources and NB pairs: every operand load is issued before the first value is used
-    template <int NA, int NB>
-    __device__ __forceinline__ void tree_dot(line_reader const& rd, lane_ws const& at, pe_b200_rrun const& r, bool en, bool check, bool& nconv, bool& fail)
+    // one DOT with NA rows of packed sources and NB pairs for the J instances of this thread (lanes 32 apart: 256 bytes
+    // apart in a workspace row): every operand load is issued before the first value is used
+    template <int J, int NA, int NB>
+    __device__ __forceinline__ void tree_dot(line_reader const& rd, lane_ws const& at, pe_b200_rrun const& r, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
     {
         // words of the op: [h][mask][ctl][scale][src x NA][pair x NB]
         uint32_t const flags = rd.raw(2) >> 16;
         uint32_t const dst = rd.lo(2) & 0x7fffu;
         uint32_t g[2 * NA + 1];
-        double sv[2 * NA + 1], av[NB + 1], bv[NB + 1];
+        double sv[2 * NA + 1][J], av[NB + 1][J], bv[NB + 1][J];
 #pragma unroll
         for(int i = 0; i < NA; ++i)
         {
             g[2 * i] = rd.lo(4 + i);
             g[2 * i + 1] = rd.hi(4 + i);
-            sv[2 * i] = *at(g[2 * i] & 0x7fffu);
-            sv[2 * i + 1] = *at(g[2 * i + 1] & 0x7fffu);
+            double const* p0 = at(g[2 * i] & 0x7fffu);
+            double const* p1 = at(g[2 * i + 1] & 0x7fffu);
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                sv[2 * i][j] = p0[32 * j];
+                sv[2 * i + 1][j] = p1[32 * j];
+            }
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i)
         {
-            av[i] = *at(rd.lo(4 + NA + i) & 0x7fffu);
-            bv[i] = *at(rd.hi(4 + NA + i) & 0x7fffu);
+            double const* pa = at(rd.lo(4 + NA + i) & 0x7fffu);
+            double const* pb = at(rd.hi(4 + NA + i) & 0x7fffu);
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                av[i][j] = pa[32 * j];
+                bv[i][j] = pb[32 * j];
+            }
         }
-        double sc = 1.0, xo = 0.0;
-        if(flags & PE_F_SCALE) { sc = *at(rd.lo(3) & 0x7fffu); }
+        double sc[J], xo[J];
+#pragma unroll
+        for(int j = 0; j < J; ++j)
+        {
+            sc[j] = 1.0;
+            xo[j] = 0.0;
+        }
+        if(flags & PE_F_SCALE)
+        {
+            double const* ps = at(rd.lo(3) & 0x7fffu);
+#pragma unroll
+            for(int j = 0; j < J; ++j) { sc[j] = ps[32 * j]; }
+        }
         bool const chk = check && (flags & (PE_F_CHECK_V | PE_F_CHECK_I));
-        if(chk) { xo = *at(dst); }
-        double acc = 0.0;
+        double* const pd = at(dst);
+        if(chk)
+        {
 #pragma unroll
+            for(int j = 0; j < J; ++j) { xo[j] = pd[32 * j]; }
+        }
+        double acc[J];
+#pragma unroll
+        for(int j = 0; j < J; ++j) { acc[j] = 0.0; }
         // acc +/- s as fma(s, +/-1.0, acc): one rounding, the same value as the add, no select on the operand
-        for(int i = 0; i < 2 * NA; ++i) { acc = fma(sv[i], __hiloint2double((int)(0x3ff00000u | (g[i] & 0x80000000u)), 0), acc); }
 #pragma unroll
-        for(int i = 0; i < NB; ++i) { acc = fma(-av[i], bv[i], acc); }
-        if(flags & PE_F_SCALE) { acc = PE_MUL(acc, sc); }
+        for(int i = 0; i < 2 * NA; ++i)
+        {
+            double const sg = __hiloint2double((int)(0x3ff00000u | (g[i] & 0x80000000u)), 0);
+#pragma unroll
+            for(int j = 0; j < J; ++j) { acc[j] = fma(sv[i][j], sg, acc[j]); }
+        }
+#pragma unroll
+        for(int i = 0; i < NB; ++i)
+        {
+#pragma unroll
+            for(int j = 0; j < J; ++j) { acc[j] = fma(-av[i][j], bv[i][j], acc[j]); }
+        }
+        if(flags & PE_F_SCALE)
+        {
+#pragma unroll
+            for(int j = 0; j < J; ++j) { acc[j] = PE_MUL(acc[j], sc[j]); }
+        }
         if(flags & PE_F_RECIP)
         {
-            if(acc == 0.0 || !isfinite(acc)) { fail = true; }
-            acc = PE_RCP(acc);
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                if(acc[j] == 0.0 || !isfinite(acc[j])) { fail[j] = true; }
+                acc[j] = PE_RCP(acc[j]);
+            }
         }
         if(chk)
         {
             // circuit.h:923-948: |new - old| > abstol + reltol * max(|new|, |old|)  => not converged
             bool const br = (flags & PE_F_CHECK_I) != 0u;
-            double const tl = (br ? r.i_abstol : r.v_abstol) + (br ? r.i_reltol : r.v_reltol) * fmax(fabs(acc), fabs(xo));
-            if(fabs(acc - xo) > tl) { nconv = true; }
+            double const at_ = br ? r.i_abstol : r.v_abstol, rt_ = br ? r.i_reltol : r.v_reltol;
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                double const tl = at_ + rt_ * fmax(fabs(acc[j]), fabs(xo[j]));
+                if(fabs(acc[j] - xo[j]) > tl) { nconv[j] = true; }
+            }
         }
-        if(en) { *at(dst) = acc; }
+#pragma unroll
+        for(int j = 0; j < J; ++j)
+        {
+            if(en[j]) { pd[32 * j] = acc[j]; }
+        }
     }
 
-    template <int MAXT, int MINB>
+    // CTA = S warps x (32 x J) lanes: thread (warp s, lane l) runs stream s for lanes l, l + 32, ... of the group
+    template <int J, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
     {
-        __shared__ uint32_t s_flags[3][32];
+        __shared__ uint32_t s_flags[3][32 * J];
         __shared__ uint32_t s_item;
         using namespace pe_rinterp;
         uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
         uint32_t const S = (uint32_t)r.S;
-        uint32_t const NG = (uint32_t)((r.n_lanes + 31) / 32), NC = r.sched != nullptr ? (uint32_t)r.n_chunks : 1u;
+        uint32_t const GL = 32u * J;  // lanes per group
+        uint32_t const NG = (uint32_t)((r.n_lanes + GL - 1) / GL), NC = r.sched != nullptr ? (uint32_t)r.n_chunks : 1u;
         for(;;)
         {
-        // ---- next work item: (chunk c of the time loop, 32-lane group g)
-        uint32_t item = blockIdx.x;
-        if(r.sched != nullptr)
-        {
-            if(tid == 0) { s_item = atomicAdd(r.sched, 1u); }
-            __syncthreads();
-            item = s_item;
-        }
-        if(item >= NC * NG) { break; }
-        uint32_t const chunk = item / NG, group = item - chunk * NG;
-        if(r.sched != nullptr && chunk > 0u)
-        {
-            // chunk c of a group starts when its chunk c - 1 (run by some other CTA) has published its results; the
-            // acquire load also drops whatever this SM's L1 still holds of the group's workspace
-            if(tid == 0)
+            // ---- next work item: (chunk c of the time loop, lane group g)
+            uint32_t item = blockIdx.x;
+            if(r.sched != nullptr)
             {
-                uint32_t v;
-                for(;;)
+                if(tid == 0) { s_item = atomicAdd(r.sched, 1u); }
+                __syncthreads();
+                item = s_item;
+            }
+            if(item >= NC * NG) { break; }
+            uint32_t const chunk = item / NG, group = item - chunk * NG;
+            if(r.sched != nullptr && chunk > 0u)
+            {
+                // chunk c of a group starts when its chunk c - 1 (run by some other CTA) has published its results; the
+                // acquire load also drops whatever this SM's L1 still holds of the group's workspace
+                if(tid == 0)
                 {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(r.sched + 1 + group) : "memory");
-                    if(v >= chunk) { break; }
-                    __nanosleep(256);
+                    uint32_t v;
+                    for(;;)
+                    {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(r.sched + 1 + group) : "memory");
+                        if(v >= chunk) { break; }
+                        __nanosleep(256);
+                    }
+                }
+                __syncthreads();
+            }
+            int64_t const glane = (int64_t)group * GL + lane;  // first of this thread's lanes; the others are + 32 j
+            lane_ws const at{reinterpret_cast<char*>(r.wsg + glane), (uint32_t)(r.LSw * 8)};
+            bool const first_chunk = chunk == 0u, last_chunk = chunk + 1u == NC;
+            int32_t const s_begin = r.sched != nullptr ? (int32_t)chunk * r.chunk_steps : 0;
+            int32_t const s_end = r.sched != nullptr ? min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
+
+            bool real_lane[J], counted[J], ok[J], done[J];
+            int32_t status[J];
+            uint32_t solves[J];
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                real_lane[j] = glane + 32 * j < r.n_lanes;
+                status[j] = real_lane[j] ? r.status[glane + 32 * j] : (int32_t)PE_ST_SINGULAR;
+                counted[j] = real_lane[j] && status[j] == PE_ST_OK;
+                ok[j] = counted[j];
+                done[j] = false;
+                solves[j] = 0;
+            }
+
+            for(uint32_t e = warp; first_chunk && e < (uint32_t)r.n_io; e += n_warps)
+            {
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
+                uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
+                double* const dst = at(io.slot_kind & 0xffffu);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    double v = 0.0;
+                    if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+                    else if(real_lane[j])
+                    {
+                        v = kind == PE_IO_U ? r.wu[(int64_t)io.src * r.LSu + glane + 32 * j] : r.wx[(int64_t)io.src * r.LSx + (glane + 32 * j) / r.ppi];
+                    }
+                    dst[32 * j] = v;
                 }
             }
+            if(tid < 96 * J) { (&s_flags[0][0])[tid] = 0u; }
             __syncthreads();
-        }
-        int64_t const glane = (int64_t)group * 32 + lane;
-        lane_ws const at{reinterpret_cast<char*>(r.wsg + glane), (uint32_t)(r.LSw * 8)};
-        bool const first_chunk = chunk == 0u, last_chunk = chunk + 1u == NC;
-        int32_t const s_begin = r.sched != nullptr ? (int32_t)chunk * r.chunk_steps : 0;
-        int32_t const s_end = r.sched != nullptr ? min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
 
-        bool const real_lane = glane < r.n_lanes;
-        int32_t status = real_lane ? r.status[glane] : (int32_t)PE_ST_SINGULAR;
-        bool const counted = real_lane && status == PE_ST_OK;
-        bool ok = counted;
-        uint32_t solves = 0;
-
-        for(uint32_t e = warp; first_chunk && e < (uint32_t)r.n_io; e += n_warps)
-        {
-            pe_b200_io const io = r.io[e];
-            if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
-            uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
-            double v;
-            if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
-            else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + glane]; }
-            else { v = r.wx[(int64_t)io.src * r.LSx + (real_lane ? glane / r.ppi : 0)]; }
-            *at(io.slot_kind & 0xffffu) = v;
-        }
-        if(tid < 96) { (&s_flags[0][0])[tid] = 0u; }
-        __syncthreads();
-
-        // One copy of the interpreter serves the three sections: stage 0 = prep, 1 = the step section of time step s,
-        // 2 = one Newton iteration (the iter section).  The sequencing is uniform over the CTA.
-        double t = r.sched != nullptr ? r.t_chunk[chunk] : r.t0;
-        int32_t s = s_begin, it = 0;
-        int stage = (r.has_prep && first_chunk) ? 0 : 1;
-        int fi = 0;
-        bool done = false;
-        for(;;)
-        {
-            int sec;
-            bool en1, check;
-            if(stage == 0)
+            // One copy of the interpreter serves the three sections: stage 0 = prep, 1 = the step section of time step
+            // s, 2 = one Newton iteration (the iter section).  The sequencing is uniform over the CTA.
+            double t = r.sched != nullptr ? r.t_chunk[chunk] : r.t0;
+            int32_t s = s_begin, it = 0;
+            int stage = (r.has_prep && first_chunk) ? 0 : 1;
+            int fi = 0;
+            for(;;)
             {
-                sec = 0;
-                en1 = ok;
-                check = false;
-            }
-            else if(stage == 1)
-            {
-                if(s >= s_end) { break; }
-                if(!(r.time_stepping && r.has_step))
+                int sec;
+                bool en[J], check;
+                if(stage == 0)
                 {
-                    if(r.time_stepping) { t = t + r.dt; }
-                    done = !ok;
+                    sec = 0;
+                    check = false;
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { en[j] = ok[j]; }
+                }
+                else if(stage == 1)
+                {
+                    if(s >= s_end) { break; }
+                    if(!(r.time_stepping && r.has_step))
+                    {
+                        if(r.time_stepping) { t = t + r.dt; }
+#pragma unroll
+                        for(int j = 0; j < J; ++j) { done[j] = !ok[j]; }
+                        it = 0;
+                        stage = 2;
+                        continue;
+                    }
+                    // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
+                    sec = 1;
+                    check = false;
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { en[j] = ok[j]; }
+                }
+                else
+                {
+                    sec = 2;
+                    check = r.nonlinear != 0;
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { en[j] = !done[j]; }
+                    if(warp == 0)
+                    {
+#pragma unroll
+                        for(int j = 0; j < J; ++j) { s_flags[fi == 2 ? 0 : fi + 1][lane + 32 * j] = 0u; }
+                    }
+                }
+
+                // ---- run the section
+                bool nconv[J], fail[J];
+#pragma unroll
+                for(int j = 0; j < J; ++j) { nconv[j] = fail[j] = false; }
+                {
+                    line_reader rd;
+                    rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
+                    rd.fresh = false;
+                    for(;;)
+                    {
+                        if(rd.fresh)
+                        {
+                            rd.fresh = false;
+                            if(r.prefetch)
+                            {
+#pragma unroll
+                                for(int j = 0; j < J; ++j) { rd.prefetch_operands(at.wl - lane * 8u + 256u * j, at.LS8, (uint32_t)r.n_slots); }
+                            }
+                        }
+                        uint32_t const h = rd.raw(0);
+                        uint32_t const op = h & 0xffu;
+                        uint32_t const na = (h >> 8) & 0x1fu, nb = (h >> 18) & 0x3fu;
+                        if(op == PE_OP_DOT && na <= 2u && nb <= 3u)
+                        {
+                            switch(na * 4u + nb)
+                            {
+                                case 0: tree_dot<J, 0, 0>(rd, at, r, en, check, nconv, fail); break;
+                                case 1: tree_dot<J, 0, 1>(rd, at, r, en, check, nconv, fail); break;
+                                case 2: tree_dot<J, 0, 2>(rd, at, r, en, check, nconv, fail); break;
+                                case 3: tree_dot<J, 0, 3>(rd, at, r, en, check, nconv, fail); break;
+                                case 4: tree_dot<J, 1, 0>(rd, at, r, en, check, nconv, fail); break;
+                                case 5: tree_dot<J, 1, 1>(rd, at, r, en, check, nconv, fail); break;
+                                case 6: tree_dot<J, 1, 2>(rd, at, r, en, check, nconv, fail); break;
+                                case 7: tree_dot<J, 1, 3>(rd, at, r, en, check, nconv, fail); break;
+                                case 8: tree_dot<J, 2, 0>(rd, at, r, en, check, nconv, fail); break;
+                                case 9: tree_dot<J, 2, 1>(rd, at, r, en, check, nconv, fail); break;
+                                case 10: tree_dot<J, 2, 2>(rd, at, r, en, check, nconv, fail); break;
+                                default: tree_dot<J, 2, 3>(rd, at, r, en, check, nconv, fail); break;
+                            }
+                            rd.fresh = rd.adv(4u + na + nb);
+                            continue;
+                        }
+                        if(op == PE_OP_CAP_STEP)
+                        {
+                            // [h][mask][hist][prev_g][C][dt][va][vb]  (capacitor.h:106-128)
+                            double* const ph = at(rd.lo(2) & 0x7fffu);
+                            double* const pg = at(rd.lo(3) & 0x7fffu);
+                            double const* const pc = at(rd.lo(4) & 0x7fffu);
+                            double const* const pt = at(rd.lo(5) & 0x7fffu);
+                            double const* const pa = at(rd.lo(6) & 0x7fffu);
+                            double const* const pb = at(rd.lo(7) & 0x7fffu);
+                            double hv[J], gv[J], cv[J], tv[J], va[J], vb[J];
+#pragma unroll
+                            for(int j = 0; j < J; ++j)
+                            {
+                                hv[j] = ph[32 * j];
+                                gv[j] = pg[32 * j];
+                                cv[j] = pc[32 * j];
+                                tv[j] = pt[32 * j];
+                                va[j] = pa[32 * j];
+                                vb[j] = pb[32 * j];
+                            }
+#pragma unroll
+                            for(int j = 0; j < J; ++j)
+                            {
+                                pe_models::cap_step(cv[j], tv[j], PE_SUB(va[j], vb[j]), hv[j], gv[j]);
+                                if(en[j])
+                                {
+                                    ph[32 * j] = hv[j];
+                                    pg[32 * j] = gv[j];
+                                }
+                            }
+                            rd.fresh = rd.adv(8u);
+                            continue;
+                        }
+                        // everything else goes through the generic vector-op executor (pe_b200_rinterp.h)
+                        rctx c;
+                        c.ws = r.wsg + glane;
+                        c.I = (uint64_t)r.LSw;
+                        c.S = S;
+                        c.C = 1;
+                        c.col = 0;
+                        c.stream = warp;
+                        c.js = 32;
+                        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+                        int const k = rvop<J>(rd, c, t, tol, en, check, nconv, fail);
+                        if(k == V_END || k == V_BAD) { break; }
+                        if(k == V_BAR)
+                        {
+                            __syncthreads();
+                            rd.bar();
+                        }
+                        else if(k == V_SKIP) { rd.skip(); }
+                        else
+                        {
+                            rd.close();
+                        }
+                    }
+                    __syncthreads();  // results of this section are visible to every warp of the CTA
+                }
+
+                // ---- what comes next
+                if(stage == 0) { stage = 1; }
+                else if(stage == 1)
+                {
+                    t = t + r.dt;
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { done[j] = !ok[j]; }
                     it = 0;
                     stage = 2;
-                    continue;
                 }
-                // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
-                sec = 1;
-                en1 = ok;
-                check = false;
-            }
-            else
-            {
-                sec = 2;
-                en1 = !done;
-                check = r.nonlinear != 0;
-                if(warp == 0) { s_flags[fi == 2 ? 0 : fi + 1][lane] = 0u; }
-            }
-
-            // ---- run the section
-            bool nconv1 = false, fail1 = false;
-            {
-                line_reader rd;
-                rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
-                rd.fresh = false;
-                for(;;)
+                else
                 {
-                    if(rd.fresh)
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
                     {
-                        rd.fresh = false;
-                        if(r.prefetch) { rd.prefetch_operands(at.wl - lane * 8u, at.LS8, (uint32_t)r.n_slots); }
+                        if(nconv[j] || fail[j]) { atomicOr(&s_flags[fi][lane + 32 * j], (nconv[j] ? 1u : 0u) | (fail[j] ? 2u : 0u)); }
                     }
-                    uint32_t const h = rd.raw(0);
-                    uint32_t const op = h & 0xffu;
-                    uint32_t const na = (h >> 8) & 0x1fu, nb = (h >> 18) & 0x3fu;
-                    if(op == PE_OP_DOT && na <= 2u && nb <= 3u)
+                    __syncthreads();
+                    ++it;
+                    bool all_done = true;
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
                     {
-                        switch(na * 4u + nb)
+                        uint32_t const f = s_flags[fi][lane + 32 * j];
+                        if(!done[j])
                         {
-                            case 0: tree_dot<0, 0>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 1: tree_dot<0, 1>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 2: tree_dot<0, 2>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 3: tree_dot<0, 3>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 4: tree_dot<1, 0>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 5: tree_dot<1, 1>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 6: tree_dot<1, 2>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 7: tree_dot<1, 3>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 8: tree_dot<2, 0>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 9: tree_dot<2, 1>(rd, at, r, en1, check, nconv1, fail1); break;
-                            case 10: tree_dot<2, 2>(rd, at, r, en1, check, nconv1, fail1); break;
-                            default: tree_dot<2, 3>(rd, at, r, en1, check, nconv1, fail1); break;
+                            ++solves[j];
+                            if(f & 2u)
+                            {
+                                status[j] = PE_ST_SINGULAR;
+                                ok[j] = false;
+                                done[j] = true;
+                            }
+                            else if(!r.nonlinear || !(f & 1u)) { done[j] = true; }
+                            else if(it >= r.max_iter)
+                            {
+                                status[j] = PE_ST_NO_CONVERGENCE;
+                                ok[j] = false;
+                                done[j] = true;
+                            }
                         }
-                        rd.fresh = rd.adv(4u + na + nb);
-                        continue;
+                        all_done = all_done && done[j];
                     }
-                    if(op == PE_OP_CAP_STEP)
+                    fi = fi == 2 ? 0 : fi + 1;
+                    if(__syncthreads_and(all_done ? 1 : 0))
                     {
-                        // [h][mask][hist][prev_g][C][dt][va][vb]  (capacitor.h:106-128)
-                        double* const ph = at(rd.lo(2) & 0x7fffu);
-                        double* const pg = at(rd.lo(3) & 0x7fffu);
-                        double hv = *ph, gv = *pg;
-                        double const C_ = *at(rd.lo(4) & 0x7fffu), dtv = *at(rd.lo(5) & 0x7fffu);
-                        double const va = *at(rd.lo(6) & 0x7fffu), vb = *at(rd.lo(7) & 0x7fffu);
-                        pe_models::cap_step(C_, dtv, PE_SUB(va, vb), hv, gv);
-                        if(en1)
+                        if(r.wave != nullptr && warp == 0)
                         {
-                            *ph = hv;
-                            *pg = gv;
+#pragma unroll
+                            for(int j = 0; j < J; ++j)
+                            {
+                                if(!ok[j]) { continue; }
+                                for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + glane + 32 * j] = at(__ldg(r.probes + p))[32 * j]; }
+                            }
                         }
-                        rd.fresh = rd.adv(8u);
-                        continue;
-                    }
-                    // everything else goes through the generic vector-op executor (pe_b200_rinterp.h)
-                    rctx c;
-                    c.ws = r.wsg + glane;
-                    c.I = (uint64_t)r.LSw;
-                    c.S = S;
-                    c.C = 1;
-                    c.col = 0;
-                    c.stream = warp;
-                    tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
-                    bool const en[1] = {en1};
-                    bool nconv[1] = {false}, fail[1] = {false};
-                    int const k = rvop<1>(rd, c, t, tol, en, check, nconv, fail);
-                    nconv1 = nconv1 || nconv[0];
-                    fail1 = fail1 || fail[0];
-                    if(k == V_END || k == V_BAD) { break; }
-                    if(k == V_BAR)
-                    {
-                        __syncthreads();
-                        rd.bar();
-                    }
-                    else if(k == V_SKIP) { rd.skip(); }
-                    else
-                    {
-                        rd.close();
+                        ++s;
+                        stage = 1;
                     }
                 }
-                __syncthreads();  // results of this section are visible to every warp of the CTA
             }
-
-            // ---- what comes next
-            if(stage == 0) { stage = 1; }
-            else if(stage == 1)
+            for(uint32_t e = warp; last_chunk && e < (uint32_t)r.n_io; e += n_warps)
             {
-                t = t + r.dt;
-                done = !ok;
-                it = 0;
-                stage = 2;
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
+                double const* const src = at(io.slot_kind & 0xffffu);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    if(counted[j]) { r.wu[(int64_t)io.src * r.LSu + glane + 32 * j] = src[32 * j]; }
+                }
             }
-            else
+            if(warp == 0)
             {
-                if(nconv1 || fail1) { atomicOr(&s_flags[fi][lane], (nconv1 ? 1u : 0u) | (fail1 ? 2u : 0u)); }
-                __syncthreads();
-                uint32_t const f = s_flags[fi][lane];
-                fi = fi == 2 ? 0 : fi + 1;
-                ++it;
-                if(!done)
+#pragma unroll
+                for(int j = 0; j < J; ++j)
                 {
-                    ++solves;
-                    if(f & 2u)
+                    if(counted[j])
                     {
-                        status = PE_ST_SINGULAR;
-                        ok = false;
-                        done = true;
+                        r.status[glane + 32 * j] = status[j];
+                        r.solves[glane + 32 * j] += solves[j];
                     }
-                    else if(!r.nonlinear || !(f & 1u)) { done = true; }
-                    else if(it >= r.max_iter)
-                    {
-                        status = PE_ST_NO_CONVERGENCE;
-                        ok = false;
-                        done = true;
-                    }
-                }
-                if(__syncthreads_and(done ? 1 : 0))
-                {
-                    if(r.wave != nullptr && ok && warp == 0)
-                    {
-                        for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + glane] = *at(__ldg(r.probes + p)); }
-                    }
-                    ++s;
-                    stage = 1;
                 }
             }
-        }
-        for(uint32_t e = warp; last_chunk && e < (uint32_t)r.n_io; e += n_warps)
-        {
-            pe_b200_io const io = r.io[e];
-            if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
-            if(counted) { r.wu[(int64_t)io.src * r.LSu + glane] = *at(io.slot_kind & 0xffffu); }
-        }
-        if(warp == 0 && counted)
-        {
-            r.status[glane] = status;
-            r.solves[glane] += solves;
-        }
-        if(r.sched == nullptr) { break; }
-        // publish the chunk: every thread's stores are visible device-wide before the group's counter moves
-        __threadfence();
-        __syncthreads();
-        if(tid == 0) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(r.sched + 1 + group), "r"(chunk + 1u) : "memory"); }
+            if(r.sched == nullptr) { break; }
+            // publish the chunk: every thread's stores are visible device-wide before the group's counter moves
+            __threadfence();
+            __syncthreads();
+            if(tid == 0) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(r.sched + 1 + group), "r"(chunk + 1u) : "memory"); }
         }
     }
 
@@ -902,15 +1031,16 @@ extern "C"
     {
         if(run == nullptr || run->n_lanes <= 0) { return 0; }
         int const I = run->I, J = run->J, S = run->S;
-        if(I < 1 || I > 32 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024)
+        if(I < 1 || I > 64 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
+           (run->wsg == nullptr && I > 32))
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
             return 1;
         }
         bool const hbm{run->wsg != nullptr};
-        if(hbm && (I != 32 || J != 1 || S > 32))
+        if(hbm && (I != 32 * J || S > 32))
         {
-            snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: the HBM form needs I=32 J=1 S<=32 (S=%d I=%d J=%d)", S, I, J);
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: the HBM form needs I = 32 J and S <= 32 (S=%d I=%d J=%d)", S, I, J);
             return 1;
         }
         int const block = S * (I / J);
@@ -926,14 +1056,11 @@ extern "C"
                 cudaEventCreate(&e1);
                 cudaEventRecord(e0, (cudaStream_t)stream);
             }
-            void (*tk)(pe_b200_rrun) = block <= 256 ? pe_b200_tree_kernel<256, 4> : (block <= 512 ? pe_b200_tree_kernel<512, 2> : pe_b200_tree_kernel<1024, 1>);
-            if(char const* ev = getenv("PE_B200_TREE_VARIANT"))
+            void (*tk)(pe_b200_rrun) = nullptr;
+            if(J == 2) { tk = block <= 256 ? pe_b200_tree_kernel<2, 256, 4> : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2> : pe_b200_tree_kernel<2, 1024, 1>); }
+            else
             {
-                // tuning experiments: register budget / CTAs per SM
-                int const v = atoi(ev);
-                if(v == 3 && block <= 512) { tk = pe_b200_tree_kernel<512, 3>; }
-                if(v == 6 && block <= 256) { tk = pe_b200_tree_kernel<256, 6>; }
-                if(v == 2 && block <= 1024) { tk = pe_b200_tree_kernel<1024, 2>; }
+                tk = block <= 256 ? pe_b200_tree_kernel<1, 256, 4> : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2> : pe_b200_tree_kernel<1, 1024, 1>);
             }
             int tgrid = grid;
             if(run->sched != nullptr)

@@ -22,6 +22,7 @@ namespace pe_rinterp
         uint32_t C;    // streams (word columns) per warp
         uint32_t col;  // this thread's column
         uint32_t stream;  // this thread's stream: operand words are relative to it (row * S + ((column - stream) mod S))
+        uint32_t js{1};   // distance (in doubles) between the J instances of this thread: 1 (shared memory), 32 (HBM form)
     };
 
     // absolute slot of a stream-relative operand word (S is a power of two)
@@ -52,16 +53,19 @@ namespace pe_rinterp
 #if defined(__CUDA_ARCH__)
         if constexpr(J == 2)
         {
-            double2 const t = *reinterpret_cast<double2 const*>(p);
-            r.v[0] = t.x;
-            r.v[1] = t.y;
-            return r;
+            if(c.js == 1u)
+            {
+                double2 const t = *reinterpret_cast<double2 const*>(p);
+                r.v[0] = t.x;
+                r.v[1] = t.y;
+                return r;
+            }
         }
 #endif
         for(int j = 0; j < J; ++j)
         {
-            PE_TRACE_LD(p + j);
-            r.v[j] = p[j];
+            PE_TRACE_LD(p + j * c.js);
+            r.v[j] = p[j * c.js];
         }
         return r;
     }
@@ -85,7 +89,7 @@ namespace pe_rinterp
 #if defined(__CUDA_ARCH__)
         if constexpr(J == 2)
         {
-            if(en[0] && en[1])
+            if(c.js == 1u && en[0] && en[1])
             {
                 *reinterpret_cast<double2*>(p) = make_double2(x.v[0], x.v[1]);
                 return;
@@ -96,8 +100,8 @@ namespace pe_rinterp
         {
             if(en[j])
             {
-                PE_TRACE_ST(p + j);
-                p[j] = x.v[j];
+                PE_TRACE_ST(p + j * c.js);
+                p[j * c.js] = x.v[j];
             }
         }
     }

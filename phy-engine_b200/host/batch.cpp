@@ -179,8 +179,10 @@ namespace pe_b200
     {
         if(use_hbm(pr))
         {
-            I = 32;
-            J = 1;
+            // tree-streaming form: 32 J lanes per CTA, J of them per thread (0 = choose: two when every sub-tree warp of a
+            // full-width CTA still leaves the GPU enough independent groups)
+            J = res_J > 0 ? res_J : 1;
+            I = 32 * J;
             return pr.rS <= 32;
         }
         std::size_t const limit{pe_b200_resident_smem_limit()};
@@ -440,7 +442,7 @@ namespace pe_b200
         r.LSw = 0;
         if(use_hbm(pr))
         {
-            std::int64_t const LSw{round_up32(lanes)};
+            std::int64_t const LSw{static_cast<std::int64_t>((lanes + static_cast<std::size_t>(I) - 1) / static_cast<std::size_t>(I) * static_cast<std::size_t>(I))};
             if(!d_ws.ensure(static_cast<std::size_t>(pr.r_slots) * static_cast<std::size_t>(LSw) * sizeof(double))) { return dev_fail(error, "alloc HBM workspace"); }
             r.wsg = static_cast<double*>(d_ws.p);
             r.LSw = LSw;
@@ -452,7 +454,7 @@ namespace pe_b200
             {
                 int const cs{(n_steps + nc - 1) / nc};
                 nc = (n_steps + cs - 1) / cs;
-                std::size_t const groups{(lanes + 31) / 32};
+                std::size_t const groups{(lanes + static_cast<std::size_t>(I) - 1) / static_cast<std::size_t>(I)};
                 if(!d_sched.ensure((1 + groups) * sizeof(std::uint32_t))) { return dev_fail(error, "alloc scheduler"); }
                 if(pe_b200_dev_memset0(d_sched.p, (1 + groups) * sizeof(std::uint32_t), stream) != 0) { return dev_fail(error, "zero scheduler"); }
                 r.sched = static_cast<std::uint32_t*>(d_sched.p);

@@ -240,6 +240,9 @@ namespace
         bool const hbm = r.wsg != nullptr;
         uint64_t const sstride = hbm ? (uint64_t)r.LSw : (uint64_t)I;  // distance between consecutive slots
         std::vector<double> ws_local(hbm ? 0 : (size_t)r.n_slots * I);
+        // column of instance j of instance-group ig inside the CTA's block of I lanes: consecutive in shared memory, 32
+        // apart in the HBM form
+        auto col_of = [&](uint32_t ig, int j) -> uint32_t { return hbm ? (uint32_t)j * 32u + ig : ig * (uint32_t)J + (uint32_t)j; };
         struct tstate
         {
             bool real_lane[J], counted[J], ok[J], done[J];
@@ -257,7 +260,7 @@ namespace
             int32_t const s_begin = chunked ? chunk * r.chunk_steps : 0;
             int32_t const s_end = chunked ? std::min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
             // poison the workspace: a slot read before it is loaded or written shows up as NaN in the results
-            double* const wsb = hbm ? r.wsg + cta * 32 : ws_local.data();
+            double* const wsb = hbm ? r.wsg + cta * I : ws_local.data();
             if(!first_chunk) {}
             else if(hbm)
             {
@@ -272,16 +275,16 @@ namespace
             }
             emu_trace::g_map.clear();
             emu_trace::g_phase = 0;
-            uint32_t s_flags[3][32] = {};
+            uint32_t s_flags[3][64] = {};
             for(uint32_t tid = 0; tid < T; ++tid)
             {
                 uint32_t const ig = tid % IG;
-                int64_t const lane0 = cta * I + ig * J;
                 auto& st = ts[tid];
                 for(int j = 0; j < J; ++j)
                 {
-                    st.real_lane[j] = lane0 + j < r.n_lanes;
-                    st.status[j] = st.real_lane[j] ? r.status[lane0 + j] : (int32_t)PE_ST_SINGULAR;
+                    int64_t const lane_j = cta * I + col_of(ig, j);
+                    st.real_lane[j] = lane_j < r.n_lanes;
+                    st.status[j] = st.real_lane[j] ? r.status[lane_j] : (int32_t)PE_ST_SINGULAR;
                     st.counted[j] = st.real_lane[j] && st.status[j] == PE_ST_OK;
                     st.ok[j] = st.counted[j];
                     st.solves[j] = 0;
@@ -298,8 +301,9 @@ namespace
                 {
                     int64_t const lane = cta * I + i;
                     bool const real = lane < r.n_lanes;
-                    double v;
+                    double v = 0.0;
                     if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+                    else if(hbm && !real) { v = 0.0; }
                     else if(kind == PE_IO_U) { v = r.wu[(int64_t)io.src * r.LSu + lane]; }
                     else { v = r.wx[(int64_t)io.src * r.LSx + (real ? lane / r.ppi : 0)]; }
                     wsb[(uint64_t)(io.slot_kind & 0xffffu) * sstride + i] = v;
@@ -335,7 +339,8 @@ namespace
                                 uint32_t const tid = w * 32 + l;
                                 uint32_t const ig = tid % IG;
                                 rctx c;
-                                c.ws = wsb + ig * J;
+                                c.ws = wsb + col_of(ig, 0);
+                                c.js = hbm ? 32u : 1u;
                                 c.I = sstride;
                                 c.S = S;
                                 c.C = C;
@@ -424,13 +429,13 @@ namespace
                 int fi = 0;
                 for(;;)
                 {
-                    for(uint32_t i = 0; i < 32; ++i) { s_flags[fi][i] = 0; }
+                    for(uint32_t i = 0; i < 64; ++i) { s_flags[fi][i] = 0; }
                     clear_flags();
                     run_section(2, true, r.nonlinear != 0, nconv, fail);
                     for(uint32_t tid = 0; tid < T; ++tid)
                     {
                         uint32_t const ig = tid % IG;
-                        for(int j = 0; j < J; ++j) { s_flags[fi][ig * J + j] |= (nconv[tid][j] ? 1u : 0u) | (fail[tid][j] ? 2u : 0u); }
+                        for(int j = 0; j < J; ++j) { s_flags[fi][col_of(ig, j)] |= (nconv[tid][j] ? 1u : 0u) | (fail[tid][j] ? 2u : 0u); }
                     }
                     ++it;
                     bool all_done = true;
@@ -440,7 +445,7 @@ namespace
                         auto& st = ts[tid];
                         for(int j = 0; j < J; ++j)
                         {
-                            uint32_t const f = s_flags[fi][ig * J + j];
+                            uint32_t const f = s_flags[fi][col_of(ig, j)];
                             if(!st.done[j])
                             {
                                 ++st.solves[j];
@@ -471,8 +476,8 @@ namespace
                         for(int j = 0; j < J; ++j)
                         {
                             if(!st.ok[j]) { continue; }
-                            int64_t const lane = cta * I + ig * J + j;
-                            for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = wsb[(uint64_t)r.probes[p] * sstride + ig * J + j]; }
+                            int64_t const lane = cta * I + col_of(ig, j);
+                            for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = wsb[(uint64_t)r.probes[p] * sstride + col_of(ig, j)]; }
                         }
                     }
                 }
@@ -485,7 +490,7 @@ namespace
                 {
                     for(int j = 0; j < J; ++j)
                     {
-                        if(ts[ig].counted[j]) { r.wu[(int64_t)io.src * r.LSu + cta * I + ig * J + j] = wsb[(uint64_t)(io.slot_kind & 0xffffu) * sstride + ig * J + j]; }
+                        if(ts[ig].counted[j]) { r.wu[(int64_t)io.src * r.LSu + cta * I + col_of(ig, j)] = wsb[(uint64_t)(io.slot_kind & 0xffffu) * sstride + col_of(ig, j)]; }
                     }
                 }
             }
@@ -495,8 +500,8 @@ namespace
                 {
                     if(ts[ig].counted[j])
                     {
-                        r.status[cta * I + ig * J + j] = ts[ig].status[j];
-                        r.solves[cta * I + ig * J + j] += ts[ig].solves[j];
+                        r.status[cta * I + col_of(ig, j)] = ts[ig].status[j];
+                        r.solves[cta * I + col_of(ig, j)] += ts[ig].solves[j];
                     }
                 }
             }
@@ -512,7 +517,8 @@ extern "C"
     {
         if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
         int const I = rp->I, J = rp->J, S = rp->S;
-        if(I < 1 || I > 32 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024)
+        if(I < 1 || I > 64 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
+           (rp->wsg == nullptr && I > 32) || (rp->wsg != nullptr && I != 32 * J))
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
             return 1;

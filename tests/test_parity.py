@@ -31,6 +31,7 @@ def abi(request):
 #                   workspace, one warp per sub-tree) otherwise
 #   tree-hbm-s4     tree-streaming kernel forced, 4 sub-tree warps per 32 lanes
 #   tree-hbm-s16    ... 16 sub-tree warps
+#   tree-hbm-s8j2   ... 8 sub-tree warps, 64 lanes per CTA (two per thread)
 #   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp)
 #   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
 #   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
@@ -39,6 +40,7 @@ PATHS = {
     "auto": (0, 0, 0, 0, 0),
     "tree-hbm-s4": (4, 0, 0, 0, 2),
     "tree-hbm-s16": (16, 0, 0, 0, 2),
+    "tree-hbm-s8j2": (8, 0, 2, 0, 2),
     "resident-s8": (8, 0, 1, 0, 1),
     "resident-s32j2": (32, 2, 2, 0, 1),
     "flat": (-1, 0, 0, 0, 0),
@@ -140,7 +142,7 @@ def test_rc_ladder_batch_sweep(ref, abi, path, n_sections, n_inst):
         assert b.program_info(pe.MODE_TR)["warps"] == 4
     if path.startswith("tree-hbm"):
         ri = b.resident_info(pe.MODE_TR)
-        assert ri["resident"] == 1 and ri["hbm"] == 1 and (ri["last_I"], ri["last_J"]) == (32, 1)
+        assert ri["resident"] == 1 and ri["hbm"] == 1 and ri["last_I"] == 32 * ri["last_J"]
     if path.startswith("resident"):
         ri = b.resident_info(pe.MODE_TR)
         assert ri["resident"] == 1 and ri["last_S"] == ri["streams"] and ri["last_I"] > 0
