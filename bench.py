@@ -56,14 +56,16 @@ def workload(args, seed):
     return nl, info, items, nominal, rng
 
 
-def config_of(args):
+def config_of(args, ws_gb=None):
+    ws = f"{ws_gb:.1f}" if ws_gb is not None else "~1.5"
     return {
         "workload": f"RC ladder {args.sections} sections ({args.sections + 2} unknowns) transient, {args.time_steps} time steps, "
                     f"{args.instances} instances/GPU batched R_i,C_i parameter sweep (BASELINE.json configs[1])",
         "instances_per_gpu": args.instances,
         "time_steps": args.time_steps,
         "t_step": 1e-8,
-        "l2_policy": "working set (~0.6 GB per GPU) is larger than the 126 MB L2; no explicit flush",
+        "l2_policy": f"inputs larger than L2: the per-GPU working set ({ws} GB of per-instance parameters, state and LU workspace) is streamed every time step "
+                     "and is ~10x the 126 MB L2; no explicit flush",
     }
 
 
@@ -76,7 +78,7 @@ class ClockSampler:
         self.rows = []
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -134,9 +136,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_inst = args.cpu_sample or max(cores, 2 * cores)
+    # each step = a bounded sample of the workload (~3-5 s of CPU work on all host cores): 48 instances per core
+    n_inst = args.cpu_sample or 48 * cores
     for _ in range(args.warmup):
-        cpu_reference_run(args, max(1, cores // 2))
+        cpu_reference_run(args, max(1, 4 * cores))
     t_total, solves = 0.0, 0
     for _ in range(args.steps):
         r = cpu_reference_run(args, n_inst)
@@ -286,17 +289,27 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    rinfo = b.resident_info(pe.MODE_TR)
+    kernel_name = ("pe_b200_tree_kernel" if rinfo["hbm"] else "pe_b200_resident_kernel") if rinfo["resident"] else "pe_b200_solve_kernel"
     solves_per_launch = solves / max(launches, 1)
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r01_traffic.json), scaled to one launch
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("kernel", "").startswith(kernel_name) and (rinfo["last_S"], rinfo["last_J"]) == (32, 2):
+            traffic = tj["dram_bytes_per_solve"] * solves_per_launch
+            traffic_src = "profiles/r01_traffic.json: " + tj["capture"]
     avg_launch_ms = kernel_ms / max(launches, 1)
     achieved = bytes_per_solve * solves_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "pe_b200_resident_kernel" if rinfo["resident"] else "pe_b200_solve_kernel", "avg_launch_ms": avg_launch_ms, "bytes_per_solve": bytes_per_solve, "solves_per_launch": solves_per_launch,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": kernel_name, "avg_launch_ms": avg_launch_ms, "bytes_per_solve": bytes_per_solve, "solves_per_launch": solves_per_launch,
                 "peak_source": peak_src, "kernel_share_of_step": kernel_ms / ms if ms > 0 else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or 2 * cores
+        sample = args.cpu_sample or 192 * cores  # ~10-30 s of CPU work on all host cores
         try:
             r = cpu_reference_run(args, sample)
             cpu = {"value": r["solves"] / r["wall_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
@@ -307,7 +320,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args, 8e-9 * n_inst * (st["n_inst_slots"] + (rinfo["smem_slots"] if rinfo["hbm"] else st["n_lane_slots"]))),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "program": st, "resident": b.resident_info(pe.MODE_TR), "checksum": checksum,
         }

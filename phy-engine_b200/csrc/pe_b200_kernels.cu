@@ -145,7 +145,7 @@ namespace
             col = col_;
             lane = lane_;
             line = 0;
-            pos = 0;
+            pos = C_ == 1u ? 2u : 0u;  // one stream per warp: every line starts with two prefetch bitmaps
             w0 = __ldg(main + lane);
             w1 = __ldg(main + 32 + lane);
             w2 = __ldg(main + 64 + lane);
@@ -191,6 +191,7 @@ namespace
         }
         __device__ __forceinline__ void advance(uint32_t np)
         {
+            if(C == 1u && (np & 31u) == 0u) { np += 2u; }
             pos = np;
             while((pos >> 5) > line)
             {
@@ -409,29 +410,12 @@ namespace
     {
         uint32_t const* base;
         uint32_t lane, stream, sm;
-        uint32_t w, nw;      // this lane's raw word of the current / next line
-        uint32_t dlo, dhi;   // its two operand fields decoded: absolute slot | neg << 31
-        uint32_t line, off;  // current line, offset of the current op inside it
+        uint32_t w, nw, n2w;  // this lane's raw word of the current line and of the next two (in flight)
+        uint32_t dlo, dhi;    // the two operand fields of w decoded: absolute slot | neg << 31
+        uint32_t line, off;   // current line, offset of the current op inside it
         // generic-reader state (ops the fast path does not take)
         uint32_t cur, m;
-        // operand prefetch: when a line of words arrives, lane l asks L2 for the two workspace rows word l names (a
-        // row = this group's 32 lanes = two 128-byte lines), five or so ops before they are used
-        __device__ __forceinline__ void prefetch_operands(char const* group_base, uint32_t LS8, uint32_t n_slots) const
-        {
-            uint32_t const a = dlo & 0x7fffu, b = dhi & 0x7fffu;
-            if(a < n_slots)
-            {
-                char const* p = group_base + (uint64_t)a * LS8;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-            }
-            if(b < n_slots && b != a)
-            {
-                char const* p = group_base + (uint64_t)b * LS8;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-            }
-        }
+        bool fresh;  // a line was taken since the caller last looked (it then prefetches the operands of the next one)
 
         __device__ __forceinline__ uint32_t dec(uint32_t f) const
         {
@@ -443,6 +427,31 @@ namespace
             dlo = dec(w & 0xffffu);
             dhi = dec(w >> 16);
         }
+        // Every 32-word line starts with two bitmaps: bit l of word 0 (word 1) says that the low (high) half of word l
+        // names a workspace row that is cold by the time it is used.  Lane l asks L2 for the rows of its word of the
+        // NEXT line (a row = this group's 32 J lanes = 2 J 128-byte lines; complex values: the imaginary row too), a
+        // line's worth of ops before they are used.
+        template <int J>
+        __device__ __forceinline__ void prefetch_next(char const* group_base, uint32_t LS8, uint32_t S, bool cplx) const
+        {
+            uint32_t const bl = __shfl_sync(0xffffffffu, nw, 0), bh = __shfl_sync(0xffffffffu, nw, 1);
+            uint32_t const f[2] = {nw & 0xffffu, nw >> 16};
+            uint32_t const on[2] = {(bl >> lane) & 1u, (bh >> lane) & 1u};
+#pragma unroll
+            for(int h = 0; h < 2; ++h)
+            {
+                if(!on[h]) { continue; }
+                char const* p = group_base + (uint64_t)(dec(f[h]) & 0x7fffu) * LS8;
+#pragma unroll
+                for(int k = 0; k < 2 * J; ++k) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128 * k)); }
+                if(cplx)
+                {
+                    p += (uint64_t)S * LS8;
+#pragma unroll
+                    for(int k = 0; k < 2 * J; ++k) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128 * k)); }
+                }
+            }
+        }
         __device__ __forceinline__ void init(uint32_t const* b, uint32_t lane_, uint32_t stream_, uint32_t S)
         {
             base = b;
@@ -450,10 +459,12 @@ namespace
             stream = stream_;
             sm = S - 1u;
             line = 0;
-            off = 0;
+            off = 2;
             w = __ldg(base + lane);
             nw = __ldg(base + 32 + lane);
+            n2w = __ldg(base + 64 + lane);
             decode();
+            fresh = true;
         }
         __device__ __forceinline__ uint32_t raw(uint32_t k) const { return __shfl_sync(0xffffffffu, w, (int)(off + k)); }
         __device__ __forceinline__ uint32_t lo(uint32_t k) const { return __shfl_sync(0xffffffffu, dlo, (int)(off + k)); }
@@ -461,21 +472,17 @@ namespace
         __device__ __forceinline__ void next_line()
         {
             w = nw;
+            nw = n2w;
             ++line;
-            off = 0;
-            nw = __ldg(base + (line + 1u) * 32u + lane);
+            off = 2;
+            n2w = __ldg(base + (line + 2u) * 32u + lane);
             decode();
+            fresh = true;
         }
-        // returns true when a new line of words was taken (the caller then prefetches its operands)
-        __device__ __forceinline__ bool adv(uint32_t n)
+        __device__ __forceinline__ void adv(uint32_t n)
         {
             off += n;
-            if(off >= 32u)
-            {
-                next_line();
-                return true;
-            }
-            return false;
+            if(off >= 32u) { next_line(); }
         }
         // pe_rinterp reader interface (mask is always 0: one stream per warp has no per-column rows)
         __device__ __forceinline__ uint32_t head() const { return raw(0); }
@@ -486,14 +493,9 @@ namespace
             return 0u;
         }
         __device__ __forceinline__ uint32_t next() { return raw(cur++); }
-        __device__ __forceinline__ void close() { fresh = adv(2u + m) || fresh; }
-        __device__ __forceinline__ void bar() { fresh = adv(1u) || fresh; }
-        __device__ __forceinline__ void skip()
-        {
-            next_line();
-            fresh = true;
-        }
-        bool fresh;  // a line was taken through the generic interface since the caller last looked
+        __device__ __forceinline__ void close() { adv(2u + m); }
+        __device__ __forceinline__ void bar() { adv(1u); }
+        __device__ __forceinline__ void skip() { next_line(); }
     };
 
     // address of slot `slot` of this thread's lane in the HBM workspace (by-value functor: lives in registers)
@@ -746,17 +748,12 @@ namespace
                 {
                     line_reader rd;
                     rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
-                    rd.fresh = false;
                     for(;;)
                     {
                         if(rd.fresh)
                         {
                             rd.fresh = false;
-                            if(r.prefetch)
-                            {
-#pragma unroll
-                                for(int j = 0; j < J; ++j) { rd.prefetch_operands(at.wl - lane * 8u + 256u * j, at.LS8, (uint32_t)r.n_slots); }
-                            }
+                            if(r.prefetch) { rd.template prefetch_next<J>(at.wl - lane * 8u, at.LS8, S, r.cplx != 0); }
                         }
                         uint32_t const h = rd.raw(0);
                         uint32_t const op = h & 0xffu;
@@ -778,7 +775,7 @@ namespace
                                 case 10: tree_dot<J, 2, 2>(rd, at, r, en, check, nconv, fail); break;
                                 default: tree_dot<J, 2, 3>(rd, at, r, en, check, nconv, fail); break;
                             }
-                            rd.fresh = rd.adv(4u + na + nb);
+                            rd.adv(4u + na + nb);
                             continue;
                         }
                         if(op == PE_OP_CAP_STEP)
@@ -811,7 +808,7 @@ namespace
                                     pg[32 * j] = gv[j];
                                 }
                             }
-                            rd.fresh = rd.adv(8u);
+                            rd.adv(8u);
                             continue;
                         }
                         // everything else goes through the generic vector-op executor (pe_b200_rinterp.h)

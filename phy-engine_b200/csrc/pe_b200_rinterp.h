@@ -155,13 +155,32 @@ namespace pe_rinterp
             m >>= 1;
             return w;
         }
+        // one stream per warp (C == 1): every 32-word line of the main stream starts with two prefetch bitmaps
+        void normalize()
+        {
+            if(C == 1u && ((p - p0) & 31) == 0) { p += 2; }
+        }
+        void start()
+        {
+            p = p0;
+            normalize();
+        }
         void close()
         {
             p = p_next;
             q = q_next;
+            normalize();
         }
-        void bar() { p += 1; }
-        void skip() { p = p0 + (((p - p0) >> 5) + 1) * 32; }
+        void bar()
+        {
+            p += 1;
+            normalize();
+        }
+        void skip()
+        {
+            p = p0 + (((p - p0) >> 5) + 1) * 32;
+            normalize();
+        }
     };
 
     // Execute the vector op the reader stands on, for this thread.  en[j]: stores of instance j are enabled (the lane

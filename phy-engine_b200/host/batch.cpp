@@ -181,7 +181,7 @@ namespace pe_b200
         {
             // tree-streaming form: 32 J lanes per CTA, J of them per thread (0 = choose: two when every sub-tree warp of a
             // full-width CTA still leaves the GPU enough independent groups)
-            J = res_J > 0 ? res_J : 1;
+            J = res_J > 0 ? res_J : ((pr.rS >= 32 && n_inst * std::max<std::size_t>(last_points_hint, 1) >= 148u * 64u) ? 2 : 1);
             I = 32 * J;
             return pr.rS <= 32;
         }
@@ -499,6 +499,7 @@ namespace pe_b200
             set_last_error(error);
             return false;
         }
+        last_points_hint = 1;
         if(!ensure_compiled() || !upload_sweeps()) { return false; }
         auto const at{parent->at};
         int const n{cc->num.unknowns()};
@@ -582,6 +583,7 @@ namespace pe_b200
                 return dev_fail(error, "zero status");
             }
             last_points = P;
+            last_points_hint = P;
             return run_phase(prog_mode::AC, false, false, 1, false, 0.0, parent->tr.t_step, lanes, static_cast<int>(P));
         };
 

@@ -520,10 +520,10 @@ extern "C"
 
     int circuit_batch_set_chunks(void* b, int chunks)
     {
-        // bit 8 of `chunks` switches the L2 operand prefetch of the tree-streaming kernel off (tuning knob)
+        // bit 8 of `chunks` switches the L2 operand prefetch of the tree-streaming kernel on (tuning knob)
         if(b == nullptr || chunks < 0 || (chunks & 0xff) > 32) { return 1; }
         static_cast<batch*>(b)->res_chunks = chunks & 0xff;
-        static_cast<batch*>(b)->res_prefetch = (chunks & 0x100) ? 0 : ((chunks & 0x200) ? 2 : 1);  // bit 9: prefetch into L1
+        static_cast<batch*>(b)->res_prefetch = (chunks & 0x100) ? 1 : 0;  // bit 8: L2 operand prefetch on
         return 0;
     }
 

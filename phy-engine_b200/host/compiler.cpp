@@ -16,6 +16,7 @@
 // Numeric factorisation itself never runs here.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -1322,7 +1323,8 @@ namespace pe_b200
                                     std::vector<std::uint32_t> const& sim, std::vector<std::pair<std::uint32_t, std::uint32_t>> const& pp)
                 {
                     // a vector op holds at most 32 rows (one mask bit each): ctl, scale, packed sources, pairs
-                    std::size_t const max_src{cplx ? 12u : 16u}, max_pair{cplx ? 16u : 20u};
+                    // (two header words + ctl + scale + rows must fit the 30 program words of a line, see pack())
+                    std::size_t const max_src{cplx ? 12u : 16u}, max_pair{cplx ? 12u : 16u};
                     auto& dstv{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(phase)]};
                     std::size_t ri{}, ii{}, pi{};
                     bool first{true};
@@ -2497,6 +2499,33 @@ namespace pe_b200
             {
                 ww.clear();
                 sw.clear();
+                // C == 1 only: prefetch bitmaps of the current line, and which workspace rows are warm (touched by one
+                // of the last 64 ops of this stream: they sit in L1 / L2 anyway)
+                std::size_t line_bm{};
+                std::size_t op_counter{};
+                static std::size_t const pf_window{std::getenv("PE_B200_PF_WINDOW") ? static_cast<std::size_t>(std::atoi(std::getenv("PE_B200_PF_WINDOW"))) : 64u};
+                static bool const pf_dst{std::getenv("PE_B200_PF_DST") != nullptr};
+                std::map<std::uint32_t, std::size_t> last_touch;
+                auto line_start = [&]()
+                {
+                    if(ww.size() % 32 == 0)
+                    {
+                        line_bm = ww.size();
+                        ww.push_back(0u);
+                        ww.push_back(0u);
+                    }
+                };
+                // true when the row the operand field names is cold and not the zero pad
+                auto touch = [&](std::uint32_t field, bool write) -> bool
+                {
+                    std::uint32_t const rel{field & 0x7fffu};
+                    std::uint32_t const sm{static_cast<std::uint32_t>(rS - 1)};
+                    std::uint32_t const slot{(rel & ~sm) | ((rel + static_cast<std::uint32_t>(wv)) & sm)};
+                    auto it{last_touch.find(slot)};
+                    bool const cold{it == last_touch.end() || op_counter - it->second > pf_window};
+                    last_touch[slot] = op_counter;
+                    return cold && (!write || pf_dst) && rel != zero;
+                };
                 std::size_t n_ph{};
                 for(int c{}; c < C; ++c)
                 {
@@ -2623,12 +2652,44 @@ namespace pe_b200
                         }
                         if(C == 1)
                         {
-                            // one stream per warp: an op never straddles two 32-word lines of the main stream
+                            // one stream per warp: an op never straddles two 32-word lines of the main stream, and every
+                            // line starts with two bitmaps: which of its words name (in their low / high half) a
+                            // workspace row worth prefetching (pe_b200_program.h)
+                            line_start();
                             std::size_t const len{2 + rows.size()};
                             if(ww.size() % 32 + len > 32)
                             {
                                 ww.push_back(PE_OP_SKIP);
                                 while(ww.size() % 32 != 0) { ww.push_back(PE_OP_SKIP); }
+                                line_start();
+                            }
+                            ++op_counter;
+                            bool const dotlike{opc == PE_OP_DOT || opc == PE_OP_CDOT};
+                            rop const* const o{any};
+                            for(std::size_t r{}; r < rows.size(); ++r)
+                            {
+                                std::size_t const wi{(ww.size() + 2 + r) % 32};
+                                std::uint32_t const word{rows[r][0]};
+                                bool lo{}, hi{};
+                                if(dotlike)
+                                {
+                                    if(r == 0)
+                                    {
+                                        // the destination: written here, warm from now on
+                                        if(touch(word, true)) { ww[line_bm] |= 1u << wi; }
+                                    }
+                                    else if(r == 1) { lo = (o->flags & PE_F_SCALE) != 0u; }
+                                    else
+                                    {
+                                        lo = hi = true;
+                                    }
+                                }
+                                else
+                                {
+                                    lo = true;
+                                }
+                                if(lo && touch(word, false)) { ww[line_bm] |= 1u << wi; }
+                                if(hi && touch(word >> 16, false)) { ww[line_bm + 1] |= 1u << wi; }
                             }
                         }
                         ww.push_back(h0);
@@ -2639,8 +2700,10 @@ namespace pe_b200
                             dst.insert(dst.end(), rows[r].begin(), rows[r].end());
                         }
                     }
+                    if(C == 1) { line_start(); }
                     if(ph + 1 < n_ph) { ww.push_back(PE_OP_BAR); }
                 }
+                if(C == 1) { line_start(); }
                 ww.push_back(PE_OP_END);
                 max_warp_words = std::max(max_warp_words, ww.size() + sw.size());
                 auto key{std::make_pair(ww, sw)};

@@ -320,10 +320,10 @@ namespace
                 for(uint32_t w = 0; w < W; ++w)
                 {
                     rdw[w].p0 = r.words + r.sec_off[sec * W + w];
-                    rdw[w].p = rdw[w].p0;
                     rdw[w].q = r.words + r.sec_off[3 * W + sec * W + w];
                     rdw[w].C = C;
                     rdw[w].col = 0;
+                    rdw[w].start();
                 }
                 for(;;)
                 {
