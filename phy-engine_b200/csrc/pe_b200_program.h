@@ -162,16 +162,22 @@ extern "C"
     // slot k * S + s, so the threads of a warp touching "their" k-th value hit consecutive addresses (no bank
     // conflicts), and a complex value (re at q) has its imaginary part at q + S.
     //
-    //   header            op | a << 8 | b << 16 | c << 24
-    //   END / BAR         as above (BAR = __syncthreads of the CTA; every warp holds the same number per section)
-    //   DOT               a = rows of packed sources, b = rows of pairs, c = union of the streams' flags
-    //                     rows: [ctl] [scale, iff c & F_SCALE] [src x a] [pair x b]
-    //   CDOT              same, a = rows of packed re-sources; a second uniform header word holds the im-source rows
-    //                     rows: [ctl] [scale] [src_re x a] [src_im x a2] [pair x b]
-    //   value ops         a = number of operand rows (one operand per row, the same order as the v2 encoding)
-    //   ctl word          dst | ACTIVE << 15 | flags << 16      (value ops: operand 0 | ACTIVE << 16)
-    //   src word          s0 | neg0 << 15 | s1 << 16 | neg1 << 31      (padding: the -0.0 slot)
+    //   per warp and section, two word sequences: the MAIN stream holds, per vector op, [h0][mask][uniform rows ...]
+    //   (BAR / END / SKIP are single words); the SIDE stream holds the per-column rows (C words each) in consumption order
+    //   h0                op | a << 8 | a2 << 13 | b << 18 | flags << 24
+    //                     DOT / CDOT: a = rows of packed (re-)sources, a2 = rows of packed im-sources (CDOT), b = rows of
+    //                     pairs, flags = union of the streams' flags; value ops: a = number of operand rows
+    //   mask              bit r set = row r is per-column (side stream), clear = warp-uniform (one word, main stream)
+    //   DOT / CDOT rows   [ctl] [scale] [src_re x a] [src_im x a2] [pair x b]
+    //   value-op rows     one operand per row, the same order as the v2 encoding; row 0 carries VACTIVE
+    //   ctl word          dst | ACTIVE << 15 | flags << 16
+    //   src word          s0 | neg0 << 15 | s1 << 16 | neg1 << 31      (padding: the -0.0 operand)
     //   pair word         a | b << 16                                   (padding: (zero, zero))
+    //   every operand is STREAM-RELATIVE: row * S + ((column - stream) mod S); the executing stream adds its own index
+    //   back (mod S), which is what makes the rows of isomorphic sub-trees identical (warp-uniform)
+    //   one stream per warp (C = 1): every 32-word line of the main stream starts with two prefetch bitmaps (bit l of
+    //   word 0 / word 1: the low / high half of word l names a workspace row that is cold when used) and an op never
+    //   straddles two lines (PE_OP_SKIP pads)
 #define PE_R_SLOT(w) ((w) & 0x7fffu)
 #define PE_R_NEG 0x8000u
 #define PE_R_ACTIVE 0x8000u       /* in a DOT ctl word */
