@@ -532,10 +532,14 @@ namespace
             }
         }
 #pragma unroll
+        uint32_t gp[NB + 1];  // sign of the product of pair i (aliased entries carry a negate bit)
+#pragma unroll
         for(int i = 0; i < NB; ++i)
         {
-            double const* pa = at(rd.lo(4 + NA + i) & 0x7fffu);
-            double const* pb = at(rd.hi(4 + NA + i) & 0x7fffu);
+            uint32_t const ga = rd.lo(4 + NA + i), gb = rd.hi(4 + NA + i);
+            gp[i] = (ga ^ gb) & 0x80000000u;
+            double const* pa = at(ga & 0x7fffu);
+            double const* pb = at(gb & 0x7fffu);
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
@@ -578,7 +582,12 @@ namespace
         for(int i = 0; i < NB; ++i)
         {
 #pragma unroll
-            for(int j = 0; j < J; ++j) { acc[j] = fma(-av[i][j], bv[i][j], acc[j]); }
+            for(int j = 0; j < J; ++j)
+            {
+                // -(+/-a)(+/-b): flipping the sign bit of a is exact
+                double const a = __hiloint2double(__double2hiint(av[i][j]) ^ (int)(0x80000000u ^ gp[i]), __double2loint(av[i][j]));
+                acc[j] = fma(a, bv[i][j], acc[j]);
+            }
         }
         if(flags & PE_F_SCALE)
         {

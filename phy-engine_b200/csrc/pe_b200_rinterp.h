@@ -244,8 +244,8 @@ namespace pe_rinterp
                 {
                     if(r < nb)
                     {
-                        vd<J> const a = ldv<J>(c, abs_slot(c, pw[r]));
-                        vd<J> const b = ldv<J>(c, abs_slot(c, pw[r] >> 16));
+                        vd<J> const a = ldo<J>(c, pw[r] & 0xffffu);  // pair operands carry a sign (aliased entries)
+                        vd<J> const b = ldo<J>(c, pw[r] >> 16);
                         for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
                     }
                 }
@@ -268,8 +268,8 @@ namespace pe_rinterp
                 for(uint32_t r = 0; r < nb; ++r)
                 {
                     uint32_t const w = fetch();
-                    vd<J> const a = ldv<J>(c, abs_slot(c, w));
-                    vd<J> const b = ldv<J>(c, abs_slot(c, w >> 16));
+                    vd<J> const a = ldo<J>(c, w & 0xffffu);
+                    vd<J> const b = ldo<J>(c, w >> 16);
                     for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
                 }
                 if(idle) { return V_OK; }

@@ -1412,6 +1412,15 @@ namespace pe_b200
                     {
                         load_sources(rc.orig[static_cast<std::size_t>(e)]);
                         load_updates(e, rc.pairs[static_cast<std::size_t>(e)], st.node, false);
+                        // a U entry that is just (+/-) one stamped value, with no update and no contribution, is never
+                        // materialised: its consumers name the value itself (pair operands carry a sign bit)
+                        if(!cplx && pp.empty() && sim.empty() && sre.size() == 1 && !ehas[static_cast<std::size_t>(e)])
+                        {
+                            ekey[static_cast<std::size_t>(e)] = sre[0];  // internal word incl. its negate bit
+                            ehas[static_cast<std::size_t>(e)] = 1;
+                            ++pr.n_aliased;
+                            continue;
+                        }
                         emit_dot(sj, ph, key_e(e), 0, 0, sre, sim, pp);
                     }
                     for(int e: st.l_ent)

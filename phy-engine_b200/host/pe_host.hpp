@@ -197,6 +197,7 @@ namespace pe_b200
         // statistics for the roofline and the schedule
         std::size_t nnz_a{}, nnz_lu{}, n_fma{};
         std::size_t n_leaf_rows{}, n_top_rows{}, n_leaves{};
+        std::size_t n_aliased{};  // U entries that are a signed copy of one stamped value and were never materialised
         std::size_t max_warp_words{};  // longest iter stream (critical path in words)
     };
 

@@ -28,7 +28,7 @@ def program(b, mode):
     k = lib.circuit_batch_resident_secoff(b.h, mode, None)
     so = np.zeros(k, dtype=np.uint32)
     lib.circuit_batch_resident_secoff(b.h, mode, so.ctypes.data_as(ct.c_void_p))
-    return w, so.reshape(3, -1)
+    return w, so.reshape(6, -1)  # rows 0-2: main stream of prep / step / iter, rows 3-5: side stream
 
 
 def walk(w, off, C):
