@@ -64,6 +64,7 @@ namespace pe_b200
             val p[k_max_attr];
             val d[6];
             val s[6];
+            val bs[4][5];  // full bridge rectifier: state of its four internal junctions
         };
 
         class builder
@@ -190,6 +191,16 @@ namespace pe_b200
                             v.s[3] = inst_slot(0.0);
                             v.s[4] = inst_slot(0.0);
                             break;
+                        case E_BRIDGE:
+                            for(auto& q: v.bs)
+                            {
+                                q[0] = inst_slot(0.0);
+                                q[1] = inst_slot(k_nl_nominal);
+                                q[2] = inst_slot(0.0);
+                                q[3] = inst_slot(0.0);
+                                q[4] = inst_slot(0.0);
+                            }
+                            break;
                         case E_NPN:
                         case E_PNP:
                             v.s[0] = inst_slot(k_nl_nominal);
@@ -290,6 +301,21 @@ namespace pe_b200
                             }
                             // Ud_last re-seeded from the node voltages on every prepare() (PN_junction.h:351 via base.h:373)
                             emit(prep, PE_OP_SUB, {v.s[0].op, vx(e.pin_node[0]).op, vx(e.pin_node[1]).op});
+                            break;
+                        }
+                        case E_BRIDGE:
+                        {
+                            // the bridge exposes no "Temp" attribute, so the load_temperature fallback never touches its
+                            // junctions: they keep the PN defaults, Temp = 27 C, and their Ud_last is seeded once, at the
+                            // first prepare(), from the zero initial voltages (full_bridge_rectifier.h:28-52)
+                            auto const* pd{find_desc(E_PN)};
+                            auto const dn{pe_models::pn_prepare(pd->attr_default[0], pd->attr_default[2], pd->attr_default[8], pd->attr_default[1], pd->attr_default[4],
+                                                                pd->attr_default[5], pd->attr_default[6], pd->attr_default[7] != 0.0)};
+                            v.d[0] = constant(dn.is_eff);
+                            v.d[1] = constant(dn.isr_eff);
+                            v.d[2] = constant(dn.bv_eff);
+                            v.d[3] = constant(dn.ut);
+                            v.d[4] = constant(dn.uth);
                             break;
                         }
                         case E_NPN:
@@ -604,6 +630,36 @@ namespace pe_b200
                                 G4(ps, n0, n1, v.s[4]);
                                 Z_add(ps, n0, v.s[3], true);
                                 Z_add(ps, n1, v.s[3], false);
+                            }
+                        }
+                        break;
+                    }
+                    case E_BRIDGE:
+                    {
+                        // pins A, B, +, -; D1: A->+, D2: B->+, D3: - -> A, D4: - -> B (full_bridge_rectifier.h:28-90).
+                        // No iterate_tr_define: TR stamps like DC, the junction history is still stepped (:80-90).
+                        auto const* pd{find_desc(E_PN)};
+                        val const N{constant(pd->attr_default[1])}, Nr{constant(pd->attr_default[3])}, bvs{constant(pd->attr_default[7])}, tt{constant(pd->attr_default[9])};
+                        int const pa[4]{0, 1, 3, 3}, pk[4]{2, 2, 0, 1};
+                        for(int q{}; q < 4; ++q)
+                        {
+                            auto& bs{v.bs[q]};
+                            int const na{nidx(e.pin_node[pa[q]])}, nk{nidx(e.pin_node[pk[q]])};
+                            if(mode == prog_mode::AC)
+                            {
+                                G4(ps, na, nk, bs[1]);
+                                continue;
+                            }
+                            emit(ps.head,
+                                 PE_OP_PN_EVAL,
+                                 {bs[0].op, bs[1].op, bs[2].op, vx(e.pin_node[pa[q]]).op, vx(e.pin_node[pk[q]]).op, v.d[0].op, v.d[1].op, v.d[2].op, v.d[3].op, v.d[4].op, N.op,
+                                  Nr.op, bvs.op});
+                            G4(ps, na, nk, bs[1]);
+                            Z_add(ps, na, bs[2], true);
+                            Z_add(ps, nk, bs[2], false);
+                            if(mode == prog_mode::TR)
+                            {
+                                emit(ps.step, PE_OP_PN_STEP, {bs[0].op, bs[3].op, bs[4].op, vx(e.pin_node[pa[q]]).op, vx(e.pin_node[pk[q]]).op, bs[1].op, tt.op, dt_val().op});
                             }
                         }
                         break;

@@ -39,6 +39,8 @@ namespace pe_b200
             {E_PNP, "PNP BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},
             {E_NMOS, "NMOSFET", 3, 0, 3, {"Kp", "lambda", "Vth"}, {1e-3, 0.0, 1.0}, 3, true},
             {E_PMOS, "PMOSFET", 3, 0, 3, {"Kp", "lambda", "Vth"}, {1e-3, 0.0, 1.0}, 3, true},
+            // four default PN junctions D1: A->+, D2: B->+, D3: - -> A, D4: - -> B; no attributes (full_bridge_rectifier.h:10-24)
+            {E_BRIDGE, "Full Bridge Rectifier", 4, 0, 0, {}, {}, 0, true},
         };
 
         bool ieq(char a, char b) noexcept { return std::tolower(static_cast<unsigned char>(a)) == std::tolower(static_cast<unsigned char>(b)); }

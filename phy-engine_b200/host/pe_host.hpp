@@ -39,6 +39,7 @@ namespace pe_b200
         E_PNP = 51,
         E_NMOS = 52,
         E_PMOS = 53,
+        E_BRIDGE = 54,
     };
 
     // analyze_type (circuits/analyze.h)

@@ -188,3 +188,21 @@ def random_links(n_nodes: int = 1000, n_links: int = 10, seed: int = 1, r: float
 
 def sweep_values(rng: np.random.Generator, nominal: float, n_inst: int, lo: float = 0.8, hi: float = 1.2) -> np.ndarray:
     return nominal * rng.uniform(lo, hi, size=n_inst)
+
+
+def bridge_rectifier(v: float = 5.0, r_load: float = 1e3, r_src: float = 10.0):
+    """Full bridge rectifier (element 54 = four default PN junctions) between a source with series resistance and a
+    resistive load (model/models/non-linear/full_bridge_rectifier.h)."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, v)
+    rs = nl.add(pe.R, r_src)
+    br = nl.add(pe.BRIDGE)
+    rl = nl.add(pe.R, r_load)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, rs, 0)
+    nl.wire(rs, 1, br, 0)   # A
+    nl.wire(br, 1, g, 0)    # B
+    nl.wire(br, 2, rl, 0)   # +
+    nl.wire(br, 3, rl, 1)   # -
+    return nl, {"V": src, "Rs": rs, "B": br, "R": rl}

@@ -20,6 +20,8 @@ CASES = {
     "rlc_ladder_ac_16": {"at": pe.AC, "n_inst": 3},
     # nonlinear transient with the diffusion capacitance companion
     "diode_tr_tt": {"at": pe.TR, "n_inst": 9},
+    # full bridge rectifier (element 54)
+    "bridge_rectifier_op": {"at": pe.OP, "n_inst": 24},
 }
 
 
@@ -65,4 +67,8 @@ def build(name):
         nl, info = wl.diode_resistor(v=2.0)
         rng = np.random.default_rng(9)
         return nl, [(info["D"][0], "tt", rng.uniform(1e-9, 1e-8, n)), (info["R"], "r", wl.sweep_values(rng, 1e3, n))], {"t_step": 1e-9, "t_stop": 2e-8}
+    if name == "bridge_rectifier_op":
+        nl, info = wl.bridge_rectifier()
+        rng = np.random.default_rng(17)
+        return nl, [(info["V"], "V", rng.uniform(-8.0, 8.0, n)), (info["R"], "r", rng.uniform(200.0, 5000.0, n))], {}
     raise KeyError(name)

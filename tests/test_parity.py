@@ -331,3 +331,26 @@ def test_emulator_saw_no_races_or_unbalanced_barriers():
 
     assert emuapi.races() == 0
     assert emuapi.unbalanced() == 0
+
+
+def test_full_bridge_rectifier_op_and_tr(ref, abi):
+    # element 54 = 4 default PN junctions bound to A, B, +, - (full_bridge_rectifier.h:28-90)
+    nl, info = wl.bridge_rectifier()
+    n_inst = 40
+    rng = np.random.default_rng(17)
+    over = [(info["V"], "V", rng.uniform(-8.0, 8.0, n_inst)), (info["R"], "r", rng.uniform(200.0, 5000.0, n_inst))]
+    for at, kw in ((pe.OP, {}), (pe.TR, {"t_step": 1e-6, "t_stop": 5e-6})):
+        want = refapi.run_batch(nl, at, n_inst, over, **kw)
+        c = pe.Circuit(nl, abi)
+        c.set_analyze_type(at)
+        if kw:
+            c.set_tr(kw["t_step"], kw["t_stop"])
+        b = c.batch(n_inst)
+        for e, name, v in over:
+            b.set_param(e, name, v)
+        ok = b.analyze()
+        assert ok == bool((want["ok"] == 1).all())
+        good = want["ok"] == 1
+        assert good.sum() >= n_inst // 2
+        assert (b.newton_iters() == want["solves"]).all()
+        assert_close(b.solution()[good], want["x"].real[good], "bridge rectifier")
