@@ -521,9 +521,12 @@ extern "C"
     int circuit_batch_set_chunks(void* b, int chunks)
     {
         // bit 8 of `chunks` switches the L2 operand prefetch of the tree-streaming kernel on (tuning knob)
-        if(b == nullptr || chunks < 0 || (chunks & 0xff) > 32) { return 1; }
+        if(b == nullptr || chunks < 0 || (chunks & 0xff) > 32) { return 1; }  // tuning bits above bit 7, see below
         static_cast<batch*>(b)->res_chunks = chunks & 0xff;
-        static_cast<batch*>(b)->res_prefetch = (chunks & 0x100) ? 1 : 0;  // bit 8: L2 operand prefetch on
+        // bit 8: line-ahead L2 operand prefetch
+        // bit 9: ... two lines ahead instead of one
+        // bit 11: switch the (default) L1 re-fetch off
+        static_cast<batch*>(b)->res_prefetch = ((chunks & 0x100) ? 1 : 0) | ((chunks & 0x200) ? 2 : 0) | ((chunks & 0x800) ? 0 : 4);
         return 0;
     }
 

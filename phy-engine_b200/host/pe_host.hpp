@@ -283,7 +283,9 @@ namespace pe_b200
         int res_ws{0};  // where the tree-scheduled program keeps its workspace: 0 = choose, 1 = shared memory, 2 = HBM
         device_buf d_ws;  // HBM workspace of the tree-streaming form [slots][lanes]
         device_buf d_sched;  // work-item counter + per-group chunk counters of the tree-streaming form
-        int res_prefetch{0};  // tree-streaming form: L2 operand prefetch (off by default: measured neutral to harmful at J = 2)
+        // tree-streaming form, bit set: 1 = line-ahead L2 operand prefetch (measured neutral at J = 2: off), 2 = ... two lines
+        // ahead, 4 = L1 re-fetch of every DOT result right after its store (+3 %: on)
+        int res_prefetch{4};
         std::size_t last_points_hint{1};  // frequency points per instance of the AC sweep being launched (lane count = n_inst * points)
         int res_chunks{0};   // chunks the time loop is cut into for dynamic scheduling: 0 = choose, 1 = static (one CTA per group)
         bool use_hbm(program const& pr) const;
