@@ -630,6 +630,167 @@ namespace
         }
     }
 
+    // complex DOT (AC sweeps) with at most 2 rows of packed re-sources, 2 of im-sources and 3 pairs: a complex value has
+    // its real part in row q and its imaginary part in row q + S; every operand load is issued before the first use
+    template <int J>
+    __device__ __forceinline__ void tree_cdot(line_reader const& rd, lane_ws const& at, uint32_t S, uint32_t nre, uint32_t nim, uint32_t nb, bool const (&en)[J],
+                                              bool (&fail)[J])
+    {
+        // words of the op: [h][mask][ctl][scale][src_re x nre][src_im x nim][pair x nb]
+        uint32_t const flags = rd.raw(2) >> 16;
+        uint32_t const dst = rd.lo(2) & 0x7fffu;
+        uint64_t const im_off = (uint64_t)S * at.LS8;  // bytes between the re and the im row of a complex value
+        auto im_of = [&](double const* p) -> double const* { return reinterpret_cast<double const*>(reinterpret_cast<char const*>(p) + im_off); };
+        uint32_t gre[4], gim[4];
+        double sre[4][J], sim[4][J], ar[3][J], ai[3][J], br[3][J], bi[3][J], scr[J], sci[J];
+#pragma unroll
+        for(int i = 0; i < 2; ++i)
+        {
+            if((uint32_t)i < nre)
+            {
+                gre[2 * i] = rd.lo(4 + i);
+                gre[2 * i + 1] = rd.hi(4 + i);
+                double const* p0 = at(gre[2 * i] & 0x7fffu);
+                double const* p1 = at(gre[2 * i + 1] & 0x7fffu);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    sre[2 * i][j] = p0[32 * j];
+                    sre[2 * i + 1][j] = p1[32 * j];
+                }
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 2; ++i)
+        {
+            if((uint32_t)i < nim)
+            {
+                gim[2 * i] = rd.lo(4 + nre + i);
+                gim[2 * i + 1] = rd.hi(4 + nre + i);
+                double const* p0 = at(gim[2 * i] & 0x7fffu);
+                double const* p1 = at(gim[2 * i + 1] & 0x7fffu);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    sim[2 * i][j] = p0[32 * j];
+                    sim[2 * i + 1][j] = p1[32 * j];
+                }
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 3; ++i)
+        {
+            if((uint32_t)i < nb)
+            {
+                double const* pa = at(rd.lo(4 + nre + nim + i) & 0x7fffu);
+                double const* pb = at(rd.hi(4 + nre + nim + i) & 0x7fffu);
+                double const* pai = im_of(pa);
+                double const* pbi = im_of(pb);
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    ar[i][j] = pa[32 * j];
+                    ai[i][j] = pai[32 * j];
+                    br[i][j] = pb[32 * j];
+                    bi[i][j] = pbi[32 * j];
+                }
+            }
+        }
+        if(flags & PE_F_SCALE)
+        {
+            double const* ps = at(rd.lo(3) & 0x7fffu);
+            double const* psi = im_of(ps);
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                scr[j] = ps[32 * j];
+                sci[j] = psi[32 * j];
+            }
+        }
+        double are[J], aim[J];
+#pragma unroll
+        for(int j = 0; j < J; ++j) { are[j] = aim[j] = 0.0; }
+        // the same operation order as pe_rinterp::rvop's CDOT (the emulator and the generic path): sources pairwise, then
+        // the four fused multiply-adds of every complex product
+#pragma unroll
+        for(int i = 0; i < 2; ++i)
+        {
+            if((uint32_t)i < nre)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    double const s0 = (gre[2 * i] >> 31) ? -sre[2 * i][j] : sre[2 * i][j];
+                    double const s1 = (gre[2 * i + 1] >> 31) ? -sre[2 * i + 1][j] : sre[2 * i + 1][j];
+                    are[j] = PE_ADD(PE_ADD(are[j], s0), s1);
+                }
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 2; ++i)
+        {
+            if((uint32_t)i < nim)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    double const s0 = (gim[2 * i] >> 31) ? -sim[2 * i][j] : sim[2 * i][j];
+                    double const s1 = (gim[2 * i + 1] >> 31) ? -sim[2 * i + 1][j] : sim[2 * i + 1][j];
+                    aim[j] = PE_ADD(PE_ADD(aim[j], s0), s1);
+                }
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 3; ++i)
+        {
+            if((uint32_t)i < nb)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    are[j] = fma(-ar[i][j], br[i][j], are[j]);
+                    are[j] = fma(ai[i][j], bi[i][j], are[j]);
+                    aim[j] = fma(-ar[i][j], bi[i][j], aim[j]);
+                    aim[j] = fma(-ai[i][j], br[i][j], aim[j]);
+                }
+            }
+        }
+        if(flags & PE_F_SCALE)
+        {
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                double const nr = are[j] * scr[j] - aim[j] * sci[j];
+                double const ni = are[j] * sci[j] + aim[j] * scr[j];
+                are[j] = nr;
+                aim[j] = ni;
+            }
+        }
+        if(flags & PE_F_RECIP)
+        {
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                double const mm = are[j] * are[j] + aim[j] * aim[j];
+                if(!(mm > 0.0) || !isfinite(mm)) { fail[j] = true; }
+                double const sc = 1.0 / mm;
+                are[j] = are[j] * sc;
+                aim[j] = -aim[j] * sc;
+            }
+        }
+        double* const pd = at(dst);
+        double* const pdi = const_cast<double*>(im_of(pd));
+#pragma unroll
+        for(int j = 0; j < J; ++j)
+        {
+            if(en[j])
+            {
+                pd[32 * j] = are[j];
+                pdi[32 * j] = aim[j];
+            }
+        }
+    }
+
     // CTA = S warps x (32 x J) lanes: thread (warp s, lane l) runs stream s for lanes l, l + 32, ... of the group
     template <int J, int MAXT, int MINB>
     __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
@@ -794,6 +955,16 @@ namespace
                             }
                             rd.adv(4u + na + nb);
                             continue;
+                        }
+                        if(op == PE_OP_CDOT)
+                        {
+                            uint32_t const nim = (h >> 13) & 0x1fu;
+                            if(na <= 2u && nim <= 2u && nb <= 3u)
+                            {
+                                tree_cdot<J>(rd, at, S, na, nim, nb, en, fail);
+                                rd.adv(4u + na + nim + nb);
+                                continue;
+                            }
                         }
                         if(op == PE_OP_CAP_STEP)
                         {
