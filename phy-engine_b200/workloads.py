@@ -206,3 +206,84 @@ def bridge_rectifier(v: float = 5.0, r_load: float = 1e3, r_src: float = 10.0):
     nl.wire(br, 2, rl, 0)   # +
     nl.wire(br, 3, rl, 1)   # -
     return nl, {"V": src, "Rs": rs, "B": br, "R": rl}
+
+
+def linear_zoo(vac: bool = False):
+    """One netlist with every in-scope linear element: R, C, L, VDC / VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, op-amp and a
+    closed + an open single-pole switch (stamps of SURVEY.md Appendix A).  Every node has a DC path to ground."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, 5.0, 1e5, 30.0) if vac else nl.add(pe.VDC, 5.0)
+    r1, r2 = nl.add(pe.R, 1e3), nl.add(pe.R, 2e3)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, r1, 0)
+    nl.wire(r1, 1, r2, 0)  # n2
+    nl.wire(r2, 1, g, 0)
+    # VCCS: pins S, T, P, Q; controlled by V(n2)
+    gm = nl.add(pe.VCCS, 1e-3)
+    r3 = nl.add(pe.R, 1e3)
+    nl.wire(gm, 2, r1, 1)
+    nl.wire(gm, 3, g, 0)
+    nl.wire(gm, 0, r3, 0)  # n3
+    nl.wire(gm, 1, g, 0)
+    nl.wire(r3, 1, g, 0)
+    # VCVS (x2 of n2) driving R4 - sense branch of the CCCS - R5
+    ev = nl.add(pe.VCVS, 2.0)
+    r4, r5 = nl.add(pe.R, 1e3), nl.add(pe.R, 1e3)
+    nl.wire(ev, 2, r1, 1)
+    nl.wire(ev, 3, g, 0)
+    nl.wire(ev, 0, r4, 0)  # n4
+    nl.wire(ev, 1, g, 0)
+    fc = nl.add(pe.CCCS, 3.0)  # pins S, T (output), P, Q (sense)
+    nl.wire(r4, 1, fc, 2)  # n5
+    nl.wire(fc, 3, r5, 0)  # n6
+    nl.wire(r5, 1, g, 0)
+    r6 = nl.add(pe.R, 500.0)
+    nl.wire(fc, 0, r6, 0)  # n7
+    nl.wire(fc, 1, g, 0)
+    nl.wire(r6, 1, g, 0)
+    # CCVS sensing the current through R7 (fed from n3)
+    hv = nl.add(pe.CCVS, 250.0)  # pins S, T (output), P, Q (sense)
+    r7, r8 = nl.add(pe.R, 2e3), nl.add(pe.R, 1e3)
+    nl.wire(r7, 0, r3, 0)
+    nl.wire(r7, 1, hv, 2)  # n8
+    nl.wire(hv, 3, g, 0)
+    nl.wire(hv, 0, r8, 0)  # n9
+    nl.wire(hv, 1, g, 0)
+    nl.wire(r8, 1, g, 0)
+    # inverting op-amp stage on n2: pins +, -, OUT+, OUT-
+    oa = nl.add(pe.OPAMP, 1e5)
+    ri, rf = nl.add(pe.R, 1e3), nl.add(pe.R, 4.7e3)
+    nl.wire(ri, 0, r1, 1)
+    nl.wire(ri, 1, oa, 1)  # inverting input
+    nl.wire(oa, 0, g, 0)
+    nl.wire(oa, 3, g, 0)
+    nl.wire(rf, 0, oa, 1)
+    nl.wire(rf, 1, oa, 2)  # output
+    rl = nl.add(pe.R, 1e4)
+    nl.wire(rl, 0, oa, 2)
+    nl.wire(rl, 1, g, 0)
+    # switches: closed one in series with R9 from n1, open one bridging R9
+    s1, s2 = nl.add(pe.SWITCH, 1.0), nl.add(pe.SWITCH, 0.0)
+    r9, r10 = nl.add(pe.R, 1e3), nl.add(pe.R, 1e3)
+    nl.wire(s1, 0, src, 0)
+    nl.wire(s1, 1, r9, 0)
+    nl.wire(r9, 1, r10, 0)
+    nl.wire(r10, 1, g, 0)
+    nl.wire(s2, 0, r9, 0)
+    nl.wire(s2, 1, r9, 1)
+    # RLC tail with current sources
+    l1, c1, r11 = nl.add(pe.L, 1e-3), nl.add(pe.C, 1e-7), nl.add(pe.R, 100.0)
+    idc = nl.add(pe.IDC, 1e-3)
+    iac = nl.add(pe.IAC, 2e-3, 1e5, -45.0)
+    nl.wire(l1, 0, r10, 0)
+    nl.wire(l1, 1, r11, 0)  # n_l
+    nl.wire(r11, 1, g, 0)
+    nl.wire(c1, 0, l1, 1)
+    nl.wire(c1, 1, g, 0)
+    nl.wire(idc, 0, g, 0)
+    nl.wire(idc, 1, l1, 1)
+    nl.wire(iac, 0, g, 0)
+    nl.wire(iac, 1, l1, 1)
+    return nl, {"src": src, "R": [r1, r2, r3, r4, r5, r6, r7, r8, ri, rf, rl, r9, r10, r11], "G": gm, "E": ev, "F": fc, "H": hv, "OA": oa, "L": l1, "C": c1, "IDC": idc,
+                "IAC": iac}

@@ -354,3 +354,33 @@ def test_full_bridge_rectifier_op_and_tr(ref, abi):
         assert good.sum() >= n_inst // 2
         assert (b.newton_iters() == want["solves"]).all()
         assert_close(b.solution()[good], want["x"].real[good], "bridge rectifier")
+
+
+@pytest.mark.parametrize("at", ["DC", "TR", "TROP", "AC"])
+def test_linear_zoo_every_linear_element(ref, abi, at):
+    # R, C, L, VDC/VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, op-amp, switch in one netlist
+    n_inst = 19
+    nl, info = wl.linear_zoo(vac=at in ("TR", "TROP", "AC"))
+    rng = np.random.default_rng(23)
+    over = [(info["R"][0], "r", rng.uniform(500.0, 2000.0, n_inst)), (info["G"], "G", rng.uniform(5e-4, 2e-3, n_inst)), (info["E"], "Mu", rng.uniform(1.0, 3.0, n_inst)),
+            (info["F"], "alpha", rng.uniform(1.0, 5.0, n_inst)), (info["H"], "r", rng.uniform(100.0, 400.0, n_inst)), (info["L"], "L", rng.uniform(5e-4, 2e-3, n_inst)),
+            (info["C"], "C", rng.uniform(5e-8, 2e-7, n_inst)), (info["IDC"], "I", rng.uniform(5e-4, 2e-3, n_inst))]
+    code = {"DC": pe.DC, "TR": pe.TR, "TROP": pe.TROP, "AC": pe.AC}[at]
+    kw = {"t_step": 2e-7, "t_stop": 4e-6} if at in ("TR", "TROP") else ({"ac": (pe.SWEEP_LOG, 1e4, 1e7, 13)} if at == "AC" else {})
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at in ("TR", "TROP"):
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if at == "AC":
+        b.set_ac_sweep(*kw["ac"])
+    assert b.analyze(), c.abi.last_error()
+    if at == "AC":
+        assert_close(b.ac_solution(), want["x"], "linear zoo AC")
+    else:
+        assert_close(b.solution(), want["x"].real, "linear zoo " + at)
+        assert b.total_solves == int(want["solves"].sum())
