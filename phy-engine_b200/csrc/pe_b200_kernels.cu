@@ -1,13 +1,17 @@
-// pe_b200_kernels.cu — the sm_100a solve kernel of the batched MNA hot path + the POD device seam.
+// pe_b200_kernels.cu — the sm_100a kernels of the batched MNA hot path + the POD device seam.
 //
-// CTA = 32 lanes x G warps.  Thread (g, l) interprets warp stream g of the batch program on lane l; its data accesses
-// hit lane-interleaved HBM arrays w[slot][lane] (32 consecutive doubles per warp request) and program words are
-// warp-uniform (no divergence on opcodes).  The G warps of a CTA work on disjoint sub-trees of the elimination tree
-// of the SAME 32 circuits and meet at CTA barriers (PE_OP_BAR) around the separator rows, which is what gives a
-// 10k-instance batch enough resident warps to hide HBM latency.  One launch runs a whole analysis
-// phase per lane: [prep] -> for each time step { [step]; Newton loop { eval + assemble + LU + substitution with the
-// convergence test fused into the back substitution } }.  Replaces, per lane, the reference's circult::solve /
-// solve_once / update_tr_step (circuit.h:363-374, 892-1527) and Eigen::SparseLU compute + solve.
+//   pe_b200_tree_kernel      tree-streaming kernel, the hot path of large circuits (configs B, D): the tree-scheduled
+//                            program (pe_b200_program.h, "RESIDENT programs") with its workspace ws[row][lane] in HBM,
+//                            CTA = S sub-tree warps x 32 J lanes, warp-cooperative word decode, persistent CTAs with
+//                            dynamic (group, chunk) scheduling of the time loop.
+//   pe_b200_resident_kernel  the same programs with the workspace in shared memory for the whole launch (small
+//                            circuits, configs C, E: no HBM traffic inside the Newton / time loops).
+//   pe_b200_solve_kernel     first-generation flat streaming interpreter (fallback for programs of > 32 768 rows).
+//
+// One launch runs a whole analysis phase per lane: [prep] -> for each time step { [step]; Newton loop { device
+// evaluation + assembly + LU + substitution with the convergence test fused into the back substitution } }.  Replaces,
+// per lane, the reference's circult::solve / solve_once / update_tr_step (circuit.h:363-374, 892-1527) and
+// Eigen::SparseLU compute + solve.
 //
 // This TU includes no reference header (nvcc ICEs on fast_io; SURVEY.md probe table).
 #include <cuda_runtime.h>
@@ -206,15 +210,13 @@ namespace
         __device__ __forceinline__ void skip() { advance(((pos >> 5) + 1u) << 5); }
     };
 
-    template <int J, int MAXT, bool HBM>
-    __global__ void __launch_bounds__(MAXT, HBM ? 2 : 1) pe_b200_resident_kernel(pe_b200_rrun const r)
+    template <int J, int MAXT>
+    __global__ void __launch_bounds__(MAXT, 1) pe_b200_resident_kernel(pe_b200_rrun const r)
     {
-        extern __shared__ __align__(16) double ws_shared[];
+        extern __shared__ __align__(16) double ws[];
         __shared__ uint32_t s_flags[3][32];
 
         using namespace pe_rinterp;
-        // HBM form: the CTA's 32 lanes own columns [32 * blockIdx.x, +32) of the global workspace ws[slot][LSw]
-        double* const ws = HBM ? r.wsg + (int64_t)blockIdx.x * 32 : ws_shared;
         uint32_t const I = (uint32_t)r.I, IG = I / J, S = (uint32_t)r.S;
         uint32_t const tid = threadIdx.x;
         uint32_t const ig = tid % IG, stream = tid / IG;
@@ -223,7 +225,7 @@ namespace
 
         rctx c;
         c.ws = ws + ig * J;
-        c.I = HBM ? (uint64_t)r.LSw : (uint64_t)I;
+        c.I = (uint64_t)I;
         c.S = S;
         c.C = 32u / IG;
         c.col = (tid & 31u) / IG;
@@ -1270,8 +1272,8 @@ extern "C"
             g_launches.fetch_add(1);
             return chk(cudaGetLastError(), "pe_b200_tree_kernel launch");
         }
-        auto kern = block <= 512 ? (J == 2 ? pe_b200_resident_kernel<2, 512, false> : pe_b200_resident_kernel<1, 512, false>)
-                                 : (J == 2 ? pe_b200_resident_kernel<2, 1024, false> : pe_b200_resident_kernel<1, 1024, false>);
+        auto kern = block <= 512 ? (J == 2 ? pe_b200_resident_kernel<2, 512> : pe_b200_resident_kernel<1, 512>)
+                                 : (J == 2 ? pe_b200_resident_kernel<2, 1024> : pe_b200_resident_kernel<1, 1024>);
         if(chk(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)") != 0) { return 1; }
         cudaEvent_t e0{}, e1{};
         if(g_timing)
