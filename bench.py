@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--resident", default="0,0,0", help="streams,instances_per_cta,instances_per_thread of the resident kernel (0 = automatic, streams -1 = HBM-streaming kernel)")
     ap.add_argument("--workspace", type=int, default=0, help="0 = automatic, 1 = shared memory (resident kernel), 2 = HBM (tree-streaming kernel)")
     ap.add_argument("--chunks", type=int, default=0, help="tree-streaming kernel: chunks of the time loop (0 = automatic, 1 = static scheduling)")
+    ap.add_argument("--tuning", type=int, default=0, help="circuit_batch_set_tuning flags (bit 0/1 L2 prefetch, bit 2 no L1 re-fetch, bit 3 fused elimination steps)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,6 +200,7 @@ def main():
     b.set_resident(*[int(v) for v in args.resident.split(",")])
     b.set_workspace(args.workspace)
     b.set_chunks(args.chunks)
+    b.set_tuning(args.tuning)
     table = b.param_table(items)
     b.set_params(table, host_vals.data_ptr())  # first time: host copies + layout
     b.prepare()

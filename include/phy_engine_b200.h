@@ -161,6 +161,10 @@ extern "C"
     /* tree-streaming kernel: number of chunks the time loop is cut into for dynamic (group, chunk) scheduling over
      * persistent CTAs: 0 = automatic, 1 = static (one CTA per 32-lane group runs the whole launch), up to 32 */
     int circuit_batch_set_chunks(void* batch, int chunks);
+    /* tuning flags of the tree-scheduled kernels (defaults = 0): bit 0 line-ahead L2 prefetch of operand rows, bit 1 ... two
+     * lines ahead, bit 2 no L1 re-fetch of a DOT result after its store, bit 3 fuse small elimination steps into one op
+     * (PE_OP_CROUT2; takes effect at the next compile) */
+    int circuit_batch_set_tuning(void* batch, unsigned flags);
     /* info[13] = resident, streams, workspace slots per instance, I, J (0 = does not fit), io entries,
      * last launch S / I / J (0 = the flat HBM-streaming kernel ran), phases of the iter section, words, longest warp
      * stream, workspace in HBM (1) or shared memory (0) */
@@ -215,8 +219,9 @@ extern "C"
     int circuit_batch_swept_values(void* batch, long long slot, double* out);
 
     /* process-wide defaults every batch created afterwards (including the one behind circuit_analyze) starts from:
-     * the arguments of circuit_batch_set_resident, circuit_batch_set_subtree_warps and circuit_batch_set_workspace */
-    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace);
+     * the arguments of circuit_batch_set_resident, circuit_batch_set_subtree_warps, circuit_batch_set_workspace and
+     * circuit_batch_set_tuning */
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace, unsigned tuning);
     int phy_engine_b200_device_count(void);
     uint64_t phy_engine_b200_launch_count(void);
     /* device-side timing of the solve kernels (CUDA events on the launching stream): enable, then read-and-reset the

@@ -632,169 +632,101 @@ namespace
         }
     }
 
-    // complex DOT (AC sweeps) with at most 2 rows of packed re-sources, 2 of im-sources and 3 pairs: a complex value has
-    // its real part in row q and its imaginary part in row q + S; every operand load is issued before the first use
+    // fused elimination step (PE_OP_CROUT2): six DOT slots [pivot | U entries, L entries, rhs entry]; all 26 operand
+    // rows of the step are requested before the first is used, the pivot reciprocal stays in a register
     template <int J>
-    __device__ __forceinline__ void tree_cdot(line_reader const& rd, lane_ws const& at, uint32_t S, uint32_t nre, uint32_t nim, uint32_t nb, bool const (&en)[J],
-                                              bool (&fail)[J])
+    __device__ __forceinline__ void tree_crout2(line_reader const& rd, lane_ws const& at, bool const (&en)[J], bool (&fail)[J])
     {
-        // words of the op: [h][mask][ctl][scale][src_re x nre][src_im x nim][pair x nb]
-        uint32_t const flags = rd.raw(2) >> 16;
-        uint32_t const dst = rd.lo(2) & 0x7fffu;
-        uint64_t const im_off = (uint64_t)S * at.LS8;  // bytes between the re and the im row of a complex value
-        auto im_of = [&](double const* p) -> double const* { return reinterpret_cast<double const*>(reinterpret_cast<char const*>(p) + im_off); };
-        uint32_t gre[4], gim[4];
-        double sre[4][J], sim[4][J], ar[3][J], ai[3][J], br[3][J], bi[3][J], scr[J], sci[J];
+        // words: [h][mask] then slot 0: [ctl][src][src][pair], slots 1..5: [ctl][src][pair]
+        uint32_t gs[14], gp[6];
+        double sv[14][J], pa[6][J], pb[6][J];
 #pragma unroll
-        for(int i = 0; i < 2; ++i)
+        for(int q = 0; q < 6; ++q)
         {
-            if((uint32_t)i < nre)
+            int const base = q == 0 ? 0 : 4 + 3 * (q - 1);
+            int const nsr = q == 0 ? 2 : 1;
+            int const s0 = q == 0 ? 0 : 4 + 2 * (q - 1);
+#pragma unroll
+            for(int r = 0; r < nsr; ++r)
             {
-                gre[2 * i] = rd.lo(4 + i);
-                gre[2 * i + 1] = rd.hi(4 + i);
-                double const* p0 = at(gre[2 * i] & 0x7fffu);
-                double const* p1 = at(gre[2 * i + 1] & 0x7fffu);
+                gs[s0 + 2 * r] = rd.lo(2 + base + 1 + r);
+                gs[s0 + 2 * r + 1] = rd.hi(2 + base + 1 + r);
+                double const* p0 = at(gs[s0 + 2 * r] & 0x7fffu);
+                double const* p1 = at(gs[s0 + 2 * r + 1] & 0x7fffu);
 #pragma unroll
                 for(int j = 0; j < J; ++j)
                 {
-                    sre[2 * i][j] = p0[32 * j];
-                    sre[2 * i + 1][j] = p1[32 * j];
+                    sv[s0 + 2 * r][j] = p0[32 * j];
+                    sv[s0 + 2 * r + 1][j] = p1[32 * j];
                 }
             }
-        }
-#pragma unroll
-        for(int i = 0; i < 2; ++i)
-        {
-            if((uint32_t)i < nim)
-            {
-                gim[2 * i] = rd.lo(4 + nre + i);
-                gim[2 * i + 1] = rd.hi(4 + nre + i);
-                double const* p0 = at(gim[2 * i] & 0x7fffu);
-                double const* p1 = at(gim[2 * i + 1] & 0x7fffu);
-#pragma unroll
-                for(int j = 0; j < J; ++j)
-                {
-                    sim[2 * i][j] = p0[32 * j];
-                    sim[2 * i + 1][j] = p1[32 * j];
-                }
-            }
-        }
-#pragma unroll
-        for(int i = 0; i < 3; ++i)
-        {
-            if((uint32_t)i < nb)
-            {
-                double const* pa = at(rd.lo(4 + nre + nim + i) & 0x7fffu);
-                double const* pb = at(rd.hi(4 + nre + nim + i) & 0x7fffu);
-                double const* pai = im_of(pa);
-                double const* pbi = im_of(pb);
-#pragma unroll
-                for(int j = 0; j < J; ++j)
-                {
-                    ar[i][j] = pa[32 * j];
-                    ai[i][j] = pai[32 * j];
-                    br[i][j] = pb[32 * j];
-                    bi[i][j] = pbi[32 * j];
-                }
-            }
-        }
-        if(flags & PE_F_SCALE)
-        {
-            double const* ps = at(rd.lo(3) & 0x7fffu);
-            double const* psi = im_of(ps);
+            uint32_t const ga = rd.lo(2 + base + 1 + nsr), gb = rd.hi(2 + base + 1 + nsr);
+            gp[q] = (ga ^ gb) & 0x80000000u;
+            double const* a = at(ga & 0x7fffu);
+            double const* b = at(gb & 0x7fffu);
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
-                scr[j] = ps[32 * j];
-                sci[j] = psi[32 * j];
+                pa[q][j] = a[32 * j];
+                pb[q][j] = b[32 * j];
             }
         }
-        double are[J], aim[J];
+        double piv[J];
 #pragma unroll
-        for(int j = 0; j < J; ++j) { are[j] = aim[j] = 0.0; }
-        // the same operation order as pe_rinterp::rvop's CDOT (the emulator and the generic path): sources pairwise, then
-        // the four fused multiply-adds of every complex product
+        for(int j = 0; j < J; ++j) { piv[j] = 0.0; }
 #pragma unroll
-        for(int i = 0; i < 2; ++i)
+        for(int q = 0; q < 6; ++q)
         {
-            if((uint32_t)i < nre)
+            int const base = q == 0 ? 0 : 4 + 3 * (q - 1);
+            int const nsr = q == 0 ? 2 : 1;
+            int const s0 = q == 0 ? 0 : 4 + 2 * (q - 1);
+            uint32_t const ctl = rd.raw(2 + base);
+            if(!(ctl & PE_R_ACTIVE)) { continue; }
+            uint32_t const flags = ctl >> 16;
+            double acc[J];
+#pragma unroll
+            for(int j = 0; j < J; ++j) { acc[j] = 0.0; }
+#pragma unroll
+            for(int i = 0; i < 2 * nsr; ++i)
             {
+                double const sg = __hiloint2double((int)(0x3ff00000u | (gs[s0 + i] & 0x80000000u)), 0);
 #pragma unroll
-                for(int j = 0; j < J; ++j)
-                {
-                    double const s0 = (gre[2 * i] >> 31) ? -sre[2 * i][j] : sre[2 * i][j];
-                    double const s1 = (gre[2 * i + 1] >> 31) ? -sre[2 * i + 1][j] : sre[2 * i + 1][j];
-                    are[j] = PE_ADD(PE_ADD(are[j], s0), s1);
-                }
+                for(int j = 0; j < J; ++j) { acc[j] = fma(sv[s0 + i][j], sg, acc[j]); }
             }
-        }
-#pragma unroll
-        for(int i = 0; i < 2; ++i)
-        {
-            if((uint32_t)i < nim)
-            {
-#pragma unroll
-                for(int j = 0; j < J; ++j)
-                {
-                    double const s0 = (gim[2 * i] >> 31) ? -sim[2 * i][j] : sim[2 * i][j];
-                    double const s1 = (gim[2 * i + 1] >> 31) ? -sim[2 * i + 1][j] : sim[2 * i + 1][j];
-                    aim[j] = PE_ADD(PE_ADD(aim[j], s0), s1);
-                }
-            }
-        }
-#pragma unroll
-        for(int i = 0; i < 3; ++i)
-        {
-            if((uint32_t)i < nb)
-            {
-#pragma unroll
-                for(int j = 0; j < J; ++j)
-                {
-                    are[j] = fma(-ar[i][j], br[i][j], are[j]);
-                    are[j] = fma(ai[i][j], bi[i][j], are[j]);
-                    aim[j] = fma(-ar[i][j], bi[i][j], aim[j]);
-                    aim[j] = fma(-ai[i][j], br[i][j], aim[j]);
-                }
-            }
-        }
-        if(flags & PE_F_SCALE)
-        {
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
-                double const nr = are[j] * scr[j] - aim[j] * sci[j];
-                double const ni = are[j] * sci[j] + aim[j] * scr[j];
-                are[j] = nr;
-                aim[j] = ni;
+                double const a = __hiloint2double(__double2hiint(pa[q][j]) ^ (int)(0x80000000u ^ gp[q]), __double2loint(pa[q][j]));
+                acc[j] = fma(a, pb[q][j], acc[j]);
             }
-        }
-        if(flags & PE_F_RECIP)
-        {
+            if(flags & PE_F_SCALE)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j) { acc[j] = PE_MUL(acc[j], piv[j]); }
+            }
+            if(flags & PE_F_RECIP)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    if(acc[j] == 0.0 || !isfinite(acc[j])) { fail[j] = true; }
+                    acc[j] = PE_RCP(acc[j]);
+                    piv[j] = acc[j];
+                }
+            }
+            double* const pd = at(rd.lo(2 + base) & 0x7fffu);
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
-                double const mm = are[j] * are[j] + aim[j] * aim[j];
-                if(!(mm > 0.0) || !isfinite(mm)) { fail[j] = true; }
-                double const sc = 1.0 / mm;
-                are[j] = are[j] * sc;
-                aim[j] = -aim[j] * sc;
-            }
-        }
-        double* const pd = at(dst);
-        double* const pdi = const_cast<double*>(im_of(pd));
-#pragma unroll
-        for(int j = 0; j < J; ++j)
-        {
-            if(en[j])
-            {
-                pd[32 * j] = are[j];
-                pdi[32 * j] = aim[j];
+                if(en[j]) { pd[32 * j] = acc[j]; }
             }
         }
     }
 
     // CTA = S warps x (32 x J) lanes: thread (warp s, lane l) runs stream s for lanes l, l + 32, ... of the group
-    template <int J, int MAXT, int MINB>
+    // FUSED: the program may hold fused elimination steps (PE_OP_CROUT2); the code for them is kept out of the other
+    // instances, whose register budget it would blow
+    template <int J, int MAXT, int MINB, bool FUSED>
     __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
     {
         __shared__ uint32_t s_flags[3][32 * J];
@@ -958,13 +890,12 @@ namespace
                             rd.adv(4u + na + nb);
                             continue;
                         }
-                        if(op == PE_OP_CDOT)
+                        if constexpr(FUSED)
                         {
-                            uint32_t const nim = (h >> 13) & 0x1fu;
-                            if(na <= 2u && nim <= 2u && nb <= 3u)
+                            if(op == PE_OP_CROUT2)
                             {
-                                tree_cdot<J>(rd, at, S, na, nim, nb, en, fail);
-                                rd.adv(4u + na + nim + nb);
+                                tree_crout2<J>(rd, at, en, fail);
+                                rd.adv(21u);
                                 continue;
                             }
                         }
@@ -1011,7 +942,7 @@ namespace
                         c.stream = warp;
                         c.js = 32;
                         tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
-                        int const k = rvop<J>(rd, c, t, tol, en, check, nconv, fail);
+                        int const k = rvop<J, line_reader, false>(rd, c, t, tol, en, check, nconv, fail);
                         if(k == V_END || k == V_BAD) { break; }
                         if(k == V_BAR)
                         {
@@ -1244,10 +1175,18 @@ extern "C"
                 cudaEventRecord(e0, (cudaStream_t)stream);
             }
             void (*tk)(pe_b200_rrun) = nullptr;
-            if(J == 2) { tk = block <= 256 ? pe_b200_tree_kernel<2, 256, 4> : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2> : pe_b200_tree_kernel<2, 1024, 1>); }
+            // register budgets: 64 per thread by default; programs with fused elimination steps (26 J operand rows in
+            // flight per thread) get 128 when the CTA has at most 512 threads
+            bool const fused{run->regs128 != 0};
+            if(J == 2)
+            {
+                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<2, 512, 1, true> : pe_b200_tree_kernel<2, 1024, 1, true>)
+                           : (block <= 256 ? pe_b200_tree_kernel<2, 256, 4, false> : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2, false> : pe_b200_tree_kernel<2, 1024, 1, false>));
+            }
             else
             {
-                tk = block <= 256 ? pe_b200_tree_kernel<1, 256, 4> : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2> : pe_b200_tree_kernel<1, 1024, 1>);
+                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<1, 512, 1, true> : pe_b200_tree_kernel<1, 1024, 1, true>)
+                           : (block <= 256 ? pe_b200_tree_kernel<1, 256, 4, false> : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2, false> : pe_b200_tree_kernel<1, 1024, 1, false>));
             }
             int tgrid = grid;
             if(run->sched != nullptr)

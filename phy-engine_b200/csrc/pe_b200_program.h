@@ -60,6 +60,12 @@ extern "C"
         // resident programs packed for one stream per warp: the rest of this 32-word line of the main stream is padding
         // (a vector op never straddles two lines, so that the warp reader hands out its words with one shuffle each)
         PE_OP_SKIP = 4,
+        // resident programs: one whole Crout elimination step whose pivot has at most two U and two L entries, fused:
+        // six DOT slots [pivot | up to five of: U entries, L entries, the rhs entry], semantically the six DOTs in a row,
+        // with the L entries scaled by the fresh pivot reciprocal from a register.  19 rows (header field a = 19):
+        //   slot 0: [ctl][src][src][pair]      slots 1..5: [ctl][src][pair]      (ctl = dst | ACTIVE << 15 | flags << 16)
+        // The kernels request all 26 operands of the step before they use the first one.
+        PE_OP_CROUT2 = 5,
 
         // scalar value ops (real), generic operands
         PE_OP_RECIP = 10,    // [dst][a]          dst = 1.0 / a
@@ -229,6 +235,7 @@ extern "C"
         // n_chunks chunks of chunk_steps steps; persistent CTAs take (chunk, group) items from an atomic counter in
         // chunk-major order, so a group migrates between SMs and the last wave is one chunk long instead of one run.
         // sched = NULL: one CTA per group runs the whole launch.
+        int32_t regs128;      // tree-streaming form: 1 = the program has fused elimination steps, give CTAs of <= 512 threads 128 registers
         int32_t prefetch;     // tree-streaming form: 1 = L2 prefetch of the operands of the next line of program words
         int32_t chunk_steps;
         int32_t n_chunks;

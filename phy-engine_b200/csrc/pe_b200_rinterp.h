@@ -188,7 +188,7 @@ namespace pe_rinterp
     // caller closes the op on the reader (rd.close()), after V_BAR it steps over the barrier word (rd.bar()).
     // On the GPU every thread of the warp consumes every row of the op before any divergence (the reader is
     // warp-cooperative); an idle column then simply does not store.
-    template <int J, class R>
+    template <int J, class R, bool FUSED = true>
     PE_HD int rvop(R& rd, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
     {
         uint32_t const h = rd.head();
@@ -372,6 +372,60 @@ namespace pe_rinterp
             uint32_t const dst = abs_slot(c, ctl);
             stv<J>(c, dst, are, en);
             stv<J>(c, dst + c.S, aim, en);
+            return V_OK;
+        }
+        if(FUSED && op == PE_OP_CROUT2)
+        {
+            // fused elimination step: six DOT slots, the same arithmetic as the six DOTs one after the other; the L
+            // entries are scaled by the pivot reciprocal just computed (identical to the value stored for it)
+            rd.open(19u);
+            uint32_t wd[19];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for(uint32_t r = 0; r < 19u; ++r) { wd[r] = fetch(); }
+            vd<J> piv;
+            for(int j = 0; j < J; ++j) { piv.v[j] = 0.0; }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for(uint32_t q = 0; q < 6u; ++q)
+            {
+                uint32_t const base = q == 0u ? 0u : 4u + 3u * (q - 1u);
+                uint32_t const nsr = q == 0u ? 2u : 1u;
+                uint32_t const ctl = wd[base];
+                if(!(ctl & PE_R_ACTIVE)) { continue; }
+                vd<J> acc;
+                for(int j = 0; j < J; ++j) { acc.v[j] = 0.0; }
+                for(uint32_t r = 0; r < nsr; ++r)
+                {
+                    uint32_t const w = wd[base + 1u + r];
+                    vd<J> const s0 = ldo<J>(c, w & 0xffffu);
+                    vd<J> const s1 = ldo<J>(c, w >> 16);
+                    for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
+                }
+                {
+                    uint32_t const w = wd[base + 1u + nsr];
+                    vd<J> const a = ldo<J>(c, w & 0xffffu);
+                    vd<J> const b = ldo<J>(c, w >> 16);
+                    for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
+                }
+                uint32_t const flags = ctl >> 16;
+                if(flags & PE_F_SCALE)
+                {
+                    for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], piv.v[j]); }
+                }
+                if(flags & PE_F_RECIP)
+                {
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { fail[j] = true; }
+                        acc.v[j] = PE_RCP(acc.v[j]);
+                        piv.v[j] = acc.v[j];
+                    }
+                }
+                stv<J>(c, abs_slot(c, ctl), acc, en);
+            }
             return V_OK;
         }
         // ---- value ops: a = operand rows; row 0 carries the ACTIVE bit

@@ -68,7 +68,7 @@ namespace pe_b200
         int r_real{pick_streams(n_unk)};
         int r_ac{pick_streams(n_unk)};
         bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac ||
-                        r_real != cc_res_real || r_ac != cc_res_ac};
+                        r_real != cc_res_real || r_ac != cc_res_ac || res_fuse != cc_fuse};
         if(!need) { return true; }
         layout_keys = keys;
 
@@ -86,10 +86,12 @@ namespace pe_b200
         cc_warps_ac = w_ac;
         cc_res_real = r_real;
         cc_res_ac = r_ac;
+        cc_fuse = res_fuse;
         for(int attempt{}; attempt < 3; ++attempt)
         {
             in.resident_real = r_real;
             in.resident_ac = r_ac;
+            in.fuse_steps = res_fuse != 0;
             cc = compile_circuit(in);
             if(!cc)
             {
@@ -447,6 +449,7 @@ namespace pe_b200
             r.wsg = static_cast<double*>(d_ws.p);
             r.LSw = LSw;
             r.prefetch = res_prefetch;
+            r.regs128 = pr.n_fused > 0 ? 1 : 0;
             // dynamic (group, chunk) scheduling of long time loops: up to 32 chunks of at least 4 steps
             int nc{res_chunks > 0 ? res_chunks : std::min(32, n_steps / 4)};
             nc = std::clamp(nc, 1, 32);
@@ -777,6 +780,8 @@ namespace pe_b200
             solo->subtree_warps = d.subtree_warps;
             solo->res_ws = d.res_ws;
             solo->res_chunks = d.res_chunks;
+            solo->res_prefetch = ((d.tuning & 1u) ? 1 : 0) | ((d.tuning & 2u) ? 2 : 0) | ((d.tuning & 4u) ? 0 : 4);
+            solo->res_fuse = (d.tuning & 8u) ? 1 : 0;
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

@@ -479,6 +479,7 @@ extern "C"
         b->subtree_warps = d.subtree_warps;
         b->res_ws = d.res_ws;
         b->res_chunks = d.res_chunks;
+        circuit_batch_set_tuning(b, d.tuning);
         return b;
     }
 
@@ -520,13 +521,17 @@ extern "C"
 
     int circuit_batch_set_chunks(void* b, int chunks)
     {
-        // bit 8 of `chunks` switches the L2 operand prefetch of the tree-streaming kernel on (tuning knob)
-        if(b == nullptr || chunks < 0 || (chunks & 0xff) > 32) { return 1; }  // tuning bits above bit 7, see below
-        static_cast<batch*>(b)->res_chunks = chunks & 0xff;
-        // bit 8: line-ahead L2 operand prefetch
-        // bit 9: ... two lines ahead instead of one
-        // bit 11: switch the (default) L1 re-fetch off
-        static_cast<batch*>(b)->res_prefetch = ((chunks & 0x100) ? 1 : 0) | ((chunks & 0x200) ? 2 : 0) | ((chunks & 0x800) ? 0 : 4);
+        if(b == nullptr || chunks < 0 || chunks > 32) { return 1; }
+        static_cast<batch*>(b)->res_chunks = chunks;
+        return 0;
+    }
+
+    int circuit_batch_set_tuning(void* b, unsigned flags)
+    {
+        if(b == nullptr || flags > 15u) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        bp->res_prefetch = ((flags & 1u) ? 1 : 0) | ((flags & 2u) ? 2 : 0) | ((flags & 4u) ? 0 : 4);
+        bp->res_fuse = (flags & 8u) ? 1 : 0;
         return 0;
     }
 
@@ -872,9 +877,9 @@ extern "C"
         return 1;
     }
 
-    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace)
+    int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace, unsigned tuning)
     {
-        if(workspace < 0 || workspace > 2) { return 1; }
+        if(workspace < 0 || workspace > 2 || tuning > 15u) { return 1; }
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
@@ -886,6 +891,7 @@ extern "C"
         d.res_J = instances_per_thread;
         d.subtree_warps = subtree_warps;
         d.res_ws = workspace;
+        d.tuning = tuning;
         return 0;
     }
 

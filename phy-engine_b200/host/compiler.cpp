@@ -1278,6 +1278,7 @@ namespace pe_b200
                 int const L{tree.n_levels};
                 int const n_ph{2 * L};
                 constexpr std::uint32_t NEG{0x80000000u};
+                bool const fuse_steps{in.fuse_steps};
 
                 pr.resident = true;
                 pr.rS = S;
@@ -1461,6 +1462,7 @@ namespace pe_b200
                     auto const& st{steps[k]};
                     int const sj{node_stream(st.node)};
                     int const ph{fwd_phase(st.node)};
+                    std::size_t const step_begin{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(ph)].size()};
                     load_sources(rc.orig[static_cast<std::size_t>(st.piv)]);
                     load_updates(st.piv, rc.pairs[static_cast<std::size_t>(st.piv)], st.node, false);
                     emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
@@ -1490,6 +1492,29 @@ namespace pe_b200
                         load_sources(&ps.Z[static_cast<std::size_t>(st.r)]);
                         load_updates(static_cast<std::int64_t>(n_ent) + st.r, rc.ypairs[static_cast<std::size_t>(st.r)], st.node, true);
                         emit_dot(sj, ph, key_y(st.r), 0, 0, sre, sim, pp);
+                    }
+                    // a step whose DOTs are all small becomes one fused op (PE_OP_CROUT2): the kernels then request every
+                    // operand of the step at once and keep the pivot reciprocal in a register
+                    if(fuse_steps && !cplx)
+                    {
+                        auto& lst{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(ph)]};
+                        std::size_t const n_new{lst.size() - step_begin};
+                        bool fits{n_new >= 2 && n_new <= 6};
+                        for(std::size_t q{}; fits && q < n_new; ++q)
+                        {
+                            auto const& o{lst[step_begin + q]};
+                            fits = o.opcode == PE_OP_DOT && o.sim.empty() && o.pp.size() <= 1 && o.sre.size() <= (q == 0 ? 4u : 2u) &&
+                                   (q == 0 ? o.flags == PE_F_RECIP : (o.flags == 0u || (o.flags == PE_F_SCALE && o.scale == lst[step_begin].dst)));
+                        }
+                        if(fits)
+                        {
+                            rop f;
+                            f.opcode = PE_OP_CROUT2;
+                            f.sub.assign(std::make_move_iterator(lst.begin() + static_cast<std::ptrdiff_t>(step_begin)), std::make_move_iterator(lst.end()));
+                            lst.resize(step_begin);
+                            lst.push_back(std::move(f));
+                            ++pr.n_fused;
+                        }
                     }
                 }
                 for(std::size_t m{}; m < node_contribs.size(); ++m)
@@ -1654,8 +1679,10 @@ namespace pe_b200
                     return {k, 1};
                 };
                 // the scalar keys an op touches, in a canonical role order: fn(key, is_write)
-                auto visit = [&](rop const& o, auto&& fn)
+                auto visit = [&](rop const& o0, auto&& fn)
                 {
+                  auto one = [&](rop const& o)
+                  {
                     if(o.bubble) { return; }
                     if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
                     {
@@ -1685,6 +1712,15 @@ namespace pe_b200
                         int const no{value_op_outputs(o.opcode)};
                         for(std::size_t k{}; k < o.opnd.size(); ++k) { fn(o.opnd[k] & ~NEG, static_cast<int>(k) < no); }
                     }
+                  };
+                  if(o0.opcode == PE_OP_CROUT2)
+                  {
+                      for(auto const& sb: o0.sub) { one(sb); }
+                  }
+                  else
+                  {
+                      one(o0);
+                  }
                 };
                 struct vinfo
                 {
@@ -1828,9 +1864,9 @@ namespace pe_b200
                     {
                         for(auto& ph: sec)
                         {
-                            for(auto& o: ph)
+                            auto translate = [&](rop& o)
                             {
-                                if(o.bubble) { continue; }
+                                if(o.bubble) { return; }
                                 if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT)
                                 {
                                     o.dst = rel_of(o.dst, sj);
@@ -1846,6 +1882,17 @@ namespace pe_b200
                                 else if(o.opcode != 0xffu)
                                 {
                                     for(auto& k: o.opnd) { k = rel_of(k, sj); }
+                                }
+                            };
+                            for(auto& o: ph)
+                            {
+                                if(o.opcode == PE_OP_CROUT2)
+                                {
+                                    for(auto& sb: o.sub) { translate(sb); }
+                                }
+                                else
+                                {
+                                    translate(o);
                                 }
                             }
                         }
@@ -2667,6 +2714,41 @@ namespace pe_b200
                                 add_row([&](rop const* o) { return (o && r < o->pp.size()) ? (o->pp[r].first | (o->pp[r].second << 16)) : pad_pair; });
                             }
                         }
+                        else if(opc == PE_OP_CROUT2)
+                        {
+                            h0 = opc | (19u << 8);
+                            for(std::size_t q{}; q < 6; ++q)
+                            {
+                                auto sub_of = [&](rop const* o) -> rop const* { return (o && q < o->sub.size()) ? &o->sub[q] : nullptr; };
+                                rows.emplace_back(static_cast<std::size_t>(C));
+                                for(int c{}; c < C; ++c)
+                                {
+                                    auto const* sb{sub_of(act[static_cast<std::size_t>(c)])};
+                                    rows.back()[static_cast<std::size_t>(c)] = sb ? (sb->dst | PE_R_ACTIVE | (sb->flags << 16)) : 0u;
+                                }
+                                for(std::size_t r{}; r < (q == 0 ? 2u : 1u); ++r)
+                                {
+                                    rows.emplace_back(static_cast<std::size_t>(C));
+                                    for(int c{}; c < C; ++c)
+                                    {
+                                        auto const* sb{sub_of(act[static_cast<std::size_t>(c)])};
+                                        std::uint32_t s0{zero | PE_R_NEG}, s1{zero | PE_R_NEG};
+                                        if(sb)
+                                        {
+                                            if(2 * r < sb->sre.size()) { s0 = sb->sre[2 * r]; }
+                                            if(2 * r + 1 < sb->sre.size()) { s1 = sb->sre[2 * r + 1]; }
+                                        }
+                                        rows.back()[static_cast<std::size_t>(c)] = s0 | (s1 << 16);
+                                    }
+                                }
+                                rows.emplace_back(static_cast<std::size_t>(C));
+                                for(int c{}; c < C; ++c)
+                                {
+                                    auto const* sb{sub_of(act[static_cast<std::size_t>(c)])};
+                                    rows.back()[static_cast<std::size_t>(c)] = (sb && !sb->pp.empty()) ? (sb->pp[0].first | (sb->pp[0].second << 16)) : pad_pair;
+                                }
+                            }
+                        }
                         else
                         {
                             std::size_t nr{};
@@ -2699,7 +2781,10 @@ namespace pe_b200
                             for(int c{}; c < C; ++c)
                             {
                                 bool const on{act[static_cast<std::size_t>(c)] != nullptr};
-                                if(r == 0 && !on) { uni = false; }
+                                // rows that carry an activity bit (row 0; every ctl row of a fused step) must reach an
+                                // idle column as its own (inactive) word
+                                bool const ctl_row{r == 0 || (opc == PE_OP_CROUT2 && r >= 4 && (r - 4) % 3 == 0)};
+                                if(ctl_row && !on) { uni = false; }
                                 if(!on) { continue; }
                                 if(!have)
                                 {

@@ -163,6 +163,7 @@ namespace pe_b200
         std::vector<std::uint32_t> sre, sim;
         std::vector<std::pair<std::uint32_t, std::uint32_t>> pp;
         std::vector<std::uint32_t> opnd;  // value ops, encoding order
+        std::vector<rop> sub;             // PE_OP_CROUT2: the DOTs of the fused elimination step (pivot first)
     };
     using rphase = std::vector<rop>;
     struct rstream
@@ -198,6 +199,7 @@ namespace pe_b200
         // statistics for the roofline and the schedule
         std::size_t nnz_a{}, nnz_lu{}, n_fma{};
         std::size_t n_leaf_rows{}, n_top_rows{}, n_leaves{};
+        std::size_t n_fused{};    // elimination steps emitted as one fused PE_OP_CROUT2
         std::size_t n_aliased{};  // U entries that are a signed copy of one stamped value and were never materialised
         std::size_t max_warp_words{};  // longest iter stream (critical path in words)
     };
@@ -228,6 +230,7 @@ namespace pe_b200
         int warps_ac{1};    // ... for the AC program
         int resident_real{0};  // > 0: build the real-valued programs in resident form with this many streams
         int resident_ac{0};    // > 0: ... the AC program
+        bool fuse_steps{false};  // resident programs: emit small elimination steps as one fused op
     };
 
     // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot
@@ -287,6 +290,8 @@ namespace pe_b200
         // ahead, 4 = L1 re-fetch of every DOT result right after its store (+3 %: on)
         int res_prefetch{4};
         std::size_t last_points_hint{1};  // frequency points per instance of the AC sweep being launched (lane count = n_inst * points)
+        int res_fuse{0};     // emit small elimination steps as one fused op (PE_OP_CROUT2); measured slower on config B (register file bound): off
+        int cc_fuse{-1};
         int res_chunks{0};   // chunks the time loop is cut into for dynamic scheduling: 0 = choose, 1 = static (one CTA per group)
         bool use_hbm(program const& pr) const;
         int cc_res_real{-1}, cc_res_ac{-1};
@@ -353,6 +358,7 @@ namespace pe_b200
         int subtree_warps{0};
         int res_ws{0};
         int res_chunks{0};
+        unsigned tuning{0};  // circuit_batch_set_tuning flags
     };
     path_defaults& default_path();
 

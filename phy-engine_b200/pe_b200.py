@@ -226,7 +226,8 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_set_probes.argtypes = [V, _PSZ, _SZ]
     lib.circuit_batch_set_subtree_warps.argtypes = [V, ct.c_int]
     lib.circuit_batch_set_resident.argtypes = [V, ct.c_int, ct.c_int, ct.c_int]
-    lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int]
+    lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_uint]
+    lib.circuit_batch_set_tuning.argtypes = [V, ct.c_uint]
     lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
     lib.circuit_batch_set_chunks.argtypes = [V, ct.c_int]
     lib.circuit_batch_resident_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
@@ -366,6 +367,10 @@ class Batch:
     def set_chunks(self, chunks: int):
         """tree-streaming kernel: chunks of the time loop for dynamic scheduling (0 = automatic, 1 = static)"""
         self._rc(self.lib.circuit_batch_set_chunks(self.h, chunks), "circuit_batch_set_chunks")
+
+    def set_tuning(self, flags: int):
+        """bit 0 L2 operand prefetch, bit 1 two lines ahead, bit 2 no L1 re-fetch of results, bit 3 fused elimination steps"""
+        self._rc(self.lib.circuit_batch_set_tuning(self.h, flags), "circuit_batch_set_tuning")
 
     def resident_info(self, mode: int) -> dict:
         v = (ct.c_int64 * 13)()

@@ -28,7 +28,7 @@ def abi(request):
 def path(request, abi):
     assert abi.lib.phy_engine_b200_set_default_path(*PATHS[request.param]) == 0
     yield request.param
-    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0, 0)
+    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0, 0, 0)
 
 
 @pytest.mark.parametrize("name", list(golden_cases.CASES))

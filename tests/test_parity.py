@@ -30,21 +30,21 @@ def abi(request):
 #   auto            the product default: shared-memory resident kernel for small circuits, tree-streaming (HBM
 #                   workspace, one warp per sub-tree) otherwise
 #   tree-hbm-s4     tree-streaming kernel forced, 4 sub-tree warps per 32 lanes
-#   tree-hbm-s16    ... 16 sub-tree warps
-#   tree-hbm-s8j2   ... 8 sub-tree warps, 64 lanes per CTA (two per thread)
-#   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp)
+#   tree-hbm-s16    ... 16 sub-tree warps, L2 operand prefetch on
+#   tree-hbm-s8j2   ... 8 sub-tree warps, 64 lanes per CTA (two per thread), fused elimination steps
+#   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp), fused elimination steps
 #   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
 #   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
 #   flat-g4         ... 4 sub-tree warps per 32 instances
 PATHS = {
-    "auto": (0, 0, 0, 0, 0),
-    "tree-hbm-s4": (4, 0, 0, 0, 2),
-    "tree-hbm-s16": (16, 0, 0, 0, 2),
-    "tree-hbm-s8j2": (8, 0, 2, 0, 2),
-    "resident-s8": (8, 0, 1, 0, 1),
-    "resident-s32j2": (32, 2, 2, 0, 1),
-    "flat": (-1, 0, 0, 0, 0),
-    "flat-g4": (-1, 0, 0, 4, 0),
+    "auto": (0, 0, 0, 0, 0, 0),
+    "tree-hbm-s4": (4, 0, 0, 0, 2, 0),
+    "tree-hbm-s16": (16, 0, 0, 0, 2, 1),
+    "tree-hbm-s8j2": (8, 0, 2, 0, 2, 8),
+    "resident-s8": (8, 0, 1, 0, 1, 8),
+    "resident-s32j2": (32, 2, 2, 0, 1, 0),
+    "flat": (-1, 0, 0, 0, 0, 0),
+    "flat-g4": (-1, 0, 0, 4, 0, 0),
 }
 
 
@@ -53,7 +53,7 @@ def path(request, abi):
     rc = abi.lib.phy_engine_b200_set_default_path(*PATHS[request.param])
     assert rc == 0
     yield request.param
-    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0, 0)
+    abi.lib.phy_engine_b200_set_default_path(0, 0, 0, 0, 0, 0)
 
 
 def assert_close(got, want, what=""):
