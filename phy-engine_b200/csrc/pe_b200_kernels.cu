@@ -1149,8 +1149,8 @@ extern "C"
     {
         if(run == nullptr || run->n_lanes <= 0) { return 0; }
         int const I = run->I, J = run->J, S = run->S;
-        if(I < 1 || I > 64 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
-           (run->wsg == nullptr && I > 32))
+        if(I < 1 || I > 128 || (J != 1 && J != 2 && J != 4) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
+           (run->wsg == nullptr && (I > 32 || J > 2)))
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
             return 1;
@@ -1178,7 +1178,17 @@ extern "C"
             // register budgets: 64 per thread by default; programs with fused elimination steps (26 J operand rows in
             // flight per thread) get 128 when the CTA has at most 512 threads
             bool const fused{run->regs128 != 0};
-            if(J == 2)
+            if(J == 4)
+            {
+                // 128-lane groups (1 KB workspace rows): CTAs of at most 512 threads, 128 registers
+                if(block > 512)
+                {
+                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: J = 4 needs S <= 16");
+                    return 1;
+                }
+                tk = fused ? pe_b200_tree_kernel<4, 512, 1, true> : pe_b200_tree_kernel<4, 512, 1, false>;
+            }
+            else if(J == 2)
             {
                 tk = fused ? (block <= 512 ? pe_b200_tree_kernel<2, 512, 1, true> : pe_b200_tree_kernel<2, 1024, 1, true>)
                            : (block <= 256 ? pe_b200_tree_kernel<2, 256, 4, false> : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2, false> : pe_b200_tree_kernel<2, 1024, 1, false>));

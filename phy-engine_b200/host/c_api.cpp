@@ -504,7 +504,7 @@ extern "C"
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(b == nullptr || streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
-        if(instances_per_thread < 0 || instances_per_thread > 2) { return 1; }
+        if(instances_per_thread < 0 || (instances_per_thread > 2 && instances_per_thread != 4)) { return 1; }
         auto* bp{static_cast<batch*>(b)};
         bp->res_S = streams;
         bp->res_I = instances_per_cta;
@@ -883,7 +883,7 @@ extern "C"
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }
-        if(instances_per_thread < 0 || instances_per_thread > 2) { return 1; }
+        if(instances_per_thread < 0 || (instances_per_thread > 2 && instances_per_thread != 4)) { return 1; }
         if(subtree_warps < 0 || subtree_warps > PE_MAX_WARPS || (subtree_warps > 0 && !pow2(subtree_warps))) { return 1; }
         auto& d{default_path()};
         d.res_S = streams;

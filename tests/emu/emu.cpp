@@ -275,7 +275,7 @@ namespace
             }
             emu_trace::g_map.clear();
             emu_trace::g_phase = 0;
-            uint32_t s_flags[3][64] = {};
+            uint32_t s_flags[3][128] = {};
             for(uint32_t tid = 0; tid < T; ++tid)
             {
                 uint32_t const ig = tid % IG;
@@ -314,7 +314,7 @@ namespace
 
             // one section: warps advance phase by phase; within a phase thread after thread (no cross-thread
             // dependency may exist inside a phase: the race detector checks exactly that)
-            auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 2>>& nconv, std::vector<std::array<bool, 2>>& fail)
+            auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 4>>& nconv, std::vector<std::array<bool, 4>>& fail)
             {
                 std::vector<host_reader> rdw(W);
                 for(uint32_t w = 0; w < W; ++w)
@@ -399,11 +399,11 @@ namespace
                     if(n_end != 0) { return; }
                 }
             };
-            std::vector<std::array<bool, 2>> nconv(T), fail(T);
+            std::vector<std::array<bool, 4>> nconv(T), fail(T);
             auto clear_flags = [&]()
             {
-                for(auto& a: nconv) { a = {false, false}; }
-                for(auto& a: fail) { a = {false, false}; }
+                for(auto& a: nconv) { a = {false, false, false, false}; }
+                for(auto& a: fail) { a = {false, false, false, false}; }
             };
             if(r.has_prep && first_chunk)
             {
@@ -429,7 +429,7 @@ namespace
                 int fi = 0;
                 for(;;)
                 {
-                    for(uint32_t i = 0; i < 64; ++i) { s_flags[fi][i] = 0; }
+                    for(uint32_t i = 0; i < 128; ++i) { s_flags[fi][i] = 0; }
                     clear_flags();
                     run_section(2, true, r.nonlinear != 0, nconv, fail);
                     for(uint32_t tid = 0; tid < T; ++tid)
@@ -517,7 +517,7 @@ extern "C"
     {
         if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
         int const I = rp->I, J = rp->J, S = rp->S;
-        if(I < 1 || I > 64 || (J != 1 && J != 2) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
+        if(I < 1 || I > 128 || (J != 1 && J != 2 && J != 4) || I % J != 0 || S < 1 || (32 % (I / J)) != 0 || (S * (I / J)) % 32 != 0 || S * (I / J) > 1024 ||
            (rp->wsg == nullptr && I > 32) || (rp->wsg != nullptr && I != 32 * J))
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: bad geometry S=%d I=%d J=%d", S, I, J);
@@ -525,7 +525,8 @@ extern "C"
         }
         ++g_launches;
         ++g_resident_launches;
-        if(J == 2) { run_resident<2>(*rp); }
+        if(J == 4) { run_resident<4>(*rp); }
+        else if(J == 2) { run_resident<2>(*rp); }
         else
         {
             run_resident<1>(*rp);

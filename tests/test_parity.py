@@ -32,6 +32,7 @@ def abi(request):
 #   tree-hbm-s4     tree-streaming kernel forced, 4 sub-tree warps per 32 lanes
 #   tree-hbm-s16    ... 16 sub-tree warps, L2 operand prefetch on
 #   tree-hbm-s8j2   ... 8 sub-tree warps, 64 lanes per CTA (two per thread), fused elimination steps
+#   tree-hbm-s4j4   ... 4 sub-tree warps, 128 lanes per CTA (four per thread: 1 KB workspace rows)
 #   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp), fused elimination steps
 #   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
 #   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
@@ -41,6 +42,7 @@ PATHS = {
     "tree-hbm-s4": (4, 0, 0, 0, 2, 0),
     "tree-hbm-s16": (16, 0, 0, 0, 2, 1),
     "tree-hbm-s8j2": (8, 0, 2, 0, 2, 8),
+    "tree-hbm-s4j4": (4, 0, 4, 0, 2, 0),
     "resident-s8": (8, 0, 1, 0, 1, 8),
     "resident-s32j2": (32, 2, 2, 0, 1, 0),
     "flat": (-1, 0, 0, 0, 0, 0),
