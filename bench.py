@@ -299,7 +299,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("kernel", "").startswith(kernel_name) and (rinfo["last_S"], rinfo["last_J"]) == (32, 2):
+        if tj.get("kernel", "").startswith(kernel_name) and (rinfo["last_S"], rinfo["last_J"]) == (tj.get("S", 32), tj.get("J", 2)):
             traffic = tj["dram_bytes_per_solve"] * solves_per_launch
             traffic_src = "profiles/r01_traffic.json: " + tj["capture"]
     avg_launch_ms = kernel_ms / max(launches, 1)

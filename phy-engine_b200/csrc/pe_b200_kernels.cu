@@ -15,6 +15,7 @@
 //
 // This TU includes no reference header (nvcc ICEs on fast_io; SURVEY.md probe table).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -726,25 +727,52 @@ namespace
     // CTA = S warps x (32 x J) lanes: thread (warp s, lane l) runs stream s for lanes l, l + 32, ... of the group
     // FUSED: the program may hold fused elimination steps (PE_OP_CROUT2); the code for them is kept out of the other
     // instances, whose register budget it would blow
-    template <int J, int MAXT, int MINB, bool FUSED>
+    // CL: CTAs per lane group.  CL = 2: a thread-block cluster of two CTAs (two SMs) shares a group, each CTA running half
+    // of its S sub-tree warps; the barriers of the program are cluster barriers (release / acquire at cluster scope), the
+    // per-lane Newton flags of the two CTAs are combined through distributed shared memory.  That is what lets 128-lane
+    // groups (1 KB workspace rows, twice the DRAM efficiency of 512 B rows) still cover all 148 SMs with 10 000 lanes.
+    template <int CL>
+    __device__ __forceinline__ void group_sync()
+    {
+        if constexpr(CL == 1) { __syncthreads(); }
+        else
+        {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+    }
+
+    template <int J, int MAXT, int MINB, bool FUSED, int CL>
     __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
     {
         __shared__ uint32_t s_flags[3][32 * J];
         __shared__ uint32_t s_item;
         using namespace pe_rinterp;
-        uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, n_warps = blockDim.x >> 5;
+        uint32_t const tid = threadIdx.x, lane = tid & 31u, n_warps_cta = blockDim.x >> 5;
+        uint32_t const rank = CL == 1 ? 0u : (uint32_t)cooperative_groups::this_cluster().block_rank();
+        // warp = index of this warp among the S sub-tree warps of the group (over the CTAs of the cluster)
+        uint32_t const warp = rank * n_warps_cta + (tid >> 5), n_warps = n_warps_cta * CL;
+        uint32_t const first_block = blockIdx.x / CL;  // static assignment: one group per cluster
+        // the other CTA's shared memory (CL = 2)
+        uint32_t const* peer_flags = &s_flags[0][0];
+        uint32_t const* lead_item = &s_item;
+        if constexpr(CL == 2)
+        {
+            peer_flags = cooperative_groups::this_cluster().map_shared_rank(&s_flags[0][0], rank ^ 1u);
+            lead_item = cooperative_groups::this_cluster().map_shared_rank(&s_item, 0u);
+        }
         uint32_t const S = (uint32_t)r.S;
         uint32_t const GL = 32u * J;  // lanes per group
         uint32_t const NG = (uint32_t)((r.n_lanes + GL - 1) / GL), NC = r.sched != nullptr ? (uint32_t)r.n_chunks : 1u;
         for(;;)
         {
             // ---- next work item: (chunk c of the time loop, lane group g)
-            uint32_t item = blockIdx.x;
+            uint32_t item = first_block;
             if(r.sched != nullptr)
             {
-                if(tid == 0) { s_item = atomicAdd(r.sched, 1u); }
-                __syncthreads();
-                item = s_item;
+                if(tid == 0 && rank == 0u) { s_item = atomicAdd(r.sched, 1u); }
+                group_sync<CL>();
+                item = *lead_item;
+                if constexpr(CL == 2) { group_sync<CL>(); }  // the leader may overwrite s_item only after both CTAs have read it
             }
             if(item >= NC * NG) { break; }
             uint32_t const chunk = item / NG, group = item - chunk * NG;
@@ -752,7 +780,7 @@ namespace
             {
                 // chunk c of a group starts when its chunk c - 1 (run by some other CTA) has published its results; the
                 // acquire load also drops whatever this SM's L1 still holds of the group's workspace
-                if(tid == 0)
+                if(tid == 0)  // thread 0 of every CTA of the cluster: each SM drops its own L1
                 {
                     uint32_t v;
                     for(;;)
@@ -803,7 +831,7 @@ namespace
                 }
             }
             if(tid < 96 * J) { (&s_flags[0][0])[tid] = 0u; }
-            __syncthreads();
+            group_sync<CL>();
 
             // One copy of the interpreter serves the three sections: stage 0 = prep, 1 = the step section of time step
             // s, 2 = one Newton iteration (the iter section).  The sequencing is uniform over the CTA.
@@ -846,7 +874,7 @@ namespace
                     check = r.nonlinear != 0;
 #pragma unroll
                     for(int j = 0; j < J; ++j) { en[j] = !done[j]; }
-                    if(warp == 0)
+                    if((tid >> 5) == 0)  // first warp of every CTA: its own flag buffer
                     {
 #pragma unroll
                         for(int j = 0; j < J; ++j) { s_flags[fi == 2 ? 0 : fi + 1][lane + 32 * j] = 0u; }
@@ -946,7 +974,7 @@ namespace
                         if(k == V_END || k == V_BAD) { break; }
                         if(k == V_BAR)
                         {
-                            __syncthreads();
+                            group_sync<CL>();
                             rd.bar();
                         }
                         else if(k == V_SKIP) { rd.skip(); }
@@ -955,7 +983,7 @@ namespace
                             rd.close();
                         }
                     }
-                    __syncthreads();  // results of this section are visible to every warp of the CTA
+                    group_sync<CL>();  // results of this section are visible to every warp of the group
                 }
 
                 // ---- what comes next
@@ -975,13 +1003,14 @@ namespace
                     {
                         if(nconv[j] || fail[j]) { atomicOr(&s_flags[fi][lane + 32 * j], (nconv[j] ? 1u : 0u) | (fail[j] ? 2u : 0u)); }
                     }
-                    __syncthreads();
+                    group_sync<CL>();
                     ++it;
                     bool all_done = true;
 #pragma unroll
                     for(int j = 0; j < J; ++j)
                     {
-                        uint32_t const f = s_flags[fi][lane + 32 * j];
+                        uint32_t f = s_flags[fi][lane + 32 * j];
+                        if constexpr(CL == 2) { f |= peer_flags[fi * 32 * J + lane + 32 * j]; }
                         if(!done[j])
                         {
                             ++solves[j];
@@ -1044,9 +1073,10 @@ namespace
             if(r.sched == nullptr) { break; }
             // publish the chunk: every thread's stores are visible device-wide before the group's counter moves
             __threadfence();
-            __syncthreads();
-            if(tid == 0) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(r.sched + 1 + group), "r"(chunk + 1u) : "memory"); }
+            group_sync<CL>();
+            if(tid == 0 && rank == 0u) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(r.sched + 1 + group), "r"(chunk + 1u) : "memory"); }
         }
+        if constexpr(CL == 2) { group_sync<CL>(); }  // neither CTA leaves while the other may still read its shared memory
     }
 
     thread_local char g_err[256] = "";
@@ -1176,48 +1206,84 @@ extern "C"
             }
             void (*tk)(pe_b200_rrun) = nullptr;
             // register budgets: 64 per thread by default; programs with fused elimination steps (26 J operand rows in
-            // flight per thread) get 128 when the CTA has at most 512 threads
+            // flight per thread) and 128-lane groups get 128 in CTAs of at most 512 threads
             bool const fused{run->regs128 != 0};
+            int const CL{run->cluster == 2 ? 2 : 1};
+            int const cta_threads{block / CL};
             if(J == 4)
             {
-                // 128-lane groups (1 KB workspace rows): CTAs of at most 512 threads, 128 registers
-                if(block > 512)
+                if(cta_threads > 512)
                 {
-                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: J = 4 needs S <= 16");
+                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: J = 4 needs at most 16 sub-tree warps per CTA");
                     return 1;
                 }
-                tk = fused ? pe_b200_tree_kernel<4, 512, 1, true> : pe_b200_tree_kernel<4, 512, 1, false>;
+                tk = CL == 2 ? (fused ? pe_b200_tree_kernel<4, 512, 1, true, 2> : pe_b200_tree_kernel<4, 512, 1, false, 2>)
+                             : (fused ? pe_b200_tree_kernel<4, 512, 1, true, 1> : pe_b200_tree_kernel<4, 512, 1, false, 1>);
+            }
+            else if(CL == 2)
+            {
+                snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: clusters are used with J = 4 only");
+                return 1;
             }
             else if(J == 2)
             {
-                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<2, 512, 1, true> : pe_b200_tree_kernel<2, 1024, 1, true>)
-                           : (block <= 256 ? pe_b200_tree_kernel<2, 256, 4, false> : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2, false> : pe_b200_tree_kernel<2, 1024, 1, false>));
+                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<2, 512, 1, true, 1> : pe_b200_tree_kernel<2, 1024, 1, true, 1>)
+                           : (block <= 256 ? pe_b200_tree_kernel<2, 256, 4, false, 1>
+                                           : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2, false, 1> : pe_b200_tree_kernel<2, 1024, 1, false, 1>));
             }
             else
             {
-                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<1, 512, 1, true> : pe_b200_tree_kernel<1, 1024, 1, true>)
-                           : (block <= 256 ? pe_b200_tree_kernel<1, 256, 4, false> : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2, false> : pe_b200_tree_kernel<1, 1024, 1, false>));
+                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<1, 512, 1, true, 1> : pe_b200_tree_kernel<1, 1024, 1, true, 1>)
+                           : (block <= 256 ? pe_b200_tree_kernel<1, 256, 4, false, 1>
+                                           : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2, false, 1> : pe_b200_tree_kernel<1, 1024, 1, false, 1>));
             }
-            int tgrid = grid;
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute attr[1];
+            cfg.blockDim = dim3((unsigned)cta_threads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = (cudaStream_t)stream;
+            cfg.numAttrs = 0;
+            if(CL == 2)
+            {
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+            }
+            int tgroups = grid;  // CTAs (CL = 1) or clusters (CL = 2) to launch
             if(run->sched != nullptr)
             {
-                // persistent CTAs, all co-resident (an item may wait for the previous chunk of its group, which is always
-                // already running): grid = occupancy x SMs
-                int dev = 0, sms = 0, occ = 0;
-                if(cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-                   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, block, 0) != cudaSuccess || occ < 1)
+                // persistent CTAs / clusters, all co-resident (an item may wait for the previous chunk of its group, which is
+                // always already running)
+                int dev = 0, sms = 0, occ = 0, max_clusters = 0;
+                bool ok = cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+                if(ok && CL == 1) { ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, cta_threads, 0) == cudaSuccess && occ >= 1; }
+                if(ok && CL == 2)
                 {
-                    return chk(cudaGetLastError(), "occupancy query") != 0 ? 1 : (snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: occupancy query failed"), 1);
+                    cfg.gridDim = dim3(2u * (unsigned)sms);
+                    ok = cudaOccupancyMaxActiveClusters(&max_clusters, tk, &cfg) == cudaSuccess && max_clusters >= 1;
+                }
+                if(!ok)
+                {
+                    (void)cudaGetLastError();
+                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: occupancy query failed");
+                    return 1;
                 }
                 long long const items = (long long)run->n_chunks * grid;
-                tgrid = (int)std::min<long long>(items, (long long)occ * sms);
+                tgroups = (int)std::min<long long>(items, CL == 2 ? (long long)max_clusters : (long long)occ * sms);
             }
-            tk<<<tgrid, block, 0, (cudaStream_t)stream>>>(*run);
+            cfg.gridDim = dim3((unsigned)(tgroups * CL));
+            pe_b200_rrun arg = *run;
+            void* kargs[1] = {&arg};
+            cudaError_t const le = cudaLaunchKernelExC(&cfg, (void const*)tk, kargs);
             if(g_timing)
             {
                 cudaEventRecord(e1, (cudaStream_t)stream);
                 g_events.emplace_back(e0, e1);
             }
+            if(le != cudaSuccess) { return chk(le, "pe_b200_tree_kernel launch"); }
             g_launches.fetch_add(1);
             return chk(cudaGetLastError(), "pe_b200_tree_kernel launch");
         }

@@ -235,6 +235,8 @@ extern "C"
         // n_chunks chunks of chunk_steps steps; persistent CTAs take (chunk, group) items from an atomic counter in
         // chunk-major order, so a group migrates between SMs and the last wave is one chunk long instead of one run.
         // sched = NULL: one CTA per group runs the whole launch.
+        int32_t cluster;      // tree-streaming form: CTAs per lane group (1, or 2 = thread-block cluster; needs J = 4); the S
+                              // sub-tree warps are split evenly over them
         int32_t regs128;      // tree-streaming form: 1 = the program has fused elimination steps, give CTAs of <= 512 threads 128 registers
         int32_t prefetch;     // tree-streaming form: 1 = L2 prefetch of the operands of the next line of program words
         int32_t chunk_steps;

@@ -183,7 +183,10 @@ namespace pe_b200
         {
             // tree-streaming form: 32 J lanes per CTA, J of them per thread (0 = choose: two when every sub-tree warp of a
             // full-width CTA still leaves the GPU enough independent groups)
-            J = res_J > 0 ? res_J : ((pr.rS >= 32 && n_inst * std::max<std::size_t>(last_points_hint, 1) >= 148u * 64u) ? 2 : 1);
+            // lanes per thread: the more lanes share one decode and the longer a workspace row (128 lanes = 1 KB), the
+            // better, as long as there are enough groups for all SMs: 128-lane groups run on a cluster of two CTAs
+            std::size_t const lanes_total{n_inst * std::max<std::size_t>(last_points_hint, 1)};
+            J = res_J > 0 ? res_J : ((pr.rS >= 32 && lanes_total >= 74u * 128u) ? 4 : ((pr.rS >= 32 && lanes_total >= 148u * 64u) ? 2 : 1));
             I = 32 * J;
             return pr.rS <= 32;
         }
@@ -450,6 +453,8 @@ namespace pe_b200
             r.LSw = LSw;
             r.prefetch = res_prefetch;
             r.regs128 = pr.n_fused > 0 ? 1 : 0;
+            // 128-lane groups whose sub-tree warps do not fit one CTA of 512 threads are run by a cluster of two CTAs
+            r.cluster = (J == 4 && pr.rS * 32 > 512) ? 2 : 1;
             // dynamic (group, chunk) scheduling of long time loops: up to 32 chunks of at least 4 steps
             int nc{res_chunks > 0 ? res_chunks : std::min(32, n_steps / 4)};
             nc = std::clamp(nc, 1, 32);

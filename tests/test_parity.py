@@ -33,6 +33,7 @@ def abi(request):
 #   tree-hbm-s16    ... 16 sub-tree warps, L2 operand prefetch on
 #   tree-hbm-s8j2   ... 8 sub-tree warps, 64 lanes per CTA (two per thread), fused elimination steps
 #   tree-hbm-s4j4   ... 4 sub-tree warps, 128 lanes per CTA (four per thread: 1 KB workspace rows)
+#   tree-hbm-s32j4  ... 32 sub-tree warps split over a thread-block cluster of two CTAs (two SMs per 128-lane group)
 #   resident-s8     shared-memory kernel forced, 8 word streams per instance (4 instances per warp), fused elimination steps
 #   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
 #   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
@@ -43,6 +44,7 @@ PATHS = {
     "tree-hbm-s16": (16, 0, 0, 0, 2, 1),
     "tree-hbm-s8j2": (8, 0, 2, 0, 2, 8),
     "tree-hbm-s4j4": (4, 0, 4, 0, 2, 0),
+    "tree-hbm-s32j4": (32, 0, 4, 0, 2, 0),
     "resident-s8": (8, 0, 1, 0, 1, 8),
     "resident-s32j2": (32, 2, 2, 0, 1, 0),
     "flat": (-1, 0, 0, 0, 0, 0),
