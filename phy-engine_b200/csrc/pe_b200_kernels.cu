@@ -269,13 +269,13 @@ namespace
         __syncthreads();
 
         double t = r.t0;
-        auto run_section = [&](int sec, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
+        auto run_section = [&](int sec, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J], bool first_iter)
         {
             warp_reader rd;
             rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), r.words + __ldg(r.sec_off + (3 + sec) * n_warps + warp), c.C, c.col, tid & 31u);
             for(;;)
             {
-                int const k = rvop<J>(rd, c, t, tol, en, check, nconv, fail);
+                int const k = rvop<J>(rd, c, t, tol, en, check, nconv, fail, first_iter);
                 if(k == V_END || k == V_BAD) { break; }
                 if(k == V_BAR)
                 {
@@ -297,7 +297,7 @@ namespace
             bool a[J], b[J];
 #pragma unroll
             for(int j = 0; j < J; ++j) { a[j] = b[j] = false; }
-            run_section(0, ok, false, a, b);
+            run_section(0, ok, false, a, b, true);
         }
         for(int32_t s = 0; s < r.n_steps; ++s)
         {
@@ -309,7 +309,7 @@ namespace
                     bool a[J], b[J];
 #pragma unroll
                     for(int j = 0; j < J; ++j) { a[j] = b[j] = false; }
-                    run_section(1, ok, false, a, b);
+                    run_section(1, ok, false, a, b, true);
                 }
                 t = t + r.dt;
             }
@@ -332,7 +332,7 @@ namespace
                     nconv[j] = fail[j] = false;
                     en[j] = !done[j];
                 }
-                run_section(2, en, r.nonlinear != 0, nconv, fail);
+                run_section(2, en, r.nonlinear != 0, nconv, fail, it == 0);
 #pragma unroll
                 for(int j = 0; j < J; ++j)
                 {
@@ -929,6 +929,11 @@ namespace
                         }
                         if(op == PE_OP_CAP_STEP)
                         {
+                            if((h & 0x2000u) && it > 0)  // folded time-step update: first Newton iteration only
+                            {
+                                rd.adv(8u);
+                                continue;
+                            }
                             // [h][mask][hist][prev_g][C][dt][va][vb]  (capacitor.h:106-128)
                             double* const ph = at(rd.lo(2) & 0x7fffu);
                             double* const pg = at(rd.lo(3) & 0x7fffu);
@@ -970,7 +975,7 @@ namespace
                         c.stream = warp;
                         c.js = 32;
                         tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
-                        int const k = rvop<J, line_reader, false>(rd, c, t, tol, en, check, nconv, fail);
+                        int const k = rvop<J, line_reader, false>(rd, c, t, tol, en, check, nconv, fail, it == 0);
                         if(k == V_END || k == V_BAD) { break; }
                         if(k == V_BAR)
                         {

@@ -189,7 +189,7 @@ namespace pe_rinterp
     // On the GPU every thread of the warp consumes every row of the op before any divergence (the reader is
     // warp-cooperative); an idle column then simply does not store.
     template <int J, class R, bool FUSED = true>
-    PE_HD int rvop(R& rd, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J])
+    PE_HD int rvop(R& rd, rctx const& c, double t, tol_t const& tol, bool const (&en)[J], bool check, bool (&nconv)[J], bool (&fail)[J], bool first_iter = true)
     {
         uint32_t const h = rd.head();
         uint32_t const op = h & 0xffu;
@@ -437,6 +437,8 @@ namespace pe_rinterp
             return V_BAD;
         }
         rd.open(rows);
+        // a time-step update folded into the iter section (header bit 13) runs in the first Newton iteration only
+        if((h & 0x2000u) && !first_iter) { return V_OK; }
         uint32_t ow[13];
 #if defined(__CUDACC__)
 #pragma unroll

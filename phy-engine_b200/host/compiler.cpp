@@ -1601,10 +1601,133 @@ namespace pe_b200
                     }
                 };
                 if(!cplx) { deal(prep_ops, 0, 0); }
-                deal(ps.step, 1, 0);
                 deal(ps.head, 2, 0);
+                bool const merge_step{in.merge_step && !ps.step.empty()};
+                bool step_left{false};
+                if(merge_step)
+                {
+                    // update_tr_step (circuit.h:363-374) folded into the elimination sweep: the companion update of an
+                    // element runs right before the first op of its stream that reads what it writes (first Newton iteration
+                    // of the time step only), so the fresh history / conductance is consumed from L1 instead of being
+                    // written in a separate section and fetched back from DRAM hundreds of ops later
+                    auto reads_any = [&](rop const& o, std::vector<std::uint32_t> const& keys) -> bool
+                    {
+                        auto hit = [&](std::uint32_t k) { return std::find(keys.begin(), keys.end(), k & ~NEG) != keys.end(); };
+                        auto one = [&](rop const& d) -> bool
+                        {
+                            if(d.opcode == PE_OP_DOT || d.opcode == PE_OP_CDOT)
+                            {
+                                for(auto k: d.sre)
+                                {
+                                    if(hit(k)) { return true; }
+                                }
+                                for(auto k: d.sim)
+                                {
+                                    if(hit(k)) { return true; }
+                                }
+                                for(auto const& [a, b]: d.pp)
+                                {
+                                    if(hit(a) || hit(b)) { return true; }
+                                }
+                                return (d.flags & PE_F_SCALE) && hit(d.scale);
+                            }
+                            for(auto k: d.opnd)
+                            {
+                                if(hit(k)) { return true; }
+                            }
+                            return false;
+                        };
+                        if(o.opcode == PE_OP_CROUT2)
+                        {
+                            for(auto const& sb: o.sub)
+                            {
+                                if(one(sb)) { return true; }
+                            }
+                            return false;
+                        }
+                        return one(o);
+                    };
+                    // what the head phase (device evaluation, sources: phase 0 of every stream) reads and writes: an update
+                    // whose outputs it reads, or whose inputs it writes (PN_STEP <-> PN_EVAL), keeps its place in the step
+                    // section, which runs before the Newton loop
+                    std::vector<std::uint32_t> head_reads, head_writes;
+                    for(auto const& rs: RS)
+                    {
+                        for(auto const& o: rs.sec[2][0])
+                        {
+                            int const no{value_op_outputs(o.opcode)};
+                            for(std::size_t k{}; k < o.opnd.size(); ++k)
+                            {
+                                (static_cast<int>(k) < no ? head_writes : head_reads).push_back(o.opnd[k] & ~NEG);
+                                if(static_cast<int>(k) < no) { head_reads.push_back(o.opnd[k] & ~NEG); }  // in/out operands
+                            }
+                        }
+                    }
+                    auto in_list = [](std::vector<std::uint32_t> const& v, std::uint32_t k) { return std::find(v.begin(), v.end(), k) != v.end(); };
+                    std::vector<op_t> unfolded;
+                    std::size_t rr{};
+                    for(auto const& o: ps.step)
+                    {
+                        rop r;
+                        r.opcode = o.w[0];
+                        r.opnd.assign(o.w.begin() + 1, o.w.end());
+                        r.first_only = 1;
+                        std::vector<std::uint32_t> outs;
+                        for(int k{}; k < value_op_outputs(r.opcode) && k < static_cast<int>(r.opnd.size()); ++k) { outs.push_back(r.opnd[static_cast<std::size_t>(k)] & ~NEG); }
+                        bool clash{false};
+                        for(std::size_t k{}; k < r.opnd.size(); ++k)
+                        {
+                            std::uint32_t const key{r.opnd[k] & ~NEG};
+                            bool const is_out{static_cast<int>(k) < value_op_outputs(r.opcode)};
+                            clash = clash || (is_out && in_list(head_reads, key)) || in_list(head_writes, key);
+                        }
+                        if(clash)
+                        {
+                            unfolded.push_back(o);
+                            continue;
+                        }
+                        int sj{static_cast<int>(rr % static_cast<std::size_t>(S))}, ph{0};
+                        if(o.aff >= 0 && o.aff < n)
+                        {
+                            int const node{tree.region[static_cast<std::size_t>(o.aff)]};
+                            sj = node_stream(node);
+                            ph = fwd_phase(node);
+                        }
+                        else
+                        {
+                            ++rr;
+                        }
+                        auto& lst{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(ph)]};
+                        std::size_t pos{lst.size()};
+                        for(std::size_t q{}; q < lst.size(); ++q)
+                        {
+                            if(reads_any(lst[q], outs))
+                            {
+                                pos = q;
+                                break;
+                            }
+                        }
+                        if(pos == lst.size() && ph != 0)
+                        {
+                            // nobody in that phase reads it (a consumer on another stream or level): the head phase
+                            // precedes every reader
+                            RS[static_cast<std::size_t>(sj)].sec[2][0].push_back(std::move(r));
+                        }
+                        else
+                        {
+                            lst.insert(lst.begin() + static_cast<std::ptrdiff_t>(pos), std::move(r));
+                        }
+                    }
+                    deal(unfolded, 1, 0);
+                    step_left = !unfolded.empty();
+                }
+                else
+                {
+                    deal(ps.step, 1, 0);
+                    step_left = !ps.step.empty();
+                }
                 pr.has_sec[0] = !cplx && !prep_ops.empty();
-                pr.has_sec[1] = !ps.step.empty();
+                pr.has_sec[1] = step_left;
                 pr.has_sec[2] = true;
 
                 // ---- global alignment: within every phase the S op lists are merged position by position (greedy on
@@ -1612,7 +1735,7 @@ namespace pe_b200
                 // position, which is what makes their operand rows warp-uniform after the relative slot encoding below.
                 auto signature = [](rop const& o) -> std::uint64_t
                 {
-                    return (static_cast<std::uint64_t>(o.opcode) << 56) ^ (static_cast<std::uint64_t>(o.flags) << 48) ^ (static_cast<std::uint64_t>(o.sre.size()) << 36) ^
+                    return (static_cast<std::uint64_t>(o.opcode) << 56) ^ (static_cast<std::uint64_t>(o.flags | (o.first_only ? 0x80u : 0u)) << 48) ^ (static_cast<std::uint64_t>(o.sre.size()) << 36) ^
                            (static_cast<std::uint64_t>(o.sim.size()) << 24) ^ (static_cast<std::uint64_t>(o.pp.size()) << 12) ^ static_cast<std::uint64_t>(o.opnd.size());
                 };
                 for(int sec{}; sec < 3; ++sec)
@@ -2756,7 +2879,7 @@ namespace pe_b200
                             {
                                 if(o) { nr = std::max(nr, o->opnd.size()); }
                             }
-                            h0 = opc | (static_cast<std::uint32_t>(nr) << 8);
+                            h0 = opc | (static_cast<std::uint32_t>(nr) << 8) | (any->first_only ? 0x2000u : 0u);  // bit 13: first Newton iteration only
                             for(std::size_t r{}; r < nr; ++r)
                             {
                                 rows.emplace_back(static_cast<std::size_t>(C));

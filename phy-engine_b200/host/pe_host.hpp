@@ -158,6 +158,7 @@ namespace pe_b200
         std::uint32_t opcode{};
         std::uint32_t flags{};
         std::uint8_t bubble{};  // no op for this stream at this (globally aligned) position
+        std::uint8_t first_only{};  // a time-step update folded into the iter section: runs in the first Newton iteration only
         std::uint32_t dst{}, scale{};                               // shared-memory slots
         // operand words are stream-relative: row * S + ((column - stream) mod S), | neg << 15 for sources
         std::vector<std::uint32_t> sre, sim;
@@ -231,6 +232,7 @@ namespace pe_b200
         int resident_real{0};  // > 0: build the real-valued programs in resident form with this many streams
         int resident_ac{0};    // > 0: ... the AC program
         bool fuse_steps{false};  // resident programs: emit small elimination steps as one fused op
+        bool merge_step{true};   // resident programs: fold the per-time-step companion updates into the iter section
     };
 
     // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot

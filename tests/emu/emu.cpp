@@ -314,7 +314,7 @@ namespace
 
             // one section: warps advance phase by phase; within a phase thread after thread (no cross-thread
             // dependency may exist inside a phase: the race detector checks exactly that)
-            auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 4>>& nconv, std::vector<std::array<bool, 4>>& fail)
+            auto run_section = [&](int sec, bool use_done, bool check, std::vector<std::array<bool, 4>>& nconv, std::vector<std::array<bool, 4>>& fail, bool first_iter)
             {
                 std::vector<host_reader> rdw(W);
                 for(uint32_t w = 0; w < W; ++w)
@@ -355,7 +355,7 @@ namespace
                                 }
                                 host_reader rd = rdw[w];
                                 rd.col = c.col;
-                                kind = rvop<J>(rd, c, t, tol, en, check, nc, fl);
+                                kind = rvop<J>(rd, c, t, tol, en, check, nc, fl, first_iter);
                                 if(kind == V_OK) { rd.close(); }
                                 if(kind == V_BAR) { rd.bar(); }
                                 if(kind == V_SKIP) { rd.skip(); }
@@ -408,7 +408,7 @@ namespace
             if(r.has_prep && first_chunk)
             {
                 clear_flags();
-                run_section(0, false, false, nconv, fail);
+                run_section(0, false, false, nconv, fail, true);
             }
             for(int32_t s = s_begin; s < s_end; ++s)
             {
@@ -417,7 +417,7 @@ namespace
                     if(r.has_step)
                     {
                         clear_flags();
-                        run_section(1, false, false, nconv, fail);
+                        run_section(1, false, false, nconv, fail, true);
                     }
                     t = t + r.dt;
                 }
@@ -431,7 +431,7 @@ namespace
                 {
                     for(uint32_t i = 0; i < 128; ++i) { s_flags[fi][i] = 0; }
                     clear_flags();
-                    run_section(2, true, r.nonlinear != 0, nconv, fail);
+                    run_section(2, true, r.nonlinear != 0, nconv, fail, it == 0);
                     for(uint32_t tid = 0; tid < T; ++tid)
                     {
                         uint32_t const ig = tid % IG;
