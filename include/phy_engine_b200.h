@@ -198,6 +198,12 @@ extern "C"
     int circuit_batch_status(void* batch, int32_t* status);    /* [lanes] 0 ok, 1 no convergence, 2 singular */
     int circuit_batch_newton_iters(void* batch, uint32_t* n);  /* [lanes] solves per lane */
     int circuit_batch_waveform(void* batch, double* w);        /* [steps][n_probes][n_instances] */
+    /* mixed-signal boundary, analog -> digital: the update_digital_clk of every comparator (element 19) of the netlist,
+     * vA >= vB (controller/comparator.h:73-108), for every instance, on the device; states [n_instances][n_comparators]
+     * in element order.  Digital logic behind the comparators stays with the caller. */
+    int circuit_batch_digital_clk(void* batch);
+    size_t circuit_batch_comparator_count(void* batch);
+    int circuit_batch_comparator_states(void* batch, uint8_t* states);
     /* program statistics for roofline accounting: mode 0 DC/OP, 1 TR, 2 TROP, 3 AC */
     int circuit_batch_stats(void* batch, int mode, size_t* n_unknowns, size_t* nnz_a, size_t* nnz_lu, size_t* n_fma, size_t* n_lane_slots, size_t* n_inst_slots);
     /* HBM-resident access: device row of a swept parameter (n_instances doubles) and of the real solution

@@ -1084,6 +1084,19 @@ namespace
         if constexpr(CL == 2) { group_sync<CL>(); }  // neither CTA leaves while the other may still read its shared memory
     }
 
+    // mixed-signal boundary, analog -> digital (controller/comparator.h:88-101): one thread per (comparator, lane)
+    __global__ void pe_b200_compare_kernel(double const* __restrict__ x, int64_t LS, int32_t n_lanes, int32_t const* __restrict__ ab, int32_t n_cmp,
+                                           uint8_t* __restrict__ out)
+    {
+        int64_t const lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int32_t const cmp = (int32_t)blockIdx.y;
+        if(lane >= n_lanes || cmp >= n_cmp) { return; }
+        int32_t const a = __ldg(ab + 2 * cmp), b = __ldg(ab + 2 * cmp + 1);
+        double const va = a < 0 ? 0.0 : x[(int64_t)a * LS + lane];
+        double const vb = b < 0 ? 0.0 : x[(int64_t)b * LS + lane];
+        out[(int64_t)cmp * LS + lane] = va >= vb ? 1 : 0;
+    }
+
     thread_local char g_err[256] = "";
     std::atomic<uint64_t> g_launches{0};
 
@@ -1310,6 +1323,15 @@ extern "C"
         }
         g_launches.fetch_add(1);
         return chk(cudaGetLastError(), "pe_b200_resident_kernel launch");
+    }
+
+    int pe_b200_compare(double const* x, int64_t LS, int32_t n_lanes, int32_t const* ab, int32_t n_cmp, uint8_t* out, void* stream)
+    {
+        if(n_lanes <= 0 || n_cmp <= 0) { return 0; }
+        dim3 const grid((unsigned)((n_lanes + 255) / 256), (unsigned)n_cmp);
+        pe_b200_compare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, LS, n_lanes, ab, n_cmp, out);
+        g_launches.fetch_add(1);
+        return chk(cudaGetLastError(), "pe_b200_compare_kernel launch");
     }
 
     void pe_b200_timing_enable(int on) { g_timing = on != 0; }

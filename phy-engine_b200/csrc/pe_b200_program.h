@@ -266,6 +266,9 @@ extern "C"
     int pe_b200_dev_h2d_2d(void* dst, size_t dpitch, void const* src, size_t spitch, size_t width, size_t height, void* stream);
     int pe_b200_dev_d2h_2d(void* dst, size_t dpitch, void const* src, size_t spitch, size_t width, size_t height, void* stream);
     int pe_b200_launch(pe_b200_run const* run, void* stream);
+    // analog -> digital boundary: out[c * LS + lane] = (x[a_c][lane] >= x[b_c][lane]) for the comparators c (ab = pairs of
+    // unknown indices, -1 = ground = 0 V), x = lane-interleaved solution rows x[unknown * LS + lane]
+    int pe_b200_compare(double const* x, int64_t LS, int32_t n_lanes, int32_t const* ab, int32_t n_cmp, uint8_t* out, void* stream);
     int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream);
     // largest dynamic shared memory (bytes) one CTA of the resident kernel may use on the current device
     size_t pe_b200_resident_smem_limit(void);

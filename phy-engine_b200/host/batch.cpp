@@ -759,6 +759,55 @@ namespace pe_b200
         return true;
     }
 
+    bool batch::digital_clk()
+    {
+        if(!cc || d_wi.p == nullptr)
+        {
+            error = "digital_clk: analyze first";
+            set_last_error(error);
+            return false;
+        }
+        // comparators in element order; pin unknowns: -1 ground / no analog node (reads 0 V like an unconnected node)
+        std::vector<std::int32_t> ab;
+        auto const& nl{parent->nl};
+        for(auto const& e: nl.elems)
+        {
+            if(e.d->code != E_CMP) { continue; }
+            for(int p{}; p < 2; ++p)
+            {
+                int const node{e.pin_node[p]};
+                int const u{node < 0 ? -1 : cc->num.node_index[static_cast<std::size_t>(node)]};
+                ab.push_back(u < 0 ? -1 : u);
+            }
+        }
+        n_cmp = ab.size() / 2;
+        if(n_cmp == 0) { return true; }
+        if(!d_cmp_idx.ensure(ab.size() * 4) || !d_cmp_out.ensure(n_cmp * static_cast<std::size_t>(LSi))) { return dev_fail(error, "alloc comparator buffers"); }
+        if(pe_b200_dev_h2d(d_cmp_idx.p, ab.data(), ab.size() * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "upload comparator table"); }
+        if(pe_b200_compare(static_cast<double const*>(d_wi.p), LSi, static_cast<std::int32_t>(n_inst), static_cast<std::int32_t const*>(d_cmp_idx.p),
+                           static_cast<std::int32_t>(n_cmp), static_cast<std::uint8_t*>(d_cmp_out.p), stream) != 0)
+        {
+            return dev_fail(error, "comparator kernel");
+        }
+        return true;
+    }
+
+    bool batch::get_comparator_states(std::uint8_t* out)
+    {
+        if(n_cmp == 0) { return true; }
+        if(d_cmp_out.p == nullptr) { return false; }
+        std::vector<std::uint8_t> tmp(n_cmp * n_inst);
+        if(pe_b200_dev_d2h_2d(tmp.data(), n_inst, d_cmp_out.p, static_cast<std::size_t>(LSi), n_inst, n_cmp, stream) != 0 || pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "download comparator states");
+        }
+        for(std::size_t c{}; c < n_cmp; ++c)
+        {
+            for(std::size_t i{}; i < n_inst; ++i) { out[i * n_cmp + c] = tmp[c * n_inst + i]; }
+        }
+        return true;
+    }
+
     bool batch::get_wave(double* w)
     {
         if(probes.empty() || wave_steps == 0 || d_wave.p == nullptr) { return false; }

@@ -727,6 +727,12 @@ extern "C"
 
     int circuit_batch_newton_iters(void* bp, uint32_t* n) { return (bp && n && static_cast<batch*>(bp)->get_solves(n)) ? 0 : 1; }
 
+    int circuit_batch_digital_clk(void* bp) { return (bp && static_cast<batch*>(bp)->digital_clk()) ? 0 : 1; }
+
+    size_t circuit_batch_comparator_count(void* bp) { return bp ? static_cast<batch*>(bp)->n_cmp : 0; }
+
+    int circuit_batch_comparator_states(void* bp, uint8_t* out) { return (bp && out && static_cast<batch*>(bp)->get_comparator_states(out)) ? 0 : 1; }
+
     int circuit_batch_waveform(void* bp, double* w) { return (bp && w && static_cast<batch*>(bp)->get_wave(w)) ? 0 : 1; }
 
     int circuit_batch_stats(void* bp, int mode, size_t* n_unknowns, size_t* nnz_a, size_t* nnz_lu, size_t* n_fma, size_t* n_lane_slots, size_t* n_inst_slots)

@@ -35,6 +35,8 @@ namespace pe_b200
              9,
              true},
             {E_OPAMP, "OpAmp", 4, 1, 1, {"mu"}, {1.0e5}, 1, false},
+            // pins A, B (analog inputs), o (digital output): no MNA stamp; its state is vA >= vB at digital_clk (comparator.h:73-108)
+            {E_CMP, "Comparator", 3, 0, 2, {"Ll", "Hl"}, {0.0, 5.0}, 2, false, true},
             {E_NPN, "NPN BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},
             {E_PNP, "PNP BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},
             {E_NMOS, "NMOSFET", 3, 0, 3, {"Kp", "lambda", "Vth"}, {1e-3, 0.0, 1.0}, 3, true},
@@ -148,6 +150,7 @@ namespace pe_b200
         std::vector<int> analog_pins(static_cast<std::size_t>(nl.n_created_nodes), 0);
         for(auto const& e: nl.elems)
         {
+            if(e.d->digital) { continue; }  // pins of digital models do not make a node analog (circuit.h:481-540)
             for(int p{}; p < e.d->pins; ++p)
             {
                 if(e.pin_node[p] >= 0) { ++analog_pins[static_cast<std::size_t>(e.pin_node[p])]; }

@@ -35,6 +35,7 @@ namespace pe_b200
         E_SWITCH = 12,
         E_PN = 13,
         E_OPAMP = 17,
+        E_CMP = 19,  // comparator: the analog -> digital boundary (controller/comparator.h)
         E_NPN = 50,
         E_PNP = 51,
         E_NMOS = 52,
@@ -74,6 +75,7 @@ namespace pe_b200
         double attr_default[k_max_attr];
         int n_cabi_props;  // how many doubles create_circuit() consumes (dll_main.cpp:1707-1956)
         bool nonlinear;    // model_device_type::non_linear
+        bool digital{false};  // model_device_type::digital: its pins are not analog pins (no node numbering, no stamps)
     };
 
     elem_desc const* find_desc(int code) noexcept;
@@ -333,6 +335,12 @@ namespace pe_b200
         bool get_status(std::int32_t* st /* [lanes] */);
         bool get_solves(std::uint32_t* sv /* [lanes] */);
         bool get_wave(double* w /* [steps][probes][n_inst] */);
+        // mixed-signal boundary, analog -> digital: update_digital_clk of every comparator of the netlist (vA >= vB,
+        // controller/comparator.h:73-108) for every instance, on the device
+        device_buf d_cmp_idx, d_cmp_out;
+        std::size_t n_cmp{};
+        bool digital_clk();
+        bool get_comparator_states(std::uint8_t* out /* [n_inst][n_cmp] */);
     };
 
     struct circuit

@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libphyengine_b200.so")
 
 # phy_engine_element_code (dll_api.h:51-135), in-scope subset
 GROUND, R, C, L, VDC, VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, SWITCH, PN = range(14)
+COMPARATOR = 19  # pins A, B (analog), o (digital output); properties Ll, Hl
 OPAMP = 17
 NPN, PNP, NMOS, PMOS = 50, 51, 52, 53
 BRIDGE = 54  # full bridge rectifier (pins A, B, +, -)
@@ -31,11 +32,11 @@ SWEEP_SINGLE, SWEEP_LINEAR, SWEEP_LOG = range(3)
 MODE_DC, MODE_TR, MODE_TROP, MODE_AC = range(4)
 
 PROPS = {GROUND: 0, R: 1, C: 1, L: 1, VDC: 1, VAC: 3, IDC: 1, IAC: 3, VCCS: 1, VCVS: 1, CCCS: 1, CCVS: 1, SWITCH: 1,
-         PN: 9, OPAMP: 1, NPN: 5, PNP: 5, NMOS: 3, PMOS: 3, BRIDGE: 0}
+         PN: 9, OPAMP: 1, NPN: 5, PNP: 5, NMOS: 3, PMOS: 3, BRIDGE: 0, COMPARATOR: 2}
 PINS = {GROUND: 1, R: 2, C: 2, L: 2, VDC: 2, VAC: 2, IDC: 2, IAC: 2, VCCS: 4, VCVS: 4, CCCS: 4, CCVS: 4, SWITCH: 2,
-        PN: 2, OPAMP: 4, NPN: 3, PNP: 3, NMOS: 3, PMOS: 3, BRIDGE: 4}
+        PN: 2, OPAMP: 4, NPN: 3, PNP: 3, NMOS: 3, PMOS: 3, BRIDGE: 4, COMPARATOR: 3}
 BRANCHES = {GROUND: 0, R: 0, C: 0, L: 1, VDC: 1, VAC: 1, IDC: 0, IAC: 0, VCCS: 0, VCVS: 1, CCCS: 1, CCVS: 2, SWITCH: 1,
-            PN: 0, OPAMP: 1, NPN: 0, PNP: 0, NMOS: 0, PMOS: 0, BRIDGE: 0}
+            PN: 0, OPAMP: 1, NPN: 0, PNP: 0, NMOS: 0, PMOS: 0, BRIDGE: 0, COMPARATOR: 0}
 # defaults of the PN junction's 9 positional properties (PN_junction.h:22-33): Is N Isr Nr Temp Ibv Bv Bv_set Area
 PN_DEFAULT = (1e-14, 1.0, 0.0, 2.0, 27.0, 1e-3, 40.0, 1.0, 1.0)
 
@@ -229,6 +230,10 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_uint]
     lib.circuit_batch_set_tuning.argtypes = [V, ct.c_uint]
     lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
+    lib.circuit_batch_digital_clk.argtypes = [V]
+    lib.circuit_batch_comparator_count.restype = _SZ
+    lib.circuit_batch_comparator_count.argtypes = [V]
+    lib.circuit_batch_comparator_states.argtypes = [V, ct.POINTER(ct.c_uint8)]
     lib.circuit_batch_set_chunks.argtypes = [V, ct.c_int]
     lib.circuit_batch_resident_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
     for f in ("circuit_batch_prepare", "circuit_batch_reset_state", "circuit_batch_analyze", "circuit_batch_compile_host"):
@@ -371,6 +376,14 @@ class Batch:
     def set_tuning(self, flags: int):
         """bit 0 L2 operand prefetch, bit 1 two lines ahead, bit 2 no L1 re-fetch of results, bit 3 fused elimination steps"""
         self._rc(self.lib.circuit_batch_set_tuning(self.h, flags), "circuit_batch_set_tuning")
+
+    def digital_clk(self) -> np.ndarray:
+        """comparator states [n_instances, n_comparators] (vA >= vB) after the last analyze()"""
+        self._rc(self.lib.circuit_batch_digital_clk(self.h), "circuit_batch_digital_clk")
+        n = int(self.lib.circuit_batch_comparator_count(self.h))
+        out = np.zeros((self.n_inst, max(n, 1)), dtype=np.uint8)
+        self._rc(self.lib.circuit_batch_comparator_states(self.h, out.ctypes.data_as(ct.POINTER(ct.c_uint8))), "circuit_batch_comparator_states")
+        return out[:, :n]
 
     def resident_info(self, mode: int) -> dict:
         v = (ct.c_int64 * 13)()

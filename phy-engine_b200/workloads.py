@@ -287,3 +287,28 @@ def linear_zoo(vac: bool = False):
     nl.wire(iac, 1, l1, 1)
     return nl, {"src": src, "R": [r1, r2, r3, r4, r5, r6, r7, r8, ri, rf, rl, r9, r10, r11], "G": gm, "E": ev, "F": fc, "H": hv, "OA": oa, "L": l1, "C": c1, "IDC": idc,
                 "IAC": iac}
+
+
+def flash_adc(levels: int = 16, vref: float = 5.0, r: float = 1e3):
+    """Config E shape (test/0028.16b_adc): Vref across `levels` equal resistors (levels taps incl. the top), an input
+    source Vin, and levels - 1 comparators (A = vin, B = tap k, output on a pure digital node).
+    17 analog nodes + 2 source branches = 19 unknowns for levels = 16."""
+    nl = Netlist()
+    g = nl.ground()
+    vr = nl.add(pe.VDC, vref)
+    vin = nl.add(pe.VDC, 2.5)
+    nl.wire(vr, 1, g, 0)
+    nl.wire(vin, 1, g, 0)
+    rs = [nl.add(pe.R, r) for _ in range(levels)]
+    nl.wire(rs[0], 0, g, 0)
+    for k in range(1, levels):
+        nl.wire(rs[k - 1], 1, rs[k], 0)  # tap k
+    nl.wire(rs[-1], 1, vr, 0)
+    cmps = []
+    for k in range(1, levels):
+        cm = nl.add(pe.COMPARATOR, 0.0, 5.0)
+        nl.wire(cm, 0, vin, 0)
+        nl.wire(cm, 1, rs[k], 0)  # tap k = junction of rs[k-1] and rs[k]
+        nl.wire(cm, 2, cm, 2)  # a net of its own for the output pin: a pure digital node
+        cmps.append(cm)
+    return nl, {"Vref": vr, "Vin": vin, "R": rs, "CMP": cmps}

@@ -149,6 +149,21 @@ extern "C"
 
     size_t pe_b200_resident_smem_limit(void) { return 227 * 1024 - 1024; }
 
+    int pe_b200_compare(double const* x, int64_t LS, int32_t n_lanes, int32_t const* ab, int32_t n_cmp, uint8_t* out, void*)
+    {
+        for(int32_t c = 0; c < n_cmp; ++c)
+        {
+            for(int64_t l = 0; l < n_lanes; ++l)
+            {
+                double const va = ab[2 * c] < 0 ? 0.0 : x[(int64_t)ab[2 * c] * LS + l];
+                double const vb = ab[2 * c + 1] < 0 ? 0.0 : x[(int64_t)ab[2 * c + 1] * LS + l];
+                out[(int64_t)c * LS + l] = va >= vb ? 1 : 0;
+            }
+        }
+        ++g_launches;
+        return 0;
+    }
+
     uint64_t pe_emu_resident_launches(void);
     uint64_t pe_emu_races(void) { return emu_trace::g_races; }
     uint64_t pe_emu_unbalanced_barriers(void) { return g_unbalanced; }

@@ -1,0 +1,98 @@
+"""Mixed-signal boundary, analog -> digital (SURVEY.md 8a row a16, config E shape): the comparators of a flash ADC,
+evaluated for every instance on the device (circuit_batch_digital_clk), against (1) the reference's own
+update_digital_clk through its C ABI on a few instances and (2) the comparator rule vA >= vB applied to the reference's
+analog solution for the whole batch.  Bit-exact."""
+import ctypes as ct
+
+import numpy as np
+import pytest
+
+import pe_b200 as pe
+import refapi
+import workloads as wl
+from test_parity import PATHS, assert_close
+
+
+@pytest.fixture(params=[pytest.param("gpu", marks=pytest.mark.gpu), "emu"])
+def abi(request):
+    if request.param == "gpu":
+        return pe.product()
+    import emuapi
+
+    return emuapi.emulator()
+
+
+def reference_comparator_bits(nl, info, vin, r_vals):
+    """the reference's digital states of the comparator outputs for ONE instance: circuit_analyze (DC) + circuit_digital_clk
+    + circuit_sample_digital_state_u8 (dll_api.h:220-235)"""
+    c = refapi.RefCircuit(nl)
+    c.set_analyze_type(pe.DC)
+    assert c.set_param(info["Vin"], "V", float(vin)) == 0
+    for e, v in zip(info["R"], r_vals):
+        assert c.set_param(e, "r", float(v)) == 0
+    assert c.analyze()
+    lib = c.abi.lib
+    lib.circuit_digital_clk.argtypes = [ct.c_void_p]
+    assert lib.circuit_digital_clk(c.h) == 0
+    SZ, PSZ, PD = ct.c_size_t, ct.POINTER(ct.c_size_t), ct.POINTER(ct.c_double)
+    lib.circuit_sample_digital_state_u8.argtypes = [ct.c_void_p, PSZ, PSZ, SZ, PD, PSZ, PD, PSZ, ct.POINTER(ct.c_uint8), PSZ]
+    n = c.comp_size
+    vo, co, dg = (SZ * (n + 1))(), (SZ * (n + 1))(), (SZ * (n + 1))()
+    volt, cur, dig = (ct.c_double * 256)(), (ct.c_double * 64)(), (ct.c_uint8 * 256)()
+    assert lib.circuit_sample_digital_state_u8(c.h, c._vp, c._cp, n, volt, vo, cur, co, dig, dg) == 0
+    bits = []
+    for cm in info["CMP"]:
+        k = nl.component_index(cm)
+        bits.append(int(dig[dg[k] + 2]))  # pin o of the comparator: 0 false, 1 true (2 X, 3 Z)
+    return np.array(bits, dtype=np.uint8)
+
+
+def test_flash_adc_comparators_match_the_reference(ref, abi):
+    n_inst = 257
+    nl, info = wl.flash_adc(16)
+    rng = np.random.default_rng(31)
+    vin = rng.uniform(0.0, 5.0, n_inst)
+    r_vals = [1e3 * rng.uniform(0.97, 1.03, n_inst) for _ in info["R"]]
+    over = [(info["Vin"], "V", vin)] + [(e, "r", v) for e, v in zip(info["R"], r_vals)]
+    want = refapi.run_batch(nl, pe.DC, n_inst, over)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.DC)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    x = b.solution()
+    assert x.shape[1] == 19  # 17 analog nodes + 2 source branches: the comparator pins add none
+    assert_close(x, want["x"].real, "adc ladder")
+    bits = b.digital_clk()
+    assert bits.shape == (n_inst, 15)
+    # (2) the comparator rule on the reference's analog solution, whole batch
+    vin_u = c.pin_unknown(info["Vin"], 0)
+    taps = [c.pin_unknown(info["R"][k], 0) for k in range(1, 16)]
+    expect = (want["x"].real[:, [vin_u]] >= want["x"].real[:, taps]).astype(np.uint8)
+    assert (bits == expect).all()
+    # thermometer code: monotone, and its height is the quantised input
+    assert (np.diff(bits.astype(int), axis=1) <= 0).all()
+    # (1) the reference's own digital engine on a few instances
+    for i in (0, 1, 100, n_inst - 1):
+        rb = reference_comparator_bits(nl, info, vin[i], [v[i] for v in r_vals])
+        assert (rb == bits[i]).all(), (i, rb, bits[i])
+
+
+@pytest.mark.gpu
+def test_flash_adc_full_size_4096_instances():
+    nl, info = wl.flash_adc(16)
+    n_inst = 4096
+    rng = np.random.default_rng(5)
+    vin = rng.uniform(0.0, 5.0, n_inst)
+    c = pe.Circuit(nl)
+    c.set_analyze_type(pe.DC)
+    b = c.batch(n_inst)
+    b.set_param(info["Vin"], "V", vin)
+    assert b.analyze()
+    bits = b.digital_clk()
+    # nominal ladder: tap k = 5 k / 16 V (random inputs: no tie within 1e-9)
+    expect = (vin[:, None] >= 5.0 * np.arange(1, 16)[None, :] / 16.0).astype(np.uint8)
+    safe = np.abs(vin[:, None] - 5.0 * np.arange(1, 16)[None, :] / 16.0).min(axis=1) > 1e-9
+    assert (bits[safe] == expect[safe]).all()
