@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--resident", default="0,0,0", help="streams,instances_per_cta,instances_per_thread of the resident kernel (0 = automatic, streams -1 = HBM-streaming kernel)")
     ap.add_argument("--workspace", type=int, default=0, help="0 = automatic, 1 = shared memory (resident kernel), 2 = HBM (tree-streaming kernel)")
     ap.add_argument("--chunks", type=int, default=0, help="tree-streaming kernel: chunks of the time loop (0 = automatic, 1 = static scheduling)")
-    ap.add_argument("--tuning", type=int, default=0, help="circuit_batch_set_tuning flags (bit 0/1 L2 prefetch, bit 2 no L1 re-fetch, bit 3 fused elimination steps)")
+    ap.add_argument("--tuning", type=int, default=0, help="circuit_batch_set_tuning flags (bit 0/1 L2 prefetch, bit 2 no L1 re-fetch, bit 3 fused elimination steps, bit 4 require / bit 5 forbid the specialised kernel)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -292,11 +292,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     rinfo = b.resident_info(pe.MODE_TR)
+    specialised = b.last_kernel() == 1  # the run-time specialised tree-streaming kernel (host/jit.cpp) ran
     kernel_name = ("pe_b200_tree_kernel" if rinfo["hbm"] else "pe_b200_resident_kernel") if rinfo["resident"] else "pe_b200_solve_kernel"
+    if specialised:
+        kernel_name = "pe_b200_jit_kernel"
     solves_per_launch = solves / max(launches, 1)
     # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r01_traffic.json), scaled to one launch
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic_jit.json" if specialised else "r01_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(kernel_name) and (rinfo["last_S"], rinfo["last_J"]) == (tj.get("S", 32), tj.get("J", 2)):
@@ -325,7 +328,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(args, 8e-9 * n_inst * (st["n_inst_slots"] + (rinfo["smem_slots"] if rinfo["hbm"] else st["n_lane_slots"]))),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "program": st, "resident": b.resident_info(pe.MODE_TR), "checksum": checksum,
+            "program": st, "resident": b.resident_info(pe.MODE_TR), "specialised_kernel": bool(specialised), "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

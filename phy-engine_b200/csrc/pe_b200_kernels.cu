@@ -22,6 +22,8 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -32,6 +34,7 @@ namespace
 {
     using namespace pe_interp;
 
+#ifndef PE_JIT
     __global__ void __launch_bounds__(32 * PE_MAX_WARPS, 2) pe_b200_solve_kernel(pe_b200_run const r)
     {
         // per-lane Newton flags of the current iteration, OR-ed in by the G warps (bit 0 not converged, bit 1 singular);
@@ -133,6 +136,8 @@ namespace
     // flight while the current one is consumed, so L2 latency never sits on the critical path of an op.
     // SIDE stream (per-column rows, C words each): every lane reads the word of its own column (one coalesced line per
     // row); the next four rows are kept in flight in a register queue.
+#endif  // PE_JIT
+
     struct warp_reader
     {
         uint32_t const* main;
@@ -211,6 +216,7 @@ namespace
         __device__ __forceinline__ void skip() { advance(((pos >> 5) + 1u) << 5); }
     };
 
+#ifndef PE_JIT
     template <int J, int MAXT>
     __global__ void __launch_bounds__(MAXT, 1) pe_b200_resident_kernel(pe_b200_rrun const r)
     {
@@ -402,6 +408,8 @@ namespace
             }
         }
     }
+
+#endif  // PE_JIT
 
     // ---- tree-streaming kernel: the tree-scheduled program with its workspace in HBM ---------------
     // CTA = S warps x 32 lanes: warp s runs word stream s (a sub-tree of the elimination tree) for the CTA's 32
@@ -741,8 +749,85 @@ namespace
         }
     }
 
-    template <int J, int MAXT, int MINB, bool FUSED, int CL>
-    __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
+#ifdef PE_JIT
+    // ---- run-time specialisation (host/jit.cpp): this file is compiled again by nvcc at run time with -DPE_JIT; the
+    // generated source (PE_JIT_SOURCE) holds the iter section of one tree-scheduled program as straight-line code --
+    // one function per (sub-tree stream, phase), operand rows addressed by constants, results of the last few ops
+    // forwarded in registers, the loads of an op issued PE_JIT_D ops ahead -- and replaces the word interpreter for that
+    // section.  Everything around it (scheduling, time / Newton loops, flags, I/O) is the code of the tree kernel below.
+    struct jv
+    {
+        double v[4];
+    };
+    __device__ __forceinline__ jv jld(char const* p)
+    {
+        jv x;
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { x.v[j] = *reinterpret_cast<double const*>(p + 256 * j); }
+        return x;
+    }
+    __device__ __forceinline__ void jst(char* p, jv const& x, uint32_t enm)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+            if((enm >> j) & 1u) { *reinterpret_cast<double*>(p + 256 * j) = x.v[j]; }
+        }
+    }
+    __device__ __forceinline__ jv jzero()
+    {
+        jv x;
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { x.v[j] = 0.0; }
+        return x;
+    }
+    // acc +/- s  (the interpreter's fma(s, +/-1.0, acc): the same single rounding)
+    __device__ __forceinline__ void jadd(jv& acc, jv const& s)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { acc.v[j] = __dadd_rn(acc.v[j], s.v[j]); }
+    }
+    __device__ __forceinline__ void jsub(jv& acc, jv const& s)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { acc.v[j] = __dsub_rn(acc.v[j], s.v[j]); }
+    }
+    // acc -/+ a b
+    __device__ __forceinline__ void jfms(jv& acc, jv const& a, jv const& b)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { acc.v[j] = __fma_rn(-a.v[j], b.v[j], acc.v[j]); }
+    }
+    __device__ __forceinline__ void jfma(jv& acc, jv const& a, jv const& b)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { acc.v[j] = __fma_rn(a.v[j], b.v[j], acc.v[j]); }
+    }
+    __device__ __forceinline__ void jmul(jv& acc, jv const& s)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { acc.v[j] = PE_MUL(acc.v[j], s.v[j]); }
+    }
+    __device__ __forceinline__ void jrcp(jv& acc, uint32_t& failm)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+            if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { failm |= 1u << j; }
+            acc.v[j] = PE_RCP(acc.v[j]);
+        }
+    }
+    // CAP_STEP (capacitor.h:106-128): hist, prev_g updated in place
+    __device__ __forceinline__ void jcap(jv const& C, jv const& dt, jv const& va, jv const& vb, jv& hist, jv& prev_g)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]); }
+    }
+#include PE_JIT_SOURCE
+#endif  // PE_JIT
+
+    template <int J, bool FUSED, int CL>
+    __device__ __forceinline__ void tree_body(pe_b200_rrun const& r)
     {
         __shared__ uint32_t s_flags[3][32 * J];
         __shared__ uint32_t s_item;
@@ -793,7 +878,13 @@ namespace
                 __syncthreads();
             }
             int64_t const glane = (int64_t)group * GL + lane;  // first of this thread's lanes; the others are + 32 j
+#ifdef PE_JIT
+            // specialised kernel: the workspace of a lane group is one block, ws[group][slot][32 J lanes] (1 KB rows whose
+            // addresses are a column base plus a load / store immediate, host/jit.cpp)
+            lane_ws const at{reinterpret_cast<char*>(r.wsg + (int64_t)group * r.n_slots * GL + lane), GL * 8u};
+#else
             lane_ws const at{reinterpret_cast<char*>(r.wsg + glane), (uint32_t)(r.LSw * 8)};
+#endif
             bool const first_chunk = chunk == 0u, last_chunk = chunk + 1u == NC;
             int32_t const s_begin = r.sched != nullptr ? (int32_t)chunk * r.chunk_steps : 0;
             int32_t const s_end = r.sched != nullptr ? min(r.n_steps, s_begin + r.chunk_steps) : r.n_steps;
@@ -885,6 +976,14 @@ namespace
                 bool nconv[J], fail[J];
 #pragma unroll
                 for(int j = 0; j < J; ++j) { nconv[j] = fail[j] = false; }
+#ifdef PE_JIT
+                if(sec == 2)
+                {
+                    pe_jit_iter<CL>(warp, at.wl, en, fail);
+                    group_sync<CL>();
+                }
+                else
+#endif
                 {
                     line_reader rd;
                     rd.init(r.words + __ldg(r.sec_off + sec * n_warps + warp), lane, warp, S);
@@ -967,8 +1066,13 @@ namespace
                         }
                         // everything else goes through the generic vector-op executor (pe_b200_rinterp.h)
                         rctx c;
+#ifdef PE_JIT
+                        c.ws = reinterpret_cast<double*>(at.wl);
+                        c.I = (uint64_t)GL;
+#else
                         c.ws = r.wsg + glane;
                         c.I = (uint64_t)r.LSw;
+#endif
                         c.S = S;
                         c.C = 1;
                         c.col = 0;
@@ -1084,6 +1188,13 @@ namespace
         if constexpr(CL == 2) { group_sync<CL>(); }  // neither CTA leaves while the other may still read its shared memory
     }
 
+#ifndef PE_JIT
+    template <int J, int MAXT, int MINB, bool FUSED, int CL>
+    __global__ void __launch_bounds__(MAXT, MINB) pe_b200_tree_kernel(pe_b200_rrun const r)
+    {
+        tree_body<J, FUSED, CL>(r);
+    }
+
     // mixed-signal boundary, analog -> digital (controller/comparator.h:88-101): one thread per (comparator, lane)
     __global__ void pe_b200_compare_kernel(double const* __restrict__ x, int64_t LS, int32_t n_lanes, int32_t const* __restrict__ ab, int32_t n_cmp,
                                            uint8_t* __restrict__ out)
@@ -1110,7 +1221,12 @@ namespace
         snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
         return 1;
     }
+#endif  // PE_JIT
 }  // namespace
+
+#ifdef PE_JIT
+extern "C" __global__ void __launch_bounds__(512, 1) pe_b200_jit_kernel(pe_b200_rrun const r) { tree_body<4, false, PE_JIT_CL>(r); }
+#else
 
 extern "C"
 {
@@ -1193,6 +1309,41 @@ extern "C"
         return v > 1024 ? (size_t)v - 1024 : 0;  // static shared memory of the kernel (flags) comes out of the same budget
     }
 
+    // specialised kernels (host/jit.cpp): cubin -> kernel handle, loaded once per process and key
+    static thread_local void const* g_jit_kernel = nullptr;
+
+    int pe_b200_jit_supported(void) { return 1; }
+
+    int pe_b200_launch_jit(pe_b200_rrun const* run, void const* cubin, size_t bytes, uint64_t key, void* stream)
+    {
+        static std::mutex mu;
+        static std::map<std::pair<int, uint64_t>, cudaKernel_t> loaded;
+        int dev = 0;
+        if(chk(cudaGetDevice(&dev), "cudaGetDevice") != 0) { return 1; }
+        cudaKernel_t k{};
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = loaded.find({dev, key});
+            if(it == loaded.end())
+            {
+                if(cubin == nullptr || bytes == 0)
+                {
+                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_jit: no cubin");
+                    return 1;
+                }
+                cudaLibrary_t lib{};
+                if(chk(cudaLibraryLoadData(&lib, cubin, nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData") != 0) { return 1; }
+                if(chk(cudaLibraryGetKernel(&k, lib, "pe_b200_jit_kernel"), "cudaLibraryGetKernel(pe_b200_jit_kernel)") != 0) { return 1; }
+                it = loaded.emplace(std::make_pair(dev, key), k).first;
+            }
+            k = it->second;
+        }
+        g_jit_kernel = (void const*)k;
+        int const rc = pe_b200_launch_resident(run, stream);
+        g_jit_kernel = nullptr;
+        return rc;
+    }
+
     int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream)
     {
         if(run == nullptr || run->n_lanes <= 0) { return 0; }
@@ -1222,7 +1373,7 @@ extern "C"
                 cudaEventCreate(&e1);
                 cudaEventRecord(e0, (cudaStream_t)stream);
             }
-            void (*tk)(pe_b200_rrun) = nullptr;
+            void const* tk = nullptr;
             // register budgets: 64 per thread by default; programs with fused elimination steps (26 J operand rows in
             // flight per thread) and 128-lane groups get 128 in CTAs of at most 512 threads
             bool const fused{run->regs128 != 0};
@@ -1235,8 +1386,9 @@ extern "C"
                     snprintf(g_err, sizeof(g_err), "pe_b200_launch_resident: J = 4 needs at most 16 sub-tree warps per CTA");
                     return 1;
                 }
-                tk = CL == 2 ? (fused ? pe_b200_tree_kernel<4, 512, 1, true, 2> : pe_b200_tree_kernel<4, 512, 1, false, 2>)
-                             : (fused ? pe_b200_tree_kernel<4, 512, 1, true, 1> : pe_b200_tree_kernel<4, 512, 1, false, 1>);
+                tk = CL == 2 ? (fused ? (void const*)pe_b200_tree_kernel<4, 512, 1, true, 2> : (void const*)pe_b200_tree_kernel<4, 512, 1, false, 2>)
+                             : (fused ? (void const*)pe_b200_tree_kernel<4, 512, 1, true, 1> : (void const*)pe_b200_tree_kernel<4, 512, 1, false, 1>);
+                if(g_jit_kernel != nullptr) { tk = g_jit_kernel; }
             }
             else if(CL == 2)
             {
@@ -1245,15 +1397,15 @@ extern "C"
             }
             else if(J == 2)
             {
-                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<2, 512, 1, true, 1> : pe_b200_tree_kernel<2, 1024, 1, true, 1>)
-                           : (block <= 256 ? pe_b200_tree_kernel<2, 256, 4, false, 1>
-                                           : (block <= 512 ? pe_b200_tree_kernel<2, 512, 2, false, 1> : pe_b200_tree_kernel<2, 1024, 1, false, 1>));
+                tk = fused ? (block <= 512 ? (void const*)pe_b200_tree_kernel<2, 512, 1, true, 1> : (void const*)pe_b200_tree_kernel<2, 1024, 1, true, 1>)
+                           : (block <= 256 ? (void const*)pe_b200_tree_kernel<2, 256, 4, false, 1>
+                                           : (block <= 512 ? (void const*)pe_b200_tree_kernel<2, 512, 2, false, 1> : (void const*)pe_b200_tree_kernel<2, 1024, 1, false, 1>));
             }
             else
             {
-                tk = fused ? (block <= 512 ? pe_b200_tree_kernel<1, 512, 1, true, 1> : pe_b200_tree_kernel<1, 1024, 1, true, 1>)
-                           : (block <= 256 ? pe_b200_tree_kernel<1, 256, 4, false, 1>
-                                           : (block <= 512 ? pe_b200_tree_kernel<1, 512, 2, false, 1> : pe_b200_tree_kernel<1, 1024, 1, false, 1>));
+                tk = fused ? (block <= 512 ? (void const*)pe_b200_tree_kernel<1, 512, 1, true, 1> : (void const*)pe_b200_tree_kernel<1, 1024, 1, true, 1>)
+                           : (block <= 256 ? (void const*)pe_b200_tree_kernel<1, 256, 4, false, 1>
+                                           : (block <= 512 ? (void const*)pe_b200_tree_kernel<1, 512, 2, false, 1> : (void const*)pe_b200_tree_kernel<1, 1024, 1, false, 1>));
             }
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute attr[1];
@@ -1295,7 +1447,7 @@ extern "C"
             cfg.gridDim = dim3((unsigned)(tgroups * CL));
             pe_b200_rrun arg = *run;
             void* kargs[1] = {&arg};
-            cudaError_t const le = cudaLaunchKernelExC(&cfg, (void const*)tk, kargs);
+            cudaError_t const le = cudaLaunchKernelExC(&cfg, tk, kargs);
             if(g_timing)
             {
                 cudaEventRecord(e1, (cudaStream_t)stream);
@@ -1356,3 +1508,4 @@ extern "C"
 
     uint64_t pe_b200_launch_count(void) { return g_launches.load(); }
 }
+#endif  // PE_JIT

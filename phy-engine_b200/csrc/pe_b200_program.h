@@ -270,6 +270,10 @@ extern "C"
     // unknown indices, -1 = ground = 0 V), x = lane-interleaved solution rows x[unknown * LS + lane]
     int pe_b200_compare(double const* x, int64_t LS, int32_t n_lanes, int32_t const* ab, int32_t n_cmp, uint8_t* out, void* stream);
     int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream);
+    // specialised tree-streaming kernel (host/jit.cpp): the same launch with the kernel taken from a cubin (loaded once
+    // per process, device and key); geometry J = 4 only
+    int pe_b200_jit_supported(void);
+    int pe_b200_launch_jit(pe_b200_rrun const* run, void const* cubin, size_t bytes, uint64_t key, void* stream);
     // largest dynamic shared memory (bytes) one CTA of the resident kernel may use on the current device
     size_t pe_b200_resident_smem_limit(void);
     char const* pe_b200_dev_last_error(void);

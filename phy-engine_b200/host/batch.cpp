@@ -7,6 +7,9 @@
 
 #include "pe_host.hpp"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace pe_b200
 {
     namespace
@@ -494,6 +497,39 @@ namespace pe_b200
         last_I = I;
         last_J = J;
         last_S = pr.rS;
+        // Specialised kernel: linear real programs on 128-lane groups whose iter section is DOT / CAP_STEP only.  Required
+        // (res_jit = 1): built on the spot if it is not in the cache (minutes for a 1000-node circuit), a failure is an
+        // error; automatic: large batches take it when the cache holds it, the word interpreter runs otherwise.
+        bool const jit_auto{res_jit == 0 && lanes >= 4096 && std::getenv("PE_B200_NO_JIT") == nullptr};
+        if(r.wsg != nullptr && J == 4 && !nonlinear && !pr.cplx && (res_jit == 1 || jit_auto) && pe_b200_jit_supported() != 0)
+        {
+            if(pr.jit_state == 0 || (pr.jit_state == 1 && pr.jit_cl != r.cluster))
+            {
+                pr.jit_state = -1;
+                if(jit_supported(pr))
+                {
+                    pr.jit_cl = r.cluster;
+                    if(jit_compile(jit_generate(pr, jit_load_distance()), r.cluster, pr.jit_cubin, pr.jit_key, pr.jit_error, res_jit == 1)) { pr.jit_state = 1; }
+                }
+                else
+                {
+                    pr.jit_error = "jit: the iter section holds ops the specialised kernel does not cover";
+                }
+            }
+            if(pr.jit_state == 1)
+            {
+                if(pe_b200_launch_jit(&r, pr.jit_cubin.data(), pr.jit_cubin.size(), pr.jit_key, stream) != 0) { return dev_fail(error, "launch (specialised kernel)"); }
+                last_jit = 1;
+                return true;
+            }
+            if(res_jit == 1)
+            {
+                error = pr.jit_error;
+                set_last_error(error);
+                return false;
+            }
+        }
+        last_jit = 0;
         if(pe_b200_launch_resident(&r, stream) != 0) { return dev_fail(error, "launch"); }
         return true;
     }
@@ -836,6 +872,7 @@ namespace pe_b200
             solo->res_chunks = d.res_chunks;
             solo->res_prefetch = ((d.tuning & 1u) ? 1 : 0) | ((d.tuning & 2u) ? 2 : 0) | ((d.tuning & 4u) ? 0 : 4);
             solo->res_fuse = (d.tuning & 8u) ? 1 : 0;
+            solo->res_jit = (d.tuning & 16u) ? 1 : ((d.tuning & 32u) ? -1 : 0);
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

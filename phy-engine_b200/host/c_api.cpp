@@ -528,12 +528,15 @@ extern "C"
 
     int circuit_batch_set_tuning(void* b, unsigned flags)
     {
-        if(b == nullptr || flags > 15u) { return 1; }
+        if(b == nullptr || flags > 63u || (flags & 48u) == 48u) { return 1; }
         auto* bp{static_cast<batch*>(b)};
         bp->res_prefetch = ((flags & 1u) ? 1 : 0) | ((flags & 2u) ? 2 : 0) | ((flags & 4u) ? 0 : 4);
         bp->res_fuse = (flags & 8u) ? 1 : 0;
+        bp->res_jit = (flags & 16u) ? 1 : ((flags & 32u) ? -1 : 0);
         return 0;
     }
+
+    int circuit_batch_last_kernel(void* b) { return b == nullptr ? -1 : static_cast<batch*>(b)->last_jit; }
 
     int circuit_batch_resident_info(void* b, int mode, int64_t* info)
     {
@@ -786,6 +789,42 @@ extern "C"
         return 0;
     }
 
+    // tooling: the generated source of the specialised kernel's iter section (returns its length; copies at most cap bytes)
+    size_t circuit_batch_jit_source(void* bp, int mode, char* out, size_t cap)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 0; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        if(!jit_supported(pr)) { return 0; }
+        std::string const src{jit_generate(pr, jit_load_distance())};
+        if(out != nullptr && cap > 0) { std::memcpy(out, src.data(), std::min(cap, src.size())); }
+        return src.size();
+    }
+
+    // build (or find in the cache) the specialised kernel of a compiled program without a device: nvcc cross-compiles, so
+    // __graft_entry__.build() can ship the cubin of the bench configuration to the GPU box.  cluster = CTAs per lane group.
+    int circuit_batch_jit_build(void* bp, int mode, int cluster)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT) || (cluster != 1 && cluster != 2)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc) { return 1; }
+        auto& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        if(!jit_supported(pr))
+        {
+            set_last_error("jit: the iter section holds ops the specialised kernel does not cover");
+            return 1;
+        }
+        if(!jit_compile(jit_generate(pr, jit_load_distance()), cluster, pr.jit_cubin, pr.jit_key, pr.jit_error))
+        {
+            set_last_error(pr.jit_error);
+            return 1;
+        }
+        pr.jit_state = 1;
+        pr.jit_cl = cluster;
+        return 0;
+    }
+
     size_t circuit_batch_program_words(void* bp, int mode)
     {
         if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
@@ -885,7 +924,7 @@ extern "C"
 
     int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace, unsigned tuning)
     {
-        if(workspace < 0 || workspace > 2 || tuning > 15u) { return 1; }
+        if(workspace < 0 || workspace > 2 || tuning > 63u || (tuning & 48u) == 48u) { return 1; }
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }

@@ -189,6 +189,12 @@ namespace pe_b200
         std::vector<std::uint32_t> sec_off;  // [3][n_warps]
         bool has_sec[3]{};
         void pack(int ig);                   // (re)build words / sec_off for CTAs of rS * ig threads
+        // specialised kernel of the iter section (host/jit.cpp): 0 = not tried, 1 = cubin ready, -1 = not available
+        int jit_state{0};
+        int jit_cl{0};
+        std::uint64_t jit_key{};
+        std::vector<char> jit_cubin;
+        std::string jit_error;
 
         bool built{};
         bool cplx{};
@@ -256,6 +262,12 @@ namespace pe_b200
 
     struct circuit;
 
+    // host/jit.cpp: run-time specialisation of the tree-streaming kernel
+    bool jit_supported(program const& pr);
+    std::string jit_generate(program const& pr, int load_distance);
+    bool jit_compile(std::string const& gen, int CL, std::vector<char>& cubin, std::uint64_t& key, std::string& err, bool allow_compile = true);
+    int jit_load_distance();
+
     struct batch
     {
         circuit* parent{};
@@ -294,6 +306,7 @@ namespace pe_b200
         // ahead, 4 = L1 re-fetch of every DOT result right after its store (+3 %: on)
         int res_prefetch{4};
         std::size_t last_points_hint{1};  // frequency points per instance of the AC sweep being launched (lane count = n_inst * points)
+int res_jit{0};      // specialised (run-time compiled) tree-streaming kernel: 0 = automatic, 1 = required, -1 = off
         int res_fuse{0};     // emit small elimination steps as one fused op (PE_OP_CROUT2); measured slower on config B (register file bound): off
         int cc_fuse{-1};
         int res_chunks{0};   // chunks the time loop is cut into for dynamic scheduling: 0 = choose, 1 = static (one CTA per group)
@@ -303,6 +316,7 @@ namespace pe_b200
         bool pick_geometry(program const& pr, int& I, int& J) const;
         std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_secoff, d_io;
         std::array<int, static_cast<int>(prog_mode::COUNT)> uploaded_ig{};
+        int last_jit{};  // 1 = the last tree-streaming launch ran the specialised (run-time compiled) kernel
         int last_I{}, last_J{}, last_S{};  // geometry of the last resident launch (0 = the HBM-streaming kernel ran)
 
         // results of the last analyze()

@@ -229,6 +229,8 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_set_resident.argtypes = [V, ct.c_int, ct.c_int, ct.c_int]
     lib.phy_engine_b200_set_default_path.argtypes = [ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_uint]
     lib.circuit_batch_set_tuning.argtypes = [V, ct.c_uint]
+    lib.circuit_batch_last_kernel.argtypes = [V]
+    lib.circuit_batch_last_kernel.restype = ct.c_int
     lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
     lib.circuit_batch_digital_clk.argtypes = [V]
     lib.circuit_batch_comparator_count.restype = _SZ
@@ -376,6 +378,10 @@ class Batch:
     def set_tuning(self, flags: int):
         """bit 0 L2 operand prefetch, bit 1 two lines ahead, bit 2 no L1 re-fetch of results, bit 3 fused elimination steps"""
         self._rc(self.lib.circuit_batch_set_tuning(self.h, flags), "circuit_batch_set_tuning")
+
+    def last_kernel(self) -> int:
+        """0 = word interpreter, 1 = specialised (run-time compiled) tree-streaming kernel"""
+        return int(self.lib.circuit_batch_last_kernel(self.h))
 
     def digital_clk(self) -> np.ndarray:
         """comparator states [n_instances, n_comparators] (vA >= vB) after the last analyze()"""

@@ -528,6 +528,14 @@ extern "C"
 {
     uint64_t pe_emu_resident_launches(void) { return g_resident_launches; }
 
+    // the emulator replays the word interpreter only: specialised (run-time compiled) kernels are GPU-only
+    int pe_b200_jit_supported(void) { return 0; }
+    int pe_b200_launch_jit(pe_b200_rrun const*, void const*, size_t, uint64_t, void*)
+    {
+        snprintf(g_err, sizeof(g_err), "pe_b200_launch_jit: not available in the emulator");
+        return 1;
+    }
+
     int pe_b200_launch_resident(pe_b200_rrun const* rp, void*)
     {
         if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
