@@ -759,6 +759,7 @@ namespace
     {
         double v[4];
     };
+    __device__ __forceinline__ char* jopq(char* p) { return p; }
     __device__ __forceinline__ jv jld(char const* p)
     {
         jv x;

@@ -73,104 +73,497 @@ namespace pe_b200
             std::vector<std::uint32_t> writes;  // rel slots
         };
 
-        // source of one (stream, phase) function body; `S` = streams per instance, D = load distance = forwarding window
-        // The relative columns a function touches are its parameters k0, k1, ... (numbered in order of first use), so that
-        // sub-trees which differ only in where their separators live share one function.
-        std::string gen_body(std::vector<jop> const& ops, int S, int D, std::vector<std::uint32_t>& cols)
+        // ---- code generation of one (stream, phase) function ------------------------------------------------------
+        // Relative columns are the function's parameters k0, k1, ... (numbered in order of first use): sub-trees that
+        // differ only in where their separators live share one function.  The workspace of a 128-lane group is one
+        // block, ws[group][slot][128 lanes]: a row is 1 KB and an operand address is a column base (one pointer per column
+        // and 4 MB anchor) plus a constant that fits the immediate field of the load / store.
+        //
+        // Periodic runs of ops (the elimination of a chain of like nodes repeats one pattern with all rows shifted by a
+        // constant) are rolled into a loop: the code of one period with moving row pointers, so that the instruction
+        // footprint of a sub-tree is a few KB instead of a few hundred KB (the straight-line form stalls on instruction
+        // fetch).  Forwarding and the load-ahead pipeline run across the back edge in named registers.
+        struct gen
         {
-            std::uint32_t const sm{static_cast<std::uint32_t>(S - 1)};
-            std::ostringstream out;
-            cols.clear();
-            // The specialised kernel keeps the workspace of a 128-lane group in one block, ws[group][slot][128 lanes]: a
-            // row is 1 KB, the address of an operand is a column base (one register pair per column and 4 MB anchor) plus
-            // a constant that fits the immediate field of the load / store.
+            std::vector<jop> const& ops;
+            int S, D;
+            int K;  // forwarding window (>= D): a result is taken from its register by the ops up to K positions later
+            std::uint32_t sm;
+            std::vector<std::uint32_t>& cols;
+            std::uint32_t stream{};                        // absolute slot = (rel & ~sm) | ((rel + stream) & sm)
+            std::vector<std::uint8_t>* mem_reads{};        // pass 1: absolute slots some load takes from memory
+            std::vector<std::uint8_t> const* needed{};     // pass 2: a store to a slot nobody loads is left out
             std::set<std::pair<std::size_t, std::uint32_t>> anchors;
-            auto addr = [&](std::uint32_t rel) -> std::string
+            std::ostringstream body;
+            int n_regions{};
+
+            gen(std::vector<jop> const& o, int S_, int D_, int K_, std::vector<std::uint32_t>& c) : ops{o}, S{S_}, D{D_}, K{std::max(K_, D_)}, sm{static_cast<std::uint32_t>(S_ - 1)}, cols{c}
+            {
+                cols.clear();
+            }
+            std::uint32_t abs_slot(std::int64_t rel) const { return (static_cast<std::uint32_t>(rel) & ~sm) | ((static_cast<std::uint32_t>(rel) + stream) & sm); }
+            void note_read(std::int64_t rel)
+            {
+                if(mem_reads != nullptr && rel >= 0 && abs_slot(rel) < mem_reads->size()) { (*mem_reads)[abs_slot(rel)] = 1; }
+            }
+            bool store_needed(std::int64_t rel) const { return needed == nullptr || abs_slot(rel) >= needed->size() || (*needed)[abs_slot(rel)] != 0; }
+
+            std::size_t col_of(std::uint32_t rel)
             {
                 std::size_t ci{};
                 while(ci < cols.size() && cols[ci] != (rel & sm)) { ++ci; }
                 if(ci == cols.size()) { cols.push_back(rel & sm); }
+                return ci;
+            }
+            std::string addr(std::uint32_t rel)
+            {
+                std::size_t const ci{col_of(rel)};
                 std::uint64_t const off{static_cast<std::uint64_t>(rel & ~sm) * 1024u};
                 std::uint32_t const an{static_cast<std::uint32_t>(off >> 22)};
                 anchors.insert({ci, an});
                 std::ostringstream a;
                 a << "c" << ci << "_" << an << " + " << (off & 0x3fffffu);
                 return a.str();
-            };
-            int const n{static_cast<int>(ops.size())};
-            // value of rel slot as seen by op k: a forwarded register (written / loaded within the last D ops) or a load
-            // issued at op max(0, k - D)
-            std::map<std::uint32_t, std::pair<int, std::string>> last_write;  // rel -> (op, variable)
-            std::map<std::uint32_t, std::pair<int, std::string>> last_load;   // rel -> (op the load was made for, variable)
-            std::vector<std::vector<std::string>> opnd(static_cast<std::size_t>(n));
-            std::vector<std::vector<std::string>> loads_at(static_cast<std::size_t>(n));  // load statements emitted before op p runs
-            for(int k{}; k < n; ++k)
-            {
-                auto const& j{ops[static_cast<std::size_t>(k)]};
-                for(std::size_t i{}; i < j.reads.size(); ++i)
-                {
-                    std::uint32_t const rel{j.reads[i]};
-                    auto const w{last_write.find(rel)};
-                    if(w != last_write.end() && k - w->second.first <= D)
-                    {
-                        opnd[static_cast<std::size_t>(k)].push_back(w->second.second);
-                        continue;
-                    }
-                    auto const l{last_load.find(rel)};
-                    if(l != last_load.end() && k - l->second.first <= D && (w == last_write.end() || w->second.first < l->second.first - D))
-                    {
-                        opnd[static_cast<std::size_t>(k)].push_back(l->second.second);
-                        continue;
-                    }
-                    std::ostringstream v;
-                    v << "l" << k << "_" << i;
-                    std::ostringstream st;
-                    st << "jv const " << v.str() << " = jld(" << addr(rel) << ");";
-                    loads_at[static_cast<std::size_t>(std::max(0, k - D))].push_back(st.str());
-                    last_load[rel] = {k, v.str()};
-                    opnd[static_cast<std::size_t>(k)].push_back(v.str());
-                }
-                for(std::size_t i{}; i < j.writes.size(); ++i)
-                {
-                    std::ostringstream v;
-                    v << "w" << k << "_" << i;
-                    last_write[j.writes[i]] = {k, v.str()};
-                }
             }
-            std::ostringstream body;
-            for(int k{}; k < n; ++k)
+
+            // the statement(s) of one op: x = operand expressions, w = names of its result variables, st = store addresses
+            static std::string op_text(rop const& o, std::vector<std::string> const& x, std::vector<std::string> const& w, std::vector<std::string> const& st, bool declare)
             {
-                for(auto const& s: loads_at[static_cast<std::size_t>(k)]) { body << "    " << s << "\n"; }
-                auto const& j{ops[static_cast<std::size_t>(k)]};
-                auto const& x{opnd[static_cast<std::size_t>(k)]};
-                rop const& o{*j.o};
+                std::ostringstream t;
+                char const* const dv{declare ? "jv " : ""};
                 if(o.opcode == PE_OP_DOT)
                 {
                     std::size_t q{};
-                    body << "    jv w" << k << "_0 = jzero();";
-                    for(auto const s: o.sre) { body << ((s & PE_R_NEG) ? " jsub(" : " jadd(") << "w" << k << "_0, " << x[q++] << ");"; }
+                    t << dv << w[0] << " = jzero();";
+                    for(auto const s: o.sre) { t << ((s & PE_R_NEG) ? " jsub(" : " jadd(") << w[0] << ", " << x[q++] << ");"; }
                     for(auto const& pp: o.pp)
                     {
                         bool const pos{((pp.first ^ pp.second) & PE_R_NEG) != 0u};  // -(+-a)(+-b)
-                        body << (pos ? " jfma(" : " jfms(") << "w" << k << "_0, " << x[q] << ", " << x[q + 1] << ");";
+                        t << (pos ? " jfma(" : " jfms(") << w[0] << ", " << x[q] << ", " << x[q + 1] << ");";
                         q += 2;
                     }
-                    if(o.flags & PE_F_SCALE) { body << " jmul(w" << k << "_0, " << x[q++] << ");"; }
-                    if(o.flags & PE_F_RECIP) { body << " jrcp(w" << k << "_0, fm);"; }
-                    body << " jst(" << addr(j.writes[0]) << ", w" << k << "_0, enm);\n";
+                    if(o.flags & PE_F_SCALE) { t << " jmul(" << w[0] << ", " << x[q++] << ");"; }
+                    if(o.flags & PE_F_RECIP) { t << " jrcp(" << w[0] << ", fm);"; }
+                    if(!st[0].empty()) { t << " jst(" << st[0] << ", " << w[0] << ", enm);"; }
                 }
                 else  // PE_OP_CAP_STEP: [hist][prev_g][C][dt][va][vb]
                 {
-                    body << "    jv w" << k << "_0 = " << x[0] << ", w" << k << "_1 = " << x[1] << "; jcap(" << x[2] << ", " << x[3] << ", " << x[4] << ", " << x[5] << ", w" << k
-                         << "_0, w" << k << "_1); jst(" << addr(j.writes[0]) << ", w" << k << "_0, enm); jst(" << addr(j.writes[1]) << ", w" << k << "_1, enm);\n";
+                    t << dv << w[0] << " = " << x[0] << "; " << dv << w[1] << " = " << x[1] << "; jcap(" << x[2] << ", " << x[3] << ", " << x[4] << ", " << x[5] << ", " << w[0] << ", " << w[1]
+                      << ");";
+                    if(!st[0].empty()) { t << " jst(" << st[0] << ", " << w[0] << ", enm);"; }
+                    if(!st[1].empty()) { t << " jst(" << st[1] << ", " << w[1] << ", enm);"; }
+                }
+                return t.str();
+            }
+
+            // a DOT with many terms (the update a sub-tree owes its separators sums one product per eliminated node): its
+            // own loads are made eight terms at a time right where they are consumed, in the op's own order of accumulation,
+            // instead of all ahead of the op (hundreds of registers).  ld[i] = address to load operand i from ("" = x[i] is a
+            // register that already holds it)
+            static constexpr std::size_t long_reads{12};
+            static std::string long_dot_text(rop const& o, std::vector<std::string> const& x, std::vector<std::string> const& ld, std::string const& w, std::string const& st)
+            {
+                std::ostringstream t;
+                t << "jv " << w << " = jzero();\n";
+                struct term
+                {
+                    int kind;  // 0 add, 1 sub, 2 fms, 3 fma, 4 mul
+                    std::size_t a, b;
+                };
+                std::vector<term> terms;
+                std::size_t q{};
+                for(auto const s: o.sre) { terms.push_back({(s & PE_R_NEG) ? 1 : 0, q, q}), ++q; }
+                for(auto const& pp: o.pp)
+                {
+                    terms.push_back({((pp.first ^ pp.second) & PE_R_NEG) ? 3 : 2, q, q + 1});
+                    q += 2;
+                }
+                if(o.flags & PE_F_SCALE) { terms.push_back({4, q, q}), ++q; }
+                for(std::size_t b{}; b < terms.size(); b += 8)
+                {
+                    std::size_t const e{std::min(terms.size(), b + 8)};
+                    t << "    {\n";
+                    std::set<std::size_t> loaded;
+                    for(std::size_t k{b}; k < e; ++k)
+                    {
+                        for(std::size_t const i: {terms[k].a, terms[k].b})
+                        {
+                            if(!ld[i].empty() && loaded.insert(i).second) { t << "        jv const " << x[i] << " = jld(" << ld[i] << ");\n"; }
+                        }
+                    }
+                    t << "       ";
+                    for(std::size_t k{b}; k < e; ++k)
+                    {
+                        static char const* const fn[5]{"jadd", "jsub", "jfms", "jfma", "jmul"};
+                        t << " " << fn[terms[k].kind] << "(" << w << ", " << x[terms[k].a];
+                        if(terms[k].kind == 2 || terms[k].kind == 3) { t << ", " << x[terms[k].b]; }
+                        t << ");";
+                    }
+                    t << "\n        asm volatile(\"\" ::: \"memory\");  // keeps the loads of the next block behind this one\n    }\n";
+                }
+                t << "   ";
+                if(o.flags & PE_F_RECIP) { t << " jrcp(" << w << ", fm);"; }
+                if(!st.empty()) { t << " jst(" << st << ", " << w << ", enm);"; }
+                return t.str();
+            }
+
+            // where the value of read i of op k comes from, for a self-contained run of ops starting at `first`
+            struct src_t
+            {
+                int kind{};  // 0 = its own load, 1 = result of op k - d (output o), 2 = the load made for read o of op k - d
+                int d{}, o{};
+                bool operator== (src_t const& b) const { return kind == b.kind && d == b.d && o == b.o; }
+            };
+            static bool is_long(jop const& j) { return j.o->opcode == PE_OP_DOT && j.reads.size() > long_reads; }
+            std::vector<std::vector<src_t>> analyse(int first, int count) const
+            {
+                std::map<std::uint32_t, std::pair<int, int>> last_write, last_load;  // rel -> (op, output / read index)
+                std::vector<std::vector<src_t>> res(static_cast<std::size_t>(count));
+                for(int k{first}; k < first + count; ++k)
+                {
+                    auto const& j{ops[static_cast<std::size_t>(k)]};
+                    for(std::size_t i{}; i < j.reads.size(); ++i)
+                    {
+                        std::uint32_t const rel{j.reads[i]};
+                        auto const w{last_write.find(rel)};
+                        auto const l{last_load.find(rel)};
+                        src_t sr{};
+                        if(w != last_write.end() && k - w->second.first <= K) { sr = {1, k - w->second.first, w->second.second}; }
+                        else if(l != last_load.end() && k - l->second.first <= D && (w == last_write.end() || w->second.first < l->second.first - D))
+                        {
+                            sr = {2, k - l->second.first, l->second.second};
+                        }
+                        else if(!is_long(j))  // the loads of a long op live in its own blocks only
+                        {
+                            last_load[rel] = {k, static_cast<int>(i)};
+                        }
+                        res[static_cast<std::size_t>(k - first)].push_back(sr);
+                    }
+                    for(std::size_t i{}; i < j.writes.size(); ++i) { last_write[j.writes[i]] = {k, static_cast<int>(i)}; }
+                }
+                return res;
+            }
+
+            static bool same_shape(jop const& a, jop const& b)
+            {
+                rop const &x{*a.o}, &y{*b.o};
+                if(x.opcode != y.opcode || x.flags != y.flags || a.reads.size() != b.reads.size() || a.writes.size() != b.writes.size() || x.sre.size() != y.sre.size() ||
+                   x.pp.size() != y.pp.size())
+                {
+                    return false;
+                }
+                for(std::size_t i{}; i < x.sre.size(); ++i)
+                {
+                    if((x.sre[i] ^ y.sre[i]) & PE_R_NEG) { return false; }
+                }
+                for(std::size_t i{}; i < x.pp.size(); ++i)
+                {
+                    if(((x.pp[i].first ^ x.pp[i].second) ^ (y.pp[i].first ^ y.pp[i].second)) & PE_R_NEG) { return false; }
+                }
+                return true;
+            }
+            // op b repeats op a with every row shifted by m * (the shift between a and a + period)
+            bool shifted(int a, int per, int m) const
+            {
+                jop const &x{ops[static_cast<std::size_t>(a)]}, &y{ops[static_cast<std::size_t>(a + per)]}, &z{ops[static_cast<std::size_t>(a + m * per)]};
+                if(!same_shape(x, z)) { return false; }
+                auto ok = [&](std::uint32_t s0, std::uint32_t s1, std::uint32_t sm_) -> bool
+                {
+                    std::int64_t const d{static_cast<std::int64_t>(s1) - static_cast<std::int64_t>(s0)};
+                    return (s0 & sm) == (s1 & sm) && static_cast<std::int64_t>(sm_) == static_cast<std::int64_t>(s0) + m * d;
+                };
+                for(std::size_t i{}; i < x.reads.size(); ++i)
+                {
+                    if(!ok(x.reads[i], y.reads[i], z.reads[i])) { return false; }
+                }
+                for(std::size_t i{}; i < x.writes.size(); ++i)
+                {
+                    if(!ok(x.writes[i], y.writes[i], z.writes[i])) { return false; }
+                }
+                return true;
+            }
+
+            // longest periodic run starting at k0: period per (in ops), iterations n_it; returns covered ops (0 = none)
+            int find_run(int k0, int& per, int& n_it) const
+            {
+                int const n{static_cast<int>(ops.size())};
+                int best{};
+                for(int p{1}; p <= 24 && k0 + 2 * p <= n; ++p)
+                {
+                    int m{1};
+                    for(;; ++m)
+                    {
+                        if(k0 + (m + 1) * p > n) { break; }
+                        bool all{true};
+                        for(int q{}; q < p && all; ++q) { all = shifted(k0 + q, p, m); }
+                        if(!all) { break; }
+                    }
+                    if(m >= 4 && m * p > best)
+                    {
+                        best = m * p;
+                        per = p;
+                        n_it = m;
+                    }
+                }
+                return best;
+            }
+
+            void straight(int first, int count)
+            {
+                if(count <= 0) { return; }
+                auto const srcs{analyse(first, count)};
+                std::vector<std::vector<std::string>> loads_at(static_cast<std::size_t>(count));
+                std::vector<std::vector<std::string>> opnd(static_cast<std::size_t>(count));
+                for(int r{}; r < count; ++r)
+                {
+                    int const k{first + r};
+                    auto const& j{ops[static_cast<std::size_t>(k)]};
+                    for(std::size_t i{}; i < j.reads.size(); ++i)
+                    {
+                        auto const& sr{srcs[static_cast<std::size_t>(r)][i]};
+                        std::ostringstream v;
+                        if(sr.kind == 1) { v << "w" << (k - sr.d) << "_" << sr.o; }
+                        else if(sr.kind == 2) { v << "l" << (k - sr.d) << "_" << sr.o; }
+                        else
+                        {
+                            v << "l" << k << "_" << i;
+                            note_read(j.reads[i]);
+                            if(!is_long(j)) { loads_at[static_cast<std::size_t>(std::max(0, r - D))].push_back("jv const " + v.str() + " = jld(" + addr(j.reads[i]) + ");"); }
+                        }
+                        opnd[static_cast<std::size_t>(r)].push_back(v.str());
+                    }
+                }
+                for(int r{}; r < count; ++r)
+                {
+                    int const k{first + r};
+                    for(auto const& st: loads_at[static_cast<std::size_t>(r)]) { body << "    " << st << "\n"; }
+                    auto const& j{ops[static_cast<std::size_t>(k)]};
+                    std::vector<std::string> w, st;
+                    for(std::size_t i{}; i < j.writes.size(); ++i)
+                    {
+                        w.push_back("w" + std::to_string(k) + "_" + std::to_string(i));
+                        st.push_back(store_needed(j.writes[i]) ? addr(j.writes[i]) : std::string{});
+                    }
+                    if(is_long(j))
+                    {
+                        std::vector<std::string> ld;
+                        for(std::size_t i{}; i < j.reads.size(); ++i) { ld.push_back(srcs[static_cast<std::size_t>(r)][i].kind == 0 ? addr(j.reads[i]) : std::string{}); }
+                        body << "    " << long_dot_text(*j.o, opnd[static_cast<std::size_t>(r)], ld, w[0], st[0]) << "\n";
+                        continue;
+                    }
+                    body << "    " << op_text(*j.o, opnd[static_cast<std::size_t>(r)], w, st, true) << "\n";
                 }
             }
-            for(auto const& [ci, an]: anchors)
+
+            // ops [k0, k0 + n_it * per) as a loop of n_it iterations; false = the run does not qualify (nothing emitted)
+            bool rolled(int k0, int per, int n_it)
             {
-                out << "    char* const c" << ci << "_" << an << " = wl + (((k" << ci << " + stream) & " << sm << "u) * 1024u + " << (static_cast<std::uint64_t>(an) << 22) << "ull);\n";
+                if(per < std::max(2 * D + 1, K + D + 1) || n_it < 3) { return false; }
+                for(int q{}; q < per; ++q)
+                {
+                    if(is_long(ops[static_cast<std::size_t>(k0 + q)])) { return false; }
+                }
+                auto const srcs{analyse(k0, per * n_it)};
+                // steady state = iteration 1; every later iteration must take its operands from the same places
+                for(int m{2}; m < n_it; ++m)
+                {
+                    for(int q{}; q < per; ++q)
+                    {
+                        if(!(srcs[static_cast<std::size_t>(m * per + q)] == srcs[static_cast<std::size_t>(per + q)])) { return false; }
+                    }
+                }
+                int const rid{n_regions};
+                std::string const pre{"r" + std::to_string(rid) + "_"};
+                // moving pointers: one per (column, row shift per iteration); the others are fixed addresses
+                struct mov_t
+                {
+                    std::size_t ci;
+                    std::int64_t delta;      // slots per iteration
+                    std::uint32_t base;      // lowest slot (iteration 0) of the operands using it
+                };
+                std::vector<mov_t> movs;
+                auto delta_of = [&](int q, bool wr, std::size_t i) -> std::int64_t
+                {
+                    auto const &a{ops[static_cast<std::size_t>(k0 + q)]}, &b{ops[static_cast<std::size_t>(k0 + per + q)]};
+                    return wr ? static_cast<std::int64_t>(b.writes[i]) - static_cast<std::int64_t>(a.writes[i]) : static_cast<std::int64_t>(b.reads[i]) - static_cast<std::int64_t>(a.reads[i]);
+                };
+                auto mov_of = [&](std::uint32_t slot0, std::int64_t delta) -> std::size_t
+                {
+                    std::size_t const ci{col_of(slot0)};
+                    for(std::size_t m{}; m < movs.size(); ++m)
+                    {
+                        if(movs[m].ci == ci && movs[m].delta == delta)
+                        {
+                            movs[m].base = std::min(movs[m].base, slot0 & ~sm);
+                            return m;
+                        }
+                    }
+                    movs.push_back({ci, delta, slot0 & ~sm});
+                    return movs.size() - 1;
+                };
+                for(int q{}; q < per; ++q)
+                {
+                    auto const& a{ops[static_cast<std::size_t>(k0 + q)]};
+                    for(std::size_t i{}; i < a.reads.size(); ++i)
+                    {
+                        if(delta_of(q, false, i) != 0) { mov_of(a.reads[i], delta_of(q, false, i)); }
+                    }
+                    for(std::size_t i{}; i < a.writes.size(); ++i)
+                    {
+                        if(delta_of(q, true, i) != 0) { mov_of(a.writes[i], delta_of(q, true, i)); }
+                    }
+                }
+                bool fits{true};
+                // address of an operand in iteration it + ahead (ahead = 0 / 1), as an expression valid inside the loop
+                auto loop_addr = [&](std::uint32_t slot0, std::int64_t delta, int ahead) -> std::string
+                {
+                    if(delta == 0) { return addr(slot0); }
+                    std::size_t const m{mov_of(slot0, delta)};
+                    std::int64_t const imm{(static_cast<std::int64_t>(slot0 & ~sm) - static_cast<std::int64_t>(movs[m].base) + ahead * delta) * 1024};
+                    if(imm >= (1 << 22) || imm <= -(1 << 22)) { fits = false; }
+                    return pre + "m" + std::to_string(m) + " + " + std::to_string(imm);
+                };
+                auto wname = [&](int q, int o) { return pre + "w" + std::to_string(q) + "_" + std::to_string(o); };
+                auto lname = [&](int q, int i) { return pre + "l" + std::to_string(q) + "_" + std::to_string(i); };
+                std::ostringstream decl, init, prologue, loop;
+                std::set<std::string> declared;
+                auto declare = [&](std::string const& v)
+                {
+                    if(declared.insert(v).second) { decl << "    jv " << v << ";\n"; }
+                };
+                // operand names of the steady state; values carried over the back edge are seeded from memory before the loop
+                std::vector<std::vector<std::string>> opnd(static_cast<std::size_t>(per));
+                std::vector<std::vector<std::pair<std::string, std::string>>> loads_of(static_cast<std::size_t>(per));  // per op: (variable, read index) of its own loads
+                for(int q{}; q < per; ++q)
+                {
+                    auto const& a{ops[static_cast<std::size_t>(k0 + q)]};
+                    for(std::size_t i{}; i < a.reads.size(); ++i)
+                    {
+                        auto const& sr{srcs[static_cast<std::size_t>(per + q)][i]};
+                        std::string v;
+                        if(sr.kind == 0)
+                        {
+                            v = lname(q, static_cast<int>(i));
+                            loads_of[static_cast<std::size_t>(q)].push_back({v, std::to_string(i)});
+                            for(int m{}; m < n_it; ++m) { note_read(static_cast<std::int64_t>(a.reads[i]) + m * delta_of(q, false, i)); }
+                        }
+                        else
+                        {
+                            int const qp{((q - sr.d) % per + per) % per};
+                            v = sr.kind == 1 ? wname(qp, sr.o) : lname(qp, sr.o);
+                            if(q - sr.d < 0)
+                            {
+                                init << "    " << v << " = jld(" << loop_addr(a.reads[i], delta_of(q, false, i), 0) << ");\n";
+                                note_read(a.reads[i]);
+                            }
+                        }
+                        declare(v);
+                        opnd[static_cast<std::size_t>(q)].push_back(v);
+                    }
+                    for(std::size_t i{}; i < a.writes.size(); ++i) { declare(wname(q, static_cast<int>(i))); }
+                }
+                auto emit_loads = [&](std::ostringstream& o, int q, int ahead, char const* indent)
+                {
+                    auto const& a{ops[static_cast<std::size_t>(k0 + q)]};
+                    for(auto const& [v, is]: loads_of[static_cast<std::size_t>(q)])
+                    {
+                        std::size_t const i{static_cast<std::size_t>(std::stoi(is))};
+                        o << indent << v << " = jld(" << loop_addr(a.reads[i], delta_of(q, false, i), ahead) << ");\n";
+                    }
+                };
+                for(int q{}; q < std::min(D, per); ++q) { emit_loads(prologue, q, 0, "    "); }
+                for(int q{}; q < per; ++q)
+                {
+                    int const q2{q + D};
+                    if(q2 < per) { emit_loads(loop, q2, 0, "        "); }
+                    else if(!loads_of[static_cast<std::size_t>(q2 - per)].empty())
+                    {
+                        loop << "        if(it + 1u < " << n_it << "u)\n        {\n";
+                        emit_loads(loop, q2 - per, 1, "            ");
+                        loop << "        }\n";
+                    }
+                    auto const& a{ops[static_cast<std::size_t>(k0 + q)]};
+                    std::vector<std::string> w, st;
+                    for(std::size_t i{}; i < a.writes.size(); ++i)
+                    {
+                        w.push_back(wname(q, static_cast<int>(i)));
+                        bool any{};
+                        for(int m{}; m < n_it && !any; ++m) { any = store_needed(static_cast<std::int64_t>(a.writes[i]) + m * delta_of(q, true, i)); }
+                        st.push_back(any ? loop_addr(a.writes[i], delta_of(q, true, i), 0) : std::string{});
+                    }
+                    loop << "        " << op_text(*a.o, opnd[static_cast<std::size_t>(q)], w, st, false) << "\n";
+                }
+                if(!fits) { return false; }
+                ++n_regions;
+                body << "    // ops " << k0 << " .. " << (k0 + per * n_it - 1) << ": " << n_it << " x " << per << "\n" << decl.str();
+                for(std::size_t m{}; m < movs.size(); ++m)
+                {
+                    body << "    char* " << pre << "m" << m << " = jopq(wl + (((k" << movs[m].ci << " + stream) & " << sm << "u) * 1024u + " << static_cast<std::uint64_t>(movs[m].base) * 1024u << "ull));\n";
+                }
+                body << init.str() << prologue.str() << "#pragma unroll 1\n    for(uint32_t it = 0u; it < " << n_it << "u; ++it)\n    {\n" << loop.str();
+                for(std::size_t m{}; m < movs.size(); ++m) { body << "        " << pre << "m" << m << " += " << movs[m].delta * 1024 << "ll;\n"; }
+                body << "    }\n";
+                return true;
             }
-            out << "    uint32_t fm = 0u;\n" << body.str() << "    return fm;\n";
-            return out.str();
+
+            std::string run(bool roll)
+            {
+                int const n{static_cast<int>(ops.size())};
+                int k{}, pending{};  // `pending` ops before k wait to be emitted as straight-line code
+                while(k < n)
+                {
+                    int per{}, n_it{};
+                    if(roll && find_run(k, per, n_it) > 0)
+                    {
+                        // a period long enough for the pipeline: unroll short periods; the operand sources (which loads are
+                        // shared between neighbouring ops) may repeat with a multiple of the period only
+                        int u{1};
+                        while(per * u < std::max(2 * D + 1, K + D + 1)) { ++u; }
+                        bool done{};
+                        for(int tries{}; tries < 4 && !done; ++tries, ++u)
+                        {
+                            int const P{per * u}, N{n_it / u};
+                            if(N < 3 || P > 32) { break; }
+                            std::string const saved{body.str()};
+                            auto const saved_regions{n_regions};
+                            straight(k - pending, pending);
+                            if(rolled(k, P, N))
+                            {
+                                pending = 0;
+                                k += P * N;
+                                done = true;
+                                break;
+                            }
+                            body.str(saved);
+                            body.seekp(0, std::ios::end);
+                            n_regions = saved_regions;
+                        }
+                        if(done) { continue; }
+                    }
+                    ++pending;
+                    ++k;
+                }
+                straight(n - pending, pending);
+                std::ostringstream out;
+                for(auto const& [ci, an]: anchors)
+                {
+                    out << "    char* const c" << ci << "_" << an << " = jopq(wl + (((k" << ci << " + stream) & " << sm << "u) * 1024u + " << (static_cast<std::uint64_t>(an) << 22) << "ull));\n";
+                }
+                out << "    uint32_t fm = 0u;\n" << body.str() << "    return fm;\n";
+                return out.str();
+            }
+        };
+
+        std::string gen_body(std::vector<jop> const& ops, int S, int D, std::vector<std::uint32_t>& cols, std::uint32_t stream, std::vector<std::uint8_t>* mem_reads,
+                             std::vector<std::uint8_t> const* needed)
+        {
+            static bool const roll{std::getenv("PE_B200_JIT_NOROLL") == nullptr};
+            static int const K{env_int("PE_B200_JIT_K", 1)};
+            gen g{ops, S, D, K, cols};
+            g.stream = stream;
+            g.mem_reads = mem_reads;
+            g.needed = needed;
+            return g.run(roll);
         }
     }  // namespace
 
@@ -204,6 +597,49 @@ namespace pe_b200
         std::vector<std::size_t> n_cols;                      // per function: number of column parameters
         std::vector<std::vector<int>> call(n_ph, std::vector<int>(static_cast<std::size_t>(S), -1));  // [phase][stream] -> function
         std::vector<std::vector<std::vector<std::uint32_t>>> call_cols(n_ph, std::vector<std::vector<std::uint32_t>>(static_cast<std::size_t>(S)));
+        // Pass 0 finds the slots some load takes from memory; a store to any other slot is dead (its value only ever
+        // travels in registers, e.g. the L entries of a refactorisation) unless the slot is read outside the generated
+        // code: by the interpreted sections, the load / store tables, the solution read-out or the waveform probes.
+        std::uint32_t const smk{static_cast<std::uint32_t>(S - 1)};
+        std::vector<std::uint8_t> needed(static_cast<std::size_t>(pr.r_slots) + 2u * static_cast<std::size_t>(S), 0);
+        auto keep = [&](std::uint32_t abs)
+        {
+            if(abs < needed.size()) { needed[abs] = 1; }
+        };
+        for(int sj{}; sj < S; ++sj)
+        {
+            auto abs_of = [&](std::uint32_t field) { return ((field & 0x7fffu) & ~smk) | (((field & 0x7fffu) + static_cast<std::uint32_t>(sj)) & smk); };
+            for(int sec{}; sec < 3; ++sec)
+            {
+                for(auto const& ph: pr.rstreams[static_cast<std::size_t>(sj)].sec[sec])
+                {
+                    for(auto const& o: ph)
+                    {
+                        if(o.bubble) { continue; }
+                        if(sec == 2)
+                        {
+                            if(o.flags & (PE_F_CHECK_V | PE_F_CHECK_I)) { keep(abs_of(o.dst)); }
+                            continue;
+                        }
+                        keep(abs_of(o.dst));
+                        keep(abs_of(o.scale));
+                        for(auto const w: o.sre) { keep(abs_of(w)); }
+                        for(auto const w: o.sim) { keep(abs_of(w)); }
+                        for(auto const& pp: o.pp)
+                        {
+                            keep(abs_of(pp.first));
+                            keep(abs_of(pp.second));
+                        }
+                        for(auto const w: o.opnd) { keep(abs_of(w)); }
+                        for(auto const& sb: o.sub) { keep(abs_of(sb.dst)); }
+                    }
+                }
+            }
+        }
+        for(auto const& io: pr.io) { keep(io.slot_kind & 0xffffu); }
+        for(auto const x: pr.x_slot) { keep(x); }
+        static bool const keep_stores{std::getenv("PE_B200_JIT_KEEP_STORES") != nullptr};
+        for(int pass{}; pass < 2; ++pass)
         for(std::size_t ph{}; ph < n_ph; ++ph)
         {
             for(int sj{}; sj < S; ++sj)
@@ -237,7 +673,12 @@ namespace pe_b200
                 }
                 if(ops.empty()) { continue; }
                 std::vector<std::uint32_t> cols;
-                std::string body{gen_body(ops, S, D, cols)};
+                if(pass == 0)
+                {
+                    (void)gen_body(ops, S, D, cols, static_cast<std::uint32_t>(sj), &needed, nullptr);
+                    continue;
+                }
+                std::string body{gen_body(ops, S, D, cols, static_cast<std::uint32_t>(sj), nullptr, keep_stores ? nullptr : &needed)};
                 auto it{fid.find(body)};
                 if(it == fid.end())
                 {
@@ -253,7 +694,7 @@ namespace pe_b200
         src << "// generated by host/jit.cpp: iter section of a tree-scheduled program, S = " << S << ", load distance " << D << "\n";
         for(std::size_t f{}; f < bodies.size(); ++f)
         {
-            src << "__device__ __noinline__ uint32_t jf" << f << "(char* const wl, uint32_t const stream, uint32_t const enm";
+            src << "__device__ __forceinline__ uint32_t jf" << f << "(char* const wl, uint32_t const stream, uint32_t const enm";
             for(std::size_t ci{}; ci < n_cols[f]; ++ci) { src << ", uint32_t const k" << ci; }
             src << ")\n{\n" << bodies[f] << "}\n";
         }
@@ -261,22 +702,38 @@ namespace pe_b200
             << "    uint32_t const enm = (en[0] ? 1u : 0u) | (en[1] ? 2u : 0u) | (en[2] ? 4u : 0u) | (en[3] ? 8u : 0u);\n    uint32_t fm = 0u;\n";
         for(std::size_t ph{}; ph < n_ph; ++ph)
         {
-            // streams that call the same function with the same columns share a case
-            std::map<std::pair<int, std::vector<std::uint32_t>>, std::vector<int>> by_f;
+            // every function is inlined exactly once per phase (a callee would have to move the memory descriptor into a
+            // uniform register before every access): the first switch picks the function and its column arguments for this
+            // warp's stream, the second one runs it
+            std::size_t max_cols{};
+            std::set<int> used;
             for(int sj{}; sj < S; ++sj)
             {
-                if(call[ph][static_cast<std::size_t>(sj)] >= 0) { by_f[{call[ph][static_cast<std::size_t>(sj)], call_cols[ph][static_cast<std::size_t>(sj)]}].push_back(sj); }
+                if(call[ph][static_cast<std::size_t>(sj)] >= 0)
+                {
+                    used.insert(call[ph][static_cast<std::size_t>(sj)]);
+                    max_cols = std::max(max_cols, call_cols[ph][static_cast<std::size_t>(sj)].size());
+                }
             }
-            src << "    switch(warp)\n    {\n";
-            for(auto const& [fc, ss]: by_f)
+            src << "    {\n        uint32_t f = 0xffffffffu";
+            for(std::size_t ci{}; ci < max_cols; ++ci) { src << ", a" << ci << " = 0u"; }
+            src << ";\n        switch(warp)\n        {\n";
+            for(int sj{}; sj < S; ++sj)
             {
-                src << "       ";
-                for(int const sj: ss) { src << " case " << sj << ":"; }
-                src << " fm |= jf" << fc.first << "(wl, warp, enm";
-                for(auto const c: fc.second) { src << ", " << c << "u"; }
+                if(call[ph][static_cast<std::size_t>(sj)] < 0) { continue; }
+                src << "            case " << sj << ": f = " << call[ph][static_cast<std::size_t>(sj)] << "u;";
+                auto const& cc{call_cols[ph][static_cast<std::size_t>(sj)]};
+                for(std::size_t ci{}; ci < cc.size(); ++ci) { src << " a" << ci << " = " << cc[ci] << "u;"; }
+                src << " break;\n";
+            }
+            src << "            default: break;\n        }\n        switch(f)\n        {\n";
+            for(int const f: used)
+            {
+                src << "            case " << f << ": fm |= jf" << f << "(wl, warp, enm";
+                for(std::size_t ci{}; ci < n_cols[static_cast<std::size_t>(f)]; ++ci) { src << ", a" << ci; }
                 src << "); break;\n";
             }
-            src << "        default: break;\n    }\n";
+            src << "            default: break;\n        }\n    }\n";
             if(ph + 1 < n_ph) { src << "    group_sync<CL>();\n"; }
         }
         src << "#pragma unroll\n    for(int j = 0; j < 4; ++j)\n    {\n        if((fm >> j) & 1u) { fail[j] = true; }\n    }\n}\n";
@@ -354,5 +811,5 @@ namespace pe_b200
         return true;
     }
 
-    int jit_load_distance() { return std::clamp(env_int("PE_B200_JIT_D", 2), 0, 8); }
+    int jit_load_distance() { return std::clamp(env_int("PE_B200_JIT_D", 1), 0, 8); }
 }  // namespace pe_b200

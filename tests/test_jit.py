@@ -46,7 +46,7 @@ def test_generator_covers_linear_transient_and_shares_isomorphic_subtrees():
     b.compile_host()
     src = _source(b, pe.MODE_TR)
     assert "pe_jit_iter" in src and "jcap(" in src and "jrcp(" in src
-    n_funcs = src.count("__device__ __noinline__")
+    n_funcs = src.count("__device__ __forceinline__ uint32_t jf")
     n_calls = src.count("fm |= jf")
     assert 0 < n_funcs < 8 * 8  # (stream, phase) functions are shared between isomorphic sub-trees
     assert n_calls >= n_funcs
