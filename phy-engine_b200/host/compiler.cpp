@@ -574,6 +574,24 @@ namespace pe_b200
                         A_set(ps, k, k, &v.d[0], true);
                         break;
                     }
+                    case E_XFMR:
+                    {
+                        // pins P,Q,S,T, branches kP,kS (transformer.h:66-99): B/C assign +-1 on both windings, the primary row
+                        // accumulates -/+n on the secondary nodes (Vp - n Vs = 0), the secondary row is Is + n Ip = 0
+                        int const kS{k + 1};
+                        val const one{constant(1.0)};
+                        A_set(ps, n0, k, &one, false);
+                        A_set(ps, n1, k, &one, true);
+                        A_set(ps, k, n0, &one, false);
+                        A_set(ps, k, n1, &one, true);
+                        A_set(ps, n2, kS, &one, false);
+                        A_set(ps, n3, kS, &one, true);
+                        A_add(ps, k, n2, v.p[0], true);
+                        A_add(ps, k, n3, v.p[0], false);
+                        A_set(ps, kS, kS, &one, false);
+                        A_set(ps, kS, k, &v.p[0], false);
+                        break;
+                    }
                     case E_OPAMP:
                     {
                         // pins +,-,OUT+,OUT- (op_amp.h:64-83): B/C assign on the outputs, C accumulates -/+mu on the inputs

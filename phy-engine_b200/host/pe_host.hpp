@@ -34,6 +34,7 @@ namespace pe_b200
         E_CCVS = 11,
         E_SWITCH = 12,
         E_PN = 13,
+        E_XFMR = 14,  // ideal transformer (transformer.h)
         E_OPAMP = 17,
         E_CMP = 19,  // comparator: the analog -> digital boundary (controller/comparator.h)
         E_NPN = 50,

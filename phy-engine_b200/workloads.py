@@ -208,6 +208,30 @@ def bridge_rectifier(v: float = 5.0, r_load: float = 1e3, r_src: float = 10.0):
     return nl, {"V": src, "Rs": rs, "B": br, "R": rl}
 
 
+def transformer_stage(vac: bool = False, n: float = 4.0):
+    """Source with series resistance -> ideal transformer (element 14, model/models/linear/transformer.h) -> RC load on
+    the secondary; the secondary's low side is grounded through a resistor so that every node has a DC path."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, 3.0, 2e5, 30.0) if vac else nl.add(pe.VDC, 3.0)
+    rs = nl.add(pe.R, 50.0)
+    tx = nl.add(pe.TRANSFORMER, n)
+    rl = nl.add(pe.R, 1e3)
+    cl = nl.add(pe.C, 1e-8)
+    rg = nl.add(pe.R, 10.0)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, rs, 0)
+    nl.wire(rs, 1, tx, 0)   # P
+    nl.wire(tx, 1, g, 0)    # Q
+    nl.wire(tx, 2, rl, 0)   # S
+    nl.wire(tx, 3, rg, 0)   # T
+    nl.wire(rg, 1, g, 0)
+    nl.wire(rl, 1, tx, 3)
+    nl.wire(cl, 0, tx, 2)
+    nl.wire(cl, 1, tx, 3)
+    return nl, {"V": src, "Rs": rs, "TX": tx, "R": rl, "C": cl}
+
+
 def linear_zoo(vac: bool = False):
     """One netlist with every in-scope linear element: R, C, L, VDC / VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, op-amp and a
     closed + an open single-pole switch (stamps of SURVEY.md Appendix A).  Every node has a DC path to ground."""

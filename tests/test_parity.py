@@ -388,3 +388,38 @@ def test_linear_zoo_every_linear_element(ref, abi, at):
     else:
         assert_close(b.solution(), want["x"].real, "linear zoo " + at)
         assert b.total_solves == int(want["solves"].sum())
+
+
+@pytest.mark.parametrize("at", ["DC", "TR", "AC"])
+def test_ideal_transformer(ref, abi, at):
+    # transformer.h:66-99 (two branch rows: Vp - n Vs = 0, Is + n Ip = 0), turns ratio swept per instance
+    n_inst = 21
+    nl, info = wl.transformer_stage(vac=at != "DC")
+    rng = np.random.default_rng(31)
+    over = [(info["TX"], "n", rng.uniform(0.5, 8.0, n_inst)), (info["R"], "r", rng.uniform(500.0, 2000.0, n_inst)), (info["Rs"], "r", rng.uniform(20.0, 100.0, n_inst))]
+    code = {"DC": pe.DC, "TR": pe.TR, "AC": pe.AC}[at]
+    kw = {"t_step": 1e-7, "t_stop": 3e-6} if at == "TR" else ({"ac": (pe.SWEEP_LOG, 1e4, 1e8, 11)} if at == "AC" else {})
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at == "TR":
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if at == "AC":
+        b.set_ac_sweep(*kw["ac"])
+    assert b.analyze(), c.abi.last_error()
+    if at == "AC":
+        assert_close(b.ac_solution(), want["x"], "transformer AC")
+    else:
+        x = b.solution()
+        assert_close(x, want["x"].real, "transformer " + at)
+        assert b.total_solves == int(want["solves"].sum())
+        if at == "DC":
+            # the ideal transformer relation itself: V(P) - V(Q) = n (V(S) - V(T))
+            up, uq = c.pin_unknown(info["TX"], 0), c.pin_unknown(info["TX"], 1)
+            us, ut = c.pin_unknown(info["TX"], 2), c.pin_unknown(info["TX"], 3)
+            vq = 0.0 if uq < 0 else x[:, uq]
+            assert_close(x[:, up] - vq, over[0][2] * (x[:, us] - x[:, ut]), "Vp = n Vs")
