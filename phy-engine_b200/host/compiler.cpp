@@ -256,6 +256,19 @@ namespace pe_b200
                             }
                             break;
                         }
+                        case E_XFMR_CT:
+                        {
+                            // n_half = 2 n_total (prepare_foundation, transformer_center_tap.h:72-76), invnh = 1 / n_half (:99, :109, :119)
+                            if(v.p[0].cst) { v.d[0] = constant(1.0 / (2.0 * v.p[0].nom)); }
+                            else
+                            {
+                                // one op (prep ops of an element do not depend on each other): 2 * 0.25 / n is the same real
+                                // number as 1 / (2 n), both scalings by two are exact, so the quotient rounds identically
+                                v.d[0] = inst_slot(1.0 / (2.0 * v.p[0].nom));
+                                emit(prep, PE_OP_MUL2DIV, {v.d[0].op, constant(0.25).op, v.p[0].op});
+                            }
+                            break;
+                        }
                         case E_SWITCH:
                         {
                             // r_contact = cut_through ? 0.0 : mna.r_open (switch.h:93, circuit.h:1012)
@@ -590,6 +603,40 @@ namespace pe_b200
                         A_add(ps, k, n3, v.p[0], false);
                         A_set(ps, kS, kS, &one, false);
                         A_set(ps, kS, k, &v.p[0], false);
+                        break;
+                    }
+                    case E_XFMR_CT:
+                    {
+                        // pins P,Q,S1,CT,S2, branches kP,kH1,kH2 (transformer_center_tap.h:80-125).  The coupling terms are
+                        // stamped when the nominal n_half is non-zero (the reference tests n_half != 0.0 per instance; a
+                        // swept ratio that reaches 0 is not supported).
+                        int const n4{nidx(e.pin_node[4])};
+                        int const kH1{k + 1}, kH2{k + 2};
+                        val const one{constant(1.0)};
+                        bool const coupled{v.p[0].nom != 0.0};
+                        A_set(ps, n0, k, &one, false);
+                        A_set(ps, n1, k, &one, true);
+                        A_set(ps, n2, kH1, &one, false);
+                        A_set(ps, n3, kH1, &one, true);
+                        A_set(ps, n3, kH2, &one, false);
+                        A_set(ps, n4, kH2, &one, true);
+                        A_set(ps, kH1, n2, &one, false);
+                        A_set(ps, kH1, n3, &one, true);
+                        if(coupled)
+                        {
+                            A_add(ps, kH1, n0, v.d[0], true);
+                            A_add(ps, kH1, n1, v.d[0], false);
+                        }
+                        A_set(ps, kH2, n3, &one, false);
+                        A_set(ps, kH2, n4, &one, true);
+                        if(coupled)
+                        {
+                            A_add(ps, kH2, n0, v.d[0], true);
+                            A_add(ps, kH2, n1, v.d[0], false);
+                            A_set(ps, k, k, &one, false);
+                            A_set(ps, k, kH1, &v.d[0], false);
+                            A_set(ps, k, kH2, &v.d[0], false);
+                        }
                         break;
                     }
                     case E_OPAMP:

@@ -35,6 +35,7 @@ namespace pe_b200
         E_SWITCH = 12,
         E_PN = 13,
         E_XFMR = 14,  // ideal transformer (transformer.h)
+        E_XFMR_CT = 16,  // centre-tapped transformer (transformer_center_tap.h)
         E_OPAMP = 17,
         E_CMP = 19,  // comparator: the analog -> digital boundary (controller/comparator.h)
         E_NPN = 50,
@@ -63,7 +64,7 @@ namespace pe_b200
     };
 
     constexpr int k_max_attr = 10;
-    constexpr int k_max_pins = 4;
+    constexpr int k_max_pins = 5;
 
     struct elem_desc
     {
@@ -85,7 +86,7 @@ namespace pe_b200
     {
         elem_desc const* d{};
         double attr[k_max_attr]{};  // internal units (VAC/IAC: omega rad/s, phase rad — VAC.h:29-50)
-        int pin_node[k_max_pins]{-2, -2, -2, -2};  // -2 unconnected, -1 ground, >= 0 node id (creation order)
+        int pin_node[k_max_pins]{-2, -2, -2, -2, -2};  // -2 unconnected, -1 ground, >= 0 node id (creation order)
     };
 
     // environment (circuits/environment/environment.h:7-22)

@@ -232,6 +232,32 @@ def transformer_stage(vac: bool = False, n: float = 4.0):
     return nl, {"V": src, "Rs": rs, "TX": tx, "R": rl, "C": cl}
 
 
+def center_tap_stage(vac: bool = False, n_total: float = 2.0):
+    """Source with series resistance -> centre-tapped transformer (element 16, transformer_center_tap.h) -> two unequal
+    resistive half loads (one with a shunt capacitor) against the grounded centre tap."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, 3.0, 2e5, 30.0) if vac else nl.add(pe.VDC, 3.0)
+    rs = nl.add(pe.R, 50.0)
+    tx = nl.add(pe.TRANSFORMER_CT, n_total)
+    r1, r2 = nl.add(pe.R, 1e3), nl.add(pe.R, 2.2e3)
+    c1 = nl.add(pe.C, 1e-8)
+    rg = nl.add(pe.R, 5.0)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, rs, 0)
+    nl.wire(rs, 1, tx, 0)   # P
+    nl.wire(tx, 1, g, 0)    # Q
+    nl.wire(tx, 3, rg, 0)   # CT through a small resistor to ground
+    nl.wire(rg, 1, g, 0)
+    nl.wire(tx, 2, r1, 0)   # S1
+    nl.wire(r1, 1, tx, 3)
+    nl.wire(c1, 0, tx, 2)
+    nl.wire(c1, 1, tx, 3)
+    nl.wire(tx, 4, r2, 0)   # S2
+    nl.wire(r2, 1, tx, 3)
+    return nl, {"V": src, "Rs": rs, "TX": tx, "R1": r1, "R2": r2, "C": c1}
+
+
 def linear_zoo(vac: bool = False):
     """One netlist with every in-scope linear element: R, C, L, VDC / VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, op-amp and a
     closed + an open single-pole switch (stamps of SURVEY.md Appendix A).  Every node has a DC path to ground."""

@@ -423,3 +423,36 @@ def test_ideal_transformer(ref, abi, at):
             us, ut = c.pin_unknown(info["TX"], 2), c.pin_unknown(info["TX"], 3)
             vq = 0.0 if uq < 0 else x[:, uq]
             assert_close(x[:, up] - vq, over[0][2] * (x[:, us] - x[:, ut]), "Vp = n Vs")
+
+
+@pytest.mark.parametrize("at", ["DC", "TR", "AC"])
+def test_center_tap_transformer(ref, abi, at):
+    # transformer_center_tap.h:72-125 (n_half = 2 n_total, three branch rows), ratio swept per instance
+    n_inst = 17
+    nl, info = wl.center_tap_stage(vac=at != "DC")
+    rng = np.random.default_rng(37)
+    over = [(info["TX"], "n_total", rng.uniform(0.5, 6.0, n_inst)), (info["R1"], "r", rng.uniform(500.0, 2000.0, n_inst)), (info["R2"], "r", rng.uniform(500.0, 4000.0, n_inst))]
+    code = {"DC": pe.DC, "TR": pe.TR, "AC": pe.AC}[at]
+    kw = {"t_step": 1e-7, "t_stop": 3e-6} if at == "TR" else ({"ac": (pe.SWEEP_LOG, 1e4, 1e8, 11)} if at == "AC" else {})
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at == "TR":
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if at == "AC":
+        b.set_ac_sweep(*kw["ac"])
+    assert b.analyze(), c.abi.last_error()
+    if at == "AC":
+        assert_close(b.ac_solution(), want["x"], "centre-tap transformer AC")
+    else:
+        assert_close(b.solution(), want["x"].real, "centre-tap transformer " + at)
+        assert b.total_solves == int(want["solves"].sum())
+    # the solo (reference-compatible) path with the constant-folded ratio
+    rc, rok, _ = ref_solo(nl, code, ref, **({"tr": (1e-7, 3e-6)} if at == "TR" else ({"omega": 1e6} if at == "AC" else {})))
+    gc, gok = gpu_solo(nl, code, abi, **({"tr": (1e-7, 3e-6)} if at == "TR" else ({"omega": 1e6} if at == "AC" else {})))
+    assert rok and gok, gc.abi.last_error()
+    assert_close(gc.solution(), rc.solution(), "centre-tap transformer solo " + at)
