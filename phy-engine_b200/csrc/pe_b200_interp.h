@@ -258,6 +258,16 @@ namespace pe_interp
                     pc += 4;
                     break;
                 }
+                case PE_OP_RELAY_EVAL:
+                {
+                    uint32_t const oe = PE_LDW(pc + 1), orc = PE_LDW(pc + 2);
+                    double en_ = ld(c, oe), rc = 0.0;
+                    pe_models::relay_eval(ld(c, PE_LDW(pc + 3)), ld(c, PE_LDW(pc + 4)), ld(c, PE_LDW(pc + 5)), ld(c, PE_LDW(pc + 6)), ld(c, PE_LDW(pc + 7)), en_, rc);
+                    st(c, oe, en_, live);
+                    st(c, orc, rc, live);
+                    pc += 8;
+                    break;
+                }
                 case PE_OP_CAP_STEP:
                 {
                     uint32_t const oh = PE_LDW(pc + 1), og = PE_LDW(pc + 2);

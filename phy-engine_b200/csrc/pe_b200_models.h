@@ -293,4 +293,20 @@ namespace pe_models
         req = PE_DIV(PE_MUL(2.0, L), dt);
         ueq = PE_SUB(-v_prev, PE_MUL(req, i_prev));
     }
+
+    // iterate_dc_define(relay) (relay.h:81-94): the coil voltage of the previous solve moves the state, the contact is a
+    // short (0) when engaged and mna.r_open otherwise
+    PE_HD void relay_eval(double vcp, double vcn, double von, double voff, double r_open, double& engaged, double& r_contact)
+    {
+        double const vctrl = PE_SUB(vcp, vcn);
+        if(engaged == 0.0)
+        {
+            if(vctrl >= von) { engaged = 1.0; }
+        }
+        else
+        {
+            if(vctrl <= voff) { engaged = 0.0; }
+        }
+        r_contact = engaged != 0.0 ? 0.0 : r_open;
+    }
 }  // namespace pe_models

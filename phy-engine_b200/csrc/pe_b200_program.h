@@ -80,6 +80,9 @@ extern "C"
         PE_OP_CAP_STEP = 20,  // [hist][prev_g][C][dt][va][vb]
         PE_OP_IND_STEP = 21,  // [req][ueq][L][dt][va][vb][ib]
 
+        // relay (controller/relay.h:74-105): hysteresis on the coil voltage, contact resistance 0 / r_open
+        PE_OP_RELAY_EVAL = 22,  // [engaged][r_contact] <- [vcp][vcn][Von][Voff][r_open]   (engaged: 0.0 / 1.0, updated in place)
+
         // PN junction (PN_junction.h)
         PE_OP_PN_PREP = 30,   // [is_eff][isr_eff][bv_eff][ut][uth] <- [Is][Isr][Area][N][Temp][Ibv][Bv][bv_set]
         PE_OP_PN_EVAL = 31,   // [ud_last][geq][ieq] <- [va][vb][is_eff][isr_eff][bv_eff][ut][uth][N][Nr][bv_set]

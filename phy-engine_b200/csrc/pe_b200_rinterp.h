@@ -520,6 +520,15 @@ namespace pe_rinterp
                 PE_STR(1, gv);
                 return V_OK;
             }
+            case PE_OP_RELAY_EVAL:
+            {
+                vd<J> en_ = PE_LDR(0), rc;
+                vd<J> const vp = PE_LDR(2), vn = PE_LDR(3), von = PE_LDR(4), voff = PE_LDR(5), ro = PE_LDR(6);
+                for(int j = 0; j < J; ++j) { pe_models::relay_eval(vp.v[j], vn.v[j], von.v[j], voff.v[j], ro.v[j], en_.v[j], rc.v[j]); }
+                PE_STR(0, en_);
+                PE_STR(1, rc);
+                return V_OK;
+            }
             case PE_OP_IND_STEP:
             {
                 vd<J> const L = PE_LDR(2), dt = PE_LDR(3), va = PE_LDR(4), vb = PE_LDR(5), ib = PE_LDR(6);

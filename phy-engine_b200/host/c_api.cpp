@@ -628,19 +628,28 @@ extern "C"
             return 0;
         }
         if(pe_b200_dev_set(b->device) != 0) { return 1; }
+        // parameters whose device rows are consecutive travel as one strided 2-D copy (one DMA descriptor instead of one
+        // per 80 KB row: a table of 2000 parameters is a handful of copies)
+        std::vector<std::int64_t> slot(n_params);
         for(size_t k{}; k < n_params; ++k)
         {
             int const ei{elem_of(*b->parent, vec_pos[k], chunk_pos[k])};
             int const idx{b->parent->nl.find_attribute(ei, names[k], std::strlen(names[k]))};
-            double const* src{values + k * b->n_inst};
             auto& v{b->sweeps[{ei, idx}]};
-            v.assign(1, src[0]);  // nominal (lane-0) value for the symbolic phase; the full row lives on the device only
-            auto* dst{static_cast<double*>(b->d_wi.p) + static_cast<std::int64_t>(b->cc->swept_slot.at({ei, idx})) * b->LSi};
-            if(pe_b200_dev_h2d(dst, src, b->n_inst * sizeof(double), b->stream) != 0)
+            v.assign(1, values[k * b->n_inst]);  // nominal (lane-0) value for the symbolic phase; the full row lives on the device only
+            slot[k] = static_cast<std::int64_t>(b->cc->swept_slot.at({ei, idx}));
+        }
+        for(size_t k{}; k < n_params;)
+        {
+            size_t e{k + 1};
+            while(e < n_params && slot[e] == slot[e - 1] + 1) { ++e; }
+            auto* dst{static_cast<double*>(b->d_wi.p) + slot[k] * b->LSi};
+            if(pe_b200_dev_h2d_2d(dst, static_cast<std::size_t>(b->LSi) * sizeof(double), values + k * b->n_inst, b->n_inst * sizeof(double), b->n_inst * sizeof(double), e - k, b->stream) != 0)
             {
                 set_last_error(std::string{"circuit_batch_set_params: "} + pe_b200_dev_last_error());
                 return 1;
             }
+            k = e;
         }
         // the caller's buffer may be reused as soon as we return
         return pe_b200_dev_sync(b->stream) == 0 ? 0 : 1;

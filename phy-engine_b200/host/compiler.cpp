@@ -184,6 +184,12 @@ namespace pe_b200
                             break;
                         case E_VAC:
                         case E_IAC: v.s[0] = inst_slot(0.0); break;
+                        case E_RELAY:
+                            // state: engaged (the "Engaged" attribute is its initial value), contact resistance; nominal for the
+                            // pivot search = closed contact, so that the static order never pivots on D(k,k)
+                            v.s[0] = inst_slot(v.p[2].nom != 0.0 ? 1.0 : 0.0);
+                            v.s[1] = inst_slot(0.0);
+                            break;
                         case E_PN:
                             v.s[0] = inst_slot(0.0);
                             v.s[1] = inst_slot(k_nl_nominal);
@@ -585,6 +591,17 @@ namespace pe_b200
                     {
                         BC(ps, n0, n1, k);  // switch.h:85-104
                         A_set(ps, k, k, &v.d[0], true);
+                        break;
+                    }
+                    case E_RELAY:
+                    {
+                        // pins C+,C-,A,B (relay.h:74-105): the coil draws no current; the contact is a switch whose state follows
+                        // the coil voltage of the previous solve (evaluated in every solve_once, AC included: iterate_ac falls
+                        // back to iterate_dc)
+                        double const r_open{in.env.r_open > 0.0 ? in.env.r_open : 1e12};
+                        emit(ps.head, PE_OP_RELAY_EVAL, {v.s[0].op, v.s[1].op, vx(e.pin_node[0]).op, vx(e.pin_node[1]).op, v.p[0].op, v.p[1].op, constant(r_open).op});
+                        BC(ps, n2, n3, k);
+                        A_set(ps, k, k, &v.s[1], true);
                         break;
                     }
                     case E_XFMR:
@@ -1293,6 +1310,7 @@ namespace pe_b200
                 {
                     case PE_OP_SINCOS:
                     case PE_OP_CAP_STEP:
+                    case PE_OP_RELAY_EVAL:
                     case PE_OP_IND_STEP: return 2;
                     case PE_OP_PN_PREP: return 5;
                     case PE_OP_PN_EVAL:

@@ -39,6 +39,8 @@ namespace pe_b200
             // pins P, Q, S1, CT, S2; branches kP, kH1, kH2; n_total = Vp / V(S1 - S2) (transformer_center_tap.h:8-22)
             {E_XFMR_CT, "Transformer Center Tap", 5, 3, 1, {"n_total"}, {1.0}, 1, false},
             {E_OPAMP, "OpAmp", 4, 1, 1, {"mu"}, {1.0e5}, 1, false},
+            // pins C+, C- (coil), A, B (contact); one branch; Von, Voff, Engaged (relay.h:8-22: non-linear, so solve() iterates)
+            {E_RELAY, "Relay", 4, 1, 3, {"Von", "Voff", "Engaged"}, {5.0, 3.0, 0.0}, 2, true},
             // pins A, B (analog inputs), o (digital output): no MNA stamp; its state is vA >= vB at digital_clk (comparator.h:73-108)
             {E_CMP, "Comparator", 3, 0, 2, {"Ll", "Hl"}, {0.0, 5.0}, 2, false, true},
             {E_NPN, "NPN BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},

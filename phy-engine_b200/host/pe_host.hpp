@@ -37,6 +37,7 @@ namespace pe_b200
         E_XFMR = 14,  // ideal transformer (transformer.h)
         E_XFMR_CT = 16,  // centre-tapped transformer (transformer_center_tap.h)
         E_OPAMP = 17,
+        E_RELAY = 18,  // controller/relay.h
         E_CMP = 19,  // comparator: the analog -> digital boundary (controller/comparator.h)
         E_NPN = 50,
         E_PNP = 51,

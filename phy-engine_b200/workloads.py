@@ -258,6 +258,32 @@ def center_tap_stage(vac: bool = False, n_total: float = 2.0):
     return nl, {"V": src, "Rs": rs, "TX": tx, "R1": r1, "R2": r2, "C": c1}
 
 
+def relay_stage(vac: bool = False, v_ctl: float = 6.0):
+    """A relay (element 18, controller/relay.h): the coil hangs on a resistive divider driven by a control source (DC, or a
+    sine that crosses both hysteresis thresholds), the contact switches a 5 V supply onto an RC load."""
+    nl = Netlist()
+    g = nl.ground()
+    ctl = nl.add(pe.VAC, 8.0, 2.5e5, 0.0) if vac else nl.add(pe.VDC, v_ctl)
+    ra, rb = nl.add(pe.R, 1e3), nl.add(pe.R, 9e3)
+    ry = nl.add(pe.RELAY, 5.0, 3.0)
+    vs = nl.add(pe.VDC, 5.0)
+    rl = nl.add(pe.R, 470.0)
+    cl = nl.add(pe.C, 2e-9)
+    nl.wire(ctl, 1, g, 0)
+    nl.wire(ctl, 0, ra, 0)
+    nl.wire(ra, 1, rb, 0)
+    nl.wire(rb, 1, g, 0)
+    nl.wire(ry, 0, ra, 1)   # C+ on the divider tap
+    nl.wire(ry, 1, g, 0)    # C-
+    nl.wire(vs, 1, g, 0)
+    nl.wire(vs, 0, ry, 2)   # A
+    nl.wire(ry, 3, rl, 0)   # B
+    nl.wire(rl, 1, g, 0)
+    nl.wire(cl, 0, ry, 3)
+    nl.wire(cl, 1, g, 0)
+    return nl, {"Vctl": ctl, "Ra": ra, "Rb": rb, "RY": ry, "Vs": vs, "R": rl, "C": cl}
+
+
 def linear_zoo(vac: bool = False):
     """One netlist with every in-scope linear element: R, C, L, VDC / VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, op-amp and a
     closed + an open single-pole switch (stamps of SURVEY.md Appendix A).  Every node has a DC path to ground."""

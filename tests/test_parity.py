@@ -456,3 +456,36 @@ def test_center_tap_transformer(ref, abi, at):
     gc, gok = gpu_solo(nl, code, abi, **({"tr": (1e-7, 3e-6)} if at == "TR" else ({"omega": 1e6} if at == "AC" else {})))
     assert rok and gok, gc.abi.last_error()
     assert_close(gc.solution(), rc.solution(), "centre-tap transformer solo " + at)
+
+
+@pytest.mark.parametrize("at", ["OP", "TR"])
+def test_relay_hysteresis(ref, abi, at):
+    # relay.h:74-105 -- the contact follows the coil voltage of the previous solve with hysteresis
+    # (Von 5 V, Voff 3 V); instances sit on both sides of the thresholds, the transient drives the coil through both of them
+    n_inst = 24
+    nl, info = wl.relay_stage(vac=at == "TR")
+    rng = np.random.default_rng(41)
+    over = [(info["R"], "r", rng.uniform(200.0, 900.0, n_inst)), (info["Rb"], "r", rng.uniform(4e3, 2e4, n_inst))]
+    if at == "OP":
+        over.append((info["Vctl"], "V", np.linspace(2.0, 9.0, n_inst)))
+    else:
+        over.append((info["Vctl"], "Vp", rng.uniform(4.0, 9.0, n_inst)))
+    code = pe.OP if at == "OP" else pe.TR
+    kw = {"t_step": 1e-7, "t_stop": 8e-6} if at == "TR" else {}
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at == "TR":
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    x = b.solution()
+    assert_close(x, want["x"].real, "relay " + at)
+    assert (b.newton_iters() == want["solves"]).all(), "Newton iteration counts differ from the reference"
+    if at == "OP":
+        ub = c.pin_unknown(info["RY"], 3)
+        closed = x[:, ub] > 2.5
+        assert closed.any() and (~closed).any()  # both contact states occur in the batch
