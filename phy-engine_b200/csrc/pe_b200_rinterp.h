@@ -438,7 +438,13 @@ namespace pe_rinterp
         }
         rd.open(rows);
         // a time-step update folded into the iter section (header bit 13) runs in the first Newton iteration only
-        if((h & 0x2000u) && !first_iter) { return V_OK; }
+        // (its rows are consumed all the same: a reader that feeds per-column rows from a side stream only advances that
+        // stream in next())
+        if((h & 0x2000u) && !first_iter)
+        {
+            for(uint32_t r = 0; r < rows; ++r) { (void)fetch(); }
+            return V_OK;
+        }
         uint32_t ow[13];
 #if defined(__CUDACC__)
 #pragma unroll

@@ -258,6 +258,28 @@ def center_tap_stage(vac: bool = False, n_total: float = 2.0):
     return nl, {"V": src, "Rs": rs, "TX": tx, "R1": r1, "R2": r2, "C": c1}
 
 
+def diode_rc(vac: bool = True):
+    """A diode charging an RC load next to an independent resistive divider: a non-linear transient whose plain capacitor
+    takes the folded (first Newton iteration only) companion update."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, 8.0, 2.5e5, 0.0) if vac else nl.add(pe.VDC, 5.0)
+    ra, rb = nl.add(pe.R, 1e3), nl.add(pe.R, 9e3)
+    d = nl.add(pe.PN, *pe.PN_DEFAULT)
+    rl = nl.add(pe.R, 470.0)
+    cl = nl.add(pe.C, 2e-9)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, ra, 0)
+    nl.wire(ra, 1, rb, 0)
+    nl.wire(rb, 1, g, 0)
+    nl.wire(d, 0, ra, 1)
+    nl.wire(d, 1, rl, 0)
+    nl.wire(rl, 1, g, 0)
+    nl.wire(cl, 0, d, 1)
+    nl.wire(cl, 1, g, 0)
+    return nl, {"V": src, "Ra": ra, "Rb": rb, "D": d, "R": rl, "C": cl}
+
+
 def relay_stage(vac: bool = False, v_ctl: float = 6.0):
     """A relay (element 18, controller/relay.h): the coil hangs on a resistive divider driven by a control source (DC, or a
     sine that crosses both hysteresis thresholds), the contact switches a 5 V supply onto an RC load."""

@@ -489,3 +489,23 @@ def test_relay_hysteresis(ref, abi, at):
         ub = c.pin_unknown(info["RY"], 3)
         closed = x[:, ub] > 2.5
         assert closed.any() and (~closed).any()  # both contact states occur in the batch
+
+
+def test_nonlinear_tr_with_plain_capacitor(ref, abi):
+    # regression: a companion update folded into the iter section is skipped after the first Newton iteration; the skip
+    # must still consume the op's per-column rows (shared-memory kernel, several streams per warp)
+    n_inst = 20
+    nl, info = wl.diode_rc(vac=True)
+    rng = np.random.default_rng(43)
+    over = [(info["R"], "r", rng.uniform(200.0, 900.0, n_inst)), (info["C"], "C", rng.uniform(1e-9, 4e-9, n_inst)), (info["V"], "Vp", rng.uniform(4.0, 9.0, n_inst))]
+    want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=1e-7, t_stop=4e-6)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.TR)
+    c.set_tr(1e-7, 4e-6)
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    assert b.analyze(), c.abi.last_error()
+    assert_close(b.solution(), want["x"].real, "diode + RC transient")
+    assert (b.newton_iters() == want["solves"]).all(), "Newton iteration counts differ from the reference"
