@@ -258,6 +258,23 @@ namespace pe_interp
                     pc += 4;
                     break;
                 }
+                case PE_OP_KMUT:
+                {
+                    st(c, PE_LDW(pc + 1), pe_models::k_mutual(ld(c, PE_LDW(pc + 2)), ld(c, PE_LDW(pc + 3)), ld(c, PE_LDW(pc + 4))), live);
+                    pc += 5;
+                    break;
+                }
+                case PE_OP_KIND_STEP:
+                {
+                    double ra, rb, ue;
+                    pe_models::kind_step(ld(c, PE_LDW(pc + 4)), ld(c, PE_LDW(pc + 5)), ld(c, PE_LDW(pc + 6)), PE_SUB(ld(c, PE_LDW(pc + 7)), ld(c, PE_LDW(pc + 8))), ld(c, PE_LDW(pc + 9)),
+                                         ld(c, PE_LDW(pc + 10)), ra, rb, ue);
+                    st(c, PE_LDW(pc + 1), ra, live);
+                    st(c, PE_LDW(pc + 2), rb, live);
+                    st(c, PE_LDW(pc + 3), ue, live);
+                    pc += 11;
+                    break;
+                }
                 case PE_OP_RELAY_EVAL:
                 {
                     uint32_t const oe = PE_LDW(pc + 1), orc = PE_LDW(pc + 2);

@@ -294,6 +294,18 @@ namespace pe_models
         ueq = PE_SUB(-v_prev, PE_MUL(req, i_prev));
     }
 
+    // step_changed_tr_define(coupled_inductors), one winding (coupled_inductors.h:172-186)
+    PE_HD void kind_step(double LA, double LB, double dt, double v_prev, double ia, double ib, double& rA, double& rB, double& ueq)
+    {
+        double const req_scale = PE_DIV(2.0, dt);
+        rA = PE_MUL(req_scale, LA);
+        rB = PE_MUL(req_scale, LB);
+        ueq = PE_SUB(-v_prev, PE_ADD(PE_MUL(rA, ia), PE_MUL(rB, ib)));
+    }
+
+    // M = k sqrt(L1 L2) (coupled_inductors.h:135, :170); sqrt is correctly rounded on both sides
+    PE_HD double k_mutual(double k, double L1, double L2) { return PE_MUL(k, sqrt(PE_MUL(L1, L2))); }
+
     // iterate_dc_define(relay) (relay.h:81-94): the coil voltage of the previous solve moves the state, the contact is a
     // short (0) when engaged and mna.r_open otherwise
     PE_HD void relay_eval(double vcp, double vcn, double von, double voff, double r_open, double& engaged, double& r_contact)

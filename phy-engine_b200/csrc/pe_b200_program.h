@@ -76,9 +76,15 @@ extern "C"
         PE_OP_SINCOS = 15,   // [dre][dim][Vp][phase]     dre = Vp cos(phase), dim = Vp sin(phase) (VAC.h:115-121)
         PE_OP_MUL2DIV = 16,  // [dst][a][b]       dst = 2.0 * a / b                              (2C/dt, 2L/dt)
 
+        PE_OP_KMUT = 17,     // [dst][k][L1][L2]  dst = k * sqrt(L1 * L2)    (mutual inductance, coupled_inductors.h:135, :170)
+
         // trapezoidal companions (capacitor.h:106-128, inductor.h:134-160)
         PE_OP_CAP_STEP = 20,  // [hist][prev_g][C][dt][va][vb]
         PE_OP_IND_STEP = 21,  // [req][ueq][L][dt][va][vb][ib]
+
+        // one winding of a pair of coupled inductors (coupled_inductors.h:160-200): rA = (2 / dt) LA, rB = (2 / dt) LB,
+        // ueq = -(vp - vn) - (rA ia + rB ib); winding 1: (LA, LB) = (L1, M), winding 2: (M, L2), (ia, ib) = (i1, i2) for both
+        PE_OP_KIND_STEP = 23,  // [rA][rB][ueq] <- [LA][LB][dt][vp][vn][ia][ib]
 
         // relay (controller/relay.h:74-105): hysteresis on the coil voltage, contact resistance 0 / r_open
         PE_OP_RELAY_EVAL = 22,  // [engaged][r_contact] <- [vcp][vcn][Von][Voff][r_open]   (engaged: 0.0 / 1.0, updated in place)

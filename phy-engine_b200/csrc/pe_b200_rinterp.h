@@ -526,6 +526,24 @@ namespace pe_rinterp
                 PE_STR(1, gv);
                 return V_OK;
             }
+            case PE_OP_KMUT:
+            {
+                vd<J> const k_ = PE_LDR(1), l1 = PE_LDR(2), l2 = PE_LDR(3);
+                vd<J> m_;
+                for(int j = 0; j < J; ++j) { m_.v[j] = pe_models::k_mutual(k_.v[j], l1.v[j], l2.v[j]); }
+                PE_STR(0, m_);
+                return V_OK;
+            }
+            case PE_OP_KIND_STEP:
+            {
+                vd<J> const la = PE_LDR(3), lb = PE_LDR(4), dt = PE_LDR(5), vp = PE_LDR(6), vn = PE_LDR(7), ia = PE_LDR(8), ib = PE_LDR(9);
+                vd<J> ra, rb, ue;
+                for(int j = 0; j < J; ++j) { pe_models::kind_step(la.v[j], lb.v[j], dt.v[j], PE_SUB(vp.v[j], vn.v[j]), ia.v[j], ib.v[j], ra.v[j], rb.v[j], ue.v[j]); }
+                PE_STR(0, ra);
+                PE_STR(1, rb);
+                PE_STR(2, ue);
+                return V_OK;
+            }
             case PE_OP_RELAY_EVAL:
             {
                 vd<J> en_ = PE_LDR(0), rc;

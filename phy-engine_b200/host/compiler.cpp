@@ -184,6 +184,10 @@ namespace pe_b200
                             break;
                         case E_VAC:
                         case E_IAC: v.s[0] = inst_slot(0.0); break;
+                        case E_KIND:
+                            // req11, req12 (winding 1's copy), ueq1, req12 (winding 2's copy), req22, ueq2
+                            for(int q{}; q < 6; ++q) { v.s[q] = inst_slot(0.0); }
+                            break;
                         case E_RELAY:
                             // state: engaged (the "Engaged" attribute is its initial value), contact resistance; nominal for the
                             // pivot search = closed contact, so that the static order never pivots on D(k,k)
@@ -259,6 +263,17 @@ namespace pe_b200
                                 v.d[0] = inst_slot(v.p[0].nom * std::cos(v.p[2].nom));
                                 v.d[1] = inst_slot(v.p[0].nom * std::sin(v.p[2].nom));
                                 emit(prep, PE_OP_SINCOS, {v.d[0].op, v.d[1].op, v.p[0].op, v.p[2].op});
+                            }
+                            break;
+                        }
+                        case E_KIND:
+                        {
+                            // M = k sqrt(L1 L2) (coupled_inductors.h:135, :170)
+                            if(v.p[0].cst && v.p[1].cst && v.p[2].cst) { v.d[0] = constant(pe_models::k_mutual(v.p[2].nom, v.p[0].nom, v.p[1].nom)); }
+                            else
+                            {
+                                v.d[0] = inst_slot(pe_models::k_mutual(v.p[2].nom, v.p[0].nom, v.p[1].nom));
+                                emit(prep, PE_OP_KMUT, {v.d[0].op, v.p[2].op, v.p[0].op, v.p[1].op});
                             }
                             break;
                         }
@@ -591,6 +606,40 @@ namespace pe_b200
                     {
                         BC(ps, n0, n1, k);  // switch.h:85-104
                         A_set(ps, k, k, &v.d[0], true);
+                        break;
+                    }
+                    case E_KIND:
+                    {
+                        // pins P1,P2,S1,S2, branches k1,k2 (coupled_inductors.h:92-246): both windings are B/C branches; DC / OP /
+                        // TROP: shorts; TR: Thevenin companions with the 2x2 Req matrix; AC: -j omega [[L1 M],[M L2]]
+                        int const k2{k + 1};
+                        BC(ps, n0, n1, k);
+                        BC(ps, n2, n3, k2);
+                        if(mode == prog_mode::AC)
+                        {
+                            val const w1{lane_slot(ps, ps.omega.nom * v.p[0].nom)}, w2{lane_slot(ps, ps.omega.nom * v.p[1].nom)}, wm{lane_slot(ps, ps.omega.nom * v.d[0].nom)};
+                            emit(ps.head, PE_OP_MUL, {w1.op, ps.omega.op, v.p[0].op});
+                            emit(ps.head, PE_OP_MUL, {w2.op, ps.omega.op, v.p[1].op});
+                            emit(ps.head, PE_OP_MUL, {wm.op, ps.omega.op, v.d[0].op});
+                            A_set(ps, k, k, nullptr, false, &w1, true);
+                            A_set(ps, k, k2, nullptr, false, &wm, true);
+                            A_set(ps, k2, k, nullptr, false, &wm, true);
+                            A_set(ps, k2, k2, nullptr, false, &w2, true);
+                        }
+                        else if(mode == prog_mode::TR)
+                        {
+                            std::uint32_t const i1{IOP(I_INST, k)}, i2{IOP(I_INST, k2)};
+                            emit(ps.step, PE_OP_KIND_STEP,
+                                 {v.s[0].op, v.s[1].op, v.s[2].op, v.p[0].op, v.d[0].op, dt_val().op, vx(e.pin_node[0]).op, vx(e.pin_node[1]).op, i1, i2});
+                            emit(ps.step, PE_OP_KIND_STEP,
+                                 {v.s[3].op, v.s[4].op, v.s[5].op, v.d[0].op, v.p[1].op, dt_val().op, vx(e.pin_node[2]).op, vx(e.pin_node[3]).op, i1, i2});
+                            A_set(ps, k, k, &v.s[0], true);
+                            A_set(ps, k, k2, &v.s[1], true);
+                            A_set(ps, k2, k, &v.s[3], true);
+                            A_set(ps, k2, k2, &v.s[4], true);
+                            Z_set(ps, k, &v.s[2]);
+                            Z_set(ps, k2, &v.s[5]);
+                        }
                         break;
                     }
                     case E_RELAY:
@@ -1313,6 +1362,7 @@ namespace pe_b200
                     case PE_OP_RELAY_EVAL:
                     case PE_OP_IND_STEP: return 2;
                     case PE_OP_PN_PREP: return 5;
+                    case PE_OP_KIND_STEP:
                     case PE_OP_PN_EVAL:
                     case PE_OP_PN_STEP:
                     case PE_OP_NMOS_EVAL:

@@ -36,6 +36,8 @@ namespace pe_b200
              true},
             // pins P, Q (primary), S, T (secondary); branches kP, kS; n = Vp / Vs (transformer.h:8-19)
             {E_XFMR, "Transformer", 4, 2, 1, {"n"}, {1.0}, 1, false},
+            // pins P1, P2 (winding 1), S1, S2 (winding 2); branches k1, k2 (coupled_inductors.h:8-30)
+            {E_KIND, "Coupled Inductors", 4, 2, 3, {"L1", "L2", "k"}, {1e-3, 1e-3, 0.99}, 3, false},
             // pins P, Q, S1, CT, S2; branches kP, kH1, kH2; n_total = Vp / V(S1 - S2) (transformer_center_tap.h:8-22)
             {E_XFMR_CT, "Transformer Center Tap", 5, 3, 1, {"n_total"}, {1.0}, 1, false},
             {E_OPAMP, "OpAmp", 4, 1, 1, {"mu"}, {1.0e5}, 1, false},

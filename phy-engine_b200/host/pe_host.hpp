@@ -35,6 +35,7 @@ namespace pe_b200
         E_SWITCH = 12,
         E_PN = 13,
         E_XFMR = 14,  // ideal transformer (transformer.h)
+        E_KIND = 15,  // coupled inductors (coupled_inductors.h)
         E_XFMR_CT = 16,  // centre-tapped transformer (transformer_center_tap.h)
         E_OPAMP = 17,
         E_RELAY = 18,  // controller/relay.h

@@ -280,6 +280,30 @@ def diode_rc(vac: bool = True):
     return nl, {"V": src, "Ra": ra, "Rb": rb, "D": d, "R": rl, "C": cl}
 
 
+def coupled_inductors_stage(vac: bool = False):
+    """Source with series resistance -> winding 1 of a pair of coupled inductors (element 15, coupled_inductors.h); winding 2
+    drives an RC load, its low side is grounded through a small resistor."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VAC, 3.0, 2e5, 30.0) if vac else nl.add(pe.VDC, 3.0)
+    rs = nl.add(pe.R, 50.0)
+    kl = nl.add(pe.COUPLED_INDUCTORS, 1e-3, 4e-4, 0.95)
+    rl = nl.add(pe.R, 1e3)
+    cl = nl.add(pe.C, 1e-8)
+    rg = nl.add(pe.R, 10.0)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, rs, 0)
+    nl.wire(rs, 1, kl, 0)   # P1
+    nl.wire(kl, 1, g, 0)    # P2
+    nl.wire(kl, 2, rl, 0)   # S1
+    nl.wire(kl, 3, rg, 0)   # S2
+    nl.wire(rg, 1, g, 0)
+    nl.wire(rl, 1, kl, 3)
+    nl.wire(cl, 0, kl, 2)
+    nl.wire(cl, 1, kl, 3)
+    return nl, {"V": src, "Rs": rs, "K": kl, "R": rl, "C": cl}
+
+
 def relay_stage(vac: bool = False, v_ctl: float = 6.0):
     """A relay (element 18, controller/relay.h): the coil hangs on a resistive divider driven by a control source (DC, or a
     sine that crosses both hysteresis thresholds), the contact switches a 5 V supply onto an RC load."""

@@ -509,3 +509,38 @@ def test_nonlinear_tr_with_plain_capacitor(ref, abi):
     assert b.analyze(), c.abi.last_error()
     assert_close(b.solution(), want["x"].real, "diode + RC transient")
     assert (b.newton_iters() == want["solves"]).all(), "Newton iteration counts differ from the reference"
+
+
+@pytest.mark.parametrize("at", ["DC", "TR", "TROP", "AC"])
+def test_coupled_inductors(ref, abi, at):
+    # coupled_inductors.h:92-246 (DC shorts, trapezoidal 2x2 Thevenin companion, AC -j omega [[L1 M],[M L2]])
+    n_inst = 18
+    nl, info = wl.coupled_inductors_stage(vac=at != "DC")
+    rng = np.random.default_rng(47)
+    over = [(info["K"], "L1", rng.uniform(5e-4, 2e-3, n_inst)), (info["K"], "L2", rng.uniform(2e-4, 8e-4, n_inst)), (info["K"], "k", rng.uniform(0.5, 0.99, n_inst)),
+            (info["R"], "r", rng.uniform(500.0, 2000.0, n_inst))]
+    code = {"DC": pe.DC, "TR": pe.TR, "TROP": pe.TROP, "AC": pe.AC}[at]
+    kw = {"t_step": 1e-7, "t_stop": 4e-6} if at in ("TR", "TROP") else ({"ac": (pe.SWEEP_LOG, 1e4, 1e8, 11)} if at == "AC" else {})
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at in ("TR", "TROP"):
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if at == "AC":
+        b.set_ac_sweep(*kw["ac"])
+    assert b.analyze(), c.abi.last_error()
+    if at == "AC":
+        assert_close(b.ac_solution(), want["x"], "coupled inductors AC")
+    else:
+        assert_close(b.solution(), want["x"].real, "coupled inductors " + at)
+        assert b.total_solves == int(want["solves"].sum())
+    # constant-folded M on the solo path
+    skw = {"tr": (1e-7, 4e-6)} if at in ("TR", "TROP") else ({"omega": 1e6} if at == "AC" else {})
+    rc, rok, _ = ref_solo(nl, code, ref, **skw)
+    gc, gok = gpu_solo(nl, code, abi, **skw)
+    assert rok and gok, gc.abi.last_error()
+    assert_close(gc.solution(), rc.solution(), "coupled inductors solo " + at)
