@@ -275,6 +275,16 @@ namespace pe_interp
                     pc += 11;
                     break;
                 }
+                case PE_OP_GEN_EVAL:
+                {
+                    double const tt = ld(c, PE_LDW(pc + 3)) != 0.0 ? t : 0.0;
+                    st(c, PE_LDW(pc + 1),
+                       pe_models::gen_eval((int)ld(c, PE_LDW(pc + 2)), tt, ld(c, PE_LDW(pc + 4)), ld(c, PE_LDW(pc + 5)), ld(c, PE_LDW(pc + 6)), ld(c, PE_LDW(pc + 7)), ld(c, PE_LDW(pc + 8)),
+                                           ld(c, PE_LDW(pc + 9)), ld(c, PE_LDW(pc + 10))),
+                       live);
+                    pc += 11;
+                    break;
+                }
                 case PE_OP_RELAY_EVAL:
                 {
                     uint32_t const oe = PE_LDW(pc + 1), orc = PE_LDW(pc + 2);

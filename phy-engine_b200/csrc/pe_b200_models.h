@@ -306,6 +306,29 @@ namespace pe_models
     // M = k sqrt(L1 L2) (coupled_inductors.h:135, :170); sqrt is correctly rounded on both sides
     PE_HD double k_mutual(double k, double L1, double L2) { return PE_MUL(k, sqrt(PE_MUL(L1, L2))); }
 
+    // iterate_tr_define of the four generators (sawtooth.h:92-112, square.h:92-110, pulse.h:108-146, triangle.h:92-118):
+    // t = fmod(tTime + phase / (2 pi) / freq, 1 / freq), then the wave shape; fmod is exact on both sides
+    PE_HD double gen_eval(int kind, double t_time, double vh, double vl, double freq, double duty, double phase, double tr, double tf)
+    {
+        double const T = PE_DIV(1.0, freq);
+        double const t0 = PE_ADD(t_time, PE_DIV(PE_DIV(phase, PE_MUL(2.0, 3.141592653589793)), freq));
+        double const t = fmod(t0, T);
+        if(kind == 1) { return t < PE_MUL(duty, T) ? vh : vl; }
+        if(kind == 0) { return PE_ADD(vl, PE_MUL(PE_DIV(PE_SUB(vh, vl), T), t)); }
+        if(kind == 3)
+        {
+            double const amp = PE_SUB(vh, vl);
+            double const half = PE_MUL(0.5, T);
+            double const s2 = PE_DIV(PE_MUL(2.0, amp), T);
+            return t < half ? PE_ADD(vl, PE_MUL(s2, t)) : PE_SUB(vh, PE_MUL(s2, PE_SUB(t, half)));
+        }
+        double const ton = PE_MUL(duty, T);
+        if(t < tr) { return PE_ADD(vl, PE_MUL(PE_DIV(PE_SUB(vh, vl), tr > 1e-30 ? tr : 1e-30), t)); }
+        if(t < PE_SUB(ton, tf)) { return vh; }
+        if(t < ton) { return PE_SUB(vh, PE_MUL(PE_DIV(PE_SUB(vh, vl), tf > 1e-30 ? tf : 1e-30), PE_SUB(t, PE_SUB(ton, tf)))); }
+        return vl;
+    }
+
     // iterate_dc_define(relay) (relay.h:81-94): the coil voltage of the previous solve moves the state, the contact is a
     // short (0) when engaged and mna.r_open otherwise
     PE_HD void relay_eval(double vcp, double vcn, double von, double voff, double r_open, double& engaged, double& r_contact)

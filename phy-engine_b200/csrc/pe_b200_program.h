@@ -86,6 +86,9 @@ extern "C"
         // ueq = -(vp - vn) - (rA ia + rB ib); winding 1: (LA, LB) = (L1, M), winding 2: (M, L2), (ia, ib) = (i1, i2) for both
         PE_OP_KIND_STEP = 23,  // [rA][rB][ueq] <- [LA][LB][dt][vp][vn][ia][ib]
 
+        // time-domain generators (generator/{sawtooth,square,pulse,triangle}.h: iterate_tr_define; DC = the value at t = 0)
+        PE_OP_GEN_EVAL = 24,  // [dst] <- [kind 0 saw / 1 square / 2 pulse / 3 triangle][tsel 1 = section time, 0 = t = 0][Vh][Vl][freq][duty][phase][tr][tf]
+
         // relay (controller/relay.h:74-105): hysteresis on the coil voltage, contact resistance 0 / r_open
         PE_OP_RELAY_EVAL = 22,  // [engaged][r_contact] <- [vcp][vcn][Von][Voff][r_open]   (engaged: 0.0 / 1.0, updated in place)
 

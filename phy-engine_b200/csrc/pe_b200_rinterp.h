@@ -544,6 +544,17 @@ namespace pe_rinterp
                 PE_STR(2, ue);
                 return V_OK;
             }
+            case PE_OP_GEN_EVAL:
+            {
+                vd<J> const kd = PE_LDR(1), ts = PE_LDR(2), vh = PE_LDR(3), vl = PE_LDR(4), fq = PE_LDR(5), du = PE_LDR(6), ph = PE_LDR(7), tr_ = PE_LDR(8), tf_ = PE_LDR(9);
+                vd<J> o;
+                for(int j = 0; j < J; ++j)
+                {
+                    o.v[j] = pe_models::gen_eval((int)kd.v[j], ts.v[j] != 0.0 ? t : 0.0, vh.v[j], vl.v[j], fq.v[j], du.v[j], ph.v[j], tr_.v[j], tf_.v[j]);
+                }
+                PE_STR(0, o);
+                return V_OK;
+            }
             case PE_OP_RELAY_EVAL:
             {
                 vd<J> en_ = PE_LDR(0), rc;

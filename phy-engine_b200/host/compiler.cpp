@@ -183,7 +183,11 @@ namespace pe_b200
                             v.s[1] = inst_slot(0.0);
                             break;
                         case E_VAC:
-                        case E_IAC: v.s[0] = inst_slot(0.0); break;
+                        case E_IAC:
+                        case E_GEN_SAW:
+                        case E_GEN_SQUARE:
+                        case E_GEN_PULSE:
+                        case E_GEN_TRI: v.s[0] = inst_slot(0.0); break;
                         case E_KIND:
                             // req11, req12 (winding 1's copy), ueq1, req12 (winding 2's copy), req22, ueq2
                             for(int q{}; q < 6; ++q) { v.s[q] = inst_slot(0.0); }
@@ -606,6 +610,30 @@ namespace pe_b200
                     {
                         BC(ps, n0, n1, k);  // switch.h:85-104
                         A_set(ps, k, k, &v.d[0], true);
+                        break;
+                    }
+                    case E_GEN_SAW:
+                    case E_GEN_SQUARE:
+                    case E_GEN_PULSE:
+                    case E_GEN_TRI:
+                    {
+                        // a voltage source whose value is a function of tr_duration (iterate_tr_define); iterate_dc evaluates it
+                        // at t = 0 (DC, OP, TROP), AC drives 0 V (generator/*.h)
+                        BC(ps, n0, n1, k);
+                        if(mode != prog_mode::AC)
+                        {
+                            int const code{e.d->code};
+                            double const kind{code == E_GEN_SAW ? 0.0 : (code == E_GEN_SQUARE ? 1.0 : (code == E_GEN_PULSE ? 2.0 : 3.0))};
+                            bool const has_duty{code == E_GEN_SQUARE || code == E_GEN_PULSE};
+                            val const zero{constant(0.0)};
+                            val const& duty{has_duty ? v.p[3] : zero};
+                            val const& phase{has_duty ? v.p[4] : v.p[3]};
+                            val const& tr_{code == E_GEN_PULSE ? v.p[5] : zero};
+                            val const& tf_{code == E_GEN_PULSE ? v.p[6] : zero};
+                            emit(ps.head, PE_OP_GEN_EVAL,
+                                 {v.s[0].op, constant(kind).op, constant(mode == prog_mode::TR ? 1.0 : 0.0).op, v.p[0].op, v.p[1].op, v.p[2].op, duty.op, phase.op, tr_.op, tf_.op});
+                            Z_set(ps, k, &v.s[0]);
+                        }
                         break;
                     }
                     case E_KIND:

@@ -157,7 +157,7 @@ namespace pe_b200
             }
 
             // a DOT with many terms (the update a sub-tree owes its separators sums one product per eliminated node): its
-            // own loads are made eight terms at a time right where they are consumed, in the op's own order of accumulation,
+            // own loads are made a few terms at a time (PE_B200_JIT_BLOCK, default 8; 3 measured the same) right where they are consumed, in the op's own order of accumulation,
             // instead of all ahead of the op (hundreds of registers).  ld[i] = address to load operand i from ("" = x[i] is a
             // register that already holds it)
             static constexpr std::size_t long_reads{12};
@@ -179,9 +179,10 @@ namespace pe_b200
                     q += 2;
                 }
                 if(o.flags & PE_F_SCALE) { terms.push_back({4, q, q}), ++q; }
-                for(std::size_t b{}; b < terms.size(); b += 8)
+                static std::size_t const blk{static_cast<std::size_t>(std::clamp(env_int("PE_B200_JIT_BLOCK", 8), 1, 16))};
+                for(std::size_t b{}; b < terms.size(); b += blk)
                 {
-                    std::size_t const e{std::min(terms.size(), b + 8)};
+                    std::size_t const e{std::min(terms.size(), b + blk)};
                     t << "    {\n";
                     std::set<std::size_t> loaded;
                     for(std::size_t k{b}; k < e; ++k)

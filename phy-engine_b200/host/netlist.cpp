@@ -45,6 +45,11 @@ namespace pe_b200
             {E_RELAY, "Relay", 4, 1, 3, {"Von", "Voff", "Engaged"}, {5.0, 3.0, 0.0}, 2, true},
             // pins A, B (analog inputs), o (digital output): no MNA stamp; its state is vA >= vB at digital_clk (comparator.h:73-108)
             {E_CMP, "Comparator", 3, 0, 2, {"Ll", "Hl"}, {0.0, 5.0}, 2, false, true},
+            // time-domain generators: pins +, -, one branch (generator/*.h); phase in radians
+            {E_GEN_SAW, "Sawtooth Wave Generator", 2, 1, 4, {"Vh", "Vl", "freq", "phase"}, {5.0, 0.0, 1e3, 0.0}, 4, false},
+            {E_GEN_SQUARE, "Square Wave Generator", 2, 1, 5, {"Vh", "Vl", "freq", "duty", "phase"}, {5.0, 0.0, 1e3, 0.5, 0.0}, 5, false},
+            {E_GEN_PULSE, "Pulse Wave Generator", 2, 1, 7, {"Vh", "Vl", "freq", "duty", "phase", "tr", "tf"}, {5.0, 0.0, 1e3, 0.5, 0.0, 0.0, 0.0}, 7, false},
+            {E_GEN_TRI, "Triangle Wave Generator", 2, 1, 4, {"Vh", "Vl", "freq", "phase"}, {5.0, 0.0, 1e3, 0.0}, 4, false},
             {E_NPN, "NPN BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},
             {E_PNP, "PNP BJT", 3, 0, 5, {"Is", "N", "BetaF", "Temp", "Area"}, {1e-16, 1.0, 100.0, 27.0, 1.0}, 5, true},
             {E_NMOS, "NMOSFET", 3, 0, 3, {"Kp", "lambda", "Vth"}, {1e-3, 0.0, 1.0}, 3, true},

@@ -40,6 +40,10 @@ namespace pe_b200
         E_OPAMP = 17,
         E_RELAY = 18,  // controller/relay.h
         E_CMP = 19,  // comparator: the analog -> digital boundary (controller/comparator.h)
+        E_GEN_SAW = 20,  // generator/sawtooth.h
+        E_GEN_SQUARE = 21,
+        E_GEN_PULSE = 22,
+        E_GEN_TRI = 23,
         E_NPN = 50,
         E_PNP = 51,
         E_NMOS = 52,

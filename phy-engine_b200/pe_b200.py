@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "libphyengine_b200.so")
 GROUND, R, C, L, VDC, VAC, IDC, IAC, VCCS, VCVS, CCCS, CCVS, SWITCH, PN = range(14)
 COMPARATOR = 19  # pins A, B (analog), o (digital output); properties Ll, Hl
 OPAMP = 17
+GEN_SAWTOOTH, GEN_SQUARE, GEN_PULSE, GEN_TRIANGLE = 20, 21, 22, 23  # generators: Vh, Vl, freq [, duty], phase(rad) [, tr, tf]
 COUPLED_INDUCTORS = 15  # pins P1, P2 (winding 1), S1, S2 (winding 2); properties L1, L2, k
 RELAY = 18  # pins C+, C- (coil), A, B (contact); properties Von, Voff
 TRANSFORMER_CT = 16  # centre-tapped transformer: pins P, Q, S1, CT, S2; property n_total = Vp / V(S1 - S2)
@@ -36,11 +37,11 @@ SWEEP_SINGLE, SWEEP_LINEAR, SWEEP_LOG = range(3)
 MODE_DC, MODE_TR, MODE_TROP, MODE_AC = range(4)
 
 PROPS = {GROUND: 0, R: 1, C: 1, L: 1, VDC: 1, VAC: 3, IDC: 1, IAC: 3, VCCS: 1, VCVS: 1, CCCS: 1, CCVS: 1, SWITCH: 1,
-         PN: 9, OPAMP: 1, NPN: 5, PNP: 5, NMOS: 3, PMOS: 3, BRIDGE: 0, COMPARATOR: 2, TRANSFORMER: 1, TRANSFORMER_CT: 1, RELAY: 2, COUPLED_INDUCTORS: 3}
+         PN: 9, OPAMP: 1, NPN: 5, PNP: 5, NMOS: 3, PMOS: 3, BRIDGE: 0, COMPARATOR: 2, TRANSFORMER: 1, TRANSFORMER_CT: 1, RELAY: 2, COUPLED_INDUCTORS: 3, GEN_SAWTOOTH: 4, GEN_SQUARE: 5, GEN_PULSE: 7, GEN_TRIANGLE: 4}
 PINS = {GROUND: 1, R: 2, C: 2, L: 2, VDC: 2, VAC: 2, IDC: 2, IAC: 2, VCCS: 4, VCVS: 4, CCCS: 4, CCVS: 4, SWITCH: 2,
-        PN: 2, OPAMP: 4, NPN: 3, PNP: 3, NMOS: 3, PMOS: 3, BRIDGE: 4, COMPARATOR: 3, TRANSFORMER: 4, TRANSFORMER_CT: 5, RELAY: 4, COUPLED_INDUCTORS: 4}
+        PN: 2, OPAMP: 4, NPN: 3, PNP: 3, NMOS: 3, PMOS: 3, BRIDGE: 4, COMPARATOR: 3, TRANSFORMER: 4, TRANSFORMER_CT: 5, RELAY: 4, COUPLED_INDUCTORS: 4, GEN_SAWTOOTH: 2, GEN_SQUARE: 2, GEN_PULSE: 2, GEN_TRIANGLE: 2}
 BRANCHES = {GROUND: 0, R: 0, C: 0, L: 1, VDC: 1, VAC: 1, IDC: 0, IAC: 0, VCCS: 0, VCVS: 1, CCCS: 1, CCVS: 2, SWITCH: 1,
-            PN: 0, OPAMP: 1, NPN: 0, PNP: 0, NMOS: 0, PMOS: 0, BRIDGE: 0, COMPARATOR: 0, TRANSFORMER: 2, TRANSFORMER_CT: 3, RELAY: 1, COUPLED_INDUCTORS: 2}
+            PN: 0, OPAMP: 1, NPN: 0, PNP: 0, NMOS: 0, PMOS: 0, BRIDGE: 0, COMPARATOR: 0, TRANSFORMER: 2, TRANSFORMER_CT: 3, RELAY: 1, COUPLED_INDUCTORS: 2, GEN_SAWTOOTH: 1, GEN_SQUARE: 1, GEN_PULSE: 1, GEN_TRIANGLE: 1}
 # defaults of the PN junction's 9 positional properties (PN_junction.h:22-33): Is N Isr Nr Temp Ibv Bv Bv_set Area
 PN_DEFAULT = (1e-14, 1.0, 0.0, 2.0, 27.0, 1e-3, 40.0, 1.0, 1.0)
 

@@ -304,6 +304,27 @@ def coupled_inductors_stage(vac: bool = False):
     return nl, {"V": src, "Rs": rs, "K": kl, "R": rl, "C": cl}
 
 
+def generator_rc(kind: str = "square"):
+    """A time-domain generator (elements 20-23, model/models/generator/*.h) driving an RC low-pass."""
+    nl = Netlist()
+    g = nl.ground()
+    if kind == "sawtooth":
+        src = nl.add(pe.GEN_SAWTOOTH, 4.0, -1.0, 2.5e5, 0.7)
+    elif kind == "square":
+        src = nl.add(pe.GEN_SQUARE, 4.0, -1.0, 2.5e5, 0.3, 0.7)
+    elif kind == "pulse":
+        src = nl.add(pe.GEN_PULSE, 4.0, -1.0, 2.5e5, 0.6, 0.7, 4e-7, 6e-7)
+    else:
+        src = nl.add(pe.GEN_TRIANGLE, 4.0, -1.0, 2.5e5, 0.7)
+    r = nl.add(pe.R, 1e3)
+    c = nl.add(pe.C, 1e-9)
+    nl.wire(src, 1, g, 0)
+    nl.wire(src, 0, r, 0)
+    nl.wire(r, 1, c, 0)
+    nl.wire(c, 1, g, 0)
+    return nl, {"G": src, "R": r, "C": c}
+
+
 def relay_stage(vac: bool = False, v_ctl: float = 6.0):
     """A relay (element 18, controller/relay.h): the coil hangs on a resistive divider driven by a control source (DC, or a
     sine that crosses both hysteresis thresholds), the contact switches a 5 V supply onto an RC load."""

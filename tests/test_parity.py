@@ -544,3 +544,35 @@ def test_coupled_inductors(ref, abi, at):
     gc, gok = gpu_solo(nl, code, abi, **skw)
     assert rok and gok, gc.abi.last_error()
     assert_close(gc.solution(), rc.solution(), "coupled inductors solo " + at)
+
+
+@pytest.mark.parametrize("kind", ["sawtooth", "square", "pulse", "triangle"])
+@pytest.mark.parametrize("at", ["DC", "TR", "AC"])
+def test_time_domain_generators(ref, abi, kind, at):
+    # generator/{sawtooth,square,pulse,triangle}.h -- E(k) = f(tr_duration); DC = f(0); AC drives 0 V
+    n_inst = 16
+    nl, info = wl.generator_rc(kind)
+    rng = np.random.default_rng(53)
+    over = [(info["G"], "Vh", rng.uniform(2.0, 5.0, n_inst)), (info["G"], "freq", rng.uniform(1.5e5, 4e5, n_inst)), (info["G"], "phase", rng.uniform(0.0, 6.0, n_inst)),
+            (info["R"], "r", rng.uniform(500.0, 2000.0, n_inst))]
+    if kind in ("square", "pulse"):
+        over.append((info["G"], "duty", rng.uniform(0.2, 0.8, n_inst)))
+    code = {"DC": pe.DC, "TR": pe.TR, "AC": pe.AC}[at]
+    kw = {"t_step": 5e-8, "t_stop": 1.2e-5} if at == "TR" else ({"ac": (pe.SWEEP_LOG, 1e4, 1e8, 7)} if at == "AC" else {})
+    want = refapi.run_batch(nl, code, n_inst, over, **kw)
+    assert (want["ok"] == 1).all()
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(code)
+    if at == "TR":
+        c.set_tr(kw["t_step"], kw["t_stop"])
+    b = c.batch(n_inst)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if at == "AC":
+        b.set_ac_sweep(*kw["ac"])
+    assert b.analyze(), c.abi.last_error()
+    if at == "AC":
+        assert_close(b.ac_solution(), want["x"], kind + " generator AC")
+    else:
+        assert_close(b.solution(), want["x"].real, kind + " generator " + at)
+        assert b.total_solves == int(want["solves"].sum())

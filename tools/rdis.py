@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pe_b200 as pe  # noqa: E402
 
 NAMES = {0: "END", 1: "BAR", 2: "DOT", 3: "CDOT", 10: "RECIP", 11: "MUL", 12: "SUB", 13: "COPY", 14: "VSIN", 15: "SINCOS", 16: "MUL2DIV", 17: "KMUT", 20: "CAP_STEP",
-         21: "IND_STEP", 22: "RELAY_EVAL", 23: "KIND_STEP", 30: "PN_PREP", 31: "PN_EVAL", 32: "PN_STEP", 33: "PN_ACCAP", 40: "BJT_PREP", 41: "BJT_EVAL", 50: "NMOS_EVAL", 51: "PMOS_EVAL"}
+         21: "IND_STEP", 22: "RELAY_EVAL", 23: "KIND_STEP", 24: "GEN_EVAL", 30: "PN_PREP", 31: "PN_EVAL", 32: "PN_STEP", 33: "PN_ACCAP", 40: "BJT_PREP", 41: "BJT_EVAL", 50: "NMOS_EVAL", 51: "PMOS_EVAL"}
 
 
 def program(b, mode):
