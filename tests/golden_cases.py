@@ -22,6 +22,14 @@ CASES = {
     "diode_tr_tt": {"at": pe.TR, "n_inst": 9},
     # full bridge rectifier (element 54)
     "bridge_rectifier_op": {"at": pe.OP, "n_inst": 24},
+    # the rest of SURVEY 8(a) row a4 and 8(f) row 4: transformers, coupled inductors, relay, generators
+    "transformer_tr": {"at": pe.TR, "n_inst": 12},
+    "center_tap_dc": {"at": pe.DC, "n_inst": 12},
+    "coupled_inductors_tr": {"at": pe.TR, "n_inst": 12},
+    "coupled_inductors_ac": {"at": pe.AC, "n_inst": 4},
+    "relay_tr": {"at": pe.TR, "n_inst": 16},
+    "pulse_generator_tr": {"at": pe.TR, "n_inst": 10},
+    "triangle_generator_tr": {"at": pe.TR, "n_inst": 10},
 }
 
 
@@ -71,4 +79,25 @@ def build(name):
         nl, info = wl.bridge_rectifier()
         rng = np.random.default_rng(17)
         return nl, [(info["V"], "V", rng.uniform(-8.0, 8.0, n)), (info["R"], "r", rng.uniform(200.0, 5000.0, n))], {}
+    if name == "transformer_tr":
+        nl, info = wl.transformer_stage(vac=True)
+        rng = np.random.default_rng(61)
+        return nl, [(info["TX"], "n", rng.uniform(0.5, 8.0, n)), (info["R"], "r", rng.uniform(500.0, 2000.0, n))], {"t_step": 1e-7, "t_stop": 3e-6}
+    if name == "center_tap_dc":
+        nl, info = wl.center_tap_stage(vac=False)
+        rng = np.random.default_rng(62)
+        return nl, [(info["TX"], "n_total", rng.uniform(0.5, 6.0, n)), (info["R2"], "r", rng.uniform(500.0, 4000.0, n))], {}
+    if name in ("coupled_inductors_tr", "coupled_inductors_ac"):
+        nl, info = wl.coupled_inductors_stage(vac=True)
+        rng = np.random.default_rng(63)
+        over = [(info["K"], "L1", rng.uniform(5e-4, 2e-3, n)), (info["K"], "L2", rng.uniform(2e-4, 8e-4, n)), (info["K"], "k", rng.uniform(0.5, 0.99, n))]
+        return nl, over, ({"t_step": 1e-7, "t_stop": 4e-6} if name.endswith("_tr") else {"ac": (pe.SWEEP_LOG, 1e4, 1e8, 9)})
+    if name == "relay_tr":
+        nl, info = wl.relay_stage(vac=True)
+        rng = np.random.default_rng(64)
+        return nl, [(info["Vctl"], "Vp", rng.uniform(4.0, 9.0, n)), (info["R"], "r", rng.uniform(200.0, 900.0, n))], {"t_step": 1e-7, "t_stop": 8e-6}
+    if name in ("pulse_generator_tr", "triangle_generator_tr"):
+        nl, info = wl.generator_rc("pulse" if name.startswith("pulse") else "triangle")
+        rng = np.random.default_rng(65)
+        return nl, [(info["G"], "freq", rng.uniform(1.5e5, 4e5, n)), (info["G"], "phase", rng.uniform(0.0, 6.0, n)), (info["R"], "r", rng.uniform(500.0, 2000.0, n))], {"t_step": 5e-8, "t_stop": 1.2e-5}
     raise KeyError(name)
