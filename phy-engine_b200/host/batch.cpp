@@ -189,7 +189,11 @@ namespace pe_b200
             // lanes per thread: the more lanes share one decode and the longer a workspace row (128 lanes = 1 KB), the
             // better, as long as there are enough groups for all SMs: 128-lane groups run on a cluster of two CTAs
             std::size_t const lanes_total{n_inst * std::max<std::size_t>(last_points_hint, 1)};
-            J = res_J > 0 ? res_J : ((pr.rS >= 32 && lanes_total >= 74u * 128u) ? 4 : ((pr.rS >= 32 && lanes_total >= 148u * 64u) ? 2 : 1));
+            // narrower programs (fewer sub-tree warps per group): two lanes per thread (512-byte rows) as soon as the batch still
+            // fills every SM several times over -- config D, 1e6 frequency points on 8 streams: 40.9 -> 57.1 M points/s
+            J = res_J > 0 ? res_J
+                          : ((pr.rS >= 32 && lanes_total >= 74u * 128u) ? 4
+                                                                        : (((pr.rS >= 32 && lanes_total >= 148u * 64u) || lanes_total >= 148u * 64u * 8u) ? 2 : 1));
             I = 32 * J;
             return pr.rS <= 32;
         }

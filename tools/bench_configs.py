@@ -124,6 +124,13 @@ def case_ac(n_sections, points):
 
 
 def main():
+    # PE_CFG_PATH = "streams,I,J,subtree_warps,workspace,tuning" forces a solve path (phy_engine_b200_set_default_path)
+    if os.environ.get("PE_CFG_PATH"):
+        abi = pe.bind_full_abi(pe.product())
+        assert abi.lib.phy_engine_b200_set_default_path(*[int(v) for v in os.environ["PE_CFG_PATH"].split(",")]) == 0
+    if os.environ.get("PE_CFG_ONLY_AC"):
+        case_ac(64, int(os.environ.get("PE_CFG_POINTS", "1000000")))
+        return
     n = int(os.environ.get("PE_CFG_INSTANCES", "100000"))
     rng = np.random.default_rng(1)
     nl, info = wl.diode_resistor()
