@@ -628,7 +628,7 @@ extern "C"
             return 0;
         }
         if(pe_b200_dev_set(b->device) != 0) { return 1; }
-        // parameters whose device rows are consecutive travel as one strided 2-D copy (one DMA descriptor instead of one
+        // parameters whose device rows are equally spaced travel as one strided 2-D copy (one DMA descriptor instead of one
         // per 80 KB row: a table of 2000 parameters is a handful of copies)
         std::vector<std::int64_t> slot(n_params);
         for(size_t k{}; k < n_params; ++k)
@@ -641,10 +641,17 @@ extern "C"
         }
         for(size_t k{}; k < n_params;)
         {
+            // a run of parameters whose device rows are equally spaced (every R of a ladder: rows 0, 2, 4, ...) = one copy
+            // whose destination pitch is that spacing
+            std::int64_t const d{k + 1 < n_params ? slot[k + 1] - slot[k] : 1};
             size_t e{k + 1};
-            while(e < n_params && slot[e] == slot[e - 1] + 1) { ++e; }
+            if(d > 0)
+            {
+                while(e < n_params && slot[e] - slot[e - 1] == d) { ++e; }
+            }
             auto* dst{static_cast<double*>(b->d_wi.p) + slot[k] * b->LSi};
-            if(pe_b200_dev_h2d_2d(dst, static_cast<std::size_t>(b->LSi) * sizeof(double), values + k * b->n_inst, b->n_inst * sizeof(double), b->n_inst * sizeof(double), e - k, b->stream) != 0)
+            std::size_t const dpitch{static_cast<std::size_t>(d > 0 ? d : 1) * static_cast<std::size_t>(b->LSi) * sizeof(double)};
+            if(pe_b200_dev_h2d_2d(dst, dpitch, values + k * b->n_inst, b->n_inst * sizeof(double), b->n_inst * sizeof(double), e - k, b->stream) != 0)
             {
                 set_last_error(std::string{"circuit_batch_set_params: "} + pe_b200_dev_last_error());
                 return 1;
