@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-pipeline", action="store_true", help="e2e leg on two batch handles / host threads / streams (a step's copies may overlap the other step's solve; measured +1.5 %)")
+    ap.add_argument("--e2e-pipeline", action="store_true", help="e2e leg on two batch handles / host threads / streams (a step's copies may overlap the other step's solve; measured +5 %: 20.1 vs 19.1 M solves/s)")
     return ap.parse_args()
 
 
