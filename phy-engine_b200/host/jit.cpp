@@ -812,5 +812,5 @@ namespace pe_b200
         return true;
     }
 
-    int jit_load_distance() { return std::clamp(env_int("PE_B200_JIT_D", 1), 0, 8); }
+    int jit_load_distance() { return std::clamp(env_int("PE_B200_JIT_D", 0), 0, 8); }
 }  // namespace pe_b200
