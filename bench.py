@@ -373,15 +373,19 @@ def main():
     kernel_name = ("pe_b200_tree_kernel" if rinfo["hbm"] else "pe_b200_resident_kernel") if rinfo["resident"] else "pe_b200_solve_kernel"
     if specialised:
         kernel_name = "pe_b200_jit_kernel"
+    streamed = b.last_kernel() == 2  # the stream kernel (host/stream.cpp, csrc/pe_b200_stream.cu) ran
+    if streamed:
+        kernel_name = "pe_b200_stream_kernel"
     solves_per_launch = solves / max(launches, 1)
     # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/r01_traffic.json), scaled to one launch
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic_jit.json" if specialised else "r01_traffic.json")
+    tname = "r02_traffic_stream.json" if streamed else ("r01_traffic_jit.json" if specialised else "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", tname)
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(kernel_name) and (rinfo["last_S"], rinfo["last_J"]) == (tj.get("S", 32), tj.get("J", 2)):
             traffic = tj["dram_bytes_per_solve"] * solves_per_launch
-            traffic_src = "profiles/r01_traffic.json: " + tj["capture"]
+            traffic_src = f"profiles/{tname}: " + tj["capture"]
     avg_launch_ms = kernel_ms / max(launches, 1)
     achieved = bytes_per_solve * solves_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -405,7 +409,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(args, 8e-9 * n_inst * (st["n_inst_slots"] + (rinfo["smem_slots"] if rinfo["hbm"] else st["n_lane_slots"]))),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "program": st, "resident": b.resident_info(pe.MODE_TR), "specialised_kernel": bool(specialised), "checksum": checksum,
+            "program": st, "resident": b.resident_info(pe.MODE_TR), "specialised_kernel": bool(specialised), "stream_kernel": b.stream_info(pe.MODE_TR) if streamed else None, "checksum": checksum,
         }
         emit_line(line)
     if world > 1:

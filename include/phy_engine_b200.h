@@ -163,12 +163,18 @@ extern "C"
     int circuit_batch_set_chunks(void* batch, int chunks);
     /* tuning flags of the tree-scheduled kernels (defaults = 0): bit 0 line-ahead L2 prefetch of operand rows, bit 1 ... two
      * lines ahead, bit 2 no L1 re-fetch of a DOT result after its store, bit 3 fuse small elimination steps into one op
-     * (PE_OP_CROUT2; takes effect at the next compile), bit 4 require / bit 5 forbid the specialised kernel */
+     * (PE_OP_CROUT2; takes effect at the next compile), bit 4 require / bit 5 forbid the specialised kernel, bit 6 require /
+     * bit 7 forbid the stream kernel */
     int circuit_batch_set_tuning(void* batch, unsigned flags);
     /* which kernel the last tree-streaming launch of the batch ran: 0 = the word interpreter, 1 = the specialised kernel
      * (iter section compiled to straight-line sm_100a code at run time, cached under jit_cache/ next to the library;
      * tuning bit 4 requires it, bit 5 forbids it, default: large linear batches), -1 = bad handle */
     int circuit_batch_last_kernel(void* batch);
+    /* stream kernel (large batches of large linear circuits: one warp per lane group, one word stream per group, the iter
+     * section generated as tiled code whose cold operand rows arrive by TMA bulk copies; tuning bit 6 requires it, bit 7
+     * forbids it; circuit_batch_last_kernel reports 2).  info[6] = last kernel, warps per CTA, ring stages, shared memory
+     * per CTA (bytes), tiles per solve, rows per ring stage */
+    int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
     /* tooling for the specialised kernel of a compiled batch (circuit_batch_compile_host first; no device needed): the
      * generated source of the iter section (returns its length, copies at most cap bytes), and build-or-fetch of its cubin
      * (cluster = CTAs per lane group, 1 or 2) */

@@ -24,8 +24,10 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <string>
 #include <utility>
 #include <vector>
+#include <unistd.h>
 
 #include "pe_b200_interp.h"
 #include "pe_b200_rinterp.h"
@@ -1312,6 +1314,7 @@ extern "C"
 
     // specialised kernels (host/jit.cpp): cubin -> kernel handle, loaded once per process and key
     static thread_local void const* g_jit_kernel = nullptr;
+    static thread_local int g_stream_geom[3] = {0, 0, 0};
 
     int pe_b200_jit_supported(void) { return 1; }
 
@@ -1343,6 +1346,131 @@ extern "C"
         int const rc = pe_b200_launch_resident(run, stream);
         g_jit_kernel = nullptr;
         return rc;
+    }
+
+    // ---- stream kernel (csrc/pe_b200_stream.cu + generated source, host/stream.cpp) ------------------------------------
+    int pe_b200_stream_supported(void) { return 1; }
+
+    // nvcc -cubin for sm_100a; the module holds pe_b200_stream_kernel specialised for one program and J lanes per thread
+    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, char* log, size_t log_cap)
+    {
+        char const* nv = std::getenv("PE_B200_NVCC");
+        std::string nvcc = nv != nullptr ? nv : "/usr/local/cuda/bin/nvcc";
+        if(::access(nvcc.c_str(), X_OK) != 0) { nvcc = "nvcc"; }
+        std::string const logf = std::string(out_path) + ".log";
+        std::string const cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin -DPE_SJ=" + std::to_string(J) + " '-DPE_STREAM_SOURCE=\"" + source_path +
+                                "\"' -I'" + csrc_dir + "' -o '" + out_path + "' '" + csrc_dir + "/pe_b200_stream.cu' > '" + logf + "' 2>&1";
+        int const rc = std::system(cmd.c_str());
+        if(rc != 0 && log != nullptr && log_cap > 0)
+        {
+            log[0] = 0;
+            if(FILE* f = std::fopen(logf.c_str(), "rb"))
+            {
+                size_t const n = std::fread(log, 1, log_cap - 1, f);
+                log[n] = 0;
+                std::fclose(f);
+            }
+        }
+        return rc == 0 ? 0 : 1;
+    }
+
+    int pe_b200_launch_stream(pe_b200_rrun const* run, void const* blob, size_t bytes, uint64_t key, uint32_t n_tiles, uint32_t stage_rows, void* stream)
+    {
+        (void)n_tiles;
+        if(run == nullptr || run->n_lanes <= 0) { return 0; }
+        static std::mutex mu;
+        static std::map<std::pair<int, uint64_t>, cudaKernel_t> loaded;
+        int dev = 0;
+        if(chk(cudaGetDevice(&dev), "cudaGetDevice") != 0) { return 1; }
+        int const J = run->J;
+        if(run->S != 1 || run->wsg == nullptr || (J != 1 && J != 2 && J != 4) || run->I != 32 * J || run->nonlinear != 0 || run->cplx != 0)
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: needs a real linear one-stream program in HBM form (S=%d I=%d J=%d)", run->S, run->I, J);
+            return 1;
+        }
+        cudaKernel_t k{};
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = loaded.find({dev, key});
+            if(it == loaded.end())
+            {
+                if(blob == nullptr || bytes == 0)
+                {
+                    snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: no module");
+                    return 1;
+                }
+                cudaLibrary_t lib{};
+                if(chk(cudaLibraryLoadData(&lib, blob, nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData") != 0) { return 1; }
+                if(chk(cudaLibraryGetKernel(&k, lib, "pe_b200_stream_kernel"), "cudaLibraryGetKernel(pe_b200_stream_kernel)") != 0) { return 1; }
+                it = loaded.emplace(std::make_pair(dev, key), k).first;
+            }
+            k = it->second;
+        }
+        int sms = 0, smem_max = 0;
+        if(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+           sms < 1)
+        {
+            (void)cudaGetLastError();
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: device query failed");
+            return 1;
+        }
+        // geometry: one CTA per SM, W warps each = lane groups resident per SM; every warp owns a ring of NS stages
+        int const GL = 32 * J;
+        long long const NG = ((long long)run->n_lanes + GL - 1) / GL;
+        size_t const stage_bytes = (size_t)stage_rows * 256u * (size_t)J;
+        static int const w_max = std::getenv("PE_B200_STREAM_WARPS") ? std::atoi(std::getenv("PE_B200_STREAM_WARPS")) : 8;
+        static int const ns_cap = std::getenv("PE_B200_STREAM_NS") ? std::atoi(std::getenv("PE_B200_STREAM_NS")) : 8;
+        int W = (int)std::min<long long>(std::max(1, std::min(w_max, 8)), (NG + sms - 1) / sms);
+        uint32_t ns_log = 0;
+        for(;;)
+        {
+            size_t const budget = (size_t)smem_max / (size_t)W;
+            ns_log = 0;
+            while(ns_log < 4 && (2u << ns_log) <= (uint32_t)ns_cap && (size_t)(2u << ns_log) * stage_bytes + 128u <= budget) { ++ns_log; }
+            if(((size_t)(1u << ns_log) * stage_bytes + 128u <= budget && ns_log >= 1) || W == 1) { break; }
+            --W;  // fewer resident groups per SM, deeper rings; the warps then walk over several groups
+        }
+        size_t const smem = (size_t)W * ((size_t)(1u << ns_log) * stage_bytes + 128u);
+        if(ns_log < 1 || smem > (size_t)smem_max)
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: a ring stage of %zu bytes does not fit shared memory", stage_bytes);
+            return 1;
+        }
+        if(chk(cudaFuncSetAttribute((void const*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(stream smem)") != 0) { return 1; }
+        cudaEvent_t e0{}, e1{};
+        if(g_timing)
+        {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, (cudaStream_t)stream);
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)std::min<long long>(sms, NG));
+        cfg.blockDim = dim3((unsigned)(32 * W));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cfg.numAttrs = 0;
+        pe_b200_rrun arg = *run;
+        uint32_t nsl = ns_log;
+        void* kargs[2] = {&arg, &nsl};
+        cudaError_t const le = cudaLaunchKernelExC(&cfg, (void const*)k, kargs);
+        if(g_timing)
+        {
+            cudaEventRecord(e1, (cudaStream_t)stream);
+            g_events.emplace_back(e0, e1);
+        }
+        if(le != cudaSuccess) { return chk(le, "pe_b200_stream_kernel launch"); }
+        g_launches.fetch_add(1);
+        g_stream_geom[0] = W;
+        g_stream_geom[1] = 1 << ns_log;
+        g_stream_geom[2] = (int)smem;
+        return chk(cudaGetLastError(), "pe_b200_stream_kernel launch");
+    }
+
+    // geometry of the last stream launch of this thread: warps per CTA, ring stages, dynamic shared memory per CTA
+    void pe_b200_stream_last_geometry(int* out3)
+    {
+        for(int i = 0; i < 3; ++i) { out3[i] = g_stream_geom[i]; }
     }
 
     int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream)

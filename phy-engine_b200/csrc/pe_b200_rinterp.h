@@ -129,18 +129,22 @@ namespace pe_rinterp
         uint32_t const* p_next{};
         uint32_t const* q_next{};
 
-        uint32_t head() const { return p[0]; }
-        uint32_t open(uint32_t rows)
+        PE_HD uint32_t head() const { return p[0]; }
+        PE_HD uint32_t open(uint32_t rows)
         {
             m = p[1];
             cur = 2;
             qc = q;
+            #if defined(__CUDA_ARCH__)
+            uint32_t const pcnt = (uint32_t)__popc(m);
+#else
             uint32_t const pcnt = (uint32_t)__builtin_popcount(m);
+#endif
             p_next = p + 2 + rows - pcnt;
             q_next = q + pcnt * C;
             return m;
         }
-        uint32_t next()
+        PE_HD uint32_t next()
         {
             uint32_t w;
             if(m & 1u)
@@ -156,27 +160,27 @@ namespace pe_rinterp
             return w;
         }
         // one stream per warp (C == 1): every 32-word line of the main stream starts with two prefetch bitmaps
-        void normalize()
+        PE_HD void normalize()
         {
             if(C == 1u && ((p - p0) & 31) == 0) { p += 2; }
         }
-        void start()
+        PE_HD void start()
         {
             p = p0;
             normalize();
         }
-        void close()
+        PE_HD void close()
         {
             p = p_next;
             q = q_next;
             normalize();
         }
-        void bar()
+        PE_HD void bar()
         {
             p += 1;
             normalize();
         }
-        void skip()
+        PE_HD void skip()
         {
             p = p0 + (((p - p0) >> 5) + 1) * 32;
             normalize();

@@ -70,6 +70,16 @@ namespace pe_b200
         int const w_ac{pick_warps(n_inst * ac_points, n_unk)};
         int r_real{pick_streams(n_unk)};
         int r_ac{pick_streams(n_unk)};
+        // Stream kernel (host/stream.cpp): large batches of large linear circuits are compiled with ONE stream per lane group
+        // (no parallel split of the elimination, no fill-in from it) and run one warp per group with TMA-fed tiles.  The
+        // program of the analysis to be run must consist of ops the generator covers, else the default geometry is used.
+        auto const at_now{parent->at};
+        bool const real_analysis{at_now == analyze_type::TR || at_now == analyze_type::TROP || at_now == analyze_type::OP || at_now == analyze_type::DC};
+        bool want_stream{res_stream >= 0 && res_S == 0 && res_ws != 1 && real_analysis && n_unk > 64 && !parent->nl.has_nonlinear() && pe_b200_stream_supported() != 0 &&
+                         stream_rejected_rev != parent->structure_rev &&
+                         (res_stream == 1 || (n_inst >= 4096 && std::getenv("PE_B200_NO_STREAM") == nullptr))};
+        if(want_stream) { r_real = 1; }
+        stream_mode = want_stream;  // decides where a one-stream program keeps its workspace (use_hbm)
         bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac ||
                         r_real != cc_res_real || r_ac != cc_res_ac || res_fuse != cc_fuse};
         if(!need) { return true; }
@@ -124,8 +134,37 @@ namespace pe_b200
                 }
             }
             if(!real_fits) { r_real = 0; }
+            if(want_stream && !redo)
+            {
+                auto const primary{(at_now == analyze_type::TR || at_now == analyze_type::TROP) ? prog_mode::TR : prog_mode::DC};
+                auto& pp{cc->prog[static_cast<std::size_t>(primary)]};
+                if(pp.built && pp.resident && pp.rS == 1 && stream_supported(pp))
+                {
+                    // every real-valued program the generator covers is re-laid out for it (the others run the interpreter on
+                    // the same workspace geometry)
+                    for(auto const m: {prog_mode::DC, prog_mode::TR, prog_mode::TROP})
+                    {
+                        auto& q{cc->prog[static_cast<std::size_t>(m)]};
+                        if(q.built && q.resident && q.rS == 1 && stream_supported(q)) { (void)stream_prepare(q); }
+                    }
+                }
+                else
+                {
+                    if(std::getenv("PE_B200_STREAM_DEBUG") != nullptr)
+                    {
+                        std::fprintf(stderr, "stream: rejected (built %d resident %d rS %d supported %d)\n", (int)pp.built, (int)pp.resident, pp.rS, (int)stream_supported(pp));
+                    }
+                    want_stream = false;
+                    stream_mode = false;
+                    stream_rejected_rev = parent->structure_rev;
+                    r_real = pick_streams(n_unk);
+                    cc_res_real = r_real;
+                    redo = true;
+                }
+            }
             if(!redo) { break; }
         }
+        stream_mode = want_stream;
         cc_structure_rev = parent->structure_rev;
         cc_param_rev = parent->param_rev;
         cc_dt = parent->tr.t_step;
@@ -177,7 +216,7 @@ namespace pe_b200
     {
         if(res_ws == 2) { return true; }
         if(res_ws == 1) { return false; }
-        return pr.rS > 1;
+        return pr.rS > 1 || stream_mode;
     }
 
     bool batch::pick_geometry(program const& pr, int& I, int& J) const
@@ -191,6 +230,13 @@ namespace pe_b200
             std::size_t const lanes_total{n_inst * std::max<std::size_t>(last_points_hint, 1)};
             // narrower programs (fewer sub-tree warps per group): two lanes per thread (512-byte rows) as soon as the batch still
             // fills every SM several times over -- config D, 1e6 frequency points on 8 streams: 40.9 -> 57.1 M points/s
+            if(stream_mode && pr.rS == 1)
+            {
+                // stream kernel: one warp per group; one lane per thread keeps the most warps per SM (more requests in flight)
+                J = res_J > 0 ? res_J : 1;
+                I = 32 * J;
+                return true;
+            }
             J = res_J > 0 ? res_J
                           : ((pr.rS >= 32 && lanes_total >= 74u * 128u) ? 4
                                                                         : (((pr.rS >= 32 && lanes_total >= 148u * 64u) || lanes_total >= 148u * 64u * 8u) ? 2 : 1));
@@ -501,6 +547,43 @@ namespace pe_b200
         last_I = I;
         last_J = J;
         last_S = pr.rS;
+        // Stream kernel: one-stream linear real programs (stream_mode).  The module is generated and compiled on first use
+        // (seconds: the sweeps are rolled loops) and cached; when it cannot be had the interpreter runs the same program.
+        if(stream_mode && r.wsg != nullptr && pr.rS == 1 && !nonlinear && !pr.cplx && pe_b200_stream_supported() != 0)
+        {
+            if(pr.stream_state == 0 || (pr.stream_state == 1 && pr.stream_j != J))
+            {
+                pr.stream_state = -1;
+                stream_geom g{};
+                std::string const src{stream_supported(pr) ? stream_generate(pr, g) : std::string{}};
+                if(src.empty()) { pr.stream_error = "stream: the iter section holds ops the stream kernel does not cover"; }
+                else if(stream_compile(src, J, pr.stream_blob, pr.stream_key, pr.stream_error))
+                {
+                    pr.stream_state = 1;
+                    pr.stream_j = J;
+                    pr.stream_tiles = g.n_tiles;
+                    pr.stream_stage_rows = g.stage_rows;
+                }
+            }
+            if(pr.stream_state == 1)
+            {
+                r.sched = nullptr;
+                r.n_chunks = 1;
+                if(pe_b200_launch_stream(&r, pr.stream_blob.data(), pr.stream_blob.size(), pr.stream_key, pr.stream_tiles, pr.stream_stage_rows, stream) == 0)
+                {
+                    last_jit = 2;
+                    return true;
+                }
+                pr.stream_state = -1;
+                pr.stream_error = std::string{"stream: "} + pe_b200_dev_last_error();
+            }
+            if(res_stream == 1)
+            {
+                error = pr.stream_error;
+                set_last_error(error);
+                return false;
+            }
+        }
         // Specialised kernel: linear real programs on 128-lane groups whose iter section is DOT / CAP_STEP only.  Required
         // (res_jit = 1): built on the spot if it is not in the cache (minutes for a 1000-node circuit), a failure is an
         // error; automatic: large batches take it when the cache holds it, the word interpreter runs otherwise.
@@ -522,9 +605,16 @@ namespace pe_b200
             }
             if(pr.jit_state == 1)
             {
-                if(pe_b200_launch_jit(&r, pr.jit_cubin.data(), pr.jit_cubin.size(), pr.jit_key, stream) != 0) { return dev_fail(error, "launch (specialised kernel)"); }
-                last_jit = 1;
-                return true;
+                if(pe_b200_launch_jit(&r, pr.jit_cubin.data(), pr.jit_cubin.size(), pr.jit_key, stream) == 0)
+                {
+                    last_jit = 1;
+                    return true;
+                }
+                // a cached module that does not load or launch (stale, wrong architecture, corrupt): required -> error,
+                // automatic -> the interpreting kernel runs the program
+                pr.jit_state = -1;
+                pr.jit_error = std::string{"jit: "} + pe_b200_dev_last_error();
+                if(res_jit == 1) { return dev_fail(error, "launch (specialised kernel)"); }
             }
             if(res_jit == 1)
             {
@@ -877,6 +967,7 @@ namespace pe_b200
             solo->res_prefetch = ((d.tuning & 1u) ? 1 : 0) | ((d.tuning & 2u) ? 2 : 0) | ((d.tuning & 4u) ? 0 : 4);
             solo->res_fuse = (d.tuning & 8u) ? 1 : 0;
             solo->res_jit = (d.tuning & 16u) ? 1 : ((d.tuning & 32u) ? -1 : 0);
+            solo->res_stream = (d.tuning & 64u) ? 1 : ((d.tuning & 128u) ? -1 : 0);
         }
         solo->ac = {};
         bool const ok{solo->analyze()};

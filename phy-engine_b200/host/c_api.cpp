@@ -528,15 +528,38 @@ extern "C"
 
     int circuit_batch_set_tuning(void* b, unsigned flags)
     {
-        if(b == nullptr || flags > 63u || (flags & 48u) == 48u) { return 1; }
+        if(b == nullptr || flags > 255u || (flags & 48u) == 48u || (flags & 192u) == 192u) { return 1; }
         auto* bp{static_cast<batch*>(b)};
         bp->res_prefetch = ((flags & 1u) ? 1 : 0) | ((flags & 2u) ? 2 : 0) | ((flags & 4u) ? 0 : 4);
         bp->res_fuse = (flags & 8u) ? 1 : 0;
         bp->res_jit = (flags & 16u) ? 1 : ((flags & 32u) ? -1 : 0);
+        bp->res_stream = (flags & 64u) ? 1 : ((flags & 128u) ? -1 : 0);  // stream kernel: required / forbidden
         return 0;
     }
 
     int circuit_batch_last_kernel(void* b) { return b == nullptr ? -1 : static_cast<batch*>(b)->last_jit; }
+
+    // stream kernel of the last launch: [0] last kernel (2 = stream), [1] warps per CTA, [2] ring stages, [3] shared memory
+    // per CTA, [4] tiles per solve, [5] rows per ring stage
+    int circuit_batch_stream_info(void* b, int mode, int64_t* info)
+    {
+        if(b == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        int g[3]{};
+        pe_b200_stream_last_geometry(g);
+        info[0] = bp->last_jit;
+        info[1] = g[0];
+        info[2] = g[1];
+        info[3] = g[2];
+        info[4] = info[5] = 0;
+        if(bp->cc)
+        {
+            auto const& pr{bp->cc->prog[static_cast<std::size_t>(mode)]};
+            info[4] = pr.stream_tiles;
+            info[5] = pr.stream_stage_rows;
+        }
+        return 0;
+    }
 
     int circuit_batch_resident_info(void* b, int mode, int64_t* info)
     {
@@ -940,7 +963,7 @@ extern "C"
 
     int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace, unsigned tuning)
     {
-        if(workspace < 0 || workspace > 2 || tuning > 63u || (tuning & 48u) == 48u) { return 1; }
+        if(workspace < 0 || workspace > 2 || tuning > 255u || (tuning & 48u) == 48u || (tuning & 192u) == 192u) { return 1; }
         auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
         if(streams < -1 || streams > 1024 || (streams > 0 && !pow2(streams))) { return 1; }
         if(instances_per_cta < 0 || instances_per_cta > 32 || (instances_per_cta > 0 && !pow2(instances_per_cta))) { return 1; }

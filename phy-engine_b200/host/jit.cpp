@@ -10,6 +10,7 @@
 #include "pe_host.hpp"
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -38,14 +39,56 @@ namespace pe_b200
             return h;
         }
 
-        bool read_file(std::string const& path, std::string& out)
+        // cache files are only ever read when they are regular files owned by this user (no symlinks: O_NOFOLLOW)
+        bool read_file(std::string const& path, std::string& out, bool owned = false)
         {
-            std::ifstream f(path, std::ios::binary);
-            if(!f) { return false; }
-            std::ostringstream ss;
-            ss << f.rdbuf();
-            out = ss.str();
+            int const fd{::open(path.c_str(), O_RDONLY | (owned ? O_NOFOLLOW : 0) | O_CLOEXEC)};
+            if(fd < 0) { return false; }
+            struct stat st{};
+            if(::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (owned && st.st_uid != ::geteuid()))
+            {
+                ::close(fd);
+                return false;
+            }
+            out.resize(static_cast<std::size_t>(st.st_size));
+            std::size_t got{};
+            while(got < out.size())
+            {
+                ssize_t const k{::read(fd, out.data() + got, out.size() - got)};
+                if(k <= 0) { break; }
+                got += static_cast<std::size_t>(k);
+            }
+            ::close(fd);
+            return got == out.size();
+        }
+
+        // write under a per-process temporary name, then rename into place (concurrent ranks compile the same key)
+        bool write_file_atomic(std::string const& path, std::string const& text)
+        {
+            std::string const tmp{path + ".tmp" + std::to_string(static_cast<long>(::getpid()))};
+            int const fd{::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_NOFOLLOW | O_CLOEXEC, 0600)};
+            if(fd < 0) { return false; }
+            std::size_t put{};
+            while(put < text.size())
+            {
+                ssize_t const k{::write(fd, text.data() + put, text.size() - put)};
+                if(k <= 0) { break; }
+                put += static_cast<std::size_t>(k);
+            }
+            ::close(fd);
+            if(put != text.size() || ::rename(tmp.c_str(), path.c_str()) != 0)
+            {
+                ::unlink(tmp.c_str());
+                return false;
+            }
             return true;
+        }
+
+        // a directory this user owns and nobody else can write to
+        bool private_dir(std::string const& d)
+        {
+            struct stat st{};
+            return ::lstat(d.c_str(), &st) == 0 && S_ISDIR(st.st_mode) && st.st_uid == ::geteuid() && (st.st_mode & (S_IWGRP | S_IWOTH)) == 0;
         }
 
         std::string lib_dir()
@@ -64,6 +107,32 @@ namespace pe_b200
         {
             char const* v{std::getenv(name)};
             return v != nullptr ? std::atoi(v) : dflt;
+        }
+
+        // Where compiled kernels are cached: <library directory>/jit_cache when this user owns it and nobody else can write
+        // to it (the in-tree build), else a per-user directory ($XDG_CACHE_HOME/pe_b200 or ~/.cache/pe_b200, mode 0700).
+        // A directory that is a symlink, belongs to somebody else or is group / world writable is refused: the files in
+        // it are loaded as GPU code.  Empty string = no usable cache.
+        std::string cache_dir(std::string& err)
+        {
+            std::string const a{lib_dir() + "/jit_cache"};
+            (void)::mkdir(a.c_str(), 0700);
+            if(private_dir(a) && ::access(a.c_str(), W_OK) == 0) { return a; }
+            std::string base;
+            if(char const* x{std::getenv("XDG_CACHE_HOME")}; x != nullptr && x[0] == '/') { base = x; }
+            else if(char const* h{std::getenv("HOME")}; h != nullptr && h[0] == '/')
+            {
+                base = std::string{h} + "/.cache";
+                (void)::mkdir(base.c_str(), 0700);
+            }
+            if(!base.empty())
+            {
+                std::string const b{base + "/pe_b200"};
+                (void)::mkdir(b.c_str(), 0700);
+                if(private_dir(b) && ::access(b.c_str(), W_OK) == 0) { return b; }
+            }
+            err = "jit: no private cache directory (tried " + a + " and $XDG_CACHE_HOME / ~/.cache): refusing a shared one";
+            return {};
         }
 
         struct jop
@@ -762,15 +831,11 @@ namespace pe_b200
         key = h;
         char name[64];
         std::snprintf(name, sizeof(name), "pe_jit_%016llx", static_cast<unsigned long long>(h));
-        std::string cache{dir + "/jit_cache"};
-        if(::mkdir(cache.c_str(), 0755) != 0 && ::access(cache.c_str(), W_OK) != 0)
-        {
-            cache = "/tmp/pe_b200_jit_cache";
-            ::mkdir(cache.c_str(), 0755);
-        }
+        std::string const cache{cache_dir(err)};
+        if(cache.empty()) { return false; }
         std::string const cub{cache + "/" + name + ".cubin"};
         std::string bytes;
-        if(read_file(cub, bytes) && !bytes.empty())
+        if(read_file(cub, bytes, true) && !bytes.empty())
         {
             cubin.assign(bytes.begin(), bytes.end());
             return true;
@@ -781,34 +846,108 @@ namespace pe_b200
             return false;
         }
         std::string const inc{cache + "/" + name + ".inc"};
+        if(!write_file_atomic(inc, gen))
         {
-            std::ofstream f(inc, std::ios::binary);
-            f << gen;
-            if(!f)
-            {
-                err = "jit: cannot write " + inc;
-                return false;
-            }
+            err = "jit: cannot write " + inc;
+            return false;
         }
         char const* nv{std::getenv("PE_B200_NVCC")};
         std::string nvcc{nv != nullptr ? nv : "/usr/local/cuda/bin/nvcc"};
         if(::access(nvcc.c_str(), X_OK) != 0) { nvcc = "nvcc"; }
         std::string const tmp{cub + ".tmp" + std::to_string(static_cast<long>(::getpid()))};
-        std::string const log{cache + "/" + name + ".log"};
+        std::string const log{tmp + ".log"};
         std::ostringstream cmd;
         cmd << nvcc << " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin -DPE_JIT -DPE_JIT_CL=" << CL << " '-DPE_JIT_SOURCE=\"" << inc << "\"' -I'" << csrc
             << "' -o '" << tmp << "' '" << csrc << "/pe_b200_kernels.cu' > '" << log << "' 2>&1";
         int const rc{std::system(cmd.str().c_str())};
-        if(rc != 0 || !read_file(tmp, bytes) || bytes.empty())
+        if(rc != 0 || !read_file(tmp, bytes, true) || bytes.empty())
         {
             std::string l;
-            read_file(log, l);
+            read_file(log, l, true);
             err = "jit: nvcc failed (" + std::to_string(WIFEXITED(rc) ? WEXITSTATUS(rc) : -1) + "): " + l.substr(0, 600);
             ::unlink(tmp.c_str());
             return false;
         }
         ::rename(tmp.c_str(), cub.c_str());
+        ::rename(log.c_str(), (cache + "/" + name + ".log").c_str());
         cubin.assign(bytes.begin(), bytes.end());
+        return true;
+    }
+
+    // the stream kernel's module (host/stream.cpp): generated source + csrc/pe_b200_stream.cu -> cubin (device seam) or a
+    // host shared object (the emulator's seam), cached under a key of everything that goes into it
+    bool stream_compile(std::string const& gen, int J, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile)
+    {
+        int const kind{pe_b200_stream_supported()};  // 1 = device (cubin bytes travel), 2 = emulator (the path travels)
+        if(kind == 0)
+        {
+            err = "stream: not available in this build";
+            return false;
+        }
+        std::string const dir{lib_dir()};
+        std::string csrc{dir + "/csrc"};
+        if(char const* e{std::getenv("PE_B200_CSRC")}; e != nullptr) { csrc = e; }
+        else if(::access((csrc + "/pe_b200_stream.cu").c_str(), R_OK) != 0 && ::access((dir + "/../../phy-engine_b200/csrc/pe_b200_stream.cu").c_str(), R_OK) == 0)
+        {
+            csrc = dir + "/../../phy-engine_b200/csrc";  // the test emulator lives in tests/emu
+        }
+        std::uint64_t h{1469598103934665603ull};
+        h = fnv(h, gen.data(), gen.size());
+        h = fnv(h, &J, sizeof(J));
+        h = fnv(h, &kind, sizeof(kind));
+        for(char const* f: {"pe_b200_stream.cu", "pe_b200_stream.h", "pe_b200_program.h", "pe_b200_models.h", "pe_b200_interp.h", "pe_b200_rinterp.h"})
+        {
+            std::string text;
+            if(!read_file(csrc + "/" + f, text))
+            {
+                err = "stream: kernel source " + csrc + "/" + f + " not found";
+                return false;
+            }
+            h = fnv(h, text.data(), text.size());
+        }
+        key = h;
+        char name[64];
+        std::snprintf(name, sizeof(name), "pe_stream_%016llx", static_cast<unsigned long long>(h));
+        std::string const cache{cache_dir(err)};
+        if(cache.empty()) { return false; }
+        std::string const mod{cache + "/" + name + (kind == 2 ? ".so" : ".cubin")};
+        std::string bytes;
+        auto deliver = [&]() -> bool
+        {
+            if(!read_file(mod, bytes, true) || bytes.empty()) { return false; }
+            if(kind == 2) { blob.assign(mod.begin(), mod.end()); }
+            else
+            {
+                blob.assign(bytes.begin(), bytes.end());
+            }
+            return true;
+        };
+        if(deliver()) { return true; }
+        if(!allow_compile)
+        {
+            err = "stream: " + mod + " is not in the cache";
+            return false;
+        }
+        std::string const inc{cache + "/" + name + ".inc"};
+        if(!write_file_atomic(inc, gen))
+        {
+            err = "stream: cannot write " + inc;
+            return false;
+        }
+        std::string const tmp{mod + ".tmp" + std::to_string(static_cast<long>(::getpid()))};
+        std::vector<char> log(2048, 0);
+        if(pe_b200_stream_build(inc.c_str(), tmp.c_str(), csrc.c_str(), J, log.data(), log.size()) != 0)
+        {
+            err = std::string{"stream: compiler failed: "} + log.data();
+            ::unlink(tmp.c_str());
+            return false;
+        }
+        ::unlink((tmp + ".log").c_str());
+        if(::rename(tmp.c_str(), mod.c_str()) != 0 || !deliver())
+        {
+            err = "stream: cannot install " + mod;
+            return false;
+        }
         return true;
     }
 

@@ -197,6 +197,14 @@ namespace pe_b200
         std::vector<std::uint32_t> sec_off;  // [3][n_warps]
         bool has_sec[3]{};
         void pack(int ig);                   // (re)build words / sec_off for CTAs of rS * ig threads
+        // stream kernel (host/stream.cpp): one-stream programs whose iter section is generated as tiled, TMA-fed code
+        int stream_state{0};                 // 0 = not tried, 1 = module ready, -1 = not available
+        bool stream_laid_out{};              // stream_prepare() has re-laid the workspace rows out (planes + replicas)
+        int stream_j{0};                     // lanes per thread the module was built for
+        std::uint64_t stream_key{};
+        std::vector<char> stream_blob;       // cubin (device) / path of the host module (emulator)
+        std::string stream_error;
+        std::uint32_t stream_tiles{}, stream_stage_rows{};
         // specialised kernel of the iter section (host/jit.cpp): 0 = not tried, 1 = cubin ready, -1 = not available
         int jit_state{0};
         int jit_cl{0};
@@ -276,6 +284,20 @@ namespace pe_b200
     bool jit_compile(std::string const& gen, int CL, std::vector<char>& cubin, std::uint64_t& key, std::string& err, bool allow_compile = true);
     int jit_load_distance();
 
+    // host/stream.cpp: the stream kernel (one warp per lane group, one stream per group, TMA-fed tiles)
+    struct stream_geom
+    {
+        std::uint32_t n_tiles{}, stage_rows{};
+        std::size_t n_loops{}, loop_ops{}, n_ops{};
+        std::size_t rows_fetched{}, n_copies{}, rows_stored{};  // per solve
+    };
+    bool stream_supported(program const& pr);
+    // re-lays the workspace rows of a one-stream program out for the stream kernel (contiguous rows per tile, replica rows
+    // of shared read-only operands); every executor of the program sees the same, value-equivalent program afterwards
+    bool stream_prepare(program& pr);
+    std::string stream_generate(program const& pr, stream_geom& g);
+    bool stream_compile(std::string const& gen, int J, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile = true);
+
     struct batch
     {
         circuit* parent{};
@@ -314,7 +336,7 @@ namespace pe_b200
         // ahead, 4 = L1 re-fetch of every DOT result right after its store (+3 %: on)
         int res_prefetch{4};
         std::size_t last_points_hint{1};  // frequency points per instance of the AC sweep being launched (lane count = n_inst * points)
-int res_jit{0};      // specialised (run-time compiled) tree-streaming kernel: 0 = automatic, 1 = required, -1 = off
+        int res_jit{0};      // specialised (run-time compiled) tree-streaming kernel: 0 = automatic, 1 = required, -1 = off
         int res_fuse{0};     // emit small elimination steps as one fused op (PE_OP_CROUT2); measured slower on config B (register file bound): off
         int cc_fuse{-1};
         int res_chunks{0};   // chunks the time loop is cut into for dynamic scheduling: 0 = choose, 1 = static (one CTA per group)
@@ -324,7 +346,10 @@ int res_jit{0};      // specialised (run-time compiled) tree-streaming kernel: 0
         bool pick_geometry(program const& pr, int& I, int& J) const;
         std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_secoff, d_io;
         std::array<int, static_cast<int>(prog_mode::COUNT)> uploaded_ig{};
-        int last_jit{};  // 1 = the last tree-streaming launch ran the specialised (run-time compiled) kernel
+        int res_stream{0};   // stream kernel: 0 = automatic, 1 = required, -1 = off
+        bool stream_mode{};  // the real-valued programs were compiled with one stream per lane group for the stream kernel
+        std::uint64_t stream_rejected_rev{};  // structure revision whose program the stream generator does not cover
+        int last_jit{};  // 1 = the last tree-streaming launch ran the specialised (run-time compiled) kernel, 2 = the stream kernel
         int last_I{}, last_J{}, last_S{};  // geometry of the last resident launch (0 = the HBM-streaming kernel ran)
 
         // results of the last analyze()

@@ -236,6 +236,8 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_set_tuning.argtypes = [V, ct.c_uint]
     lib.circuit_batch_last_kernel.argtypes = [V]
     lib.circuit_batch_last_kernel.restype = ct.c_int
+    lib.circuit_batch_stream_info.argtypes = [V, ct.c_int, ct.POINTER(ct.c_int64)]
+    lib.circuit_batch_stream_info.restype = ct.c_int
     lib.circuit_batch_set_workspace.argtypes = [V, ct.c_int]
     lib.circuit_batch_digital_clk.argtypes = [V]
     lib.circuit_batch_comparator_count.restype = _SZ
@@ -381,12 +383,18 @@ class Batch:
         self._rc(self.lib.circuit_batch_set_chunks(self.h, chunks), "circuit_batch_set_chunks")
 
     def set_tuning(self, flags: int):
-        """bit 0 L2 operand prefetch, bit 1 two lines ahead, bit 2 no L1 re-fetch of results, bit 3 fused elimination steps"""
+        """bit 0 L2 operand prefetch, bit 1 two lines ahead, bit 2 no L1 re-fetch of results, bit 3 fused elimination steps, bit 4 / 5 require / forbid the specialised kernel, bit 6 / 7 require / forbid the stream kernel"""
         self._rc(self.lib.circuit_batch_set_tuning(self.h, flags), "circuit_batch_set_tuning")
 
     def last_kernel(self) -> int:
-        """0 = word interpreter, 1 = specialised (run-time compiled) tree-streaming kernel"""
+        """0 = word interpreter, 1 = specialised (run-time compiled) tree-streaming kernel, 2 = stream kernel"""
         return int(self.lib.circuit_batch_last_kernel(self.h))
+
+    def stream_info(self, mode: int) -> dict:
+        v = (ct.c_int64 * 6)()
+        self._rc(self.lib.circuit_batch_stream_info(self.h, mode, v), "circuit_batch_stream_info")
+        keys = ("last_kernel", "warps_per_cta", "ring_stages", "smem_per_cta", "tiles_per_solve", "stage_rows")
+        return {k: int(x) for k, x in zip(keys, v)}
 
     def digital_clk(self) -> np.ndarray:
         """comparator states [n_instances, n_comparators] (vA >= vB) after the last analyze()"""

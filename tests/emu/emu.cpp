@@ -10,8 +10,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <array>
+#include <map>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -243,6 +246,7 @@ extern "C"
 namespace
 {
     uint64_t g_resident_launches = 0;
+    uint64_t g_stream_errors = 0, g_stream_launches = 0;
 
     template <int J>
     void run_resident(pe_b200_rrun const& r)
@@ -528,12 +532,173 @@ extern "C"
 {
     uint64_t pe_emu_resident_launches(void) { return g_resident_launches; }
 
-    // the emulator replays the word interpreter only: specialised (run-time compiled) kernels are GPU-only
+    // the emulator replays the word interpreter only: the specialised tree kernel is GPU-only
     int pe_b200_jit_supported(void) { return 0; }
     int pe_b200_launch_jit(pe_b200_rrun const*, void const*, size_t, uint64_t, void*)
     {
         snprintf(g_err, sizeof(g_err), "pe_b200_launch_jit: not available in the emulator");
         return 1;
+    }
+
+    // ---- stream kernel: the generated source is compiled for the host (stream_host.cpp) and run lane by lane ------------
+    int pe_b200_stream_supported(void) { return 2; }
+    uint64_t pe_emu_stream_errors(void) { return g_stream_errors; }
+    uint64_t pe_emu_stream_launches(void) { return g_stream_launches; }
+
+    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int, char* log, size_t log_cap)
+    {
+        Dl_info info{};
+        std::string here{"."};
+        if(dladdr(reinterpret_cast<void const*>(&pe_b200_stream_supported), &info) != 0 && info.dli_fname != nullptr)
+        {
+            std::string p{info.dli_fname};
+            auto const k = p.rfind('/');
+            if(k != std::string::npos) { here = p.substr(0, k); }
+        }
+        std::string const logf = std::string(out_path) + ".log";
+        std::string const cmd = std::string("g++ -std=c++17 -O1 -fPIC -shared -Wl,--exclude-libs,ALL -ffp-contract=off -DPE_SJ=1 '-DPE_STREAM_SOURCE=\"") + source_path + "\"' -I'" + csrc_dir + "' -o '" + out_path +
+                                "' '" + here + "/stream_host.cpp' > '" + logf + "' 2>&1";
+        int const rc = system(cmd.c_str());
+        if(rc != 0 && log != nullptr && log_cap > 0)
+        {
+            log[0] = 0;
+            if(FILE* f = fopen(logf.c_str(), "rb"))
+            {
+                size_t const n = fread(log, 1, log_cap - 1, f);
+                log[n] = 0;
+                fclose(f);
+            }
+        }
+        return rc == 0 ? 0 : 1;
+    }
+
+    void pe_b200_stream_last_geometry(int* out3) { out3[0] = out3[1] = out3[2] = 0; }
+
+    int pe_b200_launch_stream(pe_b200_rrun const* rp, void const* blob, size_t bytes, uint64_t, uint32_t n_tiles, uint32_t stage_rows, void*)
+    {
+        using namespace pe_rinterp;
+        if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
+        pe_b200_rrun const& r = *rp;
+        std::string const path(static_cast<char const*>(blob), bytes);
+        static std::map<std::string, void*> mods;
+        void* h = mods[path];
+        if(h == nullptr)
+        {
+            h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if(h == nullptr)
+            {
+                snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: dlopen %s: %s", path.c_str(), dlerror());
+                return 1;
+            }
+            mods[path] = h;
+        }
+        auto const f_tiles = reinterpret_cast<uint32_t (*)(void)>(dlsym(h, "pe_emu_stream_tiles"));
+        auto const f_rows = reinterpret_cast<uint32_t (*)(void)>(dlsym(h, "pe_emu_stream_stage_rows"));
+        auto const f_new = reinterpret_cast<void* (*)(uint32_t, uint32_t)>(dlsym(h, "pe_emu_stream_new"));
+        auto const f_free = reinterpret_cast<void (*)(void*)>(dlsym(h, "pe_emu_stream_free"));
+        auto const f_solve = reinterpret_cast<uint32_t (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*)>(dlsym(h, "pe_emu_stream_solve"));
+        if(!f_tiles || !f_rows || !f_new || !f_free || !f_solve || f_tiles() != n_tiles || f_rows() != stage_rows || r.S != 1 || r.wsg == nullptr || r.nonlinear || r.cplx)
+        {
+            snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: module / launch mismatch");
+            return 1;
+        }
+        ++g_launches;
+        ++g_stream_launches;
+        bool const trace_was = emu_trace::g_on;
+        emu_trace::g_on = false;
+        uint32_t const GL = (uint32_t)r.I;  // 32 J lanes per group: the workspace is one block per group, ws[group][row][GL]
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        static int const ns_log_env = getenv("PE_EMU_STREAM_NS_LOG") ? atoi(getenv("PE_EMU_STREAM_NS_LOG")) : 2;
+        for(int64_t lane = 0; lane < ((int64_t)r.n_lanes + GL - 1) / GL * GL; ++lane)
+        {
+            int64_t const group = lane / GL;
+            uint32_t const li = (uint32_t)(lane % GL);
+            double* const wl = r.wsg + group * (int64_t)r.n_slots * GL + li;
+            bool const real = lane < r.n_lanes;
+            int32_t status = real ? r.status[lane] : (int32_t)PE_ST_SINGULAR;
+            bool const counted = real && status == PE_ST_OK;
+            bool ok = counted;
+            uint32_t solves = 0;
+            for(int32_t k = 0; k < r.n_slots; ++k) { wl[(uint64_t)k * GL] = __builtin_nan(""); }  // poison
+            for(int32_t e = 0; e < r.n_io; ++e)
+            {
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
+                uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
+                double v = 0.0;
+                if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
+                else if(real) { v = kind == PE_IO_U ? r.wu[(int64_t)io.src * r.LSu + lane] : r.wx[(int64_t)io.src * r.LSx + lane / r.ppi]; }
+                wl[(uint64_t)(io.slot_kind & 0xffffu) * GL] = v;
+            }
+            rctx c;
+            c.ws = wl;
+            c.I = GL;
+            c.S = 1;
+            c.C = 1;
+            c.col = 0;
+            c.stream = 0;
+            c.js = 32;
+            auto run_section = [&](int sec, double t)
+            {
+                host_reader rd;
+                rd.p0 = r.words + r.sec_off[sec];
+                rd.q = r.words + r.sec_off[3 + sec];
+                rd.C = 1;
+                rd.col = 0;
+                rd.start();
+                bool en[1] = {ok}, nc[1] = {false}, fl[1] = {false};
+                for(;;)
+                {
+                    int const kind = rvop<1>(rd, c, t, tol, en, false, nc, fl, true);
+                    if(kind == V_END || kind == V_BAD) { break; }
+                    if(kind == V_BAR) { rd.bar(); }
+                    else if(kind == V_SKIP) { rd.skip(); }
+                    else
+                    {
+                        rd.close();
+                    }
+                }
+            };
+            void* const st = f_new((uint32_t)r.n_slots, (uint32_t)ns_log_env);
+            double t = r.t0;
+            if(r.has_prep) { run_section(0, t); }
+            for(int32_t s = 0; s < r.n_steps; ++s)
+            {
+                if(r.time_stepping)
+                {
+                    if(r.has_step) { run_section(1, t); }
+                    t = t + r.dt;
+                }
+                uint32_t const fm = f_solve(st, wl, GL, li & 31u, ok ? 1u : 0u, &g_stream_errors);
+                if(ok)
+                {
+                    ++solves;
+                    if(fm & 1u)
+                    {
+                        status = PE_ST_SINGULAR;
+                        ok = false;
+                    }
+                }
+                if(r.wave != nullptr && ok)
+                {
+                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + lane] = wl[(uint64_t)r.probes[p] * GL]; }
+                }
+            }
+            f_free(st);
+            for(int32_t e = 0; e < r.n_io; ++e)
+            {
+                pe_b200_io const io = r.io[e];
+                if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
+                if(counted) { r.wu[(int64_t)io.src * r.LSu + lane] = wl[(uint64_t)(io.slot_kind & 0xffffu) * GL]; }
+            }
+            if(counted)
+            {
+                r.status[lane] = status;
+                r.solves[lane] += solves;
+            }
+        }
+        emu_trace::g_on = trace_was;
+        return 0;
     }
 
     int pe_b200_launch_resident(pe_b200_rrun const* rp, void*)
