@@ -78,26 +78,49 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             ok[j] = counted[j];
             solves[j] = 0;
         }
-        // load table: persistent values -> workspace rows
-        for(uint32_t e = 0; e < (uint32_t)r.n_io; ++e)
+        // load table: persistent values -> workspace rows.  Lane l fetches entry e0 + l of the table, the warp then walks the 32
+        // entries in batches whose value loads are all issued before the first store (one warp per group: nothing else hides
+        // the latency of a dependent table-entry -> value -> store chain).
+        for(uint32_t e0 = 0; e0 < (uint32_t)r.n_io; e0 += 32u)
         {
-            pe_b200_io const io = r.io[e];
-            if(!((io.slot_kind >> 20) & PE_IO_LOAD)) { continue; }
-            uint32_t const kind = (io.slot_kind >> 16) & 0xfu;
-            double* const dst = at(io.slot_kind & 0xffffu);
-#pragma unroll
-            for(int j = 0; j < J; ++j)
+            pe_b200_io mine{0u, 0u};
+            if(e0 + lane < (uint32_t)r.n_io) { mine = r.io[e0 + lane]; }
+#pragma unroll 1
+            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += 8u)
             {
-                // a padding lane (beyond n_lanes) computes on the values of the last real lane: zeros would send its warp
-                // through the slow paths of the FP64 division / reciprocal at every node, and the launch ends with its slowest warp
-                int64_t const ln = real_lane[j] ? glane + 32 * j : (int64_t)r.n_lanes - 1;
-                double v;
-                if(kind == PE_IO_CONST) { v = r.cst[io.src]; }
-                else
+                double v[8][J];
+                uint32_t sk[8];
+#pragma unroll
+                for(int u = 0; u < 8; ++u)
                 {
-                    v = kind == PE_IO_U ? r.wu[(int64_t)io.src * r.LSu + ln] : r.wx[(int64_t)io.src * r.LSx + ln / r.ppi];
+                    sk[u] = __shfl_sync(0xffffffffu, mine.slot_kind, (int)(u0 + u));
+                    uint32_t const src = __shfl_sync(0xffffffffu, mine.src, (int)(u0 + u));
+                    uint32_t const kind = (sk[u] >> 16) & 0xfu;
+                    bool const on = ((sk[u] >> 20) & PE_IO_LOAD) != 0u;
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
+                    {
+                        // a padding lane (beyond n_lanes) computes on the values of the last real lane: zeros would send its
+                        // warp through the slow paths of the FP64 division / reciprocal at every node, and the launch ends
+                        // with its slowest warp
+                        int64_t const ln = real_lane[j] ? glane + 32 * j : (int64_t)r.n_lanes - 1;
+                        v[u][j] = 0.0;
+                        if(!on) { continue; }
+                        if(kind == PE_IO_CONST) { v[u][j] = __ldg(r.cst + src); }
+                        else
+                        {
+                            v[u][j] = kind == PE_IO_U ? r.wu[(int64_t)src * r.LSu + ln] : r.wx[(int64_t)src * r.LSx + ln / r.ppi];
+                        }
+                    }
                 }
-                dst[32 * j] = v;
+#pragma unroll
+                for(int u = 0; u < 8; ++u)
+                {
+                    if(!((sk[u] >> 20) & PE_IO_LOAD)) { continue; }
+                    double* const dst = at(sk[u] & 0xffffu);
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { dst[32 * j] = v[u][j]; }
+                }
             }
         }
         __syncwarp();
@@ -137,7 +160,23 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
         };
 
         double t = r.t0;
-        if(r.has_prep) { run_section(0, t); }
+        if(r.has_prep)
+        {
+#ifdef PE_STREAM_PREP
+            // the prep section as generated tiles (derived per-instance values, replica rows)
+            k.enm = 0u;
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                if(ok[j]) { k.enm |= 1u << j; }
+            }
+            uint32_t fm0 = 0u;
+            pe_stream_prep(k, fm0);
+            __syncwarp();
+#else
+            run_section(0, t);
+#endif
+        }
         for(int32_t s = 0; s < r.n_steps; ++s)
         {
             if(r.time_stepping)
@@ -176,16 +215,36 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                 }
             }
         }
-        // store table: mutable values -> persistent rows
-        for(uint32_t e = 0; e < (uint32_t)r.n_io; ++e)
+        // store table: mutable values -> persistent rows (batched like the load table)
+        for(uint32_t e0 = 0; e0 < (uint32_t)r.n_io; e0 += 32u)
         {
-            pe_b200_io const io = r.io[e];
-            if(!((io.slot_kind >> 20) & PE_IO_STORE)) { continue; }
-            double const* const src = at(io.slot_kind & 0xffffu);
-#pragma unroll
-            for(int j = 0; j < J; ++j)
+            pe_b200_io mine{0u, 0u};
+            if(e0 + lane < (uint32_t)r.n_io) { mine = r.io[e0 + lane]; }
+#pragma unroll 1
+            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += 8u)
             {
-                if(counted[j]) { r.wu[(int64_t)io.src * r.LSu + glane + 32 * j] = src[32 * j]; }
+                double v[8][J];
+                uint32_t sk[8], sr[8];
+#pragma unroll
+                for(int u = 0; u < 8; ++u)
+                {
+                    sk[u] = __shfl_sync(0xffffffffu, mine.slot_kind, (int)(u0 + u));
+                    sr[u] = __shfl_sync(0xffffffffu, mine.src, (int)(u0 + u));
+                    bool const on = ((sk[u] >> 20) & PE_IO_STORE) != 0u;
+                    double const* const src = at(sk[u] & 0xffffu);
+#pragma unroll
+                    for(int j = 0; j < J; ++j) { v[u][j] = on ? src[32 * j] : 0.0; }
+                }
+#pragma unroll
+                for(int u = 0; u < 8; ++u)
+                {
+                    if(!((sk[u] >> 20) & PE_IO_STORE)) { continue; }
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(counted[j]) { r.wu[(int64_t)sr[u] * r.LSu + glane + 32 * j] = v[u][j]; }
+                    }
+                }
             }
         }
 #pragma unroll

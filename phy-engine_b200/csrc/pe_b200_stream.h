@@ -84,6 +84,39 @@ namespace pe_stream
         for(int j = 0; j < PE_SJ; ++j) { pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]); }
     }
 
+    // simple value ops (pe_b200_rinterp.h: PE_OP_RECIP / MUL / SUB / COPY / MUL2DIV)
+    PE_SK_FN jv jneg(jv const& a)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = -a.v[j]; }
+        return x;
+    }
+    PE_SK_FN jv jvrecip(jv const& a)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_DIV(1.0, a.v[j]); }
+        return x;
+    }
+    PE_SK_FN jv jvmul(jv const& a, jv const& b)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_MUL(a.v[j], b.v[j]); }
+        return x;
+    }
+    PE_SK_FN jv jvsub(jv const& a, jv const& b)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_SUB(a.v[j], b.v[j]); }
+        return x;
+    }
+    PE_SK_FN jv jvcopy(jv const& a) { return a; }
+    PE_SK_FN jv jvmul2div(jv const& a, jv const& b)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_DIV(PE_MUL(2.0, a.v[j]), b.v[j]); }
+        return x;
+    }
+
     // geometry of one generated program (filled in by the generated pe_stream_geom())
     struct sk_geom
     {
@@ -162,6 +195,7 @@ namespace pe_stream
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows * ROWB) : "memory");
         }
     }
+    PE_SK_FN void sk_end(sk_ctx const&, uint32_t) {}
     PE_SK_FN void sk_copy(sk_ctx const& k, uint32_t p, uint32_t dst_row, uint32_t src_row, uint32_t rows)
     {
         if(k.lane == 0u)
@@ -241,6 +275,15 @@ namespace pe_stream
         if(rows > k.stage_rows) { ++k.errors; }
         k.stage_tile[stg] = (int64_t)(k.seq0 + p);
         k.stage_read[stg] = 0;
+    }
+    // end of a section: every tile was issued and consumed
+    inline void sk_end(sk_ctx& k, uint32_t n_tiles)
+    {
+        if(k.pn != n_tiles) { ++k.errors; }
+        for(uint32_t i = 0; i <= k.ns_mask; ++i)
+        {
+            if(k.stage_tile[i] >= 0 && k.stage_read[i] == 0) { ++k.errors; }
+        }
     }
     inline void sk_copy(sk_ctx& k, uint32_t p, uint32_t dst_row, uint32_t src_row, uint32_t rows)
     {

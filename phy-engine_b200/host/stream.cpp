@@ -41,12 +41,14 @@ namespace pe_b200
             std::vector<std::uint32_t> rd, wr;  // slots
         };
 
-        // ops of the iter section in program order (one stream: the phases simply follow each other)
-        bool flatten(program const& pr, std::vector<sop>& ops)
+        bool simple_value_op(std::uint32_t op) { return op == PE_OP_RECIP || op == PE_OP_MUL || op == PE_OP_SUB || op == PE_OP_COPY || op == PE_OP_MUL2DIV; }
+
+        // ops of one section in program order (one stream: the phases simply follow each other)
+        bool flatten(program const& pr, int sec, std::vector<sop>& ops)
         {
             ops.clear();
             if(pr.rstreams.size() != 1) { return false; }
-            for(auto const& ph: pr.rstreams[0].sec[2])
+            for(auto const& ph: pr.rstreams[0].sec[sec])
             {
                 for(auto const& o: ph)
                 {
@@ -71,9 +73,14 @@ namespace pe_b200
                         j.wr.push_back(o.opnd[0] & k_slot_mask);
                         j.wr.push_back(o.opnd[1] & k_slot_mask);
                     }
+                    else if(simple_value_op(o.opcode) && o.opnd.size() == (o.opcode == PE_OP_RECIP || o.opcode == PE_OP_COPY ? 2u : 3u))
+                    {
+                        for(std::size_t i{1}; i < o.opnd.size(); ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
+                        j.wr.push_back(o.opnd[0] & k_slot_mask);
+                    }
                     else
                     {
-                        if(std::getenv("PE_B200_STREAM_DEBUG") != nullptr) { std::fprintf(stderr, "stream: op %u (%zu operands) is not covered\n", o.opcode, o.opnd.size()); }
+                        if(std::getenv("PE_B200_STREAM_DEBUG") != nullptr) { std::fprintf(stderr, "stream: section %d op %u (%zu operands) is not covered\n", sec, o.opcode, o.opnd.size()); }
                         return false;
                     }
                     ops.push_back(std::move(j));
@@ -96,6 +103,11 @@ namespace pe_b200
             for(std::size_t i{}; i < x.pp.size(); ++i)
             {
                 if(((x.pp[i].first ^ x.pp[i].second) ^ (y.pp[i].first ^ y.pp[i].second)) & PE_R_NEG) { return false; }
+            }
+            if(x.opnd.size() != y.opnd.size()) { return false; }
+            for(std::size_t i{}; i < x.opnd.size(); ++i)
+            {
+                if((x.opnd[i] ^ y.opnd[i]) & PE_R_NEG) { return false; }
             }
             return true;
         }
@@ -411,9 +423,9 @@ namespace pe_b200
             return out;
         }
 
-        bool make_plan(program const& pr, plan& p)
+        bool make_plan(program const& pr, plan& p, int sec = 2)
         {
-            if(!flatten(pr, p.ops)) { return false; }
+            if(!flatten(pr, sec, p.ops)) { return false; }
             p.inv = pick_invariants(p.ops);
             p.inv_idx.clear();
             for(std::size_t i{}; i < p.inv.size(); ++i) { p.inv_idx[p.inv[i]] = static_cast<int>(i); }
@@ -500,6 +512,7 @@ namespace pe_b200
         struct emitter
         {
             plan const& p;
+            std::string sfx;  // "_iter" / "_prep"
             std::vector<std::uint8_t> needed;  // per slot: some load takes it from memory, or it is read outside this code
             std::ostringstream out;
 
@@ -536,12 +549,21 @@ namespace pe_b200
                     if(o.flags & PE_F_RECIP) { t << " jrcp(" << w[0] << ", fm);"; }
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }
-                else  // PE_OP_CAP_STEP: [hist][prev_g][C][dt][va][vb]
+                else if(o.opcode == PE_OP_CAP_STEP)  // [hist][prev_g][C][dt][va][vb]
                 {
                     t << dv << w[0] << " = " << x[0] << "; " << dv << w[1] << " = " << x[1] << "; jcap(" << x[2] << ", " << x[3] << ", " << x[4] << ", " << x[5] << ", " << w[0] << ", " << w[1]
                       << ");";
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                     if(!st[1].empty()) { t << " sk_st(k, " << st[1] << ", " << w[1] << ");"; }
+                }
+                else  // simple value ops: [dst][a]([b]), operands carry a negate bit
+                {
+                    auto arg = [&](std::size_t i) { return (o.opnd[i + 1] & PE_R_NEG) ? "jneg(" + x[i] + ")" : x[i]; };
+                    char const* fn{o.opcode == PE_OP_RECIP ? "jvrecip" : o.opcode == PE_OP_MUL ? "jvmul" : o.opcode == PE_OP_SUB ? "jvsub" : o.opcode == PE_OP_COPY ? "jvcopy" : "jvmul2div"};
+                    t << dv << w[0] << " = " << fn << "(" << arg(0);
+                    if(x.size() > 1) { t << ", " << arg(1); }
+                    t << ");";
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }
                 return t.str();
             }
@@ -574,7 +596,7 @@ namespace pe_b200
 
             void emit_tile_head(std::string const& tvar, std::string const& lim, std::string const& ind)
             {
-                out << ind << "if(k.pn <= " << tvar << ") { pe_stream_produce_upto(k, " << tvar << " + 1u, (int32_t)" << tvar << " - 1); }\n";
+                out << ind << "if(k.pn <= " << tvar << ") { pe_stream_produce_upto" << sfx << "(k, " << tvar << " + 1u, (int32_t)" << tvar << " - 1); }\n";
                 out << ind << "sk_wait(k, " << tvar << ");\n";
                 out << ind << "auto const sg = sk_stage(k, " << tvar << ");\n";
                 (void)lim;
@@ -590,7 +612,7 @@ namespace pe_b200
                 emit_tile_head(std::to_string(T) + "u", "", "        ");
                 for(std::size_t j{}; j < m.size(); ++j) { out << "        jv const m" << j << " = sk_ring(sg, " << j << "u);\n"; }
                 out << "        sk_ring_done(k, " << T << "u);\n";
-                out << "        { uint32_t tg = " << T << "u + k.ns_mask + 2u; if(tg > " << limit_after(T, T) << "u) { tg = " << limit_after(T, T) << "u; } pe_stream_produce_upto(k, tg, " << (T - 1)
+                out << "        { uint32_t tg = " << T << "u + k.ns_mask + 2u; if(tg > " << limit_after(T, T) << "u) { tg = " << limit_after(T, T) << "u; } pe_stream_produce_upto" << sfx << "(k, tg, " << (T - 1)
                     << "); }\n";
                 std::map<std::uint32_t, std::size_t> row_of;
                 for(std::size_t j{}; j < m.size(); ++j) { row_of[m[j]] = j; }
@@ -653,7 +675,7 @@ namespace pe_b200
                 emit_tile_head("t", "", "        ");
                 for(std::size_t j{}; j < m0.size(); ++j) { out << "        jv const m" << j << " = sk_ring(sg, " << j << "u);\n"; }
                 out << "        sk_ring_done(k, t);\n";
-                out << "        { uint32_t tg = t + k.ns_mask + 2u; if(tg > " << lim << "u) { tg = " << lim << "u; } pe_stream_produce_upto(k, tg, (int32_t)t - 1); }\n";
+                out << "        { uint32_t tg = t + k.ns_mask + 2u; if(tg > " << lim << "u) { tg = " << lim << "u; } pe_stream_produce_upto" << sfx << "(k, tg, (int32_t)t - 1); }\n";
                 for(auto const& [lv, cv]: carried) { out << "        jv const " << cv << " = " << lv << ";\n"; }
                 std::map<std::uint32_t, std::size_t> row_of;
                 for(std::size_t j{}; j < m0.size(); ++j) { row_of[m0[j]] = j; }
@@ -700,7 +722,7 @@ namespace pe_b200
 
             void emit_produce()
             {
-                out << "__device__ __forceinline__ void pe_stream_produce(sk_ctx& k, uint32_t const p, int32_t const t_done)\n{\n";
+                out << "__device__ __forceinline__ void pe_stream_produce" << sfx << "(sk_ctx& k, uint32_t const p, int32_t const t_done)\n{\n";
                 bool first{true};
                 std::size_t ri{};
                 while(ri < p.regs.size())
@@ -750,16 +772,15 @@ namespace pe_b200
                     ri = re;
                 }
                 out << "}\n";
-                out << "__device__ __forceinline__ void pe_stream_produce_upto(sk_ctx& k, uint32_t target, int32_t const t_done)\n{\n"
+                out << "__device__ __forceinline__ void pe_stream_produce_upto" << sfx << "(sk_ctx& k, uint32_t target, int32_t const t_done)\n{\n"
                     << "    if(target > " << p.n_tiles << "u) { target = " << p.n_tiles << "u; }\n"
-                    << "    while(k.pn < target)\n    {\n        pe_stream_produce(k, k.pn, t_done);\n        ++k.pn;\n    }\n}\n";
+                    << "    while(k.pn < target)\n    {\n        pe_stream_produce" << sfx << "(k, k.pn, t_done);\n        ++k.pn;\n    }\n}\n";
             }
 
             std::string run()
             {
                 std::ostringstream src;
-                src << "// generated by host/stream.cpp: iter section of a one-stream program as " << p.n_tiles << " tiles, ring stage = " << p.stage_rows << " rows\n";
-                src << "#define PE_STREAM_TILES " << p.n_tiles << "u\n#define PE_STREAM_STAGE_ROWS " << p.stage_rows << "u\n";
+                src << "// section" << sfx << ": " << p.n_tiles << " tiles\n";
                 emit_produce();
                 src << out.str();
                 out.str(std::string{});
@@ -771,15 +792,15 @@ namespace pe_b200
                         emit_single(static_cast<int>(ri));
                     }
                 }
-                src << "__device__ __forceinline__ void pe_stream_iter(sk_ctx& k, uint32_t& fm)\n{\n";
-                // the solve starts with the ring empty: every store of the earlier sections / solves is ordered before the
+                src << "__device__ __forceinline__ void pe_stream" << sfx << "(sk_ctx& k, uint32_t& fm)\n{\n";
+                // the section starts with the ring empty: every store of the earlier sections / solves is ordered before the
                 // bulk copies that follow
                 src << "    sk_fence(k, -1);\n    k.pn = 0u;\n";
                 for(std::size_t i{}; i < p.inv.size(); ++i) { src << "    jv const inv" << i << " = sk_ld(k, " << p.inv[i] << "u);\n"; }
-                // prologue: the tiles whose rows no tile of this solve writes, up to the ring depth
-                src << "    { uint32_t tg = k.ns_mask + 1u; if(tg > " << limit_after(0, -1) << "u) { tg = " << limit_after(0, -1) << "u; } pe_stream_produce_upto(k, tg, -1); }\n";
+                // prologue: the tiles whose rows no tile of this section writes, up to the ring depth
+                src << "    { uint32_t tg = k.ns_mask + 1u; if(tg > " << limit_after(0, -1) << "u) { tg = " << limit_after(0, -1) << "u; } pe_stream_produce_upto" << sfx << "(k, tg, -1); }\n";
                 src << decl.str() << out.str();
-                src << "    k.seq0 += " << p.n_tiles << "u;\n}\n";
+                src << "    sk_end(k, " << p.n_tiles << "u);\n    k.seq0 += " << p.n_tiles << "u;\n}\n";
                 return src.str();
             }
         };
@@ -953,6 +974,20 @@ namespace pe_b200
                     if(p.src[k][i].cls == C_MEM) { take(p.ops[k].rd[i]); }
                 }
             }
+            // then the rows the prep section fetches (its tiles are generated the same way)
+            {
+                plan pq;
+                if(pr.has_sec[0] && make_plan(pr, pq, 0))
+                {
+                    for(std::size_t k{}; k < pq.ops.size(); ++k)
+                    {
+                        for(std::size_t i{}; i < pq.ops[k].rd.size(); ++i)
+                        {
+                            if(pq.src[k][i].cls == C_MEM) { take(pq.ops[k].rd[i]); }
+                        }
+                    }
+                }
+            }
             for(std::size_t s{}; s < perm.size(); ++s) { take(s); }
             auto f = [&](std::uint32_t slot) -> std::uint32_t { return slot < perm.size() ? perm[slot] : slot; };
             for(auto& sec: pr.rstreams[0].sec)
@@ -970,18 +1005,43 @@ namespace pe_b200
         return true;
     }
 
+    // opcode histogram of a section (tooling / debug)
+    std::map<std::uint32_t, std::size_t> stream_section_ops(program const& pr, int sec)
+    {
+        std::map<std::uint32_t, std::size_t> h;
+        if(pr.rstreams.empty()) { return h; }
+        for(auto const& ph: pr.rstreams[0].sec[sec])
+        {
+            for(auto const& o: ph)
+            {
+                if(!o.bubble) { ++h[o.opcode]; }
+            }
+        }
+        return h;
+    }
+
     bool stream_supported(program const& pr)
     {
         if(!pr.resident || pr.cplx || pr.rS != 1 || pr.rstreams.size() != 1) { return false; }
         std::vector<sop> ops;
-        return flatten(pr, ops);
+        return flatten(pr, 2, ops);
     }
 
     std::string stream_generate(program const& pr, stream_geom& g)
     {
         plan p;
         if(!stream_supported(pr) || !make_plan(pr, p)) { return {}; }
-        emitter e{p, kept_slots(pr), {}, {}};
+        bool const dbg{std::getenv("PE_B200_STREAM_DEBUG") != nullptr};
+        if(dbg)
+        {
+            for(int sec{}; sec < 2; ++sec)
+            {
+                std::fprintf(stderr, "stream: section %d ops:", sec);
+                for(auto const& [op, n]: stream_section_ops(pr, sec)) { std::fprintf(stderr, " %u x %zu", op, n); }
+                std::fprintf(stderr, "\n");
+            }
+        }
+        emitter e{p, "_iter", kept_slots(pr), {}, {}};
         // a store is needed when some load takes the row from memory (now or in the next solve)
         for(std::size_t k{}; k < p.ops.size(); ++k)
         {
@@ -992,9 +1052,25 @@ namespace pe_b200
         }
         static bool const keep_all{std::getenv("PE_B200_STREAM_KEEP_STORES") != nullptr};
         if(keep_all) { std::fill(e.needed.begin(), e.needed.end(), 1); }
-        std::string src{e.run()};
-        g.n_tiles = p.n_tiles;
-        g.stage_rows = p.stage_rows;
+        std::string const iter_src{e.run()};
+        // the prep section (derived per-instance values: conductances, replica rows) as tiles too when the generator covers
+        // its ops; the kernel interprets it otherwise
+        std::string prep_src;
+        plan pp;
+        static bool const no_prep{std::getenv("PE_B200_STREAM_NO_PREP") != nullptr};
+        bool const gen_prep{!no_prep && pr.has_sec[0] && make_plan(pr, pp, 0)};
+        if(gen_prep)
+        {
+            emitter ep{pp, "_prep", std::vector<std::uint8_t>(PE_R_MAX_SLOTS + 1, 1), {}, {}};  // every result of prep is kept
+            prep_src = ep.run();
+        }
+        std::ostringstream src;
+        g.n_tiles = static_cast<std::uint32_t>(p.n_tiles);
+        g.stage_rows = static_cast<std::uint32_t>(std::max(p.stage_rows, gen_prep ? pp.stage_rows : 1));
+        src << "// generated by host/stream.cpp: one-stream program as tiles, ring stage = " << g.stage_rows << " rows\n";
+        src << "#define PE_STREAM_TILES " << p.n_tiles << "u\n#define PE_STREAM_STAGE_ROWS " << g.stage_rows << "u\n";
+        if(gen_prep) { src << "#define PE_STREAM_PREP 1\n"; }
+        src << iter_src << prep_src;
         g.n_loops = 0;
         g.loop_ops = 0;
         for(auto const& rg: p.regs)
@@ -1014,11 +1090,11 @@ namespace pe_b200
         }
         for(auto const& o: p.ops)
         {
-            for(auto const s: o.wr) { st += e.needed[s] ? 1u : 0u; }
+            for(auto const s_: o.wr) { st += e.needed[s_] ? 1u : 0u; }
         }
         g.rows_fetched = rows;
         g.n_copies = cps;
         g.rows_stored = st;
-        return src;
+        return src.str();
     }
 }  // namespace pe_b200

@@ -597,6 +597,9 @@ extern "C"
         auto const f_new = reinterpret_cast<void* (*)(uint32_t, uint32_t)>(dlsym(h, "pe_emu_stream_new"));
         auto const f_free = reinterpret_cast<void (*)(void*)>(dlsym(h, "pe_emu_stream_free"));
         auto const f_solve = reinterpret_cast<uint32_t (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*)>(dlsym(h, "pe_emu_stream_solve"));
+        auto const f_has_prep = reinterpret_cast<int (*)(void)>(dlsym(h, "pe_emu_stream_has_prep"));
+        auto const f_prep = reinterpret_cast<void (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*)>(dlsym(h, "pe_emu_stream_prep"));
+        bool const mod_prep = f_has_prep != nullptr && f_prep != nullptr && f_has_prep() != 0;
         if(!f_tiles || !f_rows || !f_new || !f_free || !f_solve || f_tiles() != n_tiles || f_rows() != stage_rows || r.S != 1 || r.wsg == nullptr || r.nonlinear || r.cplx)
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: module / launch mismatch");
@@ -661,7 +664,14 @@ extern "C"
             };
             void* const st = f_new((uint32_t)r.n_slots, (uint32_t)ns_log_env);
             double t = r.t0;
-            if(r.has_prep) { run_section(0, t); }
+            if(r.has_prep)
+            {
+                if(mod_prep) { f_prep(st, wl, GL, li & 31u, ok ? 1u : 0u, &g_stream_errors); }
+                else
+                {
+                    run_section(0, t);
+                }
+            }
             for(int32_t s = 0; s < r.n_steps; ++s)
             {
                 if(r.time_stepping)

@@ -61,7 +61,7 @@ extern "C"
 
     void pe_emu_stream_free(void* p) { delete static_cast<lane_state*>(p); }
 
-    // stores made by the interpreted sections / the load table between two solves are not tracked: the solve starts
+    // stores made by the interpreted sections / the load table between two solves are not tracked: every section starts
     // with a fence anyway.  Returns the pivot-failure mask; *errors accumulates the ordering violations.
     uint32_t pe_emu_stream_solve(void* p, double* wl, uint64_t GL, uint32_t lane, uint32_t enm, uint64_t* errors)
     {
@@ -72,14 +72,35 @@ extern "C"
         s->k.enm = enm;
         uint32_t fm = 0;
         pe_stream_iter(s->k, fm);
-        // every issued tile was consumed
-        for(size_t i = 0; i < s->stage_tile.size(); ++i)
-        {
-            if(s->stage_tile[i] >= 0 && s->stage_read[i] == 0) { ++s->k.errors; }
-        }
-        if(s->k.pn != PE_STREAM_TILES) { ++s->k.errors; }
         *errors += s->k.errors;
         s->k.errors = 0;
         return fm;
+    }
+
+    // 1 = the module holds the prep section too (pe_emu_stream_prep runs it), 0 = the caller interprets it
+    int pe_emu_stream_has_prep(void)
+    {
+#ifdef PE_STREAM_PREP
+        return 1;
+#else
+        return 0;
+#endif
+    }
+
+    void pe_emu_stream_prep(void* p, double* wl, uint64_t GL, uint32_t lane, uint32_t enm, uint64_t* errors)
+    {
+#ifdef PE_STREAM_PREP
+        auto* s = static_cast<lane_state*>(p);
+        s->k.wl = wl;
+        s->k.GL = GL;
+        s->k.lane = lane;
+        s->k.enm = enm;
+        uint32_t fm = 0;
+        pe_stream_prep(s->k, fm);
+        *errors += s->k.errors;
+        s->k.errors = 0;
+#else
+        (void)p, (void)wl, (void)GL, (void)lane, (void)enm, (void)errors;
+#endif
     }
 }
