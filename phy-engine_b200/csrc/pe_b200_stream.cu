@@ -34,6 +34,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     using namespace pe_rinterp;
     constexpr int J = PE_SJ;
     constexpr uint32_t GL = 32u * J;
+    constexpr int NB = J == 1 ? 16 : 8;  // table entries whose values are in flight together
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     uint32_t const NS = 1u << ns_log;
     uint32_t const stage_bytes = PE_STREAM_STAGE_ROWS * ROWB;
@@ -86,12 +87,12 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             pe_b200_io mine{0u, 0u};
             if(e0 + lane < (uint32_t)r.n_io) { mine = r.io[e0 + lane]; }
 #pragma unroll 1
-            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += 8u)
+            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += NB)
             {
-                double v[8][J];
-                uint32_t sk[8];
+                double v[NB][J];
+                uint32_t sk[NB];
 #pragma unroll
-                for(int u = 0; u < 8; ++u)
+                for(int u = 0; u < NB; ++u)
                 {
                     sk[u] = __shfl_sync(0xffffffffu, mine.slot_kind, (int)(u0 + u));
                     uint32_t const src = __shfl_sync(0xffffffffu, mine.src, (int)(u0 + u));
@@ -114,7 +115,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                     }
                 }
 #pragma unroll
-                for(int u = 0; u < 8; ++u)
+                for(int u = 0; u < NB; ++u)
                 {
                     if(!((sk[u] >> 20) & PE_IO_LOAD)) { continue; }
                     double* const dst = at(sk[u] & 0xffffu);
@@ -193,7 +194,15 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             }
             // one linear solve (stamp + LU + substitution): the generated tiles
             uint32_t fm = 0u;
+#ifdef PE_STREAM_STEADY
+            if(s == 0) { pe_stream_iter(k, fm); }
+            else
+            {
+                pe_stream_iters(k, fm);  // every solve but the first of a launch: state that cannot have changed is not re-read
+            }
+#else
             pe_stream_iter(k, fm);
+#endif
 #pragma unroll
             for(int j = 0; j < J; ++j)
             {
@@ -221,12 +230,12 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             pe_b200_io mine{0u, 0u};
             if(e0 + lane < (uint32_t)r.n_io) { mine = r.io[e0 + lane]; }
 #pragma unroll 1
-            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += 8u)
+            for(uint32_t u0 = 0; u0 < 32u && e0 + u0 < (uint32_t)r.n_io; u0 += NB)
             {
-                double v[8][J];
-                uint32_t sk[8], sr[8];
+                double v[NB][J];
+                uint32_t sk[NB], sr[NB];
 #pragma unroll
-                for(int u = 0; u < 8; ++u)
+                for(int u = 0; u < NB; ++u)
                 {
                     sk[u] = __shfl_sync(0xffffffffu, mine.slot_kind, (int)(u0 + u));
                     sr[u] = __shfl_sync(0xffffffffu, mine.src, (int)(u0 + u));
@@ -236,7 +245,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                     for(int j = 0; j < J; ++j) { v[u][j] = on ? src[32 * j] : 0.0; }
                 }
 #pragma unroll
-                for(int u = 0; u < 8; ++u)
+                for(int u = 0; u < NB; ++u)
                 {
                     if(!((sk[u] >> 20) & PE_IO_STORE)) { continue; }
 #pragma unroll

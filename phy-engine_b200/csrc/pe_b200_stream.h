@@ -84,6 +84,23 @@ namespace pe_stream
         for(int j = 0; j < PE_SJ; ++j) { pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]); }
     }
 
+    // CAP_STEP when prev_g is known to equal 2 C / dt already (steady variant, host/stream.cpp): the same arithmetic with the
+    // freshly computed value standing in for the stored one
+    PE_SK_FN void jcap_steady(jv const& C, jv const& dt, jv const& va, jv const& vb, jv& hist, jv& prev_g)
+    {
+        for(int j = 0; j < PE_SJ; ++j)
+        {
+            prev_g.v[j] = PE_DIV(PE_MUL(2.0, C.v[j]), dt.v[j]);
+            pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]);
+        }
+    }
+
+    // ... with g_new = prev_g taken from the fetched row instead of the division (bit-identical: the row holds 2 C / dt)
+    PE_SK_FN void jcap_loaded(jv const& va, jv const& vb, jv& hist, jv const& prev_g)
+    {
+        for(int j = 0; j < PE_SJ; ++j) { hist.v[j] = PE_SUB(PE_MUL(-PE_ADD(prev_g.v[j], prev_g.v[j]), PE_SUB(va.v[j], vb.v[j])), hist.v[j]); }
+    }
+
     // simple value ops (pe_b200_rinterp.h: PE_OP_RECIP / MUL / SUB / COPY / MUL2DIV)
     PE_SK_FN jv jneg(jv const& a)
     {
@@ -161,13 +178,13 @@ namespace pe_stream
             if((k.enm >> j) & 1u) { *reinterpret_cast<double*>(p + 256 * j) = x.v[j]; }
         }
     }
-    PE_SK_FN char const* sk_stage(sk_ctx const& k, uint32_t t) { return k.ring + (size_t)((k.seq0 + t) & k.ns_mask) * k.stage_bytes; }
-    PE_SK_FN jv sk_ring(char const* sg, uint32_t row)
+    // shared-window address of the stage of tile t, at this thread's lane
+    PE_SK_FN uint32_t sk_stage(sk_ctx const& k, uint32_t t) { return k.ring_s + k.lane * 8u + ((k.seq0 + t) & k.ns_mask) * k.stage_bytes; }
+    PE_SK_FN jv sk_ring(uint32_t sg, uint32_t row)
     {
         jv x;
-        char const* p = sg + (size_t)row * ROWB;
 #pragma unroll
-        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = *reinterpret_cast<double const*>(p + 256 * j); }
+        for(int j = 0; j < PE_SJ; ++j) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x.v[j]) : "r"(sg + row * ROWB + 256u * j) : "memory"); }
         return x;
     }
     PE_SK_FN void sk_wait(sk_ctx const& k, uint32_t t)

@@ -24,7 +24,7 @@ namespace pe_b200
     namespace
     {
         constexpr std::uint32_t k_slot_mask{0x7fffu};
-        constexpr int k_max_tile_rows{44};   // ring rows one tile may fetch (forward sweep of a chain: 8 nodes x 5 rows + 1)
+        constexpr int k_max_tile_rows{64};   // ring rows one tile may fetch (config B: 32 / 44 / 56 / 64 / 80 rows -> 43.0 / 46.2 / 47.5 / 49.1 / 46.4 M solves/s)
         constexpr int k_max_tile_ops{64};
         constexpr int k_max_single_ops{12};  // ops per tile outside the periodic runs
         constexpr int k_max_inv{8};
@@ -39,12 +39,33 @@ namespace pe_b200
         {
             rop const* o{};
             std::vector<std::uint32_t> rd, wr;  // slots
+            bool steady_cap{};  // CAP_STEP in the steady variant: prev_g equals 2 C / dt already and is not stored again
+            bool steady_load{};  // ... and is fetched instead of being recomputed
         };
+
+        // rows written by the step section (a replica of such a row would go stale between two solves)
+        std::vector<std::uint8_t> step_written(program const& pr)
+        {
+            std::vector<std::uint8_t> w(PE_R_MAX_SLOTS + 1, 0);
+            for(auto const& ph: pr.rstreams[0].sec[1])
+            {
+                for(auto const& o: ph)
+                {
+                    if(o.bubble) { continue; }
+                    if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT) { w[o.dst & k_slot_mask] = 1; }
+                    else
+                    {
+                        for(auto const f: o.opnd) { w[f & k_slot_mask] = 1; }  // conservative: outputs come first, inputs are marked too
+                    }
+                }
+            }
+            return w;
+        }
 
         bool simple_value_op(std::uint32_t op) { return op == PE_OP_RECIP || op == PE_OP_MUL || op == PE_OP_SUB || op == PE_OP_COPY || op == PE_OP_MUL2DIV; }
 
         // ops of one section in program order (one stream: the phases simply follow each other)
-        bool flatten(program const& pr, int sec, std::vector<sop>& ops)
+        bool flatten(program const& pr, int sec, std::vector<sop>& ops, bool steady = false)
         {
             ops.clear();
             if(pr.rstreams.size() != 1) { return false; }
@@ -86,13 +107,37 @@ namespace pe_b200
                     ops.push_back(std::move(j));
                 }
             }
+            if(steady)
+            {
+                // Steady variant of the iter section (every solve of a launch but the first): the trapezoidal companion of a
+                // capacitor whose C and dt no op of the step / iter sections writes finds prev_g == 2 C / dt (the first solve
+                // of the launch stored exactly that, capacitor.h:106-128), so the row is neither fetched nor stored again.
+                std::vector<std::uint8_t> w(PE_R_MAX_SLOTS + 1, 0);
+                for(auto const& o: ops)
+                {
+                    for(auto const sl: o.wr) { w[sl] = 1; }
+                }
+                auto const sw{step_written(pr)};
+                for(auto& o: ops)
+                {
+                    if(o.o->opcode != PE_OP_CAP_STEP) { continue; }
+                    auto const c{o.rd[2]}, dt{o.rd[3]};
+                    if(w[c] || w[dt] || sw[c] || sw[dt] || o.rd[1] == o.rd[0]) { continue; }
+                    o.steady_cap = true;
+                    // mode 0: prev_g (= 2 C / dt) is recomputed, its row is not fetched; mode 1: the row is fetched and stands in
+                    // for the division (8 bytes more per capacitor and solve, ~40 instructions less on the warp's serial path)
+                    static int const mode{env_int("PE_B200_STREAM_STEADY_MODE", 0)};  // measured on config B: 49.1 M solves/s (mode 0) vs 46.5 (mode 1)
+                    o.steady_load = mode == 1;
+                    if(!o.steady_load) { o.rd.erase(o.rd.begin() + 1); }
+                }
+            }
             return !ops.empty();
         }
 
         bool same_shape(sop const& a, sop const& b)
         {
             rop const &x{*a.o}, &y{*b.o};
-            if(x.opcode != y.opcode || x.flags != y.flags || a.rd.size() != b.rd.size() || a.wr.size() != b.wr.size() || x.sre.size() != y.sre.size() || x.pp.size() != y.pp.size())
+            if(a.steady_cap != b.steady_cap || a.steady_load != b.steady_load || x.opcode != y.opcode || x.flags != y.flags || a.rd.size() != b.rd.size() || a.wr.size() != b.wr.size() || x.sre.size() != y.sre.size() || x.pp.size() != y.pp.size())
             {
                 return false;
             }
@@ -423,9 +468,9 @@ namespace pe_b200
             return out;
         }
 
-        bool make_plan(program const& pr, plan& p, int sec = 2)
+        bool make_plan(program const& pr, plan& p, int sec = 2, bool steady = false)
         {
-            if(!flatten(pr, sec, p.ops)) { return false; }
+            if(!flatten(pr, sec, p.ops, steady)) { return false; }
             p.inv = pick_invariants(p.ops);
             p.inv_idx.clear();
             for(std::size_t i{}; i < p.inv.size(); ++i) { p.inv_idx[p.inv[i]] = static_cast<int>(i); }
@@ -530,7 +575,7 @@ namespace pe_b200
                 return s.str();
             }
 
-            static std::string op_text(rop const& o, std::vector<std::string> const& x, std::vector<std::string> const& w, std::vector<std::string> const& st, bool declare)
+            static std::string op_text(rop const& o, std::vector<std::string> const& x, std::vector<std::string> const& w, std::vector<std::string> const& st, bool declare, int steady_cap = 0)
             {
                 std::ostringstream t;
                 char const* const dv{declare ? "jv " : ""};
@@ -547,6 +592,16 @@ namespace pe_b200
                     }
                     if(o.flags & PE_F_SCALE) { t << " jmul(" << w[0] << ", " << x[q++] << ");"; }
                     if(o.flags & PE_F_RECIP) { t << " jrcp(" << w[0] << ", fm);"; }
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
+                }
+                else if(o.opcode == PE_OP_CAP_STEP && steady_cap == 2)  // operands [hist][prev_g][C][dt][va][vb]; prev_g == 2 C / dt is taken as loaded
+                {
+                    t << dv << w[0] << " = " << x[0] << "; " << dv << w[1] << " = " << x[1] << "; jcap_loaded(" << x[4] << ", " << x[5] << ", " << w[0] << ", " << w[1] << ");";
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
+                }
+                else if(o.opcode == PE_OP_CAP_STEP && steady_cap == 1)  // operands [hist][C][dt][va][vb]; prev_g := 2 C / dt, kept in its register only
+                {
+                    t << dv << w[0] << " = " << x[0] << "; " << dv << w[1] << " = jzero(); jcap_steady(" << x[1] << ", " << x[2] << ", " << x[3] << ", " << x[4] << ", " << w[0] << ", " << w[1] << ");";
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }
                 else if(o.opcode == PE_OP_CAP_STEP)  // [hist][prev_g][C][dt][va][vb]
@@ -639,7 +694,7 @@ namespace pe_b200
                     }
                     // results are declared at function scope (the next tile may take them from their registers)
                     for(auto const& v: w) { decl << "    jv " << v << ";\n"; }
-                    body << "        " << op_text(*j.o, x, w, st, false) << "\n";
+                    body << "        " << op_text(*j.o, x, w, st, false, j.steady_cap ? (j.steady_load ? 2 : 1) : 0) << "\n";
                 }
                 out << body.str() << "    }\n";
             }
@@ -713,7 +768,7 @@ namespace pe_b200
                             st.push_back(a.str());
                         }
                     }
-                    out << "        " << op_text(*j.o, x, w, st, false) << "\n";
+                    out << "        " << op_text(*j.o, x, w, st, false, j.steady_cap ? (j.steady_load ? 2 : 1) : 0) << "\n";
                 }
                 out << "    }\n";
             }
@@ -833,24 +888,6 @@ namespace pe_b200
             for(auto& sb: o.sub) { remap_rop(sb, f); }
         }
 
-        // rows written by the step section (a replica of such a row would go stale between two solves)
-        std::vector<std::uint8_t> step_written(program const& pr)
-        {
-            std::vector<std::uint8_t> w(PE_R_MAX_SLOTS + 1, 0);
-            for(auto const& ph: pr.rstreams[0].sec[1])
-            {
-                for(auto const& o: ph)
-                {
-                    if(o.bubble) { continue; }
-                    if(o.opcode == PE_OP_DOT || o.opcode == PE_OP_CDOT) { w[o.dst & k_slot_mask] = 1; }
-                    else
-                    {
-                        for(auto const f: o.opnd) { w[f & k_slot_mask] = 1; }  // conservative: outputs come first, inputs are marked too
-                    }
-                }
-            }
-            return w;
-        }
     }  // namespace
 
     bool stream_prepare(program& pr)
@@ -966,7 +1003,21 @@ namespace pe_b200
                 if(s < perm.size() && perm[s] == none) { perm[s] = next++; }
             };
             // rows fetched by bulk copies come first, in the order the program first reads them: the rows of a tile end up
-            // next to each other (one copy per tile) and a regular family of rows stays regular
+            // next to each other (one copy per tile) and a regular family of rows stays regular.  The steady variant of the iter
+            // section (all solves of a launch but the first) is laid out first.
+            {
+                plan pst;
+                if(make_plan(pr, pst, 2, true))
+                {
+                    for(std::size_t k{}; k < pst.ops.size(); ++k)
+                    {
+                        for(std::size_t i{}; i < pst.ops[k].rd.size(); ++i)
+                        {
+                            if(pst.src[k][i].cls == C_MEM) { take(pst.ops[k].rd[i]); }
+                        }
+                    }
+                }
+            }
             for(std::size_t k{}; k < p.ops.size(); ++k)
             {
                 for(std::size_t i{}; i < p.ops[k].rd.size(); ++i)
@@ -1053,6 +1104,31 @@ namespace pe_b200
         static bool const keep_all{std::getenv("PE_B200_STREAM_KEEP_STORES") != nullptr};
         if(keep_all) { std::fill(e.needed.begin(), e.needed.end(), 1); }
         std::string const iter_src{e.run()};
+        // steady variant (see flatten): generated when it differs from the full one
+        std::string steady_src;
+        plan ps;
+        static bool const no_steady{std::getenv("PE_B200_STREAM_NO_STEADY") != nullptr};
+        bool gen_steady{!no_steady && make_plan(pr, ps, 2, true)};
+        if(gen_steady)
+        {
+            gen_steady = false;
+            for(auto const& o: ps.ops) { gen_steady = gen_steady || o.steady_cap; }
+        }
+        if(gen_steady)
+        {
+            emitter es{ps, "_iters", kept_slots(pr), {}, {}};
+            for(std::size_t k{}; k < ps.ops.size(); ++k)
+            {
+                for(std::size_t i{}; i < ps.ops[k].rd.size(); ++i)
+                {
+                    if(ps.src[k][i].cls == C_MEM || ps.src[k][i].cls == C_INV) { es.needed[ps.ops[k].rd[i]] = 1; }
+                }
+            }
+            // rows the FULL variant fetches stay stored too (the next launch starts with it)
+            for(std::size_t sl{}; sl < es.needed.size(); ++sl) { es.needed[sl] = es.needed[sl] || e.needed[sl]; }
+            if(keep_all) { std::fill(es.needed.begin(), es.needed.end(), 1); }
+            steady_src = es.run();
+        }
         // the prep section (derived per-instance values: conductances, replica rows) as tiles too when the generator covers
         // its ops; the kernel interprets it otherwise
         std::string prep_src;
@@ -1066,11 +1142,12 @@ namespace pe_b200
         }
         std::ostringstream src;
         g.n_tiles = static_cast<std::uint32_t>(p.n_tiles);
-        g.stage_rows = static_cast<std::uint32_t>(std::max(p.stage_rows, gen_prep ? pp.stage_rows : 1));
+        g.stage_rows = static_cast<std::uint32_t>(std::max({p.stage_rows, gen_prep ? pp.stage_rows : 1, gen_steady ? ps.stage_rows : 1}));
         src << "// generated by host/stream.cpp: one-stream program as tiles, ring stage = " << g.stage_rows << " rows\n";
         src << "#define PE_STREAM_TILES " << p.n_tiles << "u\n#define PE_STREAM_STAGE_ROWS " << g.stage_rows << "u\n";
         if(gen_prep) { src << "#define PE_STREAM_PREP 1\n"; }
-        src << iter_src << prep_src;
+        if(gen_steady) { src << "#define PE_STREAM_STEADY 1\n"; }
+        src << iter_src << steady_src << prep_src;
         g.n_loops = 0;
         g.loop_ops = 0;
         for(auto const& rg: p.regs)

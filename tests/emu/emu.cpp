@@ -596,7 +596,7 @@ extern "C"
         auto const f_rows = reinterpret_cast<uint32_t (*)(void)>(dlsym(h, "pe_emu_stream_stage_rows"));
         auto const f_new = reinterpret_cast<void* (*)(uint32_t, uint32_t)>(dlsym(h, "pe_emu_stream_new"));
         auto const f_free = reinterpret_cast<void (*)(void*)>(dlsym(h, "pe_emu_stream_free"));
-        auto const f_solve = reinterpret_cast<uint32_t (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*)>(dlsym(h, "pe_emu_stream_solve"));
+        auto const f_solve = reinterpret_cast<uint32_t (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*, int)>(dlsym(h, "pe_emu_stream_solve"));
         auto const f_has_prep = reinterpret_cast<int (*)(void)>(dlsym(h, "pe_emu_stream_has_prep"));
         auto const f_prep = reinterpret_cast<void (*)(void*, double*, uint64_t, uint32_t, uint32_t, uint64_t*)>(dlsym(h, "pe_emu_stream_prep"));
         bool const mod_prep = f_has_prep != nullptr && f_prep != nullptr && f_has_prep() != 0;
@@ -679,7 +679,7 @@ extern "C"
                     if(r.has_step) { run_section(1, t); }
                     t = t + r.dt;
                 }
-                uint32_t const fm = f_solve(st, wl, GL, li & 31u, ok ? 1u : 0u, &g_stream_errors);
+                uint32_t const fm = f_solve(st, wl, GL, li & 31u, ok ? 1u : 0u, &g_stream_errors, s == 0 ? 1 : 0);
                 if(ok)
                 {
                     ++solves;

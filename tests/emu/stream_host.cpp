@@ -63,7 +63,7 @@ extern "C"
 
     // stores made by the interpreted sections / the load table between two solves are not tracked: every section starts
     // with a fence anyway.  Returns the pivot-failure mask; *errors accumulates the ordering violations.
-    uint32_t pe_emu_stream_solve(void* p, double* wl, uint64_t GL, uint32_t lane, uint32_t enm, uint64_t* errors)
+    uint32_t pe_emu_stream_solve(void* p, double* wl, uint64_t GL, uint32_t lane, uint32_t enm, uint64_t* errors, int first)
     {
         auto* s = static_cast<lane_state*>(p);
         s->k.wl = wl;
@@ -71,7 +71,16 @@ extern "C"
         s->k.lane = lane;
         s->k.enm = enm;
         uint32_t fm = 0;
+#ifdef PE_STREAM_STEADY
+        if(first) { pe_stream_iter(s->k, fm); }
+        else
+        {
+            pe_stream_iters(s->k, fm);
+        }
+#else
+        (void)first;
         pe_stream_iter(s->k, fm);
+#endif
         *errors += s->k.errors;
         s->k.errors = 0;
         return fm;
