@@ -1352,7 +1352,7 @@ extern "C"
     int pe_b200_stream_supported(void) { return 1; }
 
     // nvcc -cubin for sm_100a; the module holds pe_b200_stream_kernel specialised for one program and J lanes per thread
-    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, char* log, size_t log_cap)
+    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, int GL, char* log, size_t log_cap)
     {
         char const* nv = std::getenv("PE_B200_NVCC");
         std::string nvcc = nv != nullptr ? nv : "/usr/local/cuda/bin/nvcc";
@@ -1383,7 +1383,8 @@ extern "C"
         int dev = 0;
         if(chk(cudaGetDevice(&dev), "cudaGetDevice") != 0) { return 1; }
         int const J = run->J;
-        if(run->S != 1 || run->wsg == nullptr || (J != 1 && J != 2 && J != 4) || run->I != 32 * J || run->nonlinear != 0 || run->cplx != 0)
+        int const GLJ = run->I;  // lanes per group
+        if(run->S != 1 || run->wsg == nullptr || (J != 1 && J != 2 && J != 4) || (GLJ != 32 * J && !(J == 1 && (GLJ == 16 || GLJ == 8))) || run->nonlinear != 0 || run->cplx != 0)
         {
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: needs a real linear one-stream program in HBM form (S=%d I=%d J=%d)", run->S, run->I, J);
             return 1;
@@ -1415,9 +1416,9 @@ extern "C"
             return 1;
         }
         // geometry: one CTA per SM, W warps each = lane groups resident per SM; every warp owns a ring of NS stages
-        int const GL = 32 * J;
+        int const GL = GLJ;
         long long const NG = ((long long)run->n_lanes + GL - 1) / GL;
-        size_t const stage_bytes = (size_t)stage_rows * 256u * (size_t)J;
+        size_t const stage_bytes = (size_t)stage_rows * 8u * (size_t)GL;
         static int const w_max = std::getenv("PE_B200_STREAM_WARPS") ? std::atoi(std::getenv("PE_B200_STREAM_WARPS")) : 8;
         static int const ns_cap = std::getenv("PE_B200_STREAM_NS") ? std::atoi(std::getenv("PE_B200_STREAM_NS")) : 8;
         int W = (int)std::min<long long>(std::max(1, std::min(w_max, 8)), (NG + sms - 1) / sms);
@@ -1436,6 +1437,12 @@ extern "C"
             snprintf(g_err, sizeof(g_err), "pe_b200_launch_stream: a ring stage of %zu bytes does not fit shared memory", stage_bytes);
             return 1;
         }
+        static bool const dbg_sync = std::getenv("PE_B200_STREAM_SYNC") != nullptr;
+        if(dbg_sync)
+        {
+            fprintf(stderr, "stream launch: lanes %d GL %d groups %lld W %d NS %u stage %zu B smem %zu B; before: %s\n", run->n_lanes, GL, NG, W, 1u << ns_log, stage_bytes, smem,
+                    cudaGetErrorString(cudaStreamSynchronize((cudaStream_t)stream)));
+        }
         if(chk(cudaFuncSetAttribute((void const*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(stream smem)") != 0) { return 1; }
         cudaEvent_t e0{}, e1{};
         if(g_timing)
@@ -1453,13 +1460,15 @@ extern "C"
         pe_b200_rrun arg = *run;
         uint32_t nsl = ns_log;
         void* kargs[2] = {&arg, &nsl};
-        cudaError_t const le = cudaLaunchKernelExC(&cfg, (void const*)k, kargs);
+        static bool const dbg_skip = std::getenv("PE_B200_STREAM_SKIP") != nullptr;
+        cudaError_t const le = dbg_skip ? cudaSuccess : cudaLaunchKernelExC(&cfg, (void const*)k, kargs);
         if(g_timing)
         {
             cudaEventRecord(e1, (cudaStream_t)stream);
             g_events.emplace_back(e0, e1);
         }
         if(le != cudaSuccess) { return chk(le, "pe_b200_stream_kernel launch"); }
+        if(dbg_sync) { fprintf(stderr, "stream launch: after: %s\n", cudaGetErrorString(cudaStreamSynchronize((cudaStream_t)stream))); }
         g_launches.fetch_add(1);
         g_stream_geom[0] = W;
         g_stream_geom[1] = 1 << ns_log;

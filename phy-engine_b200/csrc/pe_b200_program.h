@@ -286,13 +286,14 @@ extern "C"
     // per process, device and key); geometry J = 4 only
     int pe_b200_jit_supported(void);
     int pe_b200_launch_jit(pe_b200_rrun const* run, void const* cubin, size_t bytes, uint64_t key, void* stream);
-    // stream kernel (host/stream.cpp, csrc/pe_b200_stream.cu): one warp per lane group of 32 J lanes, S = 1, the iter
+    // stream kernel (host/stream.cpp, csrc/pe_b200_stream.cu): one warp per lane group of GL J lanes (GL = 32, or 16 / 8 with
+    // the other lanes of the warp idle: run->I = GL J), S = 1, the iter
     // section taken from a run-time compiled module (device: cubin bytes; emulator: path of a host shared object).
     // pe_b200_stream_build turns generated source into that module with the toolchain of the seam's implementation
     // (device: nvcc -cubin for sm_100a; emulator: g++ -shared); returns 0 and writes `out_path`, or != 0 with the
     // compiler's output in log[0 .. log_cap).
     int pe_b200_stream_supported(void);
-    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, char* log, size_t log_cap);
+    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, int GL, char* log, size_t log_cap);
     int pe_b200_launch_stream(pe_b200_rrun const* run, void const* blob, size_t bytes, uint64_t key, uint32_t n_tiles, uint32_t stage_rows, void* stream);
     void pe_b200_stream_last_geometry(int* out3);  // warps per CTA, ring stages, shared memory per CTA of the last stream launch
     // largest dynamic shared memory (bytes) one CTA of the resident kernel may use on the current device

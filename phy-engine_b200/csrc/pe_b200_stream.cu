@@ -1,4 +1,4 @@
-// pe_b200_stream.cu — the STREAM kernel (sm_100a): one warp per lane group of 32 J lanes, one word stream per group.
+// pe_b200_stream.cu — the STREAM kernel (sm_100a): one warp per lane group of PE_SGL x PE_SJ lanes, one word stream per group.
 //
 // Compiled at run time by nvcc (pe_b200_stream_build in pe_b200_kernels.cu, driven by host/stream.cpp) together with the
 // generated source of one program's iter section (PE_STREAM_SOURCE: tiles, ring stage layout, bulk-copy schedule).
@@ -12,6 +12,7 @@
 // stored with plain 256-byte-per-warp stores.  See csrc/pe_b200_stream.h for the ordering rules.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "pe_b200_program.h"
 #include "pe_b200_models.h"
@@ -32,8 +33,13 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
 {
     extern __shared__ __align__(128) unsigned char smem[];
     using namespace pe_rinterp;
+#if defined(PE_SK_STOP) && PE_SK_STOP == 0
+    return;
+#endif
     constexpr int J = PE_SJ;
-    constexpr uint32_t GL = 32u * J;
+    constexpr uint32_t SGL = PE_SGL;      // lanes of the warp that carry a lane of the group (the others mirror them, stores off)
+    constexpr uint32_t GL = SGL * J;      // lanes per group
+    static_assert(SGL == 32u || J == 1, "narrow groups carry one lane per thread");
     constexpr int NB = J == 1 ? 16 : 8;  // table entries whose values are in flight together
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     uint32_t const NS = 1u << ns_log;
@@ -41,7 +47,9 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     uint32_t const ring_bytes = NS * stage_bytes;
     unsigned char* const ring = smem + (size_t)warp * (ring_bytes + 128u);  // the NS mbarriers follow the ring
     sk_ctx k;
-    k.ring = reinterpret_cast<char const*>(ring) + lane * 8u;
+    uint32_t const gl_lane = lane & (SGL - 1u);
+    bool const active = lane < SGL;
+    k.ring = reinterpret_cast<char const*>(ring) + gl_lane * 8u;
     k.ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     k.bars = k.ring_s + ring_bytes;
     k.stage_bytes = stage_bytes;
@@ -51,6 +59,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     k.pn = 0u;
     k.fenced = -1;
     k.lane = lane;
+    k.n_rows = (uint32_t)r.n_slots;
     if(lane == 0u)
     {
         for(uint32_t s = 0; s < NS; ++s) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k.bars + 8u * s), "r"(1u) : "memory"); }
@@ -58,13 +67,16 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
+#if defined(PE_SK_STOP) && PE_SK_STOP == 6
+    return;
+#endif
     uint32_t const NG = (uint32_t)((r.n_lanes + GL - 1) / GL);
     tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
     for(uint32_t group = blockIdx.x + gridDim.x * warp; group < NG; group += gridDim.x * n_warps)
     {
-        int64_t const glane = (int64_t)group * GL + lane;  // first of this thread's lanes; the others are + 32 j
+        int64_t const glane = (int64_t)group * GL + gl_lane;  // first of this thread's lanes; the others are + SGL j
         k.gbase = reinterpret_cast<char*>(r.wsg + (int64_t)group * r.n_slots * GL);
-        k.wl = k.gbase + lane * 8u;
+        k.wl = k.gbase + gl_lane * 8u;
         auto at = [&](uint32_t slot) -> double* { return reinterpret_cast<double*>(k.wl + (size_t)slot * ROWB); };
 
         bool real_lane[J], counted[J], ok[J];
@@ -73,12 +85,15 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
 #pragma unroll
         for(int j = 0; j < J; ++j)
         {
-            real_lane[j] = glane + 32 * j < r.n_lanes;
-            status[j] = real_lane[j] ? r.status[glane + 32 * j] : (int32_t)PE_ST_SINGULAR;
+            real_lane[j] = active && glane + SGL * j < r.n_lanes;
+            status[j] = real_lane[j] ? r.status[glane + SGL * j] : (int32_t)PE_ST_SINGULAR;
             counted[j] = real_lane[j] && status[j] == PE_ST_OK;
             ok[j] = counted[j];
             solves[j] = 0;
         }
+#if defined(PE_SK_STOP) && PE_SK_STOP == 7
+        return;
+#endif
         // load table: persistent values -> workspace rows.  Lane l fetches entry e0 + l of the table, the warp then walks the 32
         // entries in batches whose value loads are all issued before the first store (one warp per group: nothing else hides
         // the latency of a dependent table-entry -> value -> store chain).
@@ -104,7 +119,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                         // a padding lane (beyond n_lanes) computes on the values of the last real lane: zeros would send its
                         // warp through the slow paths of the FP64 division / reciprocal at every node, and the launch ends
                         // with its slowest warp
-                        int64_t const ln = real_lane[j] ? glane + 32 * j : (int64_t)r.n_lanes - 1;
+                        int64_t const ln = glane + SGL * j < r.n_lanes ? glane + SGL * j : (int64_t)r.n_lanes - 1;  // idle lanes of a narrow group mirror their twin
                         v[u][j] = 0.0;
                         if(!on) { continue; }
                         if(kind == PE_IO_CONST) { v[u][j] = __ldg(r.cst + src); }
@@ -120,11 +135,17 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                     if(!((sk[u] >> 20) & PE_IO_LOAD)) { continue; }
                     double* const dst = at(sk[u] & 0xffffu);
 #pragma unroll
-                    for(int j = 0; j < J; ++j) { dst[32 * j] = v[u][j]; }
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(active) { dst[SGL * j] = v[u][j]; }
+                    }
                 }
             }
         }
         __syncwarp();
+#if defined(PE_SK_STOP) && PE_SK_STOP == 1
+        return;
+#endif
 
         rctx c;
         c.ws = reinterpret_cast<double*>(k.wl);
@@ -133,7 +154,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
         c.C = 1u;
         c.col = 0u;
         c.stream = 0u;
-        c.js = 32u;
+        c.js = SGL;
         // an interpreted section (prep, step): the generic vector-op executor, words read straight from global memory
         auto run_section = [&](int sec, double t)
         {
@@ -161,6 +182,9 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
         };
 
         double t = r.t0;
+#if defined(PE_SK_STOP) && PE_SK_STOP == 2
+        return;
+#endif
         if(r.has_prep)
         {
 #ifdef PE_STREAM_PREP
@@ -178,8 +202,14 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             run_section(0, t);
 #endif
         }
+#if defined(PE_SK_STOP) && PE_SK_STOP == 3
+        return;
+#endif
         for(int32_t s = 0; s < r.n_steps; ++s)
         {
+#if defined(PE_SK_STOP) && PE_SK_STOP == 4
+            if(s == 1) { return; }
+#endif
             if(r.time_stepping)
             {
                 // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
@@ -220,10 +250,13 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                 for(int j = 0; j < J; ++j)
                 {
                     if(!ok[j]) { continue; }
-                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + glane + 32 * j] = at(__ldg(r.probes + p))[32 * j]; }
+                    for(int32_t p = 0; p < r.n_probe; ++p) { r.wave[((int64_t)s * r.n_probe + p) * r.LSu + glane + SGL * j] = at(__ldg(r.probes + p))[SGL * j]; }
                 }
             }
         }
+#if defined(PE_SK_STOP) && PE_SK_STOP == 5
+        return;
+#endif
         // store table: mutable values -> persistent rows (batched like the load table)
         for(uint32_t e0 = 0; e0 < (uint32_t)r.n_io; e0 += 32u)
         {
@@ -242,7 +275,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                     bool const on = ((sk[u] >> 20) & PE_IO_STORE) != 0u;
                     double const* const src = at(sk[u] & 0xffffu);
 #pragma unroll
-                    for(int j = 0; j < J; ++j) { v[u][j] = on ? src[32 * j] : 0.0; }
+                    for(int j = 0; j < J; ++j) { v[u][j] = on ? src[SGL * j] : 0.0; }
                 }
 #pragma unroll
                 for(int u = 0; u < NB; ++u)
@@ -251,7 +284,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
 #pragma unroll
                     for(int j = 0; j < J; ++j)
                     {
-                        if(counted[j]) { r.wu[(int64_t)sr[u] * r.LSu + glane + 32 * j] = v[u][j]; }
+                        if(counted[j]) { r.wu[(int64_t)sr[u] * r.LSu + glane + SGL * j] = v[u][j]; }
                     }
                 }
             }
@@ -261,8 +294,8 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
         {
             if(counted[j])
             {
-                r.status[glane + 32 * j] = status[j];
-                r.solves[glane + 32 * j] += solves[j];
+                r.status[glane + SGL * j] = status[j];
+                r.solves[glane + SGL * j] += solves[j];
             }
         }
         __syncwarp();

@@ -23,6 +23,9 @@
 #ifndef PE_SJ
 #define PE_SJ 1
 #endif
+#ifndef PE_SGL
+#define PE_SGL 32  // lanes of a warp that carry a lane of the group (16 / 8: the others idle; PE_SJ must be 1 then)
+#endif
 
 namespace pe_stream
 {
@@ -143,11 +146,12 @@ namespace pe_stream
 
 #if defined(__CUDA_ARCH__)
     // ---- device form ---------------------------------------------------------------------------------------------
-    constexpr uint32_t ROWB = 256u * PE_SJ;  // bytes of one workspace row of a lane group
+    constexpr uint32_t ROWB = 8u * PE_SGL * PE_SJ;  // bytes of one workspace row of a lane group
+    constexpr uint32_t JSTR = 8u * PE_SGL;           // distance between the J lanes of a thread
 
     struct sk_ctx
     {
-        char* wl;           // workspace block of the group, at this thread's first lane: row r at wl + r * ROWB (+ 256 j)
+        char* wl;           // workspace block of the group, at this thread's first lane: row r at wl + r * ROWB (+ JSTR j)
         char* gbase;        // the same block at lane 0 (source of the bulk copies)
         char const* ring;   // this warp's ring (generic address), at this thread's lane
         uint32_t ring_s;    // ... shared-window address of the ring (at lane 0)
@@ -159,32 +163,43 @@ namespace pe_stream
         int32_t fenced;     // stores of the tiles <= fenced are ordered before later bulk copies
         uint32_t lane;
         uint32_t enm;       // store mask of this thread's J lanes
+        uint32_t n_rows;    // rows of the group's workspace block (bounds checks of debug builds, -DPE_SK_DEBUG)
     };
+
+#ifdef PE_SK_DEBUG
+#define PE_SK_CHECK(cond, what, a, b)                                                                                              \
+    if(!(cond)) { printf("stream kernel check failed: %s (%u, %u) block %u thread %u\n", what, (unsigned)(a), (unsigned)(b), blockIdx.x, threadIdx.x); }
+#else
+#define PE_SK_CHECK(cond, what, a, b)
+#endif
 
     PE_SK_FN jv sk_ld(sk_ctx const& k, uint32_t row)
     {
         jv x;
+        PE_SK_CHECK(row < k.n_rows, "sk_ld row", row, k.n_rows)
         char const* p = k.wl + (size_t)row * ROWB;
 #pragma unroll
-        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = *reinterpret_cast<double const*>(p + 256 * j); }
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = *reinterpret_cast<double const*>(p + JSTR * j); }
         return x;
     }
     PE_SK_FN void sk_st(sk_ctx const& k, uint32_t row, jv const& x)
     {
+        PE_SK_CHECK(row < k.n_rows, "sk_st row", row, k.n_rows)
         char* p = k.wl + (size_t)row * ROWB;
 #pragma unroll
         for(int j = 0; j < PE_SJ; ++j)
         {
-            if((k.enm >> j) & 1u) { *reinterpret_cast<double*>(p + 256 * j) = x.v[j]; }
+            if((k.enm >> j) & 1u) { *reinterpret_cast<double*>(p + JSTR * j) = x.v[j]; }
         }
     }
     // shared-window address of the stage of tile t, at this thread's lane
-    PE_SK_FN uint32_t sk_stage(sk_ctx const& k, uint32_t t) { return k.ring_s + k.lane * 8u + ((k.seq0 + t) & k.ns_mask) * k.stage_bytes; }
+    PE_SK_FN uint32_t sk_stage(sk_ctx const& k, uint32_t t) { return k.ring_s + (k.lane & (PE_SGL - 1u)) * 8u + ((k.seq0 + t) & k.ns_mask) * k.stage_bytes; }
     PE_SK_FN jv sk_ring(uint32_t sg, uint32_t row)
     {
         jv x;
+        PE_SK_CHECK(row < PE_STREAM_STAGE_ROWS, "sk_ring row", row, PE_STREAM_STAGE_ROWS)
 #pragma unroll
-        for(int j = 0; j < PE_SJ; ++j) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x.v[j]) : "r"(sg + row * ROWB + 256u * j) : "memory"); }
+        for(int j = 0; j < PE_SJ; ++j) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x.v[j]) : "r"(sg + row * ROWB + JSTR * j) : "memory"); }
         return x;
     }
     PE_SK_FN void sk_wait(sk_ctx const& k, uint32_t t)
@@ -220,6 +235,8 @@ namespace pe_stream
             uint32_t const stg = (k.seq0 + p) & k.ns_mask;
             uint32_t const bar = k.bars + 8u * stg, dst = k.ring_s + stg * k.stage_bytes + dst_row * ROWB;
             char const* src = k.gbase + (size_t)src_row * ROWB;
+            PE_SK_CHECK(src_row + rows <= k.n_rows, "sk_copy source", src_row, rows)
+            PE_SK_CHECK(dst_row + rows <= PE_STREAM_STAGE_ROWS, "sk_copy stage", dst_row, rows)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(rows * ROWB), "r"(bar)
                          : "memory");
         }

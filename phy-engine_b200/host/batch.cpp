@@ -232,9 +232,19 @@ namespace pe_b200
             // fills every SM several times over -- config D, 1e6 frequency points on 8 streams: 40.9 -> 57.1 M points/s
             if(stream_mode && pr.rS == 1)
             {
-                // stream kernel: one warp per group; one lane per thread keeps the most warps per SM (more requests in flight)
+                // stream kernel: one warp per lane group, one lane per thread.  The warp's serial instruction stream is what
+                // bounds it (ncu: fixed-latency waits, not memory), so the SM wants a warp on every scheduler: with fewer than
+                // ~4 full groups per SM a group is 16 lanes (half of each warp's lanes idle, twice the warps)
                 J = res_J > 0 ? res_J : 1;
-                I = 32 * J;
+                std::size_t const lanes_total{n_inst * std::max<std::size_t>(last_points_hint, 1)};
+                int gl{32};
+                if(J == 1 && lanes_total < 148u * 4u * 32u) { gl = 16; }
+                if(char const* e{std::getenv("PE_B200_STREAM_GL")}; e != nullptr && J == 1)
+                {
+                    int const v{std::atoi(e)};
+                    if(v == 8 || v == 16 || v == 32) { gl = v; }
+                }
+                I = gl * J;
                 return true;
             }
             J = res_J > 0 ? res_J
@@ -426,7 +436,7 @@ namespace pe_b200
             set_last_error(error);
             return false;
         }
-        int const ig{I / J};
+        int const ig{(stream_mode && pr.rS == 1) ? 32 : I / J};  // the stream kernel reads its interpreted sections one stream per warp
         auto& d_w{d_words[static_cast<std::size_t>(mi)]};
         auto& d_so{d_secoff[static_cast<std::size_t>(mi)]};
         auto& d_i{d_io[static_cast<std::size_t>(mi)]};
@@ -551,16 +561,16 @@ namespace pe_b200
         // (seconds: the sweeps are rolled loops) and cached; when it cannot be had the interpreter runs the same program.
         if(stream_mode && r.wsg != nullptr && pr.rS == 1 && !nonlinear && !pr.cplx && pe_b200_stream_supported() != 0)
         {
-            if(pr.stream_state == 0 || (pr.stream_state == 1 && pr.stream_j != J))
+            if(pr.stream_state == 0 || (pr.stream_state == 1 && pr.stream_j != I))
             {
                 pr.stream_state = -1;
                 stream_geom g{};
                 std::string const src{stream_supported(pr) ? stream_generate(pr, g) : std::string{}};
                 if(src.empty()) { pr.stream_error = "stream: the iter section holds ops the stream kernel does not cover"; }
-                else if(stream_compile(src, J, pr.stream_blob, pr.stream_key, pr.stream_error))
+                else if(stream_compile(src, J, I / J, pr.stream_blob, pr.stream_key, pr.stream_error))
                 {
                     pr.stream_state = 1;
-                    pr.stream_j = J;
+                    pr.stream_j = I;
                     pr.stream_tiles = g.n_tiles;
                     pr.stream_stage_rows = g.stage_rows;
                 }

@@ -876,7 +876,7 @@ namespace pe_b200
 
     // the stream kernel's module (host/stream.cpp): generated source + csrc/pe_b200_stream.cu -> cubin (device seam) or a
     // host shared object (the emulator's seam), cached under a key of everything that goes into it
-    bool stream_compile(std::string const& gen, int J, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile)
+    bool stream_compile(std::string const& gen, int J, int GL, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile)
     {
         int const kind{pe_b200_stream_supported()};  // 1 = device (cubin bytes travel), 2 = emulator (the path travels)
         if(kind == 0)
@@ -894,6 +894,10 @@ namespace pe_b200
         std::uint64_t h{1469598103934665603ull};
         h = fnv(h, gen.data(), gen.size());
         h = fnv(h, &J, sizeof(J));
+        h = fnv(h, &GL, sizeof(GL));
+        int const checks{std::getenv("PE_B200_STREAM_CHECKS") != nullptr ? 1 : 0};  // debug build with bounds checks
+        h = fnv(h, &checks, sizeof(checks));
+        if(char const* stop{std::getenv("PE_B200_STREAM_STOP")}; stop != nullptr) { h = fnv(h, stop, std::strlen(stop)); }
         h = fnv(h, &kind, sizeof(kind));
         for(char const* f: {"pe_b200_stream.cu", "pe_b200_stream.h", "pe_b200_program.h", "pe_b200_models.h", "pe_b200_interp.h", "pe_b200_rinterp.h"})
         {
@@ -936,7 +940,7 @@ namespace pe_b200
         }
         std::string const tmp{mod + ".tmp" + std::to_string(static_cast<long>(::getpid()))};
         std::vector<char> log(2048, 0);
-        if(pe_b200_stream_build(inc.c_str(), tmp.c_str(), csrc.c_str(), J, log.data(), log.size()) != 0)
+        if(pe_b200_stream_build(inc.c_str(), tmp.c_str(), csrc.c_str(), J, GL, log.data(), log.size()) != 0)
         {
             err = std::string{"stream: compiler failed: "} + log.data();
             ::unlink(tmp.c_str());

@@ -200,7 +200,7 @@ namespace pe_b200
         // stream kernel (host/stream.cpp): one-stream programs whose iter section is generated as tiled, TMA-fed code
         int stream_state{0};                 // 0 = not tried, 1 = module ready, -1 = not available
         bool stream_laid_out{};              // stream_prepare() has re-laid the workspace rows out (planes + replicas)
-        int stream_j{0};                     // lanes per thread the module was built for
+        int stream_j{0};                     // lanes per group (GL x J) the module was built for
         std::uint64_t stream_key{};
         std::vector<char> stream_blob;       // cubin (device) / path of the host module (emulator)
         std::string stream_error;
@@ -296,7 +296,7 @@ namespace pe_b200
     // of shared read-only operands); every executor of the program sees the same, value-equivalent program afterwards
     bool stream_prepare(program& pr);
     std::string stream_generate(program const& pr, stream_geom& g);
-    bool stream_compile(std::string const& gen, int J, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile = true);
+    bool stream_compile(std::string const& gen, int J, int GL, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile = true);
 
     struct batch
     {

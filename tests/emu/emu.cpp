@@ -545,7 +545,7 @@ extern "C"
     uint64_t pe_emu_stream_errors(void) { return g_stream_errors; }
     uint64_t pe_emu_stream_launches(void) { return g_stream_launches; }
 
-    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int, char* log, size_t log_cap)
+    int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int, int, char* log, size_t log_cap)
     {
         Dl_info info{};
         std::string here{"."};
