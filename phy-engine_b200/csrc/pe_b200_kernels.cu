@@ -1220,6 +1220,13 @@ namespace
 
     int chk(cudaError_t e, char const* what)
     {
+        // debugging aid (PE_B200_SYNC_ALL): wait for the device after every seam call and name the first one that fails
+        static bool const sync_all = std::getenv("PE_B200_SYNC_ALL") != nullptr;
+        if(sync_all && e == cudaSuccess)
+        {
+            e = cudaDeviceSynchronize();
+            fprintf(stderr, "seam: %s -> %s\n", what, cudaGetErrorString(e));
+        }
         if(e == cudaSuccess) { return 0; }
         snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
         return 1;
@@ -1358,7 +1365,11 @@ extern "C"
         std::string nvcc = nv != nullptr ? nv : "/usr/local/cuda/bin/nvcc";
         if(::access(nvcc.c_str(), X_OK) != 0) { nvcc = "nvcc"; }
         std::string const logf = std::string(out_path) + ".log";
-        std::string const cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin -DPE_SJ=" + std::to_string(J) + " '-DPE_STREAM_SOURCE=\"" + source_path +
+        // debugging aid: bounds checks with device printf (PE_B200_STREAM_CHECKS)
+        std::string dbg_flags;
+        if(std::getenv("PE_B200_STREAM_CHECKS") != nullptr) { dbg_flags += "-DPE_SK_DEBUG "; }
+        std::string const cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin " + dbg_flags + "-DPE_SJ=" + std::to_string(J) + " -DPE_SGL=" + std::to_string(GL) +
+                                " '-DPE_STREAM_SOURCE=\"" + source_path +
                                 "\"' -I'" + csrc_dir + "' -o '" + out_path + "' '" + csrc_dir + "/pe_b200_stream.cu' > '" + logf + "' 2>&1";
         int const rc = std::system(cmd.c_str());
         if(rc != 0 && log != nullptr && log_cap > 0)
@@ -1460,8 +1471,7 @@ extern "C"
         pe_b200_rrun arg = *run;
         uint32_t nsl = ns_log;
         void* kargs[2] = {&arg, &nsl};
-        static bool const dbg_skip = std::getenv("PE_B200_STREAM_SKIP") != nullptr;
-        cudaError_t const le = dbg_skip ? cudaSuccess : cudaLaunchKernelExC(&cfg, (void const*)k, kargs);
+        cudaError_t const le = cudaLaunchKernelExC(&cfg, (void const*)k, kargs);
         if(g_timing)
         {
             cudaEventRecord(e1, (cudaStream_t)stream);

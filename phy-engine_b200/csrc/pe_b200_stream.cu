@@ -33,9 +33,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
 {
     extern __shared__ __align__(128) unsigned char smem[];
     using namespace pe_rinterp;
-#if defined(PE_SK_STOP) && PE_SK_STOP == 0
-    return;
-#endif
     constexpr int J = PE_SJ;
     constexpr uint32_t SGL = PE_SGL;      // lanes of the warp that carry a lane of the group (the others mirror them, stores off)
     constexpr uint32_t GL = SGL * J;      // lanes per group
@@ -67,9 +64,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
-#if defined(PE_SK_STOP) && PE_SK_STOP == 6
-    return;
-#endif
     uint32_t const NG = (uint32_t)((r.n_lanes + GL - 1) / GL);
     tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
     for(uint32_t group = blockIdx.x + gridDim.x * warp; group < NG; group += gridDim.x * n_warps)
@@ -91,9 +85,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             ok[j] = counted[j];
             solves[j] = 0;
         }
-#if defined(PE_SK_STOP) && PE_SK_STOP == 7
-        return;
-#endif
         // load table: persistent values -> workspace rows.  Lane l fetches entry e0 + l of the table, the warp then walks the 32
         // entries in batches whose value loads are all issued before the first store (one warp per group: nothing else hides
         // the latency of a dependent table-entry -> value -> store chain).
@@ -143,9 +134,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             }
         }
         __syncwarp();
-#if defined(PE_SK_STOP) && PE_SK_STOP == 1
-        return;
-#endif
 
         rctx c;
         c.ws = reinterpret_cast<double*>(k.wl);
@@ -182,9 +170,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
         };
 
         double t = r.t0;
-#if defined(PE_SK_STOP) && PE_SK_STOP == 2
-        return;
-#endif
         if(r.has_prep)
         {
 #ifdef PE_STREAM_PREP
@@ -202,14 +187,8 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             run_section(0, t);
 #endif
         }
-#if defined(PE_SK_STOP) && PE_SK_STOP == 3
-        return;
-#endif
         for(int32_t s = 0; s < r.n_steps; ++s)
         {
-#if defined(PE_SK_STOP) && PE_SK_STOP == 4
-            if(s == 1) { return; }
-#endif
             if(r.time_stepping)
             {
                 // update_tr_step(dt) then tr_duration = prev + dt  (circuit.h:243-248)
@@ -254,9 +233,6 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
                 }
             }
         }
-#if defined(PE_SK_STOP) && PE_SK_STOP == 5
-        return;
-#endif
         // store table: mutable values -> persistent rows (batched like the load table)
         for(uint32_t e0 = 0; e0 < (uint32_t)r.n_io; e0 += 32u)
         {

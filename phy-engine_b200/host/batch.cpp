@@ -232,13 +232,15 @@ namespace pe_b200
             // fills every SM several times over -- config D, 1e6 frequency points on 8 streams: 40.9 -> 57.1 M points/s
             if(stream_mode && pr.rS == 1)
             {
-                // stream kernel: one warp per lane group, one lane per thread.  The warp's serial instruction stream is what
-                // bounds it (ncu: fixed-latency waits, not memory), so the SM wants a warp on every scheduler: with fewer than
-                // ~4 full groups per SM a group is 16 lanes (half of each warp's lanes idle, twice the warps)
+                // stream kernel: one warp per lane group, one lane per thread (two lanes per thread halve the warps: 26.8 vs
+                // 49.2 M solves/s on config B)
                 J = res_J > 0 ? res_J : 1;
                 std::size_t const lanes_total{n_inst * std::max<std::size_t>(last_points_hint, 1)};
+                // lanes per group: full warps.  Narrow groups (16 / 8 lanes with the other lanes idle: twice / four times the
+                // warps) were measured on config B, 10 000 lanes: 49.2 (32) / 45.9 (16) / 23.9 (8) M solves/s -- the memory system
+                // wants 256-byte rows more than the schedulers want warps; PE_B200_STREAM_GL keeps the switch for experiments
                 int gl{32};
-                if(J == 1 && lanes_total < 148u * 4u * 32u) { gl = 16; }
+                (void)lanes_total;
                 if(char const* e{std::getenv("PE_B200_STREAM_GL")}; e != nullptr && J == 1)
                 {
                     int const v{std::atoi(e)};

@@ -897,7 +897,6 @@ namespace pe_b200
         h = fnv(h, &GL, sizeof(GL));
         int const checks{std::getenv("PE_B200_STREAM_CHECKS") != nullptr ? 1 : 0};  // debug build with bounds checks
         h = fnv(h, &checks, sizeof(checks));
-        if(char const* stop{std::getenv("PE_B200_STREAM_STOP")}; stop != nullptr) { h = fnv(h, stop, std::strlen(stop)); }
         h = fnv(h, &kind, sizeof(kind));
         for(char const* f: {"pe_b200_stream.cu", "pe_b200_stream.h", "pe_b200_program.h", "pe_b200_models.h", "pe_b200_interp.h", "pe_b200_rinterp.h"})
         {
