@@ -177,6 +177,11 @@ extern "C"
      * forbids it; circuit_batch_last_kernel reports 2).  info[6] = last kernel, warps per CTA, ring stages, shared memory
      * per CTA (bytes), tiles per solve, rows per ring stage */
     int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
+    /* tooling (after circuit_batch_compile_host; no device needed): generated source of the stream kernel's sections and
+     * build-or-fetch of its module.  stats[8] = tiles per solve, rows per ring stage, loops, ops in loops, ops, rows
+     * fetched / bulk copies / rows stored per solve */
+    size_t circuit_batch_stream_source(void* batch, int mode, char* out, size_t cap, uint64_t* stats);
+    int circuit_batch_stream_build(void* batch, int mode);
     /* tooling for the specialised kernel of a compiled batch (circuit_batch_compile_host first; no device needed): the
      * generated source of the iter section (returns its length, copies at most cap bytes), and build-or-fetch of its cubin
      * (cluster = CTAs per lane group, 1 or 2) */

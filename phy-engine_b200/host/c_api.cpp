@@ -828,6 +828,59 @@ extern "C"
         return 0;
     }
 
+    // tooling for the stream kernel of a compiled batch (circuit_batch_compile_host first; no device needed): the generated
+    // source (returns its length; copies at most cap bytes; 0 = this mode's program does not take the stream kernel) and
+    // build-or-fetch of its module, so that __graft_entry__.build() ships the cubin of the bench configuration to the GPU box.
+    // stats[8] (optional) = tiles per solve, rows per ring stage, loops, ops in loops, ops, rows fetched per solve, bulk copies
+    // per solve, rows stored per solve.
+    size_t circuit_batch_stream_source(void* bp, int mode, char* out, size_t cap, uint64_t* stats)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 0; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc || !b->stream_mode) { return 0; }
+        auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        if(!stream_supported(pr)) { return 0; }
+        stream_geom g{};
+        std::string const src{stream_generate(pr, g)};
+        if(out != nullptr && cap > 0) { std::memcpy(out, src.data(), std::min(cap, src.size())); }
+        if(stats != nullptr)
+        {
+            std::uint64_t const v[8]{g.n_tiles, g.stage_rows, g.n_loops, g.loop_ops, g.n_ops, g.rows_fetched, g.n_copies, g.rows_stored};
+            std::memcpy(stats, v, sizeof(v));
+        }
+        return src.size();
+    }
+
+    int circuit_batch_stream_build(void* bp, int mode)
+    {
+        if(bp == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* b{static_cast<batch*>(bp)};
+        if(!b->cc || !b->stream_mode)
+        {
+            set_last_error("stream: this batch does not take the stream kernel (small batch, small or nonlinear circuit, or ops the generator does not cover)");
+            return 1;
+        }
+        auto& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
+        int I{}, J{};
+        if(!stream_supported(pr) || !b->pick_geometry(pr, I, J))
+        {
+            set_last_error("stream: the program of this mode holds ops the stream kernel does not cover");
+            return 1;
+        }
+        stream_geom g{};
+        std::string const src{stream_generate(pr, g)};
+        if(src.empty() || !stream_compile(src, J, I / J, pr.stream_blob, pr.stream_key, pr.stream_error))
+        {
+            set_last_error(src.empty() ? std::string{"stream: generator failed"} : pr.stream_error);
+            return 1;
+        }
+        pr.stream_state = 1;
+        pr.stream_j = I;
+        pr.stream_tiles = g.n_tiles;
+        pr.stream_stage_rows = g.stage_rows;
+        return 0;
+    }
+
     // tooling: the generated source of the specialised kernel's iter section (returns its length; copies at most cap bytes)
     size_t circuit_batch_jit_source(void* bp, int mode, char* out, size_t cap)
     {

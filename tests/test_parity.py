@@ -38,6 +38,8 @@ def abi(request):
 #   resident-s32j2  ... 32 streams, 2 instances per CTA handled by the same thread (vector loads)
 #   flat            flat HBM-streaming kernel (the first-generation path), one warp per 32 instances
 #   flat-g4         ... 4 sub-tree warps per 32 instances
+#   stream          the stream kernel required wherever it applies (linear circuits of more than 64 unknowns: one warp per lane
+#                   group, one word stream, generated TMA-fed tiles); everything else takes the default path
 PATHS = {
     "auto": (0, 0, 0, 0, 0, 0),
     "tree-hbm-s4": (4, 0, 0, 0, 2, 0),
@@ -49,6 +51,7 @@ PATHS = {
     "resident-s32j2": (32, 2, 2, 0, 1, 0),
     "flat": (-1, 0, 0, 0, 0, 0),
     "flat-g4": (-1, 0, 0, 4, 0, 0),
+    "stream": (0, 0, 0, 0, 0, 64),
 }
 
 
