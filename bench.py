@@ -305,6 +305,10 @@ def main():
         import threading
 
         n_pipe = 1 if args.e2e_serial else 2
+        if n_pipe > 1:
+            # the legacy default stream synchronises with every other stream: the pipelined legs run on streams of their own
+            stream = torch.cuda.Stream(device=dev)
+            b.set_stream(stream.cuda_stream)
         lanes = [(c, b, table, host_vals, host_x, stream)]
         for _ in range(n_pipe - 1):
             c2 = pe.Circuit(nl)

@@ -1368,7 +1368,8 @@ extern "C"
         // debugging aid: bounds checks with device printf (PE_B200_STREAM_CHECKS)
         std::string dbg_flags;
         if(std::getenv("PE_B200_STREAM_CHECKS") != nullptr) { dbg_flags += "-DPE_SK_DEBUG "; }
-        std::string const cmd = nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin " + dbg_flags + "-DPE_SJ=" + std::to_string(J) + " -DPE_SGL=" + std::to_string(GL) +
+        // a module is a few rolled loops (seconds to compile); the time limit only guards against a pathological program
+        std::string const cmd = "timeout 600 " + nvcc + " -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -cubin " + dbg_flags + "-DPE_SJ=" + std::to_string(J) + " -DPE_SGL=" + std::to_string(GL) +
                                 " '-DPE_STREAM_SOURCE=\"" + source_path +
                                 "\"' -I'" + csrc_dir + "' -o '" + out_path + "' '" + csrc_dir + "/pe_b200_stream.cu' > '" + logf + "' 2>&1";
         int const rc = std::system(cmd.c_str());

@@ -138,14 +138,14 @@ namespace pe_b200
             {
                 auto const primary{(at_now == analyze_type::TR || at_now == analyze_type::TROP) ? prog_mode::TR : prog_mode::DC};
                 auto& pp{cc->prog[static_cast<std::size_t>(primary)]};
-                if(pp.built && pp.resident && pp.rS == 1 && stream_supported(pp))
+                if(pp.built && pp.resident && pp.rS == 1 && stream_profitable(pp))
                 {
                     // every real-valued program the generator covers is re-laid out for it (the others run the interpreter on
                     // the same workspace geometry)
                     for(auto const m: {prog_mode::DC, prog_mode::TR, prog_mode::TROP})
                     {
                         auto& q{cc->prog[static_cast<std::size_t>(m)]};
-                        if(q.built && q.resident && q.rS == 1 && stream_supported(q)) { (void)stream_prepare(q); }
+                        if(q.built && q.resident && q.rS == 1 && stream_profitable(q)) { (void)stream_prepare(q); }
                     }
                 }
                 else
@@ -567,7 +567,7 @@ namespace pe_b200
             {
                 pr.stream_state = -1;
                 stream_geom g{};
-                std::string const src{stream_supported(pr) ? stream_generate(pr, g) : std::string{}};
+                std::string const src{pr.stream_laid_out ? stream_generate(pr, g) : std::string{}};  // laid out = accepted by stream_profitable()
                 if(src.empty()) { pr.stream_error = "stream: the iter section holds ops the stream kernel does not cover"; }
                 else if(stream_compile(src, J, I / J, pr.stream_blob, pr.stream_key, pr.stream_error))
                 {

@@ -839,7 +839,7 @@ extern "C"
         auto* b{static_cast<batch*>(bp)};
         if(!b->cc || !b->stream_mode) { return 0; }
         auto const& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
-        if(!stream_supported(pr)) { return 0; }
+        if(!pr.stream_laid_out) { return 0; }
         stream_geom g{};
         std::string const src{stream_generate(pr, g)};
         if(out != nullptr && cap > 0) { std::memcpy(out, src.data(), std::min(cap, src.size())); }
@@ -862,7 +862,7 @@ extern "C"
         }
         auto& pr{b->cc->prog[static_cast<std::size_t>(mode)]};
         int I{}, J{};
-        if(!stream_supported(pr) || !b->pick_geometry(pr, I, J))
+        if(!pr.stream_laid_out || !b->pick_geometry(pr, I, J))
         {
             set_last_error("stream: the program of this mode holds ops the stream kernel does not cover");
             return 1;

@@ -292,6 +292,7 @@ namespace pe_b200
         std::size_t rows_fetched{}, n_copies{}, rows_stored{};  // per solve
     };
     bool stream_supported(program const& pr);
+    bool stream_profitable(program const& pr);  // ... and periodic enough for the generated code to be a few rolled loops
     // re-lays the workspace rows of a one-stream program out for the stream kernel (contiguous rows per tile, replica rows
     // of shared read-only operands); every executor of the program sees the same, value-equivalent program afterwards
     bool stream_prepare(program& pr);

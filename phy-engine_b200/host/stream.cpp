@@ -1078,6 +1078,25 @@ namespace pe_b200
         return flatten(pr, 2, ops);
     }
 
+    // The stream kernel pays off where the iter section is periodic: a long chain of like elimination steps becomes a few
+    // rolled loops.  Irregular programs would come out as thousands of straight-line tiles (minutes of nvcc, no locality for
+    // the bulk copies): they keep the tree-scheduled kernels.
+    bool stream_profitable(program const& pr)
+    {
+        plan p;
+        if(!stream_supported(pr) || !make_plan(pr, p)) { return false; }
+        std::size_t in_loops{}, straight{};
+        for(auto const& rg: p.regs)
+        {
+            if(rg.loop()) { in_loops += static_cast<std::size_t>(rg.n) * static_cast<std::size_t>(rg.per); }
+            else
+            {
+                straight += static_cast<std::size_t>(rg.per);
+            }
+        }
+        return in_loops * 10 >= p.ops.size() * 8 && straight <= 1200;
+    }
+
     std::string stream_generate(program const& pr, stream_geom& g)
     {
         plan p;

@@ -55,8 +55,14 @@ PATHS = {
 }
 
 
+# tests whose circuits the stream kernel applies to (elsewhere the "stream" path is the "auto" path again)
+STREAM_TESTS = {"test_rc_ladder_batch_sweep", "test_tr_resume_continues_like_reference", "test_random_links_dc", "test_linear_zoo_every_linear_element"}
+
+
 @pytest.fixture(params=list(PATHS), autouse=True)
 def path(request, abi):
+    if request.param == "stream" and request.node.originalname not in STREAM_TESTS:
+        pytest.skip("the stream kernel does not apply to this circuit")
     rc = abi.lib.phy_engine_b200_set_default_path(*PATHS[request.param])
     assert rc == 0
     yield request.param
