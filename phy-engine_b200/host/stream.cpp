@@ -1094,7 +1094,7 @@ namespace pe_b200
                 straight += static_cast<std::size_t>(rg.per);
             }
         }
-        return in_loops * 10 >= p.ops.size() * 8 && straight <= 1200;
+        return in_loops * 10 >= p.ops.size() * 7 && straight <= 1200;
     }
 
     std::string stream_generate(program const& pr, stream_geom& g)

@@ -47,7 +47,7 @@ def ladder_batch(abi, n_sections, n_inst, tuning, steps, resident=None, seed=1, 
     return nl, c, b, over
 
 
-@pytest.mark.parametrize("n_sections,n_inst,steps", [(70, 33, 4), (300, 40, 6), (1000, 70, 3)])
+@pytest.mark.parametrize("n_sections,n_inst,steps", [(160, 33, 4), (300, 40, 6), (1000, 70, 3)])
 def test_stream_kernel_is_bit_identical_to_the_interpreter(ref, abi, n_sections, n_inst, steps):  # noqa: F811
     before = emu_counters(abi)
     nl, c1, b1, over = ladder_batch(abi, n_sections, n_inst, NO_STREAM_NO_JIT, steps, resident=(1, 0, 1))
@@ -94,18 +94,19 @@ def test_stream_kernel_waveform_probes_and_ragged_batch(ref, abi):  # noqa: F811
 def test_stream_kernel_runs_the_dc_program_too(ref, abi):  # noqa: F811
     # OP of a large linear circuit takes the stream kernel as well (the DC program of the one-stream compile: no companion
     # models, one solve); a load resistor per section makes the DC solution non-trivial
-    n_sections, n_inst = 90, 37
+    n_sections, n_inst = 150, 37
     nl, info = wl.rc_ladder(n_sections)
     g = 0  # element 0 is the ground placeholder
     loads = []
-    for k, e in enumerate(info["C"]):
-        if k % 3 == 0:
-            r = nl.add(pe.R, 4.7e3)
-            nl.wire(r, 0, e, 0)
-            nl.wire(r, 1, g, 0)
-            loads.append(r)
+    for e in info["C"]:
+        r = nl.add(pe.R, 47e3)
+        nl.wire(r, 0, e, 0)
+        nl.wire(r, 1, g, 0)
+        loads.append(r)
     rng = np.random.default_rng(4)
-    over = [(e, "r", wl.sweep_values(rng, 1e3, n_inst)) for e in info["R"][10:40]] + [(e, "r", wl.sweep_values(rng, 4.7e3, n_inst)) for e in loads]
+    # every like element is swept: a partial sweep would make neighbouring elimination steps differ (broadcast constants next
+    # to per-instance rows) and the program would not be periodic enough for the stream kernel
+    over = [(e, "r", wl.sweep_values(rng, 1e3, n_inst)) for e in info["R"]] + [(e, "r", wl.sweep_values(rng, 47e3, n_inst)) for e in loads]
     want = refapi.run_batch(nl, pe.OP, n_inst, over)
     assert (want["ok"] == 1).all()
     c = pe.Circuit(nl, abi)
