@@ -177,6 +177,12 @@ extern "C"
      * forbids it; circuit_batch_last_kernel reports 2).  info[6] = last kernel, warps per CTA, ring stages, shared memory
      * per CTA (bytes), tiles per solve, rows per ring stage */
     int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
+    /* reduce-and-core path: DC / OP of one huge linear circuit (resistors, DC sources; >= 20 000 unknowns, config A of
+     * BASELINE.json) per instance: level-scheduled elimination of the degree <= 2 nodes, dense LU of the rest on the FP64
+     * tensor cores (circuit_batch_last_kernel reports 3).  info[8] = unknowns, eliminated nodes, levels, core rows, edges
+     * (fill included), kernel launches of the last solve, leading dimension of the dense core, edges inside the core */
+    int circuit_batch_frontal_info(void* batch, int64_t* info);
+    int phy_engine_b200_set_frontal_min(size_t n_unknowns); /* size threshold of that path (default 20 000 unknowns) */
     /* tooling (after circuit_batch_compile_host; no device needed): generated source of the stream kernel's sections and
      * build-or-fetch of its module.  stats[8] = tiles per solve, rows per ring stage, loops, ops in loops, ops, rows
      * fetched / bulk copies / rows stored per solve */

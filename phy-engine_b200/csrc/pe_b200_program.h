@@ -296,6 +296,43 @@ extern "C"
     int pe_b200_stream_build(char const* source_path, char const* out_path, char const* csrc_dir, int J, int GL, char* log, size_t log_cap);
     int pe_b200_launch_stream(pe_b200_rrun const* run, void const* blob, size_t bytes, uint64_t key, uint32_t n_tiles, uint32_t stage_rows, void* stream);
     void pe_b200_stream_last_geometry(int* out3);  // warps per CTA, ring stages, shared memory per CTA of the last stream launch
+    // ---- reduce-and-core path (csrc/pe_b200_frontal.cu, host/frontal.cpp): one huge linear DC circuit per instance ------
+    // Values are lane-interleaved over the instances: v[id * B + instance].  The symbolic phase numbers the resistor graph's
+    // edges (fill edges included), schedules the elimination of every node of degree <= 2 in levels of pairwise
+    // non-adjacent nodes, and maps what is left (the core) to a dense matrix, nodes first, source branches last.
+    typedef struct pe_b200_frontal
+    {
+        int32_t n_inst;
+        int64_t B;  // lane stride of the value arrays (>= n_inst)
+        int32_t n_nodes, n_res, n_idc, n_vdc, n_edges;
+        double const* rval;       // [n_res][B] resistances
+        int32_t const* res_a;     // [n_res] node unknown of pin A (-1 = ground)
+        int32_t const* res_b;
+        int32_t const* res_edge;  // [n_res] edge the resistor contributes to (-1: to ground / self loop)
+        int32_t const* idc_p;     // [n_idc] node unknowns (+, -)
+        int32_t const* idc_q;
+        double const* idc_val;    // [n_idc][B]
+        int32_t const* ops;       // [n_ops][6]: k, a, b, edge(k,a), edge(k,b), edge(a,b)   (-1 = absent)
+        int32_t const* level_off_host;  // HOST pointer: [n_levels + 1] first op of every level
+        int32_t n_levels;
+        int32_t n_core, n_core_nodes, n_core_edges;
+        int64_t ld_core;              // n_core rounded up to the LU block size (64)
+        int32_t const* core_unknown;  // [n_core] unknown index of every core row (nodes, then branches)
+        int32_t const* core_edges;    // [n_core_edges][3]: core row i, core row j, edge id
+        int32_t const* vdc;           // [n_vdc][3]: unused, core row of node +, core row of node - (-1 = ground)
+        double const* vdc_val;        // [n_vdc][B]
+        double* d;   // [n_nodes][B] diagonals (work)
+        double* z;   // [n_nodes][B] right-hand side of the node rows (work)
+        double* g;   // [n_edges][B] edge conductances (work)
+        double* M;   // [n_inst][ld_core * ld_core] dense core, column-major
+        double* c;   // [n_inst][ld_core]
+        double* x;   // solution rows x[unknown * LSx + instance]
+        int64_t LSx;
+        int32_t* status;  // [n_inst]
+    } pe_b200_frontal;
+    int pe_b200_frontal_run(pe_b200_frontal const* f, void* stream, uint64_t* n_launches);
+    char const* pe_b200_frontal_last_error(void);
+
     // largest dynamic shared memory (bytes) one CTA of the resident kernel may use on the current device
     size_t pe_b200_resident_smem_limit(void);
     char const* pe_b200_dev_last_error(void);

@@ -650,6 +650,17 @@ namespace pe_b200
             return false;
         }
         last_points_hint = 1;
+        // one huge linear DC circuit (config A): the parallelism is in the elimination DAG, not in static per-lane programs
+        if(frontal_applicable(*parent, static_cast<std::size_t>(make_numbering(parent->nl).unknowns())))
+        {
+            if(!frontal) { frontal = std::shared_ptr<frontal_state>(frontal_new(), frontal_delete); }
+            return frontal_run(*this, *frontal);
+        }
+        if(frontal)
+        {
+            frontal.reset();
+            cc.reset();  // the program-less record of the other path
+        }
         if(!ensure_compiled() || !upload_sweeps()) { return false; }
         auto const at{parent->at};
         int const n{cc->num.unknowns()};

@@ -539,6 +539,25 @@ extern "C"
 
     int circuit_batch_last_kernel(void* b) { return b == nullptr ? -1 : static_cast<batch*>(b)->last_jit; }
 
+    // circuits of at least this many unknowns (default 20 000) that consist of resistors and DC sources take the
+    // reduce-and-core path for DC / OP; process-wide
+    int phy_engine_b200_set_frontal_min(size_t n_unknowns)
+    {
+        frontal_min_unknowns() = n_unknowns;
+        return 0;
+    }
+
+    // reduce-and-core path (config A): info[8] = unknowns, eliminated nodes, levels, core rows, edges (fill included), kernel
+    // launches of the last solve, leading dimension of the dense core, edges inside the core; 1 = the batch did not take it
+    int circuit_batch_frontal_info(void* b, int64_t* info)
+    {
+        if(b == nullptr || info == nullptr) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        if(!bp->frontal) { return 1; }
+        frontal_stats(bp->frontal.get(), info);
+        return 0;
+    }
+
     // stream kernel of the last launch: [0] last kernel (2 = stream), [1] warps per CTA, [2] ring stages, [3] shared memory
     // per CTA, [4] tiles per solve, [5] rows per ring stage
     int circuit_batch_stream_info(void* b, int mode, int64_t* info)

@@ -299,9 +299,20 @@ namespace pe_b200
     std::string stream_generate(program const& pr, stream_geom& g);
     bool stream_compile(std::string const& gen, int J, int GL, std::vector<char>& blob, std::uint64_t& key, std::string& err, bool allow_compile = true);
 
+    // host/frontal.cpp: reduce-and-core path for one huge linear DC circuit per instance (config A)
+    struct frontal_state;
+    struct batch;
+    bool frontal_applicable(circuit const& c, std::size_t n_unknowns);
+    std::size_t& frontal_min_unknowns();
+    frontal_state* frontal_new();
+    void frontal_delete(frontal_state* s);
+    bool frontal_run(batch& b, frontal_state& s);
+    void frontal_stats(frontal_state const* s, std::int64_t* out8);  // unknowns, eliminated nodes, levels, core rows, edges, launches, ld, core edges
+
     struct batch
     {
         circuit* parent{};
+        std::shared_ptr<frontal_state> frontal;  // set once analyze() took the reduce-and-core path
         std::size_t n_inst{};
         std::int64_t LSi{};  // padded instance count
         int device{0};
@@ -350,7 +361,7 @@ namespace pe_b200
         int res_stream{0};   // stream kernel: 0 = automatic, 1 = required, -1 = off
         bool stream_mode{};  // the real-valued programs were compiled with one stream per lane group for the stream kernel
         std::uint64_t stream_rejected_rev{};  // structure revision whose program the stream generator does not cover
-        int last_jit{};  // 1 = the last tree-streaming launch ran the specialised (run-time compiled) kernel, 2 = the stream kernel
+        int last_jit{};  // 1 = the last tree-streaming launch ran the specialised (run-time compiled) kernel, 2 = the stream kernel, 3 = the reduce-and-core path
         int last_I{}, last_J{}, last_S{};  // geometry of the last resident launch (0 = the HBM-streaming kernel ran)
 
         // results of the last analyze()

@@ -390,6 +390,15 @@ class Batch:
         """0 = word interpreter, 1 = specialised (run-time compiled) tree-streaming kernel, 2 = stream kernel"""
         return int(self.lib.circuit_batch_last_kernel(self.h))
 
+    def frontal_info(self):
+        """reduce-and-core path of the last analyze(): None when it was not taken"""
+        v = (ct.c_int64 * 8)()
+        self.lib.circuit_batch_frontal_info.argtypes = [ct.c_void_p, ct.POINTER(ct.c_int64)]
+        if self.lib.circuit_batch_frontal_info(self.h, v) != 0:
+            return None
+        keys = ("unknowns", "eliminated", "levels", "core_rows", "edges", "launches", "ld_core", "core_edges")
+        return {k: int(x) for k, x in zip(keys, v)}
+
     def stream_info(self, mode: int) -> dict:
         v = (ct.c_int64 * 6)()
         self._rc(self.lib.circuit_batch_stream_info(self.h, mode, v), "circuit_batch_stream_info")

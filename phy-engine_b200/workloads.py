@@ -455,3 +455,34 @@ def flash_adc(levels: int = 16, vref: float = 5.0, r: float = 1e3):
         nl.wire(cm, 2, cm, 2)  # a net of its own for the output pin: a pure digital node
         cmps.append(cm)
     return nl, {"Vref": vr, "Vin": vin, "R": rs, "CMP": cmps}
+
+
+def series_parallel(n_ring: int = 100_000, n_merge: int = 9_000, seed: int = 1, v: float = 3.0):
+    """Config A: a seeded clone of benchmark/series_parallel.cpp (the reference draws from a non-deterministic engine,
+    series_parallel.cpp:8): ground - R2 - R3_0 - ... - R3_{n-1} - node4, VDC between node2 (+) and node4 (-), R1 from node2 to
+    ground, R4 left unconnected as in the source, resistances ~ U(1e-5, 1e5) Ohm; then n_merge random pairs of chain nodes are
+    merged (merge_node = a wire between them in the C ABI's netlist format).  Returns (netlist, info)."""
+    rng = np.random.default_rng(seed)
+    nl = Netlist()
+    g = nl.ground()
+    r1 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))
+    r2 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))
+    r4 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))  # never connected
+    src = nl.add(pe.VDC, v)
+    nl.wire(r1, 1, g, 0)
+    nl.wire(r2, 0, g, 0)
+    vals = rng.uniform(1e-5, 1e5, n_ring)
+    chain = []
+    prev = r2
+    for i in range(n_ring):
+        r3 = nl.add(pe.R, float(vals[i]))
+        nl.wire(r3, 0, prev, 1)
+        chain.append(r3)
+        prev = r3
+    nl.wire(src, 0, r1, 0)
+    nl.wire(src, 1, prev, 1)
+    pairs = rng.integers(0, n_ring, size=(n_merge, 2))
+    for a, b in pairs:
+        if a != b:
+            nl.wire(chain[int(a)], 0, chain[int(b)], 0)
+    return nl, {"V": src, "R1": r1, "R2": r2, "R4": r4, "chain": chain}

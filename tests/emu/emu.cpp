@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <dlfcn.h>
+#include <cmath>
 #include <algorithm>
 #include <array>
 #include <map>
@@ -538,6 +539,119 @@ extern "C"
     {
         snprintf(g_err, sizeof(g_err), "pe_b200_launch_jit: not available in the emulator");
         return 1;
+    }
+
+    // ---- reduce-and-core path: the same steps as csrc/pe_b200_frontal.cu, one instance at a time on the host -----------
+    char const* pe_b200_frontal_last_error(void) { return g_err; }
+    int pe_b200_frontal_run(pe_b200_frontal const* fp, void*, uint64_t* n_launches)
+    {
+        if(fp == nullptr || fp->n_inst <= 0) { return 0; }
+        pe_b200_frontal const& f = *fp;
+        int64_t const B = f.B, ld = f.ld_core;
+        for(int64_t inst = 0; inst < f.n_inst; ++inst)
+        {
+            for(int64_t k = 0; k < f.n_nodes; ++k) { f.d[k * B + inst] = f.z[k * B + inst] = 0.0; }
+            for(int64_t k = 0; k < f.n_edges; ++k) { f.g[k * B + inst] = 0.0; }
+            for(int64_t r = 0; r < f.n_res; ++r)
+            {
+                double const g = 1.0 / f.rval[r * B + inst];
+                if(f.res_a[r] >= 0) { f.d[(int64_t)f.res_a[r] * B + inst] += g; }
+                if(f.res_b[r] >= 0) { f.d[(int64_t)f.res_b[r] * B + inst] += g; }
+                if(f.res_edge[r] >= 0) { f.g[(int64_t)f.res_edge[r] * B + inst] += g; }
+            }
+            for(int64_t k = 0; k < f.n_idc; ++k)
+            {
+                double const i = f.idc_val[k * B + inst];
+                if(f.idc_p[k] >= 0) { f.z[(int64_t)f.idc_p[k] * B + inst] -= i; }
+                if(f.idc_q[k] >= 0) { f.z[(int64_t)f.idc_q[k] * B + inst] += i; }
+            }
+            int64_t const n_ops = f.level_off_host[f.n_levels];
+            for(int64_t o = 0; o < n_ops; ++o)
+            {
+                int32_t const* op = f.ops + o * 6;
+                int32_t const k = op[0], a = op[1], b = op[2];
+                double const p = f.d[(int64_t)k * B + inst];
+                if(p == 0.0 || !std::isfinite(p)) { f.status[inst] = PE_ST_SINGULAR; }
+                double const zk = f.z[(int64_t)k * B + inst];
+                double const g1 = a >= 0 ? f.g[(int64_t)op[3] * B + inst] : 0.0, g2 = b >= 0 ? f.g[(int64_t)op[4] * B + inst] : 0.0;
+                double const m1 = g1 / p, m2 = g2 / p;
+                if(a >= 0)
+                {
+                    f.d[(int64_t)a * B + inst] -= g1 * m1;
+                    f.z[(int64_t)a * B + inst] += m1 * zk;
+                }
+                if(b >= 0)
+                {
+                    f.d[(int64_t)b * B + inst] -= g2 * m2;
+                    f.z[(int64_t)b * B + inst] += m2 * zk;
+                }
+                if(op[5] >= 0) { f.g[(int64_t)op[5] * B + inst] += g1 * m2; }
+            }
+            double* const M = f.M + inst * ld * ld;
+            double* const c = f.c + inst * ld;
+            for(int64_t k = 0; k < ld * ld; ++k) { M[k] = 0.0; }
+            for(int64_t t = 0; t < ld; ++t)
+            {
+                c[t] = 0.0;
+                if(t < f.n_core_nodes)
+                {
+                    M[t + t * ld] = f.d[(int64_t)f.core_unknown[t] * B + inst];
+                    c[t] = f.z[(int64_t)f.core_unknown[t] * B + inst];
+                }
+                else if(t < f.n_core)
+                {
+                    int64_t const k = t - f.n_core_nodes;
+                    int32_t const p = f.vdc[3 * k + 1], q = f.vdc[3 * k + 2];
+                    if(p >= 0) { M[p + t * ld] = M[t + p * ld] = 1.0; }
+                    if(q >= 0) { M[q + t * ld] = M[t + q * ld] = -1.0; }
+                    c[t] = f.vdc_val[k * B + inst];
+                }
+                else
+                {
+                    M[t + t * ld] = 1.0;
+                }
+            }
+            for(int64_t k = 0; k < f.n_core_edges; ++k)
+            {
+                int32_t const i = f.core_edges[3 * k], j = f.core_edges[3 * k + 1];
+                double const g = f.g[(int64_t)f.core_edges[3 * k + 2] * B + inst];
+                M[i + j * ld] = M[j + i * ld] = -g;
+            }
+            for(int64_t k = 0; k < ld; ++k)
+            {
+                double const p = M[k + k * ld];
+                if(p == 0.0 || !std::isfinite(p)) { f.status[inst] = PE_ST_SINGULAR; }
+                for(int64_t i = k + 1; i < ld; ++i) { M[i + k * ld] /= p; }
+                for(int64_t j = k + 1; j < ld; ++j)
+                {
+                    double const u = M[k + j * ld];
+                    if(u == 0.0) { continue; }
+                    for(int64_t i = k + 1; i < ld; ++i) { M[i + j * ld] -= M[i + k * ld] * u; }
+                }
+            }
+            for(int64_t k = 0; k < ld; ++k)
+            {
+                for(int64_t i = k + 1; i < ld; ++i) { c[i] -= M[i + k * ld] * c[k]; }
+            }
+            for(int64_t k = ld - 1; k >= 0; --k)
+            {
+                c[k] /= M[k + k * ld];
+                for(int64_t i = 0; i < k; ++i) { c[i] -= M[i + k * ld] * c[k]; }
+            }
+            for(int64_t t = 0; t < f.n_core; ++t) { f.x[(int64_t)f.core_unknown[t] * f.LSx + inst] = c[t]; }
+            for(int64_t o = n_ops - 1; o >= 0; --o)
+            {
+                int32_t const* op = f.ops + o * 6;
+                int32_t const k = op[0], a = op[1], b = op[2];
+                double v = f.z[(int64_t)k * B + inst];
+                if(a >= 0) { v += f.g[(int64_t)op[3] * B + inst] * f.x[(int64_t)a * f.LSx + inst]; }
+                if(b >= 0) { v += f.g[(int64_t)op[4] * B + inst] * f.x[(int64_t)b * f.LSx + inst]; }
+                f.x[(int64_t)k * f.LSx + inst] = v / f.d[(int64_t)k * B + inst];
+            }
+        }
+        ++g_launches;
+        if(n_launches != nullptr) { *n_launches = 1; }
+        return 0;
     }
 
     // ---- stream kernel: the generated source is compiled for the host (stream_host.cpp) and run lane by lane ------------
