@@ -179,8 +179,9 @@ extern "C"
     int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
     /* reduce-and-core path: DC / OP of one huge linear circuit (resistors, DC sources; >= 20 000 unknowns, config A of
      * BASELINE.json) per instance: level-scheduled elimination of the degree <= 2 nodes, dense LU of the rest on the FP64
-     * tensor cores (circuit_batch_last_kernel reports 3).  info[8] = unknowns, eliminated nodes, levels, core rows, edges
-     * (fill included), kernel launches of the last solve, leading dimension of the dense core, edges inside the core */
+     * tensor cores (circuit_batch_last_kernel reports 3).  info[11] = unknowns, eliminated nodes, levels, core rows, edges
+     * (fill included), kernel launches of the last solve, leading dimension of the dense core, edges inside the core, device
+     * microseconds of the reduction / the core LU / the substitutions of the last solve */
     int circuit_batch_frontal_info(void* batch, int64_t* info);
     int phy_engine_b200_set_frontal_min(size_t n_unknowns); /* size threshold of that path (default 20 000 unknowns) */
     /* tooling (after circuit_batch_compile_host; no device needed): generated source of the stream kernel's sections and

@@ -385,6 +385,13 @@ extern "C"
         uint64_t nl = 0;
         int64_t const B = f.B;
         auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+        cudaEvent_t ev[4]{};
+        bool const timing = f.phase_ms_host != nullptr;
+        if(timing)
+        {
+            for(auto& e: ev) { cudaEventCreate(&e); }
+            cudaEventRecord(ev[0], st);
+        }
         if(fchk(cudaMemsetAsync(f.d, 0, sizeof(double) * (size_t)f.n_nodes * (size_t)B, st), "memset d") != 0) { return 1; }
         if(fchk(cudaMemsetAsync(f.z, 0, sizeof(double) * (size_t)f.n_nodes * (size_t)B, st), "memset z") != 0) { return 1; }
         if(fchk(cudaMemsetAsync(f.g, 0, sizeof(double) * (size_t)std::max(f.n_edges, 1) * (size_t)B, st), "memset g") != 0) { return 1; }
@@ -398,6 +405,7 @@ extern "C"
             ++nl;
         }
         int64_t const ld = f.ld_core;
+        if(timing) { cudaEventRecord(ev[1], st); }
         if(ld > 0)
         {
             if(fchk(cudaMemsetAsync(f.M, 0, sizeof(double) * (size_t)ld * (size_t)ld * (size_t)f.n_inst, st), "memset core") != 0) { return 1; }
@@ -415,6 +423,7 @@ extern "C"
                 fr_lu_update<<<dim3(tb, tb, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0);
                 nl += 2;
             }
+            if(timing) { cudaEventRecord(ev[2], st); }
             fr_solve_core<<<(unsigned)f.n_inst, 1024, 0, st>>>(f.M, f.c, ld);
             fr_core_scatter<<<dim3(blocks(f.n_core), (unsigned)f.n_inst), 256, 0, st>>>(f);
             nl += 2;
@@ -427,6 +436,17 @@ extern "C"
             ++nl;
         }
         if(n_launches != nullptr) { *n_launches = nl; }
+        if(timing)
+        {
+            cudaEventRecord(ev[3], st);
+            cudaEventSynchronize(ev[3]);
+            for(int i = 0; i < 3; ++i)
+            {
+                float ms = 0.f;
+                f.phase_ms_host[i] = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess ? (double)ms : 0.0;
+            }
+            for(auto& e: ev) { cudaEventDestroy(e); }
+        }
         return fchk(cudaGetLastError(), "frontal launch");
     }
 }

@@ -329,6 +329,7 @@ extern "C"
         double* x;   // solution rows x[unknown * LSx + instance]
         int64_t LSx;
         int32_t* status;  // [n_inst]
+        double* phase_ms_host;  // HOST pointer, optional: [3] device time of reduce / core LU / substitutions (the call then waits for the stream)
     } pe_b200_frontal;
     int pe_b200_frontal_run(pe_b200_frontal const* f, void* stream, uint64_t* n_launches);
     char const* pe_b200_frontal_last_error(void);

@@ -547,8 +547,9 @@ extern "C"
         return 0;
     }
 
-    // reduce-and-core path (config A): info[8] = unknowns, eliminated nodes, levels, core rows, edges (fill included), kernel
-    // launches of the last solve, leading dimension of the dense core, edges inside the core; 1 = the batch did not take it
+    // reduce-and-core path (config A): info[11] = unknowns, eliminated nodes, levels, core rows, edges (fill included), kernel
+    // launches of the last solve, leading dimension of the dense core, edges inside the core, device microseconds of the
+    // reduction / the core LU / the substitutions of the last solve; 1 = the batch did not take it
     int circuit_batch_frontal_info(void* b, int64_t* info)
     {
         if(b == nullptr || info == nullptr) { return 1; }

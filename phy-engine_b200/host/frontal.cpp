@@ -62,6 +62,7 @@ namespace pe_b200
         device_buf d_rval, d_idc, d_vdcv, d_ia, d_ib, d_ie, d_ip, d_iq, d_ops, d_cu, d_ce, d_vdc, d_d, d_z, d_g, d_M, d_c;
         std::size_t n_inst_built{};
         std::uint64_t launches{};
+        double phase_ms[3]{};  // device time of the last solve: reduce / core LU / substitutions
     };
 
     frontal_state* frontal_new() { return new frontal_state; }
@@ -76,6 +77,7 @@ namespace pe_b200
         out[5] = static_cast<std::int64_t>(s->launches);
         out[6] = s->ld_core;
         out[7] = static_cast<std::int64_t>(s->core_edges.size() / 3);
+        for(int i{}; i < 3; ++i) { out[8 + i] = static_cast<std::int64_t>(s->phase_ms[i] * 1000.0); }  // microseconds
     }
 
     // symbolic phase: pure integer / graph work on the host
@@ -350,6 +352,7 @@ namespace pe_b200
         f.x = static_cast<double*>(b.d_wi.p);
         f.LSx = B;
         f.status = static_cast<std::int32_t*>(b.d_status.p);
+        f.phase_ms_host = s.phase_ms;
         std::uint64_t nl{};
         if(pe_b200_frontal_run(&f, b.stream, &nl) != 0) { return fail(std::string{"frontal: "} + pe_b200_frontal_last_error()); }
         s.launches = nl;

@@ -307,7 +307,7 @@ namespace pe_b200
     frontal_state* frontal_new();
     void frontal_delete(frontal_state* s);
     bool frontal_run(batch& b, frontal_state& s);
-    void frontal_stats(frontal_state const* s, std::int64_t* out8);  // unknowns, eliminated nodes, levels, core rows, edges, launches, ld, core edges
+    void frontal_stats(frontal_state const* s, std::int64_t* out11);  // unknowns, eliminated nodes, levels, core rows, edges, launches, ld, core edges, device us of reduce / LU / substitutions
 
     struct batch
     {

@@ -73,7 +73,12 @@ class Netlist:
 
     def component_index(self, ele: int) -> int:
         """index into vec_pos/chunk_pos (components = non-ground elements in order)"""
-        return sum(1 for c in self.elements[:ele] if c != GROUND)
+        cache = self.__dict__.get("_comp_index")
+        if cache is None or len(cache) != len(self.elements):
+            # prefix count of the non-ground elements (netlists of 1e5 elements ask for this per element)
+            cache = np.concatenate(([0], np.cumsum(np.asarray(self.elements) != GROUND)))[:-1]
+            self.__dict__["_comp_index"] = cache
+        return int(cache[ele])
 
     def arrays(self):
         e = np.asarray(self.elements, dtype=np.int32)
@@ -392,11 +397,11 @@ class Batch:
 
     def frontal_info(self):
         """reduce-and-core path of the last analyze(): None when it was not taken"""
-        v = (ct.c_int64 * 8)()
+        v = (ct.c_int64 * 11)()
         self.lib.circuit_batch_frontal_info.argtypes = [ct.c_void_p, ct.POINTER(ct.c_int64)]
         if self.lib.circuit_batch_frontal_info(self.h, v) != 0:
             return None
-        keys = ("unknowns", "eliminated", "levels", "core_rows", "edges", "launches", "ld_core", "core_edges")
+        keys = ("unknowns", "eliminated", "levels", "core_rows", "edges", "launches", "ld_core", "core_edges", "reduce_us", "lu_us", "subst_us")
         return {k: int(x) for k, x in zip(keys, v)}
 
     def stream_info(self, mode: int) -> dict:

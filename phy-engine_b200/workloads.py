@@ -465,8 +465,9 @@ def series_parallel(n_ring: int = 100_000, n_merge: int = 9_000, seed: int = 1, 
     rng = np.random.default_rng(seed)
     nl = Netlist()
     g = nl.ground()
-    r1 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))
-    r2 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))
+    v12 = rng.uniform(1e-5, 1e5, 2)
+    r1 = nl.add(pe.R, float(v12[0]))
+    r2 = nl.add(pe.R, float(v12[1]))
     r4 = nl.add(pe.R, float(rng.uniform(1e-5, 1e5)))  # never connected
     src = nl.add(pe.VDC, v)
     nl.wire(r1, 1, g, 0)
@@ -485,4 +486,4 @@ def series_parallel(n_ring: int = 100_000, n_merge: int = 9_000, seed: int = 1, 
     for a, b in pairs:
         if a != b:
             nl.wire(chain[int(a)], 0, chain[int(b)], 0)
-    return nl, {"V": src, "R1": r1, "R2": r2, "R4": r4, "chain": chain}
+    return nl, {"V": src, "R1": r1, "R2": r2, "R4": r4, "chain": chain, "res": [r1, r2] + chain, "res_values": np.concatenate((v12, vals))}

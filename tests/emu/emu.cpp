@@ -651,6 +651,7 @@ extern "C"
         }
         ++g_launches;
         if(n_launches != nullptr) { *n_launches = 1; }
+        if(f.phase_ms_host != nullptr) { f.phase_ms_host[0] = f.phase_ms_host[1] = f.phase_ms_host[2] = 0.0; }
         return 0;
     }
 

@@ -123,7 +123,61 @@ def case_ac(n_sections, points):
                       "failed": int((b.status() != 0).sum()), "kernel": ri, "parity": parity}), flush=True)
 
 
+def case_series_parallel(n_ring, n_merge, batches):
+    """Config A: benchmark/series_parallel.cpp (seeded clone), DC operating point through the reduce-and-core path, batch =
+    Monte-Carlo draws of every resistance.  Device time per phase from CUDA events inside the library; FP64 figure = the dense
+    LU of the core (2/3 ld^3 flops) over its own device time."""
+    import torch
+
+    nl, info = wl.series_parallel(n_ring, n_merge, seed=1)
+    ref_s, ref_x = None, None
+    try:
+        import refapi
+
+        if os.path.exists(refapi.REF_LIB_FAST) and os.environ.get("PE_CFG_A_NO_REF") is None:
+            r = refapi.RefCircuit(nl, fast=True)
+            r.set_analyze_type(pe.DC)
+            t0 = time.perf_counter()
+            ok, _ = r.analyze_counted()
+            ref_s = time.perf_counter() - t0
+            ref_x = r.solution().real if ok else None
+    except Exception:  # noqa: BLE001
+        pass
+    rng = np.random.default_rng(2)
+    res, res_values = info["res"], info["res_values"]
+    for batch in batches:
+        c = pe.Circuit(nl)
+        c.set_analyze_type(pe.DC)
+        b = c.batch(batch)
+        b.set_stream(torch.cuda.current_stream().cuda_stream)
+        if batch > 1:
+            # instance 0 keeps the netlist's values, the others are fresh draws of every resistance
+            vals = rng.uniform(1e-5, 1e5, (len(res), batch))
+            vals[:, 0] = res_values
+            vals = np.ascontiguousarray(vals)
+            b.set_params(b.param_table([(e, "r") for e in res]), vals.ctypes.data)
+        b.analyze()  # symbolic phase + first solve
+        ms = timed(lambda: b.analyze(), reps=2)
+        fi = b.frontal_info()
+        ld = fi["ld_core"]
+        flops = 2.0 / 3.0 * ld ** 3 * batch
+        parity = "unchecked"
+        if ref_x is not None:
+            x = b.solution()[0]
+            err = np.abs(x - ref_x)
+            parity = "matches reference (1e-9 rel / 1e-12 abs), max rel err %.2e" % float((err / np.maximum(np.abs(ref_x), 1e-300)).max()) if bool(
+                (err <= 1e-12 + 1e-9 * np.maximum(np.abs(x), np.abs(ref_x))).all()) else "MISMATCH max abs err %.3e" % float(err.max())
+        print(json.dumps({"case": f"A series_parallel ring {n_ring} merges {n_merge} DC", "batch": batch, "unknowns": fi["unknowns"], "ms_per_analyze": ms, "solves_per_s": batch / (ms * 1e-3),
+                          "device_ms": {"reduce": fi["reduce_us"] / 1e3, "core_lu": fi["lu_us"] / 1e3, "substitutions": fi["subst_us"] / 1e3}, "plan": fi,
+                          "core_lu_tflops": flops / (fi["lu_us"] * 1e-6) / 1e12 if fi["lu_us"] else None, "fp64_peak_note": "B200 nominal FP64 (tensor) 40 TFLOP/s; no measured FP64 peak on this pool",
+                          "failed": int((b.status() != 0).sum()), "parity": parity,
+                          "cpu_reference": {"seconds": ref_s, "threads": 1, "build": "oracle/_ref/libpe_ref_fast.so (-O3 -march=x86-64-v3)"} if ref_s else None}), flush=True)
+
+
 def main():
+    if os.environ.get("PE_CFG_ONLY_A"):
+        case_series_parallel(int(os.environ.get("PE_CFG_A_RING", "100000")), int(os.environ.get("PE_CFG_A_MERGES", "9000")), [int(v) for v in os.environ.get("PE_CFG_A_BATCH", "1,8").split(",")])
+        return
     # PE_CFG_PATH = "streams,I,J,subtree_warps,workspace,tuning" forces a solve path (phy_engine_b200_set_default_path)
     if os.environ.get("PE_CFG_PATH"):
         abi = pe.bind_full_abi(pe.product())
