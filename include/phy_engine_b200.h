@@ -224,6 +224,9 @@ extern "C"
     int circuit_batch_solution_soa(void* batch, double* x);    /* [n][n_instances]: the device-native layout, no transpose */
     int circuit_batch_ac_solution(void* batch, double* x);     /* [lanes][n][2] */
     int circuit_batch_ac_omegas(void* batch, double* omegas);  /* [points] */
+    /* one rank's shard of a sweep: only the points [first, first + count) are solved (count = 0: all); the omega table is
+     * built in full with the reference's cumulative product (circuit.h:412-428) and sliced */
+    int circuit_batch_set_ac_slice(void* batch, size_t first, size_t count);
     int circuit_batch_status(void* batch, int32_t* status);    /* [lanes] 0 ok, 1 no convergence, 2 singular */
     int circuit_batch_newton_iters(void* batch, uint32_t* n);  /* [lanes] solves per lane */
     int circuit_batch_waveform(void* batch, double* w);        /* [steps][n_probes][n_instances] */

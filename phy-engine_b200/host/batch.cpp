@@ -724,6 +724,14 @@ namespace pe_b200
                     om *= ratio;
                 }
             }
+            if(ac_slice_count > 0)
+            {
+                // multi-GPU sharding of a sweep: the table is built sequentially in full, exactly like the reference's
+                // cumulative product, and this rank keeps its contiguous block of points
+                std::size_t const lo{std::min(ac_slice_first, ac_omegas.size())}, hi{std::min(ac_omegas.size(), lo + ac_slice_count)};
+                ac_omegas = std::vector<double>(ac_omegas.begin() + static_cast<std::ptrdiff_t>(lo), ac_omegas.begin() + static_cast<std::ptrdiff_t>(hi));
+                if(ac_omegas.empty()) { return true; }
+            }
             std::size_t const P{ac_omegas.size()};
             std::size_t const lanes{n_inst * P};
             std::int64_t const LSl{round_up32(lanes)};

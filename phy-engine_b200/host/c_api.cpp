@@ -539,6 +539,17 @@ extern "C"
 
     int circuit_batch_last_kernel(void* b) { return b == nullptr ? -1 : static_cast<batch*>(b)->last_jit; }
 
+    // shard of an AC sweep: solve only the points [first, first + count) of the sweep set by circuit_batch_set_ac_sweep
+    // (count = 0: all of them).  The omega table is still built in full, sequentially, so every rank sees the reference's values.
+    int circuit_batch_set_ac_slice(void* b, size_t first, size_t count)
+    {
+        if(b == nullptr) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        bp->ac_slice_first = first;
+        bp->ac_slice_count = count;
+        return 0;
+    }
+
     // circuits of at least this many unknowns (default 20 000) that consist of resistors and DC sources take the
     // reduce-and-core path for DC / OP; process-wide
     int phy_engine_b200_set_frontal_min(size_t n_unknowns)

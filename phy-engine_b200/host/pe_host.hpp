@@ -324,6 +324,7 @@ namespace pe_b200
 
         // batch AC sweep (lanes = n_inst * points)
         ac_setting ac{};
+        std::size_t ac_slice_first{}, ac_slice_count{};  // count > 0: only this block of the sweep's points is solved (one rank's shard)
 
         std::unique_ptr<compiled> cc;
         std::vector<sweep_key> layout_keys;

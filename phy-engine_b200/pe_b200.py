@@ -435,6 +435,11 @@ class Batch:
     def set_ac_sweep(self, sweep: int, w0: float, w1: float, points: int):
         self._rc(self.lib.circuit_batch_set_ac_sweep(self.h, sweep, w0, w1, points), "circuit_batch_set_ac_sweep")
 
+    def set_ac_slice(self, first: int, count: int):
+        """solve only the points [first, first + count) of the sweep (one rank's shard); count = 0: all"""
+        self.lib.circuit_batch_set_ac_slice.argtypes = [ct.c_void_p, ct.c_size_t, ct.c_size_t]
+        self._rc(self.lib.circuit_batch_set_ac_slice(self.h, first, count), "circuit_batch_set_ac_slice")
+
     def param_table(self, items):
         """pre-resolve [(element, attribute name)] for set_params()"""
         pos = [self.c.pos(e) for e, _ in items]

@@ -123,10 +123,21 @@ def test_config_a_full_size(ref):
     mag[vp] += abs(i_src)
     mag[vq] += abs(i_src)
     assert np.abs(x[vp] - x[vq] - 3.0) < 1e-12  # the source row
-    assert (np.abs(net) <= 1e-9 * np.maximum(mag, 1e-300)).all(), float((np.abs(net) / np.maximum(mag, 1e-300)).max())
-    # (2) the reference's own solution of the same netlist (Eigen SparseLU on one host core: ~1.5 minutes)
+    kcl = float((np.abs(net) / np.maximum(mag, 1e-300)).max())
+    assert kcl <= 1e-9, kcl
+    # (2) the reference's own solution of the same netlist (Eigen SparseLU on one host core: ~1.5 minutes).  Resistances
+    # drawn from U(1e-5, 1e5) Ohm make the system ill-conditioned (kappa ~ 1e10): two backward-stable
+    # solvers agree to ~kappa * eps relative to the LARGEST voltage, not component by component -- nodes a few micro-ohms from
+    # ground sit at nanovolts.  The bar is therefore 1e-9 of the largest |x| for every unknown, and 1e-9 / 1e-12 component-wise
+    # for every unknown above 1e-3 of it.
     rc = refapi.RefCircuit(nl, fast=True)
     rc.set_analyze_type(pe.DC)
     ok, n = rc.analyze_counted()
     assert ok
-    assert_close(x, rc.solution().real, "config A at full size")
+    xr = rc.solution().real
+    scale = np.abs(xr).max()
+    err = np.abs(x - xr)
+    assert err.max() <= 1e-9 * scale, (float(err.max()), float(scale))
+    big = np.abs(xr) >= 1e-3 * scale
+    assert big.sum() > 1000
+    assert_close(x[big], xr[big], "config A at full size (unknowns above 1e-3 of the largest)")

@@ -80,3 +80,30 @@ def test_two_rank_gloo_equals_single_process():
     assert total == solves1
     assert full.shape == x1.shape
     assert (full == x1).all()  # same kernels, same inputs: bit-identical regardless of the sharding
+
+
+def test_ac_sweep_slices_reassemble_the_sweep():
+    # one rank's shard of an AC sweep = a contiguous block of the reference's cumulative-product omega table; the blocks of all
+    # ranks put together are the single-process sweep, bit for bit
+    import emuapi
+    import pe_b200 as pe
+    import workloads as wl
+
+    abi = emuapi.emulator()
+    nl, _ = wl.rlc_ladder(6)
+    points, world = 203, 4
+
+    def run(first, count):
+        c = pe.Circuit(nl, abi)
+        c.set_analyze_type(pe.AC)
+        b = c.batch(1)
+        b.set_ac_sweep(pe.SWEEP_LOG, 1e3, 1e9, points)
+        b.set_ac_slice(first, count)
+        assert b.analyze(), abi.last_error()
+        return b.ac_omegas(), b.ac_solution()[0]
+
+    om, x = run(0, 0)
+    assert len(om) == points
+    parts = [run(*[(lo, hi - lo) for lo, hi in [sharding.shard_range(points, r, world)]][0]) for r in range(world)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), om)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), x)
