@@ -289,7 +289,64 @@ extern "C"
         return static_cast<circuit*>(p)->analyze() ? 0 : 1;
     }
 
-    int circuit_digital_clk(void* p) { return p == nullptr ? 1 : 0; }  // no digital model in scope: nothing to tick
+    // circult::digital_clk() (circuit.h:298-354) for the one digital model in scope, the comparator (comparator.h:73-108): the
+    // state of its output node becomes vA >= vB of the last analog solution.  One instance: evaluated on the host from the
+    // solution analyze() downloaded (the batch path does the same on the device: circuit_batch_digital_clk).  A comparator
+    // whose output sits on an ANALOG node would drive it through an ideal source (digital -> analog, circuit.h:1015-1022):
+    // that driver is not part of this path and the call says so instead of ticking silently.
+    int circuit_digital_clk(void* p)
+    {
+        if(p == nullptr) { return 1; }
+        auto* c{static_cast<circuit*>(p)};
+        c->digital_state.resize(static_cast<std::size_t>(c->nl.n_created_nodes), 2);  // 2 = indeterminate until first driven
+        auto volt = [&](int node) -> double
+        {
+            if(node < 0 || c->x_host.empty()) { return 0.0; }
+            int const u{c->num_host.node_index[static_cast<std::size_t>(node)]};
+            return u >= 0 ? c->x_host[static_cast<std::size_t>(u)] : 0.0;
+        };
+        for(auto const& e: c->nl.elems)
+        {
+            if(e.d->code != E_CMP) { continue; }
+            int const a{e.pin_node[0]}, b{e.pin_node[1]}, o{e.pin_node[2]};
+            if(a == -2 || b == -2 || o == -2) { continue; }  // comparator.h:85: all three pins must be connected
+            if(o >= 0 && !c->num_host.node_index.empty() && c->num_host.node_index[static_cast<std::size_t>(o)] >= 0)
+            {
+                set_last_error("circuit_digital_clk: a comparator output on an analog node (digital -> analog driver) is outside the B200 hot path");
+                return 1;
+            }
+            if(o >= 0) { c->digital_state[static_cast<std::size_t>(o)] = volt(a) >= volt(b) ? 1 : 0; }
+        }
+        return 0;
+    }
+
+    namespace
+    {
+        // digital read-out of circuit_sample*: a pin on a pure digital node reports the node's state (dll_main.cpp:2346-2355)
+        void sample_digital(circuit& c, std::size_t* vec_pos, std::size_t* chunk_pos, std::size_t comp_size, std::size_t const* dg, int mode, void* out)
+        {
+            for(std::size_t i{}; i < comp_size; ++i)
+            {
+                int const ei{elem_of(c, vec_pos[i], chunk_pos[i])};
+                if(ei < 0) { continue; }
+                auto const& e{c.nl.elems[static_cast<std::size_t>(ei)]};
+                for(int j{}; j < e.d->pins; ++j)
+                {
+                    int const node{e.pin_node[j]};
+                    bool const analog{node == -1 || (node >= 0 && !c.num_host.node_index.empty() && c.num_host.node_index[static_cast<std::size_t>(node)] >= 0)};
+                    int st{2};
+                    if(node >= 0 && !analog && static_cast<std::size_t>(node) < c.digital_state.size()) { st = c.digital_state[static_cast<std::size_t>(node)]; }
+                    std::size_t const k{static_cast<std::size_t>(j) + dg[i]};
+                    if(mode == 0) { static_cast<bool*>(out)[k] = !analog && st == 1; }
+                    else if(mode == 1) { static_cast<std::uint8_t*>(out)[k] = (!analog && st == 1) ? 1 : 0; }
+                    else
+                    {
+                        static_cast<std::uint8_t*>(out)[k] = static_cast<std::uint8_t>(analog ? 2 : st);  // analog pins report X (dll_api.h:224-226)
+                    }
+                }
+            }
+        }
+    }  // namespace
 
     int circuit_sample_layout(void* p, size_t* vec_pos, size_t* chunk_pos, size_t comp_size, size_t* vo, size_t* co, size_t* dg)
     {
@@ -317,6 +374,7 @@ extern "C"
         }
         if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
         for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = false; }
+        sample_digital(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, dg, 0, digital);
         return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
     }
 
@@ -329,6 +387,7 @@ extern "C"
         }
         if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
         for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = 0; }
+        sample_digital(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, dg, 1, digital);
         return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
     }
 
@@ -350,6 +409,7 @@ extern "C"
         }
         if(circuit_sample_layout(p, vec_pos, chunk_pos, comp_size, vo, co, dg) != 0) { return 1; }
         for(std::size_t i{}; i < dg[comp_size]; ++i) { digital[i] = 2; }  // analog pins report X (dll_api.h:224-226)
+        sample_digital(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, dg, 2, digital);
         return sample_impl(*static_cast<circuit*>(p), vec_pos, chunk_pos, comp_size, voltage, vo, current, co);
     }
 

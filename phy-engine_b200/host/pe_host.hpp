@@ -417,6 +417,7 @@ namespace pe_b200
         std::vector<double> x_host;    // last solution (re) of the solo batch, unknown order
         std::vector<double> xi_host;   // imaginary parts (AC)
         numbering num_host;
+        std::vector<std::int8_t> digital_state;  // per created node: 0 / 1 after circuit_digital_clk drove it, 2 = indeterminate
 
         bool analyze();
     };

@@ -96,3 +96,44 @@ def test_flash_adc_full_size_4096_instances():
     expect = (vin[:, None] >= 5.0 * np.arange(1, 16)[None, :] / 16.0).astype(np.uint8)
     safe = np.abs(vin[:, None] - 5.0 * np.arange(1, 16)[None, :] / 16.0).min(axis=1) > 1e-9
     assert (bits[safe] == expect[safe]).all()
+
+
+def product_comparator_bits(abi, nl, info, vin, r_vals, which="state"):
+    """the same reference sequence -- circuit_analyze, circuit_digital_clk, circuit_sample_* -- on the product's Part-1 ABI"""
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.DC)
+    assert c.set_param(info["Vin"], "V", float(vin)) == 0
+    for e, v in zip(info["R"], r_vals):
+        assert c.set_param(e, "r", float(v)) == 0
+    SZ, PSZ, PD = ct.c_size_t, ct.POINTER(ct.c_size_t), ct.POINTER(ct.c_double)
+    lib = c.abi.lib
+    lib.circuit_digital_clk.argtypes = [ct.c_void_p]
+    n = c.comp_size
+    vo, co, dg = (SZ * (n + 1))(), (SZ * (n + 1))(), (SZ * (n + 1))()
+    volt, cur, dig = (ct.c_double * 256)(), (ct.c_double * 64)(), (ct.c_uint8 * 256)()
+    fn = lib.circuit_sample_digital_state_u8 if which == "state" else lib.circuit_sample_u8
+    fn.argtypes = [ct.c_void_p, PSZ, PSZ, SZ, PD, PSZ, PD, PSZ, ct.POINTER(ct.c_uint8), PSZ]
+    before = None
+    if which == "state":
+        assert fn(c.h, c._vp, c._cp, n, volt, vo, cur, co, dig, dg) == 0
+        before = [int(dig[dg[nl.component_index(cm)] + 2]) for cm in info["CMP"]]
+    assert c.analyze(), c.abi.last_error()
+    assert lib.circuit_digital_clk(c.h) == 0
+    assert fn(c.h, c._vp, c._cp, n, volt, vo, cur, co, dig, dg) == 0
+    bits = np.array([int(dig[dg[nl.component_index(cm)] + 2]) for cm in info["CMP"]], dtype=np.uint8)
+    pins_ab = [int(dig[dg[nl.component_index(cm)] + j]) for cm in info["CMP"] for j in (0, 1)]
+    return bits, before, pins_ab
+
+
+def test_single_instance_digital_clk_follows_the_reference_sequence(ref, abi):
+    # ADVICE r01: the Part-1 ABI accepted comparators but circuit_digital_clk was a no-op and the samples always read 0 / X
+    nl, info = wl.flash_adc(16)
+    r_nom = [1e3] * len(info["R"])
+    for vin in (0.0, 0.31, 1.7, 2.5000001, 4.99, 5.0):
+        want = reference_comparator_bits(nl, info, vin, r_nom)
+        got, before, pins_ab = product_comparator_bits(abi, nl, info, vin, r_nom, "state")
+        assert (got == want).all(), (vin, got, want)
+        assert all(v == 2 for v in before)  # indeterminate until the first tick
+        assert all(v == 2 for v in pins_ab)  # analog pins report X (dll_api.h:224-226)
+        got8, _, pins8 = product_comparator_bits(abi, nl, info, vin, r_nom, "u8")
+        assert (got8 == want).all() and not any(pins8)
