@@ -153,3 +153,25 @@ def test_stream_with_inductors_falls_back(ref, abi):  # noqa: F811
     assert b.analyze(), c.abi.last_error()
     assert b.last_kernel() != 2
     assert_close(b.solution()[0], rc.solution().real, "RLC transient next to the stream request")
+
+
+def test_build_flags_reach_the_compiler(tmp_path):
+    # the stream module is compiled at run time with the lane-group geometry as -D flags; a flag that silently does not arrive
+    # gives a kernel built for another row width (this happened once: an "illegal memory access" in a kernel that was fine)
+    import os
+    import shutil
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    lib = pe.product().lib
+    lib.pe_b200_stream_build.argtypes = [ct.c_char_p, ct.c_char_p, ct.c_char_p, ct.c_int, ct.c_int, ct.c_char_p, ct.c_size_t]
+    src = tmp_path / "probe.inc"
+    src.write_text("#define PE_STREAM_TILES 0u\n#define PE_STREAM_STAGE_ROWS 1u\n"
+                   "static_assert(PE_SGL == 16 && PE_SJ == 1, \"build flags did not reach the compiler\");\n"
+                   "__device__ __forceinline__ void pe_stream_iter(sk_ctx& k, uint32_t& fm) { (void)k; (void)fm; }\n")
+    csrc = os.path.join(os.path.dirname(os.path.abspath(pe.__file__)), "csrc").encode()
+    log = ct.create_string_buffer(4096)
+    assert lib.pe_b200_stream_build(str(src).encode(), str(tmp_path / "ok.cubin").encode(), csrc, 1, 16, log, 4096) == 0, log.value.decode()
+    assert os.path.getsize(tmp_path / "ok.cubin") > 0
+    assert lib.pe_b200_stream_build(str(src).encode(), str(tmp_path / "bad.cubin").encode(), csrc, 1, 32, log, 4096) != 0
+    assert b"build flags did not reach the compiler" in log.value
