@@ -177,6 +177,15 @@ extern "C"
      * forbids it; circuit_batch_last_kernel reports 2).  info[6] = last kernel, warps per CTA, ring stages, shared memory
      * per CTA (bytes), tiles per solve, rows per ring stage */
     int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
+    /* pivot safety net.  The elimination order is static (chosen on the first instance's values; the reference re-pivots in
+     * every solve, Eigen SparseLU_pivotL.h:76-107).  Pivots that are not provably safe are tested on the device: a lane whose
+     * pivot is smaller than `guard` times the largest term that went into it is flagged, and analyze() solves the flagged
+     * instances again in a sub-batch whose order is chosen on THEIR values; what still fails goes to the next of `rounds`
+     * rounds, the last of which runs unguarded.  guard: 0 = off, < 0 = default (2^-30); rounds < 0 = default (3).
+     * info[6] = guarded pivots of the program, instances flagged, instances solved by a re-ordered sub-batch, instances that
+     * took the unguarded round, sub-batch runs, live sub-batches */
+    int circuit_batch_set_pivot_guard(void* batch, double guard, int rounds);
+    int circuit_batch_rescue_info(void* batch, int mode, int64_t* info);
     /* reduce-and-core path: DC / OP of one huge linear circuit (resistors, DC sources; >= 20 000 unknowns, config A of
      * BASELINE.json) per instance: level-scheduled elimination of the degree <= 2 nodes, dense LU of the rest on the FP64
      * tensor cores (circuit_batch_last_kernel reports 3).  info[11] = unknowns, eliminated nodes, levels, core rows, edges

@@ -56,7 +56,7 @@ namespace
         c.wx = r.wx + (real_lane ? lane / r.ppi : 0);
         c.LSu = r.LSu;
         c.LSx = r.LSx;
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
 
         if(threadIdx.x < 96) { (&s_flags[0][0])[threadIdx.x] = 0u; }
         __syncthreads();
@@ -239,7 +239,7 @@ namespace
         c.C = 32u / IG;
         c.col = (tid & 31u) / IG;
         c.stream = stream;
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
 
         bool real_lane[J], counted[J], ok[J];
         int32_t status[J];
@@ -603,6 +603,21 @@ namespace
                 acc[j] = fma(a, bv[i][j], acc[j]);
             }
         }
+        if(flags & PE_F_GUARD)
+        {
+            // pivot guard (pe_b200_program.h PE_F_GUARD): the largest magnitude that went into the pivot against what is left
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                double s = 0.0;
+#pragma unroll
+                for(int i = 0; i < 2 * NA; ++i) { s = fma(sv[i][j], __hiloint2double((int)(0x3ff00000u | (g[i] & 0x80000000u)), 0), s); }
+                double m = 0.0;
+#pragma unroll
+                for(int i = 0; i < NB; ++i) { m = fmax(m, fabs(av[i][j] * bv[i][j])); }
+                if(PE_GUARD_TRIP(fabs(acc[j]), fabs(s), m, r.guard)) { fail[j] = true; }
+            }
+        }
         if(flags & PE_F_SCALE)
         {
 #pragma unroll
@@ -646,7 +661,7 @@ namespace
     // fused elimination step (PE_OP_CROUT2): six DOT slots [pivot | U entries, L entries, rhs entry]; all 26 operand
     // rows of the step are requested before the first is used, the pivot reciprocal stays in a register
     template <int J>
-    __device__ __forceinline__ void tree_crout2(line_reader const& rd, lane_ws const& at, bool const (&en)[J], bool (&fail)[J])
+    __device__ __forceinline__ void tree_crout2(line_reader const& rd, lane_ws const& at, double guard, bool const (&en)[J], bool (&fail)[J])
     {
         // words: [h][mask] then slot 0: [ctl][src][src][pair], slots 1..5: [ctl][src][pair]
         uint32_t gs[14], gp[6];
@@ -708,6 +723,7 @@ namespace
             for(int j = 0; j < J; ++j)
             {
                 double const a = __hiloint2double(__double2hiint(pa[q][j]) ^ (int)(0x80000000u ^ gp[q]), __double2loint(pa[q][j]));
+                if((flags & PE_F_GUARD) && PE_GUARD_TRIP(fabs(fma(a, pb[q][j], acc[j])), fabs(acc[j]), fabs(a * pb[q][j]), guard)) { fail[j] = true; }
                 acc[j] = fma(a, pb[q][j], acc[j]);
             }
             if(flags & PE_F_SCALE)
@@ -818,6 +834,29 @@ namespace
         {
             if(acc.v[j] == 0.0 || !isfinite(acc.v[j])) { failm |= 1u << j; }
             acc.v[j] = PE_RCP(acc.v[j]);
+        }
+    }
+    // pivot guard (pe_b200_program.h PE_F_GUARD): gs = |sum of the stamps|, gp = largest |l * u| that went into the pivot
+    __device__ __forceinline__ void jgabs(jv& gs, jv& gp, jv const& acc)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+            gs.v[j] = fabs(acc.v[j]);
+            gp.v[j] = 0.0;
+        }
+    }
+    __device__ __forceinline__ void jgmax(jv& gp, jv const& a, jv const& b)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
+    }
+    __device__ __forceinline__ void jguard(jv const& acc, jv const& gs, jv const& gp, double const guard, uint32_t& failm)
+    {
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+        {
+            if(PE_GUARD_TRIP(fabs(acc.v[j]), gs.v[j], gp.v[j], guard)) { failm |= 1u << j; }
         }
     }
     // CAP_STEP (capacitor.h:106-128): hist, prev_g updated in place
@@ -982,7 +1021,7 @@ namespace
 #ifdef PE_JIT
                 if(sec == 2)
                 {
-                    pe_jit_iter<CL>(warp, at.wl, en, fail);
+                    pe_jit_iter<CL>(warp, at.wl, r.guard, en, fail);
                     group_sync<CL>();
                 }
                 else
@@ -1024,7 +1063,7 @@ namespace
                         {
                             if(op == PE_OP_CROUT2)
                             {
-                                tree_crout2<J>(rd, at, en, fail);
+                                tree_crout2<J>(rd, at, r.guard, en, fail);
                                 rd.adv(21u);
                                 continue;
                             }
@@ -1081,7 +1120,7 @@ namespace
                         c.col = 0;
                         c.stream = warp;
                         c.js = 32;
-                        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+                        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
                         int const k = rvop<J, line_reader, false>(rd, c, t, tol, en, check, nconv, fail, it == 0);
                         if(k == V_END || k == V_BAD) { break; }
                         if(k == V_BAR)

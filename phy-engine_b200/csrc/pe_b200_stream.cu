@@ -57,6 +57,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     k.fenced = -1;
     k.lane = lane;
     k.n_rows = (uint32_t)r.n_slots;
+    k.guard = r.guard;
     if(lane == 0u)
     {
         for(uint32_t s = 0; s < NS; ++s) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k.bars + 8u * s), "r"(1u) : "memory"); }
@@ -65,7 +66,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     __syncwarp();
 
     uint32_t const NG = (uint32_t)((r.n_lanes + GL - 1) / GL);
-    tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+    tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
     for(uint32_t group = blockIdx.x + gridDim.x * warp; group < NG; group += gridDim.x * n_warps)
     {
         int64_t const glane = (int64_t)group * GL + gl_lane;  // first of this thread's lanes; the others are + SGL j

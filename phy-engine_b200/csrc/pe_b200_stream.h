@@ -81,6 +81,26 @@ namespace pe_stream
             acc.v[j] = PE_RCP(acc.v[j]);
         }
     }
+    // pivot guard (pe_b200_program.h PE_F_GUARD): gs = |sum of the stamps|, gp = largest |l * u| that went into the pivot
+    PE_SK_FN void jgabs(jv& gs, jv& gp, jv const& acc)
+    {
+        for(int j = 0; j < PE_SJ; ++j)
+        {
+            gs.v[j] = fabs(acc.v[j]);
+            gp.v[j] = 0.0;
+        }
+    }
+    PE_SK_FN void jgmax(jv& gp, jv const& a, jv const& b)
+    {
+        for(int j = 0; j < PE_SJ; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
+    }
+    PE_SK_FN void jguard(jv const& acc, jv const& gs, jv const& gp, double const guard, uint32_t& failm)
+    {
+        for(int j = 0; j < PE_SJ; ++j)
+        {
+            if(PE_GUARD_TRIP(fabs(acc.v[j]), gs.v[j], gp.v[j], guard)) { failm |= 1u << j; }
+        }
+    }
     // CAP_STEP (capacitor.h:106-128): hist, prev_g updated in place
     PE_SK_FN void jcap(jv const& C, jv const& dt, jv const& va, jv const& vb, jv& hist, jv& prev_g)
     {
@@ -164,6 +184,7 @@ namespace pe_stream
         uint32_t lane;
         uint32_t enm;       // store mask of this thread's J lanes
         uint32_t n_rows;    // rows of the group's workspace block (bounds checks of debug builds, -DPE_SK_DEBUG)
+        double guard;       // PE_F_GUARD threshold (pe_b200_program.h)
     };
 
 #ifdef PE_SK_DEBUG
@@ -255,6 +276,7 @@ namespace pe_stream
         int32_t fenced;
         uint32_t lane;
         uint32_t enm;
+        double guard;
         // checks
         uint32_t n_rows;
         uint64_t* store_seq;   // [n_rows]: sequence number of the last store to the row

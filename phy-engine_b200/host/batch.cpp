@@ -81,7 +81,7 @@ namespace pe_b200
         if(want_stream) { r_real = 1; }
         stream_mode = want_stream;  // decides where a one-stream program keeps its workspace (use_hbm)
         bool const need{layout_change || cc_param_rev != parent->param_rev || cc_dt != parent->tr.t_step || w_real != cc_warps_real || w_ac != cc_warps_ac ||
-                        r_real != cc_res_real || r_ac != cc_res_ac || res_fuse != cc_fuse};
+                        r_real != cc_res_real || r_ac != cc_res_ac || res_fuse != cc_fuse || guard_all != cc_guard_all};
         if(!need) { return true; }
         layout_keys = keys;
 
@@ -91,7 +91,10 @@ namespace pe_b200
         in.dt = parent->tr.t_step;
         auto const& a{ac.points > 0 || ac.omega != 0.0 || ac.omega_start != 0.0 ? ac : parent->ac};
         in.omega0 = (a.sweep == sweep_type::single || a.points <= 1) ? a.omega : std::sqrt(std::fabs(a.omega_start * a.omega_stop));
+        if(omega0_override > 0.0) { in.omega0 = omega0_override; }
         if(!(in.omega0 > 0.0)) { in.omega0 = 1.0; }
+        in.guard_all = guard_all;
+        in.nl_nominal = nl_nominal;
         for(auto const& [k, v]: sweeps) { in.swept_lane0[k] = v.empty() ? 0.0 : v[0]; }
         in.warps_real = w_real;
         in.warps_ac = w_ac;
@@ -100,6 +103,12 @@ namespace pe_b200
         cc_res_real = r_real;
         cc_res_ac = r_ac;
         cc_fuse = res_fuse;
+        cc_guard_all = guard_all;
+        for(auto const& e: parent->nl.elems)
+        {
+            // guard elision (compiler.cpp) rests on positive R / C values
+            if(e.d != nullptr && (e.d->code == E_RES || e.d->code == E_CAP) && !(e.attr[0] > 0.0)) { in.guard_all = true; }
+        }
         for(int attempt{}; attempt < 3; ++attempt)
         {
             in.resident_real = r_real;
@@ -416,6 +425,7 @@ namespace pe_b200
         r.dt = dt;
         auto const& env{parent->env};
         // default tolerances of circult::solve() (circuit.h:900-903)
+        r.guard = pivot_guard;
         r.v_abstol = env.V_eps_max > 0.0 ? env.V_eps_max : 1e-6;
         r.v_reltol = env.V_epsr_max > 0.0 ? env.V_epsr_max : 1e-3;
         r.i_abstol = env.I_eps_max > 0.0 ? env.I_eps_max : 1e-12;
@@ -549,6 +559,7 @@ namespace pe_b200
         r.t0 = t0;
         r.dt = dt;
         auto const& env{parent->env};
+        r.guard = pivot_guard;
         r.v_abstol = env.V_eps_max > 0.0 ? env.V_eps_max : 1e-6;
         r.v_reltol = env.V_epsr_max > 0.0 ? env.V_epsr_max : 1e-3;
         r.i_abstol = env.I_eps_max > 0.0 ? env.I_eps_max : 1e-12;
@@ -640,15 +651,11 @@ namespace pe_b200
         return true;
     }
 
-    bool batch::analyze()
+    // one analyze() of this batch's own program; st / sv = per-lane status and solve counters (empty when nothing was launched)
+    bool batch::analyze_main(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv)
     {
-        error.clear();
-        if(parent == nullptr || n_inst == 0)
-        {
-            error = "empty batch";
-            set_last_error(error);
-            return false;
-        }
+        st.clear();
+        sv.clear();
         last_points_hint = 1;
         // one huge linear DC circuit (config A): the parallelism is in the elimination DAG, not in static per-lane programs
         if(frontal_applicable(*parent, static_cast<std::size_t>(make_numbering(parent->nl).unknowns())))
@@ -828,20 +835,199 @@ namespace pe_b200
         if(!ok) { return false; }
 
         // one host sync per analyze(): status + solve counters
-        std::vector<std::int32_t> st(last_lanes);
-        std::vector<std::uint32_t> sv(last_lanes);
+        st.assign(last_lanes, 0);
+        sv.assign(last_lanes, 0);
         if(pe_b200_dev_d2h(st.data(), d_status.p, last_lanes * 4, stream) != 0 || pe_b200_dev_d2h(sv.data(), d_solves.p, last_lanes * 4, stream) != 0 ||
            pe_b200_dev_sync(stream) != 0)
         {
+            st.clear();
+            sv.clear();
             return dev_fail(error, "download status");
         }
         total_solves = op_solves;
+        return true;
+    }
+
+    // The pivot safety net (pe_host.hpp): lanes the guard flagged are solved again in sub-batches ordered on their own values.
+    bool batch::run_rescues(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv, bool fresh_state)
+    {
+        std::size_t const P{st.size() / n_inst};  // lanes per instance (points of an AC sweep, else 1)
+        if(P == 0 || P * n_inst != st.size()) { return true; }
+        std::vector<char> taken(n_inst, 0);
+        auto merge = [&](rescue_set const& rs)
+        {
+            auto const& sb{*rs.b};
+            if(sb.last_status.size() != rs.inst.size() * P) { return; }
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                if(!rs.owned[k]) { continue; }
+                taken[rs.inst[k]] = 1;
+                for(std::size_t p{}; p < P; ++p)
+                {
+                    st[rs.inst[k] * P + p] = sb.last_status[k * P + p];
+                    sv[rs.inst[k] * P + p] = sb.last_solves[k * P + p];
+                }
+            }
+        };
+        // lanes that moved to a sub-batch in an earlier call continue there (a transient keeps its state in the sub-batch)
+        for(auto& rs: rescues)
+        {
+            rs.b->stream = stream;
+            (void)rs.b->analyze();
+            ++stat_rescue_launches;
+            if(rs.b->last_status.empty())
+            {
+                error = "rescue batch: " + rs.b->error;
+                set_last_error(error);
+                return false;
+            }
+            merge(rs);
+        }
+        std::vector<std::size_t> F;
+        std::size_t first_lane{};
+        for(std::size_t i{}; i < n_inst; ++i)
+        {
+            if(taken[i]) { continue; }
+            for(std::size_t p{}; p < P; ++p)
+            {
+                if(st[i * P + p] == PE_ST_SINGULAR)
+                {
+                    if(F.empty()) { first_lane = i * P + p; }
+                    F.push_back(i);
+                    break;
+                }
+            }
+        }
+        if(F.empty()) { return true; }
+        stat_guard_trips += F.size();
+        auto const at{parent->at};
+        if((at == analyze_type::TR || at == analyze_type::TROP) && !fresh_state) { return true; }  // the state the transient continues from is gone
+        bool const nonlin{parent->nl.has_nonlinear()};
+        static double const nl_table[3]{1.0, 1e-3, 1e-6};
+        for(int round{1}; round <= rescue_rounds && !F.empty(); ++round)
+        {
+            bool const last{round == rescue_rounds};
+            rescue_set rs;
+            rs.inst = F;
+            rs.b = std::make_unique<batch>();
+            auto& sb{*rs.b};
+            sb.parent = parent;
+            sb.n_inst = F.size();
+            sb.device = device;
+            sb.stream = stream;
+            sb.is_rescue = true;
+            sb.pivot_guard = last ? 0.0 : pivot_guard;
+            sb.guard_all = guard_all;
+            sb.nl_nominal = (nonlin && !last) ? nl_table[(round - 1) % 3] : nl_nominal;
+            sb.ac = ac;
+            sb.ac_slice_first = ac_slice_first;
+            sb.ac_slice_count = ac_slice_count;
+            sb.probes = probes;
+            if(last_cplx && !ac_omegas.empty()) { sb.omega0_override = std::fabs(ac_omegas[first_lane % P]); }
+            for(auto const& [key, v]: sweeps)
+            {
+                auto& dst{sb.sweeps[key]};
+                dst.resize(F.size());
+                if(v.size() >= n_inst)
+                {
+                    for(std::size_t k{}; k < F.size(); ++k) { dst[k] = v[F[k]]; }
+                    continue;
+                }
+                // the row lives on the device only (circuit_batch_set_params fast path)
+                auto const it{cc->swept_slot.find(key)};
+                if(it == cc->swept_slot.end())
+                {
+                    std::fill(dst.begin(), dst.end(), v.empty() ? 0.0 : v[0]);
+                    continue;
+                }
+                std::vector<double> row(n_inst);
+                if(pe_b200_dev_d2h(row.data(), static_cast<double const*>(d_wi.p) + static_cast<std::int64_t>(it->second) * LSi, n_inst * sizeof(double), stream) != 0 ||
+                   pe_b200_dev_sync(stream) != 0)
+                {
+                    return dev_fail(error, "download parameter row");
+                }
+                for(std::size_t k{}; k < F.size(); ++k) { dst[k] = row[F[k]]; }
+            }
+            (void)sb.analyze();
+            ++stat_rescue_launches;
+            if(sb.last_status.size() != F.size() * P)
+            {
+                error = "rescue batch: " + sb.error;
+                set_last_error(error);
+                return false;
+            }
+            rs.owned.assign(F.size(), 0);
+            std::vector<std::size_t> next;
+            for(std::size_t k{}; k < F.size(); ++k)
+            {
+                bool bad{false};
+                for(std::size_t p{}; p < P; ++p) { bad = bad || sb.last_status[k * P + p] == PE_ST_SINGULAR; }
+                if(last || !bad)
+                {
+                    rs.owned[k] = 1;
+                    ++(last ? stat_unguarded : stat_rescued);
+                }
+                else
+                {
+                    if(next.empty())
+                    {
+                        for(std::size_t p{}; p < P; ++p)
+                        {
+                            if(sb.last_status[k * P + p] == PE_ST_SINGULAR)
+                            {
+                                first_lane = F[k] * P + p;
+                                break;
+                            }
+                        }
+                    }
+                    next.push_back(F[k]);
+                }
+            }
+            merge(rs);
+            rescues.push_back(std::move(rs));
+            F = std::move(next);
+        }
+        rescues_sweeps_rev = sweeps_rev;
+        rescues_param_rev = parent->param_rev;
+        rescues_structure_rev = parent->structure_rev;
+        return true;
+    }
+
+    bool batch::analyze()
+    {
+        error.clear();
+        if(parent == nullptr || n_inst == 0)
+        {
+            error = "empty batch";
+            set_last_error(error);
+            return false;
+        }
+        // sub-batches of an earlier call own their lanes as long as nothing they were built from has changed
+        if(!rescues.empty() && (rescues_sweeps_rev != sweeps_rev || rescues_param_rev != parent->param_rev || rescues_structure_rev != parent->structure_rev)) { rescues.clear(); }
+        bool const fresh_state{tr_duration == 0.0};
+        std::vector<std::int32_t> st;
+        std::vector<std::uint32_t> sv;
+        bool const launched{analyze_main(st, sv)};
+        if(!launched && st.empty())
+        {
+            last_status.clear();
+            return false;
+        }
+        if(frontal || st.empty())
+        {
+            last_status = st;
+            last_solves = sv;
+            return launched;
+        }
+        if(!is_rescue && pivot_guard > 0.0 && !run_rescues(st, sv, fresh_state)) { return false; }
         bool all_ok{true};
-        for(std::size_t i{}; i < last_lanes; ++i)
+        for(std::size_t i{}; i < st.size(); ++i)
         {
             total_solves += sv[i];
             if(st[i] != PE_ST_OK) { all_ok = false; }
         }
+        last_status = st;
+        last_solves = sv;
         if(!all_ok)
         {
             error = "analyze: at least one lane failed (no convergence or singular matrix)";
@@ -853,6 +1039,11 @@ namespace pe_b200
     bool batch::get_status(std::int32_t* st)
     {
         if(last_lanes == 0) { return false; }
+        if(last_status.size() == last_lanes)
+        {
+            std::copy(last_status.begin(), last_status.end(), st);  // merged with the rescue sub-batches by analyze()
+            return true;
+        }
         if(pe_b200_dev_d2h(st, d_status.p, last_lanes * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download status"); }
         return true;
     }
@@ -860,6 +1051,11 @@ namespace pe_b200
     bool batch::get_solves(std::uint32_t* sv)
     {
         if(last_lanes == 0) { return false; }
+        if(last_solves.size() == last_lanes)
+        {
+            std::copy(last_solves.begin(), last_solves.end(), sv);
+            return true;
+        }
         if(pe_b200_dev_d2h(sv, d_solves.p, last_lanes * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download solves"); }
         return true;
     }
@@ -880,6 +1076,16 @@ namespace pe_b200
         {
             for(std::size_t i{}; i < n_inst; ++i) { x[i * n + j] = tmp[j * n_inst + i]; }
         }
+        // rows of the lanes a rescue sub-batch owns (pivot safety net)
+        for(auto const& rs: rescues)
+        {
+            std::vector<double> sx(rs.inst.size() * n);
+            if(!rs.b->get_solution(sx.data())) { return false; }
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                if(rs.owned[k]) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * n), x + rs.inst[k] * n); }
+            }
+        }
         return true;
     }
 
@@ -893,6 +1099,17 @@ namespace pe_b200
            pe_b200_dev_sync(stream) != 0)
         {
             return dev_fail(error, "download solution");
+        }
+        for(auto const& rs: rescues)
+        {
+            std::size_t const m{rs.inst.size()};
+            std::vector<double> sx(m * n);
+            if(!rs.b->get_solution_soa(sx.data())) { return false; }
+            for(std::size_t k{}; k < m; ++k)
+            {
+                if(!rs.owned[k]) { continue; }
+                for(std::size_t j{}; j < n; ++j) { x[j * n_inst + rs.inst[k]] = sx[j * m + k]; }
+            }
         }
         return true;
     }
@@ -916,6 +1133,17 @@ namespace pe_b200
         for(std::size_t j{}; j < 2 * n; ++j)
         {
             for(std::size_t l{}; l < lanes; ++l) { x[l * 2 * n + j] = tmp[j * lanes + l]; }
+        }
+        std::size_t const P{std::max<std::size_t>(last_points, 1)};
+        for(auto const& rs: rescues)
+        {
+            if(!rs.b->last_cplx || rs.b->last_lanes != rs.inst.size() * P) { continue; }
+            std::vector<double> sx(rs.b->last_lanes * 2 * n);
+            if(!rs.b->get_ac_solution(sx.data())) { return false; }
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                if(rs.owned[k]) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * P * 2 * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * P * 2 * n), x + rs.inst[k] * P * 2 * n); }
+            }
         }
         return true;
     }
@@ -977,6 +1205,18 @@ namespace pe_b200
            pe_b200_dev_sync(stream) != 0)
         {
             return dev_fail(error, "download waveform");
+        }
+        for(auto const& rs: rescues)
+        {
+            std::size_t const m{rs.inst.size()};
+            if(rs.b->wave_steps != wave_steps || rs.b->probes.size() != probes.size()) { continue; }
+            std::vector<double> sw(rows * m);
+            if(!rs.b->get_wave(sw.data())) { continue; }
+            for(std::size_t k{}; k < m; ++k)
+            {
+                if(!rs.owned[k]) { continue; }
+                for(std::size_t q{}; q < rows; ++q) { w[q * n_inst + rs.inst[k]] = sw[q * m + k]; }
+            }
         }
         return true;
     }

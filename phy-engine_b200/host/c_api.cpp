@@ -652,6 +652,32 @@ extern "C"
         return 0;
     }
 
+    // pivot safety net (pe_host.hpp): guard = relative size below which a guarded pivot flags its lane (0 = off, < 0 = default
+    // 2^-30), rounds = re-orderings tried before the last, unguarded one (< 0 = default 3)
+    int circuit_batch_set_pivot_guard(void* b, double guard, int rounds)
+    {
+        if(b == nullptr || guard >= 1.0 || rounds > 16) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        bp->pivot_guard = guard < 0.0 ? PE_GUARD_DEFAULT : guard;
+        bp->rescue_rounds = rounds < 0 ? 3 : std::max(rounds, 1);
+        return 0;
+    }
+
+    // info[6] = guarded pivots of the program of `mode`, instances the guard flagged so far, instances a re-ordered sub-batch
+    // solved, instances that went through the last (unguarded) round, sub-batch analyze() calls, live sub-batches
+    int circuit_batch_rescue_info(void* b, int mode, int64_t* info)
+    {
+        if(b == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
+        auto* bp{static_cast<batch*>(b)};
+        info[0] = bp->cc ? static_cast<std::int64_t>(bp->cc->prog[static_cast<std::size_t>(mode)].n_guarded) : -1;
+        info[1] = static_cast<std::int64_t>(bp->stat_guard_trips);
+        info[2] = static_cast<std::int64_t>(bp->stat_rescued);
+        info[3] = static_cast<std::int64_t>(bp->stat_unguarded);
+        info[4] = static_cast<std::int64_t>(bp->stat_rescue_launches);
+        info[5] = static_cast<std::int64_t>(bp->rescues.size());
+        return 0;
+    }
+
     int circuit_batch_resident_info(void* b, int mode, int64_t* info)
     {
         if(b == nullptr || info == nullptr || mode < 0 || mode >= static_cast<int>(prog_mode::COUNT)) { return 1; }
@@ -712,7 +738,16 @@ extern "C"
         auto& v{b->sweeps[{ei, idx}]};
         v.resize(b->n_inst);
         for(std::size_t i{}; i < b->n_inst; ++i) { v[i] = to_internal(code, idx, values[i]); }
+        if((code == E_RES || code == E_CAP) && idx == 0)
+        {
+            // the compiler leaves the pivot guard off rows that only carry positive conductances (compiler.cpp "guard elision")
+            for(double const x: v)
+            {
+                if(!(x > 0.0)) { b->guard_all = true; }
+            }
+        }
         b->sweeps_dirty = true;
+        ++b->sweeps_rev;
         return 0;
     }
 
@@ -742,6 +777,7 @@ extern "C"
             return 0;
         }
         if(pe_b200_dev_set(b->device) != 0) { return 1; }
+        ++b->sweeps_rev;
         // parameters whose device rows are equally spaced travel as one strided 2-D copy (one DMA descriptor instead of one
         // per 80 KB row: a table of 2000 parameters is a handful of copies)
         std::vector<std::int64_t> slot(n_params);
@@ -815,6 +851,7 @@ extern "C"
         if(bp == nullptr) { return 1; }
         auto* b{static_cast<batch*>(bp)};
         if(!b->ensure_compiled()) { return 1; }
+        b->rescues.clear();  // the sub-batches of the pivot safety net hold state of the transient that is being reset
         // INST layout: x [0,n) | swept parameters [n, n+ns) | device state + derived values
         std::size_t const n{static_cast<std::size_t>(b->cc->num.unknowns())};
         std::size_t const ns{b->cc->swept_slot.size()};

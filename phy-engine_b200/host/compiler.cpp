@@ -167,6 +167,7 @@ namespace pe_b200
                         }
                     }
                 }
+                double const nl_nom{in.nl_nominal > 0.0 ? in.nl_nominal : k_nl_nominal};
                 // device state (always per instance)
                 for(std::size_t ei{}; ei < nl.elems.size(); ++ei)
                 {
@@ -200,7 +201,7 @@ namespace pe_b200
                             break;
                         case E_PN:
                             v.s[0] = inst_slot(0.0);
-                            v.s[1] = inst_slot(k_nl_nominal);
+                            v.s[1] = inst_slot(nl_nom);
                             v.s[2] = inst_slot(0.0);
                             v.s[3] = inst_slot(0.0);
                             v.s[4] = inst_slot(0.0);
@@ -209,7 +210,7 @@ namespace pe_b200
                             for(auto& q: v.bs)
                             {
                                 q[0] = inst_slot(0.0);
-                                q[1] = inst_slot(k_nl_nominal);
+                                q[1] = inst_slot(nl_nom);
                                 q[2] = inst_slot(0.0);
                                 q[3] = inst_slot(0.0);
                                 q[4] = inst_slot(0.0);
@@ -217,15 +218,15 @@ namespace pe_b200
                             break;
                         case E_NPN:
                         case E_PNP:
-                            v.s[0] = inst_slot(k_nl_nominal);
+                            v.s[0] = inst_slot(nl_nom);
                             v.s[1] = inst_slot(0.0);
-                            v.s[2] = inst_slot(k_nl_nominal * std::fabs(v.p[2].nom));
+                            v.s[2] = inst_slot(nl_nom * std::fabs(v.p[2].nom));
                             v.s[3] = inst_slot(0.0);
                             break;
                         case E_NMOS:
                         case E_PMOS:
-                            v.s[0] = inst_slot(k_nl_nominal);
-                            v.s[1] = inst_slot(k_nl_nominal);
+                            v.s[0] = inst_slot(nl_nom);
+                            v.s[1] = inst_slot(nl_nom);
                             v.s[2] = inst_slot(0.0);
                             break;
                         default: break;
@@ -1345,6 +1346,7 @@ namespace pe_b200
             struct lu_step
             {
                 int r, c, piv;
+                bool guard{true};               // the pivot op carries PE_F_GUARD (false: provably safe, see "guard elision")
                 int leaf;                       // v2 schedule: leaf the pivot was taken in (-1 = top)
                 int node;                       // elimination-tree node the pivot was taken in
                 std::vector<int> lrows, l_ent;  // rows i with (i,c), entry ids
@@ -1626,7 +1628,7 @@ namespace pe_b200
                     std::size_t const step_begin{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(ph)].size()};
                     load_sources(rc.orig[static_cast<std::size_t>(st.piv)]);
                     load_updates(st.piv, rc.pairs[static_cast<std::size_t>(st.piv)], st.node, false);
-                    emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
+                    emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP | (st.guard ? PE_F_GUARD : 0u), 0, sre, sim, pp);
                     for(int e: st.u_ent)
                     {
                         load_sources(rc.orig[static_cast<std::size_t>(e)]);
@@ -1665,7 +1667,7 @@ namespace pe_b200
                         {
                             auto const& o{lst[step_begin + q]};
                             fits = o.opcode == PE_OP_DOT && o.sim.empty() && o.pp.size() <= 1 && o.sre.size() <= (q == 0 ? 4u : 2u) &&
-                                   (q == 0 ? o.flags == PE_F_RECIP : (o.flags == 0u || (o.flags == PE_F_SCALE && o.scale == lst[step_begin].dst)));
+                                   (q == 0 ? (o.flags & ~static_cast<std::uint32_t>(PE_F_GUARD)) == PE_F_RECIP : (o.flags == 0u || (o.flags == PE_F_SCALE && o.scale == lst[step_begin].dst)));
                         }
                         if(fits)
                         {
@@ -2500,6 +2502,45 @@ namespace pe_b200
                 pr.structurally_singular = singular;
                 pr.nnz_lu = nv.size();
 
+                // --- guard elision: which pivots need the run-time pivot guard (PE_F_GUARD).  A node row that carries nothing but
+                // two-terminal positive conductances (R, and C's companion in the real-valued modes) is symmetric and diagonally
+                // dominant whatever the per-instance values are, eliminating such a row on its diagonal leaves the rows it updates
+                // that way, and Gaussian elimination without pivoting has growth <= 2 on such a block (Wilkinson): no order can be
+                // better than the static one there, the test would only cost time in the hot loop.  Every other pivot -- branch
+                // rows, rows touched by any other element, rows such a pivot has updated -- keeps the guard.
+                {
+                    std::vector<char> clean(static_cast<std::size_t>(n), 0);
+                    if(!ac && !in.guard_all)
+                    {
+                        for(int i{}; i < num.n_nodes; ++i) { clean[static_cast<std::size_t>(i)] = 1; }
+                        for(auto const& e: nl.elems)
+                        {
+                            if(e.d == nullptr || e.d->code == E_RES || e.d->code == E_CAP) { continue; }
+                            for(int p{}; p < e.d->pins; ++p)
+                            {
+                                int const u{nidx(e.pin_node[p])};
+                                if(u >= 0) { clean[static_cast<std::size_t>(u)] = 0; }
+                            }
+                        }
+                    }
+                    pr.n_guarded = 0;
+                    for(auto& st: steps)
+                    {
+                        bool const safe{st.r == st.c && clean[static_cast<std::size_t>(st.r)] != 0};
+                        st.guard = !safe;
+                        if(st.guard)
+                        {
+                            ++pr.n_guarded;
+                            // the rows it updates are no longer what the elements stamped (a pivot row that holds nothing but
+                            // the pivot -- a grounded voltage source -- updates no matrix entry)
+                            if(!st.ucols.empty())
+                            {
+                                for(int const i: st.lrows) { clean[static_cast<std::size_t>(i)] = 0; }
+                            }
+                        }
+                    }
+                }
+
                 // --- operand translation to the kernel's spaces
                 std::uint32_t const lane0{ac ? 0u : static_cast<std::uint32_t>(out.n_inst_slots)};
                 auto xl = [&](std::uint32_t o) -> std::uint32_t
@@ -2730,7 +2771,7 @@ namespace pe_b200
                     bool const top{st.leaf < 0};
                     load_sources(orig[static_cast<std::size_t>(st.piv)]);
                     load_updates(st.piv, pairs[static_cast<std::size_t>(st.piv)], top, false);
-                    emit_dot(S, uslot_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
+                    emit_dot(S, uslot_e(st.piv), PE_F_RECIP | (st.guard ? PE_F_GUARD : 0u), 0, sre, sim, pp);
                     for(int e: st.u_ent)
                     {
                         load_sources(orig[static_cast<std::size_t>(e)]);

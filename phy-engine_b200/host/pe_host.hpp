@@ -223,6 +223,7 @@ namespace pe_b200
         int omega_slot{-1};                 // U slot holding omega (AC)
         // statistics for the roofline and the schedule
         std::size_t nnz_a{}, nnz_lu{}, n_fma{};
+        std::size_t n_guarded{};  // pivots that carry the run-time guard (PE_F_GUARD)
         std::size_t n_leaf_rows{}, n_top_rows{}, n_leaves{};
         std::size_t n_fused{};    // elimination steps emitted as one fused PE_OP_CROUT2
         std::size_t n_aliased{};  // U entries that are a signed copy of one stamped value and were never materialised
@@ -257,6 +258,8 @@ namespace pe_b200
         int resident_ac{0};    // > 0: ... the AC program
         bool fuse_steps{false};  // resident programs: emit small elimination steps as one fused op
         bool merge_step{true};   // resident programs: fold the per-time-step companion updates into the iter section
+        bool guard_all{false};   // keep the pivot guard on every pivot (a non-positive R / C value was seen: no row is provably safe)
+        double nl_nominal{0.0};  // > 0: conductance a not-yet-evaluated non-linear device enters the ordering with (default 1e-12 S)
     };
 
     // Symbolic phase: numbering, stamp maps, Markowitz/threshold pivot order on nominal values, fill pattern, slot
@@ -380,6 +383,34 @@ namespace pe_b200
         std::size_t wave_steps{};
 
         std::string error;
+
+        // ---- pivot safety net.  The elimination order is static (chosen on lane-0 values); pivots that are not provably safe
+        // carry a run-time guard (PE_F_GUARD, pe_b200_program.h), a lane whose pivot loses more than -log2(pivot_guard) bits to
+        // cancellation is flagged like a singular one, and analyze() re-runs the flagged lanes in a sub-batch whose order is
+        // chosen on THEIR values (lane 0 of the sub-batch = the first flagged lane); what still fails goes to the next round,
+        // the last round runs with the guard off (what the reference does: Eigen re-pivots per solve and has no such test,
+        // SparseLU_pivotL.h:76-107).  The sub-batches stay: they own their lanes until a parameter changes (a transient continues
+        // in them), and the download functions merge their rows in.
+        double pivot_guard{PE_GUARD_DEFAULT};  // 0 = off (no guard, no rescue)
+        int rescue_rounds{3};
+        bool is_rescue{};
+        bool guard_all{}, cc_guard_all{};  // compile with the guard on every pivot (set when a non-positive R / C value is seen)
+        double nl_nominal{};     // > 0: ordering conductance of not-yet-evaluated non-linear devices (rescue rounds vary it)
+        double omega0_override{};  // > 0: omega the AC order is chosen on
+        std::uint64_t sweeps_rev{1};  // bumped by every per-instance parameter write
+        struct rescue_set
+        {
+            std::unique_ptr<batch> b;
+            std::vector<std::size_t> inst;   // sub-batch instance k = instance inst[k] of this batch
+            std::vector<char> owned;         // [k]: its results replace this batch's
+        };
+        std::vector<rescue_set> rescues;
+        std::uint64_t rescues_sweeps_rev{}, rescues_param_rev{}, rescues_structure_rev{};
+        std::uint64_t stat_guard_trips{}, stat_rescued{}, stat_rescue_launches{}, stat_unguarded{};
+        std::vector<std::int32_t> last_status;  // merged status / solve counters of the last analyze()
+        std::vector<std::uint32_t> last_solves;
+        bool analyze_main(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv);
+        bool run_rescues(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv, bool fresh_state);
 
         bool analyze();
         bool compile_host(bool& layout_change);  // symbolic phase only, no device needed

@@ -404,6 +404,17 @@ class Batch:
         keys = ("unknowns", "eliminated", "levels", "core_rows", "edges", "launches", "ld_core", "core_edges", "reduce_us", "lu_us", "subst_us")
         return {k: int(x) for k, x in zip(keys, v)}
 
+    def set_pivot_guard(self, guard: float = -1.0, rounds: int = -1):
+        self.lib.circuit_batch_set_pivot_guard.argtypes = [ct.c_void_p, ct.c_double, ct.c_int]
+        self._rc(self.lib.circuit_batch_set_pivot_guard(self.h, guard, rounds), "circuit_batch_set_pivot_guard")
+
+    def rescue_info(self, mode: int) -> dict:
+        v = (ct.c_int64 * 6)()
+        self.lib.circuit_batch_rescue_info.argtypes = [ct.c_void_p, ct.c_int, ct.POINTER(ct.c_int64)]
+        self._rc(self.lib.circuit_batch_rescue_info(self.h, mode, v), "circuit_batch_rescue_info")
+        keys = ("guarded_pivots", "flagged", "rescued", "unguarded", "sub_runs", "sub_batches")
+        return {k: int(x) for k, x in zip(keys, v)}
+
     def stream_info(self, mode: int) -> dict:
         v = (ct.c_int64 * 6)()
         self._rc(self.lib.circuit_batch_stream_info(self.h, mode, v), "circuit_batch_stream_info")

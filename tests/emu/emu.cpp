@@ -179,7 +179,7 @@ extern "C"
         if(rp == nullptr || rp->n_lanes <= 0) { return 0; }
         pe_b200_run const& r = *rp;
         ++g_launches;
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
         for(int64_t lane = 0; lane < r.n_lanes; ++lane)
         {
             int32_t status = r.status[lane];
@@ -255,7 +255,7 @@ namespace
         using namespace pe_rinterp;
         uint32_t const I = (uint32_t)r.I, IG = I / J, S = (uint32_t)r.S;
         uint32_t const T = S * IG, W = T / 32, C = 32 / IG;
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
         int64_t const n_cta = (r.n_lanes + I - 1) / I;
         bool const hbm = r.wsg != nullptr;
         uint64_t const sstride = hbm ? (uint64_t)r.LSw : (uint64_t)I;  // distance between consecutive slots
@@ -725,7 +725,7 @@ extern "C"
         bool const trace_was = emu_trace::g_on;
         emu_trace::g_on = false;
         uint32_t const GL = (uint32_t)r.I;  // 32 J lanes per group: the workspace is one block per group, ws[group][row][GL]
-        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol};
+        tol_t const tol{r.v_abstol, r.v_reltol, r.i_abstol, r.i_reltol, r.guard};
         static int const ns_log_env = getenv("PE_EMU_STREAM_NS_LOG") ? atoi(getenv("PE_EMU_STREAM_NS_LOG")) : 2;
         for(int64_t lane = 0; lane < ((int64_t)r.n_lanes + GL - 1) / GL * GL; ++lane)
         {
@@ -778,6 +778,7 @@ extern "C"
                 }
             };
             void* const st = f_new((uint32_t)r.n_slots, (uint32_t)ns_log_env);
+            if(auto const f_guard = reinterpret_cast<void (*)(void*, double)>(dlsym(h, "pe_emu_stream_set_guard")); f_guard != nullptr) { f_guard(st, r.guard); }
             double t = r.t0;
             if(r.has_prep)
             {

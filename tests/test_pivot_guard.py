@@ -1,0 +1,147 @@
+"""Pivot safety net (host/batch.cpp run_rescues, PE_F_GUARD in csrc/pe_b200_program.h).
+
+The elimination order is static: chosen once, on the first instance's values.  Eigen's SparseLU, which the reference calls,
+re-pivots in every solve (include/Eigen/src/SparseLU/SparseLU_pivotL.h:76-107), so an instance whose values make a pivot of that
+order vanish is still solved there.  Here such an instance trips the device-side pivot guard and is solved again in a
+sub-batch whose order is chosen on ITS values.  These tests sweep a transformer ratio (the pivot of the nominal order is the
+ratio itself) through tiny values and zero and compare every instance with the compiled reference -- OP, a transient that is
+continued by a second analyze(), an AC sweep -- and check what the guard costs where it is not needed (guard elision).
+"""
+import numpy as np
+import pytest
+
+import pe_b200 as pe
+import refapi
+import workloads as wl
+from test_parity import abi, assert_close  # noqa: F401  (abi is a fixture)
+
+RATIOS = np.array([4.0, 2.0, 1e-3, 1e-9, 1e-14, 0.0, 1e6, 1e12, -3.0, 1e-20, 5.0, 1e18])
+
+
+def batch_of(abi, nl, at, over, n_inst, guard=None, tr=None, ac=None, probes=None):  # noqa: F811
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(at)
+    if tr:
+        c.set_tr(*tr)
+    b = c.batch(n_inst)
+    if ac:
+        b.set_ac_sweep(*ac)
+    if guard is not None:
+        b.set_pivot_guard(guard, -1)
+    for e, name, v in over:
+        b.set_param(e, name, v)
+    if probes is not None:
+        b.set_probes(probes)
+    return c, b
+
+
+def test_ratio_sweep_across_a_vanishing_pivot_op(ref, abi):  # noqa: F811
+    nl, info = wl.transformer_stage()
+    over = [(info["TX"], "n", RATIOS)]
+    want = refapi.run_batch(nl, pe.OP, RATIOS.size, over)
+    assert (want["ok"] == 1).all()  # the reference solves every instance, n = 0 included
+    # without the safety net the static order is silently inaccurate on some instances and singular on one
+    c0, b0 = batch_of(abi, nl, pe.OP, over, RATIOS.size, guard=0.0)
+    assert not b0.analyze()
+    st0 = b0.status()
+    x0 = b0.solution()
+    assert st0[5] == 2 and (np.delete(st0, 5) == 0).all()
+    rel0 = np.abs(x0 - want["x"].real).max(axis=1) / np.abs(want["x"].real).max(axis=1)
+    assert rel0[4] > 1e-6 and rel0[9] > 1.0  # status OK, values wrong: what the guard is for
+    # with it every instance matches the reference
+    c, b = batch_of(abi, nl, pe.OP, over, RATIOS.size)
+    assert b.analyze(), c.abi.last_error()
+    assert (b.status() == 0).all()
+    assert_close(b.solution(), want["x"].real, "ratio sweep, OP")
+    soa = np.zeros((b.n_unknowns(), RATIOS.size))
+    b.solution_soa_into(soa.ctypes.data)
+    assert_close(soa.T, want["x"].real, "ratio sweep, OP (device layout)")
+    info_r = b.rescue_info(0)
+    assert info_r["flagged"] >= 3 and info_r["rescued"] == info_r["flagged"] and info_r["unguarded"] == 0
+    assert (b.newton_iters() == 1).all()
+    # a parameter write drops the sub-batches; the next analyze() builds them again
+    b.set_param(info["R"], "r", np.full(RATIOS.size, 2e3))
+    over2 = over + [(info["R"], "r", np.full(RATIOS.size, 2e3))]
+    want2 = refapi.run_batch(nl, pe.OP, RATIOS.size, over2)
+    assert b.analyze(), c.abi.last_error()
+    assert_close(b.solution(), want2["x"].real, "ratio sweep, OP, after a parameter write")
+
+
+def test_ratio_sweep_transient_continues_in_the_sub_batch(ref, abi):  # noqa: F811
+    nl, info = wl.transformer_stage()
+    ratios = RATIOS[:8]
+    over = [(info["TX"], "n", ratios)]
+    dt, steps = 1e-7, 6
+    c, b = batch_of(abi, nl, pe.TR, over, ratios.size, tr=(dt, dt * (steps - 0.5)), probes=[1, 2, 3])
+    assert b.analyze(), c.abi.last_error()
+    want = refapi.run_batch(nl, pe.TR, ratios.size, over, t_step=dt, t_stop=dt * (steps - 0.5))
+    assert (want["ok"] == 1).all() and (want["solves"] == steps).all()
+    assert_close(b.solution(), want["x"].real, "ratio sweep, TR")
+    assert b.rescue_info(1)["rescued"] >= 2
+    w = b.waveform(steps)  # [steps, probes, n_inst]: rows of the rescued instances come from the sub-batch
+    x = b.solution()
+    for k, u in enumerate([1, 2, 3]):
+        assert np.array_equal(w[steps - 1, k], x[:, u])
+    # second call: the rescued instances continue where THEIR transient stopped; every instance alone (an order of its own,
+    # nothing to rescue) must give the same trajectory
+    assert b.analyze(), c.abi.last_error()
+    x2 = b.solution()
+    for i in (0, 3, 4, 5):
+        ci, bi = batch_of(abi, nl, pe.TR, [(info["TX"], "n", ratios[i:i + 1])], 1, tr=(dt, dt * (steps - 0.5)))
+        assert bi.analyze() and bi.analyze()
+        assert_close(x2[i], bi.solution()[0], f"continued transient of instance {i}")
+    assert b.total_solves == steps * ratios.size  # per call: the rescued instances count the solves of their sub-batch
+
+
+def test_ratio_sweep_ac(ref, abi):  # noqa: F811
+    nl, info = wl.transformer_stage(vac=True)
+    ratios = RATIOS[:8]
+    over = [(info["TX"], "n", ratios)]
+    sweep = (2, 1e3, 1e7, 5)  # log
+    want = refapi.run_batch(nl, pe.AC, ratios.size, over, ac=sweep)
+    assert (want["ok"] == 1).all()
+    c, b = batch_of(abi, nl, pe.AC, over, ratios.size, ac=sweep)
+    assert b.analyze(), c.abi.last_error()
+    got = b.ac_solution()  # [n_inst, points, n] complex
+    assert_close(got.real, want["x"].real, "ratio sweep, AC (re)")
+    assert_close(got.imag, want["x"].imag, "ratio sweep, AC (im)")
+    assert b.rescue_info(3)["rescued"] >= 2
+
+
+def test_guard_elision_and_its_limits(abi):  # noqa: F811
+    # rows that carry only positive conductances need no guard (symmetric, diagonally dominant: growth <= 2 in any order):
+    # of the 102 pivots of a 100-section RC ladder only the source's two keep it -- the hot loop of config B pays nothing
+    nl, info = wl.rc_ladder(100)
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.TR)
+    c.set_tr(1e-8, 3e-8)
+    b = c.batch(5)
+    assert b.analyze(), c.abi.last_error()
+    assert b.rescue_info(1)["guarded_pivots"] == 2
+    # a negative resistance takes the argument away: every pivot is guarded again
+    b.set_param(info["R"][3], "r", np.array([1e3, 1e3, -1e3, 1e3, 1e3]))
+    assert b.analyze(), c.abi.last_error()
+    assert b.rescue_info(1)["guarded_pivots"] == 102
+    # inductors put a branch row next to every node: nothing is provably safe
+    nl2, _ = wl.rlc_ladder(20)
+    c2 = pe.Circuit(nl2, abi)
+    c2.set_analyze_type(pe.TR)
+    c2.set_tr(1e-9, 3e-9)
+    b2 = c2.batch(3)
+    assert b2.analyze(), c2.abi.last_error()
+    r = b2.rescue_info(1)
+    assert r["guarded_pivots"] > 40 and r["flagged"] == 0
+
+
+def test_single_instance_abi_takes_the_same_net(ref, abi):  # noqa: F811
+    # circuit_analyze() (Part 1 of the ABI) runs a batch of one: its order is chosen on its own values, so there is nothing to
+    # re-order, but the guard and the final unguarded round must not change what it returns
+    for n in (4.0, 1e-14, 0.0):
+        nl, info = wl.transformer_stage(n=n)
+        rc = refapi.RefCircuit(nl)
+        rc.set_analyze_type(pe.OP)
+        assert rc.analyze()
+        c = pe.Circuit(nl, abi)
+        c.set_analyze_type(pe.OP)
+        assert c.analyze(), c.abi.last_error()
+        assert_close(c.solution().real, rc.solution().real, f"single instance, n = {n}")
