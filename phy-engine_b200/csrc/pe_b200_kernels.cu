@@ -1254,8 +1254,15 @@ namespace
     std::atomic<uint64_t> g_launches{0};
 
     // optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the roofline line
-    bool g_timing = false;
+    std::atomic<bool> g_timing{false};
+    // launches come from several host threads (one per batch handle / stream / device): the event list is shared
+    std::mutex g_events_mu;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+    void record_events(cudaEvent_t e0, cudaEvent_t e1)
+    {
+        std::lock_guard<std::mutex> lk(g_events_mu);
+        g_events.emplace_back(e0, e1);
+    }
 
     int chk(cudaError_t e, char const* what)
     {
@@ -1341,7 +1348,7 @@ extern "C"
         if(g_timing)
         {
             cudaEventRecord(e1, (cudaStream_t)stream);
-            g_events.emplace_back(e0, e1);
+            record_events(e0, e1);
         }
         g_launches.fetch_add(1);
         return chk(cudaGetLastError(), "pe_b200_solve_kernel launch");
@@ -1515,7 +1522,7 @@ extern "C"
         if(g_timing)
         {
             cudaEventRecord(e1, (cudaStream_t)stream);
-            g_events.emplace_back(e0, e1);
+            record_events(e0, e1);
         }
         if(le != cudaSuccess) { return chk(le, "pe_b200_stream_kernel launch"); }
         if(dbg_sync) { fprintf(stderr, "stream launch: after: %s\n", cudaGetErrorString(cudaStreamSynchronize((cudaStream_t)stream))); }
@@ -1639,7 +1646,7 @@ extern "C"
             if(g_timing)
             {
                 cudaEventRecord(e1, (cudaStream_t)stream);
-                g_events.emplace_back(e0, e1);
+                record_events(e0, e1);
             }
             if(le != cudaSuccess) { return chk(le, "pe_b200_tree_kernel launch"); }
             g_launches.fetch_add(1);
@@ -1659,7 +1666,7 @@ extern "C"
         if(g_timing)
         {
             cudaEventRecord(e1, (cudaStream_t)stream);
-            g_events.emplace_back(e0, e1);
+            record_events(e0, e1);
         }
         g_launches.fetch_add(1);
         return chk(cudaGetLastError(), "pe_b200_resident_kernel launch");
@@ -1680,7 +1687,12 @@ extern "C"
     double pe_b200_timing_collect(void)
     {
         double total = 0.0;
-        for(auto& [a, b]: g_events)
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+        {
+            std::lock_guard<std::mutex> lk(g_events_mu);
+            ev.swap(g_events);
+        }
+        for(auto& [a, b]: ev)
         {
             float ms = 0.f;
             cudaEventSynchronize(b);
@@ -1688,7 +1700,6 @@ extern "C"
             cudaEventDestroy(a);
             cudaEventDestroy(b);
         }
-        g_events.clear();
         return total;
     }
 

@@ -411,6 +411,13 @@ namespace pe_b200
             r.probes = static_cast<std::uint32_t const*>(d_probes.p);
             r.n_probe = static_cast<std::int32_t>(po.size());
             wave_steps = static_cast<std::size_t>(n_steps);
+            wave_pitch = LSl;
+            // rows of lanes that fail and of the steps after a failure are never written: they read as zero, not as whatever
+            // the allocation held
+            if(pe_b200_dev_memset0(d_wave.p, static_cast<std::size_t>(n_steps) * po.size() * static_cast<std::size_t>(LSl) * sizeof(double), stream) != 0)
+            {
+                return dev_fail(error, "zero waveform store");
+            }
         }
         r.LSu = LSl;
         r.LSx = LSi;
@@ -509,6 +516,13 @@ namespace pe_b200
             r.probes = static_cast<std::uint32_t const*>(d_probes.p);
             r.n_probe = static_cast<std::int32_t>(po.size());
             wave_steps = static_cast<std::size_t>(n_steps);
+            wave_pitch = LSl;
+            // rows of lanes that fail and of the steps after a failure are never written: they read as zero, not as whatever
+            // the allocation held
+            if(pe_b200_dev_memset0(d_wave.p, static_cast<std::size_t>(n_steps) * po.size() * static_cast<std::size_t>(LSl) * sizeof(double), stream) != 0)
+            {
+                return dev_fail(error, "zero waveform store");
+            }
         }
         r.LSu = LSl;
         r.LSx = LSi;
@@ -1201,7 +1215,7 @@ namespace pe_b200
     {
         if(probes.empty() || wave_steps == 0 || d_wave.p == nullptr) { return false; }
         std::size_t const rows{wave_steps * probes.size()};
-        if(pe_b200_dev_d2h_2d(w, n_inst * sizeof(double), d_wave.p, static_cast<std::size_t>(last_LSl) * sizeof(double), n_inst * sizeof(double), rows, stream) != 0 ||
+        if(pe_b200_dev_d2h_2d(w, n_inst * sizeof(double), d_wave.p, static_cast<std::size_t>(wave_pitch) * sizeof(double), n_inst * sizeof(double), rows, stream) != 0 ||
            pe_b200_dev_sync(stream) != 0)
         {
             return dev_fail(error, "download waveform");

@@ -381,6 +381,7 @@ namespace pe_b200
         // waveform probes (unknown indices), recorded per time step when non-empty
         std::vector<int> probes;
         std::size_t wave_steps{};
+        std::int64_t wave_pitch{};  // lane pitch of d_wave when it was recorded (a later AC analyze() changes last_LSl)
 
         std::string error;
 
