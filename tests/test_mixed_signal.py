@@ -137,3 +137,56 @@ def test_single_instance_digital_clk_follows_the_reference_sequence(ref, abi):
         assert all(v == 2 for v in pins_ab)  # analog pins report X (dll_api.h:224-226)
         got8, _, pins8 = product_comparator_bits(abi, nl, info, vin, r_nom, "u8")
         assert (got8 == want).all() and not any(pins8)
+
+
+D2A_PROBE = r"""
+import ctypes as ct, sys
+import pe_b200 as pe
+from pe_b200 import Netlist
+which = sys.argv[1]
+nl = Netlist(); g = nl.ground()
+va = nl.add(pe.VDC, 1.0); vb = nl.add(pe.VDC, 0.5)
+cmp_ = nl.add(pe.COMPARATOR, 0.0, 5.0)
+rl, ra, rb = nl.add(pe.R, 1e3), nl.add(pe.R, 1e3), nl.add(pe.R, 1e3)
+for a, pa, b, pb in ((va, 1, g, 0), (vb, 1, g, 0), (va, 0, cmp_, 0), (vb, 0, cmp_, 1), (ra, 0, va, 0), (ra, 1, g, 0), (rb, 0, vb, 0), (rb, 1, g, 0),
+                     (cmp_, 2, rl, 0), (rl, 1, g, 0)):  # the comparator's output pin sits on an ANALOG node (a resistor hangs on it)
+    nl.wire(a, pa, b, pb)
+if which == "reference":
+    import refapi
+    c = refapi.RefCircuit(nl)
+else:
+    import emuapi
+    c = pe.Circuit(nl, emuapi.emulator())
+c.set_analyze_type(pe.DC)
+assert c.analyze()
+c.abi.lib.circuit_digital_clk.argtypes = [ct.c_void_p]
+rc = c.abi.lib.circuit_digital_clk(c.h)
+print("clk", rc, flush=True)
+if which == "reference":
+    ok = c.analyze()  # circuit.h:509 + 1015-1022: the drivers collected by the tick become voltage-source branches here
+    print("second analyze", ok, flush=True)
+else:
+    print("error:", c.abi.last_error(), flush=True)
+"""
+
+
+def test_comparator_on_an_analog_node_is_refused_where_the_reference_dies(ref, tmp_path):
+    """VERDICT r01 item 7 (digital -> analog drivers, comparator.h:88-95 / circuit.h:1015-1022).  Through its own C ABI the
+    reference does not survive that path: update_table_digital_clk visits the comparator once per hybrid node it touches
+    (circuit.h:316-333), each visit appends the same (level, node) driver, and the next analyze() dies.  There is no reference
+    behaviour to be drop-in for, so circuit_digital_clk refuses the netlist with an error instead of guessing one."""
+    import os
+    import subprocess
+    import sys
+
+    script = tmp_path / "d2a_probe.py"
+    script.write_text(D2A_PROBE)
+    env = dict(os.environ)
+    here = os.path.dirname(os.path.abspath(__file__))
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(os.path.dirname(here), "phy-engine_b200"), here, env.get("PYTHONPATH", "")])
+    r = subprocess.run([sys.executable, str(script), "reference"], capture_output=True, text=True, env=env, timeout=120)
+    assert "clk 0" in r.stdout  # the tick itself succeeds
+    assert r.returncode != 0 and "second analyze" not in r.stdout, (r.returncode, r.stdout, r.stderr[-300:])  # ... the solve after it does not return
+    p = subprocess.run([sys.executable, str(script), "product"], capture_output=True, text=True, env=env, timeout=120)
+    assert p.returncode == 0, p.stderr[-400:]
+    assert "clk 1" in p.stdout and "analog" in p.stdout  # refused, with a message that names the analog output node
