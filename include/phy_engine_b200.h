@@ -185,6 +185,13 @@ extern "C"
      * info[6] = guarded pivots of the program, instances flagged, instances solved by a re-ordered sub-batch, instances that
      * took the unguarded round, sub-batch runs, live sub-batches */
     int circuit_batch_set_pivot_guard(void* batch, double guard, int rounds);
+    /* batch-state checkpoint (the reference persists ONE circuit with its netlist, pe_nl_fileformat.h:584-657, 805-1046; a
+     * batch persists what its instances carry between analyze() calls): solution, per-instance parameters, companion / device
+     * state of every instance, the clock of the transient and the sub-batches of the pivot safety net, in one blob.  A batch of
+     * the same netlist, parameter keys and instance count resumes from it bit-identically (load checks a fingerprint).
+     * save: buffer == NULL returns the size in *size; 0 = ok, 1 = error, 2 = buffer too small */
+    int circuit_batch_save_state(void* batch, void* buffer, size_t capacity, size_t* size);
+    int circuit_batch_load_state(void* batch, void const* buffer, size_t size);
     int circuit_batch_rescue_info(void* batch, int mode, int64_t* info);
     /* reduce-and-core path: DC / OP of one huge linear circuit (resistors, DC sources; >= 20 000 unknowns, config A of
      * BASELINE.json) per instance: level-scheduled elimination of the degree <= 2 nodes, dense LU of the rest on the FP64

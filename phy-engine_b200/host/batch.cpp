@@ -2,6 +2,7 @@
 // over the sm_100a kernels, for B independent instances at once.  The host only sequences phases and moves
 // parameters/results; every solve runs on the device.  No CUDA device => analyze() fails with an error.
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstring>
 
@@ -1231,6 +1232,225 @@ namespace pe_b200
                 if(!rs.owned[k]) { continue; }
                 for(std::size_t q{}; q < rows; ++q) { w[q * n_inst + rs.inst[k]] = sw[q * m + k]; }
             }
+        }
+        return true;
+    }
+
+    // ---- checkpoint --------------------------------------------------------------------------------------------------------
+    namespace
+    {
+        constexpr std::uint64_t k_ckpt_magic{0x3130544b43324250ull};  // "PB2CKT01"
+        template <typename T>
+        void put(std::vector<unsigned char>& o, T const& v)
+        {
+            auto const* p{reinterpret_cast<unsigned char const*>(&v)};
+            o.insert(o.end(), p, p + sizeof(T));
+        }
+        template <typename T>
+        bool get(unsigned char const*& p, unsigned char const* e, T& v)
+        {
+            if(static_cast<std::size_t>(e - p) < sizeof(T)) { return false; }
+            std::memcpy(&v, p, sizeof(T));
+            p += sizeof(T);
+            return true;
+        }
+    }  // namespace
+
+    // what a blob must agree on with the batch that loads it: the netlist (element codes, wiring), the per-instance parameter
+    // keys (they decide the row layout) and the analysis step
+    std::uint64_t batch::fingerprint() const
+    {
+        std::uint64_t h{1469598103934665603ull};
+        auto mix = [&](std::uint64_t v)
+        {
+            for(int k{}; k < 8; ++k)
+            {
+                h ^= (v >> (8 * k)) & 0xffu;
+                h *= 1099511628211ull;
+            }
+        };
+        for(auto const& e: parent->nl.elems)
+        {
+            mix(static_cast<std::uint64_t>(e.d != nullptr ? e.d->code : -1));
+            for(int const pn: e.pin_node) { mix(static_cast<std::uint64_t>(static_cast<std::int64_t>(pn))); }
+        }
+        for(auto const& [k, v]: sweeps)
+        {
+            mix(static_cast<std::uint64_t>(k.first));
+            mix(static_cast<std::uint64_t>(k.second));
+        }
+        mix(static_cast<std::uint64_t>(n_inst));
+        return h;
+    }
+
+    bool batch::save_state(std::vector<unsigned char>& out)
+    {
+        if(frontal || !cc || d_wi.p == nullptr)
+        {
+            error = "save_state: nothing to save (analyze first; the reduce-and-core path keeps no state)";
+            set_last_error(error);
+            return false;
+        }
+        std::size_t const rows{static_cast<std::size_t>(cc->n_inst_slots)};
+        put(out, k_ckpt_magic);
+        put(out, fingerprint());
+        put(out, static_cast<std::uint64_t>(n_inst));
+        put(out, static_cast<std::uint64_t>(rows));
+        put(out, tr_duration);
+        put(out, last_step);
+        put(out, static_cast<std::uint64_t>(rescues.size()));
+        std::size_t const at{out.size()};
+        out.resize(at + rows * n_inst * sizeof(double));
+        if(rows != 0 && (pe_b200_dev_d2h_2d(out.data() + at, n_inst * sizeof(double), d_wi.p, static_cast<std::size_t>(LSi) * sizeof(double), n_inst * sizeof(double), rows, stream) != 0 ||
+                         pe_b200_dev_sync(stream) != 0))
+        {
+            return dev_fail(error, "download state");
+        }
+        for(auto& rs: rescues)
+        {
+            put(out, static_cast<std::uint64_t>(rs.inst.size()));
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                put(out, static_cast<std::uint64_t>(rs.inst[k]));
+                put(out, static_cast<std::uint8_t>(rs.owned[k]));
+            }
+            put(out, rs.b->pivot_guard);
+            put(out, rs.b->nl_nominal);
+            put(out, rs.b->omega0_override);
+            if(!rs.b->save_state(out))
+            {
+                error = rs.b->error;
+                return false;
+            }
+        }
+        return true;
+    }
+
+    bool batch::load_state(unsigned char const* p, std::size_t n)
+    {
+        unsigned char const* const e{p + n};
+        std::function<bool(batch&, unsigned char const*&)> load = [&](batch& b, unsigned char const*& q) -> bool
+        {
+            std::uint64_t magic{}, fp{}, ni{}, rows{}, nres{};
+            double t{}, ls{};
+            if(!get(q, e, magic) || !get(q, e, fp) || !get(q, e, ni) || !get(q, e, rows) || !get(q, e, t) || !get(q, e, ls) || !get(q, e, nres) || magic != k_ckpt_magic)
+            {
+                error = "load_state: not a batch checkpoint (or truncated)";
+                return false;
+            }
+            std::size_t const bytes{static_cast<std::size_t>(rows) * static_cast<std::size_t>(ni) * sizeof(double)};
+            if(static_cast<std::size_t>(e - q) < bytes)
+            {
+                error = "load_state: truncated";
+                return false;
+            }
+            unsigned char const* const data{q};
+            q += bytes;
+            // the parameter rows of the blob are the authority: host copies first (they decide the elimination order), then the
+            // program, then every persistent row as it was
+            if(ni != b.n_inst)
+            {
+                error = "load_state: instance count differs";
+                return false;
+            }
+            if(fp != b.fingerprint())
+            {
+                error = "load_state: the checkpoint belongs to another netlist / parameter set";
+                return false;
+            }
+            if(!b.ensure_compiled())
+            {
+                error = b.error;
+                return false;
+            }
+            if(rows != static_cast<std::uint64_t>(b.cc->n_inst_slots))
+            {
+                error = "load_state: row layout differs (another library version?)";
+                return false;
+            }
+            auto const* rowsd{reinterpret_cast<double const*>(data)};
+            for(auto const& [key, slot]: b.cc->swept_slot)
+            {
+                auto& v{b.sweeps[key]};
+                v.assign(rowsd + static_cast<std::size_t>(slot) * ni, rowsd + (static_cast<std::size_t>(slot) + 1) * ni);
+            }
+            ++b.sweeps_rev;
+            b.sweeps_dirty = false;
+            if(rows != 0 && (pe_b200_dev_h2d_2d(b.d_wi.p, static_cast<std::size_t>(b.LSi) * sizeof(double), data, ni * sizeof(double), ni * sizeof(double), rows, b.stream) != 0 ||
+                             pe_b200_dev_sync(b.stream) != 0))
+            {
+                error = std::string{"load_state: "} + pe_b200_dev_last_error();
+                return false;
+            }
+            b.tr_duration = t;
+            b.last_step = ls;
+            b.rescues.clear();
+            for(std::uint64_t r{}; r < nres; ++r)
+            {
+                std::uint64_t m{};
+                if(!get(q, e, m) || m > ni)
+                {
+                    error = "load_state: truncated";
+                    return false;
+                }
+                rescue_set rs;
+                rs.inst.resize(m);
+                rs.owned.resize(m);
+                for(std::uint64_t k{}; k < m; ++k)
+                {
+                    std::uint64_t i{};
+                    std::uint8_t o{};
+                    if(!get(q, e, i) || !get(q, e, o) || i >= ni)
+                    {
+                        error = "load_state: truncated";
+                        return false;
+                    }
+                    rs.inst[k] = static_cast<std::size_t>(i);
+                    rs.owned[k] = static_cast<char>(o);
+                }
+                rs.b = std::make_unique<batch>();
+                auto& sb{*rs.b};
+                sb.parent = b.parent;
+                sb.n_inst = static_cast<std::size_t>(m);
+                sb.device = b.device;
+                sb.stream = b.stream;
+                sb.is_rescue = true;
+                sb.guard_all = b.guard_all;
+                sb.ac = b.ac;
+                sb.ac_slice_first = b.ac_slice_first;
+                sb.ac_slice_count = b.ac_slice_count;
+                sb.probes = b.probes;
+                if(!get(q, e, sb.pivot_guard) || !get(q, e, sb.nl_nominal) || !get(q, e, sb.omega0_override))
+                {
+                    error = "load_state: truncated";
+                    return false;
+                }
+                // its elimination order was chosen on ITS first instance: the sweeps must be there before it compiles
+                for(auto const& [key, v]: b.sweeps)
+                {
+                    auto& d{sb.sweeps[key]};
+                    d.resize(m);
+                    for(std::uint64_t k{}; k < m; ++k) { d[k] = v[rs.inst[k]]; }
+                }
+                if(!load(sb, q)) { return false; }
+                b.rescues.push_back(std::move(rs));
+            }
+            b.rescues_sweeps_rev = b.sweeps_rev;
+            b.rescues_param_rev = b.parent->param_rev;
+            b.rescues_structure_rev = b.parent->structure_rev;
+            return true;
+        };
+        unsigned char const* q{p};
+        if(frontal || parent == nullptr)
+        {
+            error = "load_state: not available on this batch";
+            set_last_error(error);
+            return false;
+        }
+        if(!load(*this, q))
+        {
+            set_last_error(error);
+            return false;
         }
         return true;
     }

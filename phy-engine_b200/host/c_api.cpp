@@ -652,6 +652,25 @@ extern "C"
         return 0;
     }
 
+    // batch-state checkpoint (pe_host.hpp): call with buffer == NULL to learn the size; 0 = ok, 1 = error, 2 = buffer too small
+    int circuit_batch_save_state(void* b, void* buffer, size_t capacity, size_t* size)
+    {
+        if(b == nullptr || size == nullptr) { return 1; }
+        std::vector<unsigned char> blob;
+        if(!static_cast<batch*>(b)->save_state(blob)) { return 1; }
+        *size = blob.size();
+        if(buffer == nullptr) { return 0; }
+        if(capacity < blob.size()) { return 2; }
+        std::memcpy(buffer, blob.data(), blob.size());
+        return 0;
+    }
+
+    int circuit_batch_load_state(void* b, void const* buffer, size_t size)
+    {
+        if(b == nullptr || buffer == nullptr) { return 1; }
+        return static_cast<batch*>(b)->load_state(static_cast<unsigned char const*>(buffer), size) ? 0 : 1;
+    }
+
     // pivot safety net (pe_host.hpp): guard = relative size below which a guarded pivot flags its lane (0 = off, < 0 = default
     // 2^-30), rounds = re-orderings tried before the last, unguarded one (< 0 = default 3)
     int circuit_batch_set_pivot_guard(void* b, double guard, int rounds)

@@ -413,6 +413,13 @@ namespace pe_b200
         bool analyze_main(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv);
         bool run_rescues(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv, bool fresh_state);
 
+        // ---- checkpoint (the reference persists a single circuit in pe_nl_fileformat.h:584-657, 805-1046): the
+        // persistent per-instance rows (solution, swept parameters, companion / device state), the clock of the transient and
+        // the sub-batches of the pivot safety net, as one self-describing blob a batch of the same netlist can resume from
+        bool save_state(std::vector<unsigned char>& out);
+        bool load_state(unsigned char const* p, std::size_t n);
+        std::uint64_t fingerprint() const;
+
         bool analyze();
         bool compile_host(bool& layout_change);  // symbolic phase only, no device needed
         bool ensure_compiled();

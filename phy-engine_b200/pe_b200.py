@@ -404,6 +404,18 @@ class Batch:
         keys = ("unknowns", "eliminated", "levels", "core_rows", "edges", "launches", "ld_core", "core_edges", "reduce_us", "lu_us", "subst_us")
         return {k: int(x) for k, x in zip(keys, v)}
 
+    def save_state(self) -> bytes:
+        self.lib.circuit_batch_save_state.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_size_t, ct.POINTER(ct.c_size_t)]
+        n = ct.c_size_t(0)
+        self._rc(self.lib.circuit_batch_save_state(self.h, None, 0, ct.byref(n)), "circuit_batch_save_state")
+        buf = ct.create_string_buffer(n.value)
+        self._rc(self.lib.circuit_batch_save_state(self.h, buf, n.value, ct.byref(n)), "circuit_batch_save_state")
+        return buf.raw[: n.value]
+
+    def load_state(self, blob: bytes):
+        self.lib.circuit_batch_load_state.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_size_t]
+        self._rc(self.lib.circuit_batch_load_state(self.h, blob, len(blob)), "circuit_batch_load_state")
+
     def set_pivot_guard(self, guard: float = -1.0, rounds: int = -1):
         self.lib.circuit_batch_set_pivot_guard.argtypes = [ct.c_void_p, ct.c_double, ct.c_int]
         self._rc(self.lib.circuit_batch_set_pivot_guard(self.h, guard, rounds), "circuit_batch_set_pivot_guard")
