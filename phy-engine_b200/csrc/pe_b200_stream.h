@@ -107,6 +107,12 @@ namespace pe_stream
         for(int j = 0; j < PE_SJ; ++j) { pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]); }
     }
 
+    // IND_STEP (inductor.h:134-160): req, ueq from the previous step's voltage and branch current
+    PE_SK_FN void jind(jv const& L, jv const& dt, jv const& va, jv const& vb, jv const& ib, jv& req, jv& ueq)
+    {
+        for(int j = 0; j < PE_SJ; ++j) { pe_models::ind_step(L.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), ib.v[j], req.v[j], ueq.v[j]); }
+    }
+
     // CAP_STEP when prev_g is known to equal 2 C / dt already (steady variant, host/stream.cpp): the same arithmetic with the
     // freshly computed value standing in for the stored one
     PE_SK_FN void jcap_steady(jv const& C, jv const& dt, jv const& va, jv const& vb, jv& hist, jv& prev_g)

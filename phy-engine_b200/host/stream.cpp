@@ -94,6 +94,13 @@ namespace pe_b200
                         j.wr.push_back(o.opnd[0] & k_slot_mask);
                         j.wr.push_back(o.opnd[1] & k_slot_mask);
                     }
+                    else if(o.opcode == PE_OP_IND_STEP && o.opnd.size() == 7)
+                    {
+                        // [req][ueq] <- [L][dt][va][vb][ib] (inductor.h:134-160)
+                        for(std::size_t i{2}; i < 7; ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
+                        j.wr.push_back(o.opnd[0] & k_slot_mask);
+                        j.wr.push_back(o.opnd[1] & k_slot_mask);
+                    }
                     else if(simple_value_op(o.opcode) && o.opnd.size() == (o.opcode == PE_OP_RECIP || o.opcode == PE_OP_COPY ? 2u : 3u))
                     {
                         for(std::size_t i{1}; i < o.opnd.size(); ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
@@ -612,6 +619,12 @@ namespace pe_b200
                 {
                     t << dv << w[0] << " = " << x[0] << "; " << dv << w[1] << " = " << x[1] << "; jcap(" << x[2] << ", " << x[3] << ", " << x[4] << ", " << x[5] << ", " << w[0] << ", " << w[1]
                       << ");";
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
+                    if(!st[1].empty()) { t << " sk_st(k, " << st[1] << ", " << w[1] << ");"; }
+                }
+                else if(o.opcode == PE_OP_IND_STEP)  // [req][ueq] <- [L][dt][va][vb][ib]
+                {
+                    t << dv << w[0] << " = jzero(); " << dv << w[1] << " = jzero(); jind(" << x[0] << ", " << x[1] << ", " << x[2] << ", " << x[3] << ", " << x[4] << ", " << w[0] << ", " << w[1] << ");";
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                     if(!st[1].empty()) { t << " sk_st(k, " << st[1] << ", " << w[1] << ");"; }
                 }

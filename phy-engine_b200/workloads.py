@@ -56,6 +56,28 @@ def rlc_ladder(n_sections: int = 64, r: float = 10.0, l: float = 1e-6, c: float 
     return nl, {"src": src, "R": rs, "L": ls, "C": cs}
 
 
+def rlc_ladder_dc(n_sections: int = 64, r: float = 10.0, l: float = 1e-6, c: float = 1e-9, v: float = 1.0):
+    """Step response of an RLC ladder: VDC -> n x (series R, series L, shunt C).  2n + 1 nodes, n + 1 branches; the transient
+    program is DOT / CAP_STEP / IND_STEP ops only (no time-dependent source), which the stream kernel covers."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.VDC, v)
+    nl.wire(src, 1, g, 0)
+    prev = (src, 0)
+    R, L, C = [], [], []
+    for _ in range(n_sections):
+        er, el, ec = nl.add(pe.R, r), nl.add(pe.L, l), nl.add(pe.C, c)
+        nl.wire(prev[0], prev[1], er, 0)
+        nl.wire(er, 1, el, 0)
+        nl.wire(el, 1, ec, 0)
+        nl.wire(ec, 1, g, 0)
+        prev = (el, 1)
+        R.append(er)
+        L.append(el)
+        C.append(ec)
+    return nl, {"V": src, "R": R, "L": L, "C": C}
+
+
 def diode_resistor(v: float = 1.0, r: float = 1e3, n_diodes: int = 1):
     """Config C (c1): V - R - n series diodes to ground (test/0011.nonlinear/op_pn_junction.cpp for n = 1)."""
     nl = Netlist()
