@@ -178,10 +178,10 @@ extern "C"
      * per CTA (bytes), tiles per solve, rows per ring stage */
     int circuit_batch_stream_info(void* batch, int mode, int64_t* info);
     /* pivot safety net.  The elimination order is static (chosen on the first instance's values; the reference re-pivots in
-     * every solve, Eigen SparseLU_pivotL.h:76-107).  Pivots that are not provably safe are tested on the device: a lane whose
-     * pivot is smaller than `guard` times the largest term that went into it is flagged, and analyze() solves the flagged
+     * every solve, Eigen SparseLU_pivotL.h:76-107).  Pivots that are not provably safe are tested on the device: a lane with an
+     * entry of L above 1 / `guard` (the pivot is that much smaller than an entry of its column) is flagged, and analyze() solves the flagged
      * instances again in a sub-batch whose order is chosen on THEIR values; what still fails goes to the next of `rounds`
-     * rounds, the last of which runs unguarded.  guard: 0 = off, < 0 = default (2^-30); rounds < 0 = default (3).
+     * rounds, the last of which runs unguarded.  guard: 0 = off, < 0 = default (2^-20); rounds < 0 = default (3).
      * info[6] = guarded pivots of the program, instances flagged, instances solved by a re-ordered sub-batch, instances that
      * took the unguarded round, sub-batch runs, live sub-batches */
     int circuit_batch_set_pivot_guard(void* batch, double guard, int rounds);

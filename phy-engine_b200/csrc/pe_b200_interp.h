@@ -126,16 +126,9 @@ namespace pe_interp
                         double const b = ldu(c, PE_LDW(p + 2 * i + 1));
                         acc = fma(-a, b, acc);
                     }
-                    if(flags & PE_F_GUARD)
-                    {
-                        // second walk over the (cached) operands of a pivot: the largest magnitude that went into it
-                        double s = 0.0, m = 0.0;
-                        for(uint32_t i = 0; i < nsrc; ++i) { s = PE_ADD(s, ld(c, PE_LDW(p - nsrc + i))); }
-                        for(uint32_t i = 0; i < npair; ++i) { m = fmax(m, fabs(ldu(c, PE_LDW(p + 2 * i)) * ldu(c, PE_LDW(p + 2 * i + 1)))); }
-                        if(PE_GUARD_TRIP(fabs(acc), fabs(s), m, tol.guard)) { fail = true; }
-                    }
                     p += 2 * npair;
                     if(flags & PE_F_SCALE) { acc = PE_MUL(acc, ldu(c, scale)); }
+                    if((flags & PE_F_GUARD) && PE_GUARD_TRIP(fabs(acc), tol.guard)) { fail = true; }  // an entry of L out of bounds
                     if(flags & PE_F_RECIP)
                     {
                         if(acc == 0.0 || !isfinite(acc)) { fail = true; }
@@ -191,19 +184,6 @@ namespace pe_interp
                         aim = fma(-ar, bi, aim);
                         aim = fma(-ai, br, aim);
                     }
-                    if(flags & PE_F_GUARD)
-                    {
-                        double sr = 0.0, si = 0.0;
-                        for(uint32_t i = 0; i < nre; ++i) { sr = PE_ADD(sr, ld(c, PE_LDW(p - nim - nre + i))); }
-                        for(uint32_t i = 0; i < nim; ++i) { si = PE_ADD(si, ld(c, PE_LDW(p - nim + i))); }
-                        double m = 0.0;
-                        for(uint32_t i = 0; i < npair; ++i)
-                        {
-                            uint32_t const sa = PE_LDW(p + 2 * i), sb = PE_LDW(p + 2 * i + 1);
-                            m = fmax(m, (fabs(ldu(c, sa)) + fabs(ldu(c, sa + 1))) * (fabs(ldu(c, sb)) + fabs(ldu(c, sb + 1))));
-                        }
-                        if(PE_GUARD_TRIP(fabs(are) + fabs(aim), fabs(sr) + fabs(si), m, tol.guard)) { fail = true; }
-                    }
                     p += 2 * npair;
                     if(flags & PE_F_SCALE)
                     {
@@ -213,6 +193,7 @@ namespace pe_interp
                         are = nr;
                         aim = ni;
                     }
+                    if((flags & PE_F_GUARD) && PE_GUARD_TRIP(fabs(are) + fabs(aim), tol.guard)) { fail = true; }
                     if(flags & PE_F_RECIP)
                     {
                         double const m = are * are + aim * aim;

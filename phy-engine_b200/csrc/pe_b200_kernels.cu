@@ -603,25 +603,19 @@ namespace
                 acc[j] = fma(a, bv[i][j], acc[j]);
             }
         }
-        if(flags & PE_F_GUARD)
-        {
-            // pivot guard (pe_b200_program.h PE_F_GUARD): the largest magnitude that went into the pivot against what is left
-#pragma unroll
-            for(int j = 0; j < J; ++j)
-            {
-                double s = 0.0;
-#pragma unroll
-                for(int i = 0; i < 2 * NA; ++i) { s = fma(sv[i][j], __hiloint2double((int)(0x3ff00000u | (g[i] & 0x80000000u)), 0), s); }
-                double m = 0.0;
-#pragma unroll
-                for(int i = 0; i < NB; ++i) { m = fmax(m, fabs(av[i][j] * bv[i][j])); }
-                if(PE_GUARD_TRIP(fabs(acc[j]), fabs(s), m, r.guard)) { fail[j] = true; }
-            }
-        }
         if(flags & PE_F_SCALE)
         {
 #pragma unroll
             for(int j = 0; j < J; ++j) { acc[j] = PE_MUL(acc[j], sc[j]); }
+        }
+        if(flags & PE_F_GUARD)
+        {
+            // an entry of L: out of bounds when the pivot is far smaller than this entry of its column (pe_b200_program.h)
+#pragma unroll
+            for(int j = 0; j < J; ++j)
+            {
+                if(PE_GUARD_TRIP(fabs(acc[j]), r.guard)) { fail[j] = true; }
+            }
         }
         if(flags & PE_F_RECIP)
         {
@@ -723,13 +717,20 @@ namespace
             for(int j = 0; j < J; ++j)
             {
                 double const a = __hiloint2double(__double2hiint(pa[q][j]) ^ (int)(0x80000000u ^ gp[q]), __double2loint(pa[q][j]));
-                if((flags & PE_F_GUARD) && PE_GUARD_TRIP(fabs(fma(a, pb[q][j], acc[j])), fabs(acc[j]), fabs(a * pb[q][j]), guard)) { fail[j] = true; }
                 acc[j] = fma(a, pb[q][j], acc[j]);
             }
             if(flags & PE_F_SCALE)
             {
 #pragma unroll
                 for(int j = 0; j < J; ++j) { acc[j] = PE_MUL(acc[j], piv[j]); }
+            }
+            if(flags & PE_F_GUARD)
+            {
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    if(PE_GUARD_TRIP(fabs(acc[j]), guard)) { fail[j] = true; }
+                }
             }
             if(flags & PE_F_RECIP)
             {
@@ -836,27 +837,13 @@ namespace
             acc.v[j] = PE_RCP(acc.v[j]);
         }
     }
-    // pivot guard (pe_b200_program.h PE_F_GUARD): gs = |sum of the stamps|, gp = largest |l * u| that went into the pivot
-    __device__ __forceinline__ void jgabs(jv& gs, jv& gp, jv const& acc)
+    // pivot guard (pe_b200_program.h PE_F_GUARD): an entry of L out of bounds marks the lane
+    __device__ __forceinline__ void jguard(jv const& l, double const guard, uint32_t& failm)
     {
 #pragma unroll
         for(int j = 0; j < 4; ++j)
         {
-            gs.v[j] = fabs(acc.v[j]);
-            gp.v[j] = 0.0;
-        }
-    }
-    __device__ __forceinline__ void jgmax(jv& gp, jv const& a, jv const& b)
-    {
-#pragma unroll
-        for(int j = 0; j < 4; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
-    }
-    __device__ __forceinline__ void jguard(jv const& acc, jv const& gs, jv const& gp, double const guard, uint32_t& failm)
-    {
-#pragma unroll
-        for(int j = 0; j < 4; ++j)
-        {
-            if(PE_GUARD_TRIP(fabs(acc.v[j]), gs.v[j], gp.v[j], guard)) { failm |= 1u << j; }
+            if(PE_GUARD_TRIP(fabs(l.v[j]), guard)) { failm |= 1u << j; }
         }
     }
     // CAP_STEP (capacitor.h:106-128): hist, prev_g updated in place

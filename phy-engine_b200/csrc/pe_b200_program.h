@@ -114,16 +114,16 @@ extern "C"
         PE_F_RECIP = 2,    // store the reciprocal; a zero / non-finite value marks the lane singular
         PE_F_CHECK_V = 4,  // Newton test against the old value at dst with the voltage tolerances (circuit.h:923-933)
         PE_F_CHECK_I = 8,  // ... with the branch-current tolerances (circuit.h:937-947)
-        // pivot guard (on PE_F_RECIP ops whose pivot is not provably safe, compiler.cpp "guard elision"; PE_GUARD_TRIP below): with
-        // s = |sum of the stamps| and p = max |l * u| over the updates, the lane is marked singular when |pivot| < guard * max(s, p)
-        // (cancellation took more than -log2(guard) bits of it) or 0 < s < guard * p (the updates swamp the stamped value: element
-        // growth after a tiny pivot) -- the static elimination order (chosen on nominal values) does not suit this lane's values.
+        // pivot guard, on the ops that produce an entry of L (PE_F_SCALE by a pivot that is not provably safe, compiler.cpp "guard
+        // elision"): the lane is marked singular when |l| * guard > 1, i.e. when the pivot is more than 1 / guard times smaller than
+        // an entry of its column.  The order was chosen with threshold pivoting (|l| <= 1e3 on the nominal values), and a partial-
+        // pivoting LU would have taken another row here: the static elimination order does not suit this lane's values.
         // The host re-runs such lanes with an order chosen on THEIR values (batch.cpp "rescue"); Eigen's SparseLU re-pivots per
         // solve instead (SparseLU_pivotL.h:76-107).  guard == 0 switches the test off.
         PE_F_GUARD = 16,
     };
-#define PE_GUARD_DEFAULT 9.313225746154785e-10 /* 2^-30 */
-#define PE_GUARD_TRIP(acc_abs, s_abs, p_max, guard) ((acc_abs) < (guard) * fmax((s_abs), (p_max)) || ((s_abs) != 0.0 && (s_abs) < (guard) * (p_max)))
+#define PE_GUARD_DEFAULT 9.5367431640625e-07 /* 2^-20: multipliers above ~1e6 */
+#define PE_GUARD_TRIP(l_abs, guard) ((l_abs) * (guard) > 1.0)
 #define PE_DOT_MAX_SRC 255u
 #define PE_DOT_MAX_PAIR 255u
 #define PE_MAX_WARPS 16

@@ -208,9 +208,8 @@ namespace pe_rinterp
             uint32_t const ctl = fetch();
             uint32_t const scale = fetch();
             constexpr uint32_t MA = 3, MB = 4;
-            vd<J> acc, gs, gp;  // guarded pivot: |sum of the stamps|, largest |l * u|
-            for(int j = 0; j < J; ++j) { acc.v[j] = gs.v[j] = gp.v[j] = 0.0; }
-            bool const guard = ((ctl >> 16) & PE_F_GUARD) != 0u;
+            vd<J> acc;
+            for(int j = 0; j < J; ++j) { acc.v[j] = 0.0; }
             if(na <= MA && nb <= MB)
             {
                 // every operand word of the op is requested before the first one is used
@@ -242,10 +241,6 @@ namespace pe_rinterp
                         for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
                     }
                 }
-                if(guard)
-                {
-                    for(int j = 0; j < J; ++j) { gs.v[j] = fabs(acc.v[j]); }
-                }
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -256,10 +251,6 @@ namespace pe_rinterp
                         vd<J> const a = ldo<J>(c, pw[r] & 0xffffu);  // pair operands carry a sign (aliased entries)
                         vd<J> const b = ldo<J>(c, pw[r] >> 16);
                         for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
-                        if(guard)
-                        {
-                            for(int j = 0; j < J; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
-                        }
                     }
                 }
             }
@@ -278,35 +269,28 @@ namespace pe_rinterp
                     vd<J> const s1 = ldo<J>(c, w >> 16);
                     for(int j = 0; j < J; ++j) { acc.v[j] = PE_ADD(PE_ADD(acc.v[j], s0.v[j]), s1.v[j]); }
                 }
-                if(guard)
-                {
-                    for(int j = 0; j < J; ++j) { gs.v[j] = fabs(acc.v[j]); }
-                }
                 for(uint32_t r = 0; r < nb; ++r)
                 {
                     uint32_t const w = fetch();
                     vd<J> const a = ldo<J>(c, w & 0xffffu);
                     vd<J> const b = ldo<J>(c, w >> 16);
                     for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
-                    if(guard)
-                    {
-                        for(int j = 0; j < J; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
-                    }
                 }
                 if(idle) { return V_OK; }
             }
             uint32_t const flags = ctl >> 16;
-            if(guard)
-            {
-                for(int j = 0; j < J; ++j)
-                {
-                    if(PE_GUARD_TRIP(fabs(acc.v[j]), gs.v[j], gp.v[j], tol.guard)) { fail[j] = true; }
-                }
-            }
             if(flags & PE_F_SCALE)
             {
                 vd<J> const sc = ldv<J>(c, abs_slot(c, scale));
                 for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], sc.v[j]); }
+                if(flags & PE_F_GUARD)
+                {
+                    // an entry of L: out of bounds when the pivot is far smaller than this entry of its column (pe_b200_program.h)
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(PE_GUARD_TRIP(fabs(acc.v[j]), tol.guard)) { fail[j] = true; }
+                    }
+                }
             }
             if(flags & PE_F_RECIP)
             {
@@ -358,13 +342,6 @@ namespace pe_rinterp
                 vd<J> const s1 = ldo<J>(c, w >> 16);
                 for(int j = 0; j < J; ++j) { aim.v[j] = PE_ADD(PE_ADD(aim.v[j], s0.v[j]), s1.v[j]); }
             }
-            bool const guard = ((ctl >> 16) & PE_F_GUARD) != 0u;
-            vd<J> gs, gp;  // guarded pivot (1-norms): |sum of the stamps|, largest |l * u|
-            for(int j = 0; j < J; ++j)
-            {
-                gs.v[j] = guard ? fabs(are.v[j]) + fabs(aim.v[j]) : 0.0;
-                gp.v[j] = 0.0;
-            }
             for(uint32_t r = 0; r < nb; ++r)
             {
                 uint32_t const w = fetch();
@@ -378,20 +355,9 @@ namespace pe_rinterp
                     aim.v[j] = fma(-ar.v[j], bi.v[j], aim.v[j]);
                     aim.v[j] = fma(-ai.v[j], br.v[j], aim.v[j]);
                 }
-                if(guard)
-                {
-                    for(int j = 0; j < J; ++j) { gp.v[j] = fmax(gp.v[j], (fabs(ar.v[j]) + fabs(ai.v[j])) * (fabs(br.v[j]) + fabs(bi.v[j]))); }
-                }
             }
             if(idle) { return V_OK; }
             uint32_t const flags = ctl >> 16;
-            if(guard)
-            {
-                for(int j = 0; j < J; ++j)
-                {
-                    if(PE_GUARD_TRIP(fabs(are.v[j]) + fabs(aim.v[j]), gs.v[j], gp.v[j], tol.guard)) { fail[j] = true; }
-                }
-            }
             if(flags & PE_F_SCALE)
             {
                 uint32_t const ss = abs_slot(c, scale);
@@ -402,6 +368,13 @@ namespace pe_rinterp
                     double const ni = are.v[j] * si.v[j] + aim.v[j] * sr.v[j];
                     are.v[j] = nr;
                     aim.v[j] = ni;
+                }
+                if(flags & PE_F_GUARD)
+                {
+                    for(int j = 0; j < J; ++j)
+                    {
+                        if(PE_GUARD_TRIP(fabs(are.v[j]) + fabs(aim.v[j]), tol.guard)) { fail[j] = true; }
+                    }
                 }
             }
             if(flags & PE_F_RECIP)
@@ -455,18 +428,18 @@ namespace pe_rinterp
                     uint32_t const w = wd[base + 1u + nsr];
                     vd<J> const a = ldo<J>(c, w & 0xffffu);
                     vd<J> const b = ldo<J>(c, w >> 16);
-                    if(flags & PE_F_GUARD)
-                    {
-                        for(int j = 0; j < J; ++j)
-                        {
-                            if(PE_GUARD_TRIP(fabs(fma(-a.v[j], b.v[j], acc.v[j])), fabs(acc.v[j]), fabs(a.v[j] * b.v[j]), tol.guard)) { fail[j] = true; }
-                        }
-                    }
                     for(int j = 0; j < J; ++j) { acc.v[j] = fma(-a.v[j], b.v[j], acc.v[j]); }
                 }
                 if(flags & PE_F_SCALE)
                 {
                     for(int j = 0; j < J; ++j) { acc.v[j] = PE_MUL(acc.v[j], piv.v[j]); }
+                    if(flags & PE_F_GUARD)
+                    {
+                        for(int j = 0; j < J; ++j)
+                        {
+                            if(PE_GUARD_TRIP(fabs(acc.v[j]), tol.guard)) { fail[j] = true; }
+                        }
+                    }
                 }
                 if(flags & PE_F_RECIP)
                 {

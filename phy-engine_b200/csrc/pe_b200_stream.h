@@ -81,24 +81,12 @@ namespace pe_stream
             acc.v[j] = PE_RCP(acc.v[j]);
         }
     }
-    // pivot guard (pe_b200_program.h PE_F_GUARD): gs = |sum of the stamps|, gp = largest |l * u| that went into the pivot
-    PE_SK_FN void jgabs(jv& gs, jv& gp, jv const& acc)
+    // pivot guard (pe_b200_program.h PE_F_GUARD): an entry of L out of bounds marks the lane
+    PE_SK_FN void jguard(jv const& l, double const guard, uint32_t& failm)
     {
         for(int j = 0; j < PE_SJ; ++j)
         {
-            gs.v[j] = fabs(acc.v[j]);
-            gp.v[j] = 0.0;
-        }
-    }
-    PE_SK_FN void jgmax(jv& gp, jv const& a, jv const& b)
-    {
-        for(int j = 0; j < PE_SJ; ++j) { gp.v[j] = fmax(gp.v[j], fabs(a.v[j] * b.v[j])); }
-    }
-    PE_SK_FN void jguard(jv const& acc, jv const& gs, jv const& gp, double const guard, uint32_t& failm)
-    {
-        for(int j = 0; j < PE_SJ; ++j)
-        {
-            if(PE_GUARD_TRIP(fabs(acc.v[j]), gs.v[j], gp.v[j], guard)) { failm |= 1u << j; }
+            if(PE_GUARD_TRIP(fabs(l.v[j]), guard)) { failm |= 1u << j; }
         }
     }
     // CAP_STEP (capacitor.h:106-128): hist, prev_g updated in place

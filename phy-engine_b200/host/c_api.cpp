@@ -671,8 +671,8 @@ extern "C"
         return static_cast<batch*>(b)->load_state(static_cast<unsigned char const*>(buffer), size) ? 0 : 1;
     }
 
-    // pivot safety net (pe_host.hpp): guard = relative size below which a guarded pivot flags its lane (0 = off, < 0 = default
-    // 2^-30), rounds = re-orderings tried before the last, unguarded one (< 0 = default 3)
+    // pivot safety net (pe_host.hpp): guard = 1 / the largest multiplier |l| a guarded column may hold (0 = off, < 0 = default
+    // 2^-20), rounds = re-orderings tried before the last, unguarded one (< 0 = default 3)
     int circuit_batch_set_pivot_guard(void* b, double guard, int rounds)
     {
         if(b == nullptr || guard >= 1.0 || rounds > 16) { return 1; }

@@ -1628,7 +1628,7 @@ namespace pe_b200
                     std::size_t const step_begin{RS[static_cast<std::size_t>(sj)].sec[2][static_cast<std::size_t>(ph)].size()};
                     load_sources(rc.orig[static_cast<std::size_t>(st.piv)]);
                     load_updates(st.piv, rc.pairs[static_cast<std::size_t>(st.piv)], st.node, false);
-                    emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP | (st.guard ? PE_F_GUARD : 0u), 0, sre, sim, pp);
+                    emit_dot(sj, ph, key_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
                     for(int e: st.u_ent)
                     {
                         load_sources(rc.orig[static_cast<std::size_t>(e)]);
@@ -1648,7 +1648,7 @@ namespace pe_b200
                     {
                         load_sources(rc.orig[static_cast<std::size_t>(e)]);
                         load_updates(e, rc.pairs[static_cast<std::size_t>(e)], st.node, false);
-                        emit_dot(sj, ph, key_e(e), PE_F_SCALE, key_e(st.piv), sre, sim, pp);
+                        emit_dot(sj, ph, key_e(e), PE_F_SCALE | (st.guard ? PE_F_GUARD : 0u), key_e(st.piv), sre, sim, pp);  // an entry of L
                     }
                     if(rc.ynz[static_cast<std::size_t>(st.r)])
                     {
@@ -1667,7 +1667,7 @@ namespace pe_b200
                         {
                             auto const& o{lst[step_begin + q]};
                             fits = o.opcode == PE_OP_DOT && o.sim.empty() && o.pp.size() <= 1 && o.sre.size() <= (q == 0 ? 4u : 2u) &&
-                                   (q == 0 ? (o.flags & ~static_cast<std::uint32_t>(PE_F_GUARD)) == PE_F_RECIP : (o.flags == 0u || (o.flags == PE_F_SCALE && o.scale == lst[step_begin].dst)));
+                                   (q == 0 ? o.flags == PE_F_RECIP : (o.flags == 0u || ((o.flags & ~static_cast<std::uint32_t>(PE_F_GUARD)) == PE_F_SCALE && o.scale == lst[step_begin].dst)));
                         }
                         if(fits)
                         {
@@ -2502,7 +2502,7 @@ namespace pe_b200
                 pr.structurally_singular = singular;
                 pr.nnz_lu = nv.size();
 
-                // --- guard elision: which pivots need the run-time pivot guard (PE_F_GUARD).  A node row that carries nothing but
+                // --- guard elision: which pivots need the run-time guard on their column of L (PE_F_GUARD).  A node row that carries nothing but
                 // two-terminal positive conductances (R, and C's companion in the real-valued modes) is symmetric and diagonally
                 // dominant whatever the per-instance values are, eliminating such a row on its diagonal leaves the rows it updates
                 // that way, and Gaussian elimination without pivoting has growth <= 2 on such a block (Wilkinson): no order can be
@@ -2530,7 +2530,7 @@ namespace pe_b200
                         st.guard = !safe;
                         if(st.guard)
                         {
-                            ++pr.n_guarded;
+                            if(!st.lrows.empty()) { ++pr.n_guarded; }
                             // the rows it updates are no longer what the elements stamped (a pivot row that holds nothing but
                             // the pivot -- a grounded voltage source -- updates no matrix entry)
                             if(!st.ucols.empty())
@@ -2771,7 +2771,7 @@ namespace pe_b200
                     bool const top{st.leaf < 0};
                     load_sources(orig[static_cast<std::size_t>(st.piv)]);
                     load_updates(st.piv, pairs[static_cast<std::size_t>(st.piv)], top, false);
-                    emit_dot(S, uslot_e(st.piv), PE_F_RECIP | (st.guard ? PE_F_GUARD : 0u), 0, sre, sim, pp);
+                    emit_dot(S, uslot_e(st.piv), PE_F_RECIP, 0, sre, sim, pp);
                     for(int e: st.u_ent)
                     {
                         load_sources(orig[static_cast<std::size_t>(e)]);
@@ -2782,7 +2782,7 @@ namespace pe_b200
                     {
                         load_sources(orig[static_cast<std::size_t>(e)]);
                         load_updates(e, pairs[static_cast<std::size_t>(e)], top, false);
-                        emit_dot(S, uslot_e(e), PE_F_SCALE, uslot_e(st.piv), sre, sim, pp);
+                        emit_dot(S, uslot_e(e), PE_F_SCALE | (st.guard ? PE_F_GUARD : 0u), uslot_e(st.piv), sre, sim, pp);  // an entry of L
                     }
                     if(ynz[static_cast<std::size_t>(st.r)])
                     {

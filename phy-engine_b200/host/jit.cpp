@@ -205,17 +205,14 @@ namespace pe_b200
                     std::size_t q{};
                     t << dv << w[0] << " = jzero();";
                     for(auto const s: o.sre) { t << ((s & PE_R_NEG) ? " jsub(" : " jadd(") << w[0] << ", " << x[q++] << ");"; }
-                    bool const guard{(o.flags & PE_F_GUARD) != 0u};  // pe_b200_program.h: pivot guard
-                    if(guard) { t << " { jv gs, gp; jgabs(gs, gp, " << w[0] << ");"; }
                     for(auto const& pp: o.pp)
                     {
                         bool const pos{((pp.first ^ pp.second) & PE_R_NEG) != 0u};  // -(+-a)(+-b)
                         t << (pos ? " jfma(" : " jfms(") << w[0] << ", " << x[q] << ", " << x[q + 1] << ");";
-                        if(guard) { t << " jgmax(gp, " << x[q] << ", " << x[q + 1] << ");"; }
                         q += 2;
                     }
-                    if(guard) { t << " jguard(" << w[0] << ", gs, gp, guard, fm); }"; }
                     if(o.flags & PE_F_SCALE) { t << " jmul(" << w[0] << ", " << x[q++] << ");"; }
+                    if((o.flags & PE_F_SCALE) && (o.flags & PE_F_GUARD)) { t << " jguard(" << w[0] << ", guard, fm);"; }  // pe_b200_program.h: an entry of L out of bounds
                     if(o.flags & PE_F_RECIP) { t << " jrcp(" << w[0] << ", fm);"; }
                     if(!st[0].empty()) { t << " jst(" << st[0] << ", " << w[0] << ", enm);"; }
                 }
@@ -237,9 +234,7 @@ namespace pe_b200
             static std::string long_dot_text(rop const& o, std::vector<std::string> const& x, std::vector<std::string> const& ld, std::string const& w, std::string const& st)
             {
                 std::ostringstream t;
-                bool const guard{(o.flags & PE_F_GUARD) != 0u};
                 t << "jv " << w << " = jzero();\n";
-                if(guard) { t << "    jv gs_" << w << " = jzero(), gp_" << w << " = jzero();\n"; }
                 struct term
                 {
                     int kind;  // 0 add, 1 sub, 2 fms, 3 fma, 4 mul
@@ -274,13 +269,11 @@ namespace pe_b200
                         t << " " << fn[terms[k].kind] << "(" << w << ", " << x[terms[k].a];
                         if(terms[k].kind == 2 || terms[k].kind == 3) { t << ", " << x[terms[k].b]; }
                         t << ");";
-                        if(guard && terms[k].kind < 2 && k + 1 == o.sre.size()) { t << " jgabs(gs_" << w << ", gp_" << w << ", " << w << ");"; }
-                        if(guard && (terms[k].kind == 2 || terms[k].kind == 3)) { t << " jgmax(gp_" << w << ", " << x[terms[k].a] << ", " << x[terms[k].b] << ");"; }
                     }
                     t << "\n        asm volatile(\"\" ::: \"memory\");  // keeps the loads of the next block behind this one\n    }\n";
                 }
                 t << "   ";
-                if(guard) { t << " jguard(" << w << ", gs_" << w << ", gp_" << w << ", guard, fm);"; }
+                if((o.flags & PE_F_SCALE) && (o.flags & PE_F_GUARD)) { t << " jguard(" << w << ", guard, fm);"; }
                 if(o.flags & PE_F_RECIP) { t << " jrcp(" << w << ", fm);"; }
                 if(!st.empty()) { t << " jst(" << st << ", " << w << ", enm);"; }
                 return t.str();

@@ -591,17 +591,14 @@ namespace pe_b200
                     std::size_t q{};
                     t << dv << w[0] << " = jzero();";
                     for(auto const s: o.sre) { t << ((s & PE_R_NEG) ? " jsub(" : " jadd(") << w[0] << ", " << x[q++] << ");"; }
-                    bool const guard{(o.flags & PE_F_GUARD) != 0u};  // pe_b200_program.h: pivot guard
-                    if(guard) { t << " { jv gs, gp; jgabs(gs, gp, " << w[0] << ");"; }
                     for(auto const& pp: o.pp)
                     {
                         bool const pos{((pp.first ^ pp.second) & PE_R_NEG) != 0u};  // -(+-a)(+-b)
                         t << (pos ? " jfma(" : " jfms(") << w[0] << ", " << x[q] << ", " << x[q + 1] << ");";
-                        if(guard) { t << " jgmax(gp, " << x[q] << ", " << x[q + 1] << ");"; }
                         q += 2;
                     }
-                    if(guard) { t << " jguard(" << w[0] << ", gs, gp, k.guard, fm); }"; }
                     if(o.flags & PE_F_SCALE) { t << " jmul(" << w[0] << ", " << x[q++] << ");"; }
+                    if((o.flags & PE_F_SCALE) && (o.flags & PE_F_GUARD)) { t << " jguard(" << w[0] << ", k.guard, fm);"; }  // pe_b200_program.h: an entry of L out of bounds
                     if(o.flags & PE_F_RECIP) { t << " jrcp(" << w[0] << ", fm);"; }
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }

@@ -2,8 +2,8 @@
 
 The elimination order is static: chosen once, on the first instance's values.  Eigen's SparseLU, which the reference calls,
 re-pivots in every solve (include/Eigen/src/SparseLU/SparseLU_pivotL.h:76-107), so an instance whose values make a pivot of that
-order vanish is still solved there.  Here such an instance trips the device-side pivot guard and is solved again in a
-sub-batch whose order is chosen on ITS values.  These tests sweep a transformer ratio (the pivot of the nominal order is the
+order vanish is still solved there.  Here such an instance trips the device-side pivot guard (an entry of L more than 2^20
+times an entry of its column's pivot) and is solved again in a sub-batch whose order is chosen on ITS values.  These tests sweep a transformer ratio (the pivot of the nominal order is the
 ratio itself) through tiny values and zero and compare every instance with the compiled reference -- OP, a transient that is
 continued by a second analyze(), an AC sweep -- and check what the guard costs where it is not needed (guard elision).
 """
@@ -110,18 +110,19 @@ def test_ratio_sweep_ac(ref, abi):  # noqa: F811
 
 def test_guard_elision_and_its_limits(abi):  # noqa: F811
     # rows that carry only positive conductances need no guard (symmetric, diagonally dominant: growth <= 2 in any order):
-    # of the 102 pivots of a 100-section RC ladder only the source's two keep it -- the hot loop of config B pays nothing
+    # of the 102 pivots of a 100-section RC ladder only the source's keep it, and only one of those has a column of L to test --
+    # the hot loop of config B pays nothing
     nl, info = wl.rc_ladder(100)
     c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.TR)
     c.set_tr(1e-8, 3e-8)
     b = c.batch(5)
     assert b.analyze(), c.abi.last_error()
-    assert b.rescue_info(1)["guarded_pivots"] == 2
+    assert b.rescue_info(1)["guarded_pivots"] == 1
     # a negative resistance takes the argument away: every pivot is guarded again
     b.set_param(info["R"][3], "r", np.array([1e3, 1e3, -1e3, 1e3, 1e3]))
     assert b.analyze(), c.abi.last_error()
-    assert b.rescue_info(1)["guarded_pivots"] == 102
+    assert b.rescue_info(1)["guarded_pivots"] >= 100  # every pivot that has a column of L
     # inductors put a branch row next to every node: nothing is provably safe
     nl2, _ = wl.rlc_ladder(20)
     c2 = pe.Circuit(nl2, abi)
