@@ -278,6 +278,7 @@ def main():
     pe.kernel_timing(True)
     pe.kernel_ms()
     l0 = pe.launch_count()
+    a0 = pe.aux_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     solves = 0
@@ -286,7 +287,8 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = pe.launch_count() - l0
+    launches = pe.launch_count() - l0  # solve-kernel launches (the roofline's unit)
+    aux_launches = pe.aux_launch_count() - a0  # + one status-reduction kernel per analyze()
     kernel_ms = pe.kernel_ms()
     pe.kernel_timing(False)
     clocks = sampler.stop() if sampler else None
@@ -420,7 +422,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(args), "working_set_gb": 8e-9 * n_inst * (st["n_inst_slots"] + (rinfo["smem_slots"] if rinfo["hbm"] else st["n_lane_slots"])),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches + aux_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "program": st, "resident": b.resident_info(pe.MODE_TR), "specialised_kernel": bool(specialised), "stream_kernel": b.stream_info(pe.MODE_TR) if streamed else None, "checksum": checksum,
         }
         emit_line(line)

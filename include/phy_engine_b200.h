@@ -277,7 +277,8 @@ extern "C"
      * circuit_batch_set_tuning */
     int phy_engine_b200_set_default_path(int streams, int instances_per_cta, int instances_per_thread, int subtree_warps, int workspace, unsigned tuning);
     int phy_engine_b200_device_count(void);
-    uint64_t phy_engine_b200_launch_count(void);
+    uint64_t phy_engine_b200_launch_count(void);     /* solve-kernel launches of this process */
+    uint64_t phy_engine_b200_aux_launch_count(void); /* launches of the small helper kernels (status reduction) */
     /* device-side timing of the solve kernels (CUDA events on the launching stream): enable, then read-and-reset the
      * accumulated milliseconds (waits for the launches to finish) */
     void phy_engine_b200_timing(int on);

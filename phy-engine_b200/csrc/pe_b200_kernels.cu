@@ -1237,8 +1237,33 @@ namespace
         out[(int64_t)cmp * LS + lane] = va >= vb ? 1 : 0;
     }
 
+    __global__ void pe_b200_status_reduce_kernel(int32_t const* __restrict__ status, uint32_t const* __restrict__ solves, int64_t n, unsigned long long* __restrict__ out)
+    {
+        unsigned long long bad = 0, sing = 0, sum = 0;
+        for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        {
+            int32_t const s = status[i];
+            bad += s != PE_ST_OK;
+            sing += s == PE_ST_SINGULAR;
+            sum += solves[i];
+        }
+#pragma unroll
+        for(int d = 16; d > 0; d >>= 1)
+        {
+            bad += __shfl_down_sync(0xffffffffu, bad, d);
+            sing += __shfl_down_sync(0xffffffffu, sing, d);
+            sum += __shfl_down_sync(0xffffffffu, sum, d);
+        }
+        if((threadIdx.x & 31u) == 0u)
+        {
+            if(bad) { atomicAdd(out, bad); }
+            if(sing) { atomicAdd(out + 1, sing); }
+            if(sum) { atomicAdd(out + 2, sum); }
+        }
+    }
+
     thread_local char g_err[256] = "";
-    std::atomic<uint64_t> g_launches{0};
+    std::atomic<uint64_t> g_launches{0}, g_aux_launches{0};
 
     // optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the roofline line
     std::atomic<bool> g_timing{false};
@@ -1668,6 +1693,16 @@ extern "C"
         return chk(cudaGetLastError(), "pe_b200_compare_kernel launch");
     }
 
+    int pe_b200_status_reduce(int32_t const* status, uint32_t const* solves, int64_t n_lanes, unsigned long long* out3, void* stream)
+    {
+        if(chk(cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream), "status reduce: zero") != 0) { return 1; }
+        if(n_lanes <= 0) { return 0; }
+        unsigned const grid = (unsigned)std::min<int64_t>((n_lanes + 255) / 256, 148 * 8);
+        pe_b200_status_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(status, solves, n_lanes, out3);
+        g_aux_launches.fetch_add(1);
+        return chk(cudaGetLastError(), "pe_b200_status_reduce_kernel launch");
+    }
+
     void pe_b200_timing_enable(int on) { g_timing = on != 0; }
 
     // total device time (ms) of the solve-kernel launches since the last collect; waits for them to finish
@@ -1693,5 +1728,6 @@ extern "C"
     char const* pe_b200_dev_last_error(void) { return g_err; }
 
     uint64_t pe_b200_launch_count(void) { return g_launches.load(); }
+    uint64_t pe_b200_aux_launch_count(void) { return g_aux_launches.load(); }
 }
 #endif  // PE_JIT

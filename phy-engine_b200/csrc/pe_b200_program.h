@@ -292,6 +292,9 @@ extern "C"
     // analog -> digital boundary: out[c * LS + lane] = (x[a_c][lane] >= x[b_c][lane]) for the comparators c (ab = pairs of
     // unknown indices, -1 = ground = 0 V), x = lane-interleaved solution rows x[unknown * LS + lane]
     int pe_b200_compare(double const* x, int64_t LS, int32_t n_lanes, int32_t const* ab, int32_t n_cmp, uint8_t* out, void* stream);
+    // out[0] = lanes whose status is not PE_ST_OK, out[1] = lanes marked PE_ST_SINGULAR, out[2] = sum of the solve counters (device
+    // memory, 3 x uint64, zeroed by the call): a batch of a million lanes reads back 24 bytes instead of 8 MB when nothing failed
+    int pe_b200_status_reduce(int32_t const* status, uint32_t const* solves, int64_t n_lanes, unsigned long long* out3, void* stream);
     int pe_b200_launch_resident(pe_b200_rrun const* run, void* stream);
     // specialised tree-streaming kernel (host/jit.cpp): the same launch with the kernel taken from a cubin (loaded once
     // per process, device and key); geometry J = 4 only
@@ -349,7 +352,8 @@ extern "C"
     size_t pe_b200_resident_smem_limit(void);
     char const* pe_b200_dev_last_error(void);
     // number of kernels this library has launched so far in this process (bench.py's gpu_launches evidence)
-    uint64_t pe_b200_launch_count(void);
+    uint64_t pe_b200_launch_count(void);      // solve-kernel launches
+    uint64_t pe_b200_aux_launch_count(void);  // launches of the small helper kernels (status reduction)
     void pe_b200_timing_enable(int on);
     double pe_b200_timing_collect(void);
 

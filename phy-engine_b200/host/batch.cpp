@@ -721,7 +721,54 @@ namespace pe_b200
         auto run_ac = [&]() -> bool
         {
             auto const& a{(ac.points > 0 || ac.omega != 0.0) ? ac : parent->ac};
+            auto same_sweep = [](ac_setting const& x, ac_setting const& y)
+            { return x.sweep == y.sweep && x.omega == y.omega && x.omega_start == y.omega_start && x.omega_stop == y.omega_stop && x.points == y.points; };
+            // an unchanged sweep keeps its table (host and device): building 1e6 points sequentially, replicating and uploading
+            // them from pageable memory costs as much as a third of the solve itself
+            bool const table_cached{lane_omegas.empty() && !ac_omegas.empty() && om_ptr != nullptr && same_sweep(om_key, a) && om_first == ac_slice_first && om_count == ac_slice_count && om_n_inst == n_inst};
+            if(table_cached)
+            {
+                std::size_t const P{ac_omegas.size()};
+                std::size_t const lanes{n_inst * P};
+                std::int64_t const LSl{round_up32(lanes)};
+                auto const& pr{cc->prog[static_cast<int>(prog_mode::AC)]};
+                auto* const dst{static_cast<double*>(d_wl.p) + static_cast<std::int64_t>(pr.omega_slot) * LSl};
+                if(d_wl.p != nullptr && static_cast<void*>(dst) == om_ptr && d_wl.bytes >= static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double) &&
+                   d_status.bytes >= static_cast<std::size_t>(LSl) * 4 && d_solves.bytes >= static_cast<std::size_t>(LSl) * 4)
+                {
+                    if(pe_b200_dev_memset0(d_status.p, d_status.bytes, stream) != 0 || pe_b200_dev_memset0(d_solves.p, d_solves.bytes, stream) != 0)
+                    {
+                        return dev_fail(error, "zero status");
+                    }
+                    last_points = P;
+                    last_points_hint = P;
+                    return run_phase(prog_mode::AC, false, false, 1, false, 0.0, parent->tr.t_step, lanes, static_cast<int>(P));
+                }
+            }
+            om_ptr = nullptr;
             ac_omegas.clear();
+            if(!lane_omegas.empty())
+            {
+                // sub-batch of the pivot safety net: every "instance" is one flagged frequency point with its own omega
+                if(lane_omegas.size() != n_inst)
+                {
+                    error = "per-lane omegas: size mismatch";
+                    set_last_error(error);
+                    return false;
+                }
+                std::size_t const lanes{n_inst};
+                std::int64_t const LSl{round_up32(lanes)};
+                auto const& pr{cc->prog[static_cast<int>(prog_mode::AC)]};
+                if(!d_wl.ensure(static_cast<std::size_t>(std::max(pr.n_lane_slots, 1)) * static_cast<std::size_t>(LSl) * sizeof(double))) { return dev_fail(error, "alloc lane workspace"); }
+                auto* dst{static_cast<double*>(d_wl.p) + static_cast<std::int64_t>(pr.omega_slot) * LSl};
+                if(pe_b200_dev_h2d(dst, lane_omegas.data(), lanes * sizeof(double), stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "upload omega"); }
+                if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
+                if(pe_b200_dev_memset0(d_status.p, d_status.bytes, stream) != 0 || pe_b200_dev_memset0(d_solves.p, d_solves.bytes, stream) != 0) { return dev_fail(error, "zero status"); }
+                ac_omegas.push_back(lane_omegas[0]);
+                last_points = 1;
+                last_points_hint = 1;
+                return run_phase(prog_mode::AC, false, false, 1, false, 0.0, parent->tr.t_step, lanes, 1);
+            }
             if(a.sweep == sweep_type::single || a.points <= 1) { ac_omegas.push_back(a.omega); }
             else if(a.sweep == sweep_type::linear)
             {
@@ -767,6 +814,11 @@ namespace pe_b200
             auto* dst{static_cast<double*>(d_wl.p) + static_cast<std::int64_t>(pr.omega_slot) * LSl};
             if(pe_b200_dev_h2d(dst, om.data(), lanes * sizeof(double), stream) != 0) { return dev_fail(error, "upload omega"); }
             if(pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "sync"); }  // `om` is pageable host memory
+            om_key = a;
+            om_first = ac_slice_first;
+            om_count = ac_slice_count;
+            om_n_inst = n_inst;
+            om_ptr = dst;
             // the AC phase re-uses status/solves with `lanes` entries
             if(!d_status.ensure(static_cast<std::size_t>(LSl) * 4) || !d_solves.ensure(static_cast<std::size_t>(LSl) * 4)) { return dev_fail(error, "alloc status"); }
             if(pe_b200_dev_memset0(d_status.p, d_status.bytes, stream) != 0 || pe_b200_dev_memset0(d_solves.p, d_solves.bytes, stream) != 0)
@@ -849,8 +901,24 @@ namespace pe_b200
         }
         if(!ok) { return false; }
 
-        // one host sync per analyze(): status + solve counters
+        // one host sync per analyze(): three counters reduced on the device; the per-lane arrays travel only when a lane failed
+        // (a sweep of a million points would read back 8 MB to learn that nothing happened)
+        unsigned long long red[3]{};
+        if(!d_red.ensure(sizeof(red)) ||
+           pe_b200_status_reduce(static_cast<std::int32_t const*>(d_status.p), static_cast<std::uint32_t const*>(d_solves.p), static_cast<std::int64_t>(last_lanes),
+                                 static_cast<unsigned long long*>(d_red.p), stream) != 0 ||
+           pe_b200_dev_d2h(red, d_red.p, sizeof(red), stream) != 0 || pe_b200_dev_sync(stream) != 0)
+        {
+            return dev_fail(error, "reduce status");
+        }
+        total_solves = op_solves;
         st.assign(last_lanes, 0);
+        if(red[0] == 0 && rescues.empty())
+        {
+            sv.clear();  // fetched on demand (get_solves)
+            total_solves += red[2];
+            return true;
+        }
         sv.assign(last_lanes, 0);
         if(pe_b200_dev_d2h(st.data(), d_status.p, last_lanes * 4, stream) != 0 || pe_b200_dev_d2h(sv.data(), d_solves.p, last_lanes * 4, stream) != 0 ||
            pe_b200_dev_sync(stream) != 0)
@@ -859,29 +927,34 @@ namespace pe_b200
             sv.clear();
             return dev_fail(error, "download status");
         }
-        total_solves = op_solves;
         return true;
     }
 
     // The pivot safety net (pe_host.hpp): lanes the guard flagged are solved again in sub-batches ordered on their own values.
+    // The unit is the LANE: an instance of a real-valued analysis, one (instance, frequency point) of an AC sweep -- a sweep of a
+    // million points with a few bad ones re-runs those few, each as a one-point "instance" of the sub-batch with its own omega.
     bool batch::run_rescues(std::vector<std::int32_t>& st, std::vector<std::uint32_t>& sv, bool fresh_state)
     {
         std::size_t const P{st.size() / n_inst};  // lanes per instance (points of an AC sweep, else 1)
         if(P == 0 || P * n_inst != st.size()) { return true; }
-        std::vector<char> taken(n_inst, 0);
-        auto merge = [&](rescue_set const& rs)
+        std::vector<char> taken(st.size(), 0);
+        auto merge = [&](rescue_set& rs)
         {
-            auto const& sb{*rs.b};
-            if(sb.last_status.size() != rs.inst.size() * P) { return; }
+            auto& sb{*rs.b};
+            if(sb.last_status.size() != rs.inst.size()) { return; }
+            if(sb.last_solves.size() != sb.last_status.size())
+            {
+                // every lane of the sub-batch was fine: its counters were reduced on the device, the per-lane ones are fetched here
+                std::vector<std::uint32_t> fetched(sb.last_status.size(), 0);
+                if(!sb.get_solves(fetched.data())) { return; }
+                sb.last_solves = std::move(fetched);
+            }
             for(std::size_t k{}; k < rs.inst.size(); ++k)
             {
-                if(!rs.owned[k]) { continue; }
+                if(!rs.owned[k] || rs.inst[k] >= st.size()) { continue; }
                 taken[rs.inst[k]] = 1;
-                for(std::size_t p{}; p < P; ++p)
-                {
-                    st[rs.inst[k] * P + p] = sb.last_status[k * P + p];
-                    sv[rs.inst[k] * P + p] = sb.last_solves[k * P + p];
-                }
+                st[rs.inst[k]] = sb.last_status[k];
+                sv[rs.inst[k]] = sb.last_solves[k];
             }
         };
         // lanes that moved to a sub-batch in an earlier call continue there (a transient keeps its state in the sub-batch)
@@ -899,19 +972,9 @@ namespace pe_b200
             merge(rs);
         }
         std::vector<std::size_t> F;
-        std::size_t first_lane{};
-        for(std::size_t i{}; i < n_inst; ++i)
+        for(std::size_t l{}; l < st.size(); ++l)
         {
-            if(taken[i]) { continue; }
-            for(std::size_t p{}; p < P; ++p)
-            {
-                if(st[i * P + p] == PE_ST_SINGULAR)
-                {
-                    if(F.empty()) { first_lane = i * P + p; }
-                    F.push_back(i);
-                    break;
-                }
-            }
+            if(!taken[l] && st[l] == PE_ST_SINGULAR) { F.push_back(l); }
         }
         if(F.empty()) { return true; }
         stat_guard_trips += F.size();
@@ -919,6 +982,21 @@ namespace pe_b200
         if((at == analyze_type::TR || at == analyze_type::TROP) && !fresh_state) { return true; }  // the state the transient continues from is gone
         bool const nonlin{parent->nl.has_nonlinear()};
         static double const nl_table[3]{1.0, 1e-3, 1e-6};
+        // rows that live on the device only (circuit_batch_set_params fast path) are fetched once
+        std::map<sweep_key, std::vector<double>> fetched_rows;
+        for(auto const& [key, v]: sweeps)
+        {
+            if(v.size() >= n_inst) { continue; }
+            auto const it{cc->swept_slot.find(key)};
+            if(it == cc->swept_slot.end()) { continue; }
+            auto& row{fetched_rows[key]};
+            row.resize(n_inst);
+            if(pe_b200_dev_d2h(row.data(), static_cast<double const*>(d_wi.p) + static_cast<std::int64_t>(it->second) * LSi, n_inst * sizeof(double), stream) != 0 ||
+               pe_b200_dev_sync(stream) != 0)
+            {
+                return dev_fail(error, "download parameter row");
+            }
+        }
         for(int round{1}; round <= rescue_rounds && !F.empty(); ++round)
         {
             bool const last{round == rescue_rounds};
@@ -934,38 +1012,35 @@ namespace pe_b200
             sb.pivot_guard = last ? 0.0 : pivot_guard;
             sb.guard_all = guard_all;
             sb.nl_nominal = (nonlin && !last) ? nl_table[(round - 1) % 3] : nl_nominal;
-            sb.ac = ac;
-            sb.ac_slice_first = ac_slice_first;
-            sb.ac_slice_count = ac_slice_count;
             sb.probes = probes;
-            if(last_cplx && !ac_omegas.empty()) { sb.omega0_override = std::fabs(ac_omegas[first_lane % P]); }
+            if(last_cplx && !ac_omegas.empty())
+            {
+                // one frequency point per unit; the order is chosen at the first flagged point's omega
+                sb.lane_omegas.resize(F.size());
+                for(std::size_t k{}; k < F.size(); ++k) { sb.lane_omegas[k] = ac_omegas[F[k] % P]; }
+                sb.omega0_override = std::fabs(sb.lane_omegas[0]);
+                sb.ac.sweep = sweep_type::single;
+                sb.ac.omega = sb.lane_omegas[0];
+                sb.ac.points = 1;
+            }
             for(auto const& [key, v]: sweeps)
             {
                 auto& dst{sb.sweeps[key]};
                 dst.resize(F.size());
-                if(v.size() >= n_inst)
+                auto const fr{fetched_rows.find(key)};
+                auto const& src{fr != fetched_rows.end() ? fr->second : v};
+                if(src.size() >= n_inst)
                 {
-                    for(std::size_t k{}; k < F.size(); ++k) { dst[k] = v[F[k]]; }
-                    continue;
+                    for(std::size_t k{}; k < F.size(); ++k) { dst[k] = src[F[k] / P]; }
                 }
-                // the row lives on the device only (circuit_batch_set_params fast path)
-                auto const it{cc->swept_slot.find(key)};
-                if(it == cc->swept_slot.end())
+                else
                 {
-                    std::fill(dst.begin(), dst.end(), v.empty() ? 0.0 : v[0]);
-                    continue;
+                    std::fill(dst.begin(), dst.end(), src.empty() ? 0.0 : src[0]);
                 }
-                std::vector<double> row(n_inst);
-                if(pe_b200_dev_d2h(row.data(), static_cast<double const*>(d_wi.p) + static_cast<std::int64_t>(it->second) * LSi, n_inst * sizeof(double), stream) != 0 ||
-                   pe_b200_dev_sync(stream) != 0)
-                {
-                    return dev_fail(error, "download parameter row");
-                }
-                for(std::size_t k{}; k < F.size(); ++k) { dst[k] = row[F[k]]; }
             }
             (void)sb.analyze();
             ++stat_rescue_launches;
-            if(sb.last_status.size() != F.size() * P)
+            if(sb.last_status.size() != F.size())
             {
                 error = "rescue batch: " + sb.error;
                 set_last_error(error);
@@ -975,26 +1050,13 @@ namespace pe_b200
             std::vector<std::size_t> next;
             for(std::size_t k{}; k < F.size(); ++k)
             {
-                bool bad{false};
-                for(std::size_t p{}; p < P; ++p) { bad = bad || sb.last_status[k * P + p] == PE_ST_SINGULAR; }
-                if(last || !bad)
+                if(last || sb.last_status[k] != PE_ST_SINGULAR)
                 {
                     rs.owned[k] = 1;
                     ++(last ? stat_unguarded : stat_rescued);
                 }
                 else
                 {
-                    if(next.empty())
-                    {
-                        for(std::size_t p{}; p < P; ++p)
-                        {
-                            if(sb.last_status[k * P + p] == PE_ST_SINGULAR)
-                            {
-                                first_lane = F[k] * P + p;
-                                break;
-                            }
-                        }
-                    }
                     next.push_back(F[k]);
                 }
             }
@@ -1034,9 +1096,9 @@ namespace pe_b200
             last_solves = sv;
             return launched;
         }
-        if(!is_rescue && pivot_guard > 0.0 && !run_rescues(st, sv, fresh_state)) { return false; }
+        if(!sv.empty() && !is_rescue && pivot_guard > 0.0 && !run_rescues(st, sv, fresh_state)) { return false; }
         bool all_ok{true};
-        for(std::size_t i{}; i < st.size(); ++i)
+        for(std::size_t i{}; i < sv.size(); ++i)  // empty: every lane is fine and total_solves already holds the device's sum
         {
             total_solves += sv[i];
             if(st[i] != PE_ST_OK) { all_ok = false; }
@@ -1094,11 +1156,12 @@ namespace pe_b200
         // rows of the lanes a rescue sub-batch owns (pivot safety net)
         for(auto const& rs: rescues)
         {
+            if(!rs.b->lane_omegas.empty()) { continue; }  // units of an AC sub-batch are frequency points: see get_ac_solution
             std::vector<double> sx(rs.inst.size() * n);
             if(!rs.b->get_solution(sx.data())) { return false; }
             for(std::size_t k{}; k < rs.inst.size(); ++k)
             {
-                if(rs.owned[k]) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * n), x + rs.inst[k] * n); }
+                if(rs.owned[k] && rs.inst[k] < n_inst) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * n), x + rs.inst[k] * n); }
             }
         }
         return true;
@@ -1118,11 +1181,12 @@ namespace pe_b200
         for(auto const& rs: rescues)
         {
             std::size_t const m{rs.inst.size()};
+            if(!rs.b->lane_omegas.empty()) { continue; }
             std::vector<double> sx(m * n);
             if(!rs.b->get_solution_soa(sx.data())) { return false; }
             for(std::size_t k{}; k < m; ++k)
             {
-                if(!rs.owned[k]) { continue; }
+                if(!rs.owned[k] || rs.inst[k] >= n_inst) { continue; }
                 for(std::size_t j{}; j < n; ++j) { x[j * n_inst + rs.inst[k]] = sx[j * m + k]; }
             }
         }
@@ -1149,15 +1213,14 @@ namespace pe_b200
         {
             for(std::size_t l{}; l < lanes; ++l) { x[l * 2 * n + j] = tmp[j * lanes + l]; }
         }
-        std::size_t const P{std::max<std::size_t>(last_points, 1)};
         for(auto const& rs: rescues)
         {
-            if(!rs.b->last_cplx || rs.b->last_lanes != rs.inst.size() * P) { continue; }
+            if(!rs.b->last_cplx || rs.b->last_lanes != rs.inst.size()) { continue; }
             std::vector<double> sx(rs.b->last_lanes * 2 * n);
             if(!rs.b->get_ac_solution(sx.data())) { return false; }
             for(std::size_t k{}; k < rs.inst.size(); ++k)
             {
-                if(rs.owned[k]) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * P * 2 * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * P * 2 * n), x + rs.inst[k] * P * 2 * n); }
+                if(rs.owned[k] && rs.inst[k] < lanes) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(k * 2 * n), sx.begin() + static_cast<std::ptrdiff_t>((k + 1) * 2 * n), x + rs.inst[k] * 2 * n); }
             }
         }
         return true;
@@ -1224,7 +1287,7 @@ namespace pe_b200
         for(auto const& rs: rescues)
         {
             std::size_t const m{rs.inst.size()};
-            if(rs.b->wave_steps != wave_steps || rs.b->probes.size() != probes.size()) { continue; }
+            if(rs.b->wave_steps != wave_steps || rs.b->probes.size() != probes.size() || !rs.b->lane_omegas.empty()) { continue; }
             std::vector<double> sw(rows * m);
             if(!rs.b->get_wave(sw.data())) { continue; }
             for(std::size_t k{}; k < m; ++k)
@@ -1298,7 +1361,9 @@ namespace pe_b200
         put(out, static_cast<std::uint64_t>(rows));
         put(out, tr_duration);
         put(out, last_step);
-        put(out, static_cast<std::uint64_t>(rescues.size()));
+        std::uint64_t n_sets{};
+        for(auto const& rs: rescues) { n_sets += rs.b->lane_omegas.empty() ? 1u : 0u; }  // AC sub-batches (frequency points) keep no state
+        put(out, n_sets);
         std::size_t const at{out.size()};
         out.resize(at + rows * n_inst * sizeof(double));
         if(rows != 0 && (pe_b200_dev_d2h_2d(out.data() + at, n_inst * sizeof(double), d_wi.p, static_cast<std::size_t>(LSi) * sizeof(double), n_inst * sizeof(double), rows, stream) != 0 ||
@@ -1308,6 +1373,7 @@ namespace pe_b200
         }
         for(auto& rs: rescues)
         {
+            if(!rs.b->lane_omegas.empty()) { continue; }
             put(out, static_cast<std::uint64_t>(rs.inst.size()));
             for(std::size_t k{}; k < rs.inst.size(); ++k)
             {

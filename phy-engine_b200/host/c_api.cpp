@@ -1182,6 +1182,7 @@ extern "C"
     int phy_engine_b200_device_count(void) { return pe_b200_dev_count(); }
 
     uint64_t phy_engine_b200_launch_count(void) { return pe_b200_launch_count(); }
+    uint64_t phy_engine_b200_aux_launch_count(void) { return pe_b200_aux_launch_count(); }
 
     void phy_engine_b200_timing(int on) { pe_b200_timing_enable(on); }
 

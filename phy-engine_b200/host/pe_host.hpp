@@ -336,7 +336,7 @@ namespace pe_b200
         bool device_stale{true};    // host program newer than what the device holds
         bool layout_pending{true};  // INST layout changed since the device workspace was sized
 
-        device_buf d_wi, d_wl, d_cst, d_status, d_solves, d_wave, d_probes;
+        device_buf d_wi, d_wl, d_cst, d_status, d_solves, d_wave, d_probes, d_red;
         std::array<device_buf, static_cast<int>(prog_mode::COUNT)> d_words;
         std::array<bool, static_cast<int>(prog_mode::COUNT)> uploaded{};
         int subtree_warps{0};  // 0 = choose from the lane count; else the requested G (power of two, <= PE_MAX_WARPS)
@@ -374,6 +374,10 @@ namespace pe_b200
         bool last_cplx{};
         std::int64_t last_LSl{};
         std::vector<double> ac_omegas;  // per point
+        // the omega table on the device is kept while the sweep, the slice, the instance count and the buffer stay the same
+        ac_setting om_key{};
+        std::size_t om_first{}, om_count{}, om_n_inst{};
+        void* om_ptr{};
         std::uint64_t total_solves{};
         double tr_duration{};
         double last_step{};
@@ -398,11 +402,12 @@ namespace pe_b200
         bool guard_all{}, cc_guard_all{};  // compile with the guard on every pivot (set when a non-positive R / C value is seen)
         double nl_nominal{};     // > 0: ordering conductance of not-yet-evaluated non-linear devices (rescue rounds vary it)
         double omega0_override{};  // > 0: omega the AC order is chosen on
+        std::vector<double> lane_omegas;  // sub-batch of flagged frequency points: one omega per "instance" (one point each)
         std::uint64_t sweeps_rev{1};  // bumped by every per-instance parameter write
         struct rescue_set
         {
             std::unique_ptr<batch> b;
-            std::vector<std::size_t> inst;   // sub-batch instance k = instance inst[k] of this batch
+            std::vector<std::size_t> inst;   // sub-batch instance k = LANE inst[k] of this batch (an instance; one point of an AC sweep)
             std::vector<char> owned;         // [k]: its results replace this batch's
         };
         std::vector<rescue_set> rescues;

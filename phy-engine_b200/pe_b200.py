@@ -281,6 +281,7 @@ def bind_full_abi(abi: CAbi) -> CAbi:
     lib.circuit_batch_swept_values.argtypes = [V, ct.c_longlong, _PD]
     lib.phy_engine_b200_device_count.restype = ct.c_int
     lib.phy_engine_b200_launch_count.restype = ct.c_uint64
+    lib.phy_engine_b200_aux_launch_count.restype = ct.c_uint64
     lib.phy_engine_b200_timing.restype = None
     lib.phy_engine_b200_timing.argtypes = [ct.c_int]
     lib.phy_engine_b200_kernel_ms.restype = ct.c_double
@@ -293,6 +294,10 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(product().lib.phy_engine_b200_launch_count())
+
+
+def aux_launch_count() -> int:
+    return int(product().lib.phy_engine_b200_aux_launch_count())
 
 
 def kernel_timing(on: bool) -> None:

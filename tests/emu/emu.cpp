@@ -69,7 +69,7 @@ namespace
 {
     using namespace pe_interp;
     char g_err[256] = "";
-    uint64_t g_launches = 0;
+    uint64_t g_launches = 0, g_aux_launches = 0;
     uint64_t g_unbalanced = 0;
 
     // one section for one lane: the G warp streams advance phase by phase (a phase ends at PE_OP_BAR / PE_OP_END)
@@ -148,6 +148,7 @@ extern "C"
     }
     char const* pe_b200_dev_last_error(void) { return g_err; }
     uint64_t pe_b200_launch_count(void) { return g_launches; }
+    uint64_t pe_b200_aux_launch_count(void) { return g_aux_launches; }
     void pe_b200_timing_enable(int) {}
     double pe_b200_timing_collect(void) { return 0.0; }
 
@@ -165,6 +166,19 @@ extern "C"
             }
         }
         ++g_launches;
+        return 0;
+    }
+
+    int pe_b200_status_reduce(int32_t const* status, uint32_t const* solves, int64_t n_lanes, unsigned long long* out3, void*)
+    {
+        out3[0] = out3[1] = out3[2] = 0;
+        for(int64_t i = 0; i < n_lanes; ++i)
+        {
+            out3[0] += status[i] != PE_ST_OK;
+            out3[1] += status[i] == PE_ST_SINGULAR;
+            out3[2] += solves[i];
+        }
+        ++g_aux_launches;
         return 0;
     }
 

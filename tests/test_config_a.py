@@ -123,8 +123,13 @@ def test_config_a_full_size(ref):
     mag[vp] += abs(i_src)
     mag[vq] += abs(i_src)
     assert np.abs(x[vp] - x[vq] - 3.0) < 1e-12  # the source row
-    kcl = float((np.abs(net) / np.maximum(mag, 1e-300)).max())
-    assert kcl <= 1e-9, kcl
+    # Resistances from U(1e-5, 1e5) Ohm: a node between micro-ohm resistors sees currents that are differences of nearly equal
+    # voltages, so its OWN balance cannot be better than eps * |v| / r.  The reference's solution of this netlist gives: worst
+    # node 1.4e-5 of the node's currents, normwise (worst imbalance over the largest current) 4.2e-10, median node 5.5e-12,
+    # 99 % of the nodes below 1.5e-9 (measured with oracle/_ref, 126 s).  The bars below are what a backward-stable solve meets.
+    rel = np.abs(net) / np.maximum(mag, 1e-300)
+    assert float(np.abs(net).max() / mag.max()) <= 1e-9, float(np.abs(net).max() / mag.max())
+    assert float(np.median(rel)) <= 1e-10 and float(np.quantile(rel, 0.99)) <= 1e-8, (float(np.median(rel)), float(np.quantile(rel, 0.99)), float(rel.max()))
     # (2) the reference's own solution of the same netlist (Eigen SparseLU on one host core: ~1.5 minutes).  Resistances
     # drawn from U(1e-5, 1e5) Ohm make the system ill-conditioned (kappa ~ 1e10): two backward-stable
     # solvers agree to ~kappa * eps relative to the LARGEST voltage, not component by component -- nodes a few micro-ohms from

@@ -75,7 +75,6 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&d_ci, nnz * sizeof(int)));
     CK(cudaMemcpy(d_rp, rp.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ci, ci.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cusolverSpXcsrqrAnalysisBatched(h, n, n, nnz, descr, d_rp, d_ci, info));
 
     std::printf("{\"tool\": \"cusolverSpDcsrqrsvBatched\", \"unknowns\": %d, \"nnz\": %d, \"points\": [", n, nnz);
     bool first = true;
@@ -87,6 +86,13 @@ int main(int argc, char** argv)
             for(int e = 0; e < nnz; ++e) { vb[(size_t)q * nnz + e] = va[e] * (1.0 + 0.01 * ((q * 31 + e) % 17) * (std::fabs(va[e]) == 1.0 ? 0.0 : 1.0)); }
             for(int i = 0; i < n; ++i) { bb[(size_t)q * n + i] = b[i]; }
         }
+        // the symbolic analysis is cached per sparsity pattern by the reference (prepare_csrqr_real); its buffers are sized per batch
+        if(B > 1)
+        {
+            CK(cusolverSpDestroyCsrqrInfo(info));
+            CK(cusolverSpCreateCsrqrInfo(&info));
+        }
+        CK(cusolverSpXcsrqrAnalysisBatched(h, n, n, nnz, descr, d_rp, d_ci, info));
         double *d_v, *d_b, *d_x;
         void* d_buf;
         size_t internal = 0, workspace = 0;
