@@ -1067,6 +1067,10 @@ namespace pe_b200
         rescues_sweeps_rev = sweeps_rev;
         rescues_param_rev = parent->param_rev;
         rescues_structure_rev = parent->structure_rev;
+        rescues_at = parent->at;
+        rescues_ac = (ac.points > 0 || ac.omega != 0.0) ? ac : parent->ac;
+        rescues_slice_first = ac_slice_first;
+        rescues_slice_count = ac_slice_count;
         return true;
     }
 
@@ -1080,7 +1084,14 @@ namespace pe_b200
             return false;
         }
         // sub-batches of an earlier call own their lanes as long as nothing they were built from has changed
-        if(!rescues.empty() && (rescues_sweeps_rev != sweeps_rev || rescues_param_rev != parent->param_rev || rescues_structure_rev != parent->structure_rev)) { rescues.clear(); }
+        auto const& ac_now{(ac.points > 0 || ac.omega != 0.0) ? ac : parent->ac};
+        auto same_ac = [](ac_setting const& x, ac_setting const& y)
+        { return x.sweep == y.sweep && x.omega == y.omega && x.omega_start == y.omega_start && x.omega_stop == y.omega_stop && x.points == y.points; };
+        if(!rescues.empty() && (rescues_sweeps_rev != sweeps_rev || rescues_param_rev != parent->param_rev || rescues_structure_rev != parent->structure_rev || rescues_at != parent->at ||
+                                !same_ac(rescues_ac, ac_now) || rescues_slice_first != ac_slice_first || rescues_slice_count != ac_slice_count))
+        {
+            rescues.clear();  // their lanes are numbered by the analysis (points of THIS sweep) they were built in
+        }
         bool const fresh_state{tr_duration == 0.0};
         std::vector<std::int32_t> st;
         std::vector<std::uint32_t> sv;
@@ -1504,6 +1515,10 @@ namespace pe_b200
             b.rescues_sweeps_rev = b.sweeps_rev;
             b.rescues_param_rev = b.parent->param_rev;
             b.rescues_structure_rev = b.parent->structure_rev;
+            b.rescues_at = b.parent->at;
+            b.rescues_ac = (b.ac.points > 0 || b.ac.omega != 0.0) ? b.ac : b.parent->ac;
+            b.rescues_slice_first = b.ac_slice_first;
+            b.rescues_slice_count = b.ac_slice_count;
             return true;
         };
         unsigned char const* q{p};

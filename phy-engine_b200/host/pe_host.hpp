@@ -412,6 +412,9 @@ namespace pe_b200
         };
         std::vector<rescue_set> rescues;
         std::uint64_t rescues_sweeps_rev{}, rescues_param_rev{}, rescues_structure_rev{};
+        analyze_type rescues_at{};
+        ac_setting rescues_ac{};
+        std::size_t rescues_slice_first{}, rescues_slice_count{};
         std::uint64_t stat_guard_trips{}, stat_rescued{}, stat_rescue_launches{}, stat_unguarded{};
         std::vector<std::int32_t> last_status;  // merged status / solve counters of the last analyze()
         std::vector<std::uint32_t> last_solves;

@@ -146,3 +146,35 @@ def test_single_instance_abi_takes_the_same_net(ref, abi):  # noqa: F811
         c.set_analyze_type(pe.OP)
         assert c.analyze(), c.abi.last_error()
         assert_close(c.solution().real, rc.solution().real, f"single instance, n = {n}")
+
+
+def test_wide_ac_sweep_re_runs_only_the_flagged_points(ref, abi):  # noqa: F811
+    # config D's circuit over seven decades: the order is chosen at the geometric mean of the sweep, a few per cent of the
+    # points (the ends) exceed the multiplier bound and are solved again -- each as a one-point unit with its own omega and an
+    # order chosen there -- not the whole sweep of their instance
+    nl, info = wl.rlc_ladder(64)
+    sweep = (pe.SWEEP_LOG, 1e3, 1e10, 256)
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.AC)
+    b = c.batch(2)
+    b.set_ac_sweep(*sweep)
+    b.set_param(info["R"][0], "r", np.array([10.0, 12.0]))
+    assert b.analyze(), c.abi.last_error()
+    r = b.rescue_info(3)
+    assert 0 < r["flagged"] < 2 * 256 // 4 and r["rescued"] == r["flagged"] and r["unguarded"] == 0 and r["sub_batches"] == 1
+    assert (b.status() == 0).all() and (b.newton_iters() == 1).all() and b.total_solves == 2 * 256
+    got = b.ac_solution()
+    want = refapi.run_batch(nl, pe.AC, 2, [(info["R"][0], "r", np.array([10.0, 12.0]))], ac=sweep)
+    assert_close(got.real, want["x"].real, "wide sweep (re)")
+    assert_close(got.imag, want["x"].imag, "wide sweep (im)")
+    # the same sweep again: the omega table stays on the device, the sub-batch is re-used, the results are the same bits
+    assert b.analyze(), c.abi.last_error()
+    assert np.array_equal(b.ac_solution(), got)
+    r2 = b.rescue_info(3)
+    assert r2["sub_batches"] == 1 and r2["flagged"] == r["flagged"]
+    # another sweep: new table, new flags (the sub-batch of the old sweep numbers ITS points: it must go)
+    b.set_ac_sweep(pe.SWEEP_LOG, 1e5, 1e7, 64)
+    assert b.analyze(), c.abi.last_error()
+    want2 = refapi.run_batch(nl, pe.AC, 2, [(info["R"][0], "r", np.array([10.0, 12.0]))], ac=(pe.SWEEP_LOG, 1e5, 1e7, 64))
+    assert_close(b.ac_solution().real, want2["x"].real, "narrow sweep (re)")
+    assert_close(b.ac_solution().imag, want2["x"].imag, "narrow sweep (im)")
