@@ -145,28 +145,47 @@ namespace
 
     // ---- blocked right-looking LU without pivoting (ld is a multiple of NB) --------------------------------------------
     // diagonal block k: in-place LU in shared memory
-    __global__ void __launch_bounds__(256) fr_lu_diag(double* __restrict__ Mall, int64_t ld, int32_t k0, int32_t* status)
+    __global__ void __launch_bounds__(NB) fr_lu_diag(double* __restrict__ Mall, int64_t ld, int32_t k0, int32_t* status)
     {
-        __shared__ double s[NB][NB + 1];
+        // thread j keeps column j of the block in registers; step k: the owner of column k publishes its multipliers, everybody
+        // to the right applies them (one barrier pair per step, 64 - k FMAs per thread: ~10 us per block instead of 80)
+        __shared__ double lk[NB];
         double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
-        int const tid = threadIdx.x;
-        for(int e = tid; e < NB * NB; e += 256) { s[e % NB][e / NB] = M[(k0 + e % NB) + (int64_t)(k0 + e / NB) * ld]; }
-        __syncthreads();
+        int const j = threadIdx.x;
+        double col[NB];
+#pragma unroll
+        for(int i = 0; i < NB; ++i) { col[i] = M[(k0 + i) + (int64_t)(k0 + j) * ld]; }
+#pragma unroll
         for(int k = 0; k < NB; ++k)
         {
-            double const p = s[k][k];
-            if(tid == 0 && (p == 0.0 || !isfinite(p))) { status[blockIdx.z] = PE_ST_SINGULAR; }
-            __syncthreads();
-            for(int i = k + 1 + tid; i < NB; i += 256) { s[i][k] = s[i][k] / p; }
-            __syncthreads();
-            for(int e = tid; e < (NB - k - 1) * (NB - k - 1); e += 256)
+            if(j == k)
             {
-                int const i = k + 1 + e % (NB - k - 1), j = k + 1 + e / (NB - k - 1);
-                s[i][j] = fma(-s[i][k], s[k][j], s[i][j]);
+                double const p = col[k];
+                if(p == 0.0 || !isfinite(p)) { status[blockIdx.z] = PE_ST_SINGULAR; }
+#pragma unroll
+                for(int i = 0; i < NB; ++i)
+                {
+                    if(i > k)
+                    {
+                        col[i] = col[i] / p;
+                        lk[i] = col[i];
+                    }
+                }
+            }
+            __syncthreads();
+            if(j > k)
+            {
+                double const ukj = col[k];
+#pragma unroll
+                for(int i = 0; i < NB; ++i)
+                {
+                    if(i > k) { col[i] = fma(-lk[i], ukj, col[i]); }
+                }
             }
             __syncthreads();
         }
-        for(int e = tid; e < NB * NB; e += 256) { M[(k0 + e % NB) + (int64_t)(k0 + e / NB) * ld] = s[e % NB][e / NB]; }
+#pragma unroll
+        for(int i = 0; i < NB; ++i) { M[(k0 + i) + (int64_t)(k0 + j) * ld] = col[i]; }
     }
 
     // panels of block step k: blockIdx.x < nbl: L21 block row = A21 U11^-1, else U12 block column = L11^-1 A12
@@ -181,19 +200,24 @@ namespace
         {
             // row r of the block row below the diagonal: l_rj = (a_rj - sum_{t<j} l_rt u_tj) / u_jj
             int64_t const r = k0 + NB + (int64_t)blockIdx.x * NB + tid;
+            // all 64 loads first, all 64 stores last: interleaved, every load would wait for the store before it (the compiler
+            // cannot tell they do not alias) -- 64 serial round trips to memory per thread
             double l[NB];
+#pragma unroll
+            for(int j = 0; j < NB; ++j) { l[j] = M[r + (int64_t)(k0 + j) * ld]; }
 #pragma unroll
             for(int j = 0; j < NB; ++j)
             {
-                double v = M[r + (int64_t)(k0 + j) * ld];
+                double v = l[j];
 #pragma unroll
                 for(int t = 0; t < NB; ++t)
                 {
                     if(t < j) { v = fma(-l[t], s[t][j], v); }
                 }
                 l[j] = v / s[j][j];
-                M[r + (int64_t)(k0 + j) * ld] = l[j];
             }
+#pragma unroll
+            for(int j = 0; j < NB; ++j) { M[r + (int64_t)(k0 + j) * ld] = l[j]; }
         }
         else
         {
@@ -201,17 +225,20 @@ namespace
             int64_t const c = k0 + NB + (int64_t)(blockIdx.x - nbl) * NB + tid;
             double u[NB];
 #pragma unroll
+            for(int i = 0; i < NB; ++i) { u[i] = M[(k0 + i) + c * ld]; }
+#pragma unroll
             for(int i = 0; i < NB; ++i)
             {
-                double v = M[(k0 + i) + c * ld];
+                double v = u[i];
 #pragma unroll
                 for(int t = 0; t < NB; ++t)
                 {
                     if(t < i) { v = fma(-s[i][t], u[t], v); }
                 }
                 u[i] = v;
-                M[(k0 + i) + c * ld] = v;
             }
+#pragma unroll
+            for(int i = 0; i < NB; ++i) { M[(k0 + i) + c * ld] = u[i]; }
         }
     }
 
@@ -281,6 +308,104 @@ namespace
                         double* const p = M + (r0 + rr) + (c0 + cc) * ld;
                         *p = *p - acc[i][j][h];
                     }
+                }
+    }
+
+    // Second version of the trailing update (the first one ran at 5 of the 37 TFLOP/s the DMMA pipe sustains -- tools/micro/
+    // fp64_rate.cu -- because its epilogue was a chain of 64 dependent read-modify-write round trips per thread, C(i,j) -= acc,
+    // that the compiler may not reorder, and because the tensor pipe idled during every slab load):
+    //   * the C tile is loaded INTO the accumulators at the start (64 independent loads in flight) and the L21 fragments are
+    //     negated, so that the DMMAs compute (-L21) U12 + C and the epilogue is 64 plain stores;
+    //   * the k-slabs are double-buffered: slab s + 1 arrives by cp.async while slab s is contracted.
+    constexpr int k_upd_smem = 4 * 16 * 132 * (int)sizeof(double);
+    __device__ __forceinline__ void cp_async8(void* smem_dst, void const* src, bool valid)
+    {
+        uint32_t const d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+        int const n = valid ? 8 : 0;  // 0 source bytes: the destination is filled with zeros
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+    }
+    __global__ void __launch_bounds__(256) fr_lu_update2(double* __restrict__ Mall, int64_t ld, int32_t k0)
+    {
+        extern __shared__ double upd_smem[];
+        double(*const sa)[16][132] = reinterpret_cast<double(*)[16][132]>(upd_smem);                  // sa[buf][k][row]
+        double(*const sb)[16][132] = reinterpret_cast<double(*)[16][132]>(upd_smem + 2 * 16 * 132);  // sb[buf][k][col]
+        double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
+        int64_t const r0 = k0 + NB + (int64_t)blockIdx.x * 128, c0 = k0 + NB + (int64_t)blockIdx.y * 128;
+        int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        int const wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
+        int64_t const rr_left = ld - r0, cc_left = ld - c0;
+        int const rows_here = rr_left < 128 ? (int)rr_left : 128, cols_here = cc_left < 128 ? (int)cc_left : 128;
+        double acc[4][8][2];
+        // C fragment: row = lane / 4, columns 2 (lane % 4) + {0, 1}
+#pragma unroll
+        for(int i = 0; i < 4; ++i)
+#pragma unroll
+            for(int j = 0; j < 8; ++j)
+#pragma unroll
+                for(int h = 0; h < 2; ++h)
+                {
+                    int const rr = wr + 8 * i + (lane >> 2), cc = wc + 8 * j + 2 * (lane & 3) + h;
+                    acc[i][j][h] = (rr < rows_here && cc < cols_here) ? M[(r0 + rr) + (c0 + cc) * ld] : 0.0;
+                }
+        // one k-slab (16 columns of L21, 16 rows of U12) straight into shared memory: 8-byte cp.async, zero fill past the edge
+        auto fetch = [&](int ks, int buf)
+        {
+#pragma unroll
+            for(int q = 0; q < 8; ++q)
+            {
+                int const e = tid + 256 * q;
+                int const kk = e >> 7, rr = e & 127;
+                bool const in = rr < rows_here;
+                cp_async8(&sa[buf][kk][rr], in ? M + (r0 + rr) + (int64_t)(k0 + ks + kk) * ld : M, in);
+            }
+#pragma unroll
+            for(int q = 0; q < 8; ++q)
+            {
+                int const e = tid + 256 * q;
+                int const cc = e >> 4, kk = e & 15;
+                bool const in = cc < cols_here;
+                cp_async8(&sb[buf][kk][cc], in ? M + (k0 + ks + kk) + (c0 + cc) * ld : M, in);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fetch(0, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll 1
+        for(int sl = 0; sl < NB / 16; ++sl)
+        {
+            int const buf = sl & 1;
+            if(sl + 1 < NB / 16) { fetch((sl + 1) * 16, buf ^ 1); }  // in flight while this slab is contracted; the other buffer was last read before the barrier that ended the previous round
+#pragma unroll
+            for(int k4 = 0; k4 < 16; k4 += 4)
+            {
+                double a[4], b[8];
+#pragma unroll
+                for(int i = 0; i < 4; ++i) { a[i] = -sa[buf][k4 + (lane & 3)][wr + 8 * i + (lane >> 2)]; }  // (-L21) U12 + C
+#pragma unroll
+                for(int j = 0; j < 8; ++j) { b[j] = sb[buf][k4 + (lane & 3)][wc + 8 * j + (lane >> 2)]; }
+#pragma unroll
+                for(int i = 0; i < 4; ++i)
+#pragma unroll
+                    for(int j = 0; j < 8; ++j)
+                    {
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                     : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                                     : "d"(a[i]), "d"(b[j]));
+                    }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
+#pragma unroll
+        for(int i = 0; i < 4; ++i)
+#pragma unroll
+            for(int j = 0; j < 8; ++j)
+#pragma unroll
+                for(int h = 0; h < 2; ++h)
+                {
+                    int const rr = wr + 8 * i + (lane >> 2), cc = wc + 8 * j + 2 * (lane & 3) + h;
+                    if(rr < rows_here && cc < cols_here) { M[(r0 + rr) + (c0 + cc) * ld] = acc[i][j][h]; }
                 }
     }
 
@@ -355,6 +480,76 @@ namespace
         }
     }
 
+    // ---- the same substitutions, one block step per launch pair, so that the rows outside the diagonal block are spread over the
+    // whole GPU (fr_solve_core walks the 456 MB of a 7 552-row factor with ONE CTA: 16.5 ms; this way it is a stream of small
+    // launches: the factor is read once at HBM speed).  Arithmetic and its order per row are those of fr_solve_core.
+    // y_k = L11^-1 c_k (unit lower): the 64 x 64 block is staged in shared memory by the whole CTA (all its loads in flight at
+    // once; read from global inside the recurrence, every step waited for memory), then one warp runs the recurrence, lane i
+    // owning rows i and i + 32
+    __global__ void __launch_bounds__(256) fr_fwd_diag(double const* __restrict__ Mall, double* __restrict__ call, int64_t ld, int64_t k0)
+    {
+        __shared__ double s[NB][NB + 1];
+        double const* const M = Mall + (int64_t)blockIdx.x * ld * ld;
+        double* const c = call + (int64_t)blockIdx.x * ld;
+        int const tid = threadIdx.x;
+        for(int e = tid; e < NB * NB; e += 256) { s[e % NB][e / NB] = M[(k0 + e % NB) + (k0 + e / NB) * ld]; }
+        __syncthreads();
+        if(tid >= 32) { return; }
+        double v0 = c[k0 + tid], v1 = c[k0 + tid + 32];
+        for(int j = 0; j < NB; ++j)
+        {
+            double const yj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31);
+            if(tid > j) { v0 = fma(-s[tid][j], yj, v0); }
+            if(tid + 32 > j) { v1 = fma(-s[tid + 32][j], yj, v1); }
+        }
+        c[k0 + tid] = v0;
+        c[k0 + tid + 32] = v1;
+    }
+    // x_k = U11^-1 y_k
+    __global__ void __launch_bounds__(256) fr_bwd_diag(double const* __restrict__ Mall, double* __restrict__ call, int64_t ld, int64_t k0)
+    {
+        __shared__ double s[NB][NB + 1];
+        double const* const M = Mall + (int64_t)blockIdx.x * ld * ld;
+        double* const c = call + (int64_t)blockIdx.x * ld;
+        int const tid = threadIdx.x;
+        for(int e = tid; e < NB * NB; e += 256) { s[e % NB][e / NB] = M[(k0 + e % NB) + (k0 + e / NB) * ld]; }
+        __syncthreads();
+        if(tid >= 32) { return; }
+        double v0 = c[k0 + tid], v1 = c[k0 + tid + 32];
+        for(int j = NB - 1; j >= 0; --j)
+        {
+            double const piv = s[j][j];
+            double xj = __shfl_sync(0xffffffffu, j < 32 ? v0 : v1, j & 31) / piv;
+            if(tid == (j & 31))
+            {
+                if(j < 32) { v0 = xj; }
+                else
+                {
+                    v1 = xj;
+                }
+            }
+            if(tid < j) { v0 = fma(-s[tid][j], xj, v0); }
+            if(tid + 32 < j) { v1 = fma(-s[tid + 32][j], xj, v1); }
+        }
+        c[k0 + tid] = v0;
+        c[k0 + tid + 32] = v1;
+    }
+    // c[r] -= sum_j M[r, k0 + j] c[k0 + j] for the rows r0 <= r < r1 (below the block: forward; above it: backward)
+    __global__ void __launch_bounds__(256) fr_subst_update(double const* __restrict__ Mall, double* __restrict__ call, int64_t ld, int64_t k0, int64_t r0, int64_t r1)
+    {
+        __shared__ double y[NB];
+        double const* const M = Mall + (int64_t)blockIdx.y * ld * ld;
+        double* const c = call + (int64_t)blockIdx.y * ld;
+        if(threadIdx.x < NB) { y[threadIdx.x] = c[k0 + threadIdx.x]; }
+        __syncthreads();
+        int64_t const r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if(r >= r1) { return; }
+        double v = c[r];
+#pragma unroll 8
+        for(int j = 0; j < NB; ++j) { v = fma(-M[r + (k0 + j) * ld], y[j], v); }
+        c[r] = v;
+    }
+
     __global__ void fr_core_scatter(pe_b200_frontal const f)
     {
         int64_t const inst = blockIdx.y;
@@ -411,22 +606,56 @@ extern "C"
             if(fchk(cudaMemsetAsync(f.M, 0, sizeof(double) * (size_t)ld * (size_t)ld * (size_t)f.n_inst, st), "memset core") != 0) { return 1; }
             fr_core_assemble<<<dim3(blocks(f.n_core + f.n_core_edges + (ld - f.n_core)), (unsigned)f.n_inst), 256, 0, st>>>(f);
             ++nl;
+            static bool const update_v1 = std::getenv("PE_B200_FRONTAL_UPDATE_V1") != nullptr;  // the first trailing update, kept for A/B runs
+            if(!update_v1 && fchk(cudaFuncSetAttribute(fr_lu_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, k_upd_smem), "fr_lu_update2 shared memory") != 0) { return 1; }
             for(int64_t k0 = 0; k0 < ld; k0 += NB)
             {
-                fr_lu_diag<<<dim3(1, 1, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0, f.status);
+                fr_lu_diag<<<dim3(1, 1, (unsigned)f.n_inst), NB, 0, st>>>(f.M, ld, (int32_t)k0, f.status);
                 ++nl;
                 int64_t const rem = ld - k0 - NB;
                 if(rem <= 0) { break; }
                 int32_t const nbl = (int32_t)(rem / NB);
                 fr_lu_panel<<<dim3((unsigned)(2 * nbl), 1, (unsigned)f.n_inst), NB, 0, st>>>(f.M, ld, (int32_t)k0, nbl);
                 unsigned const tb = (unsigned)((rem + 127) / 128);
-                fr_lu_update<<<dim3(tb, tb, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0);
+                if(update_v1) { fr_lu_update<<<dim3(tb, tb, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0); }
+                else
+                {
+                    fr_lu_update2<<<dim3(tb, tb, (unsigned)f.n_inst), 256, k_upd_smem, st>>>(f.M, ld, (int32_t)k0);
+                }
                 nl += 2;
             }
             if(timing) { cudaEventRecord(ev[2], st); }
-            fr_solve_core<<<(unsigned)f.n_inst, 1024, 0, st>>>(f.M, f.c, ld);
+            static bool const one_cta_subst = std::getenv("PE_B200_FRONTAL_ONE_CTA_SUBST") != nullptr;  // the first version, kept for A/B runs
+            if(one_cta_subst)
+            {
+                fr_solve_core<<<(unsigned)f.n_inst, 1024, 0, st>>>(f.M, f.c, ld);
+                ++nl;
+            }
+            else
+            {
+                for(int64_t k0 = 0; k0 < ld; k0 += NB)
+                {
+                    fr_fwd_diag<<<(unsigned)f.n_inst, 256, 0, st>>>(f.M, f.c, ld, k0);
+                    ++nl;
+                    if(k0 + NB < ld)
+                    {
+                        fr_subst_update<<<dim3(blocks(ld - k0 - NB), (unsigned)f.n_inst), 256, 0, st>>>(f.M, f.c, ld, k0, k0 + NB, ld);
+                        ++nl;
+                    }
+                }
+                for(int64_t k0 = ld - NB; k0 >= 0; k0 -= NB)
+                {
+                    fr_bwd_diag<<<(unsigned)f.n_inst, 256, 0, st>>>(f.M, f.c, ld, k0);
+                    ++nl;
+                    if(k0 > 0)
+                    {
+                        fr_subst_update<<<dim3(blocks(k0), (unsigned)f.n_inst), 256, 0, st>>>(f.M, f.c, ld, k0, 0, k0);
+                        ++nl;
+                    }
+                }
+            }
             fr_core_scatter<<<dim3(blocks(f.n_core), (unsigned)f.n_inst), 256, 0, st>>>(f);
-            nl += 2;
+            ++nl;
         }
         for(int32_t l = f.n_levels - 1; l >= 0; --l)
         {
