@@ -147,9 +147,10 @@ namespace
     // diagonal block k: in-place LU in shared memory
     __global__ void __launch_bounds__(NB) fr_lu_diag(double* __restrict__ Mall, int64_t ld, int32_t k0, int32_t* status)
     {
-        // thread j keeps column j of the block in registers; step k: the owner of column k publishes its multipliers, everybody
-        // to the right applies them (one barrier pair per step, 64 - k FMAs per thread: ~10 us per block instead of 80)
-        __shared__ double lk[NB];
+        // thread j keeps column j of the block in registers.  Step k: the owner of column k publishes it, thread i divides row i's
+        // entry by the pivot (one division per thread, not 63 in the owner), everybody to the right applies the multipliers:
+        // two barriers and 64 - k FMAs per thread and step
+        __shared__ double raw[NB], lk[NB];
         double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
         int const j = threadIdx.x;
         double col[NB];
@@ -160,20 +161,26 @@ namespace
         {
             if(j == k)
             {
-                double const p = col[k];
-                if(p == 0.0 || !isfinite(p)) { status[blockIdx.z] = PE_ST_SINGULAR; }
 #pragma unroll
                 for(int i = 0; i < NB; ++i)
                 {
-                    if(i > k)
-                    {
-                        col[i] = col[i] / p;
-                        lk[i] = col[i];
-                    }
+                    if(i >= k) { raw[i] = col[i]; }
                 }
             }
             __syncthreads();
-            if(j > k)
+            double const p = raw[k];
+            if(j == k && (p == 0.0 || !isfinite(p))) { status[blockIdx.z] = PE_ST_SINGULAR; }
+            if(j > k) { lk[j] = raw[j] / p; }
+            __syncthreads();
+            if(j == k)
+            {
+#pragma unroll
+                for(int i = 0; i < NB; ++i)
+                {
+                    if(i > k) { col[i] = lk[i]; }
+                }
+            }
+            else if(j > k)
             {
                 double const ukj = col[k];
 #pragma unroll
@@ -182,7 +189,6 @@ namespace
                     if(i > k) { col[i] = fma(-lk[i], ukj, col[i]); }
                 }
             }
-            __syncthreads();
         }
 #pragma unroll
         for(int i = 0; i < NB; ++i) { M[(k0 + i) + (int64_t)(k0 + j) * ld] = col[i]; }
@@ -317,30 +323,36 @@ namespace
     //   * the C tile is loaded INTO the accumulators at the start (64 independent loads in flight) and the L21 fragments are
     //     negated, so that the DMMAs compute (-L21) U12 + C and the epilogue is 64 plain stores;
     //   * the k-slabs are double-buffered: slab s + 1 arrives by cp.async while slab s is contracted.
-    constexpr int k_upd_smem = 4 * 16 * 132 * (int)sizeof(double);
+    // WN = 8-column fragments per warp: CTA tile = 128 rows x TC = 16 WN columns (8 warps as 4 x 2).  WN = 8: 128 x 128, 128
+    // accumulator registers, one CTA per SM; WN = 4: 128 x 64, 64 accumulator registers, two CTAs per SM (the prologue and the
+    // epilogue of one tile overlap the DMMAs of the other).
+    template <int WN>
+    constexpr int upd_smem() { return 2 * 16 * (132 + 16 * WN + 4) * (int)sizeof(double); }
     __device__ __forceinline__ void cp_async8(void* smem_dst, void const* src, bool valid)
     {
         uint32_t const d = (uint32_t)__cvta_generic_to_shared(smem_dst);
         int const n = valid ? 8 : 0;  // 0 source bytes: the destination is filled with zeros
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
     }
-    __global__ void __launch_bounds__(256) fr_lu_update2(double* __restrict__ Mall, int64_t ld, int32_t k0)
+    template <int WN>
+    __global__ void __launch_bounds__(256, WN == 8 ? 1 : 2) fr_lu_update2(double* __restrict__ Mall, int64_t ld, int32_t k0)
     {
+        constexpr int TC = 16 * WN, SBW = TC + 4;
         extern __shared__ double upd_smem[];
         double(*const sa)[16][132] = reinterpret_cast<double(*)[16][132]>(upd_smem);                  // sa[buf][k][row]
-        double(*const sb)[16][132] = reinterpret_cast<double(*)[16][132]>(upd_smem + 2 * 16 * 132);  // sb[buf][k][col]
+        double(*const sb)[16][SBW] = reinterpret_cast<double(*)[16][SBW]>(upd_smem + 2 * 16 * 132);  // sb[buf][k][col]
         double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
-        int64_t const r0 = k0 + NB + (int64_t)blockIdx.x * 128, c0 = k0 + NB + (int64_t)blockIdx.y * 128;
+        int64_t const r0 = k0 + NB + (int64_t)blockIdx.x * 128, c0 = k0 + NB + (int64_t)blockIdx.y * TC;
         int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-        int const wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
+        int const wr = (warp & 3) * 32, wc = (warp >> 2) * (8 * WN);
         int64_t const rr_left = ld - r0, cc_left = ld - c0;
-        int const rows_here = rr_left < 128 ? (int)rr_left : 128, cols_here = cc_left < 128 ? (int)cc_left : 128;
-        double acc[4][8][2];
+        int const rows_here = rr_left < 128 ? (int)rr_left : 128, cols_here = cc_left < TC ? (int)cc_left : TC;
+        double acc[4][WN][2];
         // C fragment: row = lane / 4, columns 2 (lane % 4) + {0, 1}
 #pragma unroll
         for(int i = 0; i < 4; ++i)
 #pragma unroll
-            for(int j = 0; j < 8; ++j)
+            for(int j = 0; j < WN; ++j)
 #pragma unroll
                 for(int h = 0; h < 2; ++h)
                 {
@@ -359,7 +371,7 @@ namespace
                 cp_async8(&sa[buf][kk][rr], in ? M + (r0 + rr) + (int64_t)(k0 + ks + kk) * ld : M, in);
             }
 #pragma unroll
-            for(int q = 0; q < 8; ++q)
+            for(int q = 0; q < TC / 16; ++q)
             {
                 int const e = tid + 256 * q;
                 int const cc = e >> 4, kk = e & 15;
@@ -379,15 +391,15 @@ namespace
 #pragma unroll
             for(int k4 = 0; k4 < 16; k4 += 4)
             {
-                double a[4], b[8];
+                double a[4], b[WN];
 #pragma unroll
                 for(int i = 0; i < 4; ++i) { a[i] = -sa[buf][k4 + (lane & 3)][wr + 8 * i + (lane >> 2)]; }  // (-L21) U12 + C
 #pragma unroll
-                for(int j = 0; j < 8; ++j) { b[j] = sb[buf][k4 + (lane & 3)][wc + 8 * j + (lane >> 2)]; }
+                for(int j = 0; j < WN; ++j) { b[j] = sb[buf][k4 + (lane & 3)][wc + 8 * j + (lane >> 2)]; }
 #pragma unroll
                 for(int i = 0; i < 4; ++i)
 #pragma unroll
-                    for(int j = 0; j < 8; ++j)
+                    for(int j = 0; j < WN; ++j)
                     {
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                                      : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
@@ -400,7 +412,7 @@ namespace
 #pragma unroll
         for(int i = 0; i < 4; ++i)
 #pragma unroll
-            for(int j = 0; j < 8; ++j)
+            for(int j = 0; j < WN; ++j)
 #pragma unroll
                 for(int h = 0; h < 2; ++h)
                 {
@@ -492,7 +504,21 @@ namespace
         double const* const M = Mall + (int64_t)blockIdx.x * ld * ld;
         double* const c = call + (int64_t)blockIdx.x * ld;
         int const tid = threadIdx.x;
-        for(int e = tid; e < NB * NB; e += 256) { s[e % NB][e / NB] = M[(k0 + e % NB) + (k0 + e / NB) * ld]; }
+        {
+            double t[NB * NB / 256];  // every load of the block in flight before the first store
+#pragma unroll
+            for(int q = 0; q < NB * NB / 256; ++q)
+            {
+                int const e = tid + 256 * q;
+                t[q] = M[(k0 + e % NB) + (k0 + e / NB) * ld];
+            }
+#pragma unroll
+            for(int q = 0; q < NB * NB / 256; ++q)
+            {
+                int const e = tid + 256 * q;
+                s[e % NB][e / NB] = t[q];
+            }
+        }
         __syncthreads();
         if(tid >= 32) { return; }
         double v0 = c[k0 + tid], v1 = c[k0 + tid + 32];
@@ -512,7 +538,21 @@ namespace
         double const* const M = Mall + (int64_t)blockIdx.x * ld * ld;
         double* const c = call + (int64_t)blockIdx.x * ld;
         int const tid = threadIdx.x;
-        for(int e = tid; e < NB * NB; e += 256) { s[e % NB][e / NB] = M[(k0 + e % NB) + (k0 + e / NB) * ld]; }
+        {
+            double t[NB * NB / 256];  // every load of the block in flight before the first store
+#pragma unroll
+            for(int q = 0; q < NB * NB / 256; ++q)
+            {
+                int const e = tid + 256 * q;
+                t[q] = M[(k0 + e % NB) + (k0 + e / NB) * ld];
+            }
+#pragma unroll
+            for(int q = 0; q < NB * NB / 256; ++q)
+            {
+                int const e = tid + 256 * q;
+                s[e % NB][e / NB] = t[q];
+            }
+        }
         __syncthreads();
         if(tid >= 32) { return; }
         double v0 = c[k0 + tid], v1 = c[k0 + tid + 32];
@@ -544,9 +584,12 @@ namespace
         __syncthreads();
         int64_t const r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if(r >= r1) { return; }
+        double m[NB];  // the row's 64 entries in flight together
+#pragma unroll
+        for(int j = 0; j < NB; ++j) { m[j] = M[r + (k0 + j) * ld]; }
         double v = c[r];
-#pragma unroll 8
-        for(int j = 0; j < NB; ++j) { v = fma(-M[r + (k0 + j) * ld], y[j], v); }
+#pragma unroll
+        for(int j = 0; j < NB; ++j) { v = fma(-m[j], y[j], v); }
         c[r] = v;
     }
 
@@ -607,7 +650,12 @@ extern "C"
             fr_core_assemble<<<dim3(blocks(f.n_core + f.n_core_edges + (ld - f.n_core)), (unsigned)f.n_inst), 256, 0, st>>>(f);
             ++nl;
             static bool const update_v1 = std::getenv("PE_B200_FRONTAL_UPDATE_V1") != nullptr;  // the first trailing update, kept for A/B runs
-            if(!update_v1 && fchk(cudaFuncSetAttribute(fr_lu_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, k_upd_smem), "fr_lu_update2 shared memory") != 0) { return 1; }
+            static bool const update_wide = std::getenv("PE_B200_FRONTAL_UPDATE_WIDE") != nullptr;  // 128 x 64 tiles, two CTAs per SM (default: 36.5 ms per solve of config A) / 128 x 128 tiles, one CTA per SM (40.0 ms)
+            if(!update_v1 && (fchk(cudaFuncSetAttribute(fr_lu_update2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem<8>()), "fr_lu_update2 shared memory") != 0 ||
+                              fchk(cudaFuncSetAttribute(fr_lu_update2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem<4>()), "fr_lu_update2 shared memory") != 0))
+            {
+                return 1;
+            }
             for(int64_t k0 = 0; k0 < ld; k0 += NB)
             {
                 fr_lu_diag<<<dim3(1, 1, (unsigned)f.n_inst), NB, 0, st>>>(f.M, ld, (int32_t)k0, f.status);
@@ -620,7 +668,11 @@ extern "C"
                 if(update_v1) { fr_lu_update<<<dim3(tb, tb, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0); }
                 else
                 {
-                    fr_lu_update2<<<dim3(tb, tb, (unsigned)f.n_inst), 256, k_upd_smem, st>>>(f.M, ld, (int32_t)k0);
+                    if(update_wide) { fr_lu_update2<8><<<dim3(tb, tb, (unsigned)f.n_inst), 256, upd_smem<8>(), st>>>(f.M, ld, (int32_t)k0); }
+                    else
+                    {
+                        fr_lu_update2<4><<<dim3(tb, (unsigned)((rem + 63) / 64), (unsigned)f.n_inst), 256, upd_smem<4>(), st>>>(f.M, ld, (int32_t)k0);
+                    }
                 }
                 nl += 2;
             }
