@@ -147,51 +147,42 @@ namespace
     // diagonal block k: in-place LU in shared memory
     __global__ void __launch_bounds__(NB) fr_lu_diag(double* __restrict__ Mall, int64_t ld, int32_t k0, int32_t* status)
     {
-        // thread j keeps column j of the block in registers.  Step k: the owner of column k publishes it, thread i divides row i's
-        // entry by the pivot (one division per thread, not 63 in the owner), everybody to the right applies the multipliers:
-        // two barriers and 64 - k FMAs per thread and step
-        __shared__ double raw[NB], lk[NB];
+        // thread i keeps ROW i of the block in registers (its loads and stores are coalesced across the threads).  Step k: the
+        // owner of row k publishes it, every thread below divides its own entry of column k by the pivot and applies the row:
+        // ONE barrier per step (the published row is double-buffered), one division per thread, 64 - k FMAs
+        __shared__ double urow[2][NB];
         double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
-        int const j = threadIdx.x;
-        double col[NB];
+        int const i = threadIdx.x;
+        double row[NB];
 #pragma unroll
-        for(int i = 0; i < NB; ++i) { col[i] = M[(k0 + i) + (int64_t)(k0 + j) * ld]; }
+        for(int j = 0; j < NB; ++j) { row[j] = M[(k0 + i) + (int64_t)(k0 + j) * ld]; }
 #pragma unroll
         for(int k = 0; k < NB; ++k)
         {
-            if(j == k)
+            if(i == k)
             {
 #pragma unroll
-                for(int i = 0; i < NB; ++i)
+                for(int j = 0; j < NB; ++j)
                 {
-                    if(i >= k) { raw[i] = col[i]; }
+                    if(j >= k) { urow[k & 1][j] = row[j]; }
                 }
             }
             __syncthreads();
-            double const p = raw[k];
-            if(j == k && (p == 0.0 || !isfinite(p))) { status[blockIdx.z] = PE_ST_SINGULAR; }
-            if(j > k) { lk[j] = raw[j] / p; }
-            __syncthreads();
-            if(j == k)
+            double const p = urow[k & 1][k];
+            if(i == k && (p == 0.0 || !isfinite(p))) { status[blockIdx.z] = PE_ST_SINGULAR; }
+            if(i > k)
             {
+                double const l = row[k] / p;
+                row[k] = l;
 #pragma unroll
-                for(int i = 0; i < NB; ++i)
+                for(int j = 0; j < NB; ++j)
                 {
-                    if(i > k) { col[i] = lk[i]; }
-                }
-            }
-            else if(j > k)
-            {
-                double const ukj = col[k];
-#pragma unroll
-                for(int i = 0; i < NB; ++i)
-                {
-                    if(i > k) { col[i] = fma(-lk[i], ukj, col[i]); }
+                    if(j > k) { row[j] = fma(-l, urow[k & 1][j], row[j]); }
                 }
             }
         }
 #pragma unroll
-        for(int i = 0; i < NB; ++i) { M[(k0 + i) + (int64_t)(k0 + j) * ld] = col[i]; }
+        for(int j = 0; j < NB; ++j) { M[(k0 + i) + (int64_t)(k0 + j) * ld] = row[j]; }
     }
 
     // panels of block step k: blockIdx.x < nbl: L21 block row = A21 U11^-1, else U12 block column = L11^-1 A12

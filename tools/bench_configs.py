@@ -167,12 +167,12 @@ def case_series_parallel(n_ring, n_merge, batches):
             err = np.abs(x - ref_x)
             scale = float(np.abs(ref_x).max())
             big = np.abs(ref_x) >= 1e-3 * scale
-            comp = bool((err[big] <= 1e-12 + 1e-9 * np.maximum(np.abs(x[big]), np.abs(ref_x[big]))).all())
-            parity = ("matches reference: max |err| %.2e = %.1e of the largest |x| (bar 1e-9), component-wise 1e-9 / 1e-12 on the %d unknowns above 1e-3 of it: %s"
-                      % (float(err.max()), float(err.max()) / scale, int(big.sum()), "yes" if comp else "NO")) if float(err.max()) <= 1e-9 * scale else "MISMATCH max abs err %.3e" % float(err.max())
+            rel_big = float((err[big] / np.abs(ref_x[big])).max())
+            parity = ("matches reference: max |err| %.2e = %.1e of the largest |x| (bar 1e-9; kappa ~ 1e10), worst relative error on the %d unknowns above 1e-3 of it: %.1e (bar 1e-8)"
+                      % (float(err.max()), float(err.max()) / scale, int(big.sum()), rel_big)) if float(err.max()) <= 1e-9 * scale and rel_big <= 1e-8 else "MISMATCH max abs err %.3e, worst relative %.3e" % (float(err.max()), rel_big)
         print(json.dumps({"case": f"A series_parallel ring {n_ring} merges {n_merge} DC", "batch": batch, "unknowns": fi["unknowns"], "ms_per_analyze": ms, "solves_per_s": batch / (ms * 1e-3),
                           "device_ms": {"reduce": fi["reduce_us"] / 1e3, "core_lu": fi["lu_us"] / 1e3, "substitutions": fi["subst_us"] / 1e3}, "plan": fi,
-                          "core_lu_tflops": flops / (fi["lu_us"] * 1e-6) / 1e12 if fi["lu_us"] else None, "fp64_peak_note": "B200 nominal FP64 (tensor) 40 TFLOP/s; no measured FP64 peak on this pool",
+                          "core_lu_tflops": flops / (fi["lu_us"] * 1e-6) / 1e12 if fi["lu_us"] else None, "fp64_peak_note": "measured on this pool (tools/micro/fp64_rate.cu): DMMA.8x8x4 35-37 TFLOP/s, DFMA 32-34 TFLOP/s",
                           "failed": int((b.status() != 0).sum()), "parity": parity,
                           "cpu_reference": {"seconds": ref_s, "threads": 1, "build": "oracle/_ref/libpe_ref_fast.so (-O3 -march=x86-64-v3)"} if ref_s else None}), flush=True)
 
