@@ -239,6 +239,8 @@ extern "C"
     int circuit_batch_solution(void* batch, double* x);        /* [n_instances][n] real state */
     int circuit_batch_solution_soa(void* batch, double* x);    /* [n][n_instances]: the device-native layout, no transpose */
     int circuit_batch_ac_solution(void* batch, double* x);     /* [lanes][n][2] */
+    /* ... of selected lanes only (lane = instance * points + point): x[n_lanes][n][2]; a sample of a sweep too large to download */
+    int circuit_batch_ac_solution_lanes(void* batch, size_t const* lanes, size_t n_lanes, double* x);
     int circuit_batch_ac_omegas(void* batch, double* omegas);  /* [points] */
     /* one rank's shard of a sweep: only the points [first, first + count) are solved (count = 0: all); the omega table is
      * built in full with the reference's cumulative product (circuit.h:412-428) and sliced */

@@ -1237,6 +1237,53 @@ namespace pe_b200
         return true;
     }
 
+    // complex solution of selected lanes of the last AC analyze(): x[k][unknown][re, im] for lanes[k] (a sweep of a million points is
+    // 3 GB per instance; a caller that wants a sample of it does not have to download all of it)
+    bool batch::get_ac_solution_lanes(std::size_t const* lanes, std::size_t n_sel, double* x)
+    {
+        if(!cc || !last_cplx) { return false; }
+        auto const& pr{cc->prog[static_cast<int>(prog_mode::AC)]};
+        std::size_t const n{static_cast<std::size_t>(cc->num.unknowns())};
+        if(n == 0 || n_sel == 0) { return true; }
+        std::size_t const slot0{PE_OPND_SLOT(pr.x_opnd[0])};
+        auto const* base{static_cast<double const*>(d_wl.p) + static_cast<std::int64_t>(slot0) * last_LSl};
+        for(std::size_t k{}; k < n_sel; ++k)
+        {
+            if(lanes[k] >= last_lanes)
+            {
+                error = "ac_solution_lanes: lane out of range";
+                set_last_error(error);
+                return false;
+            }
+            // one column of the [2 n rows][lanes] block: 2 n elements, one per row
+            if(pe_b200_dev_d2h_2d(x + k * 2 * n, sizeof(double), base + lanes[k], static_cast<std::size_t>(last_LSl) * sizeof(double), sizeof(double), 2 * n, stream) != 0)
+            {
+                return dev_fail(error, "download AC lanes");
+            }
+        }
+        if(pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download AC lanes"); }
+        // lanes a sub-batch of the pivot safety net owns
+        for(auto const& rs: rescues)
+        {
+            if(!rs.b->last_cplx || rs.b->last_lanes != rs.inst.size()) { continue; }
+            std::vector<std::size_t> sub_lane, dst;
+            for(std::size_t k{}; k < n_sel; ++k)
+            {
+                auto const it{std::lower_bound(rs.inst.begin(), rs.inst.end(), lanes[k])};
+                if(it != rs.inst.end() && *it == lanes[k] && rs.owned[static_cast<std::size_t>(it - rs.inst.begin())])
+                {
+                    sub_lane.push_back(static_cast<std::size_t>(it - rs.inst.begin()));
+                    dst.push_back(k);
+                }
+            }
+            if(sub_lane.empty()) { continue; }
+            std::vector<double> sx(sub_lane.size() * 2 * n);
+            if(!rs.b->get_ac_solution_lanes(sub_lane.data(), sub_lane.size(), sx.data())) { return false; }
+            for(std::size_t q{}; q < dst.size(); ++q) { std::copy(sx.begin() + static_cast<std::ptrdiff_t>(q * 2 * n), sx.begin() + static_cast<std::ptrdiff_t>((q + 1) * 2 * n), x + dst[q] * 2 * n); }
+        }
+        return true;
+    }
+
     bool batch::digital_clk()
     {
         if(!cc || d_wi.p == nullptr)

@@ -904,6 +904,11 @@ extern "C"
 
     int circuit_batch_ac_solution(void* bp, double* x) { return (bp && x && static_cast<batch*>(bp)->get_ac_solution(x)) ? 0 : 1; }
 
+    int circuit_batch_ac_solution_lanes(void* bp, size_t const* lanes, size_t n, double* x)
+    {
+        return (bp && (n == 0 || (lanes && x)) && static_cast<batch*>(bp)->get_ac_solution_lanes(lanes, n, x)) ? 0 : 1;
+    }
+
     int circuit_batch_ac_omegas(void* bp, double* om)
     {
         if(bp == nullptr || om == nullptr) { return 1; }

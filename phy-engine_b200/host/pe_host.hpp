@@ -439,6 +439,7 @@ namespace pe_b200
         bool get_solution(double* x /* [n_inst][n] */);
         bool get_solution_soa(double* x /* [n][n_inst] */);
         bool get_ac_solution(double* x /* [lanes][n][2] */);
+        bool get_ac_solution_lanes(std::size_t const* lanes, std::size_t n_sel, double* x /* [n_sel][n][2] */);
         bool get_status(std::int32_t* st /* [lanes] */);
         bool get_solves(std::uint32_t* sv /* [lanes] */);
         bool get_wave(double* w /* [steps][probes][n_inst] */);

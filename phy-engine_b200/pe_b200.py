@@ -532,6 +532,15 @@ class Batch:
         self._rc(self.lib.circuit_batch_ac_solution(self.h, _p(x, _PD)), "circuit_batch_ac_solution")
         return (x[..., 0] + 1j * x[..., 1]).reshape(self.n_inst, self.points, n)
 
+    def ac_solution_lanes(self, lanes) -> np.ndarray:
+        """complex solution [len(lanes), n] of selected lanes (lane = instance * points + point) of the last AC analyze()"""
+        lanes = np.ascontiguousarray(lanes, dtype=np.uintp)
+        n = self.n_unknowns()
+        x = np.zeros((lanes.size, n, 2))
+        self.lib.circuit_batch_ac_solution_lanes.argtypes = [ct.c_void_p, ct.POINTER(ct.c_size_t), ct.c_size_t, _PD]
+        self._rc(self.lib.circuit_batch_ac_solution_lanes(self.h, _p(lanes, ct.POINTER(ct.c_size_t)), lanes.size, _p(x, _PD)), "circuit_batch_ac_solution_lanes")
+        return x[..., 0] + 1j * x[..., 1]
+
     def ac_omegas(self) -> np.ndarray:
         om = np.zeros(max(self.points, 1))
         self._rc(self.lib.circuit_batch_ac_omegas(self.h, _p(om, _PD)), "circuit_batch_ac_omegas")

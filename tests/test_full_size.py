@@ -72,6 +72,25 @@ def test_config_d_full_size_ac_sweep_linearity():
     b.set_ac_sweep(pe.SWEEP_LOG, 1e3, 1e10, points)
     assert b.analyze(), c.abi.last_error()
     assert b.total_solves == 2 * points and (b.status() == 0).all()
+    # values of the big sweep itself, on a sample of its own points (every 251st: 3 985 points per instance, the ends included):
+    # linear in the source amplitude bit for bit, and equal to the reference solving the same omega on its own
+    sample = np.unique(np.concatenate([np.arange(0, points, 251), [points - 1, points - 2, 1]]))
+    x0 = b.ac_solution_lanes(sample)
+    x1 = b.ac_solution_lanes(points + sample)
+    big_s = (np.abs(x0.real) > 1e-280) & (np.abs(x0.imag) > 1e-280)
+    assert big_s.mean() > 0.1 and (x1[big_s] == 2.0 * x0[big_s]).all()
+    om_all = b.ac_omegas()
+    assert om_all.size == points
+    import refapi as _refapi
+
+    if os.path.exists(_refapi.REF_LIB):
+        rr = _refapi.RefCircuit(nl)
+        rr.set_analyze_type(pe.AC)
+        for q in range(0, sample.size, 16):  # every 16th sampled point: 250 single-point reference solves
+            rr.set_ac_omega(float(om_all[sample[q]]))
+            assert rr.analyze()
+            assert_close(x0[q].real, rr.solution().real, f"config D, point {int(sample[q])} (re)")
+            assert_close(x0[q].imag, rr.solution().imag, f"config D, point {int(sample[q])} (im)")
     # the full solution (2 x 1e6 x 194 complex) is 6 GB: check a small sweep of the same circuit point by point instead,
     # and the big one through its lane count, status flags and the linearity of a 4097-point sweep
     b2 = c.batch(2)

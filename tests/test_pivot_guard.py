@@ -167,6 +167,9 @@ def test_wide_ac_sweep_re_runs_only_the_flagged_points(ref, abi):  # noqa: F811
     want = refapi.run_batch(nl, pe.AC, 2, [(info["R"][0], "r", np.array([10.0, 12.0]))], ac=sweep)
     assert_close(got.real, want["x"].real, "wide sweep (re)")
     assert_close(got.imag, want["x"].imag, "wide sweep (im)")
+    # a sample of lanes (circuit_batch_ac_solution_lanes) reads the same values, rescued points included
+    sel = np.array([0, 3, 200, 254, 255, 256, 300, 511])
+    assert np.array_equal(b.ac_solution_lanes(sel), got.reshape(2 * 256, -1)[sel])
     # the same sweep again: the omega table stays on the device, the sub-batch is re-used, the results are the same bits
     assert b.analyze(), c.abi.last_error()
     assert np.array_equal(b.ac_solution(), got)
