@@ -913,10 +913,20 @@ namespace pe_b200
         }
         total_solves = op_solves;
         st.assign(last_lanes, 0);
+        last_fast_rescue = false;
         if(red[0] == 0 && rescues.empty())
         {
             sv.clear();  // fetched on demand (get_solves)
             total_solves += red[2];
+            return true;
+        }
+        // a single-shot analysis repeated on unchanged inputs flags the same lanes again: when the device counts say so (nothing
+        // but guard trips, as many as the sub-batches own) the 8 bytes per lane stay on the device here too
+        if(!rescues.empty() && rescue_fast_valid && red[0] == red[1] && red[1] == rescue_main_singular && at != analyze_type::TR && at != analyze_type::TROP)
+        {
+            sv.clear();
+            total_solves += red[2] - rescue_main_owned_solves;
+            last_fast_rescue = true;
             return true;
         }
         sv.assign(last_lanes, 0);
@@ -938,6 +948,28 @@ namespace pe_b200
         std::size_t const P{st.size() / n_inst};  // lanes per instance (points of an AC sweep, else 1)
         if(P == 0 || P * n_inst != st.size()) { return true; }
         std::vector<char> taken(st.size(), 0);
+        std::uint64_t main_singular{}, main_singular_solves{};
+        for(std::size_t l{}; l < st.size(); ++l)
+        {
+            if(st[l] == PE_ST_SINGULAR)
+            {
+                ++main_singular;
+                main_singular_solves += sv[l];
+            }
+        }
+        rescue_fast_valid = false;
+        auto record = [&]()
+        {
+            // the fast path of analyze_main() applies when every lane the main batch flags is owned by a sub-batch
+            std::uint64_t owned{};
+            for(auto const& rs: rescues)
+            {
+                for(char const o: rs.owned) { owned += o ? 1u : 0u; }
+            }
+            rescue_main_singular = main_singular;
+            rescue_main_owned_solves = main_singular_solves;
+            rescue_fast_valid = owned == main_singular;
+        };
         auto merge = [&](rescue_set& rs)
         {
             auto& sb{*rs.b};
@@ -976,7 +1008,11 @@ namespace pe_b200
         {
             if(!taken[l] && st[l] == PE_ST_SINGULAR) { F.push_back(l); }
         }
-        if(F.empty()) { return true; }
+        if(F.empty())
+        {
+            record();
+            return true;
+        }
         stat_guard_trips += F.size();
         auto const at{parent->at};
         if((at == analyze_type::TR || at == analyze_type::TROP) && !fresh_state) { return true; }  // the state the transient continues from is gone
@@ -1071,6 +1107,7 @@ namespace pe_b200
         rescues_ac = (ac.points > 0 || ac.omega != 0.0) ? ac : parent->ac;
         rescues_slice_first = ac_slice_first;
         rescues_slice_count = ac_slice_count;
+        record();
         return true;
     }
 
@@ -1106,6 +1143,50 @@ namespace pe_b200
             last_status = st;
             last_solves = sv;
             return launched;
+        }
+        if(last_fast_rescue)
+        {
+            // the sub-batches run again, their lanes' status and counters replace the main batch's; every other lane is fine
+            bool sub_ok{true};
+            for(auto& rs: rescues)
+            {
+                rs.b->stream = stream;
+                (void)rs.b->analyze();
+                ++stat_rescue_launches;
+                if(rs.b->last_status.size() != rs.inst.size())
+                {
+                    error = "rescue batch: " + rs.b->error;
+                    set_last_error(error);
+                    return false;
+                }
+                bool all_owned{true};
+                for(char const o: rs.owned) { all_owned = all_owned && o != 0; }
+                std::vector<std::uint32_t> ssv;
+                if(!all_owned)
+                {
+                    ssv.assign(rs.inst.size(), 0);
+                    if(!rs.b->get_solves(ssv.data())) { return false; }
+                }
+                else
+                {
+                    total_solves += rs.b->total_solves;
+                }
+                for(std::size_t k{}; k < rs.inst.size(); ++k)
+                {
+                    if(!rs.owned[k] || rs.inst[k] >= st.size()) { continue; }
+                    st[rs.inst[k]] = rs.b->last_status[k];
+                    sub_ok = sub_ok && rs.b->last_status[k] == PE_ST_OK;
+                    if(!all_owned) { total_solves += ssv[k]; }
+                }
+            }
+            last_status = std::move(st);
+            last_solves.clear();  // per-lane counters on demand (get_solves merges the sub-batches' lanes)
+            if(!sub_ok)
+            {
+                error = "analyze: at least one lane failed (no convergence or singular matrix)";
+                set_last_error(error);
+            }
+            return sub_ok;
         }
         if(!sv.empty() && !is_rescue && pivot_guard > 0.0 && !run_rescues(st, sv, fresh_state)) { return false; }
         bool all_ok{true};
@@ -1145,6 +1226,15 @@ namespace pe_b200
             return true;
         }
         if(pe_b200_dev_d2h(sv, d_solves.p, last_lanes * 4, stream) != 0 || pe_b200_dev_sync(stream) != 0) { return dev_fail(error, "download solves"); }
+        for(auto& rs: rescues)
+        {
+            std::vector<std::uint32_t> ssv(rs.inst.size(), 0);
+            if(rs.b->last_lanes != rs.inst.size() || !rs.b->get_solves(ssv.data())) { continue; }
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                if(rs.owned[k] && rs.inst[k] < last_lanes) { sv[rs.inst[k]] = ssv[k]; }
+            }
+        }
         return true;
     }
 

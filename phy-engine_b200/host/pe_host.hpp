@@ -411,6 +411,9 @@ namespace pe_b200
             std::vector<char> owned;         // [k]: its results replace this batch's
         };
         std::vector<rescue_set> rescues;
+        // what the main batch looked like when the sub-batches were built: lanes it flagged, the solve counters of those lanes
+        std::uint64_t rescue_main_singular{}, rescue_main_owned_solves{};
+        bool rescue_fast_valid{}, last_fast_rescue{};
         std::uint64_t rescues_sweeps_rev{}, rescues_param_rev{}, rescues_structure_rev{};
         analyze_type rescues_at{};
         ac_setting rescues_ac{};

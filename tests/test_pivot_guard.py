@@ -181,3 +181,28 @@ def test_wide_ac_sweep_re_runs_only_the_flagged_points(ref, abi):  # noqa: F811
     want2 = refapi.run_batch(nl, pe.AC, 2, [(info["R"][0], "r", np.array([10.0, 12.0]))], ac=(pe.SWEEP_LOG, 1e5, 1e7, 64))
     assert_close(b.ac_solution().real, want2["x"].real, "narrow sweep (re)")
     assert_close(b.ac_solution().imag, want2["x"].imag, "narrow sweep (im)")
+
+
+def test_repeated_analysis_keeps_counters_and_status_consistent(ref, abi):  # noqa: F811
+    # second and later calls on unchanged inputs take a short path (device-side counts only): status, per-lane counters, totals and
+    # values must be what the first call reported
+    nl, info = wl.transformer_stage()
+    over = [(info["TX"], "n", RATIOS)]
+    c, b = batch_of(abi, nl, pe.OP, over, RATIOS.size)
+    assert b.analyze(), c.abi.last_error()
+    first = (b.solution().copy(), b.status().copy(), b.newton_iters().copy(), b.total_solves, b.rescue_info(0))
+    for _ in range(3):
+        assert b.analyze(), c.abi.last_error()
+        assert np.array_equal(b.solution(), first[0]) and np.array_equal(b.status(), first[1]) and np.array_equal(b.newton_iters(), first[2])
+        assert b.total_solves == first[3] == RATIOS.size
+    again = b.rescue_info(0)
+    assert again["sub_batches"] == first[4]["sub_batches"] and again["flagged"] == first[4]["flagged"]  # nothing was re-built or re-flagged
+    # a non-linear batch where one instance fails for good (the reference fails there too): the failure is reported every time
+    nl2, info2 = wl.npn_resistor_biased()
+    c2 = pe.Circuit(nl2, abi)
+    c2.set_analyze_type(pe.OP)
+    b2 = c2.batch(3)
+    ok1 = b2.analyze()
+    st1 = b2.status().copy()
+    ok2 = b2.analyze()
+    assert ok1 == ok2 and np.array_equal(b2.status(), st1)
