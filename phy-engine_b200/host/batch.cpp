@@ -1420,6 +1420,17 @@ namespace pe_b200
         {
             for(std::size_t i{}; i < n_inst; ++i) { out[i * n_cmp + c] = tmp[c * n_inst + i]; }
         }
+        // instances a sub-batch of the pivot safety net owns: their comparators read THAT solution
+        for(auto& rs: rescues)
+        {
+            if(!rs.b->lane_omegas.empty()) { continue; }
+            std::vector<std::uint8_t> sub(rs.inst.size() * n_cmp);
+            if(!rs.b->digital_clk() || rs.b->n_cmp != n_cmp || !rs.b->get_comparator_states(sub.data())) { return false; }
+            for(std::size_t k{}; k < rs.inst.size(); ++k)
+            {
+                if(rs.owned[k] && rs.inst[k] < n_inst) { std::copy(sub.begin() + static_cast<std::ptrdiff_t>(k * n_cmp), sub.begin() + static_cast<std::ptrdiff_t>((k + 1) * n_cmp), out + rs.inst[k] * n_cmp); }
+            }
+        }
         return true;
     }
 

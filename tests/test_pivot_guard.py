@@ -206,3 +206,25 @@ def test_repeated_analysis_keeps_counters_and_status_consistent(ref, abi):  # no
     st1 = b2.status().copy()
     ok2 = b2.analyze()
     assert ok1 == ok2 and np.array_equal(b2.status(), st1)
+
+
+def test_comparators_read_the_rescued_solution(abi):  # noqa: F811
+    # analog -> digital boundary on top of the safety net: the comparator of a rescued instance compares THAT instance's
+    # re-solved voltages (the main batch's rows for it are what the guard rejected)
+    nl, info = wl.transformer_stage()
+    cmp_ = nl.add(pe.COMPARATOR, 0.0, 5.0)
+    vr = nl.add(pe.VDC, 1e-15)
+    nl.wire(vr, 1, 0, 0)  # element 0 is the ground placeholder
+    nl.wire(cmp_, 1, vr, 0)
+    nl.wire(cmp_, 0, info["R"], 0)
+    ratios = np.array([4.0, 1e-14, 0.0, 2.0, 1e-20, 20.0])
+    c = pe.Circuit(nl, abi)
+    c.set_analyze_type(pe.OP)
+    b = c.batch(ratios.size)
+    b.set_param(info["TX"], "n", ratios)
+    assert b.analyze(), c.abi.last_error()
+    assert b.rescue_info(0)["rescued"] >= 2
+    v = b.solution()[:, c.pin_unknown(info["R"], 0)]
+    assert v[1] > 1e-13 and 0.0 < v[4] < 1e-15  # the rescued instances carry their own tiny, accurate voltages
+    assert (b.digital_clk().ravel() == (v >= 1e-15).astype(np.uint8)).all()
+    assert b.digital_clk().ravel().tolist() == [1, 1, 0, 1, 0, 1]
