@@ -326,14 +326,28 @@ namespace
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
     }
     template <int WN>
-    __global__ void __launch_bounds__(256, WN == 8 ? 1 : 2) fr_lu_update2(double* __restrict__ Mall, int64_t ld, int32_t k0)
+    __global__ void __launch_bounds__(256, WN == 8 ? 1 : 2) fr_lu_update2(double* __restrict__ Mall, int64_t ld, int32_t k0, int32_t part, int32_t ty)
     {
         constexpr int TC = 16 * WN, SBW = TC + 4;
+        // part 0: every tile (grid tx x ty).  Look-ahead split: part 1 = the tiles of the first tile row and the first tile column
+        // (1-D grid of ty + tx - 1), which hold the next step's panel; part 2 = all the others (grid tx - 1 x ty - 1)
+        int bx = (int)blockIdx.x, by = (int)blockIdx.y;
+        if(part == 1)
+        {
+            int const t = (int)blockIdx.x;
+            bx = t < ty ? 0 : t - ty + 1;
+            by = t < ty ? t : 0;
+        }
+        else if(part == 2)
+        {
+            ++bx;
+            ++by;
+        }
         extern __shared__ double upd_smem[];
         double(*const sa)[16][132] = reinterpret_cast<double(*)[16][132]>(upd_smem);                  // sa[buf][k][row]
         double(*const sb)[16][SBW] = reinterpret_cast<double(*)[16][SBW]>(upd_smem + 2 * 16 * 132);  // sb[buf][k][col]
         double* const M = Mall + (int64_t)blockIdx.z * ld * ld;
-        int64_t const r0 = k0 + NB + (int64_t)blockIdx.x * 128, c0 = k0 + NB + (int64_t)blockIdx.y * TC;
+        int64_t const r0 = k0 + NB + (int64_t)bx * 128, c0 = k0 + NB + (int64_t)by * TC;
         int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         int const wr = (warp & 3) * 32, wc = (warp >> 2) * (8 * WN);
         int64_t const rr_left = ld - r0, cc_left = ld - c0;
@@ -647,6 +661,20 @@ extern "C"
             {
                 return 1;
             }
+            // second stream + two events for the look-ahead of the default update (PE_B200_FRONTAL_NO_LOOKAHEAD: one stream)
+            static bool const lookahead = std::getenv("PE_B200_FRONTAL_NO_LOOKAHEAD") == nullptr;
+            cudaStream_t st2 = nullptr;
+            cudaEvent_t e_panel{}, e_rest{};
+            bool rest_pending = false;
+            if(lookahead && !update_v1 && !update_wide)
+            {
+                if(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking) != cudaSuccess) { st2 = nullptr; }
+                else if(cudaEventCreateWithFlags(&e_panel, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e_rest, cudaEventDisableTiming) != cudaSuccess)
+                {
+                    cudaStreamDestroy(st2);
+                    st2 = nullptr;
+                }
+            }
             for(int64_t k0 = 0; k0 < ld; k0 += NB)
             {
                 fr_lu_diag<<<dim3(1, 1, (unsigned)f.n_inst), NB, 0, st>>>(f.M, ld, (int32_t)k0, f.status);
@@ -659,13 +687,42 @@ extern "C"
                 if(update_v1) { fr_lu_update<<<dim3(tb, tb, (unsigned)f.n_inst), 256, 0, st>>>(f.M, ld, (int32_t)k0); }
                 else
                 {
-                    if(update_wide) { fr_lu_update2<8><<<dim3(tb, tb, (unsigned)f.n_inst), 256, upd_smem<8>(), st>>>(f.M, ld, (int32_t)k0); }
+                    if(update_wide) { fr_lu_update2<8><<<dim3(tb, tb, (unsigned)f.n_inst), 256, upd_smem<8>(), st>>>(f.M, ld, (int32_t)k0, 0, (int32_t)tb); }
                     else
                     {
-                        fr_lu_update2<4><<<dim3(tb, (unsigned)((rem + 63) / 64), (unsigned)f.n_inst), 256, upd_smem<4>(), st>>>(f.M, ld, (int32_t)k0);
+                        unsigned const ty = (unsigned)((rem + 63) / 64);
+                        if(st2 != nullptr && tb > 1 && ty > 1)
+                        {
+                            // look-ahead: the first tile row / column on this stream (the next diagonal block and panel follow them),
+                            // everything else on the second stream, beside that diagonal block and panel
+                            cudaEventRecord(e_panel, st);
+                            if(rest_pending) { cudaStreamWaitEvent(st, e_rest, 0); }  // the rest of the step before: its tiles are updated again now
+                            fr_lu_update2<4><<<dim3(ty + tb - 1, 1, (unsigned)f.n_inst), 256, upd_smem<4>(), st>>>(f.M, ld, (int32_t)k0, 1, (int32_t)ty);
+                            cudaStreamWaitEvent(st2, e_panel, 0);
+                            fr_lu_update2<4><<<dim3(tb - 1, ty - 1, (unsigned)f.n_inst), 256, upd_smem<4>(), st2>>>(f.M, ld, (int32_t)k0, 2, (int32_t)ty);
+                            cudaEventRecord(e_rest, st2);
+                            rest_pending = true;
+                            ++nl;
+                        }
+                        else
+                        {
+                            if(rest_pending)
+                            {
+                                cudaStreamWaitEvent(st, e_rest, 0);
+                                rest_pending = false;
+                            }
+                            fr_lu_update2<4><<<dim3(tb, ty, (unsigned)f.n_inst), 256, upd_smem<4>(), st>>>(f.M, ld, (int32_t)k0, 0, (int32_t)ty);
+                        }
                     }
                 }
                 nl += 2;
+            }
+            if(rest_pending) { cudaStreamWaitEvent(st, e_rest, 0); }
+            if(st2 != nullptr)
+            {
+                cudaEventDestroy(e_panel);
+                cudaEventDestroy(e_rest);
+                cudaStreamDestroy(st2);  // returns at once; the stream goes when its work is done
             }
             if(timing) { cudaEventRecord(ev[2], st); }
             static bool const one_cta_subst = std::getenv("PE_B200_FRONTAL_ONE_CTA_SUBST") != nullptr;  // the first version, kept for A/B runs
