@@ -58,6 +58,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     k.lane = lane;
     k.n_rows = (uint32_t)r.n_slots;
     k.guard = r.guard;
+    k.t = r.t0;
     if(lane == 0u)
     {
         for(uint32_t s = 0; s < NS; ++s) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k.bars + 8u * s), "r"(1u) : "memory"); }
@@ -204,6 +205,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
             }
             // one linear solve (stamp + LU + substitution): the generated tiles
             uint32_t fm = 0u;
+            k.t = t;
 #ifdef PE_STREAM_STEADY
             if(s == 0) { pe_stream_iter(k, fm); }
             else

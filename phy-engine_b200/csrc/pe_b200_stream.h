@@ -95,6 +95,13 @@ namespace pe_stream
         for(int j = 0; j < PE_SJ; ++j) { pe_models::cap_step(C.v[j], dt.v[j], PE_SUB(va.v[j], vb.v[j]), hist.v[j], prev_g.v[j]); }
     }
 
+    // VSIN (VAC.h:176, IAC.h:154): Vp sin(omega t + phase), the expression of pe_b200_rinterp.h
+    PE_SK_FN jv jvsin(jv const& vp, jv const& om, jv const& ph, double const t)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_MUL(vp.v[j], sin(PE_ADD(PE_MUL(om.v[j], t), ph.v[j]))); }
+        return x;
+    }
     // IND_STEP (inductor.h:134-160): req, ueq from the previous step's voltage and branch current
     PE_SK_FN void jind(jv const& L, jv const& dt, jv const& va, jv const& vb, jv const& ib, jv& req, jv& ueq)
     {
@@ -179,6 +186,7 @@ namespace pe_stream
         uint32_t enm;       // store mask of this thread's J lanes
         uint32_t n_rows;    // rows of the group's workspace block (bounds checks of debug builds, -DPE_SK_DEBUG)
         double guard;       // PE_F_GUARD threshold (pe_b200_program.h)
+        double t;           // time of the solve being made (sources with a time dependence: VSIN)
     };
 
 #ifdef PE_SK_DEBUG
@@ -271,6 +279,7 @@ namespace pe_stream
         uint32_t lane;
         uint32_t enm;
         double guard;
+        double t;
         // checks
         uint32_t n_rows;
         uint64_t* store_seq;   // [n_rows]: sequence number of the last store to the row

@@ -94,6 +94,12 @@ namespace pe_b200
                         j.wr.push_back(o.opnd[0] & k_slot_mask);
                         j.wr.push_back(o.opnd[1] & k_slot_mask);
                     }
+                    else if(o.opcode == PE_OP_VSIN && o.opnd.size() == 4)
+                    {
+                        // [dst] <- [Vp][omega][phase] at the time of the solve (VAC.h:176, IAC.h:154)
+                        for(std::size_t i{1}; i < 4; ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
+                        j.wr.push_back(o.opnd[0] & k_slot_mask);
+                    }
                     else if(o.opcode == PE_OP_IND_STEP && o.opnd.size() == 7)
                     {
                         // [req][ueq] <- [L][dt][va][vb][ib] (inductor.h:134-160)
@@ -618,6 +624,11 @@ namespace pe_b200
                       << ");";
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                     if(!st[1].empty()) { t << " sk_st(k, " << st[1] << ", " << w[1] << ");"; }
+                }
+                else if(o.opcode == PE_OP_VSIN)  // [dst] <- [Vp][omega][phase]
+                {
+                    t << dv << w[0] << " = jvsin(" << x[0] << ", " << x[1] << ", " << x[2] << ", k.t);";
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }
                 else if(o.opcode == PE_OP_IND_STEP)  // [req][ueq] <- [L][dt][va][vb][ib]
                 {

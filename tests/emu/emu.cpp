@@ -793,6 +793,7 @@ extern "C"
             };
             void* const st = f_new((uint32_t)r.n_slots, (uint32_t)ns_log_env);
             if(auto const f_guard = reinterpret_cast<void (*)(void*, double)>(dlsym(h, "pe_emu_stream_set_guard")); f_guard != nullptr) { f_guard(st, r.guard); }
+            auto const f_time = reinterpret_cast<void (*)(void*, double)>(dlsym(h, "pe_emu_stream_set_time"));
             double t = r.t0;
             if(r.has_prep)
             {
@@ -809,6 +810,7 @@ extern "C"
                     if(r.has_step) { run_section(1, t); }
                     t = t + r.dt;
                 }
+                if(f_time != nullptr) { f_time(st, t); }
                 uint32_t const fm = f_solve(st, wl, GL, li & 31u, ok ? 1u : 0u, &g_stream_errors, s == 0 ? 1 : 0);
                 if(ok)
                 {

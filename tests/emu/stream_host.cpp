@@ -61,6 +61,7 @@ extern "C"
 
     void pe_emu_stream_free(void* p) { delete static_cast<lane_state*>(p); }
     void pe_emu_stream_set_guard(void* p, double guard) { static_cast<lane_state*>(p)->k.guard = guard; }
+    void pe_emu_stream_set_time(void* p, double t) { static_cast<lane_state*>(p)->k.t = t; }
 
     // stores made by the interpreted sections / the load table between two solves are not tracked: every section starts
     // with a fence anyway.  Returns the pivot-failure mask; *errors accumulates the ordering violations.

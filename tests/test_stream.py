@@ -168,22 +168,54 @@ def test_stream_kernel_covers_inductors(ref, abi):  # noqa: F811
     assert_close(got["stream"], want["x"].real, "RLC step response through the stream kernel")
 
 
-def test_stream_with_time_dependent_sources_falls_back(ref, abi):  # noqa: F811
-    # a VAC source is re-evaluated every step (VSIN), which the generator does not cover: the program is rejected at compile time
-    # and the default geometry runs
-    nl, info = wl.rlc_ladder(40)
+def test_stream_kernel_covers_sinusoidal_sources(ref, abi):  # noqa: F811
+    # a VAC / IAC source is re-evaluated at the time of every solve (VSIN, VAC.h:176): the generated tiles read the step's time
+    # from the kernel's context.  RLC ladder driven by a 200 kHz sine, every R / L / C swept, across a resumed transient
+    n_sections, n_inst, steps, dt = 80, 37, 6, 1e-9
+    nl, info = wl.rlc_ladder(n_sections)
+    rng = np.random.default_rng(2)
+    over = ([(e, "r", wl.sweep_values(rng, 10.0, n_inst)) for e in info["R"]] + [(e, "L", wl.sweep_values(rng, 1e-6, n_inst)) for e in info["L"]] +
+            [(e, "c", wl.sweep_values(rng, 1e-9, n_inst)) for e in info["C"]])
+    got = {}
+    for name, tuning, resident in (("interpreter", NO_STREAM_NO_JIT, (1, 0, 1)), ("stream", STREAM, None)):
+        c = pe.Circuit(nl, abi)
+        c.set_analyze_type(pe.TR)
+        c.set_tr(dt, dt * (steps - 0.5))
+        b = c.batch(n_inst)
+        if resident:
+            b.set_resident(*resident)
+            b.set_workspace(2)
+        b.set_tuning(tuning)
+        for e, name_, v in over:
+            b.set_param(e, name_, v)
+        assert b.analyze(), c.abi.last_error()
+        assert b.last_kernel() == (2 if name == "stream" else 0)
+        got[name] = b.solution()
+        assert b.analyze(), c.abi.last_error()  # the second call starts at t = 6 ns: the source's phase continues
+        got[name + "2"] = b.solution()
+    assert np.array_equal(got["interpreter"], got["stream"]) and np.array_equal(got["interpreter2"], got["stream2"])
+    assert np.abs(got["stream2"] - got["stream"]).max() > 0.0
+    want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=dt, t_stop=dt * (steps - 0.5))
+    assert (want["ok"] == 1).all()
+    assert_close(got["stream"], want["x"].real, "sine-driven RLC ladder through the stream kernel")
+
+
+def test_stream_request_on_an_uncovered_program_falls_back(ref, abi):  # noqa: F811
+    # coupled inductors (KIND_STEP) are not covered by the generator: the program is rejected at compile time, the default
+    # geometry runs and the caller gets the same answer
+    nl, info = wl.coupled_inductors_stage()
     rc = refapi.RefCircuit(nl)
     rc.set_analyze_type(pe.TR)
-    rc.set_tr(1e-9, 2e-8)
+    rc.set_tr(1e-8, 2e-7)
     assert rc.analyze()
     c = pe.Circuit(nl, abi)
     c.set_analyze_type(pe.TR)
-    c.set_tr(1e-9, 2e-8)
+    c.set_tr(1e-8, 2e-7)
     b = c.batch(3)
     b.set_tuning(STREAM)
     assert b.analyze(), c.abi.last_error()
     assert b.last_kernel() != 2
-    assert_close(b.solution()[0], rc.solution().real, "RLC transient next to the stream request")
+    assert_close(b.solution()[0], rc.solution().real, "coupled inductors next to the stream request")
 
 
 def test_build_flags_reach_the_compiler(tmp_path):
