@@ -1195,8 +1195,8 @@ namespace pe_b200
             total_solves += sv[i];
             if(st[i] != PE_ST_OK) { all_ok = false; }
         }
-        last_status = st;
-        last_solves = sv;
+        last_status = std::move(st);
+        last_solves = std::move(sv);
         if(!all_ok)
         {
             error = "analyze: at least one lane failed (no convergence or singular matrix)";

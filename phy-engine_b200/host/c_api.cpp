@@ -679,6 +679,7 @@ extern "C"
         auto* bp{static_cast<batch*>(b)};
         bp->pivot_guard = guard < 0.0 ? PE_GUARD_DEFAULT : guard;
         bp->rescue_rounds = rounds < 0 ? 3 : std::max(rounds, 1);
+        bp->rescues.clear();  // sub-batches built under the old setting no longer own anything
         return 0;
     }
 
