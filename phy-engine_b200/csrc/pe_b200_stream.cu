@@ -37,7 +37,7 @@ extern "C" __global__ void __launch_bounds__(256, 1) pe_b200_stream_kernel(pe_b2
     constexpr uint32_t SGL = PE_SGL;      // lanes of the warp that carry a lane of the group (the others mirror them, stores off)
     constexpr uint32_t GL = SGL * J;      // lanes per group
     static_assert(SGL == 32u || J == 1, "narrow groups carry one lane per thread");
-    constexpr int NB = J == 1 ? 16 : 8;  // table entries whose values are in flight together
+    constexpr int NB = J == 1 ? 32 : 8;  // table entries whose values are in flight together
     uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     uint32_t const NS = 1u << ns_log;
     uint32_t const stage_bytes = PE_STREAM_STAGE_ROWS * ROWB;
