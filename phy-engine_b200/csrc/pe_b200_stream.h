@@ -102,6 +102,14 @@ namespace pe_stream
         for(int j = 0; j < PE_SJ; ++j) { x.v[j] = PE_MUL(vp.v[j], sin(PE_ADD(PE_MUL(om.v[j], t), ph.v[j]))); }
         return x;
     }
+    // GEN_EVAL (generator/*.h: sawtooth / square / pulse / triangle at the section time or at t = 0), the expression of
+    // pe_b200_rinterp.h
+    PE_SK_FN jv jvgen(jv const& kd, jv const& ts, jv const& vh, jv const& vl, jv const& fq, jv const& du, jv const& ph, jv const& tr_, jv const& tf_, double const t)
+    {
+        jv x;
+        for(int j = 0; j < PE_SJ; ++j) { x.v[j] = pe_models::gen_eval((int)kd.v[j], ts.v[j] != 0.0 ? t : 0.0, vh.v[j], vl.v[j], fq.v[j], du.v[j], ph.v[j], tr_.v[j], tf_.v[j]); }
+        return x;
+    }
     // IND_STEP (inductor.h:134-160): req, ueq from the previous step's voltage and branch current
     PE_SK_FN void jind(jv const& L, jv const& dt, jv const& va, jv const& vb, jv const& ib, jv& req, jv& ueq)
     {

@@ -100,6 +100,12 @@ namespace pe_b200
                         for(std::size_t i{1}; i < 4; ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
                         j.wr.push_back(o.opnd[0] & k_slot_mask);
                     }
+                    else if(o.opcode == PE_OP_GEN_EVAL && o.opnd.size() == 10)
+                    {
+                        // [dst] <- [kind][tsel][Vh][Vl][freq][duty][phase][tr][tf] at the time of the solve (generator/*.h)
+                        for(std::size_t i{1}; i < 10; ++i) { j.rd.push_back(o.opnd[i] & k_slot_mask); }
+                        j.wr.push_back(o.opnd[0] & k_slot_mask);
+                    }
                     else if(o.opcode == PE_OP_IND_STEP && o.opnd.size() == 7)
                     {
                         // [req][ueq] <- [L][dt][va][vb][ib] (inductor.h:134-160)
@@ -628,6 +634,13 @@ namespace pe_b200
                 else if(o.opcode == PE_OP_VSIN)  // [dst] <- [Vp][omega][phase]
                 {
                     t << dv << w[0] << " = jvsin(" << x[0] << ", " << x[1] << ", " << x[2] << ", k.t);";
+                    if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
+                }
+                else if(o.opcode == PE_OP_GEN_EVAL)  // [dst] <- [kind][tsel][Vh][Vl][freq][duty][phase][tr][tf]
+                {
+                    t << dv << w[0] << " = jvgen(";
+                    for(std::size_t i{}; i < 9; ++i) { t << x[i] << ", "; }
+                    t << "k.t);";
                     if(!st[0].empty()) { t << " sk_st(k, " << st[0] << ", " << w[0] << ");"; }
                 }
                 else if(o.opcode == PE_OP_IND_STEP)  // [req][ueq] <- [L][dt][va][vb][ib]

@@ -347,6 +347,26 @@ def generator_rc(kind: str = "square"):
     return nl, {"G": src, "R": r, "C": c}
 
 
+def pulse_rc_ladder(n_sections: int = 100, r: float = 1e3, c: float = 1e-9):
+    """A pulse generator (element 22, generator/pulse.h) into an RC ladder: the interconnect-delay shape of config B with a
+    time-dependent source (one GEN_EVAL per solve next to the DOT / CAP_STEP ops)."""
+    nl = Netlist()
+    g = nl.ground()
+    src = nl.add(pe.GEN_PULSE, 4.0, -1.0, 2.5e6, 0.6, 0.7, 4e-8, 6e-8)
+    nl.wire(src, 1, g, 0)
+    prev = (src, 0)
+    R, C = [], []
+    for _ in range(n_sections):
+        er, ec = nl.add(pe.R, r), nl.add(pe.C, c)
+        nl.wire(prev[0], prev[1], er, 0)
+        nl.wire(er, 1, ec, 0)
+        nl.wire(ec, 1, g, 0)
+        prev = (er, 1)
+        R.append(er)
+        C.append(ec)
+    return nl, {"G": src, "R": R, "C": C}
+
+
 def relay_stage(vac: bool = False, v_ctl: float = 6.0):
     """A relay (element 18, controller/relay.h): the coil hangs on a resistive divider driven by a control source (DC, or a
     sine that crosses both hysteresis thresholds), the contact switches a 5 V supply onto an RC load."""

@@ -200,6 +200,38 @@ def test_stream_kernel_covers_sinusoidal_sources(ref, abi):  # noqa: F811
     assert_close(got["stream"], want["x"].real, "sine-driven RLC ladder through the stream kernel")
 
 
+def test_stream_kernel_covers_the_time_domain_generators(ref, abi):  # noqa: F811
+    # a pulse generator (generator/pulse.h) into an RC ladder: GEN_EVAL reads the time of the solve like VSIN does; 40 steps of
+    # 10 ns cross the rising edge, the plateau and the falling edge of the 400 ns period
+    n_sections, n_inst, steps, dt = 160, 33, 40, 1e-8
+    nl, info = wl.pulse_rc_ladder(n_sections)
+    rng = np.random.default_rng(6)
+    over = [(e, "r", wl.sweep_values(rng, 1e3, n_inst)) for e in info["R"]] + [(e, "c", wl.sweep_values(rng, 1e-9, n_inst)) for e in info["C"]]
+    got = {}
+    for name, tuning, resident in (("interpreter", NO_STREAM_NO_JIT, (1, 0, 1)), ("stream", STREAM, None)):
+        c = pe.Circuit(nl, abi)
+        c.set_analyze_type(pe.TR)
+        c.set_tr(dt, dt * (steps - 0.5))
+        b = c.batch(n_inst)
+        if resident:
+            b.set_resident(*resident)
+            b.set_workspace(2)
+        b.set_tuning(tuning)
+        for e, name_, v in over:
+            b.set_param(e, name_, v)
+        b.set_probes([0])
+        assert b.analyze(), c.abi.last_error()
+        assert b.last_kernel() == (2 if name == "stream" else 0)
+        got[name] = b.solution()
+        got[name + "w"] = b.waveform(steps)
+    assert np.array_equal(got["interpreter"], got["stream"]) and np.array_equal(got["interpreterw"], got["streamw"])
+    w = got["streamw"][:, 0, 0]
+    assert w.max() > 3.9 and w.min() < -0.9  # the source node saw both levels of the pulse
+    want = refapi.run_batch(nl, pe.TR, n_inst, over, t_step=dt, t_stop=dt * (steps - 0.5))
+    assert (want["ok"] == 1).all()
+    assert_close(got["stream"], want["x"].real, "pulse-driven RC ladder through the stream kernel")
+
+
 def test_stream_request_on_an_uncovered_program_falls_back(ref, abi):  # noqa: F811
     # coupled inductors (KIND_STEP) are not covered by the generator: the program is rejected at compile time, the default
     # geometry runs and the caller gets the same answer
